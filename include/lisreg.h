@@ -1,0 +1,152 @@
+/* lisreg — Blackwell-native (sm_100a) scan-to-map registration engine.
+ *
+ * C-ABI drop-in boundary for the ONE hot path of QingzhiWang/LIS-SLAM named by
+ * BASELINE.json:north_star.  The reference has no FFI; its boundary is the set of
+ * C++ member functions the ROS callbacks invoke.  Each entry point
+ * below cites the reference interface it replaces (paths relative to the reference
+ * repo root).  Plain pointers and sizes only; no CUDA/torch types in signatures
+ * (a CUDA stream is passed as void*).  Point clouds are packed float4
+ * {x, y, z, intensity} (16 B), labels/rings are separate uint16 arrays.
+ *
+ * Conventions: every call returns int32 status — 0 ok; >0 soft conditions that
+ * mirror the reference (LISREG_NOT_ENOUGH_FEATURES: pose untouched,
+ * odomEstimationNode.cpp:598,623-625; LISREG_FEW_CORRESPONDENCES: some iteration
+ * had < min_sel matches and was a no-op, :870-872); <0 errors, text via
+ * lisreg_last_error().  No exceptions cross the ABI.  One context must not be used
+ * from two threads at once (the reference's scratch buffers are not re-entrant
+ * either, odomEstimationNode.cpp:40-48); distinct contexts are independent.
+ * There is NO CPU fallback: without a CUDA device every compute call fails with
+ * LISREG_ERR_CUDA.
+ */
+#ifndef LISREG_H
+#define LISREG_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LISREG_OK 0
+#define LISREG_NOT_ENOUGH_FEATURES 1
+#define LISREG_FEW_CORRESPONDENCES 2
+#define LISREG_ERR_ARG (-1)
+#define LISREG_ERR_CUDA (-2)
+#define LISREG_ERR_CAPACITY (-3)
+#define LISREG_ERR_NCCL (-4)
+
+#define LISREG_LUT_SIZE 64
+#define LISREG_MAX_ITERS 32
+
+typedef struct lisreg_ctx lisreg_ctx;
+
+typedef struct lisreg_config {
+  int32_t device;        /* CUDA device ordinal */
+  void* stream;          /* cudaStream_t to run on; NULL = engine-owned stream */
+  int32_t max_grid_cells;/* per-cloud uniform-grid capacity (0 = default 4M cells) */
+  int32_t reserved[5];
+} lisreg_config;
+
+/* Parameters of the three copies of the loop (variant A odomEstimationNode.cpp:596-974,
+ * B subMapOptmizationNode.cpp:1509-2001, C :4485-4976).  lisreg_lm_params_preset fills
+ * the reference constants. */
+typedef struct lisreg_lm_params {
+  int32_t max_iters;        /* 15 / 20 / 30 */
+  int32_t early_exit;       /* 1 = reference; 0 = run exactly max_iters (benchmark mode) */
+  float sqdist_gate;        /* 1.0 (A) / 2.0 (B, C): 5th-NN squared-distance gate */
+  float conv_rot_deg;       /* 0.005 / 0.003 / 0.002 */
+  float conv_trans_cm;      /* 0.05 / 0.03 / 0.02 */
+  int32_t edge_min_valid;   /* edgeFeatureMinValidNum (-1) */
+  int32_t surf_min_valid;   /* surfFeatureMinValidNum (100) */
+  int32_t min_sel;          /* 50 */
+  float degenerate_eig;     /* 100 */
+  int32_t use_label_weight; /* B/C: w = 2.0 - LabelSorce[label] */
+  float label_score[LISREG_LUT_SIZE];
+  int32_t degenerate_in;    /* persistent isDegenerate member carried in (quirk Q1) */
+  float rot_tolerance;      /* transformUpdate clamps, <= 0 disables */
+  float z_tolerance;
+  int32_t want_iter_log;    /* 1: fill lisreg_lm_iter records (debug/parity) */
+} lisreg_lm_params;
+
+typedef struct lisreg_lm_iter {
+  float AtA[36];
+  float AtB[6];
+  float X[6];
+  float pose[6];
+  int32_t n_sel, n_corner_sel, n_surf_sel, solved;
+  float deltaR, deltaT;
+} lisreg_lm_iter;
+
+typedef struct lisreg_lm_result {
+  int32_t status;
+  int32_t iters;
+  int32_t converged;
+  int32_t is_degenerate;
+  int32_t n_sel_last;
+  float deltaR, deltaT;
+  float pose[6];
+} lisreg_lm_result;
+
+/* one registration of a batch: host OR device pointers depending on the call */
+typedef struct lisreg_batch_item {
+  const float* corner;      /* nc x float4 */
+  const uint16_t* clabel;   /* nullable */
+  const float* surf;        /* ns x float4 */
+  const uint16_t* slabel;   /* nullable */
+  int32_t nc, ns;
+  int32_t map_id;
+  int32_t reserved;
+} lisreg_batch_item;
+
+/* ---- lifecycle ---- */
+int32_t lisreg_create(const lisreg_config* cfg, lisreg_ctx** out);
+void lisreg_destroy(lisreg_ctx* ctx);
+const char* lisreg_last_error(const lisreg_ctx* ctx);
+const char* lisreg_version(void);
+int32_t lisreg_sync(lisreg_ctx* ctx);
+/* number of engine kernels launched since create (bench.py "gpu_launches") */
+int64_t lisreg_launch_count(const lisreg_ctx* ctx);
+
+void lisreg_lm_params_preset(lisreg_lm_params* p, char variant /* 'A','B','C' */);
+
+/* ---- local map + spatial index ----
+ * Replaces kdtreeCornerFromMap/SurfFromMap->setInputCloud (odomEstimationNode.cpp:602-603;
+ * B subMapOptmizationNode.cpp:1516-1517): uploads the two map clouds and builds the
+ * device index (uniform grid, exact within the sqdist gate).  gate_hint = largest
+ * sqdist_gate that will be used against this map (sets the cell size). */
+int32_t lisreg_map_create(lisreg_ctx* ctx, const float* corner, int32_t mc,
+                          const float* surf, int32_t ms, float gate_hint, int32_t* map_id);
+int32_t lisreg_map_create_dev(lisreg_ctx* ctx, const float* d_corner, int32_t mc,
+                              const float* d_surf, int32_t ms, float gate_hint, int32_t* map_id);
+int32_t lisreg_map_destroy(lisreg_ctx* ctx, int32_t map_id);
+
+/* exact k-NN against one cloud of a map (which: 0 corner, 1 surf), host buffers.
+ * Replaces KdTreeFLANN::nearestKSearch (odomEstimationNode.cpp:650, :766) for tests:
+ * idx/sqd are nq x 5, sorted ascending; entries beyond the gate are idx=-1, sqd=FLT_MAX. */
+int32_t lisreg_knn5(lisreg_ctx* ctx, int32_t map_id, int32_t which, const float* queries,
+                    int32_t nq, float sqdist_gate, int32_t* idx, float* sqd);
+
+/* ---- scan-to-map registration (B2) ----
+ * Replaces OdomEstimationNode::scan2SubMapOptimization() (odomEstimationNode.cpp:596-626)
+ * and its two copies.  pose6 = transformTobeMapped [roll,pitch,yaw,x,y,z] in: guess, out: result. */
+int32_t lisreg_scan2map(lisreg_ctx* ctx, int32_t map_id,
+                        const float* corner, const uint16_t* clabel, int32_t nc,
+                        const float* surf, const uint16_t* slabel, int32_t ns,
+                        float pose6[6], const lisreg_lm_params* prm,
+                        lisreg_lm_result* res, lisreg_lm_iter* iter_log /* nullable, max_iters */);
+
+/* throughput mode (BASELINE config 3): B independent registrations, host buffers;
+ * H2D of all clouds, the solve, and D2H of results happen inside the call. */
+int32_t lisreg_scan2map_batch(lisreg_ctx* ctx, int32_t B, const lisreg_batch_item* items,
+                              float* pose6xB, const lisreg_lm_params* prm,
+                              lisreg_lm_result* resxB, lisreg_lm_iter* iter_log /* nullable, B*max_iters */);
+
+/* same with every buffer already resident in HBM (items[] itself is a host array of
+ * device pointers; d_pose6xB and d_resxB are device pointers).  Asynchronous on the
+ * context stream; call lisreg_sync() before reading results. */
+int32_t lisreg_scan2map_batch_dev(lisreg_ctx* ctx, int32_t B, const lisreg_batch_item* items,
+                                  float* d_pose6xB, const lisreg_lm_params* prm,
+                                  lisreg_lm_result* d_resxB);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LISREG_H */

@@ -1,0 +1,522 @@
+// lisreg C-ABI implementation (include/lisreg.h): context, map index build, LM driver.
+// sm_100a only; there is no CPU fallback — every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/lisreg.h"
+#include "lm.cuh"
+
+using namespace lisreg;
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct CloudIndex {   // one cloud of a map
+  float4* sorted = nullptr;
+  uint32_t* cell_start = nullptr;
+  GridDev g{};
+};
+
+struct MapSlot {
+  bool used = false;
+  CloudIndex corner, surf;
+};
+
+struct lisreg_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int max_cells = 4 << 20;
+  std::string err;
+  int64_t launches = 0;
+  std::vector<MapSlot> maps;
+  MapDev* d_maps = nullptr; int d_maps_cap = 0; bool maps_dirty = true;
+  // scratch
+  DevBuf d_stage, d_descs, d_states, d_partials, d_tickets, d_logs, d_pose, d_res, d_tmp, d_bbox;
+  PinBuf h_stage, h_out;
+};
+
+static int fail(lisreg_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+  return fail(ctx, LISREG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define LAUNCH_CK() do { ctx->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) \
+  return fail(ctx, LISREG_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// grid build kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned f2ord(float f) { unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float ord2f(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+__global__ void k_bbox_init(unsigned* bb) { if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffu; else if (threadIdx.x < 6) bb[threadIdx.x] = 0u; }
+
+__global__ void k_bbox(const float4* __restrict__ pts, int n, unsigned* __restrict__ bb) {
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = __ldg(&pts[i]);
+    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+    mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+  }
+#pragma unroll
+  for (int d = 0; d < 3; d++)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) { atomicMin(&bb[d], f2ord(mn[d])); atomicMax(&bb[3 + d], f2ord(mx[d])); }
+  }
+}
+
+// one thread: choose the cell size (>= h_req, grown until the grid fits max_cells) and dims
+__global__ void k_grid_plan(const unsigned* __restrict__ bb, float h_req, int max_cells, int n, GridDev* __restrict__ out) {
+  GridDev g;
+  float mn[3], mx[3];
+  for (int d = 0; d < 3; d++) { mn[d] = ord2f(bb[d]); mx[d] = ord2f(bb[3 + d]); }
+  if (n <= 0) { for (int d = 0; d < 3; d++) { mn[d] = 0.f; mx[d] = 0.f; } }
+  float h = h_req;
+  int nx, ny, nz;
+  for (;;) {
+    nx = (int)floorf((mx[0] - mn[0]) / h) + 2; ny = (int)floorf((mx[1] - mn[1]) / h) + 2; nz = (int)floorf((mx[2] - mn[2]) / h) + 2;
+    if ((double)nx * (double)ny * (double)nz <= (double)max_cells) break;
+    h *= 1.25f;
+  }
+  g.ox = mn[0] - 0.5f * h; g.oy = mn[1] - 0.5f * h; g.oz = mn[2] - 0.5f * h;   // half-cell apron keeps boundary points interior
+  g.h = h; g.inv_h = 1.0f / h; g.nx = nx; g.ny = ny; g.nz = nz; g.n = n; g.ncells = nx * ny * nz;
+  g.cell_start = nullptr; g.pts = nullptr;
+  *out = g;
+}
+
+__device__ __forceinline__ int cell_of(const GridDev& g, float4 p) {
+  int cx = min(max(cell_coord(p.x, g.ox, g.inv_h), 0), g.nx - 1);
+  int cy = min(max(cell_coord(p.y, g.oy, g.inv_h), 0), g.ny - 1);
+  int cz = min(max(cell_coord(p.z, g.oz, g.inv_h), 0), g.nz - 1);
+  return (cz * g.ny + cy) * g.nx + cx;
+}
+
+__global__ void k_cell_count(const float4* __restrict__ pts, int n, GridDev g, int* __restrict__ cell_id, uint32_t* __restrict__ counts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = cell_of(g, __ldg(&pts[i]));
+  cell_id[i] = c;
+  atomicAdd(&counts[c], 1u);
+}
+
+// exclusive scan, three phases, 1024 elements per block
+constexpr int SCAN_BLOCK = 1024;
+__global__ void k_scan_local(uint32_t* __restrict__ data, int n, uint32_t* __restrict__ block_sums) {
+  __shared__ uint32_t s[SCAN_BLOCK];
+  int i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+  uint32_t v = i < n ? data[i] : 0u;
+  s[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
+    uint32_t t = threadIdx.x >= o ? s[threadIdx.x - o] : 0u;
+    __syncthreads();
+    s[threadIdx.x] += t;
+    __syncthreads();
+  }
+  if (i < n) data[i] = s[threadIdx.x] - v;   // exclusive
+  if (threadIdx.x == SCAN_BLOCK - 1) block_sums[blockIdx.x] = s[threadIdx.x];
+}
+__global__ void k_scan_sums(uint32_t* __restrict__ block_sums, int nb) {   // single block, sequential chunks
+  __shared__ uint32_t s[SCAN_BLOCK];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0u;
+  __syncthreads();
+  for (int base = 0; base < nb; base += SCAN_BLOCK) {
+    int i = base + threadIdx.x;
+    uint32_t v = i < nb ? block_sums[i] : 0u;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
+      uint32_t t = threadIdx.x >= o ? s[threadIdx.x - o] : 0u;
+      __syncthreads();
+      s[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nb) block_sums[i] = s[threadIdx.x] - v + carry;
+    __syncthreads();
+    if (threadIdx.x == SCAN_BLOCK - 1) carry += s[threadIdx.x];
+    __syncthreads();
+  }
+}
+__global__ void k_scan_add(uint32_t* __restrict__ data, int n, const uint32_t* __restrict__ block_sums) {
+  int i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+  if (i < n) data[i] += block_sums[blockIdx.x];
+}
+
+__global__ void k_cell_scatter(const float4* __restrict__ pts, int n, const int* __restrict__ cell_id,
+                               const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ fill, float4* __restrict__ sorted) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = cell_id[i];
+  uint32_t pos = cell_start[c] + atomicAdd(&fill[c], 1u);
+  float4 p = __ldg(&pts[i]);
+  p.w = __int_as_float(i);
+  sorted[pos] = p;
+}
+
+// builds one cloud index from device-resident points
+static int build_cloud_index(lisreg_ctx* ctx, const float4* d_pts, int n, float h_req, CloudIndex* ci) {
+  cudaStream_t st = ctx->stream;
+  CK(ctx->d_bbox.reserve(6 * sizeof(unsigned) + sizeof(GridDev)));
+  unsigned* bb = (unsigned*)ctx->d_bbox.p;
+  GridDev* d_g = (GridDev*)((char*)ctx->d_bbox.p + 32);
+  k_bbox_init<<<1, 32, 0, st>>>(bb); LAUNCH_CK();
+  if (n > 0) { k_bbox<<<std::min(1184, (n + 255) / 256), 256, 0, st>>>(d_pts, n, bb); LAUNCH_CK(); }
+  k_grid_plan<<<1, 1, 0, st>>>(bb, h_req, ctx->max_cells, n, d_g); LAUNCH_CK();
+  GridDev g;
+  CK(cudaMemcpyAsync(&g, d_g, sizeof(g), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const int ncells = g.ncells;
+  CK(cudaMalloc(&ci->sorted, sizeof(float4) * (size_t)std::max(n, 1)));
+  CK(cudaMalloc(&ci->cell_start, sizeof(uint32_t) * ((size_t)ncells + 1)));
+  const int nblk = (ncells + 1 + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  CK(ctx->d_tmp.reserve(sizeof(int) * (size_t)std::max(n, 1) + sizeof(uint32_t) * ((size_t)ncells + 1) + sizeof(uint32_t) * (size_t)(nblk + 1)));
+  int* cell_id = (int*)ctx->d_tmp.p;
+  uint32_t* fill = (uint32_t*)(cell_id + std::max(n, 1));
+  uint32_t* bsums = fill + (ncells + 1);
+  CK(cudaMemsetAsync(ci->cell_start, 0, sizeof(uint32_t) * ((size_t)ncells + 1), st));
+  CK(cudaMemsetAsync(fill, 0, sizeof(uint32_t) * ((size_t)ncells + 1), st));
+  if (n > 0) { k_cell_count<<<(n + 255) / 256, 256, 0, st>>>(d_pts, n, g, cell_id, ci->cell_start); LAUNCH_CK(); }
+  k_scan_local<<<nblk, SCAN_BLOCK, 0, st>>>(ci->cell_start, ncells + 1, bsums); LAUNCH_CK();
+  k_scan_sums<<<1, SCAN_BLOCK, 0, st>>>(bsums, nblk); LAUNCH_CK();
+  k_scan_add<<<nblk, SCAN_BLOCK, 0, st>>>(ci->cell_start, ncells + 1, bsums); LAUNCH_CK();
+  if (n > 0) { k_cell_scatter<<<(n + 255) / 256, 256, 0, st>>>(d_pts, n, cell_id, ci->cell_start, fill, ci->sorted); LAUNCH_CK(); }
+  g.cell_start = ci->cell_start; g.pts = ci->sorted;
+  ci->g = g;
+  return LISREG_OK;
+}
+
+static float cell_size_for_gate(float gate) { return 1.002f * sqrtf(gate > 0.f ? gate : 1.f) + 1e-3f; }
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* lisreg_version(void) { return "lisreg 0.1 (sm_100a)"; }
+
+int32_t lisreg_create(const lisreg_config* cfg, lisreg_ctx** out) {
+  if (!out) return LISREG_ERR_ARG;
+  *out = nullptr;
+  lisreg_ctx* ctx = new lisreg_ctx();
+  ctx->device = cfg ? cfg->device : 0;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || ctx->device >= ndev) {
+    // no CPU fallback: fail loudly
+    fprintf(stderr, "lisreg_create: no usable CUDA device (%s); this engine has no CPU path\n",
+            e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
+    delete ctx;
+    return LISREG_ERR_CUDA;
+  }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { delete ctx; return LISREG_ERR_CUDA; }
+  if (cfg && cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
+  else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LISREG_ERR_CUDA; } ctx->own_stream = true; }
+  if (cfg && cfg->max_grid_cells > 0) ctx->max_cells = cfg->max_grid_cells;
+  *out = ctx;
+  return LISREG_OK;
+}
+
+void lisreg_destroy(lisreg_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& m : ctx->maps) if (m.used) {
+    cudaFree(m.corner.sorted); cudaFree(m.corner.cell_start); cudaFree(m.surf.sorted); cudaFree(m.surf.cell_start);
+  }
+  if (ctx->d_maps) cudaFree(ctx->d_maps);
+  for (DevBuf* b : {&ctx->d_stage, &ctx->d_descs, &ctx->d_states, &ctx->d_partials, &ctx->d_tickets, &ctx->d_logs,
+                    &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox}) b->release();
+  ctx->h_stage.release(); ctx->h_out.release();
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* lisreg_last_error(const lisreg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int64_t lisreg_launch_count(const lisreg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t lisreg_sync(lisreg_ctx* ctx) {
+  if (!ctx) return LISREG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LISREG_OK;
+}
+
+void lisreg_lm_params_preset(lisreg_lm_params* p, char variant) {
+  static const float score[20] = {1.0f, 1.0f, 0.6f, 0.5f, 0.8f, 0.5f, 0.5f, 0.5f, 0.5f, 1.2f,
+                                  1.2f, 1.2f, 0.5f, 1.0f, 0.8f, 0.5f, 1.3f, 0.5f, 1.5f, 1.5f};   // config/label.yaml:214-234
+  memset(p, 0, sizeof(*p));
+  p->early_exit = 1; p->edge_min_valid = -1; p->surf_min_valid = 100; p->min_sel = 50; p->degenerate_eig = 100.f;
+  p->rot_tolerance = 1000.f; p->z_tolerance = 1000.f;   // config/params.yaml:123-124
+  for (int i = 0; i < 20; i++) p->label_score[i] = score[i];
+  switch (variant) {
+    case 'B': p->max_iters = 20; p->sqdist_gate = 2.0f; p->conv_rot_deg = 0.003f; p->conv_trans_cm = 0.03f; p->use_label_weight = 1; break;
+    case 'C': p->max_iters = 30; p->sqdist_gate = 2.0f; p->conv_rot_deg = 0.002f; p->conv_trans_cm = 0.02f; p->use_label_weight = 1; break;
+    default:  p->max_iters = 15; p->sqdist_gate = 1.0f; p->conv_rot_deg = 0.005f; p->conv_trans_cm = 0.05f; p->use_label_weight = 0; break;
+  }
+}
+
+static int map_alloc_slot(lisreg_ctx* ctx) {
+  for (size_t i = 0; i < ctx->maps.size(); i++) if (!ctx->maps[i].used) return (int)i;
+  ctx->maps.emplace_back();
+  return (int)ctx->maps.size() - 1;
+}
+
+int32_t lisreg_map_create_dev(lisreg_ctx* ctx, const float* d_corner, int32_t mc, const float* d_surf, int32_t ms,
+                              float gate_hint, int32_t* map_id) {
+  if (!ctx || !map_id || mc < 0 || ms < 0 || (mc > 0 && !d_corner) || (ms > 0 && !d_surf)) return fail(ctx, LISREG_ERR_ARG, "lisreg_map_create: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  const int slot = map_alloc_slot(ctx);
+  MapSlot& m = ctx->maps[slot];
+  const float h = cell_size_for_gate(gate_hint);
+  int rc = build_cloud_index(ctx, (const float4*)d_corner, mc, h, &m.corner);
+  if (rc) return rc;
+  rc = build_cloud_index(ctx, (const float4*)d_surf, ms, h, &m.surf);
+  if (rc) return rc;
+  m.used = true;
+  ctx->maps_dirty = true;
+  *map_id = slot;
+  return LISREG_OK;
+}
+
+int32_t lisreg_map_create(lisreg_ctx* ctx, const float* corner, int32_t mc, const float* surf, int32_t ms,
+                          float gate_hint, int32_t* map_id) {
+  if (!ctx || !map_id || mc < 0 || ms < 0 || (mc > 0 && !corner) || (ms > 0 && !surf)) return fail(ctx, LISREG_ERR_ARG, "lisreg_map_create: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  const size_t bc = sizeof(float4) * (size_t)mc, bs = sizeof(float4) * (size_t)ms;
+  CK(ctx->d_stage.reserve(bc + bs + 32));
+  char* d = (char*)ctx->d_stage.p;
+  if (mc) CK(cudaMemcpyAsync(d, corner, bc, cudaMemcpyHostToDevice, ctx->stream));
+  if (ms) CK(cudaMemcpyAsync(d + bc, surf, bs, cudaMemcpyHostToDevice, ctx->stream));
+  return lisreg_map_create_dev(ctx, (const float*)d, mc, (const float*)(d + bc), ms, gate_hint, map_id);
+}
+
+int32_t lisreg_map_destroy(lisreg_ctx* ctx, int32_t map_id) {
+  if (!ctx || map_id < 0 || map_id >= (int)ctx->maps.size() || !ctx->maps[map_id].used) return fail(ctx, LISREG_ERR_ARG, "lisreg_map_destroy: bad map id");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  MapSlot& m = ctx->maps[map_id];
+  cudaFree(m.corner.sorted); cudaFree(m.corner.cell_start); cudaFree(m.surf.sorted); cudaFree(m.surf.cell_start);
+  m = MapSlot();
+  ctx->maps_dirty = true;
+  return LISREG_OK;
+}
+
+static int sync_maps(lisreg_ctx* ctx) {
+  if (!ctx->maps_dirty) return LISREG_OK;
+  const int n = (int)ctx->maps.size();
+  if (n > ctx->d_maps_cap) {
+    if (ctx->d_maps) cudaFree(ctx->d_maps);
+    ctx->d_maps_cap = std::max(16, 2 * n);
+    CK(cudaMalloc(&ctx->d_maps, sizeof(MapDev) * ctx->d_maps_cap));
+  }
+  std::vector<MapDev> h(n);
+  for (int i = 0; i < n; i++) { h[i].corner = ctx->maps[i].corner.g; h[i].surf = ctx->maps[i].surf.g; }
+  if (n) {
+    CK(cudaMemcpyAsync(ctx->d_maps, h.data(), sizeof(MapDev) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // h is a stack-lifetime pageable buffer
+  }
+  ctx->maps_dirty = false;
+  return LISREG_OK;
+}
+
+int32_t lisreg_knn5(lisreg_ctx* ctx, int32_t map_id, int32_t which, const float* queries, int32_t nq, float sqdist_gate,
+                    int32_t* idx, float* sqd) {
+  if (!ctx || map_id < 0 || map_id >= (int)ctx->maps.size() || !ctx->maps[map_id].used || nq < 0) return fail(ctx, LISREG_ERR_ARG, "lisreg_knn5: bad argument");
+  if (nq == 0) return LISREG_OK;
+  CK(cudaSetDevice(ctx->device));
+  const GridDev g = which == 0 ? ctx->maps[map_id].corner.g : ctx->maps[map_id].surf.g;
+  const size_t bq = sizeof(float4) * (size_t)nq, bi = sizeof(int) * 5 * (size_t)nq, bd = sizeof(float) * 5 * (size_t)nq;
+  CK(ctx->d_stage.reserve(bq + bi + bd));
+  char* d = (char*)ctx->d_stage.p;
+  CK(cudaMemcpyAsync(d, queries, bq, cudaMemcpyHostToDevice, ctx->stream));
+  k_knn5<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(g, (const float4*)d, nq, sqdist_gate, (int*)(d + bq), (float*)(d + bq + bi)); LAUNCH_CK();
+  CK(cudaMemcpyAsync(idx, d + bq, bi, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(sqd, d + bq + bi, bd, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LISREG_OK;
+}
+
+static void to_dev_params(const lisreg_lm_params* p, LmParamsDev* d) {
+  d->max_iters = std::min(p->max_iters, (int)LISREG_MAX_ITERS); d->early_exit = p->early_exit;
+  d->gate = p->sqdist_gate; d->conv_rot = p->conv_rot_deg; d->conv_trans = p->conv_trans_cm;
+  d->edge_min = p->edge_min_valid; d->surf_min = p->surf_min_valid; d->min_sel = p->min_sel;
+  d->degenerate_eig = p->degenerate_eig; d->use_w = p->use_label_weight;
+  d->rot_tol = p->rot_tolerance; d->z_tol = p->z_tolerance; d->degenerate_in = p->degenerate_in;
+  memcpy(d->label_score, p->label_score, sizeof(d->label_score));
+}
+
+// core driver: descs already on the device. max_n = largest nc+ns of the batch.
+static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, float* d_pose, const lisreg_lm_params* prm,
+                  lisreg_lm_result* d_res, lisreg_lm_iter* d_logs) {
+  cudaStream_t st = ctx->stream;
+  int rc = sync_maps(ctx);
+  if (rc) return rc;
+  LmParamsDev dp; to_dev_params(prm, &dp);
+  // tile size: big batches amortise the 27-term reduction over 4 queries per thread; a lone
+  // registration is spread over as many SMs as possible
+  const int tile_pts = (B >= 32) ? LM_THREADS * 4 : LM_THREADS;
+  const int max_tiles = std::max(1, (max_n + tile_pts - 1) / tile_pts);
+  CK(ctx->d_states.reserve(sizeof(RegState) * (size_t)B));
+  CK(ctx->d_partials.reserve(sizeof(double) * LM_NSUM * (size_t)B * max_tiles));
+  CK(ctx->d_tickets.reserve(sizeof(int) * (size_t)B));
+  RegState* states = (RegState*)ctx->d_states.p;
+  double* partials = (double*)ctx->d_partials.p;
+  int* tickets = (int*)ctx->d_tickets.p;
+  k_lm_init<<<(B + 127) / 128, 128, 0, st>>>(d_descs, states, d_pose, dp, tickets, B); LAUNCH_CK();
+  dim3 grid(max_tiles, B);
+  for (int it = 0; it < dp.max_iters; it++) {
+    k_lm_iter<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp, partials, tickets, d_logs, max_tiles, tile_pts); LAUNCH_CK();
+  }
+  k_lm_finish<<<(B + 127) / 128, 128, 0, st>>>(states, d_pose, d_res, B); LAUNCH_CK();
+  return LISREG_OK;
+}
+
+int32_t lisreg_scan2map_batch_dev(lisreg_ctx* ctx, int32_t B, const lisreg_batch_item* items, float* d_pose6xB,
+                                  const lisreg_lm_params* prm, lisreg_lm_result* d_resxB) {
+  if (!ctx || B <= 0 || !items || !d_pose6xB || !prm || !d_resxB) return fail(ctx, LISREG_ERR_ARG, "lisreg_scan2map_batch_dev: bad argument");
+  if (prm->max_iters <= 0 || prm->max_iters > LISREG_MAX_ITERS) return fail(ctx, LISREG_ERR_ARG, "max_iters must be in 1..%d", LISREG_MAX_ITERS);
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->h_stage.reserve(sizeof(RegDesc) * (size_t)B));
+  CK(ctx->d_descs.reserve(sizeof(RegDesc) * (size_t)B));
+  RegDesc* h = (RegDesc*)ctx->h_stage.p;
+  int max_n = 0;
+  for (int b = 0; b < B; b++) {
+    const lisreg_batch_item& it = items[b];
+    if (it.nc < 0 || it.ns < 0 || it.map_id < 0 || it.map_id >= (int)ctx->maps.size() || !ctx->maps[it.map_id].used)
+      return fail(ctx, LISREG_ERR_ARG, "batch item %d: bad sizes or map id", b);
+    h[b].corner = (const float4*)it.corner; h[b].surf = (const float4*)it.surf;
+    h[b].clabel = it.clabel; h[b].slabel = it.slabel; h[b].nc = it.nc; h[b].ns = it.ns; h[b].map_slot = it.map_id; h[b].pad = 0;
+    max_n = std::max(max_n, it.nc + it.ns);
+  }
+  CK(cudaMemcpyAsync(ctx->d_descs.p, h, sizeof(RegDesc) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
+  lisreg_lm_iter* d_logs = nullptr;
+  return run_lm(ctx, B, (const RegDesc*)ctx->d_descs.p, max_n, d_pose6xB, prm, d_resxB, d_logs);
+}
+
+int32_t lisreg_scan2map_batch(lisreg_ctx* ctx, int32_t B, const lisreg_batch_item* items, float* pose6xB,
+                              const lisreg_lm_params* prm, lisreg_lm_result* resxB, lisreg_lm_iter* iter_log) {
+  if (!ctx || B <= 0 || !items || !pose6xB || !prm || !resxB) return fail(ctx, LISREG_ERR_ARG, "lisreg_scan2map_batch: bad argument");
+  if (prm->max_iters <= 0 || prm->max_iters > LISREG_MAX_ITERS) return fail(ctx, LISREG_ERR_ARG, "max_iters must be in 1..%d", LISREG_MAX_ITERS);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  // pack: [descs][poses][clouds...][labels...] into one pinned staging buffer -> one H2D copy
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
+  const size_t o_desc = take(sizeof(RegDesc) * (size_t)B);
+  const size_t o_pose = take(sizeof(float) * 6 * (size_t)B);
+  std::vector<size_t> oc(B), os(B), ocl(B), osl(B);
+  int max_n = 0;
+  for (int b = 0; b < B; b++) {
+    const lisreg_batch_item& it = items[b];
+    if (it.nc < 0 || it.ns < 0 || (it.nc > 0 && !it.corner) || (it.ns > 0 && !it.surf) ||
+        it.map_id < 0 || it.map_id >= (int)ctx->maps.size() || !ctx->maps[it.map_id].used)
+      return fail(ctx, LISREG_ERR_ARG, "batch item %d: bad sizes, pointers or map id", b);
+    oc[b] = take(sizeof(float4) * (size_t)it.nc);
+    os[b] = take(sizeof(float4) * (size_t)it.ns);
+    ocl[b] = it.clabel ? take(sizeof(uint16_t) * (size_t)it.nc) : (size_t)-1;
+    osl[b] = it.slabel ? take(sizeof(uint16_t) * (size_t)it.ns) : (size_t)-1;
+    max_n = std::max(max_n, it.nc + it.ns);
+  }
+  const size_t total = off;
+  CK(ctx->h_stage.reserve(total));
+  CK(ctx->d_stage.reserve(total));
+  char* h = (char*)ctx->h_stage.p; char* d = (char*)ctx->d_stage.p;
+  RegDesc* hd = (RegDesc*)(h + o_desc);
+  memcpy(h + o_pose, pose6xB, sizeof(float) * 6 * (size_t)B);
+  for (int b = 0; b < B; b++) {
+    const lisreg_batch_item& it = items[b];
+    if (it.nc) memcpy(h + oc[b], it.corner, sizeof(float4) * (size_t)it.nc);
+    if (it.ns) memcpy(h + os[b], it.surf, sizeof(float4) * (size_t)it.ns);
+    if (it.clabel && it.nc) memcpy(h + ocl[b], it.clabel, sizeof(uint16_t) * (size_t)it.nc);
+    if (it.slabel && it.ns) memcpy(h + osl[b], it.slabel, sizeof(uint16_t) * (size_t)it.ns);
+    hd[b].corner = (const float4*)(d + oc[b]); hd[b].surf = (const float4*)(d + os[b]);
+    hd[b].clabel = it.clabel ? (const uint16_t*)(d + ocl[b]) : nullptr;
+    hd[b].slabel = it.slabel ? (const uint16_t*)(d + osl[b]) : nullptr;
+    hd[b].nc = it.nc; hd[b].ns = it.ns; hd[b].map_slot = it.map_id; hd[b].pad = 0;
+  }
+  CK(cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, st));
+  CK(ctx->d_res.reserve(sizeof(lisreg_lm_result) * (size_t)B));
+  lisreg_lm_iter* d_logs = nullptr;
+  const bool want_log = iter_log && prm->want_iter_log;
+  if (want_log) {
+    CK(ctx->d_logs.reserve(sizeof(lisreg_lm_iter) * (size_t)B * LISREG_MAX_ITERS));
+    d_logs = (lisreg_lm_iter*)ctx->d_logs.p;
+    CK(cudaMemsetAsync(d_logs, 0, sizeof(lisreg_lm_iter) * (size_t)B * LISREG_MAX_ITERS, st));
+  }
+  int rc = run_lm(ctx, B, (const RegDesc*)(d + o_desc), max_n, (float*)(d + o_pose), prm, (lisreg_lm_result*)ctx->d_res.p, d_logs);
+  if (rc) return rc;
+  CK(ctx->h_out.reserve(sizeof(lisreg_lm_result) * (size_t)B + (want_log ? sizeof(lisreg_lm_iter) * (size_t)B * LISREG_MAX_ITERS : 0)));
+  CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_res.p, sizeof(lisreg_lm_result) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  if (want_log)
+    CK(cudaMemcpyAsync((char*)ctx->h_out.p + sizeof(lisreg_lm_result) * (size_t)B, d_logs,
+                       sizeof(lisreg_lm_iter) * (size_t)B * LISREG_MAX_ITERS, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const lisreg_lm_result* hr = (const lisreg_lm_result*)ctx->h_out.p;
+  int worst = LISREG_OK;
+  for (int b = 0; b < B; b++) {
+    resxB[b] = hr[b];
+    if (hr[b].status != LISREG_NOT_ENOUGH_FEATURES) memcpy(pose6xB + 6 * (size_t)b, hr[b].pose, sizeof(float) * 6);
+    worst = std::max(worst, hr[b].status);
+  }
+  if (want_log) {
+    const lisreg_lm_iter* hl = (const lisreg_lm_iter*)((const char*)ctx->h_out.p + sizeof(lisreg_lm_result) * (size_t)B);
+    for (int b = 0; b < B; b++)
+      memcpy(iter_log + (size_t)b * prm->max_iters, hl + (size_t)b * LISREG_MAX_ITERS, sizeof(lisreg_lm_iter) * (size_t)prm->max_iters);
+  }
+  return worst;
+}
+
+int32_t lisreg_scan2map(lisreg_ctx* ctx, int32_t map_id, const float* corner, const uint16_t* clabel, int32_t nc,
+                        const float* surf, const uint16_t* slabel, int32_t ns, float pose6[6], const lisreg_lm_params* prm,
+                        lisreg_lm_result* res, lisreg_lm_iter* iter_log) {
+  lisreg_batch_item it;
+  it.corner = corner; it.clabel = clabel; it.surf = surf; it.slabel = slabel; it.nc = nc; it.ns = ns; it.map_id = map_id; it.reserved = 0;
+  return lisreg_scan2map_batch(ctx, 1, &it, pose6, prm, res, iter_log);
+}
+
+}  // extern "C"

@@ -1,0 +1,366 @@
+// Fused scan-to-map iteration kernel:
+//   transform -> gated exact 5-NN -> {point-to-line | point-to-plane} coefficient ->
+//   Jacobian row -> 27-term J^T J / J^T r reduction -> (last block) 6x6 solve + pose update.
+// One launch = one Gauss-Newton iteration of EVERY registration of a batch.
+//
+// Reference: cornerOptimization odomEstimationNode.cpp:633-747, surfOptimization :749-827,
+// combineOptimizationCoeffs :829-850 (disappears: row order does not affect A^T A),
+// LMOptimization :852-974, transformUpdate clamps :1001-1003; variants B/C
+// subMapOptmizationNode.cpp:1509-2001, :4485-4976.  Per-point arithmetic keeps the
+// reference's fp32 expression order (translation unit is compiled with --fmad=false);
+// the 27 sums are accumulated in fp64 like OpenCV's float GEMM.
+#pragma once
+#include "grid.cuh"
+#include "smallmat.cuh"
+#include "../../include/lisreg.h"
+
+namespace lisreg {
+
+struct MapDev { GridDev corner, surf; };
+
+struct RegDesc {
+  const float4* corner; const float4* surf;
+  const uint16_t* clabel; const uint16_t* slabel;
+  int nc, ns, map_slot, pad;
+};
+
+struct RegState {
+  float pose[6];
+  float T[12];
+  float trig[6];   // srx crx sry cry srz crz  (rx<-pitch, ry<-yaw, rz<-roll, :862-867)
+  int iter, done, converged, degenerate, any_small, n_sel_last, status;
+  float deltaR, deltaT;
+};
+
+struct LmParamsDev {
+  int max_iters, early_exit;
+  float gate, conv_rot, conv_trans;
+  int edge_min, surf_min, min_sel;
+  float degenerate_eig;
+  int use_w;
+  float rot_tol, z_tol;
+  int degenerate_in;
+  float label_score[LISREG_LUT_SIZE];
+};
+
+constexpr int LM_THREADS = 128;
+constexpr int LM_NSUM = 32;   // 21 AtA (upper) + 6 AtB + nCorner + nSurf + pad
+
+__device__ __forceinline__ float sinf_cr(float x) { return (float)sin((double)x); }
+__device__ __forceinline__ float cosf_cr(float x) { return (float)cos((double)x); }
+
+// pcl::getTransformation closed form (common.cpp:55-58) + LOAM trig set (:862-867)
+__device__ inline void state_refresh(RegState& s) {
+  float roll = s.pose[0], pitch = s.pose[1], yaw = s.pose[2];
+  float A = cosf_cr(yaw), B = sinf_cr(yaw), C = cosf_cr(pitch), D = sinf_cr(pitch);
+  float E = cosf_cr(roll), F = sinf_cr(roll), DE = D * E, DF = D * F;
+  s.T[0] = A * C;  s.T[1] = A * DF - B * E;  s.T[2] = B * F + A * DE;  s.T[3] = s.pose[3];
+  s.T[4] = B * C;  s.T[5] = A * E + B * DF;  s.T[6] = B * DE - A * F;  s.T[7] = s.pose[4];
+  s.T[8] = -D;     s.T[9] = C * F;           s.T[10] = C * E;          s.T[11] = s.pose[5];
+  s.trig[0] = D; s.trig[1] = C;   // srx crx <- pitch
+  s.trig[2] = B; s.trig[3] = A;   // sry cry <- yaw
+  s.trig[4] = F; s.trig[5] = E;   // srz crz <- roll
+}
+
+// cornerOptimization body after the kNN (:657-742). nb = 5 neighbours. raw = {la,lb,lc,ld2,s}
+__device__ __forceinline__ bool corner_coeff(float x0, float y0, float z0, const float4 (&nb)[5], float (&raw)[5]) {
+  float cx = 0, cy = 0, cz = 0;
+#pragma unroll
+  for (int j = 0; j < 5; j++) { cx += nb[j].x; cy += nb[j].y; cz += nb[j].z; }
+  cx /= 5; cy /= 5; cz /= 5;
+  float a11 = 0, a12 = 0, a13 = 0, a22 = 0, a23 = 0, a33 = 0;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    float ax = nb[j].x - cx, ay = nb[j].y - cy, az = nb[j].z - cz;
+    a11 += ax * ax; a12 += ax * ay; a13 += ax * az; a22 += ay * ay; a23 += ay * az; a33 += az * az;
+  }
+  a11 /= 5; a12 /= 5; a13 /= 5; a22 /= 5; a23 /= 5; a33 /= 5;
+  float A[9] = {a11, a12, a13, a12, a22, a23, a13, a23, a33}, W[3], V[9];
+  jacobi_eigen<3>(A, W, V);
+  if (!(W[0] > 3 * W[1])) return false;
+  float x1 = (float)((double)cx + 0.1 * (double)V[0]), y1 = (float)((double)cy + 0.1 * (double)V[1]), z1 = (float)((double)cz + 0.1 * (double)V[2]);
+  float x2 = (float)((double)cx - 0.1 * (double)V[0]), y2 = (float)((double)cy - 0.1 * (double)V[1]), z2 = (float)((double)cz - 0.1 * (double)V[2]);
+  float a012 = sqrtf(((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1)) * ((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1)) +
+                     ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1)) * ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1)) +
+                     ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1)) * ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1)));
+  float l12 = sqrtf((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2));
+  float la = ((y1 - y2) * ((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1)) +
+              (z1 - z2) * ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1))) / a012 / l12;
+  float lb = -((x1 - x2) * ((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1)) -
+               (z1 - z2) * ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1))) / a012 / l12;
+  float lc = -((x1 - x2) * ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1)) +
+               (y1 - y2) * ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1))) / a012 / l12;
+  float ld2 = a012 / l12;
+  float s = (float)(1.0 - 0.9 * (double)fabsf(ld2));
+  raw[0] = la; raw[1] = lb; raw[2] = lc; raw[3] = ld2; raw[4] = s;
+  return (double)s > 0.1;
+}
+
+// surfOptimization body after the kNN (:776-821). raw = {pa,pb,pc,pd2,s}
+__device__ __forceinline__ bool surf_coeff(float x0, float y0, float z0, const float4 (&nb)[5], float (&raw)[5]) {
+  float A0[15], X0[3];
+  const float B0[5] = {-1.f, -1.f, -1.f, -1.f, -1.f};
+#pragma unroll
+  for (int j = 0; j < 5; j++) { A0[3 * j] = nb[j].x; A0[3 * j + 1] = nb[j].y; A0[3 * j + 2] = nb[j].z; }
+  colpiv_qr_solve_5x3(A0, B0, X0);
+  float pa = X0[0], pb = X0[1], pc = X0[2], pd = 1;
+  float ps = sqrtf(pa * pa + pb * pb + pc * pc);
+  pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+  bool valid = true;
+#pragma unroll
+  for (int j = 0; j < 5; j++)
+    if ((double)fabsf(pa * nb[j].x + pb * nb[j].y + pc * nb[j].z + pd) > 0.2) valid = false;
+  if (!valid) return false;
+  float pd2 = pa * x0 + pb * y0 + pc * z0 + pd;
+  float s = (float)(1.0 - 0.9 * (double)fabsf(pd2) / (double)sqrtf(sqrtf(x0 * x0 + y0 * y0 + z0 * z0)));
+  raw[0] = pa; raw[1] = pb; raw[2] = pc; raw[3] = pd2; raw[4] = s;
+  return (double)s > 0.1;
+}
+
+// LMOptimization tail (:869-973) run by one thread once all tiles of a registration are in.
+__device__ inline void lm_solve_tail(RegState& st, const LmParamsDev& prm, const double* sums, lisreg_lm_iter* log) {
+  const int nC = (int)sums[27], nS = (int)sums[28], nSel = nC + nS;
+  const int iter = st.iter;
+  st.n_sel_last = nSel;
+  if (log) {
+    for (int i = 0; i < 36; i++) log->AtA[i] = 0.f;
+    for (int i = 0; i < 6; i++) { log->AtB[i] = 0.f; log->X[i] = 0.f; log->pose[i] = st.pose[i]; }
+    log->n_sel = nSel; log->n_corner_sel = nC; log->n_surf_sel = nS; log->solved = 0; log->deltaR = 0.f; log->deltaT = 0.f;
+  }
+  bool converged = false;
+  if (nSel < prm.min_sel) {
+    st.any_small = 1;
+  } else {
+    float AtA[36], AtB[6], X[6];
+    int q = 0;
+    for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) { AtA[r * 6 + c] = AtA[c * 6 + r] = (float)sums[q]; q++; }
+    for (int r = 0; r < 6; r++) AtB[r] = (float)sums[21 + r];
+    {
+      float a[36];
+      for (int i = 0; i < 36; i++) a[i] = AtA[i];
+      for (int i = 0; i < 6; i++) X[i] = AtB[i];
+      if (!qr_solve<6>(a, X)) for (int i = 0; i < 6; i++) X[i] = 0.f;
+    }
+    float matP[36];
+    for (int i = 0; i < 36; i++) matP[i] = 0.f;   // Q1: local all-zero matP on iterations >= 1
+    if (iter == 0) {
+      float a[36], E[6], V[36], V2[36];
+      for (int i = 0; i < 36; i++) a[i] = AtA[i];
+      jacobi_eigen<6>(a, E, V);
+      for (int i = 0; i < 36; i++) V2[i] = V[i];
+      st.degenerate = 0;
+      for (int i = 5; i >= 0; i--) {
+        if (E[i] < prm.degenerate_eig) { for (int j = 0; j < 6; j++) V2[i * 6 + j] = 0.f; st.degenerate = 1; }
+        else break;
+      }
+      if (st.degenerate) {   // matP = matV.inv() * matV2 (:945); only consumed when degenerate
+        float Vc[36], Vinv[36];
+        for (int i = 0; i < 36; i++) { Vc[i] = V[i]; Vinv[i] = 0.f; }
+        for (int i = 0; i < 6; i++) Vinv[i * 6 + i] = 1.f;
+        if (!lu_solve<6, 6>(Vc, Vinv)) for (int i = 0; i < 36; i++) Vinv[i] = 0.f;
+        for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) {
+          double s = 0; for (int k = 0; k < 6; k++) s += (double)Vinv[r * 6 + k] * (double)V2[k * 6 + c];
+          matP[r * 6 + c] = (float)s;
+        }
+      }
+    }
+    if (st.degenerate) {
+      float X2[6];
+      for (int i = 0; i < 6; i++) X2[i] = X[i];
+      for (int r = 0; r < 6; r++) { double s = 0; for (int k = 0; k < 6; k++) s += (double)matP[r * 6 + k] * (double)X2[k]; X[r] = (float)s; }
+    }
+    for (int r = 0; r < 6; r++) st.pose[r] += X[r];
+    const float r2d = 57.29578f;
+    double r0 = (double)(X[0] * r2d), r1 = (double)(X[1] * r2d), r2 = (double)(X[2] * r2d);
+    double t0 = (double)(X[3] * 100), t1 = (double)(X[4] * 100), t2 = (double)(X[5] * 100);
+    float dR = (float)sqrt(r0 * r0 + r1 * r1 + r2 * r2);
+    float dT = (float)sqrt(t0 * t0 + t1 * t1 + t2 * t2);
+    st.deltaR = dR; st.deltaT = dT;
+    converged = ((double)dR < (double)prm.conv_rot) && ((double)dT < (double)prm.conv_trans);
+    st.converged = converged ? 1 : 0;
+    if (log) {
+      for (int i = 0; i < 36; i++) log->AtA[i] = AtA[i];
+      for (int i = 0; i < 6; i++) { log->AtB[i] = AtB[i]; log->X[i] = X[i]; log->pose[i] = st.pose[i]; }
+      log->solved = 1; log->deltaR = dR; log->deltaT = dT;
+    }
+  }
+  st.iter = iter + 1;
+  if ((converged && prm.early_exit) || st.iter >= prm.max_iters) {
+    st.done = 1;
+    if (prm.rot_tol > 0.f) {   // transformUpdate clamps (:1001-1003)
+      st.pose[0] = fminf(fmaxf(st.pose[0], -prm.rot_tol), prm.rot_tol);
+      st.pose[1] = fminf(fmaxf(st.pose[1], -prm.rot_tol), prm.rot_tol);
+    }
+    if (prm.z_tol > 0.f) st.pose[5] = fminf(fmaxf(st.pose[5], -prm.z_tol), prm.z_tol);
+    st.status = st.any_small ? LISREG_FEW_CORRESPONDENCES : LISREG_OK;
+  } else {
+    state_refresh(st);
+  }
+}
+
+__global__ void k_lm_init(const RegDesc* __restrict__ descs, RegState* __restrict__ states, const float* __restrict__ pose_in,
+                          LmParamsDev prm, int* __restrict__ tickets, int B) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  RegState s;
+  for (int i = 0; i < 6; i++) s.pose[i] = pose_in[6 * b + i];
+  s.iter = 0; s.done = 0; s.converged = 0; s.degenerate = prm.degenerate_in; s.any_small = 0; s.n_sel_last = 0; s.status = 0;
+  s.deltaR = 100.f; s.deltaT = 100.f;
+  const RegDesc d = descs[b];
+  if (!(d.nc > prm.edge_min && d.ns > prm.surf_min)) { s.done = 1; s.status = LISREG_NOT_ENOUGH_FEATURES; }   // :598
+  state_refresh(s);
+  states[b] = s;
+  tickets[b] = 0;
+}
+
+__global__ void k_lm_finish(const RegState* __restrict__ states, float* __restrict__ pose_out, lisreg_lm_result* __restrict__ res, int B) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const RegState s = states[b];
+  lisreg_lm_result r;
+  r.status = s.status; r.iters = s.iter; r.converged = s.converged; r.is_degenerate = s.degenerate;
+  r.n_sel_last = s.n_sel_last; r.deltaR = s.deltaR; r.deltaT = s.deltaT;
+  for (int i = 0; i < 6; i++) { r.pose[i] = s.pose[i]; pose_out[6 * b + i] = s.pose[i]; }
+  res[b] = r;
+}
+
+__global__ void __launch_bounds__(LM_THREADS)
+k_lm_iter(const RegDesc* __restrict__ descs, RegState* __restrict__ states, const MapDev* __restrict__ maps,
+          LmParamsDev prm, double* __restrict__ partials, int* __restrict__ tickets,
+          lisreg_lm_iter* __restrict__ logs, int max_tiles, int tile_pts) {
+  const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+  __shared__ RegDesc sd;
+  __shared__ float sT[12], sTrig[6];
+  __shared__ int sdone;
+  __shared__ double swarp[LM_THREADS / 32][LM_NSUM];
+  __shared__ double stot[LM_NSUM];
+  __shared__ int slast;
+  if (tid == 0) { sd = descs[b]; sdone = states[b].done; }
+  if (tid < 12) sT[tid] = states[b].T[tid];
+  if (tid >= 32 && tid < 38) sTrig[tid - 32] = states[b].trig[tid - 32];
+  __syncthreads();
+  if (sdone) return;
+  const int n = sd.nc + sd.ns;
+  const int ntiles = (n + tile_pts - 1) / tile_pts;
+  if (tile >= ntiles) return;
+  const MapDev& mp = maps[sd.map_slot];
+
+  double acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; i++) acc[i] = 0.0;
+  int cntC = 0, cntS = 0;
+  const float srx = sTrig[0], crx = sTrig[1], sry = sTrig[2], cry = sTrig[3], srz = sTrig[4], crz = sTrig[5];
+
+  const int qend = min(n, (tile + 1) * tile_pts);
+  for (int q = tile * tile_pts + tid; q < qend; q += LM_THREADS) {
+    const bool is_corner = q < sd.nc;
+    const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
+    // pointAssociateToMap (:243-258)
+    const float x0 = sT[0] * p.x + sT[1] * p.y + sT[2] * p.z + sT[3];
+    const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
+    const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
+    float bd[5]; int bi[5], bp[5];
+    const GridDev& g = is_corner ? mp.corner : mp.surf;
+    knn5_grid(g, x0, y0, z0, prm.gate, bd, bi, bp);
+    if (!(bd[4] < prm.gate) || bp[4] < 0) continue;
+    float4 nb[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) nb[j] = __ldg(&g.pts[bp[j]]);
+    float raw[5];
+    const bool ok = is_corner ? corner_coeff(x0, y0, z0, nb, raw) : surf_coeff(x0, y0, z0, nb, raw);
+    if (!ok) continue;
+    float w = 1.0f;
+    if (prm.use_w) {   // subMapOptmizationNode.cpp:1669, :1793
+      const uint16_t* lab = is_corner ? sd.clabel : sd.slabel;
+      unsigned l = lab ? lab[is_corner ? q : q - sd.nc] : 0u;
+      float sc = l < LISREG_LUT_SIZE ? prm.label_score[l] : 0.f;
+      w = (float)(2.0 - (double)sc);
+    }
+    const float ws = w * raw[4];
+    const float c_x = ws * raw[0], c_y = ws * raw[1], c_z = ws * raw[2], c_i = ws * raw[3];
+    if (is_corner) cntC++; else cntS++;
+    // LMOptimization row (:888-915): lidar -> camera permutation
+    const float px = p.y, py = p.z, pz = p.x;
+    const float cx = c_y, cy = c_z, cz = c_x;
+    const float arx = (crx * sry * srz * px + crx * crz * sry * py - srx * sry * pz) * cx +
+                      (-srx * srz * px - crz * srx * py - crx * pz) * cy +
+                      (crx * cry * srz * px + crx * cry * crz * py - cry * srx * pz) * cz;
+    const float ary = ((cry * srx * srz - crz * sry) * px + (sry * srz + cry * crz * srx) * py + crx * cry * pz) * cx +
+                      ((-cry * crz - srx * sry * srz) * px + (cry * srz - crz * srx * sry) * py - crx * sry * pz) * cz;
+    const float arz = ((crz * srx * sry - cry * srz) * px + (-cry * crz - srx * sry * srz) * py) * cx +
+                      (crx * crz * px - crx * srz * py) * cy +
+                      ((sry * srz + cry * crz * srx) * px + (crz * sry - cry * srx * srz) * py) * cz;
+    const double row[6] = {(double)arz, (double)arx, (double)ary, (double)cz, (double)cx, (double)cy};
+    const double bb = -(double)c_i;
+    int k = 0;
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = r; c < 6; c++) { acc[k] += row[r] * row[c]; k++; }
+#pragma unroll
+    for (int r = 0; r < 6; r++) acc[21 + r] += row[r] * bb;
+  }
+
+  // warp reduce -> smem -> per-block partial (fixed order => deterministic)
+  const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+  for (int i = 0; i < 27; i++) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) swarp[wid][i] = v;
+  }
+  {
+    int c = cntC, s2 = cntS;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { c += __shfl_down_sync(0xffffffffu, c, o); s2 += __shfl_down_sync(0xffffffffu, s2, o); }
+    if (lane == 0) { swarp[wid][27] = (double)c; swarp[wid][28] = (double)s2; }
+  }
+  __syncthreads();
+  double* mypart = partials + ((size_t)b * max_tiles + tile) * LM_NSUM;
+  if (tid < 29) {
+    double v = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < LM_THREADS / 32; w2++) v += swarp[w2][tid];
+    mypart[tid] = v;
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int t = atomicAdd(&tickets[b], 1);
+    slast = (t == ntiles - 1);
+  }
+  __syncthreads();
+  if (!slast) return;
+  __threadfence();
+  if (tid < 29) {
+    double v = 0.0;
+    const double* base = partials + (size_t)b * max_tiles * LM_NSUM + tid;
+    for (int t = 0; t < ntiles; t++) v += __ldcg(base + (size_t)t * LM_NSUM);
+    stot[tid] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    RegState st = states[b];
+    lisreg_lm_iter* lg = logs ? &logs[(size_t)b * LISREG_MAX_ITERS + st.iter] : nullptr;
+    lm_solve_tail(st, prm, stot, lg);
+    states[b] = st;
+    tickets[b] = 0;
+  }
+}
+
+// stand-alone exact 5-NN (tests / lisreg_knn5)
+__global__ void k_knn5(GridDev g, const float4* __restrict__ q, int nq, float gate, int* __restrict__ idx, float* __restrict__ sqd) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  float4 p = q[i];
+  float bd[5]; int bi[5], bp[5];
+  knn5_grid(g, p.x, p.y, p.z, gate, bd, bi, bp);
+  for (int j = 0; j < 5; j++) {
+    bool ok = bp[j] >= 0 && bd[j] < gate;
+    idx[5 * i + j] = ok ? bi[j] : -1;
+    sqd[5 * i + j] = ok ? bd[j] : FLT_MAX;
+  }
+}
+
+}  // namespace lisreg

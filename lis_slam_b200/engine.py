@@ -1,0 +1,220 @@
+"""ctypes binding of liblisreg.so (include/lisreg.h) used by tests/ and bench.py.
+
+This is plumbing only: every compute call goes through the C-ABI into the hand-written
+sm_100a kernels.  There is no CPU fallback — if the shared library is missing or no CUDA
+device is present the calls raise.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblisreg.so")
+LUT_SIZE = 64
+MAX_ITERS = 32
+
+OK, NOT_ENOUGH_FEATURES, FEW_CORRESPONDENCES = 0, 1, 2
+
+
+class LisregError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("stream", C.c_void_p), ("max_grid_cells", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
+class LmParams(C.Structure):
+    _fields_ = [
+        ("max_iters", C.c_int32), ("early_exit", C.c_int32), ("sqdist_gate", C.c_float),
+        ("conv_rot_deg", C.c_float), ("conv_trans_cm", C.c_float),
+        ("edge_min_valid", C.c_int32), ("surf_min_valid", C.c_int32), ("min_sel", C.c_int32),
+        ("degenerate_eig", C.c_float), ("use_label_weight", C.c_int32),
+        ("label_score", C.c_float * LUT_SIZE), ("degenerate_in", C.c_int32),
+        ("rot_tolerance", C.c_float), ("z_tolerance", C.c_float), ("want_iter_log", C.c_int32),
+    ]
+
+
+class LmIter(C.Structure):
+    _fields_ = [
+        ("AtA", C.c_float * 36), ("AtB", C.c_float * 6), ("X", C.c_float * 6), ("pose", C.c_float * 6),
+        ("n_sel", C.c_int32), ("n_corner_sel", C.c_int32), ("n_surf_sel", C.c_int32), ("solved", C.c_int32),
+        ("deltaR", C.c_float), ("deltaT", C.c_float),
+    ]
+
+
+class LmResult(C.Structure):
+    _fields_ = [
+        ("status", C.c_int32), ("iters", C.c_int32), ("converged", C.c_int32), ("is_degenerate", C.c_int32),
+        ("n_sel_last", C.c_int32), ("deltaR", C.c_float), ("deltaT", C.c_float), ("pose", C.c_float * 6),
+    ]
+
+
+class BatchItem(C.Structure):
+    _fields_ = [
+        ("corner", C.c_void_p), ("clabel", C.c_void_p), ("surf", C.c_void_p), ("slabel", C.c_void_p),
+        ("nc", C.c_int32), ("ns", C.c_int32), ("map_id", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+def build(force=False):
+    """Compile liblisreg.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    src_dir = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "lisreg.h"))
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
+        subprocess.check_call(["make", "-C", src_dir, "-s"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise LisregError("liblisreg.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                              "there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, fp = C.c_void_p, C.c_int32, C.POINTER(C.c_float)
+        L.lisreg_create.restype = i32
+        L.lisreg_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+        L.lisreg_destroy.argtypes = [vp]
+        L.lisreg_last_error.restype = C.c_char_p
+        L.lisreg_last_error.argtypes = [vp]
+        L.lisreg_version.restype = C.c_char_p
+        L.lisreg_sync.restype = i32
+        L.lisreg_sync.argtypes = [vp]
+        L.lisreg_launch_count.restype = C.c_int64
+        L.lisreg_launch_count.argtypes = [vp]
+        L.lisreg_lm_params_preset.argtypes = [C.POINTER(LmParams), C.c_char]
+        L.lisreg_map_create.restype = i32
+        L.lisreg_map_create.argtypes = [vp, vp, i32, vp, i32, C.c_float, C.POINTER(i32)]
+        L.lisreg_map_create_dev.restype = i32
+        L.lisreg_map_create_dev.argtypes = [vp, vp, i32, vp, i32, C.c_float, C.POINTER(i32)]
+        L.lisreg_map_destroy.restype = i32
+        L.lisreg_map_destroy.argtypes = [vp, i32]
+        L.lisreg_knn5.restype = i32
+        L.lisreg_knn5.argtypes = [vp, i32, i32, vp, i32, C.c_float, vp, vp]
+        L.lisreg_scan2map.restype = i32
+        L.lisreg_scan2map.argtypes = [vp, i32, vp, vp, i32, vp, vp, i32, fp, C.POINTER(LmParams), C.POINTER(LmResult), C.POINTER(LmIter)]
+        L.lisreg_scan2map_batch.restype = i32
+        L.lisreg_scan2map_batch.argtypes = [vp, i32, C.POINTER(BatchItem), fp, C.POINTER(LmParams), C.POINTER(LmResult), C.POINTER(LmIter)]
+        L.lisreg_scan2map_batch_dev.restype = i32
+        L.lisreg_scan2map_batch_dev.argtypes = [vp, i32, C.POINTER(BatchItem), vp, C.POINTER(LmParams), vp]
+        _LIB = L
+    return _LIB
+
+
+def lm_params(variant="A", **kw):
+    p = LmParams()
+    lib().lisreg_lm_params_preset(C.byref(p), variant.encode())
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _f4(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] == 4, "point clouds are (N,4) float32 {x,y,z,intensity}"
+    return a
+
+
+def _u16(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.uint16)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Engine:
+    """One lisreg context (one GPU, one stream)."""
+
+    def __init__(self, device=0, stream=None, max_grid_cells=0):
+        self._h = C.c_void_p()
+        cfg = Config(device=device, stream=stream, max_grid_cells=max_grid_cells)
+        rc = lib().lisreg_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise LisregError("lisreg_create failed (%d): no CUDA device / driver — this engine has no CPU path" % rc)
+
+    def close(self):
+        if self._h:
+            lib().lisreg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise LisregError("lisreg error %d: %s" % (rc, lib().lisreg_last_error(self._h).decode()))
+        return rc
+
+    def sync(self):
+        self._ck(lib().lisreg_sync(self._h))
+
+    @property
+    def launches(self):
+        return int(lib().lisreg_launch_count(self._h))
+
+    # ---- maps
+    def map_create(self, corner, surf, gate_hint=1.0):
+        c, s = _f4(corner), _f4(surf)
+        mid = C.c_int32(-1)
+        self._ck(lib().lisreg_map_create(self._h, _ptr(c), len(c), _ptr(s), len(s), gate_hint, C.byref(mid)))
+        return mid.value
+
+    def map_create_dev(self, d_corner_ptr, mc, d_surf_ptr, ms, gate_hint=1.0):
+        mid = C.c_int32(-1)
+        self._ck(lib().lisreg_map_create_dev(self._h, d_corner_ptr, mc, d_surf_ptr, ms, gate_hint, C.byref(mid)))
+        return mid.value
+
+    def map_destroy(self, map_id):
+        self._ck(lib().lisreg_map_destroy(self._h, map_id))
+
+    def knn5(self, map_id, which, queries, gate):
+        q = _f4(queries)
+        idx = np.empty((len(q), 5), np.int32); sqd = np.empty((len(q), 5), np.float32)
+        self._ck(lib().lisreg_knn5(self._h, map_id, which, _ptr(q), len(q), gate, _ptr(idx), _ptr(sqd)))
+        return idx, sqd
+
+    # ---- registration
+    def scan2map(self, map_id, corner, surf, pose6, params, clabel=None, slabel=None, log=False):
+        poses, res, logs = self.scan2map_batch([(map_id, corner, surf, clabel, slabel)], [pose6], params, log=log)
+        return poses[0], res[0], (logs[0] if log else [])
+
+    def scan2map_batch(self, regs, poses, params, log=False):
+        """regs: list of (map_id, corner, surf, clabel|None, slabel|None). Host buffers; H2D, solve
+        and D2H happen inside the call (this is the e2e path)."""
+        B = len(regs)
+        items = (BatchItem * B)()
+        keep = []
+        for b, (mid, c, s, cl, sl) in enumerate(regs):
+            c, s, cl, sl = _f4(c), _f4(s), _u16(cl), _u16(sl)
+            keep.append((c, s, cl, sl))
+            items[b] = BatchItem(_ptr(c), _ptr(cl), _ptr(s), _ptr(sl), len(c), len(s), mid, 0)
+        pose = np.ascontiguousarray(np.asarray(poses, dtype=np.float32).reshape(B, 6)).copy()
+        res = (LmResult * B)()
+        logs = None
+        params.want_iter_log = 1 if log else 0
+        if log:
+            logs = (LmIter * (B * params.max_iters))()
+        rc = self._ck(lib().lisreg_scan2map_batch(self._h, B, items, pose.ctypes.data_as(C.POINTER(C.c_float)),
+                                                  C.byref(params), res, logs))
+        out_logs = None
+        if log:
+            out_logs = [[logs[b * params.max_iters + i] for i in range(res[b].iters)] for b in range(B)]
+        self.last_status = rc
+        return pose, list(res), out_logs
+
+    def scan2map_batch_dev(self, items, B, d_pose_ptr, params, d_res_ptr):
+        """All buffers resident in HBM (items = ctypes array of BatchItem holding DEVICE pointers).
+        Asynchronous on the context stream."""
+        return self._ck(lib().lisreg_scan2map_batch_dev(self._h, B, items, d_pose_ptr, C.byref(params), d_res_ptr))

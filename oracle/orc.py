@@ -1,0 +1,188 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  ctypes binding of oracle/liblisreg_oracle.so.
+
+Imported only by tests/, __graft_entry__.smoke() and bench.py (cpu_baseline and
+--impl reference).  The product package lis_slam_b200 never imports this module.
+PARITY UNPINNED by the reference (no tests/golden vectors upstream); see DESIGN.md.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+LUT_SIZE = 64
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liblisreg_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.startswith("orc_") and f.endswith((".cpp", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL)
+    return so
+
+
+class LmParams(C.Structure):
+    _fields_ = [
+        ("max_iters", C.c_int32), ("early_exit", C.c_int32), ("sqdist_gate", C.c_float),
+        ("conv_rot_deg", C.c_float), ("conv_trans_cm", C.c_float),
+        ("edge_min_valid", C.c_int32), ("surf_min_valid", C.c_int32), ("min_sel", C.c_int32),
+        ("degenerate_eig", C.c_float), ("use_label_weight", C.c_int32),
+        ("label_score", C.c_float * LUT_SIZE), ("degenerate_in", C.c_int32),
+        ("rot_tolerance", C.c_float), ("z_tolerance", C.c_float), ("n_threads", C.c_int32),
+    ]
+
+
+class LmIter(C.Structure):
+    _fields_ = [
+        ("AtA", C.c_float * 36), ("AtB", C.c_float * 6), ("X", C.c_float * 6), ("pose", C.c_float * 6),
+        ("n_sel", C.c_int32), ("n_corner_sel", C.c_int32), ("n_surf_sel", C.c_int32), ("solved", C.c_int32),
+        ("deltaR", C.c_float), ("deltaT", C.c_float),
+    ]
+
+
+class LmResult(C.Structure):
+    _fields_ = [
+        ("status", C.c_int32), ("iters", C.c_int32), ("converged", C.c_int32), ("is_degenerate", C.c_int32),
+        ("n_sel_last", C.c_int32), ("deltaR", C.c_float), ("deltaT", C.c_float),
+        ("ms_build", C.c_double), ("ms_iters", C.c_double),
+    ]
+
+
+# label_sorce of config/label.yaml:214-234 (reference values)
+LABEL_SCORE = [1.0, 1.0, 0.6, 0.5, 0.8, 0.5, 0.5, 0.5, 0.5, 1.2, 1.2, 1.2, 0.5, 1.0, 0.8, 0.5, 1.3, 0.5, 1.5, 1.5]
+
+
+def lm_params(variant="A", **kw):
+    """Parameter presets of the three copies of the loop."""
+    p = LmParams()
+    p.early_exit = 1
+    p.edge_min_valid, p.surf_min_valid, p.min_sel = -1, 100, 50
+    p.degenerate_eig = 100.0
+    p.rot_tolerance = p.z_tolerance = 1000.0
+    p.n_threads = 1
+    for i, v in enumerate(LABEL_SCORE):
+        p.label_score[i] = v
+    if variant == "A":
+        p.max_iters, p.sqdist_gate, p.conv_rot_deg, p.conv_trans_cm, p.use_label_weight = 15, 1.0, 0.005, 0.05, 0
+    elif variant == "B":
+        p.max_iters, p.sqdist_gate, p.conv_rot_deg, p.conv_trans_cm, p.use_label_weight = 20, 2.0, 0.003, 0.03, 1
+    elif variant == "C":
+        p.max_iters, p.sqdist_gate, p.conv_rot_deg, p.conv_trans_cm, p.use_label_weight = 30, 2.0, 0.002, 0.02, 1
+    else:
+        raise ValueError(variant)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        fp, ip, u16p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint16)
+        L.orc_scan2map.restype = C.c_int
+        L.orc_scan2map.argtypes = [fp, u16p, C.c_int32, fp, u16p, C.c_int32, fp, C.c_int32, fp, C.c_int32,
+                                   fp, C.POINTER(LmParams), C.POINTER(LmResult), C.POINTER(LmIter)]
+        L.orc_kdtree_build.restype = C.c_void_p
+        L.orc_kdtree_build.argtypes = [fp, C.c_int32]
+        L.orc_kdtree_free.argtypes = [C.c_void_p]
+        L.orc_knn_batch.argtypes = [C.c_void_p, fp, C.c_int32, C.c_int32, ip, fp, C.c_int32]
+        L.orc_corner_coeff.restype = C.c_int
+        L.orc_corner_coeff.argtypes = [fp, fp, fp]
+        L.orc_surf_coeff.restype = C.c_int
+        L.orc_surf_coeff.argtypes = [fp, fp, fp]
+        L.orc_pose_to_affine.argtypes = [fp, fp]
+        L.orc_jacobi_eigen_f32.argtypes = [fp, C.c_int32, fp, fp]
+        L.orc_qr_solve_f32.restype = C.c_int
+        L.orc_qr_solve_f32.argtypes = [fp, C.c_int32, fp, fp]
+        L.orc_lu_inv_f32.restype = C.c_int
+        L.orc_lu_inv_f32.argtypes = [fp, C.c_int32, fp]
+        L.orc_plane_fit_5x3.argtypes = [fp, fp]
+        _LIB = L
+    return _LIB
+
+
+def _f(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _u16(a):
+    if a is None:
+        return None, None
+    a = np.ascontiguousarray(a, dtype=np.uint16)
+    return a, a.ctypes.data_as(C.POINTER(C.c_uint16))
+
+
+def scan2map(corner, surf, map_corner, map_surf, pose6, params, clabel=None, slabel=None, log=True):
+    """Returns (pose6_out, LmResult, [LmIter...])."""
+    L = lib()
+    c, cp = _f(corner); s, sp = _f(surf); mc, mcp = _f(map_corner); ms, msp = _f(map_surf)
+    cl, clp = _u16(clabel); sl, slp = _u16(slabel)
+    pose = np.array(pose6, dtype=np.float32).copy()
+    res = LmResult()
+    logs = (LmIter * params.max_iters)() if log else None
+    L.orc_scan2map(cp, clp, len(c), sp, slp, len(s), mcp, len(mc), msp, len(ms),
+                   pose.ctypes.data_as(C.POINTER(C.c_float)), C.byref(params), C.byref(res), logs)
+    return pose, res, (list(logs)[: res.iters] if log else [])
+
+
+def knn(map_pts4, queries4, k=5, n_threads=1):
+    L = lib()
+    m, mp = _f(map_pts4); q, qp = _f(queries4)
+    t = L.orc_kdtree_build(mp, len(m))
+    idx = np.empty((len(q), k), np.int32); sqd = np.empty((len(q), k), np.float32)
+    L.orc_knn_batch(t, qp, len(q), k, idx.ctypes.data_as(C.POINTER(C.c_int32)), sqd.ctypes.data_as(C.POINTER(C.c_float)), n_threads)
+    L.orc_kdtree_free(t)
+    return idx, sqd
+
+
+def jacobi_eigen(A):
+    A, ap = _f(A); n = A.shape[0]
+    W = np.empty(n, np.float32); V = np.empty((n, n), np.float32)
+    lib().orc_jacobi_eigen_f32(ap, n, W.ctypes.data_as(C.POINTER(C.c_float)), V.ctypes.data_as(C.POINTER(C.c_float)))
+    return W, V
+
+
+def qr_solve(A, b):
+    A, ap = _f(A); b, bp = _f(b); n = A.shape[0]
+    x = np.empty(n, np.float32)
+    ok = lib().orc_qr_solve_f32(ap, n, bp, x.ctypes.data_as(C.POINTER(C.c_float)))
+    return ok, x
+
+
+def lu_inv(A):
+    A, ap = _f(A); n = A.shape[0]
+    out = np.empty((n, n), np.float32)
+    ok = lib().orc_lu_inv_f32(ap, n, out.ctypes.data_as(C.POINTER(C.c_float)))
+    return ok, out
+
+
+def plane_fit(A53):
+    A, ap = _f(A53)
+    x = np.empty(3, np.float32)
+    lib().orc_plane_fit_5x3(ap, x.ctypes.data_as(C.POINTER(C.c_float)))
+    return x
+
+
+def corner_coeff(q, nb):
+    q, qp = _f(q); nb, nbp = _f(nb)
+    c = np.zeros(4, np.float32)
+    ok = lib().orc_corner_coeff(qp, nbp, c.ctypes.data_as(C.POINTER(C.c_float)))
+    return ok, c
+
+
+def surf_coeff(q, nb):
+    q, qp = _f(q); nb, nbp = _f(nb)
+    c = np.zeros(4, np.float32)
+    ok = lib().orc_surf_coeff(qp, nbp, c.ctypes.data_as(C.POINTER(C.c_float)))
+    return ok, c
+
+
+def pose_to_affine(pose6):
+    p, pp = _f(pose6)
+    T = np.empty(12, np.float32)
+    lib().orc_pose_to_affine(pp, T.ctypes.data_as(C.POINTER(C.c_float)))
+    return T.reshape(3, 4)

@@ -1,0 +1,78 @@
+/* ORACLE — TEST INFRASTRUCTURE ONLY (see orc_linalg.h header). PARITY UNPINNED.
+ * Plain-C interface of the CPU restatement of the LIS-SLAM hot path, loaded with
+ * ctypes by tests/, __graft_entry__.smoke() and bench.py (cpu_baseline /
+ * --impl reference).  Point clouds are packed float4 {x,y,z,intensity}. */
+#ifndef ORC_API_H
+#define ORC_API_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_LUT_SIZE 64
+
+typedef struct orc_lm_params {
+  int32_t max_iters;        /* 15 (A, odomEstimationNode.cpp:606) / 20 (B) / 30 (C) */
+  int32_t early_exit;       /* 1 = reference behaviour; 0 = always run max_iters   */
+  float sqdist_gate;        /* 1.0 (A :657,:776) / 2.0 (B/C subMapOptmizationNode.cpp:1610) */
+  float conv_rot_deg;       /* 0.005 / 0.003 / 0.002 */
+  float conv_trans_cm;      /* 0.05  / 0.03  / 0.02  */
+  int32_t edge_min_valid;   /* edgeFeatureMinValidNum  (-1)  */
+  int32_t surf_min_valid;   /* surfFeatureMinValidNum  (100) */
+  int32_t min_sel;          /* 50, odomEstimationNode.cpp:870 */
+  float degenerate_eig;     /* 100, :932 */
+  int32_t use_label_weight; /* variants B/C: w = 2.0 - LabelSorce[label] */
+  float label_score[ORC_LUT_SIZE];
+  int32_t degenerate_in;    /* persistent isDegenerate member carried in (Q1) */
+  float rot_tolerance;      /* transformUpdate clamps (:1001-1003); <=0 disables */
+  float z_tolerance;
+  int32_t n_threads;        /* 1 = as-built reference (OpenMP inert) */
+} orc_lm_params;
+
+typedef struct orc_lm_iter {
+  float AtA[36];
+  float AtB[6];
+  float X[6];
+  float pose[6];            /* after the update */
+  int32_t n_sel, n_corner_sel, n_surf_sel, solved;
+  float deltaR, deltaT;
+} orc_lm_iter;
+
+typedef struct orc_lm_result {
+  int32_t status;           /* 0 ok, 1 not enough features (pose untouched), 2 some iter had <min_sel */
+  int32_t iters;            /* LMOptimization calls made */
+  int32_t converged;
+  int32_t is_degenerate;
+  int32_t n_sel_last;
+  float deltaR, deltaT;
+  double ms_build, ms_iters;
+} orc_lm_result;
+
+int orc_scan2map(const float* corner, const uint16_t* clabel, int32_t nc,
+                 const float* surf, const uint16_t* slabel, int32_t ns,
+                 const float* map_corner, int32_t mc, const float* map_surf, int32_t ms,
+                 float pose6[6], const orc_lm_params* prm, orc_lm_result* res,
+                 orc_lm_iter* iter_log /* nullable, max_iters entries */);
+
+/* exact k-NN (FLANN KDTreeSingleIndex semantics: L2, sorted ascending) */
+void* orc_kdtree_build(const float* pts4, int32_t n);
+void orc_kdtree_free(void* t);
+int32_t orc_kdtree_knn(const void* t, const float* q3, int32_t k, int32_t* idx, float* sqd);
+void orc_knn_batch(const void* t, const float* q4, int32_t nq, int32_t k, int32_t* idx, float* sqd,
+                   int32_t n_threads);
+
+/* per-point coefficient functions exposed for unit tests */
+int orc_corner_coeff(const float q[3], const float nb[15], float coeff[4]);
+int orc_surf_coeff(const float q[3], const float nb[15], float coeff[4]);
+void orc_pose_to_affine(const float pose6[6], float T12[12]);
+
+/* small dense routines exposed so tests can pin them against cv2 */
+void orc_jacobi_eigen_f32(const float* A, int32_t n, float* W, float* V);
+int orc_qr_solve_f32(const float* A, int32_t n, const float* b, float* x);
+int orc_lu_inv_f32(const float* A, int32_t n, float* Ainv);
+void orc_plane_fit_5x3(const float* A15, float* x3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,184 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on the same
+seeded inputs.  Tolerances: kNN bit-exact; per-iteration selection counts equal (<= 0.1 % slack,
+SURVEY.md §8c); final pose <= 1e-4 rad / 1e-3 m (BASELINE.json north_star) — in practice ~1e-6."""
+import numpy as np
+import pytest
+
+from lis_slam_b200 import engine as E
+from lis_slam_b200 import synth
+from oracle import orc
+
+from common import local_map, reg_case, scene
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL, TRANS_TOL = 1e-4, 1e-3
+
+
+def _orc_params(variant, **kw):
+    return orc.lm_params(variant, **kw)
+
+
+def _check_against_oracle(engine, mid, f, guess, variant, m, early_exit=1, max_iters=None, labels=False):
+    kw = {"early_exit": early_exit}
+    if max_iters:
+        kw["max_iters"] = max_iters
+    po = _orc_params(variant, **kw)
+    pg = E.lm_params(variant, **kw)
+    cl = f["corner_label"] if labels else None
+    sl = f["surf_label"] if labels else None
+    pose_o, res_o, log_o = orc.scan2map(f["corner"], f["surf"], m["corner"], m["surf"], guess, po, clabel=cl, slabel=sl)
+    pose_g, res_g, log_g = engine.scan2map(mid, f["corner"], f["surf"], guess, pg, clabel=cl, slabel=sl, log=True)
+    assert res_g.status == res_o.status
+    assert res_g.iters == res_o.iters, (res_g.iters, res_o.iters)
+    assert res_g.converged == res_o.converged
+    assert res_g.is_degenerate == res_o.is_degenerate
+    for lo, lg in zip(log_o, log_g):
+        assert abs(lo.n_sel - lg.n_sel) <= max(1, int(0.001 * lo.n_sel)), (lo.n_sel, lg.n_sel)
+        A_o, A_g = np.array(lo.AtA), np.array(lg.AtA)
+        assert np.abs(A_o - A_g).max() <= 2e-4 * np.abs(A_o).max()
+        assert np.abs(np.array(lo.pose) - np.array(lg.pose))[:3].max() <= ROT_TOL
+        assert np.abs(np.array(lo.pose) - np.array(lg.pose))[3:].max() <= TRANS_TOL
+    er, et = synth.pose_error(pose_o, pose_g)
+    assert er <= ROT_TOL and et <= TRANS_TOL, (er, et)
+    return pose_o, pose_g, res_o, res_g, log_o, log_g
+
+
+@pytest.fixture(scope="module")
+def gpu_map(engine):
+    m = local_map()
+    mid = engine.map_create(m["corner"], m["surf"], gate_hint=2.0)
+    yield mid, m
+    engine.map_destroy(mid)
+
+
+@pytest.fixture(scope="module")
+def gpu_map_a(engine):
+    m = local_map()
+    mid = engine.map_create(m["corner"], m["surf"], gate_hint=1.0)
+    yield mid, m
+    engine.map_destroy(mid)
+
+
+@pytest.mark.parametrize("which", [0, 1])
+@pytest.mark.parametrize("gate", [1.0, 2.0])
+def test_knn5_bit_exact(engine, gpu_map, which, gate):
+    mid, m = gpu_map
+    cloud = m["corner"] if which == 0 else m["surf"]
+    f, truth, _ = reg_case(0)
+    T = synth.pose_to_T(truth)
+    src = f["corner"] if which == 0 else f["surf"]
+    q = np.zeros((len(src), 4), np.float32)
+    q[:, :3] = (src[:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+    # add far-away and boundary queries
+    q[:50, :3] += 500.0
+    q[50:100, 2] += 3.0
+    idx_o, sqd_o = orc.knn(cloud, q, 5)
+    idx_g, sqd_g = engine.knn5(mid, which, q, gate)
+    inside = sqd_o < gate
+    assert np.array_equal(np.where(inside, idx_o, -1), idx_g)
+    assert np.array_equal(sqd_o[inside], sqd_g[inside])
+    assert inside[:, 4].sum() > 0.5 * len(q)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_variant_a_matches_oracle(engine, gpu_map_a, seed):
+    mid, m = gpu_map_a
+    f, truth, guess = reg_case(seed)
+    pose_o, pose_g, res_o, res_g, *_ = _check_against_oracle(engine, mid, f, guess, "A", m)
+    # and both recover the ground truth to the noise floor
+    er, et = synth.pose_error(truth, pose_g)
+    assert er < 2e-3 and et < 2e-2
+
+
+def test_variant_a_fixed_10_iterations(engine, gpu_map_a):
+    mid, m = gpu_map_a
+    f, truth, guess = reg_case(3)
+    _, _, res_o, res_g, *_ = _check_against_oracle(engine, mid, f, guess, "A", m, early_exit=0, max_iters=10)
+    assert res_g.iters == 10
+
+
+@pytest.mark.parametrize("variant", ["B", "C"])
+def test_variants_b_c_label_weighted(engine, gpu_map, variant):
+    mid, m = gpu_map
+    f, truth, guess = reg_case(4)
+    _check_against_oracle(engine, mid, f, guess, variant, m, labels=True)
+
+
+def test_batch_matches_single_and_oracle(engine, gpu_map_a):
+    mid, m = gpu_map_a
+    cases = [reg_case(s, n_corner=1500 + 200 * s, n_surf=5000 + 300 * s) for s in range(40)]
+    regs = [(mid, f["corner"], f["surf"], None, None) for f, _, _ in cases]
+    guesses = [g for _, _, g in cases]
+    p = E.lm_params("A")
+    poses, res, _ = engine.scan2map_batch(regs, guesses, p)
+    for s in (0, 7, 39):
+        f, truth, guess = cases[s]
+        pose_o, res_o, _ = orc.scan2map(f["corner"], f["surf"], m["corner"], m["surf"], guess, orc.lm_params("A"), log=False)
+        er, et = synth.pose_error(pose_o, poses[s])
+        assert er <= ROT_TOL and et <= TRANS_TOL
+        assert res[s].iters == res_o.iters
+        p1, r1, _ = engine.scan2map(mid, f["corner"], f["surf"], guess, E.lm_params("A"))
+        assert np.array_equal(p1, poses[s])   # deterministic reduction: batch == single, bit for bit
+
+
+def test_not_enough_features_leaves_pose_untouched(engine, gpu_map_a):
+    mid, m = gpu_map_a
+    f, truth, guess = reg_case(5)
+    p = E.lm_params("A")
+    pose, res, _ = engine.scan2map(mid, f["corner"], f["surf"][:100], guess, p)   # ns > 100 fails
+    assert res.status == E.NOT_ENOUGH_FEATURES and res.iters == 0
+    assert np.array_equal(pose, np.asarray(guess, np.float32))
+    po, ro, _ = orc.scan2map(f["corner"], f["surf"][:100], m["corner"], m["surf"], guess, orc.lm_params("A"))
+    assert ro.status == 1
+
+
+def test_few_correspondences_is_noop(engine, gpu_map_a):
+    """< 50 matches => every iteration is a silent no-op (odomEstimationNode.cpp:870-872)."""
+    mid, m = gpu_map_a
+    f, truth, guess = reg_case(6)
+    far = np.array(guess, np.float32); far[3] += 500.0
+    p = E.lm_params("A")
+    pose, res, _ = engine.scan2map(mid, f["corner"], f["surf"], far, p)
+    po, ro, _ = orc.scan2map(f["corner"], f["surf"], m["corner"], m["surf"], far, orc.lm_params("A"))
+    assert res.status == E.FEW_CORRESPONDENCES == ro.status
+    assert res.iters == ro.iters == 15
+    assert np.array_equal(pose, far) and np.array_equal(po, far)
+
+
+def test_empty_and_tiny_maps(engine):
+    f, truth, guess = reg_case(7)
+    tiny = np.zeros((3, 4), np.float32)
+    mid = engine.map_create(tiny, tiny, gate_hint=1.0)   # Q6: < 5 map points => no correspondences
+    pose, res, _ = engine.scan2map(mid, f["corner"], f["surf"], guess, E.lm_params("A"))
+    assert res.status == E.FEW_CORRESPONDENCES
+    assert np.array_equal(pose, np.asarray(guess, np.float32))
+    engine.map_destroy(mid)
+    mid = engine.map_create(np.zeros((0, 4), np.float32), np.zeros((0, 4), np.float32))
+    pose, res, _ = engine.scan2map(mid, f["corner"], f["surf"], guess, E.lm_params("A"))
+    assert res.status == E.FEW_CORRESPONDENCES
+    engine.map_destroy(mid)
+
+
+def test_degenerate_corridor_quirk_q1(engine):
+    """A featureless ground plane leaves x, y, yaw unconstrained: isDegenerate at iteration 0, then the
+    zeroed local matP makes X = 0 and the loop reports convergence at iteration 1 (quirk Q1)."""
+    rng = np.random.default_rng(5)
+    g = np.arange(-30, 30, 0.4, dtype=np.float32)
+    gx, gy = np.meshgrid(g, g, indexing="ij")
+    ms = np.zeros((gx.size, 4), np.float32); ms[:, 0] = gx.ravel(); ms[:, 1] = gy.ravel(); ms[:, 2] = -1.73
+    ms[:, :3] += rng.normal(0, 0.005, (len(ms), 3)).astype(np.float32)
+    mc = ms[:10].copy()
+    surf = np.zeros((3000, 4), np.float32)
+    surf[:, :2] = rng.uniform(-20, 20, (3000, 2)); surf[:, 2] = -1.73 + rng.normal(0, 0.01, 3000)
+    corner = surf[:20].copy()
+    guess = np.array([0.003, -0.002, 0.01, 0.1, -0.1, 0.05], np.float32)
+    mid = engine.map_create(mc, ms, gate_hint=1.0)
+    pose_g, res_g, log_g = engine.scan2map(mid, corner, surf, guess, E.lm_params("A"), log=True)
+    pose_o, res_o, log_o = orc.scan2map(corner, surf, mc, ms, guess, orc.lm_params("A"))
+    engine.map_destroy(mid)
+    assert res_o.is_degenerate == 1 and res_g.is_degenerate == 1
+    assert res_o.iters == res_g.iters == 2 and res_g.converged == 1
+    assert np.array(log_g[1].X).tolist() == [0.0] * 6
+    er, et = synth.pose_error(pose_o, pose_g)
+    assert er <= ROT_TOL and et <= TRANS_TOL
