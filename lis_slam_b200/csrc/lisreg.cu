@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <string>
 #include <vector>
@@ -257,6 +258,7 @@ int32_t lisreg_create(const lisreg_config* cfg, lisreg_ctx** out) {
   if (cfg && cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
   else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LISREG_ERR_CUDA; } ctx->own_stream = true; }
   if (cfg && cfg->max_grid_cells > 0) ctx->max_cells = cfg->max_grid_cells;
+  if (const char* e2 = getenv("LISREG_STACK")) cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atoi(e2));
   *out = ctx;
   return LISREG_OK;
 }

@@ -46,11 +46,11 @@ struct LmParamsDev {
 constexpr int LM_THREADS = 128;
 constexpr int LM_NSUM = 32;   // 21 AtA (upper) + 6 AtB + nCorner + nSurf + pad
 
-__device__ __forceinline__ float sinf_cr(float x) { return (float)sin((double)x); }
-__device__ __forceinline__ float cosf_cr(float x) { return (float)cos((double)x); }
+LISREG_HD __forceinline__ float sinf_cr(float x) { return (float)sin((double)x); }
+LISREG_HD __forceinline__ float cosf_cr(float x) { return (float)cos((double)x); }
 
 // pcl::getTransformation closed form (common.cpp:55-58) + LOAM trig set (:862-867)
-__device__ inline void state_refresh(RegState& s) {
+LISREG_HD inline void state_refresh(RegState& s) {
   float roll = s.pose[0], pitch = s.pose[1], yaw = s.pose[2];
   float A = cosf_cr(yaw), B = sinf_cr(yaw), C = cosf_cr(pitch), D = sinf_cr(pitch);
   float E = cosf_cr(roll), F = sinf_cr(roll), DE = D * E, DF = D * F;
@@ -63,7 +63,7 @@ __device__ inline void state_refresh(RegState& s) {
 }
 
 // cornerOptimization body after the kNN (:657-742). nb = 5 neighbours. raw = {la,lb,lc,ld2,s}
-__device__ __forceinline__ bool corner_coeff(float x0, float y0, float z0, const float4 (&nb)[5], float (&raw)[5]) {
+LISREG_HD __forceinline__ bool corner_coeff(float x0, float y0, float z0, const float4 (&nb)[5], float (&raw)[5]) {
   float cx = 0, cy = 0, cz = 0;
 #pragma unroll
   for (int j = 0; j < 5; j++) { cx += nb[j].x; cy += nb[j].y; cz += nb[j].z; }
@@ -97,7 +97,7 @@ __device__ __forceinline__ bool corner_coeff(float x0, float y0, float z0, const
 }
 
 // surfOptimization body after the kNN (:776-821). raw = {pa,pb,pc,pd2,s}
-__device__ __forceinline__ bool surf_coeff(float x0, float y0, float z0, const float4 (&nb)[5], float (&raw)[5]) {
+LISREG_HD __forceinline__ bool surf_coeff(float x0, float y0, float z0, const float4 (&nb)[5], float (&raw)[5]) {
   float A0[15], X0[3];
   const float B0[5] = {-1.f, -1.f, -1.f, -1.f, -1.f};
 #pragma unroll
@@ -118,7 +118,7 @@ __device__ __forceinline__ bool surf_coeff(float x0, float y0, float z0, const f
 }
 
 // LMOptimization tail (:869-973) run by one thread once all tiles of a registration are in.
-__device__ inline void lm_solve_tail(RegState& st, const LmParamsDev& prm, const double* sums, lisreg_lm_iter* log) {
+LISREG_HD inline void lm_solve_tail(RegState& st, const LmParamsDev& prm, const double* sums, lisreg_lm_iter* log) {
   const int nC = (int)sums[27], nS = (int)sums[28], nSel = nC + nS;
   const int iter = st.iter;
   st.n_sel_last = nSel;
@@ -260,8 +260,17 @@ k_lm_iter(const RegDesc* __restrict__ descs, RegState* __restrict__ states, cons
     const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
     const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
     float bd[5]; int bi[5], bp[5];
+#ifdef LISREG_V3
+    const GridDev g = is_corner ? mp.corner : mp.surf;
+    const float gate_l = prm.gate;
+    knn5_grid(g, x0, y0, z0, gate_l, bd, bi, bp);
+#else
     const GridDev& g = is_corner ? mp.corner : mp.surf;
     knn5_grid(g, x0, y0, z0, prm.gate, bd, bi, bp);
+#endif
+#ifdef LISREG_DEBUG
+    if (q < 3 || q == sd.nc) printf("q=%d nc=%d ns=%d slot=%d g.n=%d h=%f dims=%d %d %d p=(%f %f %f) x=(%f %f %f) T0=%f T3=%f bd4=%f bp4=%d gate=%f o=(%f %f %f) invh=%f bd0=%f bp0=%d\n", q, sd.nc, sd.ns, sd.map_slot, g.n, g.h, g.nx, g.ny, g.nz, p.x, p.y, p.z, x0, y0, z0, sT[0], sT[3], bd[4], bp[4], prm.gate, g.ox, g.oy, g.oz, g.inv_h, bd[0], bp[0]);
+#endif
     if (!(bd[4] < prm.gate) || bp[4] < 0) continue;
     float4 nb[5];
 #pragma unroll

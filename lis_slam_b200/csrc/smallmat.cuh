@@ -7,21 +7,25 @@
 #pragma once
 #include <cfloat>
 #include <cuda_runtime.h>
+#include <cmath>
+#ifndef LISREG_HD
+#define LISREG_HD __host__ __device__
+#endif
 
 namespace lisreg {
 
-__device__ __forceinline__ float cv_hypotf(float a, float b) {
+LISREG_HD __forceinline__ float cv_hypotf(float a, float b) {
   a = fabsf(a); b = fabsf(b);
   if (a > b) { b /= a; return a * sqrtf(1 + b * b); }
   if (b > 0) { a /= b; return b * sqrtf(1 + a * a); }
   return 0.f;
 }
 
-__device__ __forceinline__ void swapf(float& a, float& b) { float t = a; a = b; b = t; }
+LISREG_HD __forceinline__ void swapf(float& a, float& b) { float t = a; a = b; b = t; }
 
 // Symmetric Jacobi: eigenvalues descending in W, eigenvectors in the ROWS of V.
 template <int N>
-__device__ void jacobi_eigen(float* A, float* W, float* V) {
+LISREG_HD void jacobi_eigen(float* A, float* W, float* V) {
   const float eps = FLT_EPSILON;
   int i, j, k, m;
   for (i = 0; i < N; i++) { for (j = 0; j < N; j++) V[i * N + j] = 0.f; V[i * N + i] = 1.f; }
@@ -103,7 +107,7 @@ __device__ void jacobi_eigen(float* A, float* W, float* V) {
 
 // Householder QR solve, square N x N (A destroyed, b -> x). Returns 0 if singular.
 template <int N>
-__device__ int qr_solve(float* A, float* b) {
+LISREG_HD int qr_solve(float* A, float* b) {
   const float eps = FLT_EPSILON * 10;
   float vl[N], hF[N];
   for (int l = 0; l < N; l++) {
@@ -140,7 +144,7 @@ __device__ int qr_solve(float* A, float* b) {
 
 // LU with partial pivoting: solves A X = B in place (B is N x NB row-major).
 template <int N, int NB>
-__device__ int lu_solve(float* A, float* b) {
+LISREG_HD int lu_solve(float* A, float* b) {
   const float eps = FLT_EPSILON * 10;
   int i, j, k;
   for (i = 0; i < N; i++) {
@@ -169,7 +173,7 @@ __device__ int lu_solve(float* A, float* b) {
 }
 
 // 5x3 least squares A x = rhs by column-pivoting Householder QR. A row-major, destroyed.
-__device__ __forceinline__ void colpiv_qr_solve_5x3(float* A, const float* rhs, float* x) {
+LISREG_HD __forceinline__ void colpiv_qr_solve_5x3(float* A, const float* rhs, float* x) {
   const int R = 5, C = 3;
   float c[5];
 #pragma unroll

@@ -72,6 +72,21 @@ int orc_qr_solve_f32(const float* A, int32_t n, const float* b, float* x);
 int orc_lu_inv_f32(const float* A, int32_t n, float* Ainv);
 void orc_plane_fit_5x3(const float* A15, float* x3);
 
+/* ---- feature extraction (laserProcessing.cpp:467-713) ---- */
+typedef struct orc_feat_params {
+  int32_t n_scan, horizon, downsample_rate;
+  float min_range, max_range;
+  float edge_thr, surf_thr;
+} orc_feat_params;
+
+int32_t orc_project_scan(const float* pts4, const uint16_t* ring, int32_t n, const orc_feat_params* prm,
+                         int32_t* src_index, int32_t* col_ind, float* range, int32_t* start_ring, int32_t* end_ring);
+void orc_extract_features(const float* range, const int32_t* col_ind, int32_t M,
+                          const int32_t* start_ring, const int32_t* end_ring, const orc_feat_params* prm,
+                          int32_t* corner_idx, int32_t* n_corner, int32_t* sharp_idx, int32_t* n_sharp,
+                          int32_t* flat_idx, int32_t* n_flat, int32_t* surf_idx, int32_t* n_surf,
+                          float* curvature_out, int32_t* label_out);
+
 #ifdef __cplusplus
 }
 #endif
