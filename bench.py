@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py — frames/sec of scan-to-map LM (64x1800-shaped scans vs 200k-pt local maps).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a engine
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference path
+
+One "step" = one pass of the hot path over one batch of B synthetic registrations per GPU
+(throughput mode, BASELINE.json configs[2] shape; weak scaling: B per GPU is fixed).  Prints ONE
+JSON line (see README/DESIGN.md for the keys).  `value` is measured with the inputs resident in
+HBM; `e2e` goes through the C-ABI host call with a pinned host arena (H2D of every frame packet
+and D2H of the results inside the timed region).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec scan-to-map LM (64x1800 pts)"
+UNIT = "frames/s"
+LM_ITERS = 10   # fixed iteration count, early exit disabled on both arms so the work is equal
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """per-launch DRAM traffic of the dominant kernel from the committed ncu capture (or None)."""
+    p = os.path.join(ROOT, "profiles", "lm_iter_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler(threading.Thread):
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        super().__init__(daemon=True)
+        self.idx = device_index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[1])); mx.append(float(s[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_leg(wl, n_regs, n_threads):
+    """Times the CPU restatement (oracle) of the reference path on `n_regs` registrations of the
+    workload: kd-tree build x2 per registration (as the reference does every frame) + LM_ITERS
+    iterations.  Returns (regs/s, seconds, poses)."""
+    from oracle import orc
+    prm = orc.lm_params("A", early_exit=0, max_iters=LM_ITERS, n_threads=n_threads)
+    poses = []
+    t0 = time.perf_counter()
+    for r in wl["regs"][:n_regs]:
+        f, _ = wl["scans"][r["scan"]]
+        m = wl["maps"][r["map"]]
+        pose, res, _ = orc.scan2map(f["corner"], f["surf"], m["corner"], m["surf"], r["guess"], prm, log=False)
+        poses.append(pose)
+    dt = time.perf_counter() - t0
+    return n_regs / dt, dt, poses
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from lis_slam_b200 import workload
+    wl = workload.throughput_batch(B=max(args.ref_sample, 8), n_maps=2, n_scans=min(8, max(args.ref_sample, 8)), seed=0)
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_reference_leg(wl, 1, cores)
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        v, dt, _ = cpu_reference_leg(wl, args.ref_sample, cores)
+        t_total += dt; n_total += args.ref_sample
+    value = n_total / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "throughput_batch: independent 64x1800-shaped scan-to-map registrations vs 200k-pt maps, 10 LM iters "
+                               "(CPU arm: bounded sample of %d registrations per step)" % args.ref_sample,
+                   "n_corner": 4000, "n_surf": 12000, "map_points": 200000, "lm_iters": LM_ITERS},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d registrations/step x %d steps, OpenMP over points with %d threads (races fixed), "
+                                   "kd-tree rebuilt per registration like the reference" % (args.ref_sample, args.steps, cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from lis_slam_b200 import engine as E
+    from lis_slam_b200 import synth, workload
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.Stream(dev)          # everything (engine kernels, torch copies, NCCL, events) runs on this stream
+    torch.cuda.set_stream(stream)
+    eng = E.Engine(device=local_rank, stream=stream.cuda_stream)
+    B = args.batch
+    wl = workload.throughput_batch(B=B, n_maps=args.maps, n_scans=args.scans, seed=rank)
+    map_ids = [eng.map_create(m["corner"], m["surf"], gate_hint=1.0) for m in wl["maps"]]
+
+    # ---- inputs resident in HBM (one private buffer per registration) ----
+    arena_np, offs = workload.pack_arena(wl)
+    arena_pin = torch.from_numpy(arena_np).pin_memory()
+    arena_dev = arena_pin.to(dev, non_blocking=False)
+    guess_np = np.stack([r["guess"] for r in wl["regs"]]).astype(np.float32)
+    guess_dev = torch.from_numpy(guess_np).to(dev)
+    pose_dev = torch.empty_like(guess_dev)
+    res_dev = torch.empty(B * C.sizeof(E.LmResult), dtype=torch.uint8, device=dev)
+    base = arena_dev.data_ptr()
+    NONE = C.c_void_p(-1).value
+    items_dev = (E.BatchItem * B)()
+    items_off = (E.BatchItem * B)()
+    n_pts = 0
+    for b, (r, o) in enumerate(zip(wl["regs"], offs)):
+        items_dev[b] = E.BatchItem(base + o["corner"], None, base + o["surf"], None, o["n_corner"], o["n_surf"], map_ids[r["map"]], 0)
+        items_off[b] = E.BatchItem(o["corner"], NONE, o["surf"], NONE, o["n_corner"], o["n_surf"], map_ids[r["map"]], 0)
+        n_pts += o["n_corner"] + o["n_surf"]
+    prm = E.lm_params("A", early_exit=0, max_iters=LM_ITERS)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    gathered = torch.empty(world * B, 6, dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step_dev():
+        flush.zero_()                                   # L2 flush between timed iterations
+        pose_dev.copy_(guess_dev)
+        eng.scan2map_batch_dev(items_dev, B, pose_dev.data_ptr(), prm, res_dev.data_ptr())
+        if world > 1:                                   # the single exchange step: all-gather of the 6-DoF poses
+            dist.all_gather_into_tensor(gathered, pose_dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing ----
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+    eng.profile_enable(True)
+    eng.profile_get(reset=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = eng.launches - l0
+    prof = eng.profile_get(reset=True)
+    eng.profile_enable(False)
+    pose_gpu = pose_dev.cpu().numpy().copy()
+
+    # ---- end-to-end timing through the host C-ABI call (pinned arena, H2D + D2H inside) ----
+    pose_host = guess_np.copy()
+    res_host = (E.LmResult * B)()
+    for _ in range(2):
+        pose_host[:] = guess_np
+        eng.scan2map_batch_arena(items_off, B, arena_pin.data_ptr(), arena_np.nbytes, pose_host, prm, res_host)
+    barrier()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(args.steps):
+        pose_host[:] = guess_np
+        eng.scan2map_batch_arena(items_off, B, arena_pin.data_ptr(), arena_np.nbytes, pose_host, prm, res_host)
+    f1.record(stream)
+    barrier()
+    ms_e2e = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - t0))
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- max over ranks ----
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    value = world * B * args.steps / (ms_total * 1e-3)
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_lm_iter) ----
+    peak, peak_src = load_peaks()
+    ach = (prof.lm_alg_bytes / max(prof.lm_iter_launches, 1)) / (prof.lm_iter_ms * 1e-3 / max(prof.lm_iter_launches, 1)) / 1e9
+    traffic = load_traffic()
+    roofline = {"bound": "hbm", "kernel": "k_lm_iter", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "peak_source": peak_src, "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                "alg_bytes_per_launch": prof.lm_alg_bytes / max(prof.lm_iter_launches, 1),
+                "avg_launch_ms": prof.lm_iter_ms / max(prof.lm_iter_launches, 1),
+                "kernel_share_of_step": prof.lm_iter_ms / ms_total,
+                "note": "algorithmic bytes = (nc+ns) x (16 B query + 5 x 16 B neighbours) per launch (SURVEY.md 8d A_iter); "
+                        "index traversal traffic excluded"}
+
+    # ---- CPU baseline (rank 0, N=1 only) + pose error vs the CPU reference path ----
+    cpu = None
+    pose_err = None
+    if world == 1 and not args.no_cpu:
+        n_cpu = args.cpu_sample
+        v, dt, poses_cpu = cpu_reference_leg(wl, n_cpu, 1)
+        er = [synth.pose_error(pc, pose_gpu[i]) for i, pc in enumerate(poses_cpu)]
+        pose_err = {"max_rot_rad": max(e[0] for e in er), "max_trans_m": max(e[1] for e in er), "n": n_cpu,
+                    "tolerance": {"rot_rad": 1e-4, "trans_m": 1e-3}}
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "%d registrations of this workload, %.1f s, 1 thread = as-built reference (its OpenMP pragmas are inert); "
+                         "kd-tree rebuilt per registration" % (n_cpu, dt)}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "throughput_batch (BASELINE configs[2] shape per GPU): %d independent HDL-64-shaped scan-to-map "
+                               "registrations per GPU per step vs 200k-pt edge/surf maps, %d LM iterations, early exit off" % (B, LM_ITERS),
+                   "batch_per_gpu": B, "distinct_maps": args.maps, "distinct_scans": args.scans,
+                   "mean_query_points": n_pts / B, "map_points": 200000, "lm_iters": LM_ITERS,
+                   "l2": "256 MB flush write between timed steps; per-step inputs %.0f MB" % (arena_np.nbytes / 1e6)},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(arena_np.nbytes + B * (48 + 24)),
+                "d2h_bytes_per_step": int(B * C.sizeof(E.LmResult)), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "pose_err_vs_cpu": pose_err,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="registrations per GPU per step")
+    ap.add_argument("--maps", type=int, default=8)
+    ap.add_argument("--scans", type=int, default=32)
+    ap.add_argument("--cpu-sample", type=int, default=24, help="registrations timed on the CPU for cpu_baseline")
+    ap.add_argument("--ref-sample", type=int, default=16, help="registrations per step for --impl reference")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl")
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

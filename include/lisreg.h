@@ -40,9 +40,10 @@ typedef struct lisreg_ctx lisreg_ctx;
 
 typedef struct lisreg_config {
   int32_t device;        /* CUDA device ordinal */
-  void* stream;          /* cudaStream_t to run on; NULL = engine-owned stream */
+  void* stream;          /* cudaStream_t to run on; NULL = the legacy default stream */
   int32_t max_grid_cells;/* per-cloud uniform-grid capacity (0 = default 4M cells) */
-  int32_t reserved[5];
+  int32_t own_stream;    /* 1: ignore `stream`, create a private non-blocking stream */
+  int32_t reserved[4];
 } lisreg_config;
 
 /* Parameters of the three copies of the loop (variant A odomEstimationNode.cpp:596-974,
@@ -145,6 +146,33 @@ int32_t lisreg_scan2map_batch(lisreg_ctx* ctx, int32_t B, const lisreg_batch_ite
 int32_t lisreg_scan2map_batch_dev(lisreg_ctx* ctx, int32_t B, const lisreg_batch_item* items,
                                   float* d_pose6xB, const lisreg_lm_params* prm,
                                   lisreg_lm_result* d_resxB);
+
+/* same, with the frame packets packed by the caller into ONE contiguous (ideally pinned) host
+ * arena: the corner/clabel/surf/slabel members of items[] are BYTE OFFSETS into the arena
+ * (cast to pointers; (size_t)-1 = absent label array; offsets must be 16-byte aligned).  One
+ * H2D copy of the arena, the solve, one D2H copy of the results.  This is the analogue of the
+ * reference's serialised lis_slam::cloud_info packet (msg/cloud_info.msg) arriving in one buffer. */
+int32_t lisreg_scan2map_batch_arena(lisreg_ctx* ctx, int32_t B, const lisreg_batch_item* items,
+                                    const void* host_arena, uint64_t arena_bytes,
+                                    float* pose6xB, const lisreg_lm_params* prm, lisreg_lm_result* resxB);
+
+/* device self-test of the small dense routines (cv::eigen / cv::solve(QR) / cv::Mat::inv restatements):
+ * out98 = E[6], V[36] (eigenvectors in rows), X[6] (QR solve of A x = b), ok, Ainv[36] (LU), ok,
+ * then W3[3], V3[9] of the register-only 3x3 Jacobi applied to the leading 3x3 block of A */
+int32_t lisreg_selftest_smallmat(lisreg_ctx* ctx, const float* A36, const float* b6, float* out98);
+
+/* ---- profiling (CUDA events on the context stream around the dominant kernels) ---- */
+typedef struct lisreg_profile {
+  double lm_iter_ms;        /* total device time of k_lm_iter launches */
+  int64_t lm_iter_launches;
+  double lm_alg_bytes;      /* algorithmic bytes of those launches: sum (nc+ns) * 96 B (SURVEY.md 8d A_iter) */
+  double feat_ms;  int64_t feat_launches;  double feat_alg_bytes;
+  double voxel_ms; int64_t voxel_launches; double voxel_alg_bytes;
+  double index_ms; int64_t index_launches; double index_alg_bytes;
+} lisreg_profile;
+int32_t lisreg_profile_enable(lisreg_ctx* ctx, int32_t on);
+/* synchronises the stream, accumulates all pending event pairs, returns totals since the last reset */
+int32_t lisreg_profile_get(lisreg_ctx* ctx, lisreg_profile* out, int32_t reset);
 
 #ifdef __cplusplus
 }

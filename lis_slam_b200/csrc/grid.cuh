@@ -8,11 +8,16 @@
 // matter; points whose 5th neighbour lies beyond the gate are rejected on both paths.
 //
 // Layout in HBM: map points are counting-sorted by linear cell id (x fastest) into a packed
-// float4 array {x, y, z, bits(original index)}; cell_start[] (ncells + 1, uint32) is the CSR
-// offset table.  With x fastest, the cells (cx-s .. cx+s, cy, cz) of one row are one
-// contiguous point range, so a shell of the search is a handful of coalesced streaks.
-// The search visits Chebyshev shells s = 0, 1, ... and stops as soon as the 5th best
-// distance is below the lower bound of everything not yet visited (or the gate).
+// float4 array {x, y, z, bits(original index)}, points of one cell ordered by original index;
+// cell_start[] (ncells + 1, uint32) is the CSR offset table.  With x fastest, the cells
+// (cx-s .. cx+s, cy, cz) of one row are ONE contiguous point range, so the 3x3x3 block around a
+// query is 9 coalesced streaks.  The search visits that block first, then Chebyshev shells
+// s = 2, 3, ... and stops as soon as the 5th best distance is below the lower bound of
+// everything not yet visited (or the bound reaches the gate).
+//
+// The running best-5 is kept as five 64-bit keys (float bits of d^2 << 32 | position in the
+// sorted array): d^2 >= 0 so the integer order of the key is the lexicographic (d^2, position)
+// order, and a sorted insert is five branch-free min/max stages held entirely in registers.
 #pragma once
 #include <cstdint>
 #include <cfloat>
@@ -40,9 +45,7 @@ struct GridDev {
   const float4* pts;           // sorted, w = original index bits
 };
 
-LISREG_HD __forceinline__ int cell_coord(float v, float o, float inv_h) {
-  return (int)floorf((v - o) * inv_h);
-}
+typedef unsigned long long knn_key;
 
 LISREG_HD __forceinline__ int f2i(float f) {
 #ifdef __CUDA_ARCH__
@@ -51,90 +54,105 @@ LISREG_HD __forceinline__ int f2i(float f) {
   int i; memcpy(&i, &f, 4); return i;
 #endif
 }
+LISREG_HD __forceinline__ float i2f(int i) {
+#ifdef __CUDA_ARCH__
+  return __int_as_float(i);
+#else
+  float f; memcpy(&f, &i, 4); return f;
+#endif
+}
+LISREG_HD __forceinline__ float knn_key_d(knn_key k) { return i2f((int)(unsigned)(k >> 32)); }
+LISREG_HD __forceinline__ int knn_key_pos(knn_key k) { return (int)(unsigned)(k & 0xffffffffull); }
 
-// lexicographic (distance, original index) order makes the result independent of the
-// (atomic, hence unordered) placement of points inside a cell.
-LISREG_HD __forceinline__ bool knn_less(float d, int i, float d2, int i2) {
-  return d < d2 || (d == d2 && i < i2);
+LISREG_HD __forceinline__ int cell_coord(float v, float o, float inv_h) {
+  return (int)floorf((v - o) * inv_h);
 }
 
-// Sorted insert into the running best-5 (ascending): replace the worst entry, then bubble it
-// down with select-based compare-exchanges (static indices only, so the arrays stay in registers).
-LISREG_HD __forceinline__ void knn5_insert(float (&bd)[5], int (&bi)[5], int (&bp)[5], float d, int idx, int pos) {
-  if (!knn_less(d, idx, bd[4], bi[4])) return;
-  bd[4] = d; bi[4] = idx; bp[4] = pos;
+// keeps the five smallest keys, ascending
+LISREG_HD __forceinline__ void knn5_insert(knn_key (&b)[5], knn_key k) {
 #pragma unroll
-  for (int j = 4; j > 0; j--) {
-    const bool sw = knn_less(bd[j], bi[j], bd[j - 1], bi[j - 1]);
-    const float d0 = bd[j - 1], d1 = bd[j];
-    const int i0 = bi[j - 1], i1 = bi[j], p0 = bp[j - 1], p1 = bp[j];
-    bd[j - 1] = sw ? d1 : d0; bd[j] = sw ? d0 : d1;
-    bi[j - 1] = sw ? i1 : i0; bi[j] = sw ? i0 : i1;
-    bp[j - 1] = sw ? p1 : p0; bp[j] = sw ? p0 : p1;
+  for (int j = 0; j < 5; j++) {
+    const bool lt = b[j] < k;
+    const knn_key lo = lt ? b[j] : k;
+    k = lt ? k : b[j];
+    b[j] = lo;
   }
 }
 
-LISREG_HD __forceinline__ void knn5_scan_range(const GridDev& g, uint32_t b, uint32_t e, float qx, float qy, float qz,
-                                                float (&bd)[5], int (&bi)[5], int (&bp)[5]) {
+LISREG_HD __forceinline__ void knn5_scan_range(const float4* __restrict__ pts, uint32_t b, uint32_t e,
+                                                float qx, float qy, float qz, knn_key (&best)[5]) {
   for (uint32_t p = b; p < e; p++) {
-    float4 m = LISREG_LDG(&g.pts[p]);
-    float dx = qx - m.x, dy = qy - m.y, dz = qz - m.z;
+    const float4 m = LISREG_LDG(&pts[p]);
+    const float dx = qx - m.x, dy = qy - m.y, dz = qz - m.z;
     float d = dx * dx; d = d + dy * dy; d = d + dz * dz;   // FLANN L2 functor op order, no FMA
-    if (d <= bd[4]) knn5_insert(bd, bi, bp, d, f2i(m.w), (int)p);
+    const knn_key k = ((knn_key)(unsigned)f2i(d) << 32) | (knn_key)p;
+    if (k < best[4]) knn5_insert(best, k);
   }
 }
 
-// Exact 5-NN restricted to squared distance < gate.  On return bd[] ascending; slots that
-// found no neighbour inside the gate keep bd = gate, bi = INT_MAX, bp = -1.
-LISREG_HD __forceinline__ void knn5_grid(const GridDev& g, float qx, float qy, float qz, float gate,
-                                          float (&bd)[5], int (&bi)[5], int (&bp)[5]) {
-#pragma unroll
-  for (int j = 0; j < 5; j++) { bd[j] = gate; bi[j] = 0x7fffffff; bp[j] = -1; }
-  if (g.n <= 0) return;
-  const float fx = (qx - g.ox) * g.inv_h, fy = (qy - g.oy) * g.inv_h, fz = (qz - g.oz) * g.inv_h;
-  const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
-  // distance from the query to the nearest face of its own cell (in cells), conservative
-  float rx = fx - (float)cx, ry = fy - (float)cy, rz = fz - (float)cz;
-  float minf = fminf(fminf(fminf(rx, 1.f - rx), fminf(ry, 1.f - ry)), fminf(rz, 1.f - rz));
+LISREG_HD __forceinline__ void knn_row_range(const GridDev& g, int x0, int x1, int y, int z, uint32_t& b, uint32_t& e) {
+  b = 0u; e = 0u;
+  if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) return;
+  x0 = x0 > 0 ? x0 : 0; x1 = x1 < g.nx - 1 ? x1 : g.nx - 1;
+  if (x0 > x1) return;
+  const int rowbase = (z * g.ny + y) * g.nx;
+  b = LISREG_LDG(&g.cell_start[rowbase + x0]);
+  e = LISREG_LDG(&g.cell_start[rowbase + x1 + 1]);
+}
+
+// Outer shells t = 2, 3, ... (rare: sparse neighbourhoods).  Kept out of line so that the hot
+// 3x3x3 loop stays small in the instruction cache.
+LISREG_HD __noinline__ void knn5_outer_shells(const GridDev& g, float qx, float qy, float qz, float gate,
+                                             int cx, int cy, int cz, float minf, knn_key (&best)[5]) {
   const int max_shell = (int)ceilf(sqrtf(gate) * g.inv_h) + 1;
-  for (int s = 0; s <= max_shell; s++) {
-    const int z0 = cz - s > 0 ? cz - s : 0, z1 = cz + s < g.nz - 1 ? cz + s : g.nz - 1;
-    const int y0 = cy - s > 0 ? cy - s : 0, y1 = cy + s < g.ny - 1 ? cy + s : g.ny - 1;
-    const int xa = cx - s, xb = cx + s;
-    if (!(xb < 0 || xa >= g.nx)) {
-      for (int z = z0; z <= z1; z++) {
-        const bool zface = (z == cz - s) || (z == cz + s);
-        for (int y = y0; y <= y1; y++) {
-          const bool face = zface || (y == cy - s) || (y == cy + s);
-          const int rowbase = (z * g.ny + y) * g.nx;
-          if (face) {
-            const int x0 = xa > 0 ? xa : 0, x1 = xb < g.nx - 1 ? xb : g.nx - 1;
-            uint32_t b = LISREG_LDG(&g.cell_start[rowbase + x0]);
-            uint32_t e = LISREG_LDG(&g.cell_start[rowbase + x1 + 1]);
-            knn5_scan_range(g, b, e, qx, qy, qz, bd, bi, bp);
-          } else {
-            if (xa >= 0 && xa < g.nx) {
-              uint32_t b = LISREG_LDG(&g.cell_start[rowbase + xa]);
-              uint32_t e = LISREG_LDG(&g.cell_start[rowbase + xa + 1]);
-              knn5_scan_range(g, b, e, qx, qy, qz, bd, bi, bp);
-            }
-            if (xb >= 0 && xb < g.nx && xb != xa) {
-              uint32_t b = LISREG_LDG(&g.cell_start[rowbase + xb]);
-              uint32_t e = LISREG_LDG(&g.cell_start[rowbase + xb + 1]);
-              knn5_scan_range(g, b, e, qx, qy, qz, bd, bi, bp);
-            }
-          }
+  for (int s = 1; s <= max_shell; s++) {
+    // everything not yet visited is farther than lb (margin covers the float rounding of cell assignment)
+    const float lb = ((float)s + minf - 1e-3f) * g.h;
+    const float lb2 = lb * lb;
+    if (lb > 0.f && (knn_key_d(best[4]) < lb2 || lb2 >= gate)) break;
+    const int t = s + 1;   // visit shell t
+    for (int z = cz - t; z <= cz + t; z++) {
+      const bool zface = (z == cz - t) || (z == cz + t);
+      for (int y = cy - t; y <= cy + t; y++) {
+        const bool face = zface || (y == cy - t) || (y == cy + t);
+        // a face row is one streak; an inner row contributes only its two end cells
+        for (int part = 0; part < (face ? 1 : 2); part++) {
+          uint32_t b, e;
+          if (face) knn_row_range(g, cx - t, cx + t, y, z, b, e);
+          else knn_row_range(g, part == 0 ? cx - t : cx + t, part == 0 ? cx - t : cx + t, y, z, b, e);
+          knn5_scan_range(g.pts, b, e, qx, qy, qz, best);
         }
       }
     }
-    // everything not yet visited is farther than lb (with a safety margin for the float
-    // rounding of cell assignment)
-    float lb = ((float)s + minf - 1e-3f) * g.h;
-    if (lb > 0.f) {
-      float lb2 = lb * lb;
-      if (bd[4] < lb2 || lb2 >= gate) break;
-    }
   }
+}
+
+// Exact 5-NN restricted to squared distance < gate.  best[] ascending; unused slots keep the
+// sentinel (d^2 = gate, position 0xffffffff), so "5 neighbours inside the gate" <=> key_d(best[4]) < gate.
+LISREG_HD __forceinline__ void knn5_grid(const GridDev& g, float qx, float qy, float qz, float gate, knn_key (&best)[5]) {
+  const knn_key sentinel = ((knn_key)(unsigned)f2i(gate) << 32) | 0xffffffffull;
+#pragma unroll
+  for (int j = 0; j < 5; j++) best[j] = sentinel;
+  if (g.n <= 0) return;
+  const float fx = (qx - g.ox) * g.inv_h, fy = (qy - g.oy) * g.inv_h, fz = (qz - g.oz) * g.inv_h;
+  const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
+  // distance from the query to the nearest face of its own cell (in cells)
+  const float rx = fx - (float)cx, ry = fy - (float)cy, rz = fz - (float)cz;
+  const float minf = fminf(fminf(fminf(rx, 1.f - rx), fminf(ry, 1.f - ry)), fminf(rz, 1.f - rz));
+  // ---- the 3x3x3 block: 9 row streaks; ONE copy of the scan loop (instruction-cache friendly),
+  //      the offsets of row r+1 are fetched while row r is scanned ----
+  uint32_t b, e, nb = 0u, ne = 0u;
+  knn_row_range(g, cx - 1, cx + 1, cy - 1, cz - 1, b, e);
+#pragma unroll 1
+  for (int r = 0; r < 9; r++) {
+    if (r < 8) knn_row_range(g, cx - 1, cx + 1, cy + ((r + 1) % 3) - 1, cz + ((r + 1) / 3) - 1, nb, ne);
+    knn5_scan_range(g.pts, b, e, qx, qy, qz, best);
+    b = nb; e = ne;
+  }
+  // ---- outer shells only if something unvisited could still beat the 5th best ----
+  const float lb = (1.f + minf - 1e-3f) * g.h;
+  const float lb2 = lb * lb;
+  if (!(knn_key_d(best[4]) < lb2 || lb2 >= gate)) knn5_outer_shells(g, qx, qy, qz, gate, cx, cy, cz, minf, best);
 }
 
 }  // namespace lisreg

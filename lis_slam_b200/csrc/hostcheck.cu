@@ -14,8 +14,12 @@ int hc_surf_coeff(const float* q, const float* nb15, float* raw5) {
   float raw[5] = {0,0,0,0,0}; bool ok = surf_coeff(q[0], q[1], q[2], nb, raw);
   for (int i = 0; i < 5; i++) raw5[i] = raw[i]; return ok ? 1 : 0;
 }
-void hc_jacobi3(const float* A, float* W, float* V) { float a[9]; for (int i = 0; i < 9; i++) a[i] = A[i]; jacobi_eigen<3>(a, W, V); }
-void hc_jacobi6(const float* A, float* W, float* V) { float a[36]; for (int i = 0; i < 36; i++) a[i] = A[i]; jacobi_eigen<6>(a, W, V); }
+void hc_jacobi3(const float* A, float* W, float* V) { float a[9]; int ir[3], ic[3]; for (int i = 0; i < 9; i++) a[i] = A[i]; jacobi_eigen<3>(a, W, V, ir, ic); }
+void hc_jacobi3_reg(const float* A, float* W, float* V) {
+  float w[3], v[9]; jacobi_eigen3(A[0], A[1], A[2], A[4], A[5], A[8], w, v);
+  for (int i = 0; i < 3; i++) W[i] = w[i]; for (int i = 0; i < 9; i++) V[i] = v[i];
+}
+void hc_jacobi6(const float* A, float* W, float* V) { float a[36]; int ir[6], ic[6]; for (int i = 0; i < 36; i++) a[i] = A[i]; jacobi_eigen<6>(a, W, V, ir, ic); }
 int hc_qr6(const float* A, const float* b, float* x) { float a[36]; for (int i = 0; i < 36; i++) a[i] = A[i]; for (int i = 0; i < 6; i++) x[i] = b[i]; return qr_solve<6>(a, x); }
 void hc_plane(const float* A15, float* x) { float a[15]; const float b[5] = {-1,-1,-1,-1,-1}; for (int i = 0; i < 15; i++) a[i] = A15[i]; colpiv_qr_solve_5x3(a, b, x); }
 void hc_state_refresh(const float* pose, float* T12, float* trig6) {
@@ -30,7 +34,7 @@ void hc_solve_tail(float* pose, int iter, int degenerate_in, const double* sums,
   LmParamsDev d; memset(&d, 0, sizeof(d));
   d.max_iters = p->max_iters; d.early_exit = p->early_exit; d.gate = p->sqdist_gate; d.conv_rot = p->conv_rot_deg; d.conv_trans = p->conv_trans_cm;
   d.min_sel = p->min_sel; d.degenerate_eig = p->degenerate_eig; d.rot_tol = p->rot_tolerance; d.z_tol = p->z_tolerance;
-  lm_solve_tail(st, d, sums, log);
+  SolveScratch sc; lm_solve_tail(st, d, sums, log, sc);
   for (int i = 0; i < 6; i++) pose[i] = st.pose[i];
   out_flags[0] = st.done; out_flags[1] = st.converged; out_flags[2] = st.degenerate; out_flags[3] = st.any_small;
 }
@@ -54,8 +58,12 @@ extern "C" void hc_knn5(const float* map4, int n, const float* q4, int nq, float
   for (int i = 0; i < n; i++) { float4 p = make_float4(map4[4*i], map4[4*i+1], map4[4*i+2], 0.f); memcpy(&p.w, &i, 4); sorted[fill[cid[i]]++] = p; }
   g.cell_start = start.data(); g.pts = sorted.data();
   for (int i = 0; i < nq; i++) {
-    float bd[5]; int bi[5], bp[5];
-    knn5_grid(g, q4[4*i], q4[4*i+1], q4[4*i+2], gate, bd, bi, bp);
-    for (int j = 0; j < 5; j++) { bool ok = bp[j] >= 0 && bd[j] < gate; idx[5*i+j] = ok ? bi[j] : -1; sqd[5*i+j] = ok ? bd[j] : FLT_MAX; }
+    knn_key best[5];
+    knn5_grid(g, q4[4*i], q4[4*i+1], q4[4*i+2], gate, best);
+    for (int j = 0; j < 5; j++) {
+      float d = knn_key_d(best[j]); int pos = knn_key_pos(best[j]); bool ok = pos >= 0 && d < gate;
+      int oi = 0; if (ok) memcpy(&oi, &sorted[pos].w, 4);
+      idx[5*i+j] = ok ? oi : -1; sqd[5*i+j] = ok ? d : FLT_MAX;
+    }
   }
 }

@@ -69,6 +69,28 @@ struct lisreg_ctx {
   // scratch
   DevBuf d_stage, d_descs, d_states, d_partials, d_tickets, d_logs, d_pose, d_res, d_tmp, d_bbox;
   PinBuf h_stage, h_out;
+  // profiling
+  bool prof_on = false;
+  struct EvPair { cudaEvent_t a, b; int kind; double bytes; int64_t launches; };
+  std::vector<EvPair> ev_pending;
+  std::vector<cudaEvent_t> ev_free;
+  lisreg_profile prof{};
+};
+
+enum { PROF_LM = 0, PROF_FEAT = 1, PROF_VOXEL = 2, PROF_INDEX = 3 };
+
+static cudaEvent_t ev_get(lisreg_ctx* ctx) {
+  if (!ctx->ev_free.empty()) { cudaEvent_t e = ctx->ev_free.back(); ctx->ev_free.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct ProfScope {   // records an event pair around a group of launches when profiling is on
+  lisreg_ctx* ctx; lisreg_ctx::EvPair p; bool on;
+  ProfScope(lisreg_ctx* c, int kind, double bytes, int64_t launches) : ctx(c), on(c->prof_on) {
+    if (!on) return;
+    p.a = ev_get(c); p.b = ev_get(c); p.kind = kind; p.bytes = bytes; p.launches = launches;
+    cudaEventRecord(p.a, c->stream);
+  }
+  ~ProfScope() { if (on) { cudaEventRecord(p.b, ctx->stream); ctx->ev_pending.push_back(p); } }
 };
 
 static int fail(lisreg_ctx* c, int code, const char* fmt, ...) {
@@ -199,6 +221,21 @@ __global__ void k_cell_scatter(const float4* __restrict__ pts, int n, const int*
   sorted[pos] = p;
 }
 
+// orders the points of each cell by original index (the atomic scatter leaves them unordered), so
+// the index - and every result that depends on tie-breaking by position - is reproducible
+__global__ void k_cell_order(float4* __restrict__ sorted, const uint32_t* __restrict__ cell_start, int ncells) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  const uint32_t b = cell_start[c], e = cell_start[c + 1];
+  for (uint32_t i = b + 1; i < e; i++) {
+    float4 v = sorted[i];
+    const int key = __float_as_int(v.w);
+    uint32_t j = i;
+    while (j > b && __float_as_int(sorted[j - 1].w) > key) { sorted[j] = sorted[j - 1]; j--; }
+    sorted[j] = v;
+  }
+}
+
 // builds one cloud index from device-resident points
 static int build_cloud_index(lisreg_ctx* ctx, const float4* d_pts, int n, float h_req, CloudIndex* ci) {
   cudaStream_t st = ctx->stream;
@@ -225,13 +262,23 @@ static int build_cloud_index(lisreg_ctx* ctx, const float4* d_pts, int n, float 
   k_scan_local<<<nblk, SCAN_BLOCK, 0, st>>>(ci->cell_start, ncells + 1, bsums); LAUNCH_CK();
   k_scan_sums<<<1, SCAN_BLOCK, 0, st>>>(bsums, nblk); LAUNCH_CK();
   k_scan_add<<<nblk, SCAN_BLOCK, 0, st>>>(ci->cell_start, ncells + 1, bsums); LAUNCH_CK();
-  if (n > 0) { k_cell_scatter<<<(n + 255) / 256, 256, 0, st>>>(d_pts, n, cell_id, ci->cell_start, fill, ci->sorted); LAUNCH_CK(); }
+  if (n > 0) {
+    k_cell_scatter<<<(n + 255) / 256, 256, 0, st>>>(d_pts, n, cell_id, ci->cell_start, fill, ci->sorted); LAUNCH_CK();
+    k_cell_order<<<(ncells + 127) / 128, 128, 0, st>>>(ci->sorted, ci->cell_start, ncells); LAUNCH_CK();
+  }
   g.cell_start = ci->cell_start; g.pts = ci->sorted;
   ci->g = g;
   return LISREG_OK;
 }
 
-static float cell_size_for_gate(float gate) { return 1.002f * sqrtf(gate > 0.f ? gate : 1.f) + 1e-3f; }
+// Cell size: the search is exact for ANY cell size (shell expansion); ~0.65 m keeps the 3x3x3 block
+// at ~20-30 candidates for 0.4 m voxel-grid surf maps while the 5th neighbour usually lies inside it.
+static float cell_size_for_gate(float gate) {
+  const char* e = getenv("LISREG_CELL");
+  float h = e ? (float)atof(e) : 0.65f;
+  const float r = sqrtf(gate > 0.f ? gate : 1.f);
+  return fminf(h, 1.002f * r + 1e-3f);
+}
 
 // ------------------------------------------------------------------------------------------------
 // C-ABI
@@ -255,8 +302,10 @@ int32_t lisreg_create(const lisreg_config* cfg, lisreg_ctx** out) {
     return LISREG_ERR_CUDA;
   }
   if (cudaSetDevice(ctx->device) != cudaSuccess) { delete ctx; return LISREG_ERR_CUDA; }
-  if (cfg && cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
-  else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LISREG_ERR_CUDA; } ctx->own_stream = true; }
+  if (cfg && cfg->own_stream) {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LISREG_ERR_CUDA; }
+    ctx->own_stream = true;
+  } else { ctx->stream = cfg ? (cudaStream_t)cfg->stream : nullptr; ctx->own_stream = false; }   // NULL = legacy default stream
   if (cfg && cfg->max_grid_cells > 0) ctx->max_cells = cfg->max_grid_cells;
   if (const char* e2 = getenv("LISREG_STACK")) cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atoi(e2));
   *out = ctx;
@@ -274,6 +323,8 @@ void lisreg_destroy(lisreg_ctx* ctx) {
   for (DevBuf* b : {&ctx->d_stage, &ctx->d_descs, &ctx->d_states, &ctx->d_partials, &ctx->d_tickets, &ctx->d_logs,
                     &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox}) b->release();
   ctx->h_stage.release(); ctx->h_out.release();
+  for (auto& p : ctx->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto e : ctx->ev_free) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -393,15 +444,15 @@ static void to_dev_params(const lisreg_lm_params* p, LmParamsDev* d) {
 }
 
 // core driver: descs already on the device. max_n = largest nc+ns of the batch.
-static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, float* d_pose, const lisreg_lm_params* prm,
-                  lisreg_lm_result* d_res, lisreg_lm_iter* d_logs) {
+static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, double alg_bytes_per_iter, float* d_pose,
+                  const lisreg_lm_params* prm, lisreg_lm_result* d_res, lisreg_lm_iter* d_logs) {
   cudaStream_t st = ctx->stream;
   int rc = sync_maps(ctx);
   if (rc) return rc;
   LmParamsDev dp; to_dev_params(prm, &dp);
   // tile size: big batches amortise the 27-term reduction over 4 queries per thread; a lone
   // registration is spread over as many SMs as possible
-  const int tile_pts = (B >= 32) ? LM_THREADS * 4 : LM_THREADS;
+  const int tile_pts = (B >= 32) ? LM_MAX_TILE : LM_THREADS;
   const int max_tiles = std::max(1, (max_n + tile_pts - 1) / tile_pts);
   CK(ctx->d_states.reserve(sizeof(RegState) * (size_t)B));
   CK(ctx->d_partials.reserve(sizeof(double) * LM_NSUM * (size_t)B * max_tiles));
@@ -411,8 +462,13 @@ static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, flo
   int* tickets = (int*)ctx->d_tickets.p;
   k_lm_init<<<(B + 127) / 128, 128, 0, st>>>(d_descs, states, d_pose, dp, tickets, B); LAUNCH_CK();
   dim3 grid(max_tiles, B);
-  for (int it = 0; it < dp.max_iters; it++) {
-    k_lm_iter<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp, partials, tickets, d_logs, max_tiles, tile_pts); LAUNCH_CK();
+  {
+    ProfScope ps(ctx, PROF_LM, alg_bytes_per_iter * dp.max_iters, dp.max_iters);
+    for (int it = 0; it < dp.max_iters; it++) {
+      k_lm_iter<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp, partials, max_tiles, tile_pts); LAUNCH_CK();
+      k_lm_solve<<<(B + LM_SOLVE_THREADS / 32 - 1) / (LM_SOLVE_THREADS / 32), LM_SOLVE_THREADS, 0, st>>>(
+          d_descs, states, dp, partials, d_logs, max_tiles, tile_pts, B); LAUNCH_CK();
+    }
   }
   k_lm_finish<<<(B + 127) / 128, 128, 0, st>>>(states, d_pose, d_res, B); LAUNCH_CK();
   return LISREG_OK;
@@ -423,21 +479,24 @@ int32_t lisreg_scan2map_batch_dev(lisreg_ctx* ctx, int32_t B, const lisreg_batch
   if (!ctx || B <= 0 || !items || !d_pose6xB || !prm || !d_resxB) return fail(ctx, LISREG_ERR_ARG, "lisreg_scan2map_batch_dev: bad argument");
   if (prm->max_iters <= 0 || prm->max_iters > LISREG_MAX_ITERS) return fail(ctx, LISREG_ERR_ARG, "max_iters must be in 1..%d", LISREG_MAX_ITERS);
   CK(cudaSetDevice(ctx->device));
-  CK(ctx->h_stage.reserve(sizeof(RegDesc) * (size_t)B));
   CK(ctx->d_descs.reserve(sizeof(RegDesc) * (size_t)B));
-  RegDesc* h = (RegDesc*)ctx->h_stage.p;
-  int max_n = 0;
+  // pageable staging on purpose: cudaMemcpyAsync returns once a pageable source has been
+  // consumed, so back-to-back asynchronous calls cannot race on the descriptor staging
+  std::vector<RegDesc> hvec((size_t)B);
+  RegDesc* h = hvec.data();
+  int max_n = 0; double alg = 0;
   for (int b = 0; b < B; b++) {
     const lisreg_batch_item& it = items[b];
     if (it.nc < 0 || it.ns < 0 || it.map_id < 0 || it.map_id >= (int)ctx->maps.size() || !ctx->maps[it.map_id].used)
       return fail(ctx, LISREG_ERR_ARG, "batch item %d: bad sizes or map id", b);
+    alg += 96.0 * (it.nc + it.ns);
     h[b].corner = (const float4*)it.corner; h[b].surf = (const float4*)it.surf;
     h[b].clabel = it.clabel; h[b].slabel = it.slabel; h[b].nc = it.nc; h[b].ns = it.ns; h[b].map_slot = it.map_id; h[b].pad = 0;
     max_n = std::max(max_n, it.nc + it.ns);
   }
   CK(cudaMemcpyAsync(ctx->d_descs.p, h, sizeof(RegDesc) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
   lisreg_lm_iter* d_logs = nullptr;
-  return run_lm(ctx, B, (const RegDesc*)ctx->d_descs.p, max_n, d_pose6xB, prm, d_resxB, d_logs);
+  return run_lm(ctx, B, (const RegDesc*)ctx->d_descs.p, max_n, alg, d_pose6xB, prm, d_resxB, d_logs);
 }
 
 int32_t lisreg_scan2map_batch(lisreg_ctx* ctx, int32_t B, const lisreg_batch_item* items, float* pose6xB,
@@ -452,7 +511,7 @@ int32_t lisreg_scan2map_batch(lisreg_ctx* ctx, int32_t B, const lisreg_batch_ite
   const size_t o_desc = take(sizeof(RegDesc) * (size_t)B);
   const size_t o_pose = take(sizeof(float) * 6 * (size_t)B);
   std::vector<size_t> oc(B), os(B), ocl(B), osl(B);
-  int max_n = 0;
+  int max_n = 0; double alg = 0;
   for (int b = 0; b < B; b++) {
     const lisreg_batch_item& it = items[b];
     if (it.nc < 0 || it.ns < 0 || (it.nc > 0 && !it.corner) || (it.ns > 0 && !it.surf) ||
@@ -462,7 +521,7 @@ int32_t lisreg_scan2map_batch(lisreg_ctx* ctx, int32_t B, const lisreg_batch_ite
     os[b] = take(sizeof(float4) * (size_t)it.ns);
     ocl[b] = it.clabel ? take(sizeof(uint16_t) * (size_t)it.nc) : (size_t)-1;
     osl[b] = it.slabel ? take(sizeof(uint16_t) * (size_t)it.ns) : (size_t)-1;
-    max_n = std::max(max_n, it.nc + it.ns);
+    max_n = std::max(max_n, it.nc + it.ns); alg += 96.0 * (it.nc + it.ns);
   }
   const size_t total = off;
   CK(ctx->h_stage.reserve(total));
@@ -490,7 +549,7 @@ int32_t lisreg_scan2map_batch(lisreg_ctx* ctx, int32_t B, const lisreg_batch_ite
     d_logs = (lisreg_lm_iter*)ctx->d_logs.p;
     CK(cudaMemsetAsync(d_logs, 0, sizeof(lisreg_lm_iter) * (size_t)B * LISREG_MAX_ITERS, st));
   }
-  int rc = run_lm(ctx, B, (const RegDesc*)(d + o_desc), max_n, (float*)(d + o_pose), prm, (lisreg_lm_result*)ctx->d_res.p, d_logs);
+  int rc = run_lm(ctx, B, (const RegDesc*)(d + o_desc), max_n, alg, (float*)(d + o_pose), prm, (lisreg_lm_result*)ctx->d_res.p, d_logs);
   if (rc) return rc;
   CK(ctx->h_out.reserve(sizeof(lisreg_lm_result) * (size_t)B + (want_log ? sizeof(lisreg_lm_iter) * (size_t)B * LISREG_MAX_ITERS : 0)));
   CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_res.p, sizeof(lisreg_lm_result) * (size_t)B, cudaMemcpyDeviceToHost, st));
@@ -511,6 +570,94 @@ int32_t lisreg_scan2map_batch(lisreg_ctx* ctx, int32_t B, const lisreg_batch_ite
       memcpy(iter_log + (size_t)b * prm->max_iters, hl + (size_t)b * LISREG_MAX_ITERS, sizeof(lisreg_lm_iter) * (size_t)prm->max_iters);
   }
   return worst;
+}
+
+int32_t lisreg_scan2map_batch_arena(lisreg_ctx* ctx, int32_t B, const lisreg_batch_item* items, const void* host_arena,
+                                    uint64_t arena_bytes, float* pose6xB, const lisreg_lm_params* prm, lisreg_lm_result* resxB) {
+  if (!ctx || B <= 0 || !items || !host_arena || !pose6xB || !prm || !resxB) return fail(ctx, LISREG_ERR_ARG, "lisreg_scan2map_batch_arena: bad argument");
+  if (prm->max_iters <= 0 || prm->max_iters > LISREG_MAX_ITERS) return fail(ctx, LISREG_ERR_ARG, "max_iters must be in 1..%d", LISREG_MAX_ITERS);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t head = ((sizeof(RegDesc) * (size_t)B + 15) & ~size_t(15)) + ((sizeof(float) * 6 * (size_t)B + 15) & ~size_t(15));
+  CK(ctx->h_stage.reserve(head));
+  CK(ctx->d_stage.reserve(head + (size_t)arena_bytes + 16));
+  char* h = (char*)ctx->h_stage.p; char* d = (char*)ctx->d_stage.p;
+  char* d_arena = d + head;
+  RegDesc* hd = (RegDesc*)h;
+  float* hp = (float*)(h + ((sizeof(RegDesc) * (size_t)B + 15) & ~size_t(15)));
+  memcpy(hp, pose6xB, sizeof(float) * 6 * (size_t)B);
+  int max_n = 0; double alg = 0;
+  for (int b = 0; b < B; b++) {
+    const lisreg_batch_item& it = items[b];
+    const size_t oc = (size_t)it.corner, os = (size_t)it.surf, ocl = (size_t)it.clabel, osl = (size_t)it.slabel;
+    if (it.nc < 0 || it.ns < 0 || it.map_id < 0 || it.map_id >= (int)ctx->maps.size() || !ctx->maps[it.map_id].used ||
+        (oc & 15) || (os & 15) || oc + 16ull * it.nc > arena_bytes || os + 16ull * it.ns > arena_bytes ||
+        (ocl != (size_t)-1 && ocl + 2ull * it.nc > arena_bytes) || (osl != (size_t)-1 && osl + 2ull * it.ns > arena_bytes))
+      return fail(ctx, LISREG_ERR_ARG, "arena item %d: bad sizes, offsets or map id", b);
+    hd[b].corner = (const float4*)(d_arena + oc); hd[b].surf = (const float4*)(d_arena + os);
+    hd[b].clabel = ocl != (size_t)-1 ? (const uint16_t*)(d_arena + ocl) : nullptr;
+    hd[b].slabel = osl != (size_t)-1 ? (const uint16_t*)(d_arena + osl) : nullptr;
+    hd[b].nc = it.nc; hd[b].ns = it.ns; hd[b].map_slot = it.map_id; hd[b].pad = 0;
+    max_n = std::max(max_n, it.nc + it.ns); alg += 96.0 * (it.nc + it.ns);
+  }
+  CK(cudaMemcpyAsync(d, h, head, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_arena, host_arena, (size_t)arena_bytes, cudaMemcpyHostToDevice, st));
+  CK(ctx->d_res.reserve(sizeof(lisreg_lm_result) * (size_t)B));
+  float* d_pose = (float*)(d + ((sizeof(RegDesc) * (size_t)B + 15) & ~size_t(15)));
+  int rc = run_lm(ctx, B, (const RegDesc*)d, max_n, alg, d_pose, prm, (lisreg_lm_result*)ctx->d_res.p, nullptr);
+  if (rc) return rc;
+  CK(ctx->h_out.reserve(sizeof(lisreg_lm_result) * (size_t)B));
+  CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_res.p, sizeof(lisreg_lm_result) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const lisreg_lm_result* hr = (const lisreg_lm_result*)ctx->h_out.p;
+  int worst = LISREG_OK;
+  for (int b = 0; b < B; b++) {
+    resxB[b] = hr[b];
+    memcpy(pose6xB + 6 * (size_t)b, hr[b].pose, sizeof(float) * 6);
+    worst = std::max(worst, hr[b].status);
+  }
+  return worst;
+}
+
+int32_t lisreg_selftest_smallmat(lisreg_ctx* ctx, const float* A36, const float* b6, float* out98) {
+  if (!ctx || !A36 || !b6 || !out98) return LISREG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->d_stage.reserve(sizeof(float) * (36 + 6 + 98)));
+  float* d = (float*)ctx->d_stage.p;
+  CK(cudaMemcpyAsync(d, A36, sizeof(float) * 36, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d + 36, b6, sizeof(float) * 6, cudaMemcpyHostToDevice, ctx->stream));
+  k_selftest_smallmat<<<1, 32, 0, ctx->stream>>>(d, d + 36, d + 42); LAUNCH_CK();
+  CK(cudaMemcpyAsync(out98, d + 42, sizeof(float) * 98, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LISREG_OK;
+}
+
+int32_t lisreg_profile_enable(lisreg_ctx* ctx, int32_t on) {
+  if (!ctx) return LISREG_ERR_ARG;
+  ctx->prof_on = on != 0;
+  return LISREG_OK;
+}
+
+int32_t lisreg_profile_get(lisreg_ctx* ctx, lisreg_profile* out, int32_t reset) {
+  if (!ctx || !out) return LISREG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (auto& p : ctx->ev_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      switch (p.kind) {
+        case PROF_LM:    ctx->prof.lm_iter_ms += ms; ctx->prof.lm_iter_launches += p.launches; ctx->prof.lm_alg_bytes += p.bytes; break;
+        case PROF_FEAT:  ctx->prof.feat_ms += ms; ctx->prof.feat_launches += p.launches; ctx->prof.feat_alg_bytes += p.bytes; break;
+        case PROF_VOXEL: ctx->prof.voxel_ms += ms; ctx->prof.voxel_launches += p.launches; ctx->prof.voxel_alg_bytes += p.bytes; break;
+        default:         ctx->prof.index_ms += ms; ctx->prof.index_launches += p.launches; ctx->prof.index_alg_bytes += p.bytes; break;
+      }
+    }
+    ctx->ev_free.push_back(p.a); ctx->ev_free.push_back(p.b);
+  }
+  ctx->ev_pending.clear();
+  *out = ctx->prof;
+  if (reset) ctx->prof = lisreg_profile{};
+  return LISREG_OK;
 }
 
 int32_t lisreg_scan2map(lisreg_ctx* ctx, int32_t map_id, const float* corner, const uint16_t* clabel, int32_t nc,

@@ -75,8 +75,8 @@ LISREG_HD __forceinline__ bool corner_coeff(float x0, float y0, float z0, const 
     a11 += ax * ax; a12 += ax * ay; a13 += ax * az; a22 += ay * ay; a23 += ay * az; a33 += az * az;
   }
   a11 /= 5; a12 /= 5; a13 /= 5; a22 /= 5; a23 /= 5; a33 /= 5;
-  float A[9] = {a11, a12, a13, a12, a22, a23, a13, a23, a33}, W[3], V[9];
-  jacobi_eigen<3>(A, W, V);
+  float W[3], V[9];
+  jacobi_eigen3(a11, a12, a13, a22, a23, a33, W, V);
   if (!(W[0] > 3 * W[1])) return false;
   float x1 = (float)((double)cx + 0.1 * (double)V[0]), y1 = (float)((double)cy + 0.1 * (double)V[1]), z1 = (float)((double)cz + 0.1 * (double)V[2]);
   float x2 = (float)((double)cx - 0.1 * (double)V[0]), y2 = (float)((double)cy - 0.1 * (double)V[1]), z2 = (float)((double)cz - 0.1 * (double)V[2]);
@@ -117,8 +117,15 @@ LISREG_HD __forceinline__ bool surf_coeff(float x0, float y0, float z0, const fl
   return (double)s > 0.1;
 }
 
+// scratch of the 6x6 solve; lives in SHARED memory on the device (one per solving warp)
+struct SolveScratch {
+  float AtA[36], a[36], V[36], V2[36], Vinv[36], matP[36];
+  float AtB[6], X[6], X2[6], E[6];
+  int indR[6], indC[6];
+};
+
 // LMOptimization tail (:869-973) run by one thread once all tiles of a registration are in.
-LISREG_HD inline void lm_solve_tail(RegState& st, const LmParamsDev& prm, const double* sums, lisreg_lm_iter* log) {
+LISREG_HD inline void lm_solve_tail(RegState& st, const LmParamsDev& prm, const double* sums, lisreg_lm_iter* log, SolveScratch& sc) {
   const int nC = (int)sums[27], nS = (int)sums[28], nSel = nC + nS;
   const int iter = st.iter;
   st.n_sel_last = nSel;
@@ -131,56 +138,48 @@ LISREG_HD inline void lm_solve_tail(RegState& st, const LmParamsDev& prm, const 
   if (nSel < prm.min_sel) {
     st.any_small = 1;
   } else {
-    float AtA[36], AtB[6], X[6];
     int q = 0;
-    for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) { AtA[r * 6 + c] = AtA[c * 6 + r] = (float)sums[q]; q++; }
-    for (int r = 0; r < 6; r++) AtB[r] = (float)sums[21 + r];
-    {
-      float a[36];
-      for (int i = 0; i < 36; i++) a[i] = AtA[i];
-      for (int i = 0; i < 6; i++) X[i] = AtB[i];
-      if (!qr_solve<6>(a, X)) for (int i = 0; i < 6; i++) X[i] = 0.f;
-    }
-    float matP[36];
-    for (int i = 0; i < 36; i++) matP[i] = 0.f;   // Q1: local all-zero matP on iterations >= 1
+    for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) { sc.AtA[r * 6 + c] = sc.AtA[c * 6 + r] = (float)sums[q]; q++; }
+    for (int r = 0; r < 6; r++) sc.AtB[r] = (float)sums[21 + r];
+    for (int i = 0; i < 36; i++) sc.a[i] = sc.AtA[i];
+    for (int i = 0; i < 6; i++) sc.X[i] = sc.AtB[i];
+    if (!qr_solve<6>(sc.a, sc.X)) for (int i = 0; i < 6; i++) sc.X[i] = 0.f;
+    for (int i = 0; i < 36; i++) sc.matP[i] = 0.f;   // Q1: local all-zero matP on iterations >= 1
     if (iter == 0) {
-      float a[36], E[6], V[36], V2[36];
-      for (int i = 0; i < 36; i++) a[i] = AtA[i];
-      jacobi_eigen<6>(a, E, V);
-      for (int i = 0; i < 36; i++) V2[i] = V[i];
+      for (int i = 0; i < 36; i++) sc.a[i] = sc.AtA[i];
+      jacobi_eigen<6>(sc.a, sc.E, sc.V, sc.indR, sc.indC);
+      for (int i = 0; i < 36; i++) sc.V2[i] = sc.V[i];
       st.degenerate = 0;
       for (int i = 5; i >= 0; i--) {
-        if (E[i] < prm.degenerate_eig) { for (int j = 0; j < 6; j++) V2[i * 6 + j] = 0.f; st.degenerate = 1; }
+        if (sc.E[i] < prm.degenerate_eig) { for (int j = 0; j < 6; j++) sc.V2[i * 6 + j] = 0.f; st.degenerate = 1; }
         else break;
       }
       if (st.degenerate) {   // matP = matV.inv() * matV2 (:945); only consumed when degenerate
-        float Vc[36], Vinv[36];
-        for (int i = 0; i < 36; i++) { Vc[i] = V[i]; Vinv[i] = 0.f; }
-        for (int i = 0; i < 6; i++) Vinv[i * 6 + i] = 1.f;
-        if (!lu_solve<6, 6>(Vc, Vinv)) for (int i = 0; i < 36; i++) Vinv[i] = 0.f;
+        for (int i = 0; i < 36; i++) { sc.a[i] = sc.V[i]; sc.Vinv[i] = 0.f; }
+        for (int i = 0; i < 6; i++) sc.Vinv[i * 6 + i] = 1.f;
+        if (!lu_solve<6, 6>(sc.a, sc.Vinv)) for (int i = 0; i < 36; i++) sc.Vinv[i] = 0.f;
         for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) {
-          double s = 0; for (int k = 0; k < 6; k++) s += (double)Vinv[r * 6 + k] * (double)V2[k * 6 + c];
-          matP[r * 6 + c] = (float)s;
+          double s = 0; for (int k = 0; k < 6; k++) s += (double)sc.Vinv[r * 6 + k] * (double)sc.V2[k * 6 + c];
+          sc.matP[r * 6 + c] = (float)s;
         }
       }
     }
     if (st.degenerate) {
-      float X2[6];
-      for (int i = 0; i < 6; i++) X2[i] = X[i];
-      for (int r = 0; r < 6; r++) { double s = 0; for (int k = 0; k < 6; k++) s += (double)matP[r * 6 + k] * (double)X2[k]; X[r] = (float)s; }
+      for (int i = 0; i < 6; i++) sc.X2[i] = sc.X[i];
+      for (int r = 0; r < 6; r++) { double s = 0; for (int k = 0; k < 6; k++) s += (double)sc.matP[r * 6 + k] * (double)sc.X2[k]; sc.X[r] = (float)s; }
     }
-    for (int r = 0; r < 6; r++) st.pose[r] += X[r];
+    for (int r = 0; r < 6; r++) st.pose[r] += sc.X[r];
     const float r2d = 57.29578f;
-    double r0 = (double)(X[0] * r2d), r1 = (double)(X[1] * r2d), r2 = (double)(X[2] * r2d);
-    double t0 = (double)(X[3] * 100), t1 = (double)(X[4] * 100), t2 = (double)(X[5] * 100);
+    double r0 = (double)(sc.X[0] * r2d), r1 = (double)(sc.X[1] * r2d), r2 = (double)(sc.X[2] * r2d);
+    double t0 = (double)(sc.X[3] * 100), t1 = (double)(sc.X[4] * 100), t2 = (double)(sc.X[5] * 100);
     float dR = (float)sqrt(r0 * r0 + r1 * r1 + r2 * r2);
     float dT = (float)sqrt(t0 * t0 + t1 * t1 + t2 * t2);
     st.deltaR = dR; st.deltaT = dT;
     converged = ((double)dR < (double)prm.conv_rot) && ((double)dT < (double)prm.conv_trans);
     st.converged = converged ? 1 : 0;
     if (log) {
-      for (int i = 0; i < 36; i++) log->AtA[i] = AtA[i];
-      for (int i = 0; i < 6; i++) { log->AtB[i] = AtB[i]; log->X[i] = X[i]; log->pose[i] = st.pose[i]; }
+      for (int i = 0; i < 36; i++) log->AtA[i] = sc.AtA[i];
+      for (int i = 0; i < 6; i++) { log->AtB[i] = sc.AtB[i]; log->X[i] = sc.X[i]; log->pose[i] = st.pose[i]; }
       log->solved = 1; log->deltaR = dR; log->deltaT = dT;
     }
   }
@@ -224,17 +223,34 @@ __global__ void k_lm_finish(const RegState* __restrict__ states, float* __restri
   res[b] = r;
 }
 
-__global__ void __launch_bounds__(LM_THREADS)
+// Row/column of the 27 accumulated products: lanes 0..20 = upper triangle of A^T A (row-major),
+// lanes 21..26 = A^T b (column 6 of the stored row is b).
+__device__ __forceinline__ void lm_pair_of_lane(int lane, int& r, int& c) {
+  if (lane >= 21) { r = lane - 21; c = 6; return; }
+  // row starts of the row-major upper triangle: 0, 6, 11, 15, 18, 20
+  const int rr = (lane >= 6) + (lane >= 11) + (lane >= 15) + (lane >= 18) + (lane >= 20);
+  const int base = rr == 0 ? 0 : rr == 1 ? 6 : rr == 2 ? 11 : rr == 3 ? 15 : rr == 4 ? 18 : 20;
+  r = rr; c = rr + (lane - base);
+}
+
+constexpr int LM_MAX_TILE = 512;
+
+// One Gauss-Newton iteration for every registration of the batch.  grid = (tiles, B).
+// Phase A (registers: search state only): transform + exact gated 5-NN, neighbour positions -> smem.
+// Phase B (registers: coefficient math only): line/plane coefficient + Jacobian row -> smem.
+// Phase C: each warp reduces a quarter of the tile's rows, lane p owning one of the 27 products
+//          (fp64, fixed order => deterministic), then block partial -> global; the last block of a
+//          registration sums the tile partials in order and runs the 6x6 solve.
+__global__ void __launch_bounds__(LM_THREADS, 5)
 k_lm_iter(const RegDesc* __restrict__ descs, RegState* __restrict__ states, const MapDev* __restrict__ maps,
-          LmParamsDev prm, double* __restrict__ partials, int* __restrict__ tickets,
-          lisreg_lm_iter* __restrict__ logs, int max_tiles, int tile_pts) {
+          LmParamsDev prm, double* __restrict__ partials, int max_tiles, int tile_pts) {
   const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
   __shared__ RegDesc sd;
   __shared__ float sT[12], sTrig[6];
   __shared__ int sdone;
+  __shared__ int s_pos[5 * LM_MAX_TILE];
+  __shared__ float s_row[7 * LM_MAX_TILE];
   __shared__ double swarp[LM_THREADS / 32][LM_NSUM];
-  __shared__ double stot[LM_NSUM];
-  __shared__ int slast;
   if (tid == 0) { sd = descs[b]; sdone = states[b].done; }
   if (tid < 12) sT[tid] = states[b].T[tid];
   if (tid >= 32 && tid < 38) sTrig[tid - 32] = states[b].trig[tid - 32];
@@ -244,86 +260,98 @@ k_lm_iter(const RegDesc* __restrict__ descs, RegState* __restrict__ states, cons
   const int ntiles = (n + tile_pts - 1) / tile_pts;
   if (tile >= ntiles) return;
   const MapDev& mp = maps[sd.map_slot];
+  const int q0 = tile * tile_pts;
+  const int qn = min(n - q0, tile_pts);   // queries in this tile
 
-  double acc[27];
-#pragma unroll
-  for (int i = 0; i < 27; i++) acc[i] = 0.0;
-  int cntC = 0, cntS = 0;
-  const float srx = sTrig[0], crx = sTrig[1], sry = sTrig[2], cry = sTrig[3], srz = sTrig[4], crz = sTrig[5];
-
-  const int qend = min(n, (tile + 1) * tile_pts);
-  for (int q = tile * tile_pts + tid; q < qend; q += LM_THREADS) {
-    const bool is_corner = q < sd.nc;
-    const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
-    // pointAssociateToMap (:243-258)
-    const float x0 = sT[0] * p.x + sT[1] * p.y + sT[2] * p.z + sT[3];
-    const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
-    const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
-    float bd[5]; int bi[5], bp[5];
-#ifdef LISREG_V3
-    const GridDev g = is_corner ? mp.corner : mp.surf;
-    const float gate_l = prm.gate;
-    knn5_grid(g, x0, y0, z0, gate_l, bd, bi, bp);
-#else
-    const GridDev& g = is_corner ? mp.corner : mp.surf;
-    knn5_grid(g, x0, y0, z0, prm.gate, bd, bi, bp);
-#endif
-#ifdef LISREG_DEBUG
-    if (q < 3 || q == sd.nc) printf("q=%d nc=%d ns=%d slot=%d g.n=%d h=%f dims=%d %d %d p=(%f %f %f) x=(%f %f %f) T0=%f T3=%f bd4=%f bp4=%d gate=%f o=(%f %f %f) invh=%f bd0=%f bp0=%d\n", q, sd.nc, sd.ns, sd.map_slot, g.n, g.h, g.nx, g.ny, g.nz, p.x, p.y, p.z, x0, y0, z0, sT[0], sT[3], bd[4], bp[4], prm.gate, g.ox, g.oy, g.oz, g.inv_h, bd[0], bp[0]);
-#endif
-    if (!(bd[4] < prm.gate) || bp[4] < 0) continue;
-    float4 nb[5];
-#pragma unroll
-    for (int j = 0; j < 5; j++) nb[j] = __ldg(&g.pts[bp[j]]);
-    float raw[5];
-    const bool ok = is_corner ? corner_coeff(x0, y0, z0, nb, raw) : surf_coeff(x0, y0, z0, nb, raw);
-    if (!ok) continue;
-    float w = 1.0f;
-    if (prm.use_w) {   // subMapOptmizationNode.cpp:1669, :1793
-      const uint16_t* lab = is_corner ? sd.clabel : sd.slabel;
-      unsigned l = lab ? lab[is_corner ? q : q - sd.nc] : 0u;
-      float sc = l < LISREG_LUT_SIZE ? prm.label_score[l] : 0.f;
-      w = (float)(2.0 - (double)sc);
+  // ---------------- phase A: 5-NN ----------------
+  for (int l = tid; l < tile_pts; l += LM_THREADS) {
+    int accepted = 0;
+    knn_key best[5];
+    if (l < qn) {
+      const int q = q0 + l;
+      const bool is_corner = q < sd.nc;
+      const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
+      // pointAssociateToMap (:243-258)
+      const float x0 = sT[0] * p.x + sT[1] * p.y + sT[2] * p.z + sT[3];
+      const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
+      const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
+      const GridDev& g = is_corner ? mp.corner : mp.surf;
+      knn5_grid(g, x0, y0, z0, prm.gate, best);
+      accepted = knn_key_d(best[4]) < prm.gate;
     }
-    const float ws = w * raw[4];
-    const float c_x = ws * raw[0], c_y = ws * raw[1], c_z = ws * raw[2], c_i = ws * raw[3];
-    if (is_corner) cntC++; else cntS++;
-    // LMOptimization row (:888-915): lidar -> camera permutation
-    const float px = p.y, py = p.z, pz = p.x;
-    const float cx = c_y, cy = c_z, cz = c_x;
-    const float arx = (crx * sry * srz * px + crx * crz * sry * py - srx * sry * pz) * cx +
-                      (-srx * srz * px - crz * srx * py - crx * pz) * cy +
-                      (crx * cry * srz * px + crx * cry * crz * py - cry * srx * pz) * cz;
-    const float ary = ((cry * srx * srz - crz * sry) * px + (sry * srz + cry * crz * srx) * py + crx * cry * pz) * cx +
-                      ((-cry * crz - srx * sry * srz) * px + (cry * srz - crz * srx * sry) * py - crx * sry * pz) * cz;
-    const float arz = ((crz * srx * sry - cry * srz) * px + (-cry * crz - srx * sry * srz) * py) * cx +
-                      (crx * crz * px - crx * srz * py) * cy +
-                      ((sry * srz + cry * crz * srx) * px + (crz * sry - cry * srx * srz) * py) * cz;
-    const double row[6] = {(double)arz, (double)arx, (double)ary, (double)cz, (double)cx, (double)cy};
-    const double bb = -(double)c_i;
-    int k = 0;
+    if (accepted) {
 #pragma unroll
-    for (int r = 0; r < 6; r++)
-#pragma unroll
-      for (int c = r; c < 6; c++) { acc[k] += row[r] * row[c]; k++; }
-#pragma unroll
-    for (int r = 0; r < 6; r++) acc[21 + r] += row[r] * bb;
+      for (int j = 0; j < 5; j++) s_pos[j * LM_MAX_TILE + l] = knn_key_pos(best[j]);
+    } else {
+      s_pos[l] = -1;
+    }
   }
 
-  // warp reduce -> smem -> per-block partial (fixed order => deterministic)
-  const int lane = tid & 31, wid = tid >> 5;
+  // ---------------- phase B: coefficients + Jacobian rows ----------------
+  const float srx = sTrig[0], crx = sTrig[1], sry = sTrig[2], cry = sTrig[3], srz = sTrig[4], crz = sTrig[5];
+  int cntC = 0, cntS = 0;
+  for (int l = tid; l < tile_pts; l += LM_THREADS) {
+    float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int pos0 = s_pos[l];
+    if (pos0 >= 0) {
+      const int q = q0 + l;
+      const bool is_corner = q < sd.nc;
+      const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
+      const float x0 = sT[0] * p.x + sT[1] * p.y + sT[2] * p.z + sT[3];
+      const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
+      const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
+      const float4* __restrict__ pts = is_corner ? mp.corner.pts : mp.surf.pts;
+      float4 nb[5];
+      nb[0] = __ldg(&pts[pos0]);
 #pragma unroll
-  for (int i = 0; i < 27; i++) {
-    double v = acc[i];
+      for (int j = 1; j < 5; j++) nb[j] = __ldg(&pts[s_pos[j * LM_MAX_TILE + l]]);
+      float raw[5];
+      const bool ok = is_corner ? corner_coeff(x0, y0, z0, nb, raw) : surf_coeff(x0, y0, z0, nb, raw);
+      if (ok) {
+        float w = 1.0f;
+        if (prm.use_w) {   // subMapOptmizationNode.cpp:1669, :1793
+          const uint16_t* lab = is_corner ? sd.clabel : sd.slabel;
+          unsigned lb = lab ? lab[is_corner ? q : q - sd.nc] : 0u;
+          float sc = lb < LISREG_LUT_SIZE ? prm.label_score[lb] : 0.f;
+          w = (float)(2.0 - (double)sc);
+        }
+        const float ws = w * raw[4];
+        const float c_x = ws * raw[0], c_y = ws * raw[1], c_z = ws * raw[2], c_i = ws * raw[3];
+        if (is_corner) cntC++; else cntS++;
+        // LMOptimization row (:888-915): lidar -> camera permutation
+        const float px = p.y, py = p.z, pz = p.x;
+        const float cx = c_y, cy = c_z, cz = c_x;
+        const float arx = (crx * sry * srz * px + crx * crz * sry * py - srx * sry * pz) * cx +
+                          (-srx * srz * px - crz * srx * py - crx * pz) * cy +
+                          (crx * cry * srz * px + crx * cry * crz * py - cry * srx * pz) * cz;
+        const float ary = ((cry * srx * srz - crz * sry) * px + (sry * srz + cry * crz * srx) * py + crx * cry * pz) * cx +
+                          ((-cry * crz - srx * sry * srz) * px + (cry * srz - crz * srx * sry) * py - crx * sry * pz) * cz;
+        const float arz = ((crz * srx * sry - cry * srz) * px + (-cry * crz - srx * sry * srz) * py) * cx +
+                          (crx * crz * px - crx * srz * py) * cy +
+                          ((sry * srz + cry * crz * srx) * px + (crz * sry - cry * srx * srz) * py) * cz;
+        row[0] = arz; row[1] = arx; row[2] = ary; row[3] = cz; row[4] = cx; row[5] = cy; row[6] = -c_i;
+      }
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) swarp[wid][i] = v;
+    for (int k = 0; k < 7; k++) s_row[k * LM_MAX_TILE + l] = row[k];
   }
+  __syncthreads();
+
+  // ---------------- phase C: 27 products, fp64 ----------------
+  const int lane = tid & 31, wid = tid >> 5;
   {
-    int c = cntC, s2 = cntS;
+    int r, c;
+    lm_pair_of_lane(lane < 27 ? lane : 0, r, c);
+    const int per_warp = tile_pts / (LM_THREADS / 32);
+    const float* __restrict__ ra = s_row + r * LM_MAX_TILE + wid * per_warp;
+    const float* __restrict__ rc = s_row + c * LM_MAX_TILE + wid * per_warp;
+    double v = 0.0;
+    for (int i = 0; i < per_warp; i++) v += (double)ra[i] * (double)rc[i];
+    if (lane < 27) swarp[wid][lane] = v;
+    int cc = cntC, s2 = cntS;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { c += __shfl_down_sync(0xffffffffu, c, o); s2 += __shfl_down_sync(0xffffffffu, s2, o); }
-    if (lane == 0) { swarp[wid][27] = (double)c; swarp[wid][28] = (double)s2; }
+    for (int o = 16; o > 0; o >>= 1) { cc += __shfl_down_sync(0xffffffffu, cc, o); s2 += __shfl_down_sync(0xffffffffu, s2, o); }
+    if (lane == 0) { swarp[wid][27] = (double)cc; swarp[wid][28] = (double)s2; }
   }
   __syncthreads();
   double* mypart = partials + ((size_t)b * max_tiles + tile) * LM_NSUM;
@@ -332,30 +360,62 @@ k_lm_iter(const RegDesc* __restrict__ descs, RegState* __restrict__ states, cons
 #pragma unroll
     for (int w2 = 0; w2 < LM_THREADS / 32; w2++) v += swarp[w2][tid];
     mypart[tid] = v;
-    __threadfence();
   }
-  __syncthreads();
-  if (tid == 0) {
-    int t = atomicAdd(&tickets[b], 1);
-    slast = (t == ntiles - 1);
-  }
-  __syncthreads();
-  if (!slast) return;
-  __threadfence();
-  if (tid < 29) {
+}
+
+// LMOptimization tail: one warp per registration sums the tile partials in tile order (fixed
+// order => bit-reproducible) and lane 0 runs the 6x6 solve / degeneracy / pose update.
+// Kept out of k_lm_iter so that the hot kernel has no large stack frame or cold code.
+constexpr int LM_SOLVE_THREADS = 128;
+__global__ void __launch_bounds__(LM_SOLVE_THREADS)
+k_lm_solve(const RegDesc* __restrict__ descs, RegState* __restrict__ states, LmParamsDev prm,
+           const double* __restrict__ partials, lisreg_lm_iter* __restrict__ logs, int max_tiles, int tile_pts, int B) {
+  __shared__ double stot[LM_SOLVE_THREADS / 32][LM_NSUM];
+  __shared__ SolveScratch ssc[LM_SOLVE_THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = blockIdx.x * (LM_SOLVE_THREADS / 32) + wid;
+  if (b >= B) return;
+  if (states[b].done) return;
+  const int n = descs[b].nc + descs[b].ns;
+  const int ntiles = (n + tile_pts - 1) / tile_pts;
+  if (lane < 29) {
     double v = 0.0;
-    const double* base = partials + (size_t)b * max_tiles * LM_NSUM + tid;
-    for (int t = 0; t < ntiles; t++) v += __ldcg(base + (size_t)t * LM_NSUM);
-    stot[tid] = v;
+    const double* base = partials + (size_t)b * max_tiles * LM_NSUM + lane;
+    for (int t = 0; t < ntiles; t++) v += base[(size_t)t * LM_NSUM];
+    stot[wid][lane] = v;
   }
-  __syncthreads();
-  if (tid == 0) {
+  __syncwarp();
+  if (lane == 0) {
     RegState st = states[b];
     lisreg_lm_iter* lg = logs ? &logs[(size_t)b * LISREG_MAX_ITERS + st.iter] : nullptr;
-    lm_solve_tail(st, prm, stot, lg);
+    lm_solve_tail(st, prm, stot[wid], lg, ssc[wid]);
     states[b] = st;
-    tickets[b] = 0;
   }
+}
+
+// self-test of the small dense routines on the device (lisreg_selftest_smallmat)
+__global__ void k_selftest_smallmat(const float* __restrict__ A36, const float* __restrict__ b6, float* __restrict__ out) {
+  __shared__ SolveScratch sc;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int i = 0; i < 36; i++) sc.a[i] = A36[i];
+  jacobi_eigen<6>(sc.a, sc.E, sc.V, sc.indR, sc.indC);
+  for (int i = 0; i < 6; i++) out[i] = sc.E[i];
+  for (int i = 0; i < 36; i++) out[6 + i] = sc.V[i];
+  for (int i = 0; i < 36; i++) sc.a[i] = A36[i];
+  for (int i = 0; i < 6; i++) sc.X[i] = b6[i];
+  int ok = qr_solve<6>(sc.a, sc.X);
+  for (int i = 0; i < 6; i++) out[42 + i] = sc.X[i];
+  out[48] = (float)ok;
+  for (int i = 0; i < 36; i++) { sc.a[i] = A36[i]; sc.Vinv[i] = 0.f; }
+  for (int i = 0; i < 6; i++) sc.Vinv[i * 6 + i] = 1.f;
+  ok = lu_solve<6, 6>(sc.a, sc.Vinv);
+  for (int i = 0; i < 36; i++) out[49 + i] = sc.Vinv[i];
+  out[85] = (float)ok;
+  // register-only 3x3 Jacobi on the leading 3x3 block
+  float W3[3], V3[9];
+  jacobi_eigen3(A36[0], A36[1], A36[2], A36[7], A36[8], A36[14], W3, V3);
+  for (int i = 0; i < 3; i++) out[86 + i] = W3[i];
+  for (int i = 0; i < 9; i++) out[89 + i] = V3[i];
 }
 
 // stand-alone exact 5-NN (tests / lisreg_knn5)
@@ -363,12 +423,14 @@ __global__ void k_knn5(GridDev g, const float4* __restrict__ q, int nq, float ga
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   float4 p = q[i];
-  float bd[5]; int bi[5], bp[5];
-  knn5_grid(g, p.x, p.y, p.z, gate, bd, bi, bp);
+  knn_key best[5];
+  knn5_grid(g, p.x, p.y, p.z, gate, best);
   for (int j = 0; j < 5; j++) {
-    bool ok = bp[j] >= 0 && bd[j] < gate;
-    idx[5 * i + j] = ok ? bi[j] : -1;
-    sqd[5 * i + j] = ok ? bd[j] : FLT_MAX;
+    const float d = knn_key_d(best[j]);
+    const int pos = knn_key_pos(best[j]);
+    const bool ok = pos >= 0 && d < gate;
+    idx[5 * i + j] = ok ? __float_as_int(g.pts[pos].w) : -1;
+    sqd[5 * i + j] = ok ? d : FLT_MAX;
   }
 }
 

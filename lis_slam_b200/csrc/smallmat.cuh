@@ -24,12 +24,14 @@ LISREG_HD __forceinline__ float cv_hypotf(float a, float b) {
 LISREG_HD __forceinline__ void swapf(float& a, float& b) { float t = a; a = b; b = t; }
 
 // Symmetric Jacobi: eigenvalues descending in W, eigenvectors in the ROWS of V.
+// A, W, V and the index scratch indR/indC (N ints each) are caller-provided: device callers pass
+// SHARED memory (data-dependent indexing of per-thread local arrays is avoided on the device).
 template <int N>
-LISREG_HD void jacobi_eigen(float* A, float* W, float* V) {
+LISREG_HD void jacobi_eigen(float* A, float* W, float* V, int* indR, int* indC) {
   const float eps = FLT_EPSILON;
   int i, j, k, m;
   for (i = 0; i < N; i++) { for (j = 0; j < N; j++) V[i * N + j] = 0.f; V[i * N + i] = 1.f; }
-  int indR[N], indC[N];
+  for (i = 0; i < N; i++) { indR[i] = 0; indC[i] = 0; }
   float mv = 0.f;
   for (k = 0; k < N; k++) {
     W[k] = A[(N + 1) * k];
@@ -101,6 +103,73 @@ LISREG_HD void jacobi_eigen(float* A, float* W, float* V) {
     if (k != m) {
       swapf(W[m], W[k]);
       for (i = 0; i < N; i++) swapf(V[N * m + i], V[N * k + i]);
+    }
+  }
+}
+
+// 3x3 specialisation of the same algorithm with every operand in registers: the pivot pair
+// (k,l) in {(0,1),(0,2),(1,2)} selects one of three statically-indexed code paths.  Same operation
+// order as jacobi_eigen<3>, hence bit-identical results (checked in tests).
+LISREG_HD __forceinline__ void jacobi_eigen3(float a00, float a01, float a02, float a11, float a12, float a22,
+                                             float (&W)[3], float (&V)[9]) {
+  const float eps = FLT_EPSILON;
+  float w0 = a00, w1 = a11, w2 = a22;
+  float v00 = 1.f, v01 = 0.f, v02 = 0.f, v10 = 0.f, v11 = 1.f, v12 = 0.f, v20 = 0.f, v21 = 0.f, v22 = 1.f;
+  // indR[0] in {1,2}; indR[1] == 2; indC[1] == 0; indC[2] in {0,1}
+  int r0 = (fabsf(a01) < fabsf(a02)) ? 2 : 1;
+  int c2 = (fabsf(a02) < fabsf(a12)) ? 1 : 0;
+  for (int iters = 0; iters < 270; iters++) {
+    // pivot search
+    int k = 0;
+    float mv = fabsf(r0 == 1 ? a01 : a02);
+    { float val = fabsf(a12); if (mv < val) mv = val, k = 1; }
+    int l = (k == 0) ? r0 : 2;
+    { float val = fabsf(a01); if (mv < val) mv = val, k = 0, l = 1; }
+    { float val = fabsf(c2 == 0 ? a02 : a12); if (mv < val) mv = val, k = c2, l = 2; }
+    const int kl = k * 3 + l;   // 1, 2 or 5
+    const float p = kl == 1 ? a01 : (kl == 2 ? a02 : a12);
+    if (fabsf(p) <= eps) break;
+    const float wk = k == 0 ? w0 : w1, wl = l == 1 ? w1 : w2;
+    const float y = (float)((double)(wl - wk) * 0.5);
+    float t = fabsf(y) + cv_hypotf(p, y);
+    float s = cv_hypotf(p, t);
+    const float c = t / s;
+    s = p / s; t = (p / t) * p;
+    if (y < 0) s = -s, t = -t;
+#define LISREG_ROT3(v0, v1) { const float a0_ = v0, b0_ = v1; v0 = a0_ * c - b0_ * s; v1 = a0_ * s + b0_ * c; }
+    if (kl == 1) {          // (0,1)
+      a01 = 0.f; w0 -= t; w1 += t;
+      LISREG_ROT3(a02, a12);
+      LISREG_ROT3(v00, v10); LISREG_ROT3(v01, v11); LISREG_ROT3(v02, v12);
+    } else if (kl == 2) {   // (0,2)
+      a02 = 0.f; w0 -= t; w2 += t;
+      LISREG_ROT3(a01, a12);
+      LISREG_ROT3(v00, v20); LISREG_ROT3(v01, v21); LISREG_ROT3(v02, v22);
+    } else {                // (1,2)
+      a12 = 0.f; w1 -= t; w2 += t;
+      LISREG_ROT3(a01, a02);
+      LISREG_ROT3(v10, v20); LISREG_ROT3(v11, v21); LISREG_ROT3(v12, v22);
+    }
+#undef LISREG_ROT3
+    // index updates for idx = k then idx = l (only indR[0] and indC[2] can change)
+    if (k == 0) r0 = (fabsf(a01) < fabsf(a02)) ? 2 : 1;
+    if (l == 2) c2 = (fabsf(a02) < fabsf(a12)) ? 1 : 0;
+  }
+  // sort descending (selection sort with row swaps, as the reference routine)
+  W[0] = w0; W[1] = w1; W[2] = w2;
+  V[0] = v00; V[1] = v01; V[2] = v02; V[3] = v10; V[4] = v11; V[5] = v12; V[6] = v20; V[7] = v21; V[8] = v22;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    int m = k;
+#pragma unroll
+    for (int i = k + 1; i < 3; i++) if (W[m] < W[i]) m = i;
+#pragma unroll
+    for (int mm = k + 1; mm < 3; mm++) {
+      if (mm == m) {
+        swapf(W[mm], W[k]);
+#pragma unroll
+        for (int i = 0; i < 3; i++) swapf(V[3 * mm + i], V[3 * k + i]);
+      }
     }
   }
 }

@@ -23,7 +23,8 @@ class LisregError(RuntimeError):
 
 
 class Config(C.Structure):
-    _fields_ = [("device", C.c_int32), ("stream", C.c_void_p), ("max_grid_cells", C.c_int32), ("reserved", C.c_int32 * 5)]
+    _fields_ = [("device", C.c_int32), ("stream", C.c_void_p), ("max_grid_cells", C.c_int32), ("own_stream", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
 
 
 class LmParams(C.Structure):
@@ -56,6 +57,15 @@ class BatchItem(C.Structure):
     _fields_ = [
         ("corner", C.c_void_p), ("clabel", C.c_void_p), ("surf", C.c_void_p), ("slabel", C.c_void_p),
         ("nc", C.c_int32), ("ns", C.c_int32), ("map_id", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class Profile(C.Structure):
+    _fields_ = [
+        ("lm_iter_ms", C.c_double), ("lm_iter_launches", C.c_int64), ("lm_alg_bytes", C.c_double),
+        ("feat_ms", C.c_double), ("feat_launches", C.c_int64), ("feat_alg_bytes", C.c_double),
+        ("voxel_ms", C.c_double), ("voxel_launches", C.c_int64), ("voxel_alg_bytes", C.c_double),
+        ("index_ms", C.c_double), ("index_launches", C.c_int64), ("index_alg_bytes", C.c_double),
     ]
 
 
@@ -105,6 +115,14 @@ def lib():
         L.lisreg_scan2map_batch.argtypes = [vp, i32, C.POINTER(BatchItem), fp, C.POINTER(LmParams), C.POINTER(LmResult), C.POINTER(LmIter)]
         L.lisreg_scan2map_batch_dev.restype = i32
         L.lisreg_scan2map_batch_dev.argtypes = [vp, i32, C.POINTER(BatchItem), vp, C.POINTER(LmParams), vp]
+        L.lisreg_scan2map_batch_arena.restype = i32
+        L.lisreg_scan2map_batch_arena.argtypes = [vp, i32, C.POINTER(BatchItem), vp, C.c_uint64, fp, C.POINTER(LmParams), C.POINTER(LmResult)]
+        L.lisreg_selftest_smallmat.restype = i32
+        L.lisreg_selftest_smallmat.argtypes = [vp, fp, fp, fp]
+        L.lisreg_profile_enable.restype = i32
+        L.lisreg_profile_enable.argtypes = [vp, i32]
+        L.lisreg_profile_get.restype = i32
+        L.lisreg_profile_get.argtypes = [vp, C.POINTER(Profile), i32]
         _LIB = L
     return _LIB
 
@@ -134,9 +152,9 @@ def _ptr(a):
 class Engine:
     """One lisreg context (one GPU, one stream)."""
 
-    def __init__(self, device=0, stream=None, max_grid_cells=0):
+    def __init__(self, device=0, stream=None, max_grid_cells=0, own_stream=False):
         self._h = C.c_void_p()
-        cfg = Config(device=device, stream=stream, max_grid_cells=max_grid_cells)
+        cfg = Config(device=device, stream=stream, max_grid_cells=max_grid_cells, own_stream=1 if own_stream else 0)
         rc = lib().lisreg_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             raise LisregError("lisreg_create failed (%d): no CUDA device / driver — this engine has no CPU path" % rc)
@@ -213,6 +231,28 @@ class Engine:
             out_logs = [[logs[b * params.max_iters + i] for i in range(res[b].iters)] for b in range(B)]
         self.last_status = rc
         return pose, list(res), out_logs
+
+    def scan2map_batch_arena(self, items, B, arena_ptr, arena_bytes, pose, params, res):
+        """Frame packets packed in one (pinned) host arena; items hold byte offsets. pose: (B,6) f32
+        numpy array in/out, res: ctypes array of LmResult."""
+        return self._ck(lib().lisreg_scan2map_batch_arena(self._h, B, items, arena_ptr, arena_bytes,
+                                                          pose.ctypes.data_as(C.POINTER(C.c_float)), C.byref(params), res))
+
+    def selftest_smallmat(self, A, b):
+        A = np.ascontiguousarray(A, np.float32).reshape(36); b = np.ascontiguousarray(b, np.float32).reshape(6)
+        out = np.zeros(98, np.float32)
+        self._ck(lib().lisreg_selftest_smallmat(self._h, A.ctypes.data_as(C.POINTER(C.c_float)), b.ctypes.data_as(C.POINTER(C.c_float)),
+                                                out.ctypes.data_as(C.POINTER(C.c_float))))
+        return {"E": out[:6], "V": out[6:42].reshape(6, 6), "X": out[42:48], "qr_ok": int(out[48]),
+                "inv": out[49:85].reshape(6, 6), "lu_ok": int(out[85]), "W3": out[86:89], "V3": out[89:98].reshape(3, 3)}
+
+    def profile_enable(self, on=True):
+        self._ck(lib().lisreg_profile_enable(self._h, 1 if on else 0))
+
+    def profile_get(self, reset=True):
+        p = Profile()
+        self._ck(lib().lisreg_profile_get(self._h, C.byref(p), 1 if reset else 0))
+        return p
 
     def scan2map_batch_dev(self, items, B, d_pose_ptr, params, d_res_ptr):
         """All buffers resident in HBM (items = ctypes array of BatchItem holding DEVICE pointers).

@@ -22,3 +22,10 @@ for i in range(max(len(lo), len(lg))):
     if i == 0 and i < len(lo) and i < len(lg):
         print("AtA O\n", np.array(lo[0].AtA).reshape(6, 6)); print("AtA G\n", np.array(lg[0].AtA).reshape(6, 6))
         print("AtB O", np.array(lo[0].AtB)); print("AtB G", np.array(lg[0].AtB))
+A = np.array(lg[0].AtA, np.float32).reshape(6, 6); bb = np.array(lg[0].AtB, np.float32)
+print("AtB G", bb)
+ok, x = orc.qr_solve(A, bb)
+print("oracle qr on GPU AtA/AtB:", x)
+W, V = orc.jacobi_eigen(A)
+print("eig of GPU AtA", W)
+print("gpu degenerate", rg.is_degenerate)
