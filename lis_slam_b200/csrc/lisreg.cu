@@ -271,11 +271,11 @@ static int build_cloud_index(lisreg_ctx* ctx, const float4* d_pts, int n, float 
   return LISREG_OK;
 }
 
-// Cell size: the search is exact for ANY cell size (shell expansion); ~0.65 m keeps the 3x3x3 block
+// Cell size: the search is exact for ANY cell size (shell expansion); ~0.6 m keeps the 3x3x3 block
 // at ~20-30 candidates for 0.4 m voxel-grid surf maps while the 5th neighbour usually lies inside it.
 static float cell_size_for_gate(float gate) {
   const char* e = getenv("LISREG_CELL");
-  float h = e ? (float)atof(e) : 0.65f;
+  float h = e ? (float)atof(e) : 0.6f;
   const float r = sqrtf(gate > 0.f ? gate : 1.f);
   return fminf(h, 1.002f * r + 1e-3f);
 }

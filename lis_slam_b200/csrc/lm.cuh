@@ -241,7 +241,10 @@ constexpr int LM_MAX_TILE = 512;
 // Phase C: each warp reduces a quarter of the tile's rows, lane p owning one of the 27 products
 //          (fp64, fixed order => deterministic), then block partial -> global; the last block of a
 //          registration sums the tile partials in order and runs the 6x6 solve.
-__global__ void __launch_bounds__(LM_THREADS, 5)
+#ifndef LM_MIN_BLOCKS
+#define LM_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS)
 k_lm_iter(const RegDesc* __restrict__ descs, RegState* __restrict__ states, const MapDev* __restrict__ maps,
           LmParamsDev prm, double* __restrict__ partials, int max_tiles, int tile_pts) {
   const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
