@@ -156,6 +156,33 @@ int32_t lisreg_scan2map_batch_arena(lisreg_ctx* ctx, int32_t B, const lisreg_bat
                                     const void* host_arena, uint64_t arena_bytes,
                                     float* pose6xB, const lisreg_lm_params* prm, lisreg_lm_result* resxB);
 
+/* ---- LOAM feature extraction (B1) ----
+ * Replaces LaserProcessing::projectPointCloud + cloudExtraction (laserProcessing.cpp:467-539, with the
+ * de-skew step as identity: motion de-skew is out of scope) and LaserProcessing::featureExtraction()
+ * (:108-115 -> calculateSmoothness :544, markOccludedPoints :568, extractFeatures :610); the duplicate class
+ * FeatureExtraction (featureExtraction.cpp:68-80) maps to the same call.  Index lists refer to the
+ * extracted (ring-major compacted) cloud and follow the reference push order.  All output arrays are
+ * caller-allocated and optional (NULL = not wanted); capacities: src_index/col_ind/range/surf_idx/
+ * curvature/label n_scan*horizon, start_ring/end_ring n_scan, corner_idx n_scan*120, sharp_idx n_scan*24,
+ * flat_idx n_scan*60. */
+typedef struct lisreg_feat_params {
+  int32_t n_scan, horizon, downsample_rate;   /* N_SCAN 64, Horizon_SCAN 1800, downsampleRate */
+  float min_range, max_range;                 /* lidarMinRange, lidarMaxRange */
+  float edge_thr, surf_thr;                   /* edgeThreshold 1.0, surfThreshold 0.1 */
+} lisreg_feat_params;
+
+typedef struct lisreg_feat_out {
+  int32_t n_extracted, n_corner, n_sharp, n_flat, n_surf;
+  int32_t* src_index; int32_t* col_ind; float* range;
+  int32_t* start_ring; int32_t* end_ring;
+  int32_t* corner_idx; int32_t* sharp_idx; int32_t* flat_idx; int32_t* surf_idx;
+  float* curvature; int32_t* label;
+} lisreg_feat_out;
+
+void lisreg_feat_params_default(lisreg_feat_params* p);
+int32_t lisreg_extract_features(lisreg_ctx* ctx, const float* pts, const uint16_t* ring, int32_t n,
+                                const lisreg_feat_params* prm, lisreg_feat_out* out);
+
 /* device self-test of the small dense routines (cv::eigen / cv::solve(QR) / cv::Mat::inv restatements):
  * out98 = E[6], V[36] (eigenvectors in rows), X[6] (QR solve of A x = b), ok, Ainv[36] (LU), ok,
  * then W3[3], V3[9] of the register-only 3x3 Jacobi applied to the leading 3x3 block of A */

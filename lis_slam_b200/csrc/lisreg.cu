@@ -12,6 +12,7 @@
 
 #include "../../include/lisreg.h"
 #include "lm.cuh"
+#include "features.cuh"
 
 using namespace lisreg;
 
@@ -69,6 +70,9 @@ struct lisreg_ctx {
   // scratch
   DevBuf d_stage, d_descs, d_states, d_partials, d_tickets, d_logs, d_pose, d_res, d_tmp, d_bbox;
   PinBuf h_stage, h_out;
+  // feature-extraction work buffers (capacity feat_cap_frames frames of feat_cells cells)
+  DevBuf d_feat, d_feat_frames;
+  int feat_cap_frames = 0, feat_cells = 0, feat_nscan = 0;
   // profiling
   bool prof_on = false;
   struct EvPair { cudaEvent_t a, b; int kind; double bytes; int64_t launches; };
@@ -321,7 +325,7 @@ void lisreg_destroy(lisreg_ctx* ctx) {
   }
   if (ctx->d_maps) cudaFree(ctx->d_maps);
   for (DevBuf* b : {&ctx->d_stage, &ctx->d_descs, &ctx->d_states, &ctx->d_partials, &ctx->d_tickets, &ctx->d_logs,
-                    &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox}) b->release();
+                    &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox, &ctx->d_feat, &ctx->d_feat_frames}) b->release();
   ctx->h_stage.release(); ctx->h_out.release();
   for (auto& p : ctx->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : ctx->ev_free) cudaEventDestroy(e);
@@ -617,6 +621,105 @@ int32_t lisreg_scan2map_batch_arena(lisreg_ctx* ctx, int32_t B, const lisreg_bat
     worst = std::max(worst, hr[b].status);
   }
   return worst;
+}
+
+// ------------------------------------------------------------------------------------------------
+// feature extraction
+// ------------------------------------------------------------------------------------------------
+void lisreg_feat_params_default(lisreg_feat_params* p) {
+  p->n_scan = 64; p->horizon = 1800; p->downsample_rate = 1;   // benchmark pins downsampleRate = 1
+  p->min_range = 0.0f; p->max_range = 70.0f;                    // config/params.yaml:73-74
+  p->edge_thr = 1.0f; p->surf_thr = 0.1f;                       // config/params.yaml:117-118
+}
+
+static size_t feat_frame_bytes(int cells, int nscan) {
+  // owner, ext_src, col, picked, label, surf_idx (int), range, curv (float) : 8 x 4 B per cell; ext_pts 16 B per cell
+  size_t b = (size_t)cells * (8 * 4 + 16);
+  b += sizeof(int) * (size_t)nscan * 3;                 // ring_count, ring_start, ring_end
+  b += sizeof(int) * (size_t)nscan * 6 * (20 + 1 + 10 + 1 + 1 + 1 + 1);   // seg_corner, ncorner, seg_flat, nflat, valid, sp, ep
+  b += sizeof(int) * (size_t)nscan * (120 + 24 + 60);   // corner_idx, sharp_idx, flat_idx
+  b += sizeof(int) * 8;                                 // M, counts[4]
+  return (b + 255) & ~size_t(255);
+}
+
+// carves frame i's work area; raw input pointers are filled by the caller
+static void feat_carve(char* base, int cells, int nscan, FeatFrame* f) {
+  char* p = base;
+  auto take = [&](size_t bytes) { char* r = p; p += (bytes + 15) & ~size_t(15); return r; };
+  f->ext_pts = (float4*)take(sizeof(float4) * (size_t)cells);
+  f->owner = (int*)take(4 * (size_t)cells); f->ext_src = (int*)take(4 * (size_t)cells); f->col = (int*)take(4 * (size_t)cells);
+  f->range = (float*)take(4 * (size_t)cells); f->curv = (float*)take(4 * (size_t)cells);
+  f->picked = (int*)take(4 * (size_t)cells); f->label = (int*)take(4 * (size_t)cells); f->surf_idx = (int*)take(4 * (size_t)cells);
+  f->ring_count = (int*)take(4 * (size_t)nscan); f->ring_start = (int*)take(4 * (size_t)nscan); f->ring_end = (int*)take(4 * (size_t)nscan);
+  const size_t ns = (size_t)nscan * 6;
+  f->seg_corner = (int*)take(4 * ns * 20); f->seg_ncorner = (int*)take(4 * ns);
+  f->seg_flat = (int*)take(4 * ns * 10); f->seg_nflat = (int*)take(4 * ns);
+  f->seg_valid = (int*)take(4 * ns); f->seg_sp = (int*)take(4 * ns); f->seg_ep = (int*)take(4 * ns);
+  f->corner_idx = (int*)take(4 * (size_t)nscan * 120); f->sharp_idx = (int*)take(4 * (size_t)nscan * 24); f->flat_idx = (int*)take(4 * (size_t)nscan * 60);
+  f->M = (int*)take(4); f->counts = (int*)take(16);
+}
+
+static int feat_reserve(lisreg_ctx* ctx, int F, int cells, int nscan) {
+  const size_t per = feat_frame_bytes(cells, nscan) + 4096;
+  CK(ctx->d_feat.reserve(per * (size_t)F));
+  CK(ctx->d_feat_frames.reserve(sizeof(FeatFrame) * (size_t)F));
+  ctx->feat_cap_frames = F; ctx->feat_cells = cells; ctx->feat_nscan = nscan;
+  return LISREG_OK;
+}
+
+// runs F1-F5 for F frames whose FeatFrame descriptors (device) are ready
+static int run_features(lisreg_ctx* ctx, FeatFrame* d_frames, int F, const lisreg_feat_params* prm, int max_n, double alg_bytes) {
+  cudaStream_t st = ctx->stream;
+  FeatParamsDev dp{prm->n_scan, prm->horizon, prm->downsample_rate, prm->min_range, prm->max_range, prm->edge_thr, prm->surf_thr};
+  const int cells = prm->n_scan * prm->horizon;
+  ProfScope ps(ctx, PROF_FEAT, alg_bytes, 7);
+  k_feat_clear<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
+  k_feat_project<<<dim3(std::max(1, (max_n + 255) / 256), F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
+  k_feat_ring_count<<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
+  k_feat_compact<<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
+  k_feat_curvature<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames); LAUNCH_CK();
+  k_feat_occlusion<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames); LAUNCH_CK();
+  k_feat_segments<<<dim3((prm->n_scan + FEAT_WARPS - 1) / FEAT_WARPS, F), 32 * FEAT_WARPS, 0, st>>>(d_frames, dp); LAUNCH_CK();
+  k_feat_gather<<<F, 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
+  return LISREG_OK;
+}
+
+int32_t lisreg_extract_features(lisreg_ctx* ctx, const float* pts, const uint16_t* ring, int32_t n,
+                                const lisreg_feat_params* prm, lisreg_feat_out* out) {
+  if (!ctx || n < 0 || (n > 0 && (!pts || !ring)) || !prm || !out) return fail(ctx, LISREG_ERR_ARG, "lisreg_extract_features: bad argument");
+  if (prm->n_scan <= 0 || prm->horizon <= 0 || prm->horizon > 2048 || prm->n_scan * 6 > 1024 || prm->downsample_rate <= 0)
+    return fail(ctx, LISREG_ERR_ARG, "lisreg_extract_features: unsupported n_scan/horizon/downsample_rate");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int cells = prm->n_scan * prm->horizon;
+  int rc = feat_reserve(ctx, 1, cells, prm->n_scan);
+  if (rc) return rc;
+  const size_t bp = sizeof(float4) * (size_t)n, br = sizeof(uint16_t) * (size_t)n;
+  CK(ctx->d_stage.reserve(bp + br + 64));
+  char* d = (char*)ctx->d_stage.p;
+  if (n) { CK(cudaMemcpyAsync(d, pts, bp, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(d + bp, ring, br, cudaMemcpyHostToDevice, st)); }
+  FeatFrame f{};
+  feat_carve((char*)ctx->d_feat.p, cells, prm->n_scan, &f);
+  f.pts = (const float4*)d; f.ring = (const uint16_t*)(d + bp); f.n = n;
+  CK(cudaMemcpyAsync(ctx->d_feat_frames.p, &f, sizeof(f), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));   // f is a stack object
+  rc = run_features(ctx, (FeatFrame*)ctx->d_feat_frames.p, 1, prm, n, 17.0 * n);
+  if (rc) return rc;
+  int h[5];
+  CK(cudaMemcpyAsync(&h[0], f.M, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&h[1], f.counts, 16, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  out->n_extracted = h[0]; out->n_corner = h[1]; out->n_sharp = h[2]; out->n_flat = h[3]; out->n_surf = h[4];
+  auto dl = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+    return (dst && bytes) ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess; };
+  const size_t M = (size_t)h[0];
+  CK(dl(out->src_index, f.ext_src, 4 * M)); CK(dl(out->col_ind, f.col, 4 * M)); CK(dl(out->range, f.range, 4 * M));
+  CK(dl(out->start_ring, f.ring_start, 4 * (size_t)prm->n_scan)); CK(dl(out->end_ring, f.ring_end, 4 * (size_t)prm->n_scan));
+  CK(dl(out->corner_idx, f.corner_idx, 4 * (size_t)h[1])); CK(dl(out->sharp_idx, f.sharp_idx, 4 * (size_t)h[2]));
+  CK(dl(out->flat_idx, f.flat_idx, 4 * (size_t)h[3])); CK(dl(out->surf_idx, f.surf_idx, 4 * (size_t)h[4]));
+  CK(dl(out->curvature, f.curv, 4 * M)); CK(dl(out->label, f.label, 4 * M));
+  CK(cudaStreamSynchronize(st));
+  return LISREG_OK;
 }
 
 int32_t lisreg_selftest_smallmat(lisreg_ctx* ctx, const float* A36, const float* b6, float* out98) {

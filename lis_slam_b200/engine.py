@@ -60,6 +60,19 @@ class BatchItem(C.Structure):
     ]
 
 
+class FeatParams(C.Structure):
+    _fields_ = [("n_scan", C.c_int32), ("horizon", C.c_int32), ("downsample_rate", C.c_int32),
+                ("min_range", C.c_float), ("max_range", C.c_float), ("edge_thr", C.c_float), ("surf_thr", C.c_float)]
+
+
+class FeatOut(C.Structure):
+    _fields_ = [("n_extracted", C.c_int32), ("n_corner", C.c_int32), ("n_sharp", C.c_int32), ("n_flat", C.c_int32), ("n_surf", C.c_int32),
+                ("src_index", C.c_void_p), ("col_ind", C.c_void_p), ("range", C.c_void_p),
+                ("start_ring", C.c_void_p), ("end_ring", C.c_void_p),
+                ("corner_idx", C.c_void_p), ("sharp_idx", C.c_void_p), ("flat_idx", C.c_void_p), ("surf_idx", C.c_void_p),
+                ("curvature", C.c_void_p), ("label", C.c_void_p)]
+
+
 class Profile(C.Structure):
     _fields_ = [
         ("lm_iter_ms", C.c_double), ("lm_iter_launches", C.c_int64), ("lm_alg_bytes", C.c_double),
@@ -117,6 +130,9 @@ def lib():
         L.lisreg_scan2map_batch_dev.argtypes = [vp, i32, C.POINTER(BatchItem), vp, C.POINTER(LmParams), vp]
         L.lisreg_scan2map_batch_arena.restype = i32
         L.lisreg_scan2map_batch_arena.argtypes = [vp, i32, C.POINTER(BatchItem), vp, C.c_uint64, fp, C.POINTER(LmParams), C.POINTER(LmResult)]
+        L.lisreg_feat_params_default.argtypes = [C.POINTER(FeatParams)]
+        L.lisreg_extract_features.restype = i32
+        L.lisreg_extract_features.argtypes = [vp, vp, vp, i32, C.POINTER(FeatParams), C.POINTER(FeatOut)]
         L.lisreg_selftest_smallmat.restype = i32
         L.lisreg_selftest_smallmat.argtypes = [vp, fp, fp, fp]
         L.lisreg_profile_enable.restype = i32
@@ -130,6 +146,14 @@ def lib():
 def lm_params(variant="A", **kw):
     p = LmParams()
     lib().lisreg_lm_params_preset(C.byref(p), variant.encode())
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def feat_params(**kw):
+    p = FeatParams()
+    lib().lisreg_feat_params_default(C.byref(p))
     for k, v in kw.items():
         setattr(p, k, v)
     return p
@@ -237,6 +261,28 @@ class Engine:
         numpy array in/out, res: ctypes array of LmResult."""
         return self._ck(lib().lisreg_scan2map_batch_arena(self._h, B, items, arena_ptr, arena_bytes,
                                                           pose.ctypes.data_as(C.POINTER(C.c_float)), C.byref(params), res))
+
+    def extract_features(self, pts, ring, prm=None):
+        """F1-F5 on one raw sweep (host buffers). Returns a dict shaped like oracle.orc.extract_features."""
+        prm = prm or feat_params()
+        p = _f4(pts); r = np.ascontiguousarray(ring, dtype=np.uint16)
+        cap = prm.n_scan * prm.horizon
+        a = {"src_index": np.zeros(cap, np.int32), "col_ind": np.zeros(cap, np.int32), "range": np.zeros(cap, np.float32),
+             "start_ring": np.zeros(prm.n_scan, np.int32), "end_ring": np.zeros(prm.n_scan, np.int32),
+             "corner_idx": np.zeros(prm.n_scan * 120, np.int32), "sharp_idx": np.zeros(prm.n_scan * 24, np.int32),
+             "flat_idx": np.zeros(prm.n_scan * 60, np.int32), "surf_idx": np.zeros(cap, np.int32),
+             "curvature": np.zeros(cap, np.float32), "label": np.zeros(cap, np.int32)}
+        out = FeatOut()
+        for k, v in a.items():
+            setattr(out, k, v.ctypes.data)
+        self._ck(lib().lisreg_extract_features(self._h, p.ctypes.data, r.ctypes.data, len(p), C.byref(prm), C.byref(out)))
+        M = out.n_extracted
+        res = {"M": M, "start_ring": a["start_ring"], "end_ring": a["end_ring"]}
+        for k in ("src_index", "col_ind", "range", "curvature", "label"):
+            res[k] = a[k][:M]
+        res["corner_idx"] = a["corner_idx"][:out.n_corner]; res["sharp_idx"] = a["sharp_idx"][:out.n_sharp]
+        res["flat_idx"] = a["flat_idx"][:out.n_flat]; res["surf_idx"] = a["surf_idx"][:out.n_surf]
+        return res
 
     def selftest_smallmat(self, A, b):
         A = np.ascontiguousarray(A, np.float32).reshape(36); b = np.ascontiguousarray(b, np.float32).reshape(6)

@@ -50,6 +50,15 @@ class LmResult(C.Structure):
     ]
 
 
+class FeatParams(C.Structure):
+    _fields_ = [("n_scan", C.c_int32), ("horizon", C.c_int32), ("downsample_rate", C.c_int32),
+                ("min_range", C.c_float), ("max_range", C.c_float), ("edge_thr", C.c_float), ("surf_thr", C.c_float)]
+
+
+def feat_params(n_scan=64, horizon=1800, downsample_rate=1, min_range=0.0, max_range=70.0, edge_thr=1.0, surf_thr=0.1):
+    return FeatParams(n_scan, horizon, downsample_rate, min_range, max_range, edge_thr, surf_thr)
+
+
 # label_sorce of config/label.yaml:214-234 (reference values)
 LABEL_SCORE = [1.0, 1.0, 0.6, 0.5, 0.8, 0.5, 0.5, 0.5, 0.5, 1.2, 1.2, 1.2, 0.5, 1.0, 0.8, 0.5, 1.3, 0.5, 1.5, 1.5]
 
@@ -100,6 +109,9 @@ def lib():
         L.orc_lu_inv_f32.restype = C.c_int
         L.orc_lu_inv_f32.argtypes = [fp, C.c_int32, fp]
         L.orc_plane_fit_5x3.argtypes = [fp, fp]
+        L.orc_project_scan.restype = C.c_int32
+        L.orc_project_scan.argtypes = [fp, u16p, C.c_int32, C.POINTER(FeatParams), ip, ip, fp, ip, ip]
+        L.orc_extract_features.argtypes = [fp, ip, C.c_int32, ip, ip, C.POINTER(FeatParams), ip, ip, ip, ip, ip, ip, ip, ip, fp, ip]
         _LIB = L
     return _LIB
 
@@ -186,3 +198,28 @@ def pose_to_affine(pose6):
     T = np.empty(12, np.float32)
     lib().orc_pose_to_affine(pp, T.ctypes.data_as(C.POINTER(C.c_float)))
     return T.reshape(3, 4)
+
+
+def extract_features(pts4, ring, prm=None):
+    """F1-F5 on one raw sweep. Returns dict of arrays (index lists refer to the extracted cloud)."""
+    L = lib()
+    prm = prm or feat_params()
+    p, pp = _f(pts4)
+    r = np.ascontiguousarray(ring, dtype=np.uint16)
+    cap = prm.n_scan * prm.horizon
+    ip = C.POINTER(C.c_int32)
+    src = np.zeros(cap, np.int32); col = np.zeros(cap, np.int32); rng = np.zeros(cap, np.float32)
+    sr = np.zeros(prm.n_scan, np.int32); er = np.zeros(prm.n_scan, np.int32)
+    M = L.orc_project_scan(pp, r.ctypes.data_as(C.POINTER(C.c_uint16)), len(p), C.byref(prm), src.ctypes.data_as(ip),
+                           col.ctypes.data_as(ip), rng.ctypes.data_as(C.POINTER(C.c_float)), sr.ctypes.data_as(ip), er.ctypes.data_as(ip))
+    corner = np.zeros(prm.n_scan * 120, np.int32); sharp = np.zeros(prm.n_scan * 24, np.int32)
+    flat = np.zeros(prm.n_scan * 60, np.int32); surf = np.zeros(cap, np.int32)
+    n = [C.c_int32(0) for _ in range(4)]
+    curv = np.zeros(max(M, 1), np.float32); label = np.zeros(max(M, 1), np.int32)
+    L.orc_extract_features(rng.ctypes.data_as(C.POINTER(C.c_float)), col.ctypes.data_as(ip), M, sr.ctypes.data_as(ip), er.ctypes.data_as(ip),
+                           C.byref(prm), corner.ctypes.data_as(ip), C.byref(n[0]), sharp.ctypes.data_as(ip), C.byref(n[1]),
+                           flat.ctypes.data_as(ip), C.byref(n[2]), surf.ctypes.data_as(ip), C.byref(n[3]),
+                           curv.ctypes.data_as(C.POINTER(C.c_float)), label.ctypes.data_as(ip))
+    return {"M": M, "src_index": src[:M], "col_ind": col[:M], "range": rng[:M], "start_ring": sr, "end_ring": er,
+            "corner_idx": corner[:n[0].value], "sharp_idx": sharp[:n[1].value], "flat_idx": flat[:n[2].value],
+            "surf_idx": surf[:n[3].value], "curvature": curv[:M], "label": label[:M]}
