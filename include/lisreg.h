@@ -183,6 +183,12 @@ void lisreg_feat_params_default(lisreg_feat_params* p);
 int32_t lisreg_extract_features(lisreg_ctx* ctx, const float* pts, const uint16_t* ring, int32_t n,
                                 const lisreg_feat_params* prm, lisreg_feat_out* out);
 
+/* ---- voxel-grid down-sampling (F6) ----
+ * Replaces pcl::VoxelGrid<PointType>::filter as used by downSizeFilterCorner/Surf
+ * (odomEstimationNode.cpp:110-111, :196-201, :272-277): centroid per occupied voxel, ascending voxel
+ * index.  out: caller-allocated n x float4 (worst case one voxel per point); *m receives the count. */
+int32_t lisreg_voxel_grid(lisreg_ctx* ctx, const float* pts, int32_t n, float leaf, float* out, int32_t* m);
+
 /* device self-test of the small dense routines (cv::eigen / cv::solve(QR) / cv::Mat::inv restatements):
  * out98 = E[6], V[36] (eigenvectors in rows), X[6] (QR solve of A x = b), ok, Ainv[36] (LU), ok,
  * then W3[3], V3[9] of the register-only 3x3 Jacobi applied to the leading 3x3 block of A */

@@ -13,6 +13,7 @@
 #include "../../include/lisreg.h"
 #include "lm.cuh"
 #include "features.cuh"
+#include "voxel.cuh"
 
 using namespace lisreg;
 
@@ -73,6 +74,8 @@ struct lisreg_ctx {
   // feature-extraction work buffers (capacity feat_cap_frames frames of feat_cells cells)
   DevBuf d_feat, d_feat_frames;
   int feat_cap_frames = 0, feat_cells = 0, feat_nscan = 0;
+  // voxel-grid work buffers
+  DevBuf d_vox, d_vox_segs;
   // profiling
   bool prof_on = false;
   struct EvPair { cudaEvent_t a, b; int kind; double bytes; int64_t launches; };
@@ -325,7 +328,7 @@ void lisreg_destroy(lisreg_ctx* ctx) {
   }
   if (ctx->d_maps) cudaFree(ctx->d_maps);
   for (DevBuf* b : {&ctx->d_stage, &ctx->d_descs, &ctx->d_states, &ctx->d_partials, &ctx->d_tickets, &ctx->d_logs,
-                    &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox, &ctx->d_feat, &ctx->d_feat_frames}) b->release();
+                    &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox, &ctx->d_feat, &ctx->d_feat_frames, &ctx->d_vox, &ctx->d_vox_segs}) b->release();
   ctx->h_stage.release(); ctx->h_out.release();
   for (auto& p : ctx->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : ctx->ev_free) cudaEventDestroy(e);
@@ -719,6 +722,77 @@ int32_t lisreg_extract_features(lisreg_ctx* ctx, const float* pts, const uint16_
   CK(dl(out->flat_idx, f.flat_idx, 4 * (size_t)h[3])); CK(dl(out->surf_idx, f.surf_idx, 4 * (size_t)h[4]));
   CK(dl(out->curvature, f.curv, 4 * M)); CK(dl(out->label, f.label, 4 * M));
   CK(cudaStreamSynchronize(st));
+  return LISREG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// voxel grid
+// ------------------------------------------------------------------------------------------------
+static size_t vox_seg_bytes(int cap) {
+  const int nblk = (cap + RS_TILE - 1) / RS_TILE + 1;
+  size_t b = 4 * (size_t)cap * 4;                 // key_a, val_a, key_b, val_b
+  b += 4 * 256 * (size_t)nblk;                    // hist
+  b += 4 * ((size_t)cap + 1);                     // seg_start
+  b += sizeof(VoxPlan) + 16;                      // plan, out_n
+  b += sizeof(float4) * (size_t)cap;              // out
+  return (b + 1024) & ~size_t(255);
+}
+static void vox_carve(char* base, int cap, VoxSeg* s) {
+  char* p = base;
+  auto take = [&](size_t bytes) { char* r = p; p += (bytes + 15) & ~size_t(15); return r; };
+  const int nblk = (cap + RS_TILE - 1) / RS_TILE + 1;
+  s->out = (float4*)take(sizeof(float4) * (size_t)cap);
+  s->key_a = (uint32_t*)take(4 * (size_t)cap); s->val_a = (uint32_t*)take(4 * (size_t)cap);
+  s->key_b = (uint32_t*)take(4 * (size_t)cap); s->val_b = (uint32_t*)take(4 * (size_t)cap);
+  s->hist = (uint32_t*)take(4 * 256 * (size_t)nblk);
+  s->seg_start = (int*)take(4 * ((size_t)cap + 1));
+  s->plan = (VoxPlan*)take(sizeof(VoxPlan));
+  s->out_n = (int*)take(4);
+  s->cap = cap;
+}
+
+// runs the voxel grid for nseg clouds whose VoxSeg descriptors (device) are ready; max_n bounds every n
+static int run_voxel(lisreg_ctx* ctx, VoxSeg* d_segs, int nseg, int max_n, double alg_bytes) {
+  cudaStream_t st = ctx->stream;
+  if (nseg <= 0) return LISREG_OK;
+  const int nblk = std::max(1, (max_n + RS_TILE - 1) / RS_TILE);
+  const int pblk = std::max(1, std::min(64, (max_n + 1023) / 1024));
+  ProfScope ps(ctx, PROF_VOXEL, alg_bytes, 16);
+  k_vox_plan<<<nseg, 256, 0, st>>>(d_segs); LAUNCH_CK();
+  k_vox_keys<<<dim3(pblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
+  for (int pass = 0; pass < 4; pass++) {
+    k_rs_hist<<<dim3(nblk, nseg), RS_THREADS, 0, st>>>(d_segs, 8 * pass, pass & 1); LAUNCH_CK();
+    k_rs_scan<<<nseg, 1024, 0, st>>>(d_segs); LAUNCH_CK();
+    k_rs_scatter<<<dim3(nblk, nseg), RS_THREADS, 0, st>>>(d_segs, 8 * pass, pass & 1); LAUNCH_CK();
+  }
+  k_vox_heads<<<nseg, 1024, 0, st>>>(d_segs); LAUNCH_CK();
+  k_vox_centroid<<<dim3(pblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
+  return LISREG_OK;
+}
+
+int32_t lisreg_voxel_grid(lisreg_ctx* ctx, const float* pts, int32_t n, float leaf, float* out, int32_t* m) {
+  if (!ctx || n < 0 || (n > 0 && (!pts || !out)) || !m || !(leaf > 0.f)) return fail(ctx, LISREG_ERR_ARG, "lisreg_voxel_grid: bad argument");
+  *m = 0;
+  if (n == 0) return LISREG_OK;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CK(ctx->d_stage.reserve(sizeof(float4) * (size_t)n));
+  CK(ctx->d_vox.reserve(vox_seg_bytes(n)));
+  CK(ctx->d_vox_segs.reserve(sizeof(VoxSeg)));
+  CK(cudaMemcpyAsync(ctx->d_stage.p, pts, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
+  VoxSeg s{};
+  vox_carve((char*)ctx->d_vox.p, n, &s);
+  s.src = (const float4*)ctx->d_stage.p; s.gather = nullptr; s.n_ptr = nullptr; s.n = n; s.leaf = leaf;
+  CK(cudaMemcpyAsync(ctx->d_vox_segs.p, &s, sizeof(s), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  int rc = run_voxel(ctx, (VoxSeg*)ctx->d_vox_segs.p, 1, n, 32.0 * n);
+  if (rc) return rc;
+  int cnt = 0;
+  CK(cudaMemcpyAsync(&cnt, s.out_n, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaMemcpyAsync(out, s.out, sizeof(float4) * (size_t)cnt, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *m = cnt;
   return LISREG_OK;
 }
 

@@ -1,0 +1,258 @@
+// pcl::VoxelGrid centroid down-sampling on the device, batched over independent clouds ("segments").
+//
+// Reference call sites: downSizeFilterCorner/Surf on the scan features (odomEstimationNode.cpp:272-277)
+// and on the assembled map (:196-201); leaf sizes 0.2 / 0.4 m (config/params.yaml:132-133).
+// PCL semantics restated in oracle/orc_voxel.cpp: voxel index from floor(p * inv_leaf) - min_b, one output
+// point per occupied voxel in ASCENDING voxel index, value = fp32 centroid of x, y, z, intensity with the
+// points of a voxel accumulated in ascending input index.
+//
+// Implementation: (1) per-cloud bounding box -> plan, (2) key = voxel index, value = point index,
+// (3) stable LSD radix sort (8-bit digits, 4 passes; per pass: tile histograms -> per-cloud scan ->
+// stable scatter with warp match-any ranking), (4) head flags + per-cloud scan -> voxel starts,
+// (5) one thread per voxel sums its points in order.  The sorted order is also spatially coherent
+// (x fastest), which is what the kNN kernel wants from its query stream.
+#pragma once
+#include <cstdint>
+#include <cfloat>
+#include <cuda_runtime.h>
+
+namespace lisreg {
+
+struct VoxPlan { float inv; int minb[3]; int mul[3]; int overflow; };
+
+struct VoxSeg {
+  const float4* src;       // source cloud
+  const int* gather;       // optional index list into src (NULL = identity)
+  const int* n_ptr;        // optional device count (overrides n when non-NULL)
+  int n;                   // number of input points
+  float leaf;
+  uint32_t* key_a; uint32_t* val_a; uint32_t* key_b; uint32_t* val_b;   // capacity cap each
+  uint32_t* hist;          // 256 * nblk_cap
+  int* seg_start;          // cap + 1 : voxel starts (positions in the sorted arrays)
+  VoxPlan* plan;
+  float4* out;             // cap
+  int* out_n;              // number of voxels
+  int cap;
+};
+
+constexpr int RS_TILE = 2048;      // keys per block per pass
+constexpr int RS_THREADS = 256;
+
+__device__ __forceinline__ int vox_n(const VoxSeg& s) { return s.n_ptr ? *s.n_ptr : s.n; }
+__device__ __forceinline__ float4 vox_point(const VoxSeg& s, int i) { return __ldg(&s.src[s.gather ? s.gather[i] : i]); }
+
+// (1) bounding box + plan: one block per cloud
+__global__ void k_vox_plan(VoxSeg* segs) {
+  const VoxSeg s = segs[blockIdx.x];
+  const int n = vox_n(s);
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float4 p = vox_point(s, i);
+    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+    mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+  }
+  __shared__ float smn[3][32], smx[3][32];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+    if ((threadIdx.x & 31) == 0) { smn[d][threadIdx.x >> 5] = mn[d]; smx[d][threadIdx.x >> 5] = mx[d]; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) / 32;
+    for (int d = 0; d < 3; d++) for (int w = 1; w < nw; w++) { smn[d][0] = fminf(smn[d][0], smn[d][w]); smx[d][0] = fmaxf(smx[d][0], smx[d][w]); }
+    VoxPlan p;
+    p.inv = 1.0f / s.leaf;
+    p.overflow = 0;
+    if (n > 0) {
+      const long long dx = (long long)((smx[0][0] - smn[0][0]) * p.inv) + 1, dy = (long long)((smx[1][0] - smn[1][0]) * p.inv) + 1,
+                      dz = (long long)((smx[2][0] - smn[2][0]) * p.inv) + 1;
+      if (dx * dy * dz > 2147483647LL) p.overflow = 1;   // PCL: "leaf size is too small" -> output = input
+      int divb[3];
+      for (int d = 0; d < 3; d++) {
+        p.minb[d] = (int)floorf(smn[d][0] * p.inv);
+        divb[d] = (int)floorf(smx[d][0] * p.inv) - p.minb[d] + 1;
+      }
+      p.mul[0] = 1; p.mul[1] = divb[0]; p.mul[2] = divb[0] * divb[1];
+    } else {
+      for (int d = 0; d < 3; d++) { p.minb[d] = 0; p.mul[d] = 0; }
+    }
+    *s.plan = p;
+  }
+}
+
+// (2) keys.  grid = (blocks, nseg)
+__global__ void k_vox_keys(VoxSeg* segs) {
+  const VoxSeg s = segs[blockIdx.y];
+  const int n = vox_n(s);
+  const VoxPlan p = *s.plan;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t key;
+    if (p.overflow) key = (uint32_t)i;
+    else {
+      const float4 q = vox_point(s, i);
+      const int i0 = (int)(floorf(q.x * p.inv) - (float)p.minb[0]);
+      const int i1 = (int)(floorf(q.y * p.inv) - (float)p.minb[1]);
+      const int i2 = (int)(floorf(q.z * p.inv) - (float)p.minb[2]);
+      key = (uint32_t)(i0 * p.mul[0] + i1 * p.mul[1] + i2 * p.mul[2]);
+    }
+    s.key_a[i] = key; s.val_a[i] = (uint32_t)i;
+  }
+}
+
+// (3a) tile histograms: hist[digit * nblk + blk].  grid = (nblk_max, nseg)
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_hist(VoxSeg* segs, int shift, int flip) {
+  const VoxSeg s = segs[blockIdx.y];
+  const int n = vox_n(s);
+  const int nblk = (n + RS_TILE - 1) / RS_TILE;
+  if ((int)blockIdx.x >= nblk) return;
+  const uint32_t* key = flip ? s.key_b : s.key_a;
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * RS_TILE;
+  for (int t = threadIdx.x; t < RS_TILE; t += RS_THREADS) {
+    const int i = base + t;
+    if (i < n) atomicAdd(&h[(key[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  s.hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+}
+
+// (3b) exclusive scan over the 256 * nblk counters of one cloud: one block per cloud
+__global__ void k_rs_scan(VoxSeg* segs) {
+  const VoxSeg s = segs[blockIdx.x];
+  const int n = vox_n(s);
+  const int nblk = (n + RS_TILE - 1) / RS_TILE;
+  const int total = 256 * nblk;
+  __shared__ uint32_t sm[1024];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0u;
+  __syncthreads();
+  for (int base = 0; base < total; base += 1024) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = i < total ? s.hist[i] : 0u;
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const uint32_t t = threadIdx.x >= o ? sm[threadIdx.x - o] : 0u;
+      __syncthreads();
+      sm[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < total) s.hist[i] = sm[threadIdx.x] - v + carry;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sm[1023];
+    __syncthreads();
+  }
+}
+
+// (3c) stable scatter.  grid = (nblk_max, nseg).  Warp w owns keys [w*256, w*256+256) of the tile.
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_scatter(VoxSeg* segs, int shift, int flip) {
+  const VoxSeg s = segs[blockIdx.y];
+  const int n = vox_n(s);
+  const int nblk = (n + RS_TILE - 1) / RS_TILE;
+  if ((int)blockIdx.x >= nblk) return;
+  const uint32_t* key = flip ? s.key_b : s.key_a;
+  const uint32_t* val = flip ? s.val_b : s.val_a;
+  uint32_t* okey = flip ? s.key_a : s.key_b;
+  uint32_t* oval = flip ? s.val_a : s.val_b;
+  constexpr int NW = RS_THREADS / 32, PER_WARP = RS_TILE / NW, ROUNDS = PER_WARP / 32;
+  __shared__ uint32_t wh[NW][256];     // per-warp digit counts, then running offsets
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int d = lane; d < 256; d += 32) wh[wid][d] = 0;
+  __syncwarp();
+  const int base = blockIdx.x * RS_TILE + wid * PER_WARP;
+  uint32_t k[ROUNDS], v[ROUNDS];
+#pragma unroll
+  for (int r = 0; r < ROUNDS; r++) {
+    const int i = base + r * 32 + lane;
+    const bool ok = i < n;
+    k[r] = ok ? key[i] : 0xffffffffu; v[r] = ok ? val[i] : 0u;
+    const uint32_t dgt = (k[r] >> shift) & 255u;
+    const unsigned act = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const unsigned m = __match_any_sync(act, dgt);
+      if (lane == __ffs(m) - 1) wh[wid][dgt] += __popc(m);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // exclusive prefix over warps per digit + global base of this (digit, tile)
+  {
+    const int d = threadIdx.x;   // 256 threads == 256 digits
+    uint32_t acc = s.hist[d * nblk + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < NW; w++) { const uint32_t t = wh[w][d]; wh[w][d] = acc; acc += t; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < ROUNDS; r++) {
+    const int i = base + r * 32 + lane;
+    const bool ok = i < n;
+    const uint32_t dgt = (k[r] >> shift) & 255u;
+    const unsigned act = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const unsigned m = __match_any_sync(act, dgt);
+      const uint32_t pos = wh[wid][dgt] + __popc(m & ((1u << lane) - 1u));
+      okey[pos] = k[r]; oval[pos] = v[r];
+    }
+    __syncwarp();
+    if (ok) {
+      const unsigned m = __match_any_sync(act, dgt);
+      if (lane == __ffs(m) - 1) wh[wid][dgt] += __popc(m);
+    }
+    __syncwarp();
+  }
+}
+
+// (4) voxel starts: one block (1024 threads) per cloud.  After 4 passes the sorted data is back in *_a.
+__global__ void k_vox_heads(VoxSeg* segs) {
+  const VoxSeg s = segs[blockIdx.x];
+  const int n = vox_n(s);
+  __shared__ int sm[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int head = (i < n && (i == 0 || s.key_a[i] != s.key_a[i - 1])) ? 1 : 0;
+    sm[threadIdx.x] = head;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int t = threadIdx.x >= o ? sm[threadIdx.x - o] : 0;
+      __syncthreads();
+      sm[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (head) s.seg_start[carry + sm[threadIdx.x] - 1] = i;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sm[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { s.seg_start[carry] = n; *s.out_n = carry; }
+}
+
+// (5) centroids: one thread per voxel, fp32 accumulation in ascending input index
+__global__ void k_vox_centroid(VoxSeg* segs) {
+  const VoxSeg s = segs[blockIdx.y];
+  const int m = *s.out_n;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < m; v += gridDim.x * blockDim.x) {
+    const int b = s.seg_start[v], e = s.seg_start[v + 1];
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    for (int j = b; j < e; j++) {
+      const float4 p = vox_point(s, (int)s.val_a[j]);
+      sx += p.x; sy += p.y; sz += p.z; si += p.w;
+    }
+    const float c = (float)(e - b);
+    s.out[v] = make_float4(sx / c, sy / c, sz / c, si / c);
+  }
+}
+
+}  // namespace lisreg

@@ -133,6 +133,8 @@ def lib():
         L.lisreg_feat_params_default.argtypes = [C.POINTER(FeatParams)]
         L.lisreg_extract_features.restype = i32
         L.lisreg_extract_features.argtypes = [vp, vp, vp, i32, C.POINTER(FeatParams), C.POINTER(FeatOut)]
+        L.lisreg_voxel_grid.restype = i32
+        L.lisreg_voxel_grid.argtypes = [vp, vp, i32, C.c_float, vp, C.POINTER(i32)]
         L.lisreg_selftest_smallmat.restype = i32
         L.lisreg_selftest_smallmat.argtypes = [vp, fp, fp, fp]
         L.lisreg_profile_enable.restype = i32
@@ -283,6 +285,13 @@ class Engine:
         res["corner_idx"] = a["corner_idx"][:out.n_corner]; res["sharp_idx"] = a["sharp_idx"][:out.n_sharp]
         res["flat_idx"] = a["flat_idx"][:out.n_flat]; res["surf_idx"] = a["surf_idx"][:out.n_surf]
         return res
+
+    def voxel_grid(self, pts, leaf):
+        p = _f4(pts)
+        out = np.zeros((max(len(p), 1), 4), np.float32)
+        m = C.c_int32(0)
+        self._ck(lib().lisreg_voxel_grid(self._h, p.ctypes.data, len(p), leaf, out.ctypes.data, C.byref(m)))
+        return out[:m.value].copy()
 
     def selftest_smallmat(self, A, b):
         A = np.ascontiguousarray(A, np.float32).reshape(36); b = np.ascontiguousarray(b, np.float32).reshape(6)

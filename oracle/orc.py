@@ -112,6 +112,8 @@ def lib():
         L.orc_project_scan.restype = C.c_int32
         L.orc_project_scan.argtypes = [fp, u16p, C.c_int32, C.POINTER(FeatParams), ip, ip, fp, ip, ip]
         L.orc_extract_features.argtypes = [fp, ip, C.c_int32, ip, ip, C.POINTER(FeatParams), ip, ip, ip, ip, ip, ip, ip, ip, fp, ip]
+        L.orc_voxel_grid.restype = C.c_int32
+        L.orc_voxel_grid.argtypes = [fp, C.c_int32, C.c_float, fp, C.c_int32]
         _LIB = L
     return _LIB
 
@@ -223,3 +225,10 @@ def extract_features(pts4, ring, prm=None):
     return {"M": M, "src_index": src[:M], "col_ind": col[:M], "range": rng[:M], "start_ring": sr, "end_ring": er,
             "corner_idx": corner[:n[0].value], "sharp_idx": sharp[:n[1].value], "flat_idx": flat[:n[2].value],
             "surf_idx": surf[:n[3].value], "curvature": curv[:M], "label": label[:M]}
+
+
+def voxel_grid(pts4, leaf):
+    p, pp = _f(pts4)
+    out = np.zeros((max(len(p), 1), 4), np.float32)
+    m = lib().orc_voxel_grid(pp, len(p), leaf, out.ctypes.data_as(C.POINTER(C.c_float)), len(out))
+    return out[:m].copy()

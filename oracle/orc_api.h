@@ -87,6 +87,9 @@ void orc_extract_features(const float* range, const int32_t* col_ind, int32_t M,
                           int32_t* flat_idx, int32_t* n_flat, int32_t* surf_idx, int32_t* n_surf,
                           float* curvature_out, int32_t* label_out);
 
+/* ---- pcl::VoxelGrid<PointXYZI> centroid down-sampling (odomEstimationNode.cpp:196-201, :272-277) ---- */
+int32_t orc_voxel_grid(const float* pts4, int32_t n, float leaf, float* out4, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,60 @@
+"""GPU parity: pcl::VoxelGrid restatement on the device vs the CPU oracle — bit-exact (same voxel order,
+same fp32 accumulation order) — plus idempotence / count properties at larger sizes."""
+import numpy as np
+import pytest
+
+from oracle import orc
+
+from common import local_map, scene
+
+pytestmark = pytest.mark.gpu
+
+
+def _cloud(n, seed, spread=40.0):
+    rng = np.random.default_rng(seed)
+    p = np.zeros((n, 4), np.float32)
+    p[:, :3] = rng.uniform(-spread, spread, (n, 3)) * np.array([1, 1, 0.1])
+    p[:, 3] = rng.uniform(0, 255, n)
+    return p
+
+
+@pytest.mark.parametrize("n,leaf", [(1, 0.4), (7, 0.2), (2047, 0.4), (2049, 0.2), (50000, 0.4), (120000, 0.2)])
+def test_voxel_grid_bit_exact(engine, n, leaf):
+    p = _cloud(n, n)
+    assert np.array_equal(orc.voxel_grid(p, leaf), engine.voxel_grid(p, leaf))
+
+
+def test_scan_features_and_map(engine):
+    s = scene().scan(np.array([0, 0, 0.3, 5, 0.5, 0], np.float32))
+    f = orc.extract_features(s["pts"], s["ring"])
+    ext = s["pts"][f["src_index"]]
+    for idx, leaf in ((f["corner_idx"], 0.2), (f["surf_idx"], 0.4)):
+        c = np.ascontiguousarray(ext[idx])
+        o = orc.voxel_grid(c, leaf); g = engine.voxel_grid(c, leaf)
+        assert np.array_equal(o, g) and 0 < len(g) < len(c)
+    m = local_map()
+    assert np.array_equal(orc.voxel_grid(m["surf"], 0.4), engine.voxel_grid(m["surf"], 0.4))
+
+
+def test_duplicates_collisions_and_empty(engine):
+    assert len(engine.voxel_grid(np.zeros((0, 4), np.float32), 0.4)) == 0
+    p = np.tile(np.array([[1.0, 2.0, 3.0, 4.0]], np.float32), (5000, 1))     # everything in one voxel
+    g = engine.voxel_grid(p, 0.4)
+    assert len(g) == 1 and np.array_equal(g, orc.voxel_grid(p, 0.4))
+    q = _cloud(30000, 5, spread=3.0)                                          # many points per voxel
+    assert np.array_equal(orc.voxel_grid(q, 0.4), engine.voxel_grid(q, 0.4))
+
+
+def test_properties_at_full_size(engine):
+    """Size-independent properties on a 2M-point cloud: each output lies in its own voxel (so a second
+    pass keeps the count), ascending voxel order, count <= n."""
+    p = _cloud(2_000_000, 9, spread=70.0)
+    g = engine.voxel_grid(p, 0.4)
+    g2 = engine.voxel_grid(g, 0.4)
+    assert len(g2) == len(g) <= len(p)
+    inv = np.float32(1.0) / np.float32(0.4)
+    ijk = np.floor(g[:, :3] * inv).astype(np.int64)
+    mn = np.floor(p[:, :3].min(0) * inv).astype(np.int64); mx = np.floor(p[:, :3].max(0) * inv).astype(np.int64)
+    div = mx - mn + 1
+    lin = (ijk[:, 0] - mn[0]) + (ijk[:, 1] - mn[1]) * div[0] + (ijk[:, 2] - mn[2]) * div[0] * div[1]
+    assert np.all(np.diff(lin) >= 0)
