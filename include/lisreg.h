@@ -84,6 +84,7 @@ typedef struct lisreg_lm_result {
   int32_t n_sel_last;
   float deltaR, deltaT;
   float pose[6];
+  int32_t n_corner, n_surf;   /* query points fed to the loop (after voxel down-sampling in the frame pipeline) */
 } lisreg_lm_result;
 
 /* one registration of a batch: host OR device pointers depending on the call */
@@ -188,6 +189,33 @@ int32_t lisreg_extract_features(lisreg_ctx* ctx, const float* pts, const uint16_
  * (odomEstimationNode.cpp:110-111, :196-201, :272-277): centroid per occupied voxel, ascending voxel
  * index.  out: caller-allocated n x float4 (worst case one voxel per point); *m receives the count. */
 int32_t lisreg_voxel_grid(lisreg_ctx* ctx, const float* pts, int32_t n, float leaf, float* out, int32_t* m);
+
+/* ---- whole-frame pipeline (B1 + F6 + B2 fused on the device) ----
+ * One call = for every frame: projectPointCloud/cloudExtraction/featureExtraction (laserProcessing.cpp:467-713)
+ * -> currentCloudInit voxel down-sampling of the corner/surface clouds (odomEstimationNode.cpp:260-281)
+ * -> scan2SubMapOptimization (:596-626) against the frame's local map.  Nothing returns to the host
+ * between the stages.  Frames are independent (throughput mode). */
+typedef struct lisreg_frame_params {
+  lisreg_feat_params feat;
+  float corner_leaf, surf_leaf;     /* mappingCornerLeafSize 0.2, mappingSurfLeafSize 0.4 */
+  lisreg_lm_params lm;
+} lisreg_frame_params;
+
+typedef struct lisreg_frame_item {
+  const float* pts;        /* n x float4 raw sweep (device pointer, or byte offset into the arena) */
+  const uint16_t* ring;    /* n ring ids */
+  int32_t n;
+  int32_t map_id;
+} lisreg_frame_item;
+
+void lisreg_frame_params_default(lisreg_frame_params* p);
+/* everything resident in HBM; asynchronous on the context stream */
+int32_t lisreg_frames_batch_dev(lisreg_ctx* ctx, int32_t F, const lisreg_frame_item* items,
+                                float* d_pose6xF, const lisreg_frame_params* prm, lisreg_lm_result* d_resxF);
+/* raw sweeps packed in one (pinned) host arena; items hold byte offsets (pts 16-byte aligned, ring 2-byte) */
+int32_t lisreg_frames_batch_arena(lisreg_ctx* ctx, int32_t F, const lisreg_frame_item* items,
+                                  const void* host_arena, uint64_t arena_bytes,
+                                  float* pose6xF, const lisreg_frame_params* prm, lisreg_lm_result* resxF);
 
 /* device self-test of the small dense routines (cv::eigen / cv::solve(QR) / cv::Mat::inv restatements):
  * out98 = E[6], V[36] (eigenvectors in rows), X[6] (QR solve of A x = b), ok, Ainv[36] (LU), ok,

@@ -498,7 +498,7 @@ int32_t lisreg_scan2map_batch_dev(lisreg_ctx* ctx, int32_t B, const lisreg_batch
       return fail(ctx, LISREG_ERR_ARG, "batch item %d: bad sizes or map id", b);
     alg += 96.0 * (it.nc + it.ns);
     h[b].corner = (const float4*)it.corner; h[b].surf = (const float4*)it.surf;
-    h[b].clabel = it.clabel; h[b].slabel = it.slabel; h[b].nc = it.nc; h[b].ns = it.ns; h[b].map_slot = it.map_id; h[b].pad = 0;
+    h[b].clabel = it.clabel; h[b].slabel = it.slabel; h[b].nc = it.nc; h[b].ns = it.ns; h[b].map_slot = it.map_id; h[b].pad = 0; h[b].nc_ptr = nullptr; h[b].ns_ptr = nullptr;
     max_n = std::max(max_n, it.nc + it.ns);
   }
   CK(cudaMemcpyAsync(ctx->d_descs.p, h, sizeof(RegDesc) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
@@ -545,7 +545,7 @@ int32_t lisreg_scan2map_batch(lisreg_ctx* ctx, int32_t B, const lisreg_batch_ite
     hd[b].corner = (const float4*)(d + oc[b]); hd[b].surf = (const float4*)(d + os[b]);
     hd[b].clabel = it.clabel ? (const uint16_t*)(d + ocl[b]) : nullptr;
     hd[b].slabel = it.slabel ? (const uint16_t*)(d + osl[b]) : nullptr;
-    hd[b].nc = it.nc; hd[b].ns = it.ns; hd[b].map_slot = it.map_id; hd[b].pad = 0;
+    hd[b].nc = it.nc; hd[b].ns = it.ns; hd[b].map_slot = it.map_id; hd[b].pad = 0; hd[b].nc_ptr = nullptr; hd[b].ns_ptr = nullptr;
   }
   CK(cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, st));
   CK(ctx->d_res.reserve(sizeof(lisreg_lm_result) * (size_t)B));
@@ -604,7 +604,7 @@ int32_t lisreg_scan2map_batch_arena(lisreg_ctx* ctx, int32_t B, const lisreg_bat
     hd[b].corner = (const float4*)(d_arena + oc); hd[b].surf = (const float4*)(d_arena + os);
     hd[b].clabel = ocl != (size_t)-1 ? (const uint16_t*)(d_arena + ocl) : nullptr;
     hd[b].slabel = osl != (size_t)-1 ? (const uint16_t*)(d_arena + osl) : nullptr;
-    hd[b].nc = it.nc; hd[b].ns = it.ns; hd[b].map_slot = it.map_id; hd[b].pad = 0;
+    hd[b].nc = it.nc; hd[b].ns = it.ns; hd[b].map_slot = it.map_id; hd[b].pad = 0; hd[b].nc_ptr = nullptr; hd[b].ns_ptr = nullptr;
     max_n = std::max(max_n, it.nc + it.ns); alg += 96.0 * (it.nc + it.ns);
   }
   CK(cudaMemcpyAsync(d, h, head, cudaMemcpyHostToDevice, st));
@@ -794,6 +794,110 @@ int32_t lisreg_voxel_grid(lisreg_ctx* ctx, const float* pts, int32_t n, float le
   CK(cudaStreamSynchronize(st));
   *m = cnt;
   return LISREG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// whole-frame pipeline
+// ------------------------------------------------------------------------------------------------
+void lisreg_frame_params_default(lisreg_frame_params* p) {
+  lisreg_feat_params_default(&p->feat);
+  p->corner_leaf = 0.2f; p->surf_leaf = 0.4f;       // config/params.yaml:132-133
+  lisreg_lm_params_preset(&p->lm, 'A');
+}
+
+// d_pts_base/d_ring_base: if arena != nullptr the item pointers are byte offsets into it
+static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, const char* d_arena, uint64_t arena_bytes,
+                      float* d_pose, const lisreg_frame_params* prm, lisreg_lm_result* d_res) {
+  cudaStream_t st = ctx->stream;
+  const lisreg_feat_params* fp = &prm->feat;
+  if (fp->n_scan <= 0 || fp->horizon <= 0 || fp->horizon > 2048 || fp->n_scan * 6 > 1024 || fp->downsample_rate <= 0)
+    return fail(ctx, LISREG_ERR_ARG, "frame pipeline: unsupported n_scan/horizon/downsample_rate");
+  if (!(prm->corner_leaf > 0.f) || !(prm->surf_leaf > 0.f)) return fail(ctx, LISREG_ERR_ARG, "frame pipeline: leaf sizes must be > 0");
+  const int cells = fp->n_scan * fp->horizon;
+  const int ccap = fp->n_scan * 120;
+  int rc = feat_reserve(ctx, F, cells, fp->n_scan);
+  if (rc) return rc;
+  const size_t feat_per = feat_frame_bytes(cells, fp->n_scan) + 4096;
+  const size_t vc_per = vox_seg_bytes(ccap), vs_per = vox_seg_bytes(cells);
+  CK(ctx->d_vox.reserve((vc_per + vs_per) * (size_t)F));
+  CK(ctx->d_vox_segs.reserve(sizeof(VoxSeg) * 2 * (size_t)F));
+  CK(ctx->d_descs.reserve(sizeof(RegDesc) * (size_t)F));
+  std::vector<FeatFrame> hf((size_t)F);
+  std::vector<VoxSeg> hv(2 * (size_t)F);
+  std::vector<RegDesc> hd((size_t)F);
+  int max_n = 0; double feat_bytes = 0;
+  for (int i = 0; i < F; i++) {
+    const lisreg_frame_item& it = items[i];
+    if (it.n < 0 || it.map_id < 0 || it.map_id >= (int)ctx->maps.size() || !ctx->maps[it.map_id].used)
+      return fail(ctx, LISREG_ERR_ARG, "frame item %d: bad size or map id", i);
+    const float4* pts; const uint16_t* ring;
+    if (d_arena) {
+      const size_t op = (size_t)it.pts, orr = (size_t)it.ring;
+      if ((op & 15) || (orr & 1) || op + 16ull * it.n > arena_bytes || orr + 2ull * it.n > arena_bytes)
+        return fail(ctx, LISREG_ERR_ARG, "frame item %d: bad arena offsets", i);
+      pts = (const float4*)(d_arena + op); ring = (const uint16_t*)(d_arena + orr);
+    } else { pts = (const float4*)it.pts; ring = it.ring; }
+    FeatFrame& f = hf[i];
+    feat_carve((char*)ctx->d_feat.p + feat_per * (size_t)i, cells, fp->n_scan, &f);
+    f.pts = pts; f.ring = ring; f.n = it.n;
+    VoxSeg& vc = hv[2 * i]; VoxSeg& vs = hv[2 * i + 1];
+    char* vb = (char*)ctx->d_vox.p + (vc_per + vs_per) * (size_t)i;
+    vox_carve(vb, ccap, &vc); vox_carve(vb + vc_per, cells, &vs);
+    vc.src = f.ext_pts; vc.gather = f.corner_idx; vc.n_ptr = f.counts + 0; vc.n = 0; vc.leaf = prm->corner_leaf;
+    vs.src = f.ext_pts; vs.gather = f.surf_idx;   vs.n_ptr = f.counts + 3; vs.n = 0; vs.leaf = prm->surf_leaf;
+    RegDesc& d = hd[i];
+    d.corner = vc.out; d.surf = vs.out; d.clabel = nullptr; d.slabel = nullptr; d.nc = 0; d.ns = 0;
+    d.map_slot = it.map_id; d.pad = 0; d.nc_ptr = vc.out_n; d.ns_ptr = vs.out_n;
+    max_n = std::max(max_n, it.n); feat_bytes += 17.0 * it.n;
+  }
+  // pageable sources: cudaMemcpyAsync returns once they are consumed
+  CK(cudaMemcpyAsync(ctx->d_feat_frames.p, hf.data(), sizeof(FeatFrame) * (size_t)F, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_vox_segs.p, hv.data(), sizeof(VoxSeg) * 2 * (size_t)F, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_descs.p, hd.data(), sizeof(RegDesc) * (size_t)F, cudaMemcpyHostToDevice, st));
+  rc = run_features(ctx, (FeatFrame*)ctx->d_feat_frames.p, F, fp, max_n, feat_bytes);
+  if (rc) return rc;
+  rc = run_voxel(ctx, (VoxSeg*)ctx->d_vox_segs.p, 2 * F, std::min(max_n, cells), 2.0 * feat_bytes);
+  if (rc) return rc;
+  // the per-frame query counts live on the device; size the LM grid for the largest possible tile count
+  // of this batch (blocks beyond a frame's real tile count exit immediately).  Voxel output never exceeds
+  // its input, and the input never exceeds the sweep size.
+  const int lm_max_n = std::min(max_n, cells);
+  return run_lm(ctx, F, (const RegDesc*)ctx->d_descs.p, lm_max_n, 0.0, d_pose, &prm->lm, d_res, nullptr);
+}
+
+int32_t lisreg_frames_batch_dev(lisreg_ctx* ctx, int32_t F, const lisreg_frame_item* items, float* d_pose6xF,
+                                const lisreg_frame_params* prm, lisreg_lm_result* d_resxF) {
+  if (!ctx || F <= 0 || !items || !d_pose6xF || !prm || !d_resxF) return fail(ctx, LISREG_ERR_ARG, "lisreg_frames_batch_dev: bad argument");
+  if (prm->lm.max_iters <= 0 || prm->lm.max_iters > LISREG_MAX_ITERS) return fail(ctx, LISREG_ERR_ARG, "max_iters must be in 1..%d", LISREG_MAX_ITERS);
+  CK(cudaSetDevice(ctx->device));
+  return run_frames(ctx, F, items, nullptr, 0, d_pose6xF, prm, d_resxF);
+}
+
+int32_t lisreg_frames_batch_arena(lisreg_ctx* ctx, int32_t F, const lisreg_frame_item* items, const void* host_arena,
+                                  uint64_t arena_bytes, float* pose6xF, const lisreg_frame_params* prm, lisreg_lm_result* resxF) {
+  if (!ctx || F <= 0 || !items || !host_arena || !pose6xF || !prm || !resxF) return fail(ctx, LISREG_ERR_ARG, "lisreg_frames_batch_arena: bad argument");
+  if (prm->lm.max_iters <= 0 || prm->lm.max_iters > LISREG_MAX_ITERS) return fail(ctx, LISREG_ERR_ARG, "max_iters must be in 1..%d", LISREG_MAX_ITERS);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t head = (sizeof(float) * 6 * (size_t)F + 255) & ~size_t(255);
+  CK(ctx->d_stage.reserve(head + (size_t)arena_bytes + 16));
+  char* d = (char*)ctx->d_stage.p;
+  CK(cudaMemcpyAsync(d, pose6xF, sizeof(float) * 6 * (size_t)F, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + head, host_arena, (size_t)arena_bytes, cudaMemcpyHostToDevice, st));
+  CK(ctx->d_res.reserve(sizeof(lisreg_lm_result) * (size_t)F));
+  int rc = run_frames(ctx, F, items, d + head, arena_bytes, (float*)d, prm, (lisreg_lm_result*)ctx->d_res.p);
+  if (rc) return rc;
+  CK(ctx->h_out.reserve(sizeof(lisreg_lm_result) * (size_t)F));
+  CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_res.p, sizeof(lisreg_lm_result) * (size_t)F, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const lisreg_lm_result* hr = (const lisreg_lm_result*)ctx->h_out.p;
+  int worst = LISREG_OK;
+  for (int b = 0; b < F; b++) {
+    resxF[b] = hr[b];
+    memcpy(pose6xF + 6 * (size_t)b, hr[b].pose, sizeof(float) * 6);
+    worst = std::max(worst, hr[b].status);
+  }
+  return worst;
 }
 
 int32_t lisreg_selftest_smallmat(lisreg_ctx* ctx, const float* A36, const float* b6, float* out98) {

@@ -22,7 +22,10 @@ struct RegDesc {
   const float4* corner; const float4* surf;
   const uint16_t* clabel; const uint16_t* slabel;
   int nc, ns, map_slot, pad;
+  const int* nc_ptr; const int* ns_ptr;   // optional device-resident counts (frame pipeline); override nc/ns
 };
+__device__ __forceinline__ int reg_nc(const RegDesc& d) { return d.nc_ptr ? *d.nc_ptr : d.nc; }
+__device__ __forceinline__ int reg_ns(const RegDesc& d) { return d.ns_ptr ? *d.ns_ptr : d.ns; }
 
 struct RegState {
   float pose[6];
@@ -30,6 +33,7 @@ struct RegState {
   float trig[6];   // srx crx sry cry srz crz  (rx<-pitch, ry<-yaw, rz<-roll, :862-867)
   int iter, done, converged, degenerate, any_small, n_sel_last, status;
   float deltaR, deltaT;
+  int nc, ns;
 };
 
 struct LmParamsDev {
@@ -206,7 +210,8 @@ __global__ void k_lm_init(const RegDesc* __restrict__ descs, RegState* __restric
   s.iter = 0; s.done = 0; s.converged = 0; s.degenerate = prm.degenerate_in; s.any_small = 0; s.n_sel_last = 0; s.status = 0;
   s.deltaR = 100.f; s.deltaT = 100.f;
   const RegDesc d = descs[b];
-  if (!(d.nc > prm.edge_min && d.ns > prm.surf_min)) { s.done = 1; s.status = LISREG_NOT_ENOUGH_FEATURES; }   // :598
+  s.nc = reg_nc(d); s.ns = reg_ns(d);
+  if (!(s.nc > prm.edge_min && s.ns > prm.surf_min)) { s.done = 1; s.status = LISREG_NOT_ENOUGH_FEATURES; }   // :598
   state_refresh(s);
   states[b] = s;
   tickets[b] = 0;
@@ -219,6 +224,7 @@ __global__ void k_lm_finish(const RegState* __restrict__ states, float* __restri
   lisreg_lm_result r;
   r.status = s.status; r.iters = s.iter; r.converged = s.converged; r.is_degenerate = s.degenerate;
   r.n_sel_last = s.n_sel_last; r.deltaR = s.deltaR; r.deltaT = s.deltaT;
+  r.n_corner = s.nc; r.n_surf = s.ns;
   for (int i = 0; i < 6; i++) { r.pose[i] = s.pose[i]; pose_out[6 * b + i] = s.pose[i]; }
   res[b] = r;
 }
@@ -254,7 +260,7 @@ k_lm_iter(const RegDesc* __restrict__ descs, RegState* __restrict__ states, cons
   __shared__ int s_pos[5 * LM_MAX_TILE];
   __shared__ float s_row[7 * LM_MAX_TILE];
   __shared__ double swarp[LM_THREADS / 32][LM_NSUM];
-  if (tid == 0) { sd = descs[b]; sdone = states[b].done; }
+  if (tid == 0) { sd = descs[b]; sd.nc = states[b].nc; sd.ns = states[b].ns; sdone = states[b].done; }
   if (tid < 12) sT[tid] = states[b].T[tid];
   if (tid >= 32 && tid < 38) sTrig[tid - 32] = states[b].trig[tid - 32];
   __syncthreads();
@@ -379,7 +385,7 @@ k_lm_solve(const RegDesc* __restrict__ descs, RegState* __restrict__ states, LmP
   const int b = blockIdx.x * (LM_SOLVE_THREADS / 32) + wid;
   if (b >= B) return;
   if (states[b].done) return;
-  const int n = descs[b].nc + descs[b].ns;
+  const int n = states[b].nc + states[b].ns;
   const int ntiles = (n + tile_pts - 1) / tile_pts;
   if (lane < 29) {
     double v = 0.0;

@@ -50,6 +50,7 @@ class LmResult(C.Structure):
     _fields_ = [
         ("status", C.c_int32), ("iters", C.c_int32), ("converged", C.c_int32), ("is_degenerate", C.c_int32),
         ("n_sel_last", C.c_int32), ("deltaR", C.c_float), ("deltaT", C.c_float), ("pose", C.c_float * 6),
+        ("n_corner", C.c_int32), ("n_surf", C.c_int32),
     ]
 
 
@@ -71,6 +72,14 @@ class FeatOut(C.Structure):
                 ("start_ring", C.c_void_p), ("end_ring", C.c_void_p),
                 ("corner_idx", C.c_void_p), ("sharp_idx", C.c_void_p), ("flat_idx", C.c_void_p), ("surf_idx", C.c_void_p),
                 ("curvature", C.c_void_p), ("label", C.c_void_p)]
+
+
+class FrameParams(C.Structure):
+    _fields_ = [("feat", FeatParams), ("corner_leaf", C.c_float), ("surf_leaf", C.c_float), ("lm", LmParams)]
+
+
+class FrameItem(C.Structure):
+    _fields_ = [("pts", C.c_void_p), ("ring", C.c_void_p), ("n", C.c_int32), ("map_id", C.c_int32)]
 
 
 class Profile(C.Structure):
@@ -135,6 +144,11 @@ def lib():
         L.lisreg_extract_features.argtypes = [vp, vp, vp, i32, C.POINTER(FeatParams), C.POINTER(FeatOut)]
         L.lisreg_voxel_grid.restype = i32
         L.lisreg_voxel_grid.argtypes = [vp, vp, i32, C.c_float, vp, C.POINTER(i32)]
+        L.lisreg_frame_params_default.argtypes = [C.POINTER(FrameParams)]
+        L.lisreg_frames_batch_dev.restype = i32
+        L.lisreg_frames_batch_dev.argtypes = [vp, i32, C.POINTER(FrameItem), vp, C.POINTER(FrameParams), vp]
+        L.lisreg_frames_batch_arena.restype = i32
+        L.lisreg_frames_batch_arena.argtypes = [vp, i32, C.POINTER(FrameItem), vp, C.c_uint64, fp, C.POINTER(FrameParams), C.POINTER(LmResult)]
         L.lisreg_selftest_smallmat.restype = i32
         L.lisreg_selftest_smallmat.argtypes = [vp, fp, fp, fp]
         L.lisreg_profile_enable.restype = i32
@@ -158,6 +172,15 @@ def feat_params(**kw):
     lib().lisreg_feat_params_default(C.byref(p))
     for k, v in kw.items():
         setattr(p, k, v)
+    return p
+
+
+def frame_params(variant="A", **lm_kw):
+    p = FrameParams()
+    lib().lisreg_frame_params_default(C.byref(p))
+    lib().lisreg_lm_params_preset(C.byref(p.lm), variant.encode())
+    for k, v in lm_kw.items():
+        setattr(p.lm, k, v)
     return p
 
 
@@ -292,6 +315,33 @@ class Engine:
         m = C.c_int32(0)
         self._ck(lib().lisreg_voxel_grid(self._h, p.ctypes.data, len(p), leaf, out.ctypes.data, C.byref(m)))
         return out[:m.value].copy()
+
+    def frames_batch(self, frames, poses, params):
+        """Whole-frame pipeline on host buffers. frames: list of (map_id, pts (n,4) f32, ring (n,) u16).
+        Packs the sweeps into one arena (the e2e path). Returns (poses (F,6), [LmResult])."""
+        F = len(frames)
+        chunks, items, off = [], (FrameItem * F)(), 0
+        for i, (mid, pts, ring) in enumerate(frames):
+            p = _f4(pts); r = np.ascontiguousarray(ring, dtype=np.uint16)
+            op = off; chunks.append(p.view(np.uint8).reshape(-1)); off += p.nbytes
+            orr = off; chunks.append(r.view(np.uint8).reshape(-1)); off += r.nbytes
+            pad = (-off) % 16
+            if pad:
+                chunks.append(np.zeros(pad, np.uint8)); off += pad
+            items[i] = FrameItem(op, orr, len(p), mid)
+        arena = np.concatenate(chunks) if chunks else np.zeros(16, np.uint8)
+        pose = np.ascontiguousarray(np.asarray(poses, dtype=np.float32).reshape(F, 6)).copy()
+        res = (LmResult * F)()
+        self.last_status = self._ck(lib().lisreg_frames_batch_arena(self._h, F, items, arena.ctypes.data, arena.nbytes,
+                                                                    pose.ctypes.data_as(C.POINTER(C.c_float)), C.byref(params), res))
+        return pose, list(res)
+
+    def frames_batch_arena(self, items, F, arena_ptr, arena_bytes, pose, params, res):
+        return self._ck(lib().lisreg_frames_batch_arena(self._h, F, items, arena_ptr, arena_bytes,
+                                                        pose.ctypes.data_as(C.POINTER(C.c_float)), C.byref(params), res))
+
+    def frames_batch_dev(self, items, F, d_pose_ptr, params, d_res_ptr):
+        return self._ck(lib().lisreg_frames_batch_dev(self._h, F, items, d_pose_ptr, C.byref(params), d_res_ptr))
 
     def selftest_smallmat(self, A, b):
         A = np.ascontiguousarray(A, np.float32).reshape(36); b = np.ascontiguousarray(b, np.float32).reshape(6)

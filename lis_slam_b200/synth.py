@@ -94,6 +94,7 @@ class Scene:
         n = d.shape[0]
         best = np.full(n, np.inf)
         lab = np.zeros(n, np.uint16)
+        reach = 80.0
         with np.errstate(divide="ignore", invalid="ignore"):
             # ground
             t = (GROUND_Z - o[2]) / d[:, 2]
@@ -102,25 +103,39 @@ class Scene:
             best = np.where(ok, t, best); lab = np.where(ok, 9, lab).astype(np.uint16)
             inv = 1.0 / d
             for b, bl in zip(self.boxes, self.box_labels):
+                # cull boxes farther than the sensor reach
+                c = np.clip(o, b[:3], b[3:])
+                if np.linalg.norm(c - o) > reach:
+                    continue
                 t1 = (b[:3] - o) * inv
                 t2 = (b[3:] - o) * inv
                 tmin = np.max(np.minimum(t1, t2), axis=1)
                 tmax = np.min(np.maximum(t1, t2), axis=1)
                 ok = (tmax >= tmin) & (tmin > 0.5) & (tmin < best)
                 best = np.where(ok, tmin, best); lab = np.where(ok, bl, lab).astype(np.uint16)
-            # vertical cylinders
+            # vertical cylinders: only rays whose azimuth can see the pole are tested
             a = d[:, 0] ** 2 + d[:, 1] ** 2
+            az = np.arctan2(d[:, 1], d[:, 0])
             for (cx, cy) in self.poles:
                 ox, oy = o[0] - cx, o[1] - cy
-                if ox * ox + oy * oy > 80.0 ** 2:
+                dist = np.hypot(ox, oy)
+                if dist > reach or dist <= self.pole_r:
                     continue
-                bq = ox * d[:, 0] + oy * d[:, 1]
+                caz = np.arctan2(-oy, -ox)
+                half = np.arcsin(min(1.0, self.pole_r / dist)) + 1e-3
+                dif = np.abs(((az - caz) + np.pi) % (2 * np.pi) - np.pi)
+                sel = np.nonzero(dif <= half)[0]
+                if len(sel) == 0:
+                    continue
+                ds = d[sel]
+                bq = ox * ds[:, 0] + oy * ds[:, 1]
                 cq = ox * ox + oy * oy - self.pole_r ** 2
-                disc = bq * bq - a * cq
-                t = (-bq - np.sqrt(np.where(disc > 0, disc, np.nan))) / a
-                z = o[2] + t * d[:, 2]
-                ok = (disc > 0) & (t > 0.5) & (t < best) & (z >= GROUND_Z) & (z <= GROUND_Z + self.pole_h)
-                best = np.where(ok, t, best); lab = np.where(ok, 18, lab).astype(np.uint16)
+                disc = bq * bq - a[sel] * cq
+                t = (-bq - np.sqrt(np.where(disc > 0, disc, np.nan))) / a[sel]
+                z = o[2] + t * ds[:, 2]
+                ok = (disc > 0) & (t > 0.5) & (t < best[sel]) & (z >= GROUND_Z) & (z <= GROUND_Z + self.pole_h)
+                hit = sel[ok]
+                best[hit] = t[ok]; lab[hit] = 18
         return best, lab
 
     def scan(self, pose6, sensor="hdl64", seed=2000, noise=0.01, max_range=70.0):

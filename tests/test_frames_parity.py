@@ -1,0 +1,69 @@
+"""GPU parity: the whole-frame pipeline (features -> voxel grid -> scan-to-map LM, all on the device,
+one C-ABI call) against the same chain run with the CPU oracle.  Index/byte stages are bit-exact, so
+the query clouds are identical and the final pose must agree to the LM tolerance (1e-4 rad / 1e-3 m)."""
+import functools
+
+import numpy as np
+import pytest
+
+from lis_slam_b200 import engine as E
+from lis_slam_b200 import synth
+from oracle import orc
+
+from common import local_map, scene
+
+pytestmark = pytest.mark.gpu
+
+
+@functools.lru_cache(maxsize=None)
+def frame(seed):
+    rng = np.random.default_rng(500 + seed)
+    truth = synth.random_pose(rng)
+    guess = synth.perturb_pose(truth, rng)
+    s = scene().scan(truth, seed=2000 + seed)
+    return s, truth, guess
+
+
+def oracle_chain(s, m, guess, variant="A", **kw):
+    f = orc.extract_features(s["pts"], s["ring"])
+    ext = s["pts"][f["src_index"]]
+    corner = orc.voxel_grid(np.ascontiguousarray(ext[f["corner_idx"]]), 0.2)
+    surf = orc.voxel_grid(np.ascontiguousarray(ext[f["surf_idx"]]), 0.4)
+    pose, res, _ = orc.scan2map(corner, surf, m["corner"], m["surf"], guess, orc.lm_params(variant, **kw), log=False)
+    return pose, res, len(corner), len(surf)
+
+
+def test_frames_batch_matches_oracle_chain(engine):
+    m = local_map()
+    mid = engine.map_create(m["corner"], m["surf"], gate_hint=1.0)
+    frames = [frame(i) for i in range(3)]
+    poses, res = engine.frames_batch([(mid, s["pts"], s["ring"]) for s, _, _ in frames], [g for _, _, g in frames], E.frame_params("A"))
+    for i, (s, truth, guess) in enumerate(frames):
+        po, ro, nc, ns = oracle_chain(s, m, guess)
+        assert (res[i].n_corner, res[i].n_surf) == (nc, ns)
+        assert res[i].iters == ro.iters and res[i].status == ro.status
+        er, et = synth.pose_error(po, poses[i])
+        assert er <= 1e-4 and et <= 1e-3, (er, et)
+        er, et = synth.pose_error(truth, poses[i])
+        assert er < 3e-3 and et < 3e-2, (er, et)      # and the registration recovers the ground truth
+    engine.map_destroy(mid)
+
+
+def test_frames_fixed_iterations_and_ragged_batch(engine):
+    m = local_map()
+    mid = engine.map_create(m["corner"], m["surf"], gate_hint=1.0)
+    s0, t0, g0 = frame(0)
+    s1, t1, g1 = frame(1)
+    half = {"pts": s1["pts"][: len(s1["pts"]) // 3], "ring": s1["ring"][: len(s1["pts"]) // 3]}   # a partial sweep
+    empty = {"pts": np.zeros((0, 4), np.float32), "ring": np.zeros(0, np.uint16)}
+    prm = E.frame_params("A", early_exit=0, max_iters=10)
+    poses, res = engine.frames_batch([(mid, s0["pts"], s0["ring"]), (mid, half["pts"], half["ring"]), (mid, empty["pts"], empty["ring"])],
+                                     [g0, g1, g0], prm)
+    po, ro, nc, ns = oracle_chain(s0, m, g0, early_exit=0, max_iters=10)
+    assert res[0].iters == 10 == ro.iters
+    er, et = synth.pose_error(po, poses[0]); assert er <= 1e-4 and et <= 1e-3
+    po, ro, nc, ns = oracle_chain(half, m, g1, early_exit=0, max_iters=10)
+    assert (res[1].n_corner, res[1].n_surf) == (nc, ns) and res[1].status == ro.status
+    er, et = synth.pose_error(po, poses[1]); assert er <= 1e-4 and et <= 1e-3
+    assert res[2].status == E.NOT_ENOUGH_FEATURES and np.array_equal(poses[2], np.asarray(g0, np.float32))
+    engine.map_destroy(mid)
