@@ -1,14 +1,17 @@
 #!/usr/bin/env python
-"""bench.py — frames/sec of scan-to-map LM (64x1800-shaped scans vs 200k-pt local maps).
+"""bench.py — frames/sec of scan-to-map LM on 64x1800 HDL-64-shaped sweeps vs 200k-pt local maps.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a engine
     python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference path
 
-One "step" = one pass of the hot path over one batch of B synthetic registrations per GPU
-(throughput mode, BASELINE.json configs[2] shape; weak scaling: B per GPU is fixed).  Prints ONE
-JSON line (see README/DESIGN.md for the keys).  `value` is measured with the inputs resident in
-HBM; `e2e` goes through the C-ABI host call with a pinned host arena (H2D of every frame packet
-and D2H of the results inside the timed region).
+One "step" = one pass of the hot path over one batch of F synthetic frames per GPU (throughput mode,
+BASELINE.json configs[1] frames processed as configs[2] independent registrations; weak scaling: F per
+GPU is fixed).  A frame = raw sweep -> LOAM feature extraction -> voxel-grid down-sampling -> 10
+Gauss-Newton ("LM") iterations against its local map, i.e. what the reference does per LiDAR frame in
+laserProcessing + odomEstimation.  `--stage lm` times the registration loop alone on pre-extracted
+feature clouds.  Prints ONE JSON line.  `value` is measured with the inputs resident in HBM; `e2e` goes
+through the C-ABI host call with a pinned host arena (H2D of every raw sweep and D2H of the results inside
+the timed region).
 """
 import argparse
 import ctypes as C
@@ -86,46 +89,73 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_leg(wl, n_regs, n_threads):
-    """Times the CPU restatement (oracle) of the reference path on `n_regs` registrations of the
-    workload: kd-tree build x2 per registration (as the reference does every frame) + LM_ITERS
-    iterations.  Returns (regs/s, seconds, poses)."""
-    from oracle import orc
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (restatement of the reference's CPU path), used only as the timed baseline/checker
+# ------------------------------------------------------------------------------------------------
+def cpu_frame(orc, sw, m, guess, n_threads):
+    f = orc.extract_features(sw["pts"], sw["ring"])
+    ext = sw["pts"][f["src_index"]]
+    corner = orc.voxel_grid(np.ascontiguousarray(ext[f["corner_idx"]]), 0.2)
+    surf = orc.voxel_grid(np.ascontiguousarray(ext[f["surf_idx"]]), 0.4)
     prm = orc.lm_params("A", early_exit=0, max_iters=LM_ITERS, n_threads=n_threads)
+    pose, res, _ = orc.scan2map(corner, surf, m["corner"], m["surf"], guess, prm, log=False)
+    return pose
+
+
+def cpu_reference_leg(wl, stage, n_regs, n_threads):
+    """Times the CPU restatement on `n_regs` units of the workload (features + voxel grid + kd-tree build x2 +
+    LM_ITERS iterations per frame, exactly what the reference recomputes every frame).  Returns (units/s, s, poses)."""
+    from oracle import orc
     poses = []
     t0 = time.perf_counter()
     for r in wl["regs"][:n_regs]:
-        f, _ = wl["scans"][r["scan"]]
         m = wl["maps"][r["map"]]
-        pose, res, _ = orc.scan2map(f["corner"], f["surf"], m["corner"], m["surf"], r["guess"], prm, log=False)
-        poses.append(pose)
+        if stage == "frame":
+            poses.append(cpu_frame(orc, wl["sweeps"][r["sweep"]][0], m, r["guess"], n_threads))
+        else:
+            f, _ = wl["scans"][r["scan"]]
+            prm = orc.lm_params("A", early_exit=0, max_iters=LM_ITERS, n_threads=n_threads)
+            pose, res, _ = orc.scan2map(f["corner"], f["surf"], m["corner"], m["surf"], r["guess"], prm, log=False)
+            poses.append(pose)
     dt = time.perf_counter() - t0
     return n_regs / dt, dt, poses
+
+
+def workload_text(stage, F):
+    if stage == "frame":
+        return ("hdl64_frames_throughput (BASELINE configs[1] frames as configs[2] independent registrations): %d raw 64x1800 "
+                "ray-cast sweeps per GPU per step, each: LOAM feature extraction -> voxel grid 0.2/0.4 m -> %d LM iterations "
+                "(early exit off) vs a 200k-pt edge/surf local map" % (F, LM_ITERS))
+    return ("lm_only_throughput: %d independent registrations per GPU per step on pre-extracted feature clouds (~4k edge + ~12k "
+            "planar points) vs 200k-pt maps, %d LM iterations (early exit off)" % (F, LM_ITERS))
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     from lis_slam_b200 import workload
-    wl = workload.throughput_batch(B=max(args.ref_sample, 8), n_maps=2, n_scans=min(8, max(args.ref_sample, 8)), seed=0)
+    n = max(args.ref_sample, 4)
+    if args.stage == "frame":
+        wl = workload.frame_batch(F=n, n_maps=2, n_sweeps=min(4, n), seed=0)
+    else:
+        wl = workload.throughput_batch(B=n, n_maps=2, n_scans=min(8, n), seed=0)
     cores = os.cpu_count() or 1
     for _ in range(args.warmup):
-        cpu_reference_leg(wl, 1, cores)
+        cpu_reference_leg(wl, args.stage, 1, cores)
     t_total, n_total = 0.0, 0
     for _ in range(args.steps):
-        v, dt, _ = cpu_reference_leg(wl, args.ref_sample, cores)
+        v, dt, _ = cpu_reference_leg(wl, args.stage, args.ref_sample, cores)
         t_total += dt; n_total += args.ref_sample
     value = n_total / t_total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "throughput_batch: independent 64x1800-shaped scan-to-map registrations vs 200k-pt maps, 10 LM iters "
-                               "(CPU arm: bounded sample of %d registrations per step)" % args.ref_sample,
-                   "n_corner": 4000, "n_surf": 12000, "map_points": 200000, "lm_iters": LM_ITERS},
+        "config": {"workload": workload_text(args.stage, args.ref_sample) + " [CPU arm: bounded sample of %d per step]" % args.ref_sample,
+                   "map_points": 200000, "lm_iters": LM_ITERS},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d registrations/step x %d steps, OpenMP over points with %d threads (races fixed), "
-                                   "kd-tree rebuilt per registration like the reference" % (args.ref_sample, args.steps, cores)},
+                         "sample": "%d frames/step x %d steps; C++ restatement of the reference path (oracle/), OpenMP over points with "
+                                   "%d threads (races fixed), kd-trees rebuilt per frame like the reference" % (args.ref_sample, args.steps, cores)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -142,37 +172,61 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.Stream(dev)          # everything (engine kernels, torch copies, NCCL, events) runs on this stream
     torch.cuda.set_stream(stream)
     eng = E.Engine(device=local_rank, stream=stream.cuda_stream)
-    B = args.batch
-    wl = workload.throughput_batch(B=B, n_maps=args.maps, n_scans=args.scans, seed=rank)
+    F = args.batch
+    frame_stage = args.stage == "frame"
+    if frame_stage:
+        wl = workload.frame_batch(F=F, n_maps=args.maps, n_sweeps=args.sweeps, seed=rank)
+        arena_np, offs = workload.pack_frame_arena(wl)
+    else:
+        wl = workload.throughput_batch(B=F, n_maps=args.maps, n_scans=args.scans, seed=rank)
+        arena_np, offs = workload.pack_arena(wl)
     map_ids = [eng.map_create(m["corner"], m["surf"], gate_hint=1.0) for m in wl["maps"]]
 
-    # ---- inputs resident in HBM (one private buffer per registration) ----
-    arena_np, offs = workload.pack_arena(wl)
+    # ---- inputs resident in HBM (one private buffer per frame) ----
     arena_pin = torch.from_numpy(arena_np).pin_memory()
     arena_dev = arena_pin.to(dev, non_blocking=False)
     guess_np = np.stack([r["guess"] for r in wl["regs"]]).astype(np.float32)
     guess_dev = torch.from_numpy(guess_np).to(dev)
     pose_dev = torch.empty_like(guess_dev)
-    res_dev = torch.empty(B * C.sizeof(E.LmResult), dtype=torch.uint8, device=dev)
+    res_dev = torch.empty(F * C.sizeof(E.LmResult), dtype=torch.uint8, device=dev)
     base = arena_dev.data_ptr()
     NONE = C.c_void_p(-1).value
-    items_dev = (E.BatchItem * B)()
-    items_off = (E.BatchItem * B)()
-    n_pts = 0
-    for b, (r, o) in enumerate(zip(wl["regs"], offs)):
-        items_dev[b] = E.BatchItem(base + o["corner"], None, base + o["surf"], None, o["n_corner"], o["n_surf"], map_ids[r["map"]], 0)
-        items_off[b] = E.BatchItem(o["corner"], NONE, o["surf"], NONE, o["n_corner"], o["n_surf"], map_ids[r["map"]], 0)
-        n_pts += o["n_corner"] + o["n_surf"]
-    prm = E.lm_params("A", early_exit=0, max_iters=LM_ITERS)
+    n_raw = 0
+    if frame_stage:
+        items_dev = (E.FrameItem * F)(); items_off = (E.FrameItem * F)()
+        for b, (r, (op, og, n)) in enumerate(zip(wl["regs"], offs)):
+            items_dev[b] = E.FrameItem(base + op, base + og, n, map_ids[r["map"]])
+            items_off[b] = E.FrameItem(op, og, n, map_ids[r["map"]])
+            n_raw += n
+        prm = E.frame_params("A", early_exit=0, max_iters=LM_ITERS)
+    else:
+        items_dev = (E.BatchItem * F)(); items_off = (E.BatchItem * F)()
+        for b, (r, o) in enumerate(zip(wl["regs"], offs)):
+            items_dev[b] = E.BatchItem(base + o["corner"], None, base + o["surf"], None, o["n_corner"], o["n_surf"], map_ids[r["map"]], 0)
+            items_off[b] = E.BatchItem(o["corner"], NONE, o["surf"], NONE, o["n_corner"], o["n_surf"], map_ids[r["map"]], 0)
+        prm = E.lm_params("A", early_exit=0, max_iters=LM_ITERS)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    gathered = torch.empty(world * B, 6, dtype=torch.float32, device=dev) if world > 1 else None
+    gathered = torch.empty(world * F, 6, dtype=torch.float32, device=dev) if world > 1 else None
 
     def step_dev():
         flush.zero_()                                   # L2 flush between timed iterations
         pose_dev.copy_(guess_dev)
-        eng.scan2map_batch_dev(items_dev, B, pose_dev.data_ptr(), prm, res_dev.data_ptr())
+        if frame_stage:
+            eng.frames_batch_dev(items_dev, F, pose_dev.data_ptr(), prm, res_dev.data_ptr())
+        else:
+            eng.scan2map_batch_dev(items_dev, F, pose_dev.data_ptr(), prm, res_dev.data_ptr())
         if world > 1:                                   # the single exchange step: all-gather of the 6-DoF poses
             dist.all_gather_into_tensor(gathered, pose_dev)
+
+    pose_host = guess_np.copy()
+    res_host = (E.LmResult * F)()
+
+    def step_e2e():
+        pose_host[:] = guess_np
+        if frame_stage:
+            eng.frames_batch_arena(items_off, F, arena_pin.data_ptr(), arena_np.nbytes, pose_host, prm, res_host)
+        else:
+            eng.scan2map_batch_arena(items_off, F, arena_pin.data_ptr(), arena_np.nbytes, pose_host, prm, res_host)
 
     def barrier():
         if world > 1:
@@ -200,25 +254,25 @@ def run_ours(args, rank, world, local_rank):
     prof = eng.profile_get(reset=True)
     eng.profile_enable(False)
     pose_gpu = pose_dev.cpu().numpy().copy()
+    res_gpu = np.frombuffer(res_dev.cpu().numpy().tobytes(), dtype=np.uint8)
+    res_arr = (E.LmResult * F).from_buffer_copy(res_gpu.tobytes())
+    n_query = sum(r.n_corner + r.n_surf for r in res_arr)
 
     # ---- end-to-end timing through the host C-ABI call (pinned arena, H2D + D2H inside) ----
-    pose_host = guess_np.copy()
-    res_host = (E.LmResult * B)()
     for _ in range(2):
-        pose_host[:] = guess_np
-        eng.scan2map_batch_arena(items_off, B, arena_pin.data_ptr(), arena_np.nbytes, pose_host, prm, res_host)
+        step_e2e()
     barrier()
     t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record(stream)
     for _ in range(args.steps):
-        pose_host[:] = guess_np
-        eng.scan2map_batch_arena(items_off, B, arena_pin.data_ptr(), arena_np.nbytes, pose_host, prm, res_host)
+        step_e2e()
     f1.record(stream)
     barrier()
     ms_e2e = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - t0))
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    e2e_matches = bool(np.array_equal(pose_host, pose_gpu))
 
     # ---- max over ranks ----
     if world > 1:
@@ -227,45 +281,54 @@ def run_ours(args, rank, world, local_rank):
         ms_total, ms_e2e = float(t[0]), float(t[1])
     if rank != 0:
         return
-    value = world * B * args.steps / (ms_total * 1e-3)
-    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    value = world * F * args.steps / (ms_total * 1e-3)
+    e2e = world * F * args.steps / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel (k_lm_iter) ----
+    # ---- roofline of the dominant kernel: k_lm_iter (kNN + residual + reduce) ----
     peak, peak_src = load_peaks()
-    ach = (prof.lm_alg_bytes / max(prof.lm_iter_launches, 1)) / (prof.lm_iter_ms * 1e-3 / max(prof.lm_iter_launches, 1)) / 1e9
+    lm_launches = max(prof.lm_iter_launches, 1)
+    alg_per_launch = 96.0 * n_query                      # (nc+ns) x (16 B query + 5 x 16 B neighbours), SURVEY.md 8d A_iter
+    avg_launch_ms = prof.lm_iter_ms / lm_launches        # event pair spans k_lm_iter + the tiny k_lm_solve
+    ach = alg_per_launch / (avg_launch_ms * 1e-3) / 1e9
     traffic = load_traffic()
+    stage_ms = {"features": prof.feat_ms / args.steps, "voxel_grid": prof.voxel_ms / args.steps, "lm_iterations": prof.lm_iter_ms / args.steps}
     roofline = {"bound": "hbm", "kernel": "k_lm_iter", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "peak_source": peak_src, "traffic": (traffic or {}).get("dram_bytes_per_launch"),
-                "alg_bytes_per_launch": prof.lm_alg_bytes / max(prof.lm_iter_launches, 1),
-                "avg_launch_ms": prof.lm_iter_ms / max(prof.lm_iter_launches, 1),
-                "kernel_share_of_step": prof.lm_iter_ms / ms_total,
-                "note": "algorithmic bytes = (nc+ns) x (16 B query + 5 x 16 B neighbours) per launch (SURVEY.md 8d A_iter); "
+                "alg_bytes_per_launch": alg_per_launch, "avg_launch_ms": avg_launch_ms,
+                "kernel_share_of_step": prof.lm_iter_ms / ms_total, "stage_ms_per_step": stage_ms,
+                "regime": "maps are shared by many frames and stay L2-resident (8 x 3.2 MB); the kernel is latency/issue bound, "
+                          "not DRAM bound (see profiles/)",
+                "note": "algorithmic bytes = query points x (16 B query + 5 x 16 B neighbours) per launch (SURVEY.md 8d A_iter); "
                         "index traversal traffic excluded"}
+    a_reg = (17.0 * n_raw / F if frame_stage else 0.0) + LM_ITERS * 96.0 * n_query / F + 16.0 * 200000
+    roofline["a_reg_bytes_per_frame"] = a_reg
+    roofline["a_reg_frac_of_peak"] = a_reg * (value / world) / 1e9 / peak
 
     # ---- CPU baseline (rank 0, N=1 only) + pose error vs the CPU reference path ----
     cpu = None
     pose_err = None
     if world == 1 and not args.no_cpu:
         n_cpu = args.cpu_sample
-        v, dt, poses_cpu = cpu_reference_leg(wl, n_cpu, 1)
+        v, dt, poses_cpu = cpu_reference_leg(wl, args.stage, n_cpu, 1)
         er = [synth.pose_error(pc, pose_gpu[i]) for i, pc in enumerate(poses_cpu)]
         pose_err = {"max_rot_rad": max(e[0] for e in er), "max_trans_m": max(e[1] for e in er), "n": n_cpu,
                     "tolerance": {"rot_rad": 1e-4, "trans_m": 1e-3}}
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "%d registrations of this workload, %.1f s, 1 thread = as-built reference (its OpenMP pragmas are inert); "
-                         "kd-tree rebuilt per registration" % (n_cpu, dt)}
+               "sample": "%d frames of this workload, %.1f s, 1 thread = as-built reference (its OpenMP pragmas are inert); "
+                         "features + voxel grid + kd-tree build + %d iterations per frame" % (n_cpu, dt, LM_ITERS)}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "throughput_batch (BASELINE configs[2] shape per GPU): %d independent HDL-64-shaped scan-to-map "
-                               "registrations per GPU per step vs 200k-pt edge/surf maps, %d LM iterations, early exit off" % (B, LM_ITERS),
-                   "batch_per_gpu": B, "distinct_maps": args.maps, "distinct_scans": args.scans,
-                   "mean_query_points": n_pts / B, "map_points": 200000, "lm_iters": LM_ITERS,
+        "config": {"workload": workload_text(args.stage, F), "frames_per_gpu_per_step": F, "distinct_maps": args.maps,
+                   "distinct_sweeps": args.sweeps if frame_stage else args.scans,
+                   "mean_raw_points": n_raw / F if frame_stage else None, "mean_query_points": n_query / F,
+                   "map_points": 200000, "lm_iters": LM_ITERS,
                    "l2": "256 MB flush write between timed steps; per-step inputs %.0f MB" % (arena_np.nbytes / 1e6)},
         "clocks": sampler.summary(),
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(arena_np.nbytes + B * (48 + 24)),
-                "d2h_bytes_per_step": int(B * C.sizeof(E.LmResult)), "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(arena_np.nbytes + F * 24),
+                "d2h_bytes_per_step": int(F * C.sizeof(E.LmResult)), "ms_per_step": ms_e2e / args.steps,
+                "bit_identical_to_device_resident_run": e2e_matches},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
@@ -280,11 +343,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=512, help="registrations per GPU per step")
+    ap.add_argument("--stage", default="frame", choices=["frame", "lm"], help="frame: raw sweep -> features -> voxel -> LM; lm: LM only")
+    ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--maps", type=int, default=8)
-    ap.add_argument("--scans", type=int, default=32)
-    ap.add_argument("--cpu-sample", type=int, default=24, help="registrations timed on the CPU for cpu_baseline")
-    ap.add_argument("--ref-sample", type=int, default=16, help="registrations per step for --impl reference")
+    ap.add_argument("--sweeps", type=int, default=8, help="distinct ray-cast sweeps (frame stage)")
+    ap.add_argument("--scans", type=int, default=32, help="distinct feature clouds (lm stage)")
+    ap.add_argument("--cpu-sample", type=int, default=16, help="frames timed on the CPU for cpu_baseline")
+    ap.add_argument("--ref-sample", type=int, default=8, help="frames per step for --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
 

@@ -50,3 +50,37 @@ def pack_arena(wl):
                 chunks.append(np.zeros(pad, np.uint8)); off += pad
         offs.append(o)
     return np.concatenate(chunks), offs
+
+
+def frame_batch(F=256, n_maps=8, n_sweeps=8, map_edge=40000, map_surf=160000, seed=0, scene=None, sensor="hdl64"):
+    """BASELINE configs[1]/[2] frames: F raw 64x1800 sweeps (ray-cast HDL-64, range noise 1 cm), each with its
+    own local map id and initial guess; `n_sweeps` distinct sweeps x F/n_sweeps distinct guesses."""
+    sc = scene or synth.Scene(seed=1001)
+    rng = np.random.default_rng(5001 + 7919 * seed)
+    maps = [sc.sample_map(n_edge=map_edge, n_surf=map_surf, seed=3001 + 13 * (seed * n_maps + i)) for i in range(n_maps)]
+    sweeps = []
+    for s in range(n_sweeps):
+        truth = synth.random_pose(rng)
+        sw = sc.scan(truth, sensor=sensor, seed=2000 + 1000 * seed + s)
+        sweeps.append((sw, truth))
+    regs = []
+    for b in range(F):
+        s = b % n_sweeps
+        regs.append({"sweep": s, "map": s % n_maps, "truth": sweeps[s][1], "guess": synth.perturb_pose(sweeps[s][1], rng)})
+    return {"maps": maps, "sweeps": sweeps, "regs": regs}
+
+
+def pack_frame_arena(wl):
+    """One private copy of the raw sweep (points + ring ids) PER FRAME in a contiguous byte arena.
+    Returns (arena uint8, [(pts_off, ring_off, n)])."""
+    chunks, offs, off = [], [], 0
+    for r in wl["regs"]:
+        sw, _ = wl["sweeps"][r["sweep"]]
+        p = np.ascontiguousarray(sw["pts"], np.float32); g = np.ascontiguousarray(sw["ring"], np.uint16)
+        op = off; chunks.append(p.view(np.uint8).reshape(-1)); off += p.nbytes
+        og = off; chunks.append(g.view(np.uint8).reshape(-1)); off += g.nbytes
+        pad = (-off) % 16
+        if pad:
+            chunks.append(np.zeros(pad, np.uint8)); off += pad
+        offs.append((op, og, len(p)))
+    return np.concatenate(chunks), offs
