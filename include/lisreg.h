@@ -217,6 +217,27 @@ int32_t lisreg_frames_batch_arena(lisreg_ctx* ctx, int32_t F, const lisreg_frame
                                   const void* host_arena, uint64_t arena_bytes,
                                   float* pose6xF, const lisreg_frame_params* prm, lisreg_lm_result* resxF);
 
+/* ---- EPSC loop-closure descriptors and scoring (B3 pieces) ----
+ * lisreg_epsc_describe replaces EPSCGeneration::calculateEPSC / calculateSEPSC / calculateFEPSC
+ * (epscGeneration.cpp:478-607) for n submaps/keyframes at once; using_map is the 256-entry label -> class
+ * LUT of config/label.yaml using_label (SemanticLabelParam::UsingLableMap, utility.h:138).  Outputs are
+ * n x 1600 bytes each (20 rings x 80 sectors, row-major), any may be NULL. */
+typedef struct lisreg_epsc_cloud {
+  const float* corner; const float* surf; const float* sem; const uint16_t* sem_label;
+  int32_t nc, ns, nsem, reserved;
+} lisreg_epsc_cloud;
+int32_t lisreg_epsc_describe(lisreg_ctx* ctx, int32_t n, const lisreg_epsc_cloud* clouds, const uint8_t using_map[256],
+                             uint8_t* epsc, uint8_t* sepsc, uint8_t* fepsc);
+/* lisreg_epsc_score_all replaces the per-candidate EPSCGeneration::calculateDistance loop of loopDetection
+ * (epscGeneration.cpp:633-660, :736-860): every descriptor q is scored against its history j < q over the
+ * 20 column shifts; per query the topk (<= 8) candidates with score > DISTANCE_THRESHOLD (0.75) are returned,
+ * best first (idx = -1 when fewer qualify); shift = winning i in [-10, 10) (yaw offset = i * 2*pi/80). */
+int32_t lisreg_epsc_score_all(lisreg_ctx* ctx, const uint8_t* desc, int32_t N, int32_t topk,
+                              int32_t* idx, float* score, int8_t* shift);
+/* same with descriptors and outputs resident in HBM; asynchronous */
+int32_t lisreg_epsc_score_all_dev(lisreg_ctx* ctx, const uint8_t* d_desc, int32_t N, int32_t topk,
+                                  int32_t* d_idx, float* d_score, int8_t* d_shift);
+
 /* device self-test of the small dense routines (cv::eigen / cv::solve(QR) / cv::Mat::inv restatements):
  * out98 = E[6], V[36] (eigenvectors in rows), X[6] (QR solve of A x = b), ok, Ainv[36] (LU), ok,
  * then W3[3], V3[9] of the register-only 3x3 Jacobi applied to the leading 3x3 block of A */

@@ -1,0 +1,185 @@
+// EPSC ring-sector loop-closure descriptors and their shift-invariant scoring on the device.
+//
+// Reference: EPSCGeneration::calculateEPSC epscGeneration.cpp:478-520, calculateSEPSC :522-562,
+// calculateFEPSC :591-607 (F15); calculateDistance :633-660 (F16); constants epscGeneration.h:9-43.
+// Quirk Q4 reproduced: unsigned-char counters wrap at 256 and the quotient is narrowed mod 256.
+//
+// k_epsc_describe: one block per submap, 32-bit shared-memory histograms (count mod 256 == the
+// reference's wrapping u8 counter), then the integer quotient and the FEPSC blend.
+// k_epsc_score: byte SAD of 20 x 80 descriptors for the 20 column shifts i in [-10, 10).  One thread per
+// (history j, query q) pair; for each of the 20 rings d1 = history row (20 words) and d2 = query row
+// extended by the wrap-around (25 words) both live in REGISTERS; a shift s = i + 10 = 4a + b is one funnel shift of two adjacent d2 words and one
+// __vsadu4 (4 byte-SADs per instruction), so the inner loop has no memory traffic at all: the kernel is
+// bound by the integer ALU (SHF + VABSDIFF4 issue), not by HBM (all descriptors = 8 MB, L2 resident).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lisreg {
+
+constexpr int EPSC_RINGS = 20, EPSC_SECTORS = 80, EPSC_SIZE = 1600;
+
+struct EpscCloud {
+  const float4* corner; const float4* surf; const float4* sem; const uint16_t* sem_label;
+  int nc, ns, nsem;
+};
+
+__device__ __forceinline__ bool epsc_bin(float x, float y, int& bin) {
+  const double distance = (double)sqrtf(x * x + y * y);
+  if (distance >= 60.0 || distance < 3.0) return false;
+  const double ring_step = (60.0 - 3.0) / 20;
+  const double sector_step = 2 * 3.14159265358979323846 / 80;
+  const int ring_id = (int)floor((distance - 3.0) / ring_step);
+  const double angle = 3.14159265358979323846 + (double)(float)atan2((double)y, (double)x);
+  const int sector_id = (int)floor(angle / sector_step);
+  if (ring_id >= EPSC_RINGS || ring_id < 0) return false;
+  if (sector_id >= EPSC_SECTORS || sector_id < 0) return false;
+  bin = ring_id * EPSC_SECTORS + sector_id;
+  return true;
+}
+
+// grid = nsubmaps, block = 256.  out: [n][3][1600] = epsc, sepsc, fepsc
+__global__ void k_epsc_describe(const EpscCloud* __restrict__ clouds, const uint8_t* __restrict__ using_map, uint8_t* __restrict__ out) {
+  const EpscCloud c = clouds[blockIdx.x];
+  __shared__ unsigned esc[EPSC_SIZE], psc[EPSC_SIZE];
+  __shared__ uint8_t s_epsc[EPSC_SIZE];
+  __shared__ uint8_t s_lut[256];
+  s_lut[threadIdx.x & 255] = using_map[threadIdx.x & 255];
+  for (int i = threadIdx.x; i < EPSC_SIZE; i += blockDim.x) { esc[i] = 0u; psc[i] = 0u; }
+  __syncthreads();
+  int bin;
+  for (int i = threadIdx.x; i < c.nc; i += blockDim.x) { const float4 p = __ldg(&c.corner[i]); if (epsc_bin(p.x, p.y, bin)) atomicAdd(&esc[bin], 1u); }
+  for (int i = threadIdx.x; i < c.ns; i += blockDim.x) { const float4 p = __ldg(&c.surf[i]); if (epsc_bin(p.x, p.y, bin)) atomicAdd(&psc[bin], 1u); }
+  __syncthreads();
+  uint8_t* o = out + (size_t)blockIdx.x * 3 * EPSC_SIZE;
+  for (int i = threadIdx.x; i < EPSC_SIZE; i += blockDim.x) {
+    const int p8 = psc[i] & 255u, e8 = esc[i] & 255u;          // unsigned char counters wrap (Q4)
+    const uint8_t v = (uint8_t)((100 * p8 / (1 + e8)) & 255);   // int quotient narrowed mod 256
+    s_epsc[i] = v; o[i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < EPSC_SIZE; i += blockDim.x) { esc[i] = 0u; psc[i] = 0u; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c.nsem; i += blockDim.x) {
+    const float4 p = __ldg(&c.sem[i]);
+    if (!epsc_bin(p.x, p.y, bin)) continue;
+    const unsigned l = c.sem_label[i];
+    const int cls = l < 256u ? s_lut[l] : 0;
+    if (cls == 40 || cls == 50) atomicAdd(&psc[bin], 1u);
+    else if (cls == 81) atomicAdd(&esc[bin], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < EPSC_SIZE; i += blockDim.x) {
+    const int p8 = psc[i] & 255u, e8 = esc[i] & 255u;
+    const uint8_t sv = (uint8_t)((100 * p8 / (1 + e8)) & 255);
+    o[EPSC_SIZE + i] = sv;
+    o[2 * EPSC_SIZE + i] = (uint8_t)((double)sv * 0.4 + (double)s_epsc[i] * 0.6);   // truncation (:603)
+  }
+}
+
+// Pair scoring.  Work item = (query q, history j < q).  Pairs are enumerated over a [Q_TILE x J_TILE] tile
+// per block; thread t handles query (t / J_TILE), history (t % J_TILE) of the tile.
+constexpr int EPSC_QT = 8, EPSC_JT = 16, EPSC_THREADS = EPSC_QT * EPSC_JT;
+constexpr int EPSC_STRIDE_W = 401;   // words per descriptor in smem (+1 pad => conflict-free across descriptors)
+
+// sad_out[q * N + j] = min over shifts of the SAD (int32), shift_out = winning i in [-10, 10)
+__global__ void __launch_bounds__(EPSC_THREADS)
+k_epsc_score(const uint8_t* __restrict__ desc, int N, int* __restrict__ sad_out, int8_t* __restrict__ shift_out) {
+  const int q0 = blockIdx.y * EPSC_QT, j0 = blockIdx.x * EPSC_JT;
+  if (j0 >= q0 + EPSC_QT - 1) return;   // whole tile on/above the diagonal (needs j < q): nothing to do
+  __shared__ unsigned s_q[EPSC_QT * EPSC_STRIDE_W];
+  __shared__ unsigned s_j[EPSC_JT * EPSC_STRIDE_W];
+  const unsigned* dw = (const unsigned*)desc;
+  for (int t = threadIdx.x; t < EPSC_QT * 400; t += EPSC_THREADS) {
+    const int d = t / 400, w = t % 400;
+    s_q[d * EPSC_STRIDE_W + w] = (q0 + d < N) ? __ldg(&dw[(size_t)(q0 + d) * 400 + w]) : 0u;
+  }
+  for (int t = threadIdx.x; t < EPSC_JT * 400; t += EPSC_THREADS) {
+    const int d = t / 400, w = t % 400;
+    s_j[d * EPSC_STRIDE_W + w] = (j0 + d < N) ? __ldg(&dw[(size_t)(j0 + d) * 400 + w]) : 0u;
+  }
+  __syncthreads();
+  const int ql = threadIdx.x / EPSC_JT, jl = threadIdx.x % EPSC_JT;
+  const int q = q0 + ql, j = j0 + jl;
+  if (q >= N || j >= q) return;
+  const unsigned* dq = s_q + ql * EPSC_STRIDE_W;   // desc2 = current/query  (shifted columns)
+  const unsigned* dj = s_j + jl * EPSC_STRIDE_W;   // desc1 = history
+  unsigned sad[20];
+#pragma unroll
+  for (int s = 0; s < 20; s++) sad[s] = 0u;
+#pragma unroll 1
+  for (int ring = 0; ring < EPSC_RINGS; ring++) {
+    unsigned a[20], r[25];
+#pragma unroll
+    for (int w = 0; w < 20; w++) a[w] = dj[ring * 20 + w];
+    // extended query row: byte t of r = d2[ring][(t - 10) mod 80], t in [0, 100)
+    //   bytes 0..9   <- columns 70..79 ; bytes 10..89 <- columns 0..79 ; bytes 90..99 <- columns 0..9
+    unsigned c[20];
+#pragma unroll
+    for (int w = 0; w < 20; w++) c[w] = dq[ring * 20 + w];
+    // r is c rotated right by 10 bytes with wrap: r_word[k] = bytes (4k-10 .. 4k-7) mod 80 of c
+#pragma unroll
+    for (int k = 0; k < 25; k++) {
+      // source byte offset (4k - 10) mod 80 = 4 * ((k - 3 + 20) % 20) + 2  => funnel of words m, m+1 at 16 bits
+      const int m = (k + 17) % 20, m1 = (k + 18) % 20;
+      r[k] = __funnelshift_r(c[m], c[m1], 16);
+    }
+#pragma unroll
+    for (int s = 0; s < 20; s++) {
+      const int aa = s >> 2, bb = s & 3;
+      unsigned acc = sad[s];
+#pragma unroll
+      for (int w = 0; w < 20; w++) {
+        const unsigned x = bb == 0 ? r[w + aa] : __funnelshift_r(r[w + aa], r[w + aa + 1], 8 * bb);
+        acc = __vsadu4(a[w], x) + acc;
+      }
+      sad[s] = acc;
+    }
+  }
+  // first minimal shift wins (strict <), i = s - 10
+  unsigned best = sad[0]; int bs = 0;
+#pragma unroll
+  for (int s = 1; s < 20; s++) if (sad[s] < best) { best = sad[s]; bs = s; }
+  sad_out[(size_t)q * N + j] = (int)best;
+  shift_out[(size_t)q * N + j] = (int8_t)(bs - 10);
+}
+
+// per-query top-k among history j < q with score > 0.75 (<=> SAD < 102000): one warp per query
+__global__ void k_epsc_topk(const int* __restrict__ sad, const int8_t* __restrict__ shiftm, int N, int topk,
+                            int* __restrict__ idx, float* __restrict__ score, int8_t* __restrict__ shift) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= N) return;
+  // each lane keeps its own sorted top-k (k <= 8) of keys (sad << 32 | j), then a warp merge by repeated min
+  unsigned long long best[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) best[k] = ~0ull;
+  for (int j = lane; j < q; j += 32) {
+    const int s = sad[(size_t)q * N + j];
+    if (s >= 102000) continue;
+    unsigned long long key = ((unsigned long long)(unsigned)s << 32) | (unsigned)j;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { const bool lt = best[k] < key; const unsigned long long lo = lt ? best[k] : key; key = lt ? key : best[k]; best[k] = lo; }
+  }
+  for (int k = 0; k < topk; k++) {
+    // warp-wide minimum of the lanes' current heads
+    unsigned long long h = best[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, h, o); h = t < h ? t : h; }
+    if (best[0] == h && h != ~0ull) {   // the owning lane pops it (keys are unique: j is unique)
+#pragma unroll
+      for (int t = 0; t < 7; t++) best[t] = best[t + 1];
+      best[7] = ~0ull;
+    }
+    if (lane == 0) {
+      if (h != ~0ull) {
+        const int j = (int)(unsigned)(h & 0xffffffffull), s = (int)(unsigned)(h >> 32);
+        idx[(size_t)q * topk + k] = j;
+        score[(size_t)q * topk + k] = (float)(1.0 - (double)s / (80 * 20 * 255));
+        shift[(size_t)q * topk + k] = shiftm[(size_t)q * N + j];
+      } else { idx[(size_t)q * topk + k] = -1; score[(size_t)q * topk + k] = 0.f; shift[(size_t)q * topk + k] = 0; }
+    }
+  }
+}
+
+}  // namespace lisreg

@@ -14,6 +14,7 @@
 #include "lm.cuh"
 #include "features.cuh"
 #include "voxel.cuh"
+#include "epsc.cuh"
 
 using namespace lisreg;
 
@@ -74,6 +75,7 @@ struct lisreg_ctx {
   // feature-extraction work buffers (capacity feat_cap_frames frames of feat_cells cells)
   DevBuf d_feat, d_feat_frames;
   int feat_cap_frames = 0, feat_cells = 0, feat_nscan = 0;
+  DevBuf d_epsc, d_epsc2;
   // voxel-grid work buffers
   DevBuf d_vox, d_vox_segs;
   // profiling
@@ -328,7 +330,7 @@ void lisreg_destroy(lisreg_ctx* ctx) {
   }
   if (ctx->d_maps) cudaFree(ctx->d_maps);
   for (DevBuf* b : {&ctx->d_stage, &ctx->d_descs, &ctx->d_states, &ctx->d_partials, &ctx->d_tickets, &ctx->d_logs,
-                    &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox, &ctx->d_feat, &ctx->d_feat_frames, &ctx->d_vox, &ctx->d_vox_segs}) b->release();
+                    &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox, &ctx->d_feat, &ctx->d_feat_frames, &ctx->d_vox, &ctx->d_vox_segs, &ctx->d_epsc, &ctx->d_epsc2}) b->release();
   ctx->h_stage.release(); ctx->h_out.release();
   for (auto& p : ctx->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : ctx->ev_free) cudaEventDestroy(e);
@@ -898,6 +900,85 @@ int32_t lisreg_frames_batch_arena(lisreg_ctx* ctx, int32_t F, const lisreg_frame
     worst = std::max(worst, hr[b].status);
   }
   return worst;
+}
+
+// ------------------------------------------------------------------------------------------------
+// EPSC
+// ------------------------------------------------------------------------------------------------
+int32_t lisreg_epsc_describe(lisreg_ctx* ctx, int32_t n, const lisreg_epsc_cloud* clouds, const uint8_t using_map[256],
+                             uint8_t* epsc, uint8_t* sepsc, uint8_t* fepsc) {
+  if (!ctx || n <= 0 || !clouds || !using_map) return fail(ctx, LISREG_ERR_ARG, "lisreg_epsc_describe: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  size_t total = 256;
+  auto al = [](size_t b) { return (b + 15) & ~size_t(15); };
+  for (int i = 0; i < n; i++) {
+    const lisreg_epsc_cloud& c = clouds[i];
+    if (c.nc < 0 || c.ns < 0 || c.nsem < 0 || (c.nc && !c.corner) || (c.ns && !c.surf) || (c.nsem && (!c.sem || !c.sem_label)))
+      return fail(ctx, LISREG_ERR_ARG, "lisreg_epsc_describe: cloud %d bad", i);
+    total += al(16 * (size_t)c.nc) + al(16 * (size_t)c.ns) + al(16 * (size_t)c.nsem) + al(2 * (size_t)c.nsem);
+  }
+  total += al(sizeof(EpscCloud) * (size_t)n);
+  CK(ctx->h_stage.reserve(total));
+  CK(ctx->d_stage.reserve(total));
+  CK(ctx->d_epsc.reserve(3 * (size_t)EPSC_SIZE * n));
+  char* h = (char*)ctx->h_stage.p; char* d = (char*)ctx->d_stage.p;
+  size_t off = 0;
+  memcpy(h, using_map, 256); off = 256;
+  EpscCloud* hc = (EpscCloud*)(h + off); const size_t o_desc = off; off += al(sizeof(EpscCloud) * (size_t)n);
+  for (int i = 0; i < n; i++) {
+    const lisreg_epsc_cloud& c = clouds[i];
+    EpscCloud e{};
+    e.nc = c.nc; e.ns = c.ns; e.nsem = c.nsem;
+    if (c.nc) memcpy(h + off, c.corner, 16 * (size_t)c.nc); e.corner = (const float4*)(d + off); off += al(16 * (size_t)c.nc);
+    if (c.ns) memcpy(h + off, c.surf, 16 * (size_t)c.ns); e.surf = (const float4*)(d + off); off += al(16 * (size_t)c.ns);
+    if (c.nsem) memcpy(h + off, c.sem, 16 * (size_t)c.nsem); e.sem = (const float4*)(d + off); off += al(16 * (size_t)c.nsem);
+    if (c.nsem) memcpy(h + off, c.sem_label, 2 * (size_t)c.nsem); e.sem_label = (const uint16_t*)(d + off); off += al(2 * (size_t)c.nsem);
+    hc[i] = e;
+  }
+  CK(cudaMemcpyAsync(d, h, off, cudaMemcpyHostToDevice, st));
+  k_epsc_describe<<<n, 256, 0, st>>>((const EpscCloud*)(d + o_desc), (const uint8_t*)d, (uint8_t*)ctx->d_epsc.p); LAUNCH_CK();
+  CK(ctx->h_out.reserve(3 * (size_t)EPSC_SIZE * n));
+  CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_epsc.p, 3 * (size_t)EPSC_SIZE * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const uint8_t* o = (const uint8_t*)ctx->h_out.p;
+  for (int i = 0; i < n; i++) {
+    if (epsc) memcpy(epsc + (size_t)i * EPSC_SIZE, o + (size_t)i * 3 * EPSC_SIZE, EPSC_SIZE);
+    if (sepsc) memcpy(sepsc + (size_t)i * EPSC_SIZE, o + (size_t)i * 3 * EPSC_SIZE + EPSC_SIZE, EPSC_SIZE);
+    if (fepsc) memcpy(fepsc + (size_t)i * EPSC_SIZE, o + (size_t)i * 3 * EPSC_SIZE + 2 * EPSC_SIZE, EPSC_SIZE);
+  }
+  return LISREG_OK;
+}
+
+int32_t lisreg_epsc_score_all_dev(lisreg_ctx* ctx, const uint8_t* d_desc, int32_t N, int32_t topk,
+                                  int32_t* d_idx, float* d_score, int8_t* d_shift) {
+  if (!ctx || N <= 0 || !d_desc || topk <= 0 || topk > 8 || !d_idx || !d_score || !d_shift) return fail(ctx, LISREG_ERR_ARG, "lisreg_epsc_score_all: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CK(ctx->d_epsc2.reserve((size_t)N * N * 5 + 64));
+  int* sad = (int*)ctx->d_epsc2.p;
+  int8_t* shm = (int8_t*)(sad + (size_t)N * N);
+  dim3 grid((N + EPSC_JT - 1) / EPSC_JT, (N + EPSC_QT - 1) / EPSC_QT);
+  k_epsc_score<<<grid, EPSC_THREADS, 0, st>>>(d_desc, N, sad, shm); LAUNCH_CK();
+  k_epsc_topk<<<(N + 3) / 4, 128, 0, st>>>(sad, shm, N, topk, d_idx, d_score, d_shift); LAUNCH_CK();
+  return LISREG_OK;
+}
+
+int32_t lisreg_epsc_score_all(lisreg_ctx* ctx, const uint8_t* desc, int32_t N, int32_t topk, int32_t* idx, float* score, int8_t* shift) {
+  if (!ctx || N <= 0 || !desc || topk <= 0 || topk > 8 || !idx || !score || !shift) return fail(ctx, LISREG_ERR_ARG, "lisreg_epsc_score_all: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t bd = (size_t)N * EPSC_SIZE, bi = 4 * (size_t)N * topk, bs = 4 * (size_t)N * topk, bh = (size_t)N * topk;
+  CK(ctx->d_epsc.reserve(bd + bi + bs + bh + 64));
+  char* d = (char*)ctx->d_epsc.p;
+  CK(cudaMemcpyAsync(d, desc, bd, cudaMemcpyHostToDevice, st));
+  int rc = lisreg_epsc_score_all_dev(ctx, (const uint8_t*)d, N, topk, (int32_t*)(d + bd), (float*)(d + bd + bi), (int8_t*)(d + bd + bi + bs));
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(idx, d + bd, bi, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(score, d + bd + bi, bs, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(shift, d + bd + bi + bs, bh, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return LISREG_OK;
 }
 
 int32_t lisreg_selftest_smallmat(lisreg_ctx* ctx, const float* A36, const float* b6, float* out98) {

@@ -82,6 +82,11 @@ class FrameItem(C.Structure):
     _fields_ = [("pts", C.c_void_p), ("ring", C.c_void_p), ("n", C.c_int32), ("map_id", C.c_int32)]
 
 
+class EpscCloud(C.Structure):
+    _fields_ = [("corner", C.c_void_p), ("surf", C.c_void_p), ("sem", C.c_void_p), ("sem_label", C.c_void_p),
+                ("nc", C.c_int32), ("ns", C.c_int32), ("nsem", C.c_int32), ("reserved", C.c_int32)]
+
+
 class Profile(C.Structure):
     _fields_ = [
         ("lm_iter_ms", C.c_double), ("lm_iter_launches", C.c_int64), ("lm_alg_bytes", C.c_double),
@@ -149,6 +154,12 @@ def lib():
         L.lisreg_frames_batch_dev.argtypes = [vp, i32, C.POINTER(FrameItem), vp, C.POINTER(FrameParams), vp]
         L.lisreg_frames_batch_arena.restype = i32
         L.lisreg_frames_batch_arena.argtypes = [vp, i32, C.POINTER(FrameItem), vp, C.c_uint64, fp, C.POINTER(FrameParams), C.POINTER(LmResult)]
+        L.lisreg_epsc_describe.restype = i32
+        L.lisreg_epsc_describe.argtypes = [vp, i32, C.POINTER(EpscCloud), vp, vp, vp, vp]
+        L.lisreg_epsc_score_all.restype = i32
+        L.lisreg_epsc_score_all.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+        L.lisreg_epsc_score_all_dev.restype = i32
+        L.lisreg_epsc_score_all_dev.argtypes = [vp, vp, i32, i32, vp, vp, vp]
         L.lisreg_selftest_smallmat.restype = i32
         L.lisreg_selftest_smallmat.argtypes = [vp, fp, fp, fp]
         L.lisreg_profile_enable.restype = i32
@@ -342,6 +353,26 @@ class Engine:
 
     def frames_batch_dev(self, items, F, d_pose_ptr, params, d_res_ptr):
         return self._ck(lib().lisreg_frames_batch_dev(self._h, F, items, d_pose_ptr, C.byref(params), d_res_ptr))
+
+    def epsc_describe(self, clouds, using_map):
+        """clouds: list of (corner (n,4), surf (n,4), sem (n,4), sem_label (n,)). Returns dict of (n,20,80) u8 arrays."""
+        n = len(clouds)
+        arr = (EpscCloud * n)(); keep = []
+        for i, (c, s, m, l) in enumerate(clouds):
+            c, s, m = _f4(c), _f4(s), _f4(m); l = np.ascontiguousarray(l, np.uint16)
+            keep.append((c, s, m, l))
+            arr[i] = EpscCloud(c.ctypes.data, s.ctypes.data, m.ctypes.data, l.ctypes.data, len(c), len(s), len(m), 0)
+        lut = np.ascontiguousarray(using_map, np.uint8)
+        out = [np.zeros((n, 20, 80), np.uint8) for _ in range(3)]
+        self._ck(lib().lisreg_epsc_describe(self._h, n, arr, lut.ctypes.data, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data))
+        return {"epsc": out[0], "sepsc": out[1], "fepsc": out[2]}
+
+    def epsc_score_all(self, desc, topk=5):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 1600)
+        N = len(d)
+        idx = np.zeros((N, topk), np.int32); score = np.zeros((N, topk), np.float32); shift = np.zeros((N, topk), np.int8)
+        self._ck(lib().lisreg_epsc_score_all(self._h, d.ctypes.data, N, topk, idx.ctypes.data, score.ctypes.data, shift.ctypes.data))
+        return idx, score, shift
 
     def selftest_smallmat(self, A, b):
         A = np.ascontiguousarray(A, np.float32).reshape(36); b = np.ascontiguousarray(b, np.float32).reshape(6)

@@ -114,6 +114,11 @@ def lib():
         L.orc_extract_features.argtypes = [fp, ip, C.c_int32, ip, ip, C.POINTER(FeatParams), ip, ip, ip, ip, ip, ip, ip, ip, fp, ip]
         L.orc_voxel_grid.restype = C.c_int32
         L.orc_voxel_grid.argtypes = [fp, C.c_int32, C.c_float, fp, C.c_int32]
+        u8p = C.POINTER(C.c_uint8)
+        L.orc_epsc_describe.argtypes = [fp, C.c_int32, fp, C.c_int32, fp, u16p, C.c_int32, u8p, u8p, u8p, u8p]
+        L.orc_epsc_distance.restype = C.c_double
+        L.orc_epsc_distance.argtypes = [u8p, u8p, ip, ip]
+        L.orc_epsc_score_all.argtypes = [u8p, C.c_int32, C.c_int32, ip, fp, C.POINTER(C.c_int8), C.c_int32]
         _LIB = L
     return _LIB
 
@@ -232,3 +237,43 @@ def voxel_grid(pts4, leaf):
     out = np.zeros((max(len(p), 1), 4), np.float32)
     m = lib().orc_voxel_grid(pp, len(p), leaf, out.ctypes.data_as(C.POINTER(C.c_float)), len(out))
     return out[:m].copy()
+
+
+# using_label of config/label.yaml:187-206: label -> class {10 dynamic, 40 ground, 50 building, 81 pole, 70 outlier}
+USING_LABEL = {1: 10, 2: 10, 3: 10, 4: 10, 5: 10, 6: 10, 7: 10, 8: 10, 9: 40, 10: 40, 11: 40, 12: 70, 13: 50, 14: 50,
+               15: 70, 16: 81, 17: 70, 18: 81, 19: 81}
+
+
+def using_map_lut():
+    lut = np.zeros(256, np.uint8)
+    for k, v in USING_LABEL.items():
+        lut[k] = v
+    return lut
+
+
+def epsc_describe(corner4, surf4, sem4, sem_label, lut=None):
+    c, cp = _f(corner4); s, sp = _f(surf4); m, mp = _f(sem4)
+    lab = np.ascontiguousarray(sem_label, np.uint16)
+    lut = using_map_lut() if lut is None else np.ascontiguousarray(lut, np.uint8)
+    u8p = C.POINTER(C.c_uint8)
+    out = [np.zeros(1600, np.uint8) for _ in range(3)]
+    lib().orc_epsc_describe(cp, len(c), sp, len(s), mp, lab.ctypes.data_as(C.POINTER(C.c_uint16)), len(m),
+                            lut.ctypes.data_as(u8p), *[o.ctypes.data_as(u8p) for o in out])
+    return {"epsc": out[0].reshape(20, 80), "sepsc": out[1].reshape(20, 80), "fepsc": out[2].reshape(20, 80)}
+
+
+def epsc_distance(d1, d2):
+    a = np.ascontiguousarray(d1, np.uint8).reshape(-1); b = np.ascontiguousarray(d2, np.uint8).reshape(-1)
+    u8p = C.POINTER(C.c_uint8)
+    sh, sad = C.c_int32(0), C.c_int32(0)
+    sc = lib().orc_epsc_distance(a.ctypes.data_as(u8p), b.ctypes.data_as(u8p), C.byref(sh), C.byref(sad))
+    return sc, sh.value, sad.value
+
+
+def epsc_score_all(desc, topk=5, n_threads=1):
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 1600)
+    N = len(d)
+    idx = np.zeros((N, topk), np.int32); score = np.zeros((N, topk), np.float32); shift = np.zeros((N, topk), np.int8)
+    lib().orc_epsc_score_all(d.ctypes.data_as(C.POINTER(C.c_uint8)), N, topk, idx.ctypes.data_as(C.POINTER(C.c_int32)),
+                             score.ctypes.data_as(C.POINTER(C.c_float)), shift.ctypes.data_as(C.POINTER(C.c_int8)), n_threads)
+    return idx, score, shift

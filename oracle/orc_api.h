@@ -90,6 +90,13 @@ void orc_extract_features(const float* range, const int32_t* col_ind, int32_t M,
 /* ---- pcl::VoxelGrid<PointXYZI> centroid down-sampling (odomEstimationNode.cpp:196-201, :272-277) ---- */
 int32_t orc_voxel_grid(const float* pts4, int32_t n, float leaf, float* out4, int32_t cap);
 
+/* ---- EPSC descriptors + scoring (epscGeneration.cpp:478-607, :633-660) ---- */
+void orc_epsc_describe(const float* corner4, int32_t nc, const float* surf4, int32_t ns,
+                       const float* sem4, const uint16_t* sem_label, int32_t nsem, const uint8_t* using_map,
+                       uint8_t* epsc, uint8_t* sepsc, uint8_t* fepsc);
+double orc_epsc_distance(const uint8_t* d1, const uint8_t* d2, int32_t* best_shift, int32_t* min_sad);
+void orc_epsc_score_all(const uint8_t* desc, int32_t N, int32_t topk, int32_t* idx, float* score, int8_t* shift, int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif
