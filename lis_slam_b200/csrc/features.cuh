@@ -169,33 +169,49 @@ __global__ void k_feat_occlusion(FeatFrame* frames) {
 // ---- F5 ----
 constexpr int FEAT_SEG_MAX = 512;       // max points of one segment handled in shared memory
 constexpr int FEAT_WARPS = 4;           // rings per block
+constexpr int FEAT_RING_MAX = 2048 + 16; // staged ring window (horizon <= 2048, +-6 apron)
 
-__device__ __forceinline__ void feat_mark_neighbours(const FeatFrame& f, int ind, int M) {
+// Neighbour suppression of a pick (:648-661) on the ring window staged in shared memory.
+// lo = global index of window slot 0; indices outside [0, M) or outside the window end the walk
+// (the window covers [first-6, last+6] of the ring, the only indices a pick of this ring can reach).
+__device__ __forceinline__ void feat_mark_neighbours(unsigned char* spick, const unsigned short* scol, int lo, int wlen, int ind, int M) {
   for (int l = 1; l <= 5; l++) {
     const int a = ind + l, b = ind + l - 1;
-    if (a < 0 || a >= M || b < 0 || b >= M) break;
-    if (abs(f.col[a] - f.col[b]) > 10) break;
-    f.picked[a] = 1;
+    if (a < 0 || a >= M || b < 0 || b >= M || a - lo >= wlen || b - lo < 0) break;
+    if (abs((int)scol[a - lo] - (int)scol[b - lo]) > 10) break;
+    spick[a - lo] = 1;
   }
   for (int l = -1; l >= -5; l--) {
     const int a = ind + l, b = ind + l + 1;
-    if (a < 0 || a >= M || b < 0 || b >= M) break;
-    if (abs(f.col[a] - f.col[b]) > 10) break;
-    f.picked[a] = 1;
+    if (a < 0 || a >= M || b < 0 || b >= M || a - lo < 0 || b - lo >= wlen) break;
+    if (abs((int)scol[a - lo] - (int)scol[b - lo]) > 10) break;
+    spick[a - lo] = 1;
   }
 }
 
-// one warp per (frame, ring).  grid = (ceil(n_scan / FEAT_WARPS), F), block = 32 * FEAT_WARPS
+// one warp per (frame, ring).  grid = (ceil(n_scan / FEAT_WARPS), F), block = 32 * FEAT_WARPS.
+// The ring's picked flags and column indices are staged in shared memory so that the sequential greedy
+// passes of lane 0 never wait on global memory; curvature comes from the sorted key itself.
 __global__ void __launch_bounds__(32 * FEAT_WARPS)
 k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
   const FeatFrame f = frames[blockIdx.y];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int ring = blockIdx.x * FEAT_WARPS + wid;
   __shared__ unsigned long long s_key[FEAT_WARPS][FEAT_SEG_MAX];
+  __shared__ unsigned char s_pick[FEAT_WARPS][FEAT_RING_MAX];
+  __shared__ unsigned short s_col[FEAT_WARPS][FEAT_RING_MAX];
   if (ring >= prm.n_scan) return;
   const int M = *f.M;
   const int start = f.ring_start[ring], end = f.ring_end[ring];
   unsigned long long* key = s_key[wid];
+  unsigned char* spick = s_pick[wid];
+  unsigned short* scol = s_col[wid];
+  // ring = extracted indices [first, last] with first = start - 4, last = end + 5; window adds a +-6 apron
+  const int lo = max(start - 4 - 6, 0);
+  const int hi = min(end + 5 + 6, M - 1);
+  const int wlen = max(hi - lo + 1, 0);
+  for (int t = lane; t < wlen; t += 32) { spick[t] = (unsigned char)f.picked[lo + t]; scol[t] = (unsigned short)f.col[lo + t]; }
+  __syncwarp();
   for (int j = 0; j < 6; j++) {
     const int seg = ring * 6 + j;
     const int sp = (start * (6 - j) + end * j) / 6;
@@ -205,7 +221,8 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
     const int len = ep - sp;            // sorted range [sp, ep); element ep stays in place (Q3)
     // ---- sort (curvature bits << 32 | index); curvature >= 0 so integer order == (value, index) order ----
     int npad = 1; while (npad < len) npad <<= 1;
-    if (npad <= FEAT_SEG_MAX) {
+    const bool in_smem = npad <= FEAT_SEG_MAX;
+    if (in_smem) {
       for (int t = lane; t < npad; t += 32) {
         const int i = sp + t;
         key[t] = t < len ? (((unsigned long long)__float_as_uint(f.curv[i]) << 32) | (unsigned)i) : ~0ull;
@@ -224,51 +241,53 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
           __syncwarp();
         }
     } else {
-      // oversize segment (never for 1800 columns / 6): slow in-place insertion sort by lane 0 in global scratch
+      // oversize segment (never for <= 2048 columns / 6): slow insertion sort by lane 0 in global scratch
       if (lane == 0) {
-        for (int t = 0; t < len; t++) f.owner[t] = sp + t;    // owner[] is free after compaction; reuse as scratch
+        for (int t = 0; t < len; t++) f.owner[t + ring * prm.horizon] = sp + t;    // owner[] is free after compaction
+        int* o = f.owner + ring * prm.horizon;
         for (int a = 1; a < len; a++) {
-          const int v = f.owner[a]; const float cv = f.curv[v]; int b = a;
-          while (b > 0 && (f.curv[f.owner[b - 1]] > cv || (f.curv[f.owner[b - 1]] == cv && f.owner[b - 1] > v))) { f.owner[b] = f.owner[b - 1]; b--; }
-          f.owner[b] = v;
+          const int v = o[a]; const float cv = f.curv[v]; int b = a;
+          while (b > 0 && (f.curv[o[b - 1]] > cv || (f.curv[o[b - 1]] == cv && o[b - 1] > v))) { o[b] = o[b - 1]; b--; }
+          o[b] = v;
         }
       }
       __syncwarp();
     }
-    // ---- greedy passes by lane 0 ----
+    // ---- greedy passes by lane 0 (order-dependent non-maximum suppression) ----
     if (lane == 0) {
-      const bool in_smem = npad <= FEAT_SEG_MAX;
-      auto sorted_ind = [&](int k) -> int {   // k in [sp, ep]
-        if (k == ep) return ep;
-        return in_smem ? (int)(unsigned)(key[k - sp] & 0xffffffffull) : f.owner[k - sp];
-      };
+      const int* o = f.owner + ring * prm.horizon;
+      const float cv_ep = f.curv[ep];
       int largestPickedNum = 0, nc = 0;
       for (int k = ep; k >= sp; k--) {
-        const int ind = sorted_ind(k);
-        const float cv = f.curv[ind];
+        int ind; float cv;
+        if (k == ep) { ind = ep; cv = cv_ep; }
+        else if (in_smem) { const unsigned long long kk = key[k - sp]; ind = (int)(unsigned)(kk & 0xffffffffull); cv = __uint_as_float((unsigned)(kk >> 32)); }
+        else { ind = o[k - sp]; cv = f.curv[ind]; }
         if (k < ep && !(cv > prm.edge_thr)) break;   // sorted ascending: nothing below can qualify
-        if (f.picked[ind] == 0 && cv > prm.edge_thr) {
+        if (spick[ind - lo] == 0 && cv > prm.edge_thr) {
           largestPickedNum++;
           if (largestPickedNum <= 20) {
             f.label[ind] = 1;
             f.seg_corner[seg * 20 + nc] = ind; nc++;
           } else break;
-          f.picked[ind] = 1;
-          feat_mark_neighbours(f, ind, M);
+          spick[ind - lo] = 1;
+          feat_mark_neighbours(spick, scol, lo, wlen, ind, M);
         }
       }
       f.seg_ncorner[seg] = nc;
       largestPickedNum = 0; int nf = 0;
       for (int k = sp; k <= ep; k++) {
-        const int ind = sorted_ind(k);
-        const float cv = f.curv[ind];
+        int ind; float cv;
+        if (k == ep) { ind = ep; cv = cv_ep; }
+        else if (in_smem) { const unsigned long long kk = key[k - sp]; ind = (int)(unsigned)(kk & 0xffffffffull); cv = __uint_as_float((unsigned)(kk >> 32)); }
+        else { ind = o[k - sp]; cv = f.curv[ind]; }
         if (k < ep && !(cv < prm.surf_thr)) { k = ep - 1; continue; }   // skip to the unsorted element ep
-        if (f.picked[ind] == 0 && cv < prm.surf_thr) {
+        if (spick[ind - lo] == 0 && cv < prm.surf_thr) {
           largestPickedNum++;
           f.label[ind] = -1;
-          f.picked[ind] = 1;
+          spick[ind - lo] = 1;
           if (largestPickedNum <= 10) { f.seg_flat[seg * 10 + nf] = ind; nf++; }
-          feat_mark_neighbours(f, ind, M);
+          feat_mark_neighbours(spick, scol, lo, wlen, ind, M);
         }
       }
       f.seg_nflat[seg] = nf;

@@ -470,7 +470,10 @@ static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, dou
   double* partials = (double*)ctx->d_partials.p;
   int* tickets = (int*)ctx->d_tickets.p;
   k_lm_init<<<(B + 127) / 128, 128, 0, st>>>(d_descs, states, d_pose, dp, tickets, B); LAUNCH_CK();
-  dim3 grid(max_tiles, B);
+  // a block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...: batches get 32 blocks per registration
+  // (the real tile count is only known on the device in the frame pipeline), a lone registration gets
+  // one block per tile so that it spreads over the whole GPU
+  dim3 grid(std::min(max_tiles, B >= 32 ? 32 : 1024), B);
   {
     ProfScope ps(ctx, PROF_LM, alg_bytes_per_iter * dp.max_iters, dp.max_iters);
     for (int it = 0; it < dp.max_iters; it++) {
@@ -735,7 +738,7 @@ static size_t vox_seg_bytes(int cap) {
   size_t b = 4 * (size_t)cap * 4;                 // key_a, val_a, key_b, val_b
   b += 4 * 256 * (size_t)nblk;                    // hist
   b += 4 * ((size_t)cap + 1);                     // seg_start
-  b += sizeof(VoxPlan) + 16;                      // plan, out_n
+  b += sizeof(VoxPlan) + 16 + 32;                 // plan, out_n, bbox
   b += sizeof(float4) * (size_t)cap;              // out
   return (b + 1024) & ~size_t(255);
 }
@@ -749,6 +752,7 @@ static void vox_carve(char* base, int cap, VoxSeg* s) {
   s->hist = (uint32_t*)take(4 * 256 * (size_t)nblk);
   s->seg_start = (int*)take(4 * ((size_t)cap + 1));
   s->plan = (VoxPlan*)take(sizeof(VoxPlan));
+  s->bbox = (unsigned*)take(24);
   s->out_n = (int*)take(4);
   s->cap = cap;
 }
@@ -760,7 +764,9 @@ static int run_voxel(lisreg_ctx* ctx, VoxSeg* d_segs, int nseg, int max_n, doubl
   const int nblk = std::max(1, (max_n + RS_TILE - 1) / RS_TILE);
   const int pblk = std::max(1, std::min(64, (max_n + 1023) / 1024));
   ProfScope ps(ctx, PROF_VOXEL, alg_bytes, 16);
-  k_vox_plan<<<nseg, 256, 0, st>>>(d_segs); LAUNCH_CK();
+  k_vox_bbox_init<<<(nseg * 6 + 255) / 256, 256, 0, st>>>(d_segs, nseg); LAUNCH_CK();
+  k_vox_bbox<<<dim3(pblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
+  k_vox_plan<<<(nseg + 127) / 128, 128, 0, st>>>(d_segs, nseg); LAUNCH_CK();
   k_vox_keys<<<dim3(pblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
   for (int pass = 0; pass < 4; pass++) {
     k_rs_hist<<<dim3(nblk, nseg), RS_THREADS, 0, st>>>(d_segs, 8 * pass, pass & 1); LAUNCH_CK();

@@ -253,7 +253,7 @@ constexpr int LM_MAX_TILE = 512;
 __global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS)
 k_lm_iter(const RegDesc* __restrict__ descs, RegState* __restrict__ states, const MapDev* __restrict__ maps,
           LmParamsDev prm, double* __restrict__ partials, int max_tiles, int tile_pts) {
-  const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.y, tid = threadIdx.x;
   __shared__ RegDesc sd;
   __shared__ float sT[12], sTrig[6];
   __shared__ int sdone;
@@ -267,8 +267,10 @@ k_lm_iter(const RegDesc* __restrict__ descs, RegState* __restrict__ states, cons
   if (sdone) return;
   const int n = sd.nc + sd.ns;
   const int ntiles = (n + tile_pts - 1) / tile_pts;
-  if (tile >= ntiles) return;
   const MapDev& mp = maps[sd.map_slot];
+  const float srx = sTrig[0], crx = sTrig[1], sry = sTrig[2], cry = sTrig[3], srz = sTrig[4], crz = sTrig[5];
+  const int lane = tid & 31, wid = tid >> 5;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
   const int q0 = tile * tile_pts;
   const int qn = min(n - q0, tile_pts);   // queries in this tile
 
@@ -297,7 +299,6 @@ k_lm_iter(const RegDesc* __restrict__ descs, RegState* __restrict__ states, cons
   }
 
   // ---------------- phase B: coefficients + Jacobian rows ----------------
-  const float srx = sTrig[0], crx = sTrig[1], sry = sTrig[2], cry = sTrig[3], srz = sTrig[4], crz = sTrig[5];
   int cntC = 0, cntS = 0;
   for (int l = tid; l < tile_pts; l += LM_THREADS) {
     float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -347,7 +348,6 @@ k_lm_iter(const RegDesc* __restrict__ descs, RegState* __restrict__ states, cons
   __syncthreads();
 
   // ---------------- phase C: 27 products, fp64 ----------------
-  const int lane = tid & 31, wid = tid >> 5;
   {
     int r, c;
     lm_pair_of_lane(lane < 27 ? lane : 0, r, c);
@@ -369,6 +369,8 @@ k_lm_iter(const RegDesc* __restrict__ descs, RegState* __restrict__ states, cons
 #pragma unroll
     for (int w2 = 0; w2 < LM_THREADS / 32; w2++) v += swarp[w2][tid];
     mypart[tid] = v;
+  }
+  __syncthreads();   // smem is reused by the next tile
   }
 }
 

@@ -30,6 +30,7 @@ struct VoxSeg {
   uint32_t* hist;          // 256 * nblk_cap
   int* seg_start;          // cap + 1 : voxel starts (positions in the sorted arrays)
   VoxPlan* plan;
+  unsigned* bbox;          // 6 order-preserving encoded floats (min xyz, max xyz)
   float4* out;             // cap
   int* out_n;              // number of voxels
   int cap;
@@ -41,48 +42,67 @@ constexpr int RS_THREADS = 256;
 __device__ __forceinline__ int vox_n(const VoxSeg& s) { return s.n_ptr ? *s.n_ptr : s.n; }
 __device__ __forceinline__ float4 vox_point(const VoxSeg& s, int i) { return __ldg(&s.src[s.gather ? s.gather[i] : i]); }
 
-// (1) bounding box + plan: one block per cloud
-__global__ void k_vox_plan(VoxSeg* segs) {
-  const VoxSeg s = segs[blockIdx.x];
+// (1) bounding box (multi-block, order-preserving integer atomics) + plan
+__device__ __forceinline__ unsigned vox_f2ord(float f) { unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float vox_ord2f(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+__global__ void k_vox_bbox_init(VoxSeg* segs, int nseg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nseg * 6) return;
+  segs[i / 6].bbox[i % 6] = (i % 6) < 3 ? 0xffffffffu : 0u;
+}
+
+// grid = (blocks, nseg)
+__global__ void k_vox_bbox(VoxSeg* segs) {
+  const VoxSeg s = segs[blockIdx.y];
   const int n = vox_n(s);
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  bool any = false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 p = vox_point(s, i);
     mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
     mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+    any = true;
   }
-  __shared__ float smn[3][32], smx[3][32];
+  if (!__any_sync(0xffffffffu, any)) return;
 #pragma unroll
-  for (int d = 0; d < 3; d++) {
+  for (int d = 0; d < 3; d++)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
       mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
     }
-    if ((threadIdx.x & 31) == 0) { smn[d][threadIdx.x >> 5] = mn[d]; smx[d][threadIdx.x >> 5] = mx[d]; }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) { atomicMin(&s.bbox[d], vox_f2ord(mn[d])); atomicMax(&s.bbox[3 + d], vox_f2ord(mx[d])); }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int nw = (blockDim.x + 31) / 32;
-    for (int d = 0; d < 3; d++) for (int w = 1; w < nw; w++) { smn[d][0] = fminf(smn[d][0], smn[d][w]); smx[d][0] = fmaxf(smx[d][0], smx[d][w]); }
-    VoxPlan p;
-    p.inv = 1.0f / s.leaf;
-    p.overflow = 0;
-    if (n > 0) {
-      const long long dx = (long long)((smx[0][0] - smn[0][0]) * p.inv) + 1, dy = (long long)((smx[1][0] - smn[1][0]) * p.inv) + 1,
-                      dz = (long long)((smx[2][0] - smn[2][0]) * p.inv) + 1;
-      if (dx * dy * dz > 2147483647LL) p.overflow = 1;   // PCL: "leaf size is too small" -> output = input
-      int divb[3];
-      for (int d = 0; d < 3; d++) {
-        p.minb[d] = (int)floorf(smn[d][0] * p.inv);
-        divb[d] = (int)floorf(smx[d][0] * p.inv) - p.minb[d] + 1;
-      }
-      p.mul[0] = 1; p.mul[1] = divb[0]; p.mul[2] = divb[0] * divb[1];
-    } else {
-      for (int d = 0; d < 3; d++) { p.minb[d] = 0; p.mul[d] = 0; }
+}
+
+// one thread per cloud
+__global__ void k_vox_plan(VoxSeg* segs, int nseg) {
+  const int si = blockIdx.x * blockDim.x + threadIdx.x;
+  if (si >= nseg) return;
+  const VoxSeg s = segs[si];
+  const int n = vox_n(s);
+  VoxPlan p;
+  p.inv = 1.0f / s.leaf;
+  p.overflow = 0;
+  if (n > 0) {
+    float mn[3], mx[3];
+    for (int d = 0; d < 3; d++) { mn[d] = vox_ord2f(s.bbox[d]); mx[d] = vox_ord2f(s.bbox[3 + d]); }
+    const long long dx = (long long)((mx[0] - mn[0]) * p.inv) + 1, dy = (long long)((mx[1] - mn[1]) * p.inv) + 1,
+                    dz = (long long)((mx[2] - mn[2]) * p.inv) + 1;
+    if (dx * dy * dz > 2147483647LL) p.overflow = 1;   // PCL: "leaf size is too small" -> output = input
+    int divb[3];
+    for (int d = 0; d < 3; d++) {
+      p.minb[d] = (int)floorf(mn[d] * p.inv);
+      divb[d] = (int)floorf(mx[d] * p.inv) - p.minb[d] + 1;
     }
-    *s.plan = p;
+    p.mul[0] = 1; p.mul[1] = divb[0]; p.mul[2] = divb[0] * divb[1];
+  } else {
+    for (int d = 0; d < 3; d++) { p.minb[d] = 0; p.mul[d] = 0; }
   }
+  *s.plan = p;
 }
 
 // (2) keys.  grid = (blocks, nseg)
