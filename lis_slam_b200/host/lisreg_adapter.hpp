@@ -1,0 +1,152 @@
+// Header-only C++ adapter: keeps LIS-SLAM's own call surface (pcl::PointCloud<PointXYZI / PointXYZIL / PointXYZIRT>,
+// float transformTobeMapped[6]) and forwards to the lisreg C-ABI (include/lisreg.h).
+//
+// It mirrors the member functions the reference's ROS callbacks invoke:
+//   LaserProcessing::featureExtraction()          src/core/laserProcessing.cpp:108-115      -> Registrar::featureExtraction
+//   OdomEstimationNode::scan2SubMapOptimization() src/node/odomEstimationNode.cpp:596-626   -> Registrar::scan2SubMapOptimization
+//     (+ variants B/C src/node/subMapOptmizationNode.cpp:1509, :4485 via the `variant` argument)
+//   kdtree*FromMap->setInputCloud                 odomEstimationNode.cpp:602-603            -> Registrar::setMap
+//   pcl::VoxelGrid::filter                        odomEstimationNode.cpp:196-201, :272-277  -> Registrar::voxelGrid
+//   EPSCGeneration::calculateFEPSC / calculateDistance  src/core/epscGeneration.cpp:591, :633 -> Registrar::describe / scoreAll
+//
+// The only thing it needs from PCL is the record layout: PCL points are 32-byte records
+// {x, y, z, 1.0f pad, intensity, ...} (common.h:9-35); they are repacked to packed float4 + uint16 here.
+// Define LISREG_ADAPTER_MOCK_PCL to compile it without PCL (unit tests in this repo do that).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/lisreg.h"
+
+#ifdef LISREG_ADAPTER_MOCK_PCL
+namespace lisreg_mock {
+struct alignas(16) PointXYZI { float x, y, z, pad; float intensity; float pad2[3]; };
+struct alignas(16) PointXYZIL { float x, y, z, pad; float intensity; uint32_t label; float pad2[2]; };
+struct alignas(16) PointXYZIRT { float x, y, z, pad; float intensity; uint16_t ring; float time; float pad2; };
+template <typename P> struct PointCloud { std::vector<P> points; size_t size() const { return points.size(); } };
+}  // namespace lisreg_mock
+#define LISREG_CLOUD(P) lisreg_mock::PointCloud<lisreg_mock::P>
+#else
+#include <pcl/point_cloud.h>
+#include <pcl/point_types.h>
+#define LISREG_CLOUD(P) pcl::PointCloud<P>
+#endif
+
+namespace lisreg_host {
+
+struct Packed {
+  std::vector<float> xyzi;        // n x 4
+  std::vector<uint16_t> aux;      // label or ring
+  int32_t n = 0;
+};
+
+template <typename CloudT> inline Packed pack_xyzi(const CloudT& c) {
+  Packed p; p.n = (int32_t)c.points.size(); p.xyzi.resize(4 * (size_t)p.n);
+  for (int32_t i = 0; i < p.n; i++) { const auto& q = c.points[i]; float* o = &p.xyzi[4 * (size_t)i]; o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.intensity; }
+  return p;
+}
+template <typename CloudT> inline Packed pack_xyzil(const CloudT& c) {
+  Packed p = pack_xyzi(c); p.aux.resize(p.n);
+  for (int32_t i = 0; i < p.n; i++) p.aux[i] = (uint16_t)c.points[i].label;
+  return p;
+}
+template <typename CloudT> inline Packed pack_xyzirt(const CloudT& c) {
+  Packed p = pack_xyzi(c); p.aux.resize(p.n);
+  for (int32_t i = 0; i < p.n; i++) p.aux[i] = (uint16_t)c.points[i].ring;
+  return p;
+}
+
+// One engine context per node process (not re-entrant, exactly like the member scratch buffers it replaces).
+class Registrar {
+ public:
+  explicit Registrar(int device = 0) {
+    lisreg_config cfg; std::memset(&cfg, 0, sizeof(cfg)); cfg.device = device;
+    if (lisreg_create(&cfg, &ctx_) != LISREG_OK) throw std::runtime_error("lisreg_create failed: no CUDA device (there is no CPU fallback)");
+  }
+  ~Registrar() { if (ctx_) lisreg_destroy(ctx_); }
+  Registrar(const Registrar&) = delete;
+  Registrar& operator=(const Registrar&) = delete;
+
+  // kdtreeCornerFromMap->setInputCloud(cornerMapDS); kdtreeSurfFromMap->setInputCloud(surfMapDS)
+  template <typename CloudT> void setMap(const CloudT& cornerMapDS, const CloudT& surfMapDS, float sqdist_gate = 1.0f) {
+    if (map_id_ >= 0) { lisreg_map_destroy(ctx_, map_id_); map_id_ = -1; }
+    Packed c = pack_xyzi(cornerMapDS), s = pack_xyzi(surfMapDS);
+    check(lisreg_map_create(ctx_, c.xyzi.data(), c.n, s.xyzi.data(), s.n, sqdist_gate, &map_id_));
+  }
+
+  // scan2SubMapOptimization(): transformTobeMapped is [roll, pitch, yaw, x, y, z] in/out.
+  // Returns the reference's soft conditions: 0 ok, 1 "Not enough features" (pose untouched), 2 some iteration had < 50 matches.
+  // Variant A (odometry, PointXYZI clouds):
+  template <typename CloudT>
+  int scan2SubMapOptimization(const CloudT& cornerLast, const CloudT& surfLast, float transformTobeMapped[6], lisreg_lm_result* out = nullptr) {
+    return solve(pack_xyzi(cornerLast), pack_xyzi(surfLast), transformTobeMapped, 'A', out);
+  }
+  // Variants B (scan-to-submap) / C (submap-to-submap) on PointXYZIL clouds: w = 2.0 - LabelSorce[label]
+  template <typename CloudT>
+  int scan2SubMapOptimizationLabelled(const CloudT& cornerLastDS, const CloudT& surfLastDS, float transformTobeSubMapped[6], char variant,
+                                      lisreg_lm_result* out = nullptr) {
+    return solve(pack_xyzil(cornerLastDS), pack_xyzil(surfLastDS), transformTobeSubMapped, variant, out);
+  }
+
+  // featureExtraction() on a raw sweep (ring ids from PointXYZIRT); index lists refer to `extracted`.
+  template <typename CloudT>
+  void featureExtraction(const CloudT& laserCloudIn, const lisreg_feat_params& prm, std::vector<int32_t>& extracted_src,
+                         std::vector<int32_t>& corner, std::vector<int32_t>& surface, std::vector<int32_t>& sharpCorner, std::vector<int32_t>& sharpSurface) {
+    Packed p = pack_xyzirt(laserCloudIn);
+    const size_t cells = (size_t)prm.n_scan * prm.horizon;
+    extracted_src.assign(cells, 0); corner.assign((size_t)prm.n_scan * 120, 0); surface.assign(cells, 0);
+    sharpCorner.assign((size_t)prm.n_scan * 24, 0); sharpSurface.assign((size_t)prm.n_scan * 60, 0);
+    lisreg_feat_out o; std::memset(&o, 0, sizeof(o));
+    o.src_index = extracted_src.data(); o.corner_idx = corner.data(); o.surf_idx = surface.data(); o.sharp_idx = sharpCorner.data(); o.flat_idx = sharpSurface.data();
+    check(lisreg_extract_features(ctx_, p.xyzi.data(), p.aux.data(), p.n, &prm, &o));
+    extracted_src.resize(o.n_extracted); corner.resize(o.n_corner); surface.resize(o.n_surf); sharpCorner.resize(o.n_sharp); sharpSurface.resize(o.n_flat);
+  }
+
+  // downSizeFilter.setInputCloud(in); downSizeFilter.filter(out)   (xyz + intensity centroids, ascending voxel index)
+  template <typename CloudT> void voxelGrid(const CloudT& in, float leaf, std::vector<float>& out_xyzi) {
+    Packed p = pack_xyzi(in); out_xyzi.assign(4 * (size_t)p.n + 4, 0.f); int32_t m = 0;
+    check(lisreg_voxel_grid(ctx_, p.xyzi.data(), p.n, leaf, out_xyzi.data(), &m));
+    out_xyzi.resize(4 * (size_t)m);
+  }
+
+  // calculateFEPSC for one keyframe (20 x 80 bytes)
+  template <typename CloudI, typename CloudL>
+  void describe(const CloudI& corner, const CloudI& surf, const CloudL& semantic, const uint8_t using_map[256], uint8_t fepsc[1600]) {
+    Packed c = pack_xyzi(corner), s = pack_xyzi(surf), m = pack_xyzil(semantic);
+    lisreg_epsc_cloud cl; std::memset(&cl, 0, sizeof(cl));
+    cl.corner = c.xyzi.data(); cl.nc = c.n; cl.surf = s.xyzi.data(); cl.ns = s.n; cl.sem = m.xyzi.data(); cl.sem_label = m.aux.data(); cl.nsem = m.n;
+    check(lisreg_epsc_describe(ctx_, 1, &cl, using_map, nullptr, nullptr, fepsc));
+  }
+
+  // calculateDistance of every descriptor against its history (top-k loop candidates per keyframe)
+  void scoreAll(const uint8_t* desc, int32_t n, int32_t topk, std::vector<int32_t>& idx, std::vector<float>& score, std::vector<int8_t>& shift) {
+    idx.assign((size_t)n * topk, -1); score.assign((size_t)n * topk, 0.f); shift.assign((size_t)n * topk, 0);
+    check(lisreg_epsc_score_all(ctx_, desc, n, topk, idx.data(), score.data(), shift.data()));
+  }
+
+  lisreg_ctx* ctx() { return ctx_; }
+  float deltaR = 100.f, deltaT = 100.f;   // same members as the reference node (odomEstimationNode.cpp:70-71)
+  bool isDegenerate() const { return is_degenerate_; }
+
+ private:
+  int solve(const Packed& c, const Packed& s, float pose6[6], char variant, lisreg_lm_result* out) {
+    if (map_id_ < 0) throw std::runtime_error("Registrar::setMap must be called first");
+    lisreg_lm_params prm; lisreg_lm_params_preset(&prm, variant);
+    prm.degenerate_in = is_degenerate_ ? 1 : 0;   // the reference's isDegenerate member persists across frames (quirk Q1)
+    lisreg_lm_result res;
+    int rc = check(lisreg_scan2map(ctx_, map_id_, c.xyzi.data(), c.aux.empty() ? nullptr : c.aux.data(), c.n,
+                                   s.xyzi.data(), s.aux.empty() ? nullptr : s.aux.data(), s.n, pose6, &prm, &res, nullptr));
+    is_degenerate_ = res.is_degenerate != 0; deltaR = res.deltaR; deltaT = res.deltaT;
+    if (out) *out = res;
+    return rc;
+  }
+  int check(int rc) { if (rc < 0) throw std::runtime_error(std::string("lisreg: ") + lisreg_last_error(ctx_)); return rc; }
+  lisreg_ctx* ctx_ = nullptr;
+  int32_t map_id_ = -1;
+  bool is_degenerate_ = false;
+};
+
+}  // namespace lisreg_host
