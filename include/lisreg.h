@@ -238,6 +238,25 @@ int32_t lisreg_epsc_score_all(lisreg_ctx* ctx, const uint8_t* desc, int32_t N, i
 int32_t lisreg_epsc_score_all_dev(lisreg_ctx* ctx, const uint8_t* d_desc, int32_t N, int32_t topk,
                                   int32_t* d_idx, float* d_score, int8_t* d_shift);
 
+/* ---- loop-closure ICP verification (B4) ----
+ * Replaces the pcl::IterativeClosestPoint block of SubMapOdometryNode::detectLoopClosureForSubMap
+ * (subMapOptmizationNode.cpp:2739-2916; settings :2763-2769): for each (keyframe cloud, candidate submap cloud)
+ * pair, point-to-point ICP from the pre-transformed source (:2822-2824), then getFitnessScore(); the caller
+ * keeps the best converged pair and accepts it iff fitness <= historyKeyframeFitnessScore (0.5, :2855).
+ * The target cloud is registered once with lisreg_map_create(ctx, NULL, 0, target, n, ...) (its "surf" cloud).
+ * T is the final 4x4 transformation (row-major) of the pre-transformed source, as getFinalTransformation(). */
+typedef struct lisreg_icp_params {
+  float max_corr_dist;     /* 10   */
+  int32_t max_iters;       /* 30   */
+  double trans_eps;        /* 1e-4 */
+  double fitness_eps;      /* 1e-4 */
+} lisreg_icp_params;
+typedef struct lisreg_icp_pair { const float* src; int32_t ns; int32_t target_id; } lisreg_icp_pair;
+typedef struct lisreg_icp_result { float T[16]; double fitness; int32_t converged, iters, n_corr_last, reserved; } lisreg_icp_result;
+void lisreg_icp_params_default(lisreg_icp_params* p);
+int32_t lisreg_icp_verify_batch(lisreg_ctx* ctx, int32_t P, const lisreg_icp_pair* pairs, const lisreg_icp_params* prm,
+                                lisreg_icp_result* out);
+
 /* device self-test of the small dense routines (cv::eigen / cv::solve(QR) / cv::Mat::inv restatements):
  * out98 = E[6], V[36] (eigenvectors in rows), X[6] (QR solve of A x = b), ok, Ainv[36] (LU), ok,
  * then W3[3], V3[9] of the register-only 3x3 Jacobi applied to the leading 3x3 block of A */

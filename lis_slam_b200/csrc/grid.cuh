@@ -68,10 +68,11 @@ LISREG_HD __forceinline__ int cell_coord(float v, float o, float inv_h) {
   return (int)floorf((v - o) * inv_h);
 }
 
-// keeps the five smallest keys, ascending
-LISREG_HD __forceinline__ void knn5_insert(knn_key (&b)[5], knn_key k) {
+// keeps the K smallest keys, ascending
+template <int K>
+LISREG_HD __forceinline__ void knn_insert(knn_key (&b)[K], knn_key k) {
 #pragma unroll
-  for (int j = 0; j < 5; j++) {
+  for (int j = 0; j < K; j++) {
     const bool lt = b[j] < k;
     const knn_key lo = lt ? b[j] : k;
     k = lt ? k : b[j];
@@ -79,14 +80,15 @@ LISREG_HD __forceinline__ void knn5_insert(knn_key (&b)[5], knn_key k) {
   }
 }
 
-LISREG_HD __forceinline__ void knn5_scan_range(const float4* __restrict__ pts, uint32_t b, uint32_t e,
-                                                float qx, float qy, float qz, knn_key (&best)[5]) {
+template <int K>
+LISREG_HD __forceinline__ void knn_scan_range(const float4* __restrict__ pts, uint32_t b, uint32_t e,
+                                               float qx, float qy, float qz, knn_key (&best)[K]) {
   for (uint32_t p = b; p < e; p++) {
     const float4 m = LISREG_LDG(&pts[p]);
     const float dx = qx - m.x, dy = qy - m.y, dz = qz - m.z;
     float d = dx * dx; d = d + dy * dy; d = d + dz * dz;   // FLANN L2 functor op order, no FMA
     const knn_key k = ((knn_key)(unsigned)f2i(d) << 32) | (knn_key)p;
-    if (k < best[4]) knn5_insert(best, k);
+    if (k < best[K - 1]) knn_insert<K>(best, k);
   }
 }
 
@@ -102,37 +104,47 @@ LISREG_HD __forceinline__ void knn_row_range(const GridDev& g, int x0, int x1, i
 
 // Outer shells t = 2, 3, ... (rare: sparse neighbourhoods).  Kept out of line so that the hot
 // 3x3x3 loop stays small in the instruction cache.
-LISREG_HD __noinline__ void knn5_outer_shells(const GridDev& g, float qx, float qy, float qz, float gate,
-                                             int cx, int cy, int cz, float minf, knn_key (&best)[5]) {
-  const int max_shell = (int)ceilf(sqrtf(gate) * g.inv_h) + 1;
+template <int K>
+LISREG_HD __noinline__ void knn_outer_shells(const GridDev& g, float qx, float qy, float qz, float gate,
+                                            int cx, int cy, int cz, float minf, knn_key (&best)[K]) {
+  // shells beyond the grid extent contain nothing
+  int reach = cx > g.nx - 1 - cx ? cx : g.nx - 1 - cx;
+  reach = reach > cy ? reach : cy; reach = reach > g.ny - 1 - cy ? reach : g.ny - 1 - cy;
+  reach = reach > cz ? reach : cz; reach = reach > g.nz - 1 - cz ? reach : g.nz - 1 - cz;
+  const float fs = ceilf(sqrtf(gate) * g.inv_h) + 1.f;
+  int max_shell = fs < 1.0e6f ? (int)fs : 1000000;
+  if (max_shell > reach) max_shell = reach;
   for (int s = 1; s <= max_shell; s++) {
     // everything not yet visited is farther than lb (margin covers the float rounding of cell assignment)
     const float lb = ((float)s + minf - 1e-3f) * g.h;
     const float lb2 = lb * lb;
-    if (lb > 0.f && (knn_key_d(best[4]) < lb2 || lb2 >= gate)) break;
+    if (lb > 0.f && (knn_key_d(best[K - 1]) < lb2 || lb2 >= gate)) break;
     const int t = s + 1;   // visit shell t
-    for (int z = cz - t; z <= cz + t; z++) {
+    const int za = cz - t > 0 ? cz - t : 0, zb = cz + t < g.nz - 1 ? cz + t : g.nz - 1;
+    const int ya = cy - t > 0 ? cy - t : 0, yb = cy + t < g.ny - 1 ? cy + t : g.ny - 1;
+    for (int z = za; z <= zb; z++) {
       const bool zface = (z == cz - t) || (z == cz + t);
-      for (int y = cy - t; y <= cy + t; y++) {
+      for (int y = ya; y <= yb; y++) {
         const bool face = zface || (y == cy - t) || (y == cy + t);
         // a face row is one streak; an inner row contributes only its two end cells
         for (int part = 0; part < (face ? 1 : 2); part++) {
           uint32_t b, e;
           if (face) knn_row_range(g, cx - t, cx + t, y, z, b, e);
           else knn_row_range(g, part == 0 ? cx - t : cx + t, part == 0 ? cx - t : cx + t, y, z, b, e);
-          knn5_scan_range(g.pts, b, e, qx, qy, qz, best);
+          knn_scan_range<K>(g.pts, b, e, qx, qy, qz, best);
         }
       }
     }
   }
 }
 
-// Exact 5-NN restricted to squared distance < gate.  best[] ascending; unused slots keep the
-// sentinel (d^2 = gate, position 0xffffffff), so "5 neighbours inside the gate" <=> key_d(best[4]) < gate.
-LISREG_HD __forceinline__ void knn5_grid(const GridDev& g, float qx, float qy, float qz, float gate, knn_key (&best)[5]) {
+// Exact K-NN restricted to squared distance < gate.  best[] ascending; unused slots keep the
+// sentinel (d^2 = gate, position 0xffffffff), so "K neighbours inside the gate" <=> key_d(best[K-1]) < gate.
+template <int K>
+LISREG_HD __forceinline__ void knn_grid(const GridDev& g, float qx, float qy, float qz, float gate, knn_key (&best)[K]) {
   const knn_key sentinel = ((knn_key)(unsigned)f2i(gate) << 32) | 0xffffffffull;
 #pragma unroll
-  for (int j = 0; j < 5; j++) best[j] = sentinel;
+  for (int j = 0; j < K; j++) best[j] = sentinel;
   if (g.n <= 0) return;
   const float fx = (qx - g.ox) * g.inv_h, fy = (qy - g.oy) * g.inv_h, fz = (qz - g.oz) * g.inv_h;
   const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
@@ -146,13 +158,17 @@ LISREG_HD __forceinline__ void knn5_grid(const GridDev& g, float qx, float qy, f
 #pragma unroll 1
   for (int r = 0; r < 9; r++) {
     if (r < 8) knn_row_range(g, cx - 1, cx + 1, cy + ((r + 1) % 3) - 1, cz + ((r + 1) / 3) - 1, nb, ne);
-    knn5_scan_range(g.pts, b, e, qx, qy, qz, best);
+    knn_scan_range<K>(g.pts, b, e, qx, qy, qz, best);
     b = nb; e = ne;
   }
-  // ---- outer shells only if something unvisited could still beat the 5th best ----
+  // ---- outer shells only if something unvisited could still beat the K-th best ----
   const float lb = (1.f + minf - 1e-3f) * g.h;
   const float lb2 = lb * lb;
-  if (!(knn_key_d(best[4]) < lb2 || lb2 >= gate)) knn5_outer_shells(g, qx, qy, qz, gate, cx, cy, cz, minf, best);
+  if (!(knn_key_d(best[K - 1]) < lb2 || lb2 >= gate)) knn_outer_shells<K>(g, qx, qy, qz, gate, cx, cy, cz, minf, best);
+}
+
+LISREG_HD __forceinline__ void knn5_grid(const GridDev& g, float qx, float qy, float qz, float gate, knn_key (&best)[5]) {
+  knn_grid<5>(g, qx, qy, qz, gate, best);
 }
 
 }  // namespace lisreg

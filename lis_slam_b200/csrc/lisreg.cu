@@ -15,6 +15,7 @@
 #include "features.cuh"
 #include "voxel.cuh"
 #include "epsc.cuh"
+#include "icp.cuh"
 
 using namespace lisreg;
 
@@ -75,7 +76,7 @@ struct lisreg_ctx {
   // feature-extraction work buffers (capacity feat_cap_frames frames of feat_cells cells)
   DevBuf d_feat, d_feat_frames;
   int feat_cap_frames = 0, feat_cells = 0, feat_nscan = 0;
-  DevBuf d_epsc, d_epsc2;
+  DevBuf d_epsc, d_epsc2, d_icp;
   // voxel-grid work buffers
   DevBuf d_vox, d_vox_segs;
   // profiling
@@ -330,7 +331,7 @@ void lisreg_destroy(lisreg_ctx* ctx) {
   }
   if (ctx->d_maps) cudaFree(ctx->d_maps);
   for (DevBuf* b : {&ctx->d_stage, &ctx->d_descs, &ctx->d_states, &ctx->d_partials, &ctx->d_tickets, &ctx->d_logs,
-                    &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox, &ctx->d_feat, &ctx->d_feat_frames, &ctx->d_vox, &ctx->d_vox_segs, &ctx->d_epsc, &ctx->d_epsc2}) b->release();
+                    &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox, &ctx->d_feat, &ctx->d_feat_frames, &ctx->d_vox, &ctx->d_vox_segs, &ctx->d_epsc, &ctx->d_epsc2, &ctx->d_icp}) b->release();
   ctx->h_stage.release(); ctx->h_out.release();
   for (auto& p : ctx->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : ctx->ev_free) cudaEventDestroy(e);
@@ -983,6 +984,60 @@ int32_t lisreg_epsc_score_all(lisreg_ctx* ctx, const uint8_t* desc, int32_t N, i
   CK(cudaMemcpyAsync(idx, d + bd, bi, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(score, d + bd + bi, bs, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(shift, d + bd + bi + bs, bh, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return LISREG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ICP verify
+// ------------------------------------------------------------------------------------------------
+void lisreg_icp_params_default(lisreg_icp_params* p) { p->max_corr_dist = 10.f; p->max_iters = 30; p->trans_eps = 1e-4; p->fitness_eps = 1e-4; }
+
+int32_t lisreg_icp_verify_batch(lisreg_ctx* ctx, int32_t P, const lisreg_icp_pair* pairs, const lisreg_icp_params* prm,
+                                lisreg_icp_result* out) {
+  if (!ctx || P <= 0 || !pairs || !prm || !out || prm->max_iters <= 0) return fail(ctx, LISREG_ERR_ARG, "lisreg_icp_verify_batch: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  int rc = sync_maps(ctx);
+  if (rc) return rc;
+  auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+  size_t src_bytes = 0; int max_ns = 0;
+  for (int i = 0; i < P; i++) {
+    const lisreg_icp_pair& pr = pairs[i];
+    if (pr.ns < 0 || (pr.ns > 0 && !pr.src) || pr.target_id < 0 || pr.target_id >= (int)ctx->maps.size() || !ctx->maps[pr.target_id].used)
+      return fail(ctx, LISREG_ERR_ARG, "icp pair %d: bad size, pointer or target id", i);
+    src_bytes += al(16 * (size_t)pr.ns); max_ns = std::max(max_ns, pr.ns);
+  }
+  const int nblk = std::max(1, std::min(64, (max_ns + ICP_THREADS - 1) / ICP_THREADS));
+  const size_t o_pairs = 0, o_states = al(sizeof(IcpPair) * (size_t)P), o_part = o_states + al(sizeof(IcpState) * (size_t)P),
+               o_res = o_part + al(sizeof(double) * ICP_NSUM * (size_t)P * nblk), o_cur = o_res + al(sizeof(lisreg_icp_result) * (size_t)P);
+  CK(ctx->d_icp.reserve(o_cur + src_bytes));
+  CK(ctx->h_stage.reserve(src_bytes + al(sizeof(IcpPair) * (size_t)P)));
+  CK(ctx->d_stage.reserve(src_bytes + 256));
+  char* h = (char*)ctx->h_stage.p; char* dsrc = (char*)ctx->d_stage.p; char* d = (char*)ctx->d_icp.p;
+  IcpPair* hp = (IcpPair*)(h + src_bytes);
+  size_t off = 0;
+  for (int i = 0; i < P; i++) {
+    const lisreg_icp_pair& pr = pairs[i];
+    if (pr.ns) memcpy(h + off, pr.src, 16 * (size_t)pr.ns);
+    hp[i].src = (const float4*)(dsrc + off); hp[i].ns = pr.ns; hp[i].cur = (float4*)(d + o_cur + off); hp[i].tgt_slot = pr.target_id; hp[i].pad = 0;
+    off += al(16 * (size_t)pr.ns);
+  }
+  if (src_bytes) CK(cudaMemcpyAsync(dsrc, h, src_bytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_pairs, hp, sizeof(IcpPair) * (size_t)P, cudaMemcpyHostToDevice, st));
+  IcpPair* dp = (IcpPair*)(d + o_pairs); IcpState* ds = (IcpState*)(d + o_states); double* part = (double*)(d + o_part);
+  lisreg_icp_result* dres = (lisreg_icp_result*)(d + o_res);
+  IcpParamsDev kp{prm->max_corr_dist * prm->max_corr_dist, prm->max_iters, 1.0 - prm->trans_eps, prm->trans_eps, prm->fitness_eps};
+  k_icp_init<<<(P + 127) / 128, 128, 0, st>>>(dp, ds, P); LAUNCH_CK();
+  k_icp_copy<<<dim3(nblk, P), ICP_THREADS, 0, st>>>(dp); LAUNCH_CK();
+  for (int it = 0; it < prm->max_iters; it++) {
+    k_icp_corr<false><<<dim3(nblk, P), ICP_THREADS, 0, st>>>(dp, ds, ctx->d_maps, kp, part, nblk); LAUNCH_CK();
+    k_icp_solve<false><<<(P + 3) / 4, 128, 0, st>>>(ds, kp, part, nblk, P); LAUNCH_CK();
+  }
+  k_icp_corr<true><<<dim3(nblk, P), ICP_THREADS, 0, st>>>(dp, ds, ctx->d_maps, kp, part, nblk); LAUNCH_CK();
+  k_icp_solve<true><<<(P + 3) / 4, 128, 0, st>>>(ds, kp, part, nblk, P); LAUNCH_CK();
+  k_icp_finish<<<(P + 127) / 128, 128, 0, st>>>(ds, dres, P); LAUNCH_CK();
+  CK(cudaMemcpyAsync(out, dres, sizeof(lisreg_icp_result) * (size_t)P, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return LISREG_OK;
 }

@@ -87,6 +87,19 @@ class EpscCloud(C.Structure):
                 ("nc", C.c_int32), ("ns", C.c_int32), ("nsem", C.c_int32), ("reserved", C.c_int32)]
 
 
+class IcpParams(C.Structure):
+    _fields_ = [("max_corr_dist", C.c_float), ("max_iters", C.c_int32), ("trans_eps", C.c_double), ("fitness_eps", C.c_double)]
+
+
+class IcpPair(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("ns", C.c_int32), ("target_id", C.c_int32)]
+
+
+class IcpResult(C.Structure):
+    _fields_ = [("T", C.c_float * 16), ("fitness", C.c_double), ("converged", C.c_int32), ("iters", C.c_int32),
+                ("n_corr_last", C.c_int32), ("reserved", C.c_int32)]
+
+
 class Profile(C.Structure):
     _fields_ = [
         ("lm_iter_ms", C.c_double), ("lm_iter_launches", C.c_int64), ("lm_alg_bytes", C.c_double),
@@ -160,6 +173,9 @@ def lib():
         L.lisreg_epsc_score_all.argtypes = [vp, vp, i32, i32, vp, vp, vp]
         L.lisreg_epsc_score_all_dev.restype = i32
         L.lisreg_epsc_score_all_dev.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+        L.lisreg_icp_params_default.argtypes = [C.POINTER(IcpParams)]
+        L.lisreg_icp_verify_batch.restype = i32
+        L.lisreg_icp_verify_batch.argtypes = [vp, i32, C.POINTER(IcpPair), C.POINTER(IcpParams), C.POINTER(IcpResult)]
         L.lisreg_selftest_smallmat.restype = i32
         L.lisreg_selftest_smallmat.argtypes = [vp, fp, fp, fp]
         L.lisreg_profile_enable.restype = i32
@@ -373,6 +389,23 @@ class Engine:
         idx = np.zeros((N, topk), np.int32); score = np.zeros((N, topk), np.float32); shift = np.zeros((N, topk), np.int8)
         self._ck(lib().lisreg_epsc_score_all(self._h, d.ctypes.data, N, topk, idx.ctypes.data, score.ctypes.data, shift.ctypes.data))
         return idx, score, shift
+
+    def target_create(self, pts):
+        """Registers an ICP target cloud (stored as the 'surf' cloud of a map slot)."""
+        return self.map_create(np.zeros((0, 4), np.float32), pts, gate_hint=1.0)
+
+    def icp_verify_batch(self, pairs, prm=None):
+        """pairs: list of (src (n,4) already pre-transformed by the initial guess, target_id). Returns [IcpResult]."""
+        P = len(pairs)
+        if prm is None:
+            prm = IcpParams(); lib().lisreg_icp_params_default(C.byref(prm))
+        arr = (IcpPair * P)(); keep = []
+        for i, (src, tid) in enumerate(pairs):
+            s = _f4(src); keep.append(s)
+            arr[i] = IcpPair(s.ctypes.data, len(s), tid)
+        out = (IcpResult * P)()
+        self._ck(lib().lisreg_icp_verify_batch(self._h, P, arr, C.byref(prm), out))
+        return list(out)
 
     def selftest_smallmat(self, A, b):
         A = np.ascontiguousarray(A, np.float32).reshape(36); b = np.ascontiguousarray(b, np.float32).reshape(6)

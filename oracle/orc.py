@@ -59,6 +59,19 @@ def feat_params(n_scan=64, horizon=1800, downsample_rate=1, min_range=0.0, max_r
     return FeatParams(n_scan, horizon, downsample_rate, min_range, max_range, edge_thr, surf_thr)
 
 
+class IcpParams(C.Structure):
+    _fields_ = [("max_corr_dist", C.c_float), ("max_iters", C.c_int32), ("trans_eps", C.c_double), ("fitness_eps", C.c_double)]
+
+
+class IcpResult(C.Structure):
+    _fields_ = [("T", C.c_float * 16), ("fitness", C.c_double), ("converged", C.c_int32), ("iters", C.c_int32),
+                ("n_corr_last", C.c_int32), ("pad", C.c_int32)]
+
+
+def icp_params(max_corr_dist=10.0, max_iters=30, trans_eps=1e-4, fitness_eps=1e-4):
+    return IcpParams(max_corr_dist, max_iters, trans_eps, fitness_eps)
+
+
 # label_sorce of config/label.yaml:214-234 (reference values)
 LABEL_SCORE = [1.0, 1.0, 0.6, 0.5, 0.8, 0.5, 0.5, 0.5, 0.5, 1.2, 1.2, 1.2, 0.5, 1.0, 0.8, 0.5, 1.3, 0.5, 1.5, 1.5]
 
@@ -119,6 +132,8 @@ def lib():
         L.orc_epsc_distance.restype = C.c_double
         L.orc_epsc_distance.argtypes = [u8p, u8p, ip, ip]
         L.orc_epsc_score_all.argtypes = [u8p, C.c_int32, C.c_int32, ip, fp, C.POINTER(C.c_int8), C.c_int32]
+        L.orc_icp.restype = C.c_int
+        L.orc_icp.argtypes = [fp, C.c_int32, fp, C.c_int32, C.POINTER(IcpParams), C.POINTER(IcpResult)]
         _LIB = L
     return _LIB
 
@@ -277,3 +292,11 @@ def epsc_score_all(desc, topk=5, n_threads=1):
     lib().orc_epsc_score_all(d.ctypes.data_as(C.POINTER(C.c_uint8)), N, topk, idx.ctypes.data_as(C.POINTER(C.c_int32)),
                              score.ctypes.data_as(C.POINTER(C.c_float)), shift.ctypes.data_as(C.POINTER(C.c_int8)), n_threads)
     return idx, score, shift
+
+
+def icp(src4, tgt4, prm=None):
+    s, sp = _f(src4); t, tp = _f(tgt4)
+    prm = prm or icp_params()
+    res = IcpResult()
+    lib().orc_icp(sp, len(s), tp, len(t), C.byref(prm), C.byref(res))
+    return np.array(res.T, np.float32).reshape(4, 4), res

@@ -97,6 +97,11 @@ void orc_epsc_describe(const float* corner4, int32_t nc, const float* surf4, int
 double orc_epsc_distance(const uint8_t* d1, const uint8_t* d2, int32_t* best_shift, int32_t* min_sad);
 void orc_epsc_score_all(const uint8_t* desc, int32_t N, int32_t topk, int32_t* idx, float* score, int8_t* shift, int32_t n_threads);
 
+/* ---- loop-closure ICP verify (subMapOptmizationNode.cpp:2739-2916, pcl::IterativeClosestPoint) ---- */
+typedef struct orc_icp_params { float max_corr_dist; int32_t max_iters; double trans_eps; double fitness_eps; } orc_icp_params;
+typedef struct orc_icp_result { float T[16]; double fitness; int32_t converged, iters, n_corr_last, pad; } orc_icp_result;
+int orc_icp(const float* src4, int32_t ns, const float* tgt4, int32_t nt, const orc_icp_params* prm, orc_icp_result* res);
+
 #ifdef __cplusplus
 }
 #endif
