@@ -138,21 +138,24 @@ LISREG_HD __noinline__ void knn_outer_shells(const GridDev& g, float qx, float q
   }
 }
 
-// Exact K-NN restricted to squared distance < gate.  best[] ascending; unused slots keep the
-// sentinel (d^2 = gate, position 0xffffffff), so "K neighbours inside the gate" <=> key_d(best[K-1]) < gate.
+// The 3x3x3 block of the search.  best[] ascending; unused slots keep the sentinel (d^2 = gate, position
+// 0xffffffff).  Returns true when something outside the block could still beat the K-th best, i.e. the outer
+// shells must be visited (knn_outer_shells) for the result to be exact.
 template <int K>
-LISREG_HD __forceinline__ void knn_grid(const GridDev& g, float qx, float qy, float qz, float gate, knn_key (&best)[K]) {
+LISREG_HD __forceinline__ bool knn_grid_block(const GridDev& g, float qx, float qy, float qz, float gate, knn_key (&best)[K],
+                                               int& cx, int& cy, int& cz, float& minf) {
   const knn_key sentinel = ((knn_key)(unsigned)f2i(gate) << 32) | 0xffffffffull;
 #pragma unroll
   for (int j = 0; j < K; j++) best[j] = sentinel;
-  if (g.n <= 0) return;
+  cx = cy = cz = 0; minf = 0.f;
+  if (g.n <= 0) return false;
   const float fx = (qx - g.ox) * g.inv_h, fy = (qy - g.oy) * g.inv_h, fz = (qz - g.oz) * g.inv_h;
-  const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
+  cx = (int)floorf(fx); cy = (int)floorf(fy); cz = (int)floorf(fz);
   // distance from the query to the nearest face of its own cell (in cells)
   const float rx = fx - (float)cx, ry = fy - (float)cy, rz = fz - (float)cz;
-  const float minf = fminf(fminf(fminf(rx, 1.f - rx), fminf(ry, 1.f - ry)), fminf(rz, 1.f - rz));
-  // ---- the 3x3x3 block: 9 row streaks; ONE copy of the scan loop (instruction-cache friendly),
-  //      the offsets of row r+1 are fetched while row r is scanned ----
+  minf = fminf(fminf(fminf(rx, 1.f - rx), fminf(ry, 1.f - ry)), fminf(rz, 1.f - rz));
+  // 9 row streaks; ONE copy of the scan loop (instruction-cache friendly), the offsets of row r+1 are
+  // fetched while row r is scanned
   uint32_t b, e, nb = 0u, ne = 0u;
   knn_row_range(g, cx - 1, cx + 1, cy - 1, cz - 1, b, e);
 #pragma unroll 1
@@ -161,10 +164,16 @@ LISREG_HD __forceinline__ void knn_grid(const GridDev& g, float qx, float qy, fl
     knn_scan_range<K>(g.pts, b, e, qx, qy, qz, best);
     b = nb; e = ne;
   }
-  // ---- outer shells only if something unvisited could still beat the K-th best ----
   const float lb = (1.f + minf - 1e-3f) * g.h;
   const float lb2 = lb * lb;
-  if (!(knn_key_d(best[K - 1]) < lb2 || lb2 >= gate)) knn_outer_shells<K>(g, qx, qy, qz, gate, cx, cy, cz, minf, best);
+  return !(knn_key_d(best[K - 1]) < lb2 || lb2 >= gate);
+}
+
+// Exact K-NN restricted to squared distance < gate ("K neighbours inside the gate" <=> key_d(best[K-1]) < gate).
+template <int K>
+LISREG_HD __forceinline__ void knn_grid(const GridDev& g, float qx, float qy, float qz, float gate, knn_key (&best)[K]) {
+  int cx, cy, cz; float minf;
+  if (knn_grid_block<K>(g, qx, qy, qz, gate, best, cx, cy, cz, minf)) knn_outer_shells<K>(g, qx, qy, qz, gate, cx, cy, cz, minf, best);
 }
 
 LISREG_HD __forceinline__ void knn5_grid(const GridDev& g, float qx, float qy, float qz, float gate, knn_key (&best)[5]) {

@@ -258,6 +258,8 @@ k_lm_iter(const RegDesc* __restrict__ descs, RegState* __restrict__ states, cons
   __shared__ float sT[12], sTrig[6];
   __shared__ int sdone;
   __shared__ int s_pos[5 * LM_MAX_TILE];
+  __shared__ unsigned short s_def[LM_MAX_TILE];
+  __shared__ int s_ndef;
   __shared__ float s_row[7 * LM_MAX_TILE];
   __shared__ double swarp[LM_THREADS / 32][LM_NSUM];
   if (tid == 0) { sd = descs[b]; sd.nc = states[b].nc; sd.ns = states[b].ns; sdone = states[b].done; }
@@ -274,9 +276,14 @@ k_lm_iter(const RegDesc* __restrict__ descs, RegState* __restrict__ states, cons
   const int q0 = tile * tile_pts;
   const int qn = min(n - q0, tile_pts);   // queries in this tile
 
-  // ---------------- phase A: 5-NN ----------------
+  // ---------------- phase A: 5-NN, 3x3x3 block ----------------
+  // Queries whose 5th neighbour may lie outside the block (sparse neighbourhoods, ~10 %) are DEFERRED to a
+  // list and finished in phase A2 with one lane per deferred query, so the rare long outer-shell walk runs
+  // on dense warps instead of stalling 31 idle lanes.
+  if (tid == 0) s_ndef = 0;
+  __syncthreads();
   for (int l = tid; l < tile_pts; l += LM_THREADS) {
-    int accepted = 0;
+    int accepted = 0, deferred = 0;
     knn_key best[5];
     if (l < qn) {
       const int q = q0 + l;
@@ -287,16 +294,40 @@ k_lm_iter(const RegDesc* __restrict__ descs, RegState* __restrict__ states, cons
       const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
       const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
       const GridDev& g = is_corner ? mp.corner : mp.surf;
-      knn5_grid(g, x0, y0, z0, prm.gate, best);
+      int cx, cy, cz; float minf;
+      deferred = knn_grid_block<5>(g, x0, y0, z0, prm.gate, best, cx, cy, cz, minf) ? 1 : 0;
       accepted = knn_key_d(best[4]) < prm.gate;
     }
-    if (accepted) {
+    if (deferred) {
+      s_def[atomicAdd(&s_ndef, 1)] = (unsigned short)l;
+    } else if (accepted) {
 #pragma unroll
       for (int j = 0; j < 5; j++) s_pos[j * LM_MAX_TILE + l] = knn_key_pos(best[j]);
     } else {
       s_pos[l] = -1;
     }
   }
+  __syncthreads();
+  // ---------------- phase A2: deferred queries, full search incl. outer shells ----------------
+  for (int d = tid; d < s_ndef; d += LM_THREADS) {
+    const int l = s_def[d];
+    const int q = q0 + l;
+    const bool is_corner = q < sd.nc;
+    const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
+    const float x0 = sT[0] * p.x + sT[1] * p.y + sT[2] * p.z + sT[3];
+    const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
+    const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
+    const GridDev& g = is_corner ? mp.corner : mp.surf;
+    knn_key best[5];
+    knn_grid<5>(g, x0, y0, z0, prm.gate, best);
+    if (knn_key_d(best[4]) < prm.gate) {
+#pragma unroll
+      for (int j = 0; j < 5; j++) s_pos[j * LM_MAX_TILE + l] = knn_key_pos(best[j]);
+    } else {
+      s_pos[l] = -1;
+    }
+  }
+  __syncthreads();
 
   // ---------------- phase B: coefficients + Jacobian rows ----------------
   int cntC = 0, cntS = 0;
