@@ -167,7 +167,9 @@ __global__ void k_feat_occlusion(FeatFrame* frames) {
 }
 
 // ---- F5 ----
-constexpr int FEAT_SEG_MAX = 512;       // max points of one segment handled in shared memory
+constexpr int FEAT_HI_MAX = 128;        // edge candidates (curvature > edgeThreshold) of one segment (power of two)
+constexpr int FEAT_LO_MAX = 512;        // flat candidates (curvature < surfThreshold) of one segment (power of two)
+constexpr int FEAT_SEG_MAX = FEAT_HI_MAX + FEAT_LO_MAX;   // key slots per warp in shared memory
 constexpr int FEAT_WARPS = 4;           // rings per block
 constexpr int FEAT_RING_MAX = 2048 + 16; // staged ring window (horizon <= 2048, +-6 apron)
 
@@ -219,36 +221,63 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
     if (lane == 0) { f.seg_sp[seg] = sp; f.seg_ep[seg] = ep; f.seg_valid[seg] = (sp < ep) ? 1 : 0; f.seg_ncorner[seg] = 0; f.seg_nflat[seg] = 0; }
     if (sp >= ep) continue;
     const int len = ep - sp;            // sorted range [sp, ep); element ep stays in place (Q3)
-    // ---- sort (curvature bits << 32 | index); curvature >= 0 so integer order == (value, index) order ----
-    int npad = 1; while (npad < len) npad <<= 1;
-    const bool in_smem = npad <= FEAT_SEG_MAX;
-    if (in_smem) {
-      for (int t = lane; t < npad; t += 32) {
+    // Only elements that can ever be picked need ordering: curvature > edge_thr (pass 1, descending) and
+    // curvature < surf_thr (pass 2, ascending); the band in between is never visited with effect.  Both
+    // candidate sets are compacted (warp ballot) into the two halves of the key buffer and bitonic-sorted
+    // separately: keys = curvature bits << 32 | index (curvature >= 0 => integer order == (value, index)).
+    unsigned long long* khi = key;                   // [0, FEAT_HI_MAX)
+    unsigned long long* klo = key + FEAT_HI_MAX;     // [FEAT_HI_MAX, FEAT_SEG_MAX)
+    int nhi = 0, nlo = 0;
+    for (int base = 0; base < len; base += 32) {
+      const int t = base + lane;
+      float cv = 0.f; bool ishi = false, islo = false;
+      if (t < len) { cv = f.curv[sp + t]; ishi = cv > prm.edge_thr; islo = cv < prm.surf_thr; }
+      const unsigned mh = __ballot_sync(0xffffffffu, ishi), ml = __ballot_sync(0xffffffffu, islo);
+      const unsigned long long kk = ((unsigned long long)__float_as_uint(cv) << 32) | (unsigned)(sp + t);
+      if (ishi) { const int o = nhi + __popc(mh & ((1u << lane) - 1u)); if (o < FEAT_HI_MAX) khi[o] = kk; }
+      if (islo) { const int o = nlo + __popc(ml & ((1u << lane) - 1u)); if (o < FEAT_LO_MAX) klo[o] = kk; }
+      nhi += __popc(mh); nlo += __popc(ml);
+    }
+    // mode 0: split candidate lists (common); mode 1: too many edge candidates -> sort the whole segment in
+    // shared memory (both passes then walk the same array and stop at their threshold); mode 2: oversize
+    // segment (never for <= 2048 columns / 6) -> slow insertion sort by lane 0 in global scratch.
+    int npad_full = 1; while (npad_full < len) npad_full <<= 1;
+    const int mode = (nhi <= FEAT_HI_MAX && nlo <= FEAT_LO_MAX) ? 0 : (npad_full <= FEAT_SEG_MAX ? 1 : 2);
+    if (mode == 1) {
+      __syncwarp();
+      for (int t = lane; t < npad_full; t += 32) {
         const int i = sp + t;
         key[t] = t < len ? (((unsigned long long)__float_as_uint(f.curv[i]) << 32) | (unsigned)i) : ~0ull;
       }
-      __syncwarp();
-      for (int k = 2; k <= npad; k <<= 1)
-        for (int jj = k >> 1; jj > 0; jj >>= 1) {
-          for (int t = lane; t < npad; t += 32) {
-            const int ixj = t ^ jj;
-            if (ixj > t) {
-              const unsigned long long a = key[t], b = key[ixj];
-              const bool up = (t & k) == 0;
-              if ((a > b) == up) { key[t] = b; key[ixj] = a; }
+    }
+    if (mode <= 1) {
+      for (int pass = 0; pass < (mode == 0 ? 2 : 1); pass++) {
+        unsigned long long* kb = mode == 1 ? key : (pass == 0 ? khi : klo);
+        const int cnt = mode == 1 ? len : (pass == 0 ? nhi : nlo);
+        int npad = 1; while (npad < cnt) npad <<= 1;
+        if (mode == 0) for (int t = cnt + lane; t < npad; t += 32) kb[t] = ~0ull;
+        __syncwarp();
+        for (int k = 2; k <= npad; k <<= 1)
+          for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int t = lane; t < npad; t += 32) {
+              const int ixj = t ^ jj;
+              if (ixj > t) {
+                const unsigned long long a = kb[t], bq = kb[ixj];
+                const bool up = (t & k) == 0;
+                if ((a > bq) == up) { kb[t] = bq; kb[ixj] = a; }
+              }
             }
+            __syncwarp();
           }
-          __syncwarp();
-        }
+      }
     } else {
-      // oversize segment (never for <= 2048 columns / 6): slow insertion sort by lane 0 in global scratch
       if (lane == 0) {
-        for (int t = 0; t < len; t++) f.owner[t + ring * prm.horizon] = sp + t;    // owner[] is free after compaction
-        int* o = f.owner + ring * prm.horizon;
+        int* o = f.owner + ring * prm.horizon;      // owner[] is free after compaction
+        for (int t = 0; t < len; t++) o[t] = sp + t;
         for (int a = 1; a < len; a++) {
-          const int v = o[a]; const float cv = f.curv[v]; int b = a;
-          while (b > 0 && (f.curv[o[b - 1]] > cv || (f.curv[o[b - 1]] == cv && o[b - 1] > v))) { o[b] = o[b - 1]; b--; }
-          o[b] = v;
+          const int v = o[a]; const float cv = f.curv[v]; int bb = a;
+          while (bb > 0 && (f.curv[o[bb - 1]] > cv || (f.curv[o[bb - 1]] == cv && o[bb - 1] > v))) { o[bb] = o[bb - 1]; bb--; }
+          o[bb] = v;
         }
       }
       __syncwarp();
@@ -256,14 +285,20 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
     // ---- greedy passes by lane 0 (order-dependent non-maximum suppression) ----
     if (lane == 0) {
       const int* o = f.owner + ring * prm.horizon;
+      const unsigned long long* l1 = mode == 0 ? khi : key;   // pass-1 list (ascending; walked from the top)
+      const unsigned long long* l2 = mode == 0 ? klo : key;   // pass-2 list (ascending; walked from the bottom)
+      const int n1 = mode == 0 ? nhi : len, n2 = mode == 0 ? nlo : len;
       const float cv_ep = f.curv[ep];
       int largestPickedNum = 0, nc = 0;
-      for (int k = ep; k >= sp; k--) {
+      // pass 1: k = ep first, then the sorted candidates from the largest curvature down
+      for (int k = n1; k >= 0; k--) {
         int ind; float cv;
-        if (k == ep) { ind = ep; cv = cv_ep; }
-        else if (in_smem) { const unsigned long long kk = key[k - sp]; ind = (int)(unsigned)(kk & 0xffffffffull); cv = __uint_as_float((unsigned)(kk >> 32)); }
-        else { ind = o[k - sp]; cv = f.curv[ind]; }
-        if (k < ep && !(cv > prm.edge_thr)) break;   // sorted ascending: nothing below can qualify
+        if (k == n1) { ind = ep; cv = cv_ep; }
+        else {
+          if (mode <= 1) { const unsigned long long kk = l1[k]; ind = (int)(unsigned)(kk & 0xffffffffull); cv = __uint_as_float((unsigned)(kk >> 32)); }
+          else { ind = o[k]; cv = f.curv[ind]; }
+          if (!(cv > prm.edge_thr)) break;   // ascending order: nothing below can qualify
+        }
         if (spick[ind - lo] == 0 && cv > prm.edge_thr) {
           largestPickedNum++;
           if (largestPickedNum <= 20) {
@@ -276,12 +311,15 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
       }
       f.seg_ncorner[seg] = nc;
       largestPickedNum = 0; int nf = 0;
-      for (int k = sp; k <= ep; k++) {
+      // pass 2: the sorted candidates from the smallest curvature up, then k = ep
+      for (int k = 0; k <= n2; k++) {
         int ind; float cv;
-        if (k == ep) { ind = ep; cv = cv_ep; }
-        else if (in_smem) { const unsigned long long kk = key[k - sp]; ind = (int)(unsigned)(kk & 0xffffffffull); cv = __uint_as_float((unsigned)(kk >> 32)); }
-        else { ind = o[k - sp]; cv = f.curv[ind]; }
-        if (k < ep && !(cv < prm.surf_thr)) { k = ep - 1; continue; }   // skip to the unsorted element ep
+        if (k == n2) { ind = ep; cv = cv_ep; }
+        else {
+          if (mode <= 1) { const unsigned long long kk = l2[k]; ind = (int)(unsigned)(kk & 0xffffffffull); cv = __uint_as_float((unsigned)(kk >> 32)); }
+          else { ind = o[k]; cv = f.curv[ind]; }
+          if (!(cv < prm.surf_thr)) { k = n2 - 1; continue; }   // nothing above can qualify: jump to the unsorted element ep
+        }
         if (spick[ind - lo] == 0 && cv < prm.surf_thr) {
           largestPickedNum++;
           f.label[ind] = -1;
