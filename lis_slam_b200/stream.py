@@ -1,0 +1,112 @@
+"""Streaming (per-frame) harness for BASELINE configs[1] / configs[4]: the host-side flow of
+OdomEstimationNode::laserCloudInfoHandler (src/node/odomEstimationNode.cpp:163-239) around the device calls.
+
+Per frame: constant-velocity initial guess (updateInitialGuess, :353-391) -> local map = concatenation of the last
+<= 19 keyframe clouds (already in the map frame, newest first) -> voxel grid 0.2 / 0.4 m (:185-207) -> voxel grid of
+the frame's corner / surface clouds (currentCloudInit, :260-281) -> scan2SubMapOptimization (:596-626) -> keyframe
+rule (:216-229) and saveKeyFrames (:421-478).  Frame t needs the pose and map of frame t-1, so this mode does not
+shard: multi-GPU = independent replicas.
+
+`backend` provides the compute: extract_features(pts, ring), voxel_grid(pts, leaf), map_create(corner, surf),
+map_destroy(id), scan2map(map_id, corner, surf, pose6, params).  lis_slam_b200.engine.Engine satisfies it (the
+product); the tests also drive it with an adapter around the CPU oracle to compare trajectories.
+"""
+import numpy as np
+
+from . import synth
+
+KEYFRAME_MIN_DISTANCE = 1.4   # keyFrameMiniDistance, config/params.yaml
+KEYFRAME_MIN_YAW = 0.5        # keyFrameMiniYaw
+WINDOW = 19                   # while (laserCloudSurfVec.size() >= 20) erase(begin)  (:463-467)
+
+
+def transform_cloud(pts4, pose6):
+    """common.cpp:113-150 transformPointCloud(cloudIn, PointTypePose*): q = R p + t in fp32, intensity kept."""
+    T = synth.pose_to_T(pose6).astype(np.float32)
+    out = np.array(pts4, dtype=np.float32, copy=True)
+    x, y, z = pts4[:, 0], pts4[:, 1], pts4[:, 2]
+    out[:, 0] = T[0, 0] * x + T[0, 1] * y + T[0, 2] * z + T[0, 3]
+    out[:, 1] = T[1, 0] * x + T[1, 1] * y + T[1, 2] * z + T[1, 3]
+    out[:, 2] = T[2, 0] * x + T[2, 1] * y + T[2, 2] * z + T[2, 3]
+    return out
+
+
+class OdometryStream:
+    def __init__(self, backend, lm_params, feat_params=None, corner_leaf=0.2, surf_leaf=0.4):
+        self.be, self.prm, self.fprm = backend, lm_params, feat_params
+        self.corner_leaf, self.surf_leaf = corner_leaf, surf_leaf
+        self.pose = np.zeros(6, np.float32)          # transformTobeMapped
+        self.last_pose = None                        # lastTransformTobeMapped
+        self.key_pose = np.zeros(6, np.float32)      # transformPriFrame
+        self.kf_corner, self.kf_surf = [], []
+        self.keyframe_id = 0
+        self.first = True
+        self.trajectory, self.results = [], []
+
+    def _update_initial_guess(self):
+        if self.last_pose is None:
+            self.last_pose = self.pose.copy()
+            return
+        T_back, T_last = synth.pose_to_T(self.pose), synth.pose_to_T(self.last_pose)
+        self.last_pose = self.pose.copy()
+        incre = np.linalg.inv(T_last) @ T_back
+        self.pose = synth.T_to_pose(T_back @ incre)
+
+    def _save_keyframe(self, corner_full, surf_full):
+        self.kf_corner.append(transform_cloud(corner_full, self.pose))
+        self.kf_surf.append(transform_cloud(surf_full, self.pose))
+        while len(self.kf_surf) >= WINDOW + 1:
+            self.kf_surf.pop(0); self.kf_corner.pop(0)
+        self.key_pose = self.pose.copy()
+        self.keyframe_id += 1
+
+    def push(self, pts, ring, initial_pose=None):
+        """One LiDAR frame.  Returns the pose estimate [roll, pitch, yaw, x, y, z]."""
+        if self.first and initial_pose is not None:
+            self.pose = np.asarray(initial_pose, np.float32).copy()
+        self._update_initial_guess()
+        f = self.be.extract_features(pts, ring, self.fprm) if self.fprm is not None else self.be.extract_features(pts, ring)
+        ext = np.ascontiguousarray(pts[f["src_index"]], np.float32)
+        corner_full = np.ascontiguousarray(ext[f["corner_idx"]]); surf_full = np.ascontiguousarray(ext[f["surf_idx"]])
+        if self.first:
+            self._save_keyframe(corner_full, surf_full)
+            self.first = False
+            self.trajectory.append(self.pose.copy()); self.results.append(None)
+            return self.pose.copy()
+        map_corner = self.be.voxel_grid(np.concatenate(self.kf_corner[::-1]), self.corner_leaf)
+        map_surf = self.be.voxel_grid(np.concatenate(self.kf_surf[::-1]), self.surf_leaf)
+        mid = self.be.map_create(map_corner, map_surf)
+        corner = self.be.voxel_grid(corner_full, self.corner_leaf)
+        surf = self.be.voxel_grid(surf_full, self.surf_leaf)
+        pose, res = self.be.scan2map(mid, corner, surf, self.pose, self.prm)
+        self.be.map_destroy(mid)
+        self.pose = np.asarray(pose, np.float32).copy()
+        if res.deltaR < 0.005 or res.deltaT < 0.05:
+            inc = synth.T_to_pose(np.linalg.inv(synth.pose_to_T(self.key_pose)) @ synth.pose_to_T(self.pose))
+            if self.keyframe_id <= 5 or abs(inc[2]) >= KEYFRAME_MIN_YAW or abs(inc[3]) >= KEYFRAME_MIN_DISTANCE or abs(inc[4]) >= KEYFRAME_MIN_DISTANCE:
+                self._save_keyframe(corner_full, surf_full)
+        self.trajectory.append(self.pose.copy()); self.results.append(res)
+        return self.pose.copy()
+
+
+class EngineBackend:
+    """Adapter: lis_slam_b200.engine.Engine -> the backend protocol above."""
+
+    def __init__(self, eng, gate_hint=1.0):
+        self.eng, self.gate = eng, gate_hint
+
+    def extract_features(self, pts, ring, prm=None):
+        return self.eng.extract_features(pts, ring, prm)
+
+    def voxel_grid(self, pts, leaf):
+        return self.eng.voxel_grid(pts, leaf)
+
+    def map_create(self, corner, surf):
+        return self.eng.map_create(corner, surf, gate_hint=self.gate)
+
+    def map_destroy(self, mid):
+        self.eng.map_destroy(mid)
+
+    def scan2map(self, mid, corner, surf, pose, prm):
+        p, r, _ = self.eng.scan2map(mid, corner, surf, pose, prm)
+        return p, r
