@@ -76,7 +76,8 @@ struct lisreg_ctx {
   // feature-extraction work buffers (capacity feat_cap_frames frames of feat_cells cells)
   DevBuf d_feat, d_feat_frames;
   int feat_cap_frames = 0, feat_cells = 0, feat_nscan = 0;
-  DevBuf d_epsc, d_epsc2, d_icp;
+  DevBuf d_epsc, d_epsc2, d_icp, d_nbr;
+  int lm_split = 1;   // 1: k_lm_knn + k_lm_resid (default, faster), 0: fused k_lm_iter (LISREG_LM_FUSED=1)
   // voxel-grid work buffers
   DevBuf d_vox, d_vox_segs;
   // profiling
@@ -317,7 +318,7 @@ int32_t lisreg_create(const lisreg_config* cfg, lisreg_ctx** out) {
     ctx->own_stream = true;
   } else { ctx->stream = cfg ? (cudaStream_t)cfg->stream : nullptr; ctx->own_stream = false; }   // NULL = legacy default stream
   if (cfg && cfg->max_grid_cells > 0) ctx->max_cells = cfg->max_grid_cells;
-  if (const char* e2 = getenv("LISREG_STACK")) cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atoi(e2));
+  if (const char* e2 = getenv("LISREG_LM_FUSED")) ctx->lm_split = atoi(e2) ? 0 : 1;
   *out = ctx;
   return LISREG_OK;
 }
@@ -331,7 +332,7 @@ void lisreg_destroy(lisreg_ctx* ctx) {
   }
   if (ctx->d_maps) cudaFree(ctx->d_maps);
   for (DevBuf* b : {&ctx->d_stage, &ctx->d_descs, &ctx->d_states, &ctx->d_partials, &ctx->d_tickets, &ctx->d_logs,
-                    &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox, &ctx->d_feat, &ctx->d_feat_frames, &ctx->d_vox, &ctx->d_vox_segs, &ctx->d_epsc, &ctx->d_epsc2, &ctx->d_icp}) b->release();
+                    &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox, &ctx->d_feat, &ctx->d_feat_frames, &ctx->d_vox, &ctx->d_vox_segs, &ctx->d_epsc, &ctx->d_epsc2, &ctx->d_icp, &ctx->d_nbr}) b->release();
   ctx->h_stage.release(); ctx->h_out.release();
   for (auto& p : ctx->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : ctx->ev_free) cudaEventDestroy(e);
@@ -477,8 +478,18 @@ static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, dou
   dim3 grid(std::min(max_tiles, B >= 32 ? 32 : 1024), B);
   {
     ProfScope ps(ctx, PROF_LM, alg_bytes_per_iter * dp.max_iters, dp.max_iters);
+    int* nbr = nullptr;
+    if (ctx->lm_split) {
+      CK(ctx->d_nbr.reserve(sizeof(int) * 5 * (size_t)tile_pts * max_tiles * B));
+      nbr = (int*)ctx->d_nbr.p;
+    }
     for (int it = 0; it < dp.max_iters; it++) {
-      k_lm_iter<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp, partials, max_tiles, tile_pts); LAUNCH_CK();
+      if (ctx->lm_split) {
+        k_lm_knn<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, max_tiles, tile_pts); LAUNCH_CK();
+        k_lm_resid<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp, nbr, partials, max_tiles, tile_pts); LAUNCH_CK();
+      } else {
+        k_lm_iter<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp, partials, max_tiles, tile_pts); LAUNCH_CK();
+      }
       k_lm_solve<<<(B + LM_SOLVE_THREADS / 32 - 1) / (LM_SOLVE_THREADS / 32), LM_SOLVE_THREADS, 0, st>>>(
           d_descs, states, dp, partials, d_logs, max_tiles, tile_pts, B); LAUNCH_CK();
     }

@@ -405,6 +405,179 @@ k_lm_iter(const RegDesc* __restrict__ descs, RegState* __restrict__ states, cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Split variant of k_lm_iter: the 5-NN search (few registers, latency bound -> wants many resident warps) and
+// the coefficient / reduction phases (many registers) run as two kernels, the 5 neighbour positions of every
+// query crossing through global memory (20 B per query, negligible next to the candidate traffic).
+// Same arithmetic, same tile partial layout, same fixed summation order => bit-identical results.
+// ---------------------------------------------------------------------------------------------------------
+#ifndef LM_KNN_MIN_BLOCKS
+#define LM_KNN_MIN_BLOCKS 12
+#endif
+__global__ void __launch_bounds__(LM_THREADS, LM_KNN_MIN_BLOCKS)
+k_lm_knn(const RegDesc* __restrict__ descs, const RegState* __restrict__ states, const MapDev* __restrict__ maps,
+         float gate, int* __restrict__ nbr, int max_tiles, int tile_pts) {
+  const int b = blockIdx.y, tid = threadIdx.x;
+  __shared__ RegDesc sd;
+  __shared__ float sT[12];
+  __shared__ int sdone;
+  __shared__ unsigned short s_def[LM_MAX_TILE];
+  __shared__ int s_ndef;
+  if (tid == 0) { sd = descs[b]; sd.nc = states[b].nc; sd.ns = states[b].ns; sdone = states[b].done; }
+  if (tid < 12) sT[tid] = states[b].T[tid];
+  __syncthreads();
+  if (sdone) return;
+  const int n = sd.nc + sd.ns;
+  const int ntiles = (n + tile_pts - 1) / tile_pts;
+  const MapDev& mp = maps[sd.map_slot];
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int q0 = tile * tile_pts;
+    const int qn = min(n - q0, tile_pts);
+    int* tnbr = nbr + ((size_t)b * max_tiles + tile) * 5 * tile_pts;   // [5][tile_pts]
+    if (tid == 0) s_ndef = 0;
+    __syncthreads();
+    for (int l = tid; l < tile_pts; l += LM_THREADS) {
+      int accepted = 0, deferred = 0;
+      knn_key best[5];
+      if (l < qn) {
+        const int q = q0 + l;
+        const bool is_corner = q < sd.nc;
+        const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
+        const float x0 = sT[0] * p.x + sT[1] * p.y + sT[2] * p.z + sT[3];
+        const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
+        const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
+        const GridDev& g = is_corner ? mp.corner : mp.surf;
+        int cx, cy, cz; float minf;
+        deferred = knn_grid_block<5>(g, x0, y0, z0, gate, best, cx, cy, cz, minf) ? 1 : 0;
+        accepted = knn_key_d(best[4]) < gate;
+      }
+      if (deferred) {
+        s_def[atomicAdd(&s_ndef, 1)] = (unsigned short)l;
+      } else if (accepted) {
+#pragma unroll
+        for (int j = 0; j < 5; j++) tnbr[j * tile_pts + l] = knn_key_pos(best[j]);
+      } else {
+        tnbr[l] = -1;
+      }
+    }
+    __syncthreads();
+    for (int d = tid; d < s_ndef; d += LM_THREADS) {
+      const int l = s_def[d];
+      const int q = q0 + l;
+      const bool is_corner = q < sd.nc;
+      const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
+      const float x0 = sT[0] * p.x + sT[1] * p.y + sT[2] * p.z + sT[3];
+      const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
+      const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
+      const GridDev& g = is_corner ? mp.corner : mp.surf;
+      knn_key best[5];
+      knn_grid<5>(g, x0, y0, z0, gate, best);
+      if (knn_key_d(best[4]) < gate) {
+#pragma unroll
+        for (int j = 0; j < 5; j++) tnbr[j * tile_pts + l] = knn_key_pos(best[j]);
+      } else {
+        tnbr[l] = -1;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(LM_THREADS, 5)
+k_lm_resid(const RegDesc* __restrict__ descs, const RegState* __restrict__ states, const MapDev* __restrict__ maps,
+           LmParamsDev prm, const int* __restrict__ nbr, double* __restrict__ partials, int max_tiles, int tile_pts) {
+  const int b = blockIdx.y, tid = threadIdx.x;
+  __shared__ RegDesc sd;
+  __shared__ float sT[12], sTrig[6];
+  __shared__ int sdone;
+  __shared__ float s_row[7 * LM_MAX_TILE];
+  __shared__ double swarp[LM_THREADS / 32][LM_NSUM];
+  if (tid == 0) { sd = descs[b]; sd.nc = states[b].nc; sd.ns = states[b].ns; sdone = states[b].done; }
+  if (tid < 12) sT[tid] = states[b].T[tid];
+  if (tid >= 32 && tid < 38) sTrig[tid - 32] = states[b].trig[tid - 32];
+  __syncthreads();
+  if (sdone) return;
+  const int n = sd.nc + sd.ns;
+  const int ntiles = (n + tile_pts - 1) / tile_pts;
+  const MapDev& mp = maps[sd.map_slot];
+  const float srx = sTrig[0], crx = sTrig[1], sry = sTrig[2], cry = sTrig[3], srz = sTrig[4], crz = sTrig[5];
+  const int lane = tid & 31, wid = tid >> 5;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int q0 = tile * tile_pts;
+    const int qn = min(n - q0, tile_pts);
+    const int* tnbr = nbr + ((size_t)b * max_tiles + tile) * 5 * tile_pts;
+    int cntC = 0, cntS = 0;
+    for (int l = tid; l < tile_pts; l += LM_THREADS) {
+      float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const int pos0 = l < qn ? tnbr[l] : -1;
+      if (pos0 >= 0) {
+        const int q = q0 + l;
+        const bool is_corner = q < sd.nc;
+        const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
+        const float x0 = sT[0] * p.x + sT[1] * p.y + sT[2] * p.z + sT[3];
+        const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
+        const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
+        const float4* __restrict__ pts = is_corner ? mp.corner.pts : mp.surf.pts;
+        float4 nb[5];
+        nb[0] = __ldg(&pts[pos0]);
+#pragma unroll
+        for (int j = 1; j < 5; j++) nb[j] = __ldg(&pts[tnbr[j * tile_pts + l]]);
+        float raw[5];
+        const bool ok = is_corner ? corner_coeff(x0, y0, z0, nb, raw) : surf_coeff(x0, y0, z0, nb, raw);
+        if (ok) {
+          float w = 1.0f;
+          if (prm.use_w) {
+            const uint16_t* lab = is_corner ? sd.clabel : sd.slabel;
+            unsigned lb = lab ? lab[is_corner ? q : q - sd.nc] : 0u;
+            float sc = lb < LISREG_LUT_SIZE ? prm.label_score[lb] : 0.f;
+            w = (float)(2.0 - (double)sc);
+          }
+          const float ws = w * raw[4];
+          const float c_x = ws * raw[0], c_y = ws * raw[1], c_z = ws * raw[2], c_i = ws * raw[3];
+          if (is_corner) cntC++; else cntS++;
+          const float px = p.y, py = p.z, pz = p.x;
+          const float cx = c_y, cy = c_z, cz = c_x;
+          const float arx = (crx * sry * srz * px + crx * crz * sry * py - srx * sry * pz) * cx +
+                            (-srx * srz * px - crz * srx * py - crx * pz) * cy +
+                            (crx * cry * srz * px + crx * cry * crz * py - cry * srx * pz) * cz;
+          const float ary = ((cry * srx * srz - crz * sry) * px + (sry * srz + cry * crz * srx) * py + crx * cry * pz) * cx +
+                            ((-cry * crz - srx * sry * srz) * px + (cry * srz - crz * srx * sry) * py - crx * sry * pz) * cz;
+          const float arz = ((crz * srx * sry - cry * srz) * px + (-cry * crz - srx * sry * srz) * py) * cx +
+                            (crx * crz * px - crx * srz * py) * cy +
+                            ((sry * srz + cry * crz * srx) * px + (crz * sry - cry * srx * srz) * py) * cz;
+          row[0] = arz; row[1] = arx; row[2] = ary; row[3] = cz; row[4] = cx; row[5] = cy; row[6] = -c_i;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 7; k++) s_row[k * LM_MAX_TILE + l] = row[k];
+    }
+    __syncthreads();
+    {
+      int r, c;
+      lm_pair_of_lane(lane < 27 ? lane : 0, r, c);
+      const int per_warp = tile_pts / (LM_THREADS / 32);
+      const float* __restrict__ ra = s_row + r * LM_MAX_TILE + wid * per_warp;
+      const float* __restrict__ rc = s_row + c * LM_MAX_TILE + wid * per_warp;
+      double v = 0.0;
+      for (int i = 0; i < per_warp; i++) v += (double)ra[i] * (double)rc[i];
+      if (lane < 27) swarp[wid][lane] = v;
+      int cc = cntC, s2 = cntS;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { cc += __shfl_down_sync(0xffffffffu, cc, o); s2 += __shfl_down_sync(0xffffffffu, s2, o); }
+      if (lane == 0) { swarp[wid][27] = (double)cc; swarp[wid][28] = (double)s2; }
+    }
+    __syncthreads();
+    double* mypart = partials + ((size_t)b * max_tiles + tile) * LM_NSUM;
+    if (tid < 29) {
+      double v = 0.0;
+#pragma unroll
+      for (int w2 = 0; w2 < LM_THREADS / 32; w2++) v += swarp[w2][tid];
+      mypart[tid] = v;
+    }
+    __syncthreads();
+  }
+}
+
 // LMOptimization tail: one warp per registration sums the tile partials in tile order (fixed
 // order => bit-reproducible) and lane 0 runs the 6x6 solve / degeneracy / pose update.
 // Kept out of k_lm_iter so that the hot kernel has no large stack frame or cold code.

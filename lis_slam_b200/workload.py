@@ -23,6 +23,16 @@ def throughput_batch(B=512, n_maps=8, n_scans=32, n_corner=4000, n_surf=12000, m
         nc = int(n_corner * rng.uniform(0.85, 1.15)); ns = int(n_surf * rng.uniform(0.85, 1.15))
         f = sc.sample_scan_features(truth, n_corner=nc, n_surf=ns, seed=1000 * seed + 100 + s)
         scans.append((f, truth))
+    import os
+    if os.environ.get("LISREG_BENCH_PRESORT"):      # experiment: queries pre-sorted by map cell (x fastest)
+        h = float(os.environ["LISREG_BENCH_PRESORT"])
+        for i, (f, truth) in enumerate(scans):
+            T = synth.pose_to_T(truth)
+            for key in ("corner", "surf"):
+                w = f[key][:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3]
+                c = np.floor((w - w.min(0)) / h).astype(np.int64)
+                order = np.lexsort((c[:, 0], c[:, 1], c[:, 2]))
+                f[key] = np.ascontiguousarray(f[key][order]); f[key + "_label"] = f[key + "_label"][order]
     regs = []
     for b in range(B):
         s = b % n_scans
