@@ -103,22 +103,25 @@ LISREG_HD __forceinline__ void knn_row_range(const GridDev& g, int x0, int x1, i
 }
 
 // Outer shells t = 2, 3, ... (rare: sparse neighbourhoods).  Kept out of line so that the hot
-// 3x3x3 loop stays small in the instruction cache.
-template <int K>
-LISREG_HD __noinline__ void knn_outer_shells(const GridDev& g, float qx, float qy, float qz, float gate,
-                                            int cx, int cy, int cz, float minf, knn_key (&best)[K]) {
+// 3x3x3 loop stays small in the instruction cache.  best[KD] is the key that drives the stop test (K > KD + 1
+// tracks extra runners-up without changing what is visited).  Returns a lower bound on the distance from the
+// query to every map point NOT visited (FLT_MAX when the whole grid has been visited).
+template <int K, int KD = K - 1>
+LISREG_HD __noinline__ float knn_outer_shells(const GridDev& g, float qx, float qy, float qz, float gate,
+                                             int cx, int cy, int cz, float minf, knn_key (&best)[K]) {
   // shells beyond the grid extent contain nothing
   int reach = cx > g.nx - 1 - cx ? cx : g.nx - 1 - cx;
   reach = reach > cy ? reach : cy; reach = reach > g.ny - 1 - cy ? reach : g.ny - 1 - cy;
   reach = reach > cz ? reach : cz; reach = reach > g.nz - 1 - cz ? reach : g.nz - 1 - cz;
   const float fs = ceilf(sqrtf(gate) * g.inv_h) + 1.f;
   int max_shell = fs < 1.0e6f ? (int)fs : 1000000;
+  const bool whole_grid = max_shell >= reach;
   if (max_shell > reach) max_shell = reach;
   for (int s = 1; s <= max_shell; s++) {
     // everything not yet visited is farther than lb (margin covers the float rounding of cell assignment)
     const float lb = ((float)s + minf - 1e-3f) * g.h;
     const float lb2 = lb * lb;
-    if (lb > 0.f && (knn_key_d(best[K - 1]) < lb2 || lb2 >= gate)) break;
+    if (lb > 0.f && (knn_key_d(best[KD]) < lb2 || lb2 >= gate)) return lb;
     const int t = s + 1;   // visit shell t
     const int za = cz - t > 0 ? cz - t : 0, zb = cz + t < g.nz - 1 ? cz + t : g.nz - 1;
     const int ya = cy - t > 0 ? cy - t : 0, yb = cy + t < g.ny - 1 ? cy + t : g.ny - 1;
@@ -136,15 +139,22 @@ LISREG_HD __noinline__ void knn_outer_shells(const GridDev& g, float qx, float q
       }
     }
   }
+  // shells 2 .. max_shell + 1 visited: either that was the whole grid, or the next shell starts beyond the gate radius
+  if (whole_grid) return FLT_MAX;
+  const float lbn = ((float)(max_shell + 1) + minf - 1e-3f) * g.h;
+  return lbn > 0.f ? lbn : 0.f;
 }
 
-// The 3x3x3 block of the search.  best[] ascending; unused slots keep the sentinel (d^2 = gate, position
-// 0xffffffff).  Returns true when something outside the block could still beat the K-th best, i.e. the outer
-// shells must be visited (knn_outer_shells) for the result to be exact.
-template <int K>
+// The 3x3x3 block of the search.  best[] ascending; unused slots keep the sentinel (d^2 = gate - or +inf when
+// INF_SENTINEL, which lets runners-up beyond the gate be tracked - position 0xffffffff).  Returns true when
+// something outside the block could still beat best[KD], i.e. the outer shells must be visited
+// (knn_outer_shells) for the result to be exact.
+LISREG_HD __forceinline__ float knn_block_lb(const GridDev& g, float minf) { return (1.f + minf - 1e-3f) * g.h; }
+
+template <int K, int KD = K - 1, bool INF_SENTINEL = false>
 LISREG_HD __forceinline__ bool knn_grid_block(const GridDev& g, float qx, float qy, float qz, float gate, knn_key (&best)[K],
                                                int& cx, int& cy, int& cz, float& minf) {
-  const knn_key sentinel = ((knn_key)(unsigned)f2i(gate) << 32) | 0xffffffffull;
+  const knn_key sentinel = ((knn_key)(unsigned)(INF_SENTINEL ? 0x7f800000 : f2i(gate)) << 32) | 0xffffffffull;
 #pragma unroll
   for (int j = 0; j < K; j++) best[j] = sentinel;
   cx = cy = cz = 0; minf = 0.f;
@@ -164,9 +174,9 @@ LISREG_HD __forceinline__ bool knn_grid_block(const GridDev& g, float qx, float 
     knn_scan_range<K>(g.pts, b, e, qx, qy, qz, best);
     b = nb; e = ne;
   }
-  const float lb = (1.f + minf - 1e-3f) * g.h;
+  const float lb = knn_block_lb(g, minf);
   const float lb2 = lb * lb;
-  return !(knn_key_d(best[K - 1]) < lb2 || lb2 >= gate);
+  return !(knn_key_d(best[KD]) < lb2 || lb2 >= gate);
 }
 
 // Exact K-NN restricted to squared distance < gate ("K neighbours inside the gate" <=> key_d(best[K-1]) < gate).
@@ -174,6 +184,16 @@ template <int K>
 LISREG_HD __forceinline__ void knn_grid(const GridDev& g, float qx, float qy, float qz, float gate, knn_key (&best)[K]) {
   int cx, cy, cz; float minf;
   if (knn_grid_block<K>(g, qx, qy, qz, gate, best, cx, cy, cz, minf)) knn_outer_shells<K>(g, qx, qy, qz, gate, cx, cy, cz, minf, best);
+}
+
+// Exact KD+1 nearest neighbours plus the K - KD - 1 runners-up among everything visited (+inf sentinel, so the
+// runners-up may lie beyond the gate).  Returns the lower bound on the distance to every point NOT visited.
+template <int K, int KD>
+LISREG_HD __forceinline__ float knn_grid_tracked(const GridDev& g, float qx, float qy, float qz, float gate, knn_key (&best)[K]) {
+  int cx, cy, cz; float minf;
+  if (knn_grid_block<K, KD, true>(g, qx, qy, qz, gate, best, cx, cy, cz, minf))
+    return knn_outer_shells<K, KD>(g, qx, qy, qz, gate, cx, cy, cz, minf, best);
+  return g.n > 0 ? knn_block_lb(g, minf) : FLT_MAX;
 }
 
 LISREG_HD __forceinline__ void knn5_grid(const GridDev& g, float qx, float qy, float qz, float gate, knn_key (&best)[5]) {

@@ -77,7 +77,13 @@ struct lisreg_ctx {
   DevBuf d_feat, d_feat_frames;
   int feat_cap_frames = 0, feat_cells = 0, feat_nscan = 0;
   DevBuf d_epsc, d_epsc2, d_icp, d_nbr;
-  int lm_split = 1;   // 1: k_lm_knn + k_lm_resid (default, faster), 0: fused k_lm_iter (LISREG_LM_FUSED=1)
+  // e2e pipeline: H2D of chunk c+1 on copy_stream overlaps the compute of chunk c on `stream`
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_ev;
+  PinBuf h_desc;       // pinned descriptor staging of the arena entry points (one slice per chunk)
+  int e2e_chunk = 32;  // frames per chunk (LISREG_E2E_CHUNK; 0 = one copy, no overlap)
+  DevBuf d_kstate;
+  int knn_noskip = 0;   // LISREG_KNN_NOSKIP=1: search every query from scratch at every iteration (parity check of the CHECK path)
   // voxel-grid work buffers
   DevBuf d_vox, d_vox_segs;
   // profiling
@@ -318,7 +324,8 @@ int32_t lisreg_create(const lisreg_config* cfg, lisreg_ctx** out) {
     ctx->own_stream = true;
   } else { ctx->stream = cfg ? (cudaStream_t)cfg->stream : nullptr; ctx->own_stream = false; }   // NULL = legacy default stream
   if (cfg && cfg->max_grid_cells > 0) ctx->max_cells = cfg->max_grid_cells;
-  if (const char* e2 = getenv("LISREG_LM_FUSED")) ctx->lm_split = atoi(e2) ? 0 : 1;
+  if (const char* e2 = getenv("LISREG_KNN_NOSKIP")) ctx->knn_noskip = atoi(e2) ? 1 : 0;
+  if (const char* e3 = getenv("LISREG_E2E_CHUNK")) ctx->e2e_chunk = std::max(0, atoi(e3));
   *out = ctx;
   return LISREG_OK;
 }
@@ -332,8 +339,10 @@ void lisreg_destroy(lisreg_ctx* ctx) {
   }
   if (ctx->d_maps) cudaFree(ctx->d_maps);
   for (DevBuf* b : {&ctx->d_stage, &ctx->d_descs, &ctx->d_states, &ctx->d_partials, &ctx->d_tickets, &ctx->d_logs,
-                    &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox, &ctx->d_feat, &ctx->d_feat_frames, &ctx->d_vox, &ctx->d_vox_segs, &ctx->d_epsc, &ctx->d_epsc2, &ctx->d_icp, &ctx->d_nbr}) b->release();
-  ctx->h_stage.release(); ctx->h_out.release();
+                    &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox, &ctx->d_feat, &ctx->d_feat_frames, &ctx->d_vox, &ctx->d_vox_segs, &ctx->d_epsc, &ctx->d_epsc2, &ctx->d_icp, &ctx->d_nbr, &ctx->d_kstate}) b->release();
+  ctx->h_stage.release(); ctx->h_out.release(); ctx->h_desc.release();
+  for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& p : ctx->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : ctx->ev_free) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -438,7 +447,7 @@ int32_t lisreg_knn5(lisreg_ctx* ctx, int32_t map_id, int32_t which, const float*
   CK(ctx->d_stage.reserve(bq + bi + bd));
   char* d = (char*)ctx->d_stage.p;
   CK(cudaMemcpyAsync(d, queries, bq, cudaMemcpyHostToDevice, ctx->stream));
-  k_knn5<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(g, (const float4*)d, nq, sqdist_gate, (int*)(d + bq), (float*)(d + bq + bi)); LAUNCH_CK();
+  k_knn5<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(g, (const float4*)d, nq, sqdist_gate, (int*)(d + bq), (float*)(d + bq + bi), nullptr); LAUNCH_CK();
   CK(cudaMemcpyAsync(idx, d + bq, bi, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(sqd, d + bq + bi, bd, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -455,15 +464,18 @@ static void to_dev_params(const lisreg_lm_params* p, LmParamsDev* d) {
 }
 
 // core driver: descs already on the device. max_n = largest nc+ns of the batch.
+// tiling_B: batch size that decides the tile size (a chunk of a larger batch must tile like the whole batch so
+// that the fixed summation order - hence every bit of the result - does not depend on the chunking); 0 = B
 static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, double alg_bytes_per_iter, float* d_pose,
-                  const lisreg_lm_params* prm, lisreg_lm_result* d_res, lisreg_lm_iter* d_logs) {
+                  const lisreg_lm_params* prm, lisreg_lm_result* d_res, lisreg_lm_iter* d_logs, int tiling_B = 0) {
   cudaStream_t st = ctx->stream;
   int rc = sync_maps(ctx);
   if (rc) return rc;
   LmParamsDev dp; to_dev_params(prm, &dp);
   // tile size: big batches amortise the 27-term reduction over 4 queries per thread; a lone
   // registration is spread over as many SMs as possible
-  const int tile_pts = (B >= 32) ? LM_MAX_TILE : LM_THREADS;
+  if (tiling_B <= 0) tiling_B = B;
+  const int tile_pts = (tiling_B >= 32) ? LM_MAX_TILE : LM_THREADS;
   const int max_tiles = std::max(1, (max_n + tile_pts - 1) / tile_pts);
   CK(ctx->d_states.reserve(sizeof(RegState) * (size_t)B));
   CK(ctx->d_partials.reserve(sizeof(double) * LM_NSUM * (size_t)B * max_tiles));
@@ -475,21 +487,18 @@ static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, dou
   // a block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...: batches get 32 blocks per registration
   // (the real tile count is only known on the device in the frame pipeline), a lone registration gets
   // one block per tile so that it spreads over the whole GPU
-  dim3 grid(std::min(max_tiles, B >= 32 ? 32 : 1024), B);
+  dim3 grid(std::min(max_tiles, tiling_B >= 32 ? 32 : 1024), B);
   {
     ProfScope ps(ctx, PROF_LM, alg_bytes_per_iter * dp.max_iters, dp.max_iters);
-    int* nbr = nullptr;
-    if (ctx->lm_split) {
-      CK(ctx->d_nbr.reserve(sizeof(int) * 5 * (size_t)tile_pts * max_tiles * B));
-      nbr = (int*)ctx->d_nbr.p;
-    }
+    CK(ctx->d_nbr.reserve(sizeof(int) * 5 * (size_t)tile_pts * max_tiles * B));
+    CK(ctx->d_kstate.reserve(sizeof(KnnState) * (size_t)tile_pts * max_tiles * B));
+    int* nbr = (int*)ctx->d_nbr.p;
+    KnnState* kstate = (KnnState*)ctx->d_kstate.p;
     for (int it = 0; it < dp.max_iters; it++) {
-      if (ctx->lm_split) {
-        k_lm_knn<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, max_tiles, tile_pts); LAUNCH_CK();
-        k_lm_resid<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp, nbr, partials, max_tiles, tile_pts); LAUNCH_CK();
-      } else {
-        k_lm_iter<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp, partials, max_tiles, tile_pts); LAUNCH_CK();
-      }
+      // iteration 0 searches every query; later iterations first try to PROVE that the neighbours did not change
+      k_lm_knn<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, kstate, max_tiles, tile_pts,
+                                            (it > 0 && !ctx->knn_noskip) ? 1 : 0); LAUNCH_CK();
+      k_lm_resid<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp, nbr, partials, max_tiles, tile_pts); LAUNCH_CK();
       k_lm_solve<<<(B + LM_SOLVE_THREADS / 32 - 1) / (LM_SOLVE_THREADS / 32), LM_SOLVE_THREADS, 0, st>>>(
           d_descs, states, dp, partials, d_logs, max_tiles, tile_pts, B); LAUNCH_CK();
     }
@@ -826,8 +835,14 @@ void lisreg_frame_params_default(lisreg_frame_params* p) {
 }
 
 // d_pts_base/d_ring_base: if arena != nullptr the item pointers are byte offsets into it
+// h_pinned: optional pinned staging (frame_desc_bytes(F) bytes, private to this call slice) for the descriptor
+// upload; NULL = pageable vectors (cudaMemcpyAsync returns once a small pageable source has been consumed).
+static size_t frame_desc_bytes(int F) {
+  return ((sizeof(FeatFrame) + 2 * sizeof(VoxSeg) + sizeof(RegDesc)) * (size_t)F + 255) & ~size_t(255);
+}
 static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, const char* d_arena, uint64_t arena_bytes,
-                      float* d_pose, const lisreg_frame_params* prm, lisreg_lm_result* d_res) {
+                      float* d_pose, const lisreg_frame_params* prm, lisreg_lm_result* d_res, char* h_pinned = nullptr,
+                      int tiling_B = 0) {
   cudaStream_t st = ctx->stream;
   const lisreg_feat_params* fp = &prm->feat;
   if (fp->n_scan <= 0 || fp->horizon <= 0 || fp->horizon > 2048 || fp->n_scan * 6 > 1024 || fp->downsample_rate <= 0)
@@ -842,9 +857,14 @@ static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, co
   CK(ctx->d_vox.reserve((vc_per + vs_per) * (size_t)F));
   CK(ctx->d_vox_segs.reserve(sizeof(VoxSeg) * 2 * (size_t)F));
   CK(ctx->d_descs.reserve(sizeof(RegDesc) * (size_t)F));
-  std::vector<FeatFrame> hf((size_t)F);
-  std::vector<VoxSeg> hv(2 * (size_t)F);
-  std::vector<RegDesc> hd((size_t)F);
+  std::vector<FeatFrame> vf; std::vector<VoxSeg> vv; std::vector<RegDesc> vd;
+  FeatFrame* hf; VoxSeg* hv; RegDesc* hd;
+  if (h_pinned) {
+    hf = (FeatFrame*)h_pinned; hv = (VoxSeg*)(hf + F); hd = (RegDesc*)(hv + 2 * (size_t)F);
+  } else {
+    vf.resize((size_t)F); vv.resize(2 * (size_t)F); vd.resize((size_t)F);
+    hf = vf.data(); hv = vv.data(); hd = vd.data();
+  }
   int max_n = 0; double feat_bytes = 0;
   for (int i = 0; i < F; i++) {
     const lisreg_frame_item& it = items[i];
@@ -871,9 +891,9 @@ static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, co
     max_n = std::max(max_n, it.n); feat_bytes += 17.0 * it.n;
   }
   // pageable sources: cudaMemcpyAsync returns once they are consumed
-  CK(cudaMemcpyAsync(ctx->d_feat_frames.p, hf.data(), sizeof(FeatFrame) * (size_t)F, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(ctx->d_vox_segs.p, hv.data(), sizeof(VoxSeg) * 2 * (size_t)F, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(ctx->d_descs.p, hd.data(), sizeof(RegDesc) * (size_t)F, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_feat_frames.p, hf, sizeof(FeatFrame) * (size_t)F, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_vox_segs.p, hv, sizeof(VoxSeg) * 2 * (size_t)F, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_descs.p, hd, sizeof(RegDesc) * (size_t)F, cudaMemcpyHostToDevice, st));
   rc = run_features(ctx, (FeatFrame*)ctx->d_feat_frames.p, F, fp, max_n, feat_bytes);
   if (rc) return rc;
   rc = run_voxel(ctx, (VoxSeg*)ctx->d_vox_segs.p, 2 * F, std::min(max_n, cells), 2.0 * feat_bytes);
@@ -882,7 +902,7 @@ static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, co
   // of this batch (blocks beyond a frame's real tile count exit immediately).  Voxel output never exceeds
   // its input, and the input never exceeds the sweep size.
   const int lm_max_n = std::min(max_n, cells);
-  return run_lm(ctx, F, (const RegDesc*)ctx->d_descs.p, lm_max_n, 0.0, d_pose, &prm->lm, d_res, nullptr);
+  return run_lm(ctx, F, (const RegDesc*)ctx->d_descs.p, lm_max_n, 0.0, d_pose, &prm->lm, d_res, nullptr, tiling_B);
 }
 
 int32_t lisreg_frames_batch_dev(lisreg_ctx* ctx, int32_t F, const lisreg_frame_item* items, float* d_pose6xF,
@@ -901,14 +921,65 @@ int32_t lisreg_frames_batch_arena(lisreg_ctx* ctx, int32_t F, const lisreg_frame
   cudaStream_t st = ctx->stream;
   const size_t head = (sizeof(float) * 6 * (size_t)F + 255) & ~size_t(255);
   CK(ctx->d_stage.reserve(head + (size_t)arena_bytes + 16));
-  char* d = (char*)ctx->d_stage.p;
-  CK(cudaMemcpyAsync(d, pose6xF, sizeof(float) * 6 * (size_t)F, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d + head, host_arena, (size_t)arena_bytes, cudaMemcpyHostToDevice, st));
   CK(ctx->d_res.reserve(sizeof(lisreg_lm_result) * (size_t)F));
-  int rc = run_frames(ctx, F, items, d + head, arena_bytes, (float*)d, prm, (lisreg_lm_result*)ctx->d_res.p);
-  if (rc) return rc;
+  char* d = (char*)ctx->d_stage.p;
+  char* d_arena = d + head;
+  float* d_pose = (float*)d;
+  lisreg_lm_result* d_res = (lisreg_lm_result*)ctx->d_res.p;
+  CK(cudaMemcpyAsync(d, pose6xF, sizeof(float) * 6 * (size_t)F, cudaMemcpyHostToDevice, st));
+
+  // Chunk plan: frames [c*C, (c+1)*C) form chunk c; its arena extent is the byte range covering its sweeps.  When
+  // the extents are disjoint and ascending (frames packed in order, the normal case) every chunk is uploaded by its
+  // own copy on a second stream and the pipeline of chunk c (features -> voxel grid -> LM) starts as soon as its
+  // bytes have landed, overlapping the PCIe transfer of the chunks behind it.
+  const int C = ctx->e2e_chunk;
+  const int nchunk = (C > 0 && F > C) ? (F + C - 1) / C : 1;
+  std::vector<uint64_t> lo((size_t)nchunk, ~0ull), hi((size_t)nchunk, 0ull);
+  bool pipelined = nchunk > 1;
+  if (pipelined) {
+    for (int i = 0; i < F; i++) {
+      const lisreg_frame_item& it = items[i];
+      if (it.n <= 0) continue;
+      const int c = i / C;
+      const uint64_t op = (uint64_t)(size_t)it.pts, orr = (uint64_t)(size_t)it.ring;
+      lo[c] = std::min(lo[c], std::min(op, orr));
+      hi[c] = std::max(hi[c], std::max(op + (uint64_t)16 * (uint64_t)it.n, orr + (uint64_t)2 * (uint64_t)it.n));
+    }
+    uint64_t prev = 0;
+    for (int c = 0; c < nchunk && pipelined; c++) {
+      if (hi[c] == 0) { lo[c] = hi[c] = prev; continue; }           // chunk without points
+      lo[c] &= ~uint64_t(15);
+      if (lo[c] < prev || hi[c] > arena_bytes) pipelined = false;   // overlapping / out of range: one copy (run_frames reports bad offsets)
+      prev = hi[c];
+    }
+  }
+  if (!pipelined) {
+    CK(cudaMemcpyAsync(d_arena, host_arena, (size_t)arena_bytes, cudaMemcpyHostToDevice, st));
+    int rc = run_frames(ctx, F, items, d_arena, arena_bytes, d_pose, prm, d_res);
+    if (rc) return rc;
+  } else {
+    if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    while ((int)ctx->chunk_ev.size() < nchunk + 1) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
+    const size_t desc_per = frame_desc_bytes(C);
+    CK(ctx->h_desc.reserve(desc_per * (size_t)nchunk));
+    // the copy stream must not overwrite the arena while earlier work of this context still reads it
+    CK(cudaEventRecord(ctx->chunk_ev[nchunk], st));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[nchunk], 0));
+    for (int c = 0; c < nchunk; c++) {
+      if (hi[c] > lo[c])
+        CK(cudaMemcpyAsync(d_arena + lo[c], (const char*)host_arena + lo[c], (size_t)(hi[c] - lo[c]), cudaMemcpyHostToDevice, ctx->copy_stream));
+      CK(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
+    }
+    for (int c = 0; c < nchunk; c++) {
+      const int f0 = c * C, fc = std::min(C, F - f0);
+      CK(cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0));
+      int rc = run_frames(ctx, fc, items + f0, d_arena, arena_bytes, d_pose + 6 * (size_t)f0, prm, d_res + f0,
+                          (char*)ctx->h_desc.p + desc_per * (size_t)c, F);
+      if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(st); return rc; }
+    }
+  }
   CK(ctx->h_out.reserve(sizeof(lisreg_lm_result) * (size_t)F));
-  CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_res.p, sizeof(lisreg_lm_result) * (size_t)F, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ctx->h_out.p, d_res, sizeof(lisreg_lm_result) * (size_t)F, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   const lisreg_lm_result* hr = (const lisreg_lm_result*)ctx->h_out.p;
   int worst = LISREG_OK;

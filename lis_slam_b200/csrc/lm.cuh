@@ -241,188 +241,129 @@ __device__ __forceinline__ void lm_pair_of_lane(int lane, int& r, int& c) {
 
 constexpr int LM_MAX_TILE = 512;
 
-// One Gauss-Newton iteration for every registration of the batch.  grid = (tiles, B).
-// Phase A (registers: search state only): transform + exact gated 5-NN, neighbour positions -> smem.
-// Phase B (registers: coefficient math only): line/plane coefficient + Jacobian row -> smem.
-// Phase C: each warp reduces a quarter of the tile's rows, lane p owning one of the 27 products
-//          (fp64, fixed order => deterministic), then block partial -> global; the last block of a
-//          registration sums the tile partials in order and runs the 6x6 solve.
-#ifndef LM_MIN_BLOCKS
-#define LM_MIN_BLOCKS 6
-#endif
-__global__ void __launch_bounds__(LM_THREADS, LM_MIN_BLOCKS)
-k_lm_iter(const RegDesc* __restrict__ descs, RegState* __restrict__ states, const MapDev* __restrict__ maps,
-          LmParamsDev prm, double* __restrict__ partials, int max_tiles, int tile_pts) {
-  const int b = blockIdx.y, tid = threadIdx.x;
-  __shared__ RegDesc sd;
-  __shared__ float sT[12], sTrig[6];
-  __shared__ int sdone;
-  __shared__ int s_pos[5 * LM_MAX_TILE];
-  __shared__ unsigned short s_def[LM_MAX_TILE];
-  __shared__ int s_ndef;
-  __shared__ float s_row[7 * LM_MAX_TILE];
-  __shared__ double swarp[LM_THREADS / 32][LM_NSUM];
-  if (tid == 0) { sd = descs[b]; sd.nc = states[b].nc; sd.ns = states[b].ns; sdone = states[b].done; }
-  if (tid < 12) sT[tid] = states[b].T[tid];
-  if (tid >= 32 && tid < 38) sTrig[tid - 32] = states[b].trig[tid - 32];
-  __syncthreads();
-  if (sdone) return;
-  const int n = sd.nc + sd.ns;
-  const int ntiles = (n + tile_pts - 1) / tile_pts;
-  const MapDev& mp = maps[sd.map_slot];
-  const float srx = sTrig[0], crx = sTrig[1], sry = sTrig[2], cry = sTrig[3], srz = sTrig[4], crz = sTrig[5];
-  const int lane = tid & 31, wid = tid >> 5;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-  const int q0 = tile * tile_pts;
-  const int qn = min(n - q0, tile_pts);   // queries in this tile
+// ---------------------------------------------------------------------------------------------------------
+// One Gauss-Newton iteration = k_lm_knn (5-NN search: few registers, latency bound -> many resident warps)
+// + k_lm_resid (coefficients + 27-term reduction: many registers) + k_lm_solve.  The 5 neighbour positions of
+// every query cross through global memory (20 B per query).
+//
+// k_lm_knn exploits the temporal coherence of the iteration: between two iterations a query moves by
+// centimetres or less, so its 5 nearest neighbours almost never change.  Every real search also records the
+// SAFE RADIUS s of the query = a lower bound on the distance from the searched position q_ref to every map
+// point that is NOT one of the 5 neighbours (the 6th best candidate visited, and the bound of everything not
+// visited).  At the next iteration the query sits at q with |q - q_ref| = delta: by the triangle inequality
+// every non-neighbour is farther than s - delta, so if (s - delta)^2 exceeds the largest of the 5 re-evaluated
+// neighbour distances the old set IS the exact 5-NN set of q - proved, not assumed - and only its order is
+// refreshed (CHECK path: 5 gathers instead of ~25 candidates).  Queries that fail the test are searched again.
+// Results are bit-identical to searching every query from scratch (LISREG_KNN_NOSKIP=1 does exactly that;
+// tests/test_lm_parity.py compares the two).
+//
+// Work decomposition: a block owns a tile of tile_pts queries, each WARP a quarter of it, and nothing in the
+// tile loop synchronises the block.  A warp runs three dense phases, compacting the work of the next phase
+// into a shared-memory list with ballots so that the lanes stay busy:
+//   1. CHECK   every query of the sub-tile (coalesced state loads, 5 gathers)
+//   2. SCAN    queries that failed the check: flattened 3x3x3 block scan - the nine row streaks of a query are
+//              staged in shared memory and walked as ONE candidate list, so a warp iterates max(total) times
+//              instead of sum(max per row) times - with a one-candidate-ahead prefetch
+//   3. SHELLS  the few queries whose 5th neighbour may lie outside the block: full search with outer shells
+// ---------------------------------------------------------------------------------------------------------
+struct KnnState { float x, y, z, s; };   // searched position q_ref and safe radius (0 = none: search again)
 
-  // ---------------- phase A: 5-NN, 3x3x3 block ----------------
-  // Queries whose 5th neighbour may lie outside the block (sparse neighbourhoods, ~10 %) are DEFERRED to a
-  // list and finished in phase A2 with one lane per deferred query, so the rare long outer-shell walk runs
-  // on dense warps instead of stalling 31 idle lanes.
-  if (tid == 0) s_ndef = 0;
-  __syncthreads();
-  for (int l = tid; l < tile_pts; l += LM_THREADS) {
-    int accepted = 0, deferred = 0;
-    knn_key best[5];
-    if (l < qn) {
-      const int q = q0 + l;
-      const bool is_corner = q < sd.nc;
-      const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
-      // pointAssociateToMap (:243-258)
-      const float x0 = sT[0] * p.x + sT[1] * p.y + sT[2] * p.z + sT[3];
-      const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
-      const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
-      const GridDev& g = is_corner ? mp.corner : mp.surf;
-      int cx, cy, cz; float minf;
-      deferred = knn_grid_block<5>(g, x0, y0, z0, prm.gate, best, cx, cy, cz, minf) ? 1 : 0;
-      accepted = knn_key_d(best[4]) < prm.gate;
-    }
-    if (deferred) {
-      s_def[atomicAdd(&s_ndef, 1)] = (unsigned short)l;
-    } else if (accepted) {
-#pragma unroll
-      for (int j = 0; j < 5; j++) s_pos[j * LM_MAX_TILE + l] = knn_key_pos(best[j]);
-    } else {
-      s_pos[l] = -1;
-    }
-  }
-  __syncthreads();
-  // ---------------- phase A2: deferred queries, full search incl. outer shells ----------------
-  for (int d = tid; d < s_ndef; d += LM_THREADS) {
-    const int l = s_def[d];
-    const int q = q0 + l;
-    const bool is_corner = q < sd.nc;
-    const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
-    const float x0 = sT[0] * p.x + sT[1] * p.y + sT[2] * p.z + sT[3];
-    const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
-    const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
-    const GridDev& g = is_corner ? mp.corner : mp.surf;
-    knn_key best[5];
-    knn_grid<5>(g, x0, y0, z0, prm.gate, best);
-    if (knn_key_d(best[4]) < prm.gate) {
-#pragma unroll
-      for (int j = 0; j < 5; j++) s_pos[j * LM_MAX_TILE + l] = knn_key_pos(best[j]);
-    } else {
-      s_pos[l] = -1;
-    }
-  }
-  __syncthreads();
+#define KNN_INF __int_as_float(0x7f800000)   // +inf
 
-  // ---------------- phase B: coefficients + Jacobian rows ----------------
-  int cntC = 0, cntS = 0;
-  for (int l = tid; l < tile_pts; l += LM_THREADS) {
-    float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const int pos0 = s_pos[l];
-    if (pos0 >= 0) {
-      const int q = q0 + l;
-      const bool is_corner = q < sd.nc;
-      const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
-      const float x0 = sT[0] * p.x + sT[1] * p.y + sT[2] * p.z + sT[3];
-      const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
-      const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
-      const float4* __restrict__ pts = is_corner ? mp.corner.pts : mp.surf.pts;
-      float4 nb[5];
-      nb[0] = __ldg(&pts[pos0]);
+// candidates arrive in ascending position order (rows in ascending cell order, points ascending inside a
+// streak), so on equal distance the resident entry - smaller position - stays ahead: float compares suffice
+// for the lexicographic (d^2, position) order of the 64-bit keys used elsewhere
+__device__ __forceinline__ void knn6_insert_mono(float (&bd)[6], unsigned (&bp)[6], float d, unsigned p) {
 #pragma unroll
-      for (int j = 1; j < 5; j++) nb[j] = __ldg(&pts[s_pos[j * LM_MAX_TILE + l]]);
-      float raw[5];
-      const bool ok = is_corner ? corner_coeff(x0, y0, z0, nb, raw) : surf_coeff(x0, y0, z0, nb, raw);
-      if (ok) {
-        float w = 1.0f;
-        if (prm.use_w) {   // subMapOptmizationNode.cpp:1669, :1793
-          const uint16_t* lab = is_corner ? sd.clabel : sd.slabel;
-          unsigned lb = lab ? lab[is_corner ? q : q - sd.nc] : 0u;
-          float sc = lb < LISREG_LUT_SIZE ? prm.label_score[lb] : 0.f;
-          w = (float)(2.0 - (double)sc);
-        }
-        const float ws = w * raw[4];
-        const float c_x = ws * raw[0], c_y = ws * raw[1], c_z = ws * raw[2], c_i = ws * raw[3];
-        if (is_corner) cntC++; else cntS++;
-        // LMOptimization row (:888-915): lidar -> camera permutation
-        const float px = p.y, py = p.z, pz = p.x;
-        const float cx = c_y, cy = c_z, cz = c_x;
-        const float arx = (crx * sry * srz * px + crx * crz * sry * py - srx * sry * pz) * cx +
-                          (-srx * srz * px - crz * srx * py - crx * pz) * cy +
-                          (crx * cry * srz * px + crx * cry * crz * py - cry * srx * pz) * cz;
-        const float ary = ((cry * srx * srz - crz * sry) * px + (sry * srz + cry * crz * srx) * py + crx * cry * pz) * cx +
-                          ((-cry * crz - srx * sry * srz) * px + (cry * srz - crz * srx * sry) * py - crx * sry * pz) * cz;
-        const float arz = ((crz * srx * sry - cry * srz) * px + (-cry * crz - srx * sry * srz) * py) * cx +
-                          (crx * crz * px - crx * srz * py) * cy +
-                          ((sry * srz + cry * crz * srx) * px + (crz * sry - cry * srx * srz) * py) * cz;
-        row[0] = arz; row[1] = arx; row[2] = ary; row[3] = cz; row[4] = cx; row[5] = cy; row[6] = -c_i;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 7; k++) s_row[k * LM_MAX_TILE + l] = row[k];
-  }
-  __syncthreads();
-
-  // ---------------- phase C: 27 products, fp64 ----------------
-  {
-    int r, c;
-    lm_pair_of_lane(lane < 27 ? lane : 0, r, c);
-    const int per_warp = tile_pts / (LM_THREADS / 32);
-    const float* __restrict__ ra = s_row + r * LM_MAX_TILE + wid * per_warp;
-    const float* __restrict__ rc = s_row + c * LM_MAX_TILE + wid * per_warp;
-    double v = 0.0;
-    for (int i = 0; i < per_warp; i++) v += (double)ra[i] * (double)rc[i];
-    if (lane < 27) swarp[wid][lane] = v;
-    int cc = cntC, s2 = cntS;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { cc += __shfl_down_sync(0xffffffffu, cc, o); s2 += __shfl_down_sync(0xffffffffu, s2, o); }
-    if (lane == 0) { swarp[wid][27] = (double)cc; swarp[wid][28] = (double)s2; }
-  }
-  __syncthreads();
-  double* mypart = partials + ((size_t)b * max_tiles + tile) * LM_NSUM;
-  if (tid < 29) {
-    double v = 0.0;
-#pragma unroll
-    for (int w2 = 0; w2 < LM_THREADS / 32; w2++) v += swarp[w2][tid];
-    mypart[tid] = v;
-  }
-  __syncthreads();   // smem is reused by the next tile
+  for (int j = 0; j < 6; j++) {
+    const bool keep = bd[j] <= d;
+    const float lo_d = keep ? bd[j] : d; const unsigned lo_p = keep ? bp[j] : p;
+    d = keep ? d : bd[j]; p = keep ? p : bp[j];
+    bd[j] = lo_d; bp[j] = lo_p;
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Split variant of k_lm_iter: the 5-NN search (few registers, latency bound -> wants many resident warps) and
-// the coefficient / reduction phases (many registers) run as two kernels, the 5 neighbour positions of every
-// query crossing through global memory (20 B per query, negligible next to the candidate traffic).
-// Same arithmetic, same tile partial layout, same fixed summation order => bit-identical results.
-// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float knn_dist2(float qx, float qy, float qz, float4 m) {
+  const float dx = qx - m.x, dy = qy - m.y, dz = qz - m.z;
+  float d = dx * dx; d = d + dy * dy; d = d + dz * dz;   // FLANN L2 functor op order, no FMA
+  return d;
+}
+
+// flattened 3x3x3 block scan; rng = this thread's column of the shared range table (stride LM_THREADS).
+// Returns true when the outer shells are needed; lb = lower bound of everything outside the block.
+__device__ __forceinline__ bool knn6_block_flat(const GridDev& g, float qx, float qy, float qz, float gate,
+                                                float (&bd)[6], unsigned (&bp)[6], uint2* rng, float& lb) {
+#pragma unroll
+  for (int j = 0; j < 6; j++) { bd[j] = KNN_INF; bp[j] = 0xffffffffu; }
+  lb = KNN_INF;
+  if (g.n <= 0) return false;
+  const float fx = (qx - g.ox) * g.inv_h, fy = (qy - g.oy) * g.inv_h, fz = (qz - g.oz) * g.inv_h;
+  const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
+  const float rx = fx - (float)cx, ry = fy - (float)cy, rz = fz - (float)cz;
+  const float minf = fminf(fminf(fminf(rx, 1.f - rx), fminf(ry, 1.f - ry)), fminf(rz, 1.f - rz));
+  int nr = 0;
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
+    uint32_t b, e;
+    knn_row_range(g, cx - 1, cx + 1, cy + (r % 3) - 1, cz + (r / 3) - 1, b, e);
+    if (e > b) { rng[nr * LM_THREADS] = make_uint2(b, e); nr++; }
+  }
+  const float4* __restrict__ pts = g.pts;
+  if (nr > 0) {
+    uint2 r0 = rng[0];
+    uint32_t p = r0.x, e = r0.y;
+    int k = 1;
+    float4 cur = __ldg(&pts[p]);
+    bool have = true;
+    while (have) {
+      const unsigned pc = p;
+      p++;
+      if (p == e) {
+        if (k < nr) { const uint2 r = rng[k * LM_THREADS]; k++; p = r.x; e = r.y; }
+        else have = false;
+      }
+      float4 nxt = cur;
+      if (have) nxt = __ldg(&pts[p]);      // prefetch the next candidate while this one is processed
+      const float d = knn_dist2(qx, qy, qz, cur);
+      if (d < bd[5]) knn6_insert_mono(bd, bp, d, pc);
+      cur = nxt;
+    }
+  }
+  lb = knn_block_lb(g, minf);
+  const float lb2 = lb * lb;
+  return !(bd[4] < lb2 || lb2 >= gate);
+}
+
+// writes the result of a real search: neighbour positions (or -1 = rejected) and the refreshed state
+__device__ __forceinline__ void knn_commit(int* __restrict__ tnbr, KnnState* __restrict__ tstate, int tile_pts, int l,
+                                           float qx, float qy, float qz, float gate,
+                                           float d5, float d6, float lbu, const unsigned (&pos)[5]) {
+  KnnState st; st.x = qx; st.y = qy; st.z = qz; st.s = 0.f;
+  if (d5 < gate) {
+#pragma unroll
+    for (int j = 0; j < 5; j++) tnbr[j * tile_pts + l] = (int)pos[j];
+    // every non-neighbour is farther than min(6th best visited, bound of the unvisited); the factor absorbs the
+    // fp32 rounding of the distance evaluation and of the square root
+    st.s = fminf(sqrtf(d6), lbu) * 0.99999f;
+  } else {
+    tnbr[l] = -1;
+  }
+  tstate[l] = st;
+}
+
 #ifndef LM_KNN_MIN_BLOCKS
-#define LM_KNN_MIN_BLOCKS 12
+#define LM_KNN_MIN_BLOCKS 8
 #endif
 __global__ void __launch_bounds__(LM_THREADS, LM_KNN_MIN_BLOCKS)
 k_lm_knn(const RegDesc* __restrict__ descs, const RegState* __restrict__ states, const MapDev* __restrict__ maps,
-         float gate, int* __restrict__ nbr, int max_tiles, int tile_pts) {
-  const int b = blockIdx.y, tid = threadIdx.x;
+         float gate, int* __restrict__ nbr, KnnState* __restrict__ kstate, int max_tiles, int tile_pts, int use_state) {
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   __shared__ RegDesc sd;
   __shared__ float sT[12];
   __shared__ int sdone;
-  __shared__ unsigned short s_def[LM_MAX_TILE];
-  __shared__ int s_ndef;
+  __shared__ uint2 s_rng[9 * LM_THREADS];
+  __shared__ unsigned char s_scan[LM_THREADS / 32][LM_MAX_TILE / 4];
+  __shared__ unsigned char s_shell[LM_THREADS / 32][LM_MAX_TILE / 4];
   if (tid == 0) { sd = descs[b]; sd.nc = states[b].nc; sd.ns = states[b].ns; sdone = states[b].done; }
   if (tid < 12) sT[tid] = states[b].T[tid];
   __syncthreads();
@@ -430,39 +371,106 @@ k_lm_knn(const RegDesc* __restrict__ descs, const RegState* __restrict__ states,
   const int n = sd.nc + sd.ns;
   const int ntiles = (n + tile_pts - 1) / tile_pts;
   const MapDev& mp = maps[sd.map_slot];
+  const int sub = tile_pts / (LM_THREADS / 32);        // queries per warp per tile (32 or 128)
+  const unsigned lt_mask = (1u << lane) - 1u;
+  uint2* rng = s_rng + tid;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int q0 = tile * tile_pts;
     const int qn = min(n - q0, tile_pts);
-    int* tnbr = nbr + ((size_t)b * max_tiles + tile) * 5 * tile_pts;   // [5][tile_pts]
-    if (tid == 0) s_ndef = 0;
-    __syncthreads();
-    for (int l = tid; l < tile_pts; l += LM_THREADS) {
-      int accepted = 0, deferred = 0;
-      knn_key best[5];
+    int* tnbr = nbr + ((size_t)b * max_tiles + tile) * 5 * tile_pts;         // [5][tile_pts]
+    KnnState* tstate = kstate + ((size_t)b * max_tiles + tile) * tile_pts;   // [tile_pts]
+    const int l0 = wid * sub;
+    int n_scan = 0, n_shell = 0;
+    // ---------------- phase 1: CHECK ----------------
+    for (int o = 0; o < sub; o += 32) {
+      const int l = l0 + o + lane;
+      bool need = false;
       if (l < qn) {
+        need = true;
+        if (use_state) {
+          const float4 ref = __ldg(reinterpret_cast<const float4*>(&tstate[l]));
+          if (ref.w > 0.f) {
+            const int q = q0 + l;
+            const bool is_corner = q < sd.nc;
+            const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
+            const float x0 = sT[0] * p.x + sT[1] * p.y + sT[2] * p.z + sT[3];
+            const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
+            const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
+            const float mx = x0 - ref.x, my = y0 - ref.y, mz = z0 - ref.z;
+            const float delta = sqrtf(mx * mx + my * my + mz * mz) * 1.00001f + 1e-6f;   // upper bound of the move
+            const float r = ref.w - delta;
+            if (r > 0.f) {
+              const float4* __restrict__ pts = is_corner ? mp.corner.pts : mp.surf.pts;
+              int pos[5]; knn_key key[5];
+              float bmax = 0.f;
+#pragma unroll
+              for (int j = 0; j < 5; j++) pos[j] = tnbr[j * tile_pts + l];
+#pragma unroll
+              for (int j = 0; j < 5; j++) {
+                const float d = knn_dist2(x0, y0, z0, __ldg(&pts[pos[j]]));
+                bmax = fmaxf(bmax, d);
+                key[j] = ((knn_key)(unsigned)__float_as_int(d) << 32) | (knn_key)(unsigned)pos[j];
+              }
+              if (r * r * 0.99999f > bmax) {     // no other map point can be as close as the farthest neighbour
+                need = false;
+                if (bmax < gate) {
+                  // refresh the (d^2, position) order: 9-comparator network
+#define LISREG_CSWAP(i, j) { const knn_key a_ = key[i], b_ = key[j]; const bool sw_ = b_ < a_; key[i] = sw_ ? b_ : a_; key[j] = sw_ ? a_ : b_; }
+                  LISREG_CSWAP(0, 1) LISREG_CSWAP(3, 4) LISREG_CSWAP(2, 4) LISREG_CSWAP(2, 3) LISREG_CSWAP(1, 4)
+                  LISREG_CSWAP(0, 3) LISREG_CSWAP(0, 2) LISREG_CSWAP(1, 3) LISREG_CSWAP(1, 2)
+#undef LISREG_CSWAP
+                  bool changed = false;
+#pragma unroll
+                  for (int j = 0; j < 5; j++) changed |= knn_key_pos(key[j]) != pos[j];
+                  if (changed) {
+#pragma unroll
+                    for (int j = 0; j < 5; j++) tnbr[j * tile_pts + l] = knn_key_pos(key[j]);
+                  }
+                } else {                          // the 5th neighbour left the gate: rejected; search again next time
+                  tnbr[l] = -1;
+                  tstate[l].s = 0.f;
+                }
+              }
+            }
+          }
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, need);
+      if (need) s_scan[wid][n_scan + __popc(m & lt_mask)] = (unsigned char)(o + lane);
+      n_scan += __popc(m);
+    }
+    __syncwarp();
+    // ---------------- phase 2: SCAN ----------------
+    for (int base = 0; base < n_scan; base += 32) {
+      const int i = base + lane;
+      bool need_shell = false;
+      int ll = 0;
+      if (i < n_scan) {
+        ll = s_scan[wid][i];
+        const int l = l0 + ll;
         const int q = q0 + l;
         const bool is_corner = q < sd.nc;
         const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
+        // pointAssociateToMap (:243-258)
         const float x0 = sT[0] * p.x + sT[1] * p.y + sT[2] * p.z + sT[3];
         const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
         const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
         const GridDev& g = is_corner ? mp.corner : mp.surf;
-        int cx, cy, cz; float minf;
-        deferred = knn_grid_block<5>(g, x0, y0, z0, gate, best, cx, cy, cz, minf) ? 1 : 0;
-        accepted = knn_key_d(best[4]) < gate;
+        float bd[6]; unsigned bp[6]; float lb;
+        need_shell = knn6_block_flat(g, x0, y0, z0, gate, bd, bp, rng, lb);
+        if (!need_shell) {
+          const unsigned pos[5] = {bp[0], bp[1], bp[2], bp[3], bp[4]};
+          knn_commit(tnbr, tstate, tile_pts, l, x0, y0, z0, gate, bd[4], bd[5], lb, pos);
+        }
       }
-      if (deferred) {
-        s_def[atomicAdd(&s_ndef, 1)] = (unsigned short)l;
-      } else if (accepted) {
-#pragma unroll
-        for (int j = 0; j < 5; j++) tnbr[j * tile_pts + l] = knn_key_pos(best[j]);
-      } else {
-        tnbr[l] = -1;
-      }
+      const unsigned m = __ballot_sync(0xffffffffu, need_shell);
+      if (need_shell) s_shell[wid][n_shell + __popc(m & lt_mask)] = (unsigned char)ll;
+      n_shell += __popc(m);
     }
-    __syncthreads();
-    for (int d = tid; d < s_ndef; d += LM_THREADS) {
-      const int l = s_def[d];
+    __syncwarp();
+    // ---------------- phase 3: SHELLS ----------------
+    for (int i = lane; i < n_shell; i += 32) {
+      const int l = l0 + s_shell[wid][i];
       const int q = q0 + l;
       const bool is_corner = q < sd.nc;
       const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
@@ -470,16 +478,13 @@ k_lm_knn(const RegDesc* __restrict__ descs, const RegState* __restrict__ states,
       const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
       const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
       const GridDev& g = is_corner ? mp.corner : mp.surf;
-      knn_key best[5];
-      knn_grid<5>(g, x0, y0, z0, gate, best);
-      if (knn_key_d(best[4]) < gate) {
-#pragma unroll
-        for (int j = 0; j < 5; j++) tnbr[j * tile_pts + l] = knn_key_pos(best[j]);
-      } else {
-        tnbr[l] = -1;
-      }
+      knn_key best[6];
+      const float lbu = knn_grid_tracked<6, 4>(g, x0, y0, z0, gate, best);
+      const unsigned pos[5] = {(unsigned)knn_key_pos(best[0]), (unsigned)knn_key_pos(best[1]), (unsigned)knn_key_pos(best[2]),
+                               (unsigned)knn_key_pos(best[3]), (unsigned)knn_key_pos(best[4])};
+      knn_commit(tnbr, tstate, tile_pts, l, x0, y0, z0, gate, knn_key_d(best[4]), knn_key_d(best[5]), lbu, pos);
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -580,7 +585,7 @@ k_lm_resid(const RegDesc* __restrict__ descs, const RegState* __restrict__ state
 
 // LMOptimization tail: one warp per registration sums the tile partials in tile order (fixed
 // order => bit-reproducible) and lane 0 runs the 6x6 solve / degeneracy / pose update.
-// Kept out of k_lm_iter so that the hot kernel has no large stack frame or cold code.
+// Kept out of k_lm_resid so that the hot kernel has no large stack frame or cold code.
 constexpr int LM_SOLVE_THREADS = 128;
 __global__ void __launch_bounds__(LM_SOLVE_THREADS)
 k_lm_solve(const RegDesc* __restrict__ descs, RegState* __restrict__ states, LmParamsDev prm,
@@ -633,20 +638,27 @@ __global__ void k_selftest_smallmat(const float* __restrict__ A36, const float* 
   for (int i = 0; i < 9; i++) out[89 + i] = V3[i];
 }
 
-// stand-alone exact 5-NN (tests / lisreg_knn5)
-__global__ void k_knn5(GridDev g, const float4* __restrict__ q, int nq, float gate, int* __restrict__ idx, float* __restrict__ sqd) {
+// stand-alone exact 5-NN (tests / lisreg_knn5): the same flattened block scan + tracked shells as k_lm_knn.
+// safe (nullable, nq): the safe radius k_lm_knn would record for the query.
+__global__ void __launch_bounds__(LM_THREADS)
+k_knn5(GridDev g, const float4* __restrict__ q, int nq, float gate, int* __restrict__ idx, float* __restrict__ sqd, float* __restrict__ safe) {
+  __shared__ uint2 s_rng[9 * LM_THREADS];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   float4 p = q[i];
-  knn_key best[5];
-  knn5_grid(g, p.x, p.y, p.z, gate, best);
-  for (int j = 0; j < 5; j++) {
-    const float d = knn_key_d(best[j]);
-    const int pos = knn_key_pos(best[j]);
-    const bool ok = pos >= 0 && d < gate;
-    idx[5 * i + j] = ok ? __float_as_int(g.pts[pos].w) : -1;
-    sqd[5 * i + j] = ok ? d : FLT_MAX;
+  float bd[6]; unsigned bp[6]; float lb;
+  if (knn6_block_flat(g, p.x, p.y, p.z, gate, bd, bp, s_rng + threadIdx.x, lb)) {
+    knn_key best[6];
+    lb = knn_grid_tracked<6, 4>(g, p.x, p.y, p.z, gate, best);
+#pragma unroll
+    for (int j = 0; j < 6; j++) { bd[j] = knn_key_d(best[j]); bp[j] = (unsigned)knn_key_pos(best[j]); }
   }
+  for (int j = 0; j < 5; j++) {
+    const bool ok = bp[j] != 0xffffffffu && bd[j] < gate;
+    idx[5 * i + j] = ok ? __float_as_int(g.pts[bp[j]].w) : -1;
+    sqd[5 * i + j] = ok ? bd[j] : FLT_MAX;
+  }
+  if (safe) safe[i] = bd[4] < gate ? fminf(sqrtf(bd[5]), lb) * 0.99999f : 0.f;
 }
 
 }  // namespace lisreg

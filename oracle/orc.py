@@ -134,6 +134,14 @@ def lib():
         L.orc_epsc_score_all.argtypes = [u8p, C.c_int32, C.c_int32, ip, fp, C.POINTER(C.c_int8), C.c_int32]
         L.orc_icp.restype = C.c_int
         L.orc_icp.argtypes = [fp, C.c_int32, fp, C.c_int32, C.POINTER(IcpParams), C.POINTER(IcpResult)]
+        L.orc_loop_create.restype = C.c_void_p
+        L.orc_loop_create.argtypes = [u8p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+        L.orc_loop_free.argtypes = [C.c_void_p]
+        L.orc_loop_detect.restype = C.c_int32
+        L.orc_loop_detect.argtypes = [C.c_void_p, fp, C.c_int32, fp, C.c_int32, fp, u16p, C.c_int32, fp, ip, ip, ip, ip,
+                                      C.POINTER(C.c_double), fp]
+        L.orc_loop_project.argtypes = [fp, u16p, C.c_int32, fp]
+        L.orc_loop_global_icp.argtypes = [fp, fp, C.c_float, fp]
         _LIB = L
     return _LIB
 
@@ -300,3 +308,48 @@ def icp(src4, tgt4, prm=None):
     res = IcpResult()
     lib().orc_icp(sp, len(s), tp, len(t), C.byref(prm), C.byref(res))
     return np.array(res.T, np.float32).reshape(4, 4), res
+
+
+
+LOOP_KINDS = ("epsc", "sepsc", "fepsc", "pose")
+
+
+class LoopDetector:
+    """EPSCGeneration::loopDetection (epscGeneration.cpp:663-992): stateful, append-only."""
+
+    def __init__(self, use_epsc=False, use_sepsc=False, use_fepsc=True, use_pose=False, lut=None):
+        lut = using_map_lut() if lut is None else np.ascontiguousarray(lut, np.uint8)
+        self._h = lib().orc_loop_create(lut.ctypes.data_as(C.POINTER(C.c_uint8)), int(use_epsc), int(use_sepsc), int(use_fepsc), int(use_pose))
+
+    def detect(self, corner4, surf4, sem4, sem_label, odom):
+        """Returns (current_frame_id, n_candidates, [(kind, matched_id, score, T 4x4)])."""
+        c, cp = _f(corner4); s, sp = _f(surf4); m, mp = _f(sem4)
+        lab = np.ascontiguousarray(sem_label, np.uint16)
+        od = np.ascontiguousarray(odom, np.float32).reshape(16)
+        cur, ncand = C.c_int32(0), C.c_int32(0)
+        kinds = np.zeros(4, np.int32); ids = np.zeros(4, np.int32); scores = np.zeros(4, np.float64); T = np.zeros((4, 16), np.float32)
+        ip = C.POINTER(C.c_int32)
+        n = lib().orc_loop_detect(self._h, cp, len(c), sp, len(s), mp, lab.ctypes.data_as(C.POINTER(C.c_uint16)), len(m),
+                                  od.ctypes.data_as(C.POINTER(C.c_float)), C.byref(cur), C.byref(ncand), kinds.ctypes.data_as(ip),
+                                  ids.ctypes.data_as(ip), scores.ctypes.data_as(C.POINTER(C.c_double)), T.ctypes.data_as(C.POINTER(C.c_float)))
+        return cur.value, ncand.value, [(LOOP_KINDS[kinds[i]], int(ids[i]), float(scores[i]), T[i].reshape(4, 4).copy()) for i in range(n)]
+
+    def close(self):
+        if self._h:
+            lib().orc_loop_free(self._h); self._h = None
+
+
+def loop_project(sem4, sem_label):
+    m, mp = _f(sem4)
+    lab = np.ascontiguousarray(sem_label, np.uint16)
+    out = np.zeros((360, 4), np.float32)
+    lib().orc_loop_project(mp, lab.ctypes.data_as(C.POINTER(C.c_uint16)), len(m), out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
+def loop_global_icp(proj1, proj2, yaw_diff):
+    a = np.ascontiguousarray(proj1, np.float32); b = np.ascontiguousarray(proj2, np.float32)
+    T = np.zeros(16, np.float32)
+    fp = C.POINTER(C.c_float)
+    lib().orc_loop_global_icp(a.ctypes.data_as(fp), b.ctypes.data_as(fp), float(yaw_diff), T.ctypes.data_as(fp))
+    return T.reshape(4, 4)

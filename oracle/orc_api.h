@@ -102,6 +102,15 @@ typedef struct orc_icp_params { float max_corr_dist; int32_t max_iters; double t
 typedef struct orc_icp_result { float T[16]; double fitness; int32_t converged, iters, n_corr_last, pad; } orc_icp_result;
 int orc_icp(const float* src4, int32_t ns, const float* tgt4, int32_t nt, const orc_icp_params* prm, orc_icp_result* res);
 
+/* ---- EPSC loop detector (epscGeneration.cpp:84-120 project, :258-401 globalICP, :663-992 loopDetection) ---- */
+void* orc_loop_create(const uint8_t* using_map, int32_t use_epsc, int32_t use_sepsc, int32_t use_fepsc, int32_t use_pose);
+void orc_loop_free(void* h);
+int32_t orc_loop_detect(void* h, const float* corner4, int32_t nc, const float* surf4, int32_t ns,
+                        const float* sem4, const uint16_t* sem_label, int32_t nsem, const float* odom16,
+                        int32_t* current_id, int32_t* n_cand, int32_t* kinds, int32_t* ids, double* scores, float* T16s);
+void orc_loop_project(const float* sem4, const uint16_t* label, int32_t n, float* out1440);
+void orc_loop_global_icp(const float* proj1, const float* proj2, float yaw_diff, float* T16);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,3 +67,27 @@ def test_frames_fixed_iterations_and_ragged_batch(engine):
     er, et = synth.pose_error(po, poses[1]); assert er <= 1e-4 and et <= 1e-3
     assert res[2].status == E.NOT_ENOUGH_FEATURES and np.array_equal(poses[2], np.asarray(g0, np.float32))
     engine.map_destroy(mid)
+
+
+def test_chunked_e2e_pipeline_is_bit_identical(monkeypatch):
+    """The arena entry point uploads the sweeps in chunks on a copy stream and starts each chunk's pipeline as soon
+    as its bytes have landed; the chunking must not change a single bit of the result (ragged + empty frames incl.)."""
+    m = local_map()
+    s0, _, g0 = frame(0)
+    s1, _, g1 = frame(1)
+    third = {"pts": s1["pts"][: len(s1["pts"]) // 3], "ring": s1["ring"][: len(s1["pts"]) // 3]}
+    empty = {"pts": np.zeros((0, 4), np.float32), "ring": np.zeros(0, np.uint16)}
+    sweeps = [s0, third, empty, s1, s0]
+    guesses = [g0, g1, g0, g1, g1]
+    prm = E.frame_params("A", early_exit=0, max_iters=6)
+    out = {}
+    for chunk in ("0", "2"):
+        monkeypatch.setenv("LISREG_E2E_CHUNK", chunk)
+        eng = E.Engine(device=0)
+        mid = eng.map_create(m["corner"], m["surf"], gate_hint=1.0)
+        poses, res = eng.frames_batch([(mid, s["pts"], s["ring"]) for s in sweeps], guesses, prm)
+        out[chunk] = (poses.copy(), [(r.status, r.iters, r.n_corner, r.n_surf, r.n_sel_last) for r in res])
+        eng.close()
+    assert np.array_equal(out["0"][0], out["2"][0])
+    assert out["0"][1] == out["2"][1]
+    assert out["0"][1][2][0] == E.NOT_ENOUGH_FEATURES

@@ -182,3 +182,30 @@ def test_degenerate_corridor_quirk_q1(engine):
     assert np.array(log_g[1].X).tolist() == [0.0] * 6
     er, et = synth.pose_error(pose_o, pose_g)
     assert er <= ROT_TOL and et <= TRANS_TOL
+
+
+@pytest.mark.parametrize("variant", ["A", "B"])
+def test_knn_check_path_is_bit_identical_to_full_search(monkeypatch, variant):
+    """k_lm_knn re-uses the previous iteration's neighbours when it can PROVE (safe radius vs movement) that they
+    are still the exact 5-NN; LISREG_KNN_NOSKIP=1 searches every query from scratch.  Every per-iteration record
+    (selection counts, A^T A, A^T b, step, pose) must be identical bit for bit, single and batched."""
+    m = local_map()
+    cases = [reg_case(s) for s in (0, 1, 2)]
+    prm = E.lm_params(variant, early_exit=0, max_iters=8)
+    logs = {}
+    for noskip in ("1", "0"):
+        monkeypatch.setenv("LISREG_KNN_NOSKIP", noskip)
+        eng = E.Engine(device=0)
+        mid = eng.map_create(m["corner"], m["surf"], gate_hint=2.0 if variant == "B" else 1.0)
+        out = []
+        for f, truth, guess in cases:
+            pose, res, log = eng.scan2map(mid, f["corner"], f["surf"], guess, prm, clabel=f["corner_label"], slabel=f["surf_label"], log=True)
+            out.append((pose.tobytes(), res.iters, res.n_sel_last,
+                        [(bytes(bytearray(L.AtA)), bytes(bytearray(L.AtB)), bytes(bytearray(L.pose)), L.n_corner_sel, L.n_surf_sel) for L in log]))
+        # the batched path tiles differently (512-query tiles): compare it with itself across the two modes
+        items = [(mid, f["corner"], f["surf"], f["corner_label"], f["surf_label"]) for f, _, _ in cases] * 12
+        poses, res, _ = eng.scan2map_batch(items, [g for _, _, g in cases] * 12, prm)
+        out.append((np.asarray(poses).tobytes(), [r.n_sel_last for r in res]))
+        logs[noskip] = out
+        eng.close()
+    assert logs["0"] == logs["1"]
