@@ -8,8 +8,8 @@
 // range-image cell), F2 one block per ring (block prefix sum) after a 64-entry ring scan, F3/F4
 // point-parallel (F4's writes are idempotent ORs), F5 one WARP per (frame, ring): its six segments are
 // processed in order because the +-5 neighbour suppression of a pick crosses segment borders; inside a
-// segment the warp bitonic-sorts (curvature, index) keys in shared memory and lane 0 runs the two
-// greedy passes (the non-maximum suppression is order-dependent, hence sequential).
+// segment the sort + greedy walk of the reference is restated as a warp-wide selection loop over the
+// picks (see k_feat_segments).
 // Documented deviations from reference UB are listed in oracle/orc_features.cpp (Q3, Q5, sort ties,
 // index -1 read): the device follows the same resolutions.
 #pragma once
@@ -167,45 +167,52 @@ __global__ void k_feat_occlusion(FeatFrame* frames) {
 }
 
 // ---- F5 ----
-constexpr int FEAT_HI_MAX = 128;        // edge candidates (curvature > edgeThreshold) of one segment (power of two)
-constexpr int FEAT_LO_MAX = 512;        // flat candidates (curvature < surfThreshold) of one segment (power of two)
-constexpr int FEAT_SEG_MAX = FEAT_HI_MAX + FEAT_LO_MAX;   // key slots per warp in shared memory
-constexpr int FEAT_WARPS = 4;           // rings per block
+constexpr int FEAT_WARPS = 4;            // rings per block
 constexpr int FEAT_RING_MAX = 2048 + 16; // staged ring window (horizon <= 2048, +-6 apron)
+constexpr int FEAT_CH = 12;              // segment elements per lane: a segment holds <= 32 * 12 points (horizon <= 2048 -> <= 341)
 
-// Neighbour suppression of a pick (:648-661) on the ring window staged in shared memory.
-// lo = global index of window slot 0; indices outside [0, M) or outside the window end the walk
-// (the window covers [first-6, last+6] of the ring, the only indices a pick of this ring can reach).
-__device__ __forceinline__ void feat_mark_neighbours(unsigned char* spick, const unsigned short* scol, int lo, int wlen, int ind, int M) {
+// Neighbour suppression of a pick (:648-661) on the ring window staged in shared memory; executed by the whole
+// warp on the same `ind` (uniform).  lo = global index of window slot 0; indices outside [0, M) or outside the
+// window end the walk (the window covers [first-6, last+6] of the ring, the only indices a pick of this ring can
+// reach).  Returns the marked index range [a0, b0].
+__device__ __forceinline__ void feat_mark_range(const unsigned short* scol, int lo, int wlen, int ind, int M, int& a0, int& b0) {
+  int rr = 0, rl = 0;
   for (int l = 1; l <= 5; l++) {
     const int a = ind + l, b = ind + l - 1;
-    if (a < 0 || a >= M || b < 0 || b >= M || a - lo >= wlen || b - lo < 0) break;
+    if (a >= M || a - lo >= wlen || b - lo < 0) break;
     if (abs((int)scol[a - lo] - (int)scol[b - lo]) > 10) break;
-    spick[a - lo] = 1;
+    rr = l;
   }
-  for (int l = -1; l >= -5; l--) {
-    const int a = ind + l, b = ind + l + 1;
-    if (a < 0 || a >= M || b < 0 || b >= M || a - lo < 0 || b - lo >= wlen) break;
+  for (int l = 1; l <= 5; l++) {
+    const int a = ind - l, b = ind - l + 1;
+    if (a < 0 || a - lo < 0 || b - lo >= wlen) break;
     if (abs((int)scol[a - lo] - (int)scol[b - lo]) > 10) break;
-    spick[a - lo] = 1;
+    rl = l;
   }
+  a0 = ind - rl; b0 = ind + rr;
 }
 
 // one warp per (frame, ring).  grid = (ceil(n_scan / FEAT_WARPS), F), block = 32 * FEAT_WARPS.
-// The ring's picked flags and column indices are staged in shared memory so that the sequential greedy
-// passes of lane 0 never wait on global memory; curvature comes from the sorted key itself.
+//
+// The reference sorts every segment by curvature and walks it twice, picking a point when it has not been
+// suppressed yet and suppressing its +-5 neighbours (order-dependent greedy non-maximum suppression).  Only the
+// PICKS change state, so the walk is restated as a selection loop: "take the best not-yet-suppressed candidate,
+// pick it, suppress its neighbours", which visits exactly the same picks in exactly the same order without ever
+// sorting.  The segment lives in registers (element sp + 32 t + lane in slot t of a lane, an alive bit per slot);
+// one step = per-lane best of the alive slots, two warp reductions (redux.sync) for the winning (curvature,
+// index) key, a uniform walk for the suppression range, and an O(1) alive-mask update per lane.  ~40 steps per
+// segment instead of a 512-key bitonic sort plus a 300-element sequential walk by one lane.
 __global__ void __launch_bounds__(32 * FEAT_WARPS)
 k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
   const FeatFrame f = frames[blockIdx.y];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int ring = blockIdx.x * FEAT_WARPS + wid;
-  __shared__ unsigned long long s_key[FEAT_WARPS][FEAT_SEG_MAX];
   __shared__ unsigned char s_pick[FEAT_WARPS][FEAT_RING_MAX];
   __shared__ unsigned short s_col[FEAT_WARPS][FEAT_RING_MAX];
   if (ring >= prm.n_scan) return;
+  const unsigned FULL = 0xffffffffu;
   const int M = *f.M;
   const int start = f.ring_start[ring], end = f.ring_end[ring];
-  unsigned long long* key = s_key[wid];
   unsigned char* spick = s_pick[wid];
   unsigned short* scol = s_col[wid];
   // ring = extracted indices [first, last] with first = start - 4, last = end + 5; window adds a +-6 apron
@@ -220,116 +227,65 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
     const int ep = (start * (5 - j) + end * (j + 1)) / 6 - 1;
     if (lane == 0) { f.seg_sp[seg] = sp; f.seg_ep[seg] = ep; f.seg_valid[seg] = (sp < ep) ? 1 : 0; f.seg_ncorner[seg] = 0; f.seg_nflat[seg] = 0; }
     if (sp >= ep) continue;
-    const int len = ep - sp;            // sorted range [sp, ep); element ep stays in place (Q3)
-    // Only elements that can ever be picked need ordering: curvature > edge_thr (pass 1, descending) and
-    // curvature < surf_thr (pass 2, ascending); the band in between is never visited with effect.  Both
-    // candidate sets are compacted (warp ballot) into the two halves of the key buffer and bitonic-sorted
-    // separately: keys = curvature bits << 32 | index (curvature >= 0 => integer order == (value, index)).
-    unsigned long long* khi = key;                   // [0, FEAT_HI_MAX)
-    unsigned long long* klo = key + FEAT_HI_MAX;     // [FEAT_HI_MAX, FEAT_SEG_MAX)
-    int nhi = 0, nlo = 0;
-    for (int base = 0; base < len; base += 32) {
-      const int t = base + lane;
-      float cv = 0.f; bool ishi = false, islo = false;
-      if (t < len) { cv = f.curv[sp + t]; ishi = cv > prm.edge_thr; islo = cv < prm.surf_thr; }
-      const unsigned mh = __ballot_sync(0xffffffffu, ishi), ml = __ballot_sync(0xffffffffu, islo);
-      const unsigned long long kk = ((unsigned long long)__float_as_uint(cv) << 32) | (unsigned)(sp + t);
-      if (ishi) { const int o = nhi + __popc(mh & ((1u << lane) - 1u)); if (o < FEAT_HI_MAX) khi[o] = kk; }
-      if (islo) { const int o = nlo + __popc(ml & ((1u << lane) - 1u)); if (o < FEAT_LO_MAX) klo[o] = kk; }
-      nhi += __popc(mh); nlo += __popc(ml);
+    if (ep - sp + 1 > 32 * FEAT_CH) continue;   // unreachable for horizon <= 2048 (checked by the host entry points)
+    // elements sp .. ep (ep is NOT part of the reference's sorted range but is visited first in pass 1 and last
+    // in pass 2, quirk Q3): slot t of this lane = sp + 32 t + lane
+    float cv[FEAT_CH];
+#pragma unroll
+    for (int t = 0; t < FEAT_CH; t++) { const int idx = sp + 32 * t + lane; cv[t] = idx <= ep ? f.curv[idx] : 0.f; }
+    // ---------------- pass 1: edges, largest curvature first (:633-663) ----------------
+    unsigned alive = 0u;
+#pragma unroll
+    for (int t = 0; t < FEAT_CH; t++) { const int idx = sp + 32 * t + lane; if (idx <= ep && cv[t] > prm.edge_thr && spick[idx - lo] == 0) alive |= 1u << t; }
+    int nc = 0;
+    for (;;) {
+      // per-lane best: key = (curvature bits + 1, index), ep outranks everything; 0 = no candidate.  Slots of a lane
+      // have ascending indices, so ">=" keeps the larger index on equal curvature (descending walk of an
+      // ascending (value, index) order)
+      unsigned bh = 0u, bl = 0u;
+#pragma unroll
+      for (int t = 0; t < FEAT_CH; t++) if (alive >> t & 1u) {
+        const int idx = sp + 32 * t + lane;
+        const unsigned h = idx == ep ? 0xffffffffu : __float_as_uint(cv[t]) + 1u;
+        if (h >= bh) { bh = h; bl = (unsigned)idx; }
+      }
+      const unsigned mh = __reduce_max_sync(FULL, bh);
+      if (mh == 0u) break;
+      const int ind = (int)__reduce_max_sync(FULL, bh == mh ? bl : 0u);
+      if (nc == 20) break;                       // the 21st pick ends the pass without being marked (:640-645)
+      if (lane == 0) { f.label[ind] = 1; f.seg_corner[seg * 20 + nc] = ind; }
+      nc++;
+      int a0, b0;
+      feat_mark_range(scol, lo, wlen, ind, M, a0, b0);
+      if (lane <= b0 - a0) spick[a0 + lane - lo] = 1;
+      { const int o = a0 - sp - lane; const int t0 = o <= 0 ? 0 : (o + 31) >> 5; if (t0 < FEAT_CH && sp + 32 * t0 + lane <= b0) alive &= ~(1u << t0); }
     }
-    // mode 0: split candidate lists (common); mode 1: too many edge candidates -> sort the whole segment in
-    // shared memory (both passes then walk the same array and stop at their threshold); mode 2: oversize
-    // segment (never for <= 2048 columns / 6) -> slow insertion sort by lane 0 in global scratch.
-    int npad_full = 1; while (npad_full < len) npad_full <<= 1;
-    const int mode = (nhi <= FEAT_HI_MAX && nlo <= FEAT_LO_MAX) ? 0 : (npad_full <= FEAT_SEG_MAX ? 1 : 2);
-    if (mode == 1) {
-      __syncwarp();
-      for (int t = lane; t < npad_full; t += 32) {
-        const int i = sp + t;
-        key[t] = t < len ? (((unsigned long long)__float_as_uint(f.curv[i]) << 32) | (unsigned)i) : ~0ull;
+    __syncwarp();
+    // ---------------- pass 2: flat points, smallest curvature first (:665-694) ----------------
+    alive = 0u;
+#pragma unroll
+    for (int t = 0; t < FEAT_CH; t++) { const int idx = sp + 32 * t + lane; if (idx <= ep && cv[t] < prm.surf_thr && spick[idx - lo] == 0) alive |= 1u << t; }
+    int nf = 0;
+    for (;;) {
+      // key = (curvature bits, index) ascending, ep is visited last; 0xffffffff = no candidate
+      unsigned bh = 0xffffffffu, bl = 0xffffffffu;
+#pragma unroll
+      for (int t = 0; t < FEAT_CH; t++) if (alive >> t & 1u) {
+        const int idx = sp + 32 * t + lane;
+        const unsigned h = idx == ep ? 0xfffffffeu : __float_as_uint(cv[t]);
+        if (h < bh) { bh = h; bl = (unsigned)idx; }
       }
+      const unsigned mh = __reduce_min_sync(FULL, bh);
+      if (mh == 0xffffffffu) break;
+      const int ind = (int)__reduce_min_sync(FULL, bh == mh ? bl : 0xffffffffu);
+      if (lane == 0) { f.label[ind] = -1; if (nf < 10) f.seg_flat[seg * 10 + nf] = ind; }
+      if (nf < 10) nf++;
+      int a0, b0;
+      feat_mark_range(scol, lo, wlen, ind, M, a0, b0);
+      if (lane <= b0 - a0) spick[a0 + lane - lo] = 1;
+      { const int o = a0 - sp - lane; const int t0 = o <= 0 ? 0 : (o + 31) >> 5; if (t0 < FEAT_CH && sp + 32 * t0 + lane <= b0) alive &= ~(1u << t0); }
     }
-    if (mode <= 1) {
-      for (int pass = 0; pass < (mode == 0 ? 2 : 1); pass++) {
-        unsigned long long* kb = mode == 1 ? key : (pass == 0 ? khi : klo);
-        const int cnt = mode == 1 ? len : (pass == 0 ? nhi : nlo);
-        int npad = 1; while (npad < cnt) npad <<= 1;
-        if (mode == 0) for (int t = cnt + lane; t < npad; t += 32) kb[t] = ~0ull;
-        __syncwarp();
-        for (int k = 2; k <= npad; k <<= 1)
-          for (int jj = k >> 1; jj > 0; jj >>= 1) {
-            for (int t = lane; t < npad; t += 32) {
-              const int ixj = t ^ jj;
-              if (ixj > t) {
-                const unsigned long long a = kb[t], bq = kb[ixj];
-                const bool up = (t & k) == 0;
-                if ((a > bq) == up) { kb[t] = bq; kb[ixj] = a; }
-              }
-            }
-            __syncwarp();
-          }
-      }
-    } else {
-      if (lane == 0) {
-        int* o = f.owner + ring * prm.horizon;      // owner[] is free after compaction
-        for (int t = 0; t < len; t++) o[t] = sp + t;
-        for (int a = 1; a < len; a++) {
-          const int v = o[a]; const float cv = f.curv[v]; int bb = a;
-          while (bb > 0 && (f.curv[o[bb - 1]] > cv || (f.curv[o[bb - 1]] == cv && o[bb - 1] > v))) { o[bb] = o[bb - 1]; bb--; }
-          o[bb] = v;
-        }
-      }
-      __syncwarp();
-    }
-    // ---- greedy passes by lane 0 (order-dependent non-maximum suppression) ----
-    if (lane == 0) {
-      const int* o = f.owner + ring * prm.horizon;
-      const unsigned long long* l1 = mode == 0 ? khi : key;   // pass-1 list (ascending; walked from the top)
-      const unsigned long long* l2 = mode == 0 ? klo : key;   // pass-2 list (ascending; walked from the bottom)
-      const int n1 = mode == 0 ? nhi : len, n2 = mode == 0 ? nlo : len;
-      const float cv_ep = f.curv[ep];
-      int largestPickedNum = 0, nc = 0;
-      // pass 1: k = ep first, then the sorted candidates from the largest curvature down
-      for (int k = n1; k >= 0; k--) {
-        int ind; float cv;
-        if (k == n1) { ind = ep; cv = cv_ep; }
-        else {
-          if (mode <= 1) { const unsigned long long kk = l1[k]; ind = (int)(unsigned)(kk & 0xffffffffull); cv = __uint_as_float((unsigned)(kk >> 32)); }
-          else { ind = o[k]; cv = f.curv[ind]; }
-          if (!(cv > prm.edge_thr)) break;   // ascending order: nothing below can qualify
-        }
-        if (spick[ind - lo] == 0 && cv > prm.edge_thr) {
-          largestPickedNum++;
-          if (largestPickedNum <= 20) {
-            f.label[ind] = 1;
-            f.seg_corner[seg * 20 + nc] = ind; nc++;
-          } else break;
-          spick[ind - lo] = 1;
-          feat_mark_neighbours(spick, scol, lo, wlen, ind, M);
-        }
-      }
-      f.seg_ncorner[seg] = nc;
-      largestPickedNum = 0; int nf = 0;
-      // pass 2: the sorted candidates from the smallest curvature up, then k = ep
-      for (int k = 0; k <= n2; k++) {
-        int ind; float cv;
-        if (k == n2) { ind = ep; cv = cv_ep; }
-        else {
-          if (mode <= 1) { const unsigned long long kk = l2[k]; ind = (int)(unsigned)(kk & 0xffffffffull); cv = __uint_as_float((unsigned)(kk >> 32)); }
-          else { ind = o[k]; cv = f.curv[ind]; }
-          if (!(cv < prm.surf_thr)) { k = n2 - 1; continue; }   // nothing above can qualify: jump to the unsorted element ep
-        }
-        if (spick[ind - lo] == 0 && cv < prm.surf_thr) {
-          largestPickedNum++;
-          f.label[ind] = -1;
-          spick[ind - lo] = 1;
-          if (largestPickedNum <= 10) { f.seg_flat[seg * 10 + nf] = ind; nf++; }
-          feat_mark_neighbours(spick, scol, lo, wlen, ind, M);
-        }
-      }
-      f.seg_nflat[seg] = nf;
-    }
+    if (lane == 0) { f.seg_ncorner[seg] = nc; f.seg_nflat[seg] = nf; }
     __syncwarp();
   }
 }

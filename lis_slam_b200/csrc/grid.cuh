@@ -196,6 +196,71 @@ LISREG_HD __forceinline__ float knn_grid_tracked(const GridDev& g, float qx, flo
   return g.n > 0 ? knn_block_lb(g, minf) : FLT_MAX;
 }
 
+// Ball walk: exact KD+1 nearest neighbours (plus K-KD-1 runners-up among the visited points, +inf sentinel) for
+// queries in sparse neighbourhoods.  Visits the Chebyshev shells t = 0, 1, 2, ... around the query's cell, but
+// inside a shell only the rows - and inside a row only the cells - whose distance to the query is within the
+// pruning radius Rp = sqrt(min(d2(best[KD]), gate)) + pad, which shrinks as the result improves.  Every point
+// NOT visited is therefore farther than the returned radius (>= sqrt(d2 of the KD-th result) + pad when found
+// inside the gate): the caller gets an exact result and a proof margin of `pad` metres around it.
+// eps (in cells) absorbs the fp32 rounding of the cell assignment.
+template <int K, int KD>
+LISREG_HD __noinline__ float knn_ball_walk(const GridDev& g, float qx, float qy, float qz, float gate, float pad, knn_key (&best)[K]) {
+  const knn_key sentinel = ((knn_key)0x7f800000u << 32) | 0xffffffffull;
+#pragma unroll
+  for (int j = 0; j < K; j++) best[j] = sentinel;
+  if (g.n <= 0) return FLT_MAX;
+  const float eps = 1e-3f;
+  const float fx = (qx - g.ox) * g.inv_h, fy = (qy - g.oy) * g.inv_h, fz = (qz - g.oz) * g.inv_h;
+  const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
+  const float rx = fx - (float)cx, ry = fy - (float)cy, rz = fz - (float)cz;
+  const float minf = fminf(fminf(fminf(rx, 1.f - rx), fminf(ry, 1.f - ry)), fminf(rz, 1.f - rz));
+  int reach = cx > g.nx - 1 - cx ? cx : g.nx - 1 - cx;
+  reach = reach > cy ? reach : cy; reach = reach > g.ny - 1 - cy ? reach : g.ny - 1 - cy;
+  reach = reach > cz ? reach : cz; reach = reach > g.nz - 1 - cz ? reach : g.nz - 1 - cz;
+  const float sg = sqrtf(gate);
+  float Rp = sg + pad;
+  for (int t = 0; t <= reach; t++) {
+    if (t >= 1 && ((float)(t - 1) + minf - eps) * g.h > Rp) break;   // the whole shell is out of reach
+    const int za = cz - t > 0 ? cz - t : 0, zb = cz + t < g.nz - 1 ? cz + t : g.nz - 1;
+    const int ya = cy - t > 0 ? cy - t : 0, yb = cy + t < g.ny - 1 ? cy + t : g.ny - 1;
+    for (int z = za; z <= zb; z++) {
+      const bool zface = (z == cz - t) || (z == cz + t);
+      float dz = z < cz ? fz - (float)(z + 1) : (z > cz ? (float)z - fz : 0.f);
+      dz = dz - eps > 0.f ? dz - eps : 0.f;
+      for (int y = ya; y <= yb; y++) {
+        const bool face = zface || (y == cy - t) || (y == cy + t);
+        float dy = y < cy ? fy - (float)(y + 1) : (y > cy ? (float)y - fy : 0.f);
+        dy = dy - eps > 0.f ? dy - eps : 0.f;
+        const float dyz2 = (dy * dy + dz * dz) * g.h * g.h;
+        const float rem = Rp * Rp - dyz2;
+        if (rem < 0.f) continue;                                      // the whole row is out of reach
+        const float rad = sqrtf(rem) * g.inv_h + eps;                 // reach along x, in cells
+        const int xlo = (int)floorf(fx - rad), xhi = (int)floorf(fx + rad);
+        bool scanned = false;
+        if (face) {                                                   // a face row is one streak
+          const int x0 = cx - t > xlo ? cx - t : xlo, x1 = cx + t < xhi ? cx + t : xhi;
+          uint32_t b, e;
+          knn_row_range(g, x0, x1, y, z, b, e);
+          if (e > b) { knn_scan_range<K>(g.pts, b, e, qx, qy, qz, best); scanned = true; }
+        } else {                                                      // an inner row contributes its two end cells
+          for (int part = 0; part < 2; part++) {
+            const int x = part == 0 ? cx - t : cx + t;
+            if (x < xlo || x > xhi) continue;
+            uint32_t b, e;
+            knn_row_range(g, x, x, y, z, b, e);
+            if (e > b) { knn_scan_range<K>(g.pts, b, e, qx, qy, qz, best); scanned = true; }
+          }
+        }
+        if (scanned) {
+          const float dk = knn_key_d(best[KD]);
+          if (dk < gate) { const float r2 = sqrtf(dk) + pad; Rp = r2 < Rp ? r2 : Rp; }
+        }
+      }
+    }
+  }
+  return Rp;
+}
+
 LISREG_HD __forceinline__ void knn5_grid(const GridDev& g, float qx, float qy, float qz, float gate, knn_key (&best)[5]) {
   knn_grid<5>(g, qx, qy, qz, gate, best);
 }

@@ -61,6 +61,19 @@ struct MapSlot {
   CloudIndex corner, surf;
 };
 
+// Everything one in-flight batch (or chunk of a batch) of the frame pipeline / LM loop needs.  A context owns three:
+// ws[0] runs on the context stream (every synchronous entry point); ws[1] and ws[2] have private streams and
+// alternate between the chunks of the pipelined e2e path, so that two chunks are in flight while a third uploads.
+struct WorkSet {
+  cudaStream_t stream = nullptr;
+  DevBuf d_descs, d_states, d_partials, d_tickets, d_nbr, d_kstate, d_klist;
+  DevBuf d_feat, d_feat_frames, d_vox, d_vox_segs;
+  int feat_cap_frames = 0, feat_cells = 0, feat_nscan = 0;
+  void release() {
+    for (DevBuf* b : {&d_descs, &d_states, &d_partials, &d_tickets, &d_nbr, &d_kstate, &d_klist, &d_feat, &d_feat_frames, &d_vox, &d_vox_segs}) b->release();
+  }
+};
+
 struct lisreg_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -71,21 +84,18 @@ struct lisreg_ctx {
   std::vector<MapSlot> maps;
   MapDev* d_maps = nullptr; int d_maps_cap = 0; bool maps_dirty = true;
   // scratch
-  DevBuf d_stage, d_descs, d_states, d_partials, d_tickets, d_logs, d_pose, d_res, d_tmp, d_bbox;
+  DevBuf d_stage, d_logs, d_pose, d_res, d_tmp, d_bbox;
   PinBuf h_stage, h_out;
-  // feature-extraction work buffers (capacity feat_cap_frames frames of feat_cells cells)
-  DevBuf d_feat, d_feat_frames;
-  int feat_cap_frames = 0, feat_cells = 0, feat_nscan = 0;
-  DevBuf d_epsc, d_epsc2, d_icp, d_nbr;
+  WorkSet ws[3];
+  WorkSet* cur = &ws[0];   // work set (and stream) the run_* drivers use; only the pipelined e2e path switches it
+  DevBuf d_epsc, d_epsc2, d_icp;
   // e2e pipeline: H2D of chunk c+1 on copy_stream overlaps the compute of chunk c on `stream`
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_ev;
   PinBuf h_desc;       // pinned descriptor staging of the arena entry points (one slice per chunk)
   int e2e_chunk = 32;  // frames per chunk (LISREG_E2E_CHUNK; 0 = one copy, no overlap)
-  DevBuf d_kstate;
+  int n_sm = 148;
   int knn_noskip = 0;   // LISREG_KNN_NOSKIP=1: search every query from scratch at every iteration (parity check of the CHECK path)
-  // voxel-grid work buffers
-  DevBuf d_vox, d_vox_segs;
   // profiling
   bool prof_on = false;
   struct EvPair { cudaEvent_t a, b; int kind; double bytes; int64_t launches; };
@@ -105,9 +115,9 @@ struct ProfScope {   // records an event pair around a group of launches when pr
   ProfScope(lisreg_ctx* c, int kind, double bytes, int64_t launches) : ctx(c), on(c->prof_on) {
     if (!on) return;
     p.a = ev_get(c); p.b = ev_get(c); p.kind = kind; p.bytes = bytes; p.launches = launches;
-    cudaEventRecord(p.a, c->stream);
+    cudaEventRecord(p.a, c->cur->stream);
   }
-  ~ProfScope() { if (on) { cudaEventRecord(p.b, ctx->stream); ctx->ev_pending.push_back(p); } }
+  ~ProfScope() { if (on) { cudaEventRecord(p.b, ctx->cur->stream); ctx->ev_pending.push_back(p); } }
 };
 
 static int fail(lisreg_ctx* c, int code, const char* fmt, ...) {
@@ -323,7 +333,9 @@ int32_t lisreg_create(const lisreg_config* cfg, lisreg_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LISREG_ERR_CUDA; }
     ctx->own_stream = true;
   } else { ctx->stream = cfg ? (cudaStream_t)cfg->stream : nullptr; ctx->own_stream = false; }   // NULL = legacy default stream
+  ctx->ws[0].stream = ctx->stream;
   if (cfg && cfg->max_grid_cells > 0) ctx->max_cells = cfg->max_grid_cells;
+  { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, ctx->device) == cudaSuccess && v > 0) ctx->n_sm = v; }
   if (const char* e2 = getenv("LISREG_KNN_NOSKIP")) ctx->knn_noskip = atoi(e2) ? 1 : 0;
   if (const char* e3 = getenv("LISREG_E2E_CHUNK")) ctx->e2e_chunk = std::max(0, atoi(e3));
   *out = ctx;
@@ -338,8 +350,8 @@ void lisreg_destroy(lisreg_ctx* ctx) {
     cudaFree(m.corner.sorted); cudaFree(m.corner.cell_start); cudaFree(m.surf.sorted); cudaFree(m.surf.cell_start);
   }
   if (ctx->d_maps) cudaFree(ctx->d_maps);
-  for (DevBuf* b : {&ctx->d_stage, &ctx->d_descs, &ctx->d_states, &ctx->d_partials, &ctx->d_tickets, &ctx->d_logs,
-                    &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox, &ctx->d_feat, &ctx->d_feat_frames, &ctx->d_vox, &ctx->d_vox_segs, &ctx->d_epsc, &ctx->d_epsc2, &ctx->d_icp, &ctx->d_nbr, &ctx->d_kstate}) b->release();
+  for (DevBuf* b : {&ctx->d_stage, &ctx->d_logs, &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox, &ctx->d_epsc, &ctx->d_epsc2, &ctx->d_icp}) b->release();
+  for (int i = 0; i < 3; i++) { if (i > 0 && ctx->ws[i].stream) { cudaStreamSynchronize(ctx->ws[i].stream); cudaStreamDestroy(ctx->ws[i].stream); } ctx->ws[i].release(); }
   ctx->h_stage.release(); ctx->h_out.release(); ctx->h_desc.release();
   for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -468,7 +480,7 @@ static void to_dev_params(const lisreg_lm_params* p, LmParamsDev* d) {
 // that the fixed summation order - hence every bit of the result - does not depend on the chunking); 0 = B
 static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, double alg_bytes_per_iter, float* d_pose,
                   const lisreg_lm_params* prm, lisreg_lm_result* d_res, lisreg_lm_iter* d_logs, int tiling_B = 0) {
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = ctx->cur->stream;
   int rc = sync_maps(ctx);
   if (rc) return rc;
   LmParamsDev dp; to_dev_params(prm, &dp);
@@ -477,12 +489,12 @@ static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, dou
   if (tiling_B <= 0) tiling_B = B;
   const int tile_pts = (tiling_B >= 32) ? LM_MAX_TILE : LM_THREADS;
   const int max_tiles = std::max(1, (max_n + tile_pts - 1) / tile_pts);
-  CK(ctx->d_states.reserve(sizeof(RegState) * (size_t)B));
-  CK(ctx->d_partials.reserve(sizeof(double) * LM_NSUM * (size_t)B * max_tiles));
-  CK(ctx->d_tickets.reserve(sizeof(int) * (size_t)B));
-  RegState* states = (RegState*)ctx->d_states.p;
-  double* partials = (double*)ctx->d_partials.p;
-  int* tickets = (int*)ctx->d_tickets.p;
+  CK(ctx->cur->d_states.reserve(sizeof(RegState) * (size_t)B));
+  CK(ctx->cur->d_partials.reserve(sizeof(double) * LM_NSUM * (size_t)B * max_tiles));
+  CK(ctx->cur->d_tickets.reserve(sizeof(int) * (size_t)B));
+  RegState* states = (RegState*)ctx->cur->d_states.p;
+  double* partials = (double*)ctx->cur->d_partials.p;
+  int* tickets = (int*)ctx->cur->d_tickets.p;
   k_lm_init<<<(B + 127) / 128, 128, 0, st>>>(d_descs, states, d_pose, dp, tickets, B); LAUNCH_CK();
   // a block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...: batches get 32 blocks per registration
   // (the real tile count is only known on the device in the frame pipeline), a lone registration gets
@@ -490,14 +502,27 @@ static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, dou
   dim3 grid(std::min(max_tiles, tiling_B >= 32 ? 32 : 1024), B);
   {
     ProfScope ps(ctx, PROF_LM, alg_bytes_per_iter * dp.max_iters, dp.max_iters);
-    CK(ctx->d_nbr.reserve(sizeof(int) * 5 * (size_t)tile_pts * max_tiles * B));
-    CK(ctx->d_kstate.reserve(sizeof(KnnState) * (size_t)tile_pts * max_tiles * B));
-    int* nbr = (int*)ctx->d_nbr.p;
-    KnnState* kstate = (KnnState*)ctx->d_kstate.p;
+    const size_t slots = (size_t)tile_pts * max_tiles * B;
+    if (slots >= (size_t)0xffffffffu) return fail(ctx, LISREG_ERR_CAPACITY, "batch too large: %zu query slots (split the batch)", slots);
+    CK(ctx->cur->d_nbr.reserve(sizeof(int) * 5 * slots));
+    CK(ctx->cur->d_kstate.reserve(sizeof(KnnState) * slots));
+    CK(ctx->cur->d_klist.reserve(sizeof(unsigned) * 2 * slots + sizeof(int) * 2 * LISREG_MAX_ITERS));
+    int* nbr = (int*)ctx->cur->d_nbr.p;
+    KnnState* kstate = (KnnState*)ctx->cur->d_kstate.p;
+    unsigned* scan_list = (unsigned*)ctx->cur->d_klist.p;
+    unsigned* shell_list = scan_list + slots;
+    int* counters = (int*)(shell_list + slots);          // [it][2]: scan / shell list lengths of iteration it
+    CK(cudaMemsetAsync(counters, 0, sizeof(int) * 2 * LISREG_MAX_ITERS, st));
+    const int tile_shift = tile_pts == LM_MAX_TILE ? 9 : 7;
+    static_assert(LM_MAX_TILE == 512 && LM_THREADS == 128, "tile_shift assumes 512 / 128 query tiles");
     for (int it = 0; it < dp.max_iters; it++) {
       // iteration 0 searches every query; later iterations first try to PROVE that the neighbours did not change
-      k_lm_knn<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, kstate, max_tiles, tile_pts,
-                                            (it > 0 && !ctx->knn_noskip) ? 1 : 0); LAUNCH_CK();
+      k_knn_check<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, kstate, scan_list, counters + 2 * it,
+                                               max_tiles, tile_shift, (it > 0 && !ctx->knn_noskip) ? 1 : 0); LAUNCH_CK();
+      k_knn_search<false><<<ctx->n_sm * LM_KNN_MIN_BLOCKS, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, kstate, scan_list,
+                                               counters + 2 * it, shell_list, counters + 2 * it + 1, max_tiles, tile_shift); LAUNCH_CK();
+      k_knn_search<true><<<ctx->n_sm * 4, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, kstate, shell_list,
+                                               counters + 2 * it + 1, nullptr, nullptr, max_tiles, tile_shift); LAUNCH_CK();
       k_lm_resid<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp, nbr, partials, max_tiles, tile_pts); LAUNCH_CK();
       k_lm_solve<<<(B + LM_SOLVE_THREADS / 32 - 1) / (LM_SOLVE_THREADS / 32), LM_SOLVE_THREADS, 0, st>>>(
           d_descs, states, dp, partials, d_logs, max_tiles, tile_pts, B); LAUNCH_CK();
@@ -512,7 +537,7 @@ int32_t lisreg_scan2map_batch_dev(lisreg_ctx* ctx, int32_t B, const lisreg_batch
   if (!ctx || B <= 0 || !items || !d_pose6xB || !prm || !d_resxB) return fail(ctx, LISREG_ERR_ARG, "lisreg_scan2map_batch_dev: bad argument");
   if (prm->max_iters <= 0 || prm->max_iters > LISREG_MAX_ITERS) return fail(ctx, LISREG_ERR_ARG, "max_iters must be in 1..%d", LISREG_MAX_ITERS);
   CK(cudaSetDevice(ctx->device));
-  CK(ctx->d_descs.reserve(sizeof(RegDesc) * (size_t)B));
+  CK(ctx->cur->d_descs.reserve(sizeof(RegDesc) * (size_t)B));
   // pageable staging on purpose: cudaMemcpyAsync returns once a pageable source has been
   // consumed, so back-to-back asynchronous calls cannot race on the descriptor staging
   std::vector<RegDesc> hvec((size_t)B);
@@ -527,9 +552,9 @@ int32_t lisreg_scan2map_batch_dev(lisreg_ctx* ctx, int32_t B, const lisreg_batch
     h[b].clabel = it.clabel; h[b].slabel = it.slabel; h[b].nc = it.nc; h[b].ns = it.ns; h[b].map_slot = it.map_id; h[b].pad = 0; h[b].nc_ptr = nullptr; h[b].ns_ptr = nullptr;
     max_n = std::max(max_n, it.nc + it.ns);
   }
-  CK(cudaMemcpyAsync(ctx->d_descs.p, h, sizeof(RegDesc) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->cur->d_descs.p, h, sizeof(RegDesc) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
   lisreg_lm_iter* d_logs = nullptr;
-  return run_lm(ctx, B, (const RegDesc*)ctx->d_descs.p, max_n, alg, d_pose6xB, prm, d_resxB, d_logs);
+  return run_lm(ctx, B, (const RegDesc*)ctx->cur->d_descs.p, max_n, alg, d_pose6xB, prm, d_resxB, d_logs);
 }
 
 int32_t lisreg_scan2map_batch(lisreg_ctx* ctx, int32_t B, const lisreg_batch_item* items, float* pose6xB,
@@ -690,15 +715,15 @@ static void feat_carve(char* base, int cells, int nscan, FeatFrame* f) {
 
 static int feat_reserve(lisreg_ctx* ctx, int F, int cells, int nscan) {
   const size_t per = feat_frame_bytes(cells, nscan) + 4096;
-  CK(ctx->d_feat.reserve(per * (size_t)F));
-  CK(ctx->d_feat_frames.reserve(sizeof(FeatFrame) * (size_t)F));
-  ctx->feat_cap_frames = F; ctx->feat_cells = cells; ctx->feat_nscan = nscan;
+  CK(ctx->cur->d_feat.reserve(per * (size_t)F));
+  CK(ctx->cur->d_feat_frames.reserve(sizeof(FeatFrame) * (size_t)F));
+  ctx->cur->feat_cap_frames = F; ctx->cur->feat_cells = cells; ctx->cur->feat_nscan = nscan;
   return LISREG_OK;
 }
 
 // runs F1-F5 for F frames whose FeatFrame descriptors (device) are ready
 static int run_features(lisreg_ctx* ctx, FeatFrame* d_frames, int F, const lisreg_feat_params* prm, int max_n, double alg_bytes) {
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = ctx->cur->stream;
   FeatParamsDev dp{prm->n_scan, prm->horizon, prm->downsample_rate, prm->min_range, prm->max_range, prm->edge_thr, prm->surf_thr};
   const int cells = prm->n_scan * prm->horizon;
   ProfScope ps(ctx, PROF_FEAT, alg_bytes, 7);
@@ -728,11 +753,11 @@ int32_t lisreg_extract_features(lisreg_ctx* ctx, const float* pts, const uint16_
   char* d = (char*)ctx->d_stage.p;
   if (n) { CK(cudaMemcpyAsync(d, pts, bp, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(d + bp, ring, br, cudaMemcpyHostToDevice, st)); }
   FeatFrame f{};
-  feat_carve((char*)ctx->d_feat.p, cells, prm->n_scan, &f);
+  feat_carve((char*)ctx->cur->d_feat.p, cells, prm->n_scan, &f);
   f.pts = (const float4*)d; f.ring = (const uint16_t*)(d + bp); f.n = n;
-  CK(cudaMemcpyAsync(ctx->d_feat_frames.p, &f, sizeof(f), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->cur->d_feat_frames.p, &f, sizeof(f), cudaMemcpyHostToDevice, st));
   CK(cudaStreamSynchronize(st));   // f is a stack object
-  rc = run_features(ctx, (FeatFrame*)ctx->d_feat_frames.p, 1, prm, n, 17.0 * n);
+  rc = run_features(ctx, (FeatFrame*)ctx->cur->d_feat_frames.p, 1, prm, n, 17.0 * n);
   if (rc) return rc;
   int h[5];
   CK(cudaMemcpyAsync(&h[0], f.M, 4, cudaMemcpyDeviceToHost, st));
@@ -780,7 +805,7 @@ static void vox_carve(char* base, int cap, VoxSeg* s) {
 
 // runs the voxel grid for nseg clouds whose VoxSeg descriptors (device) are ready; max_n bounds every n
 static int run_voxel(lisreg_ctx* ctx, VoxSeg* d_segs, int nseg, int max_n, double alg_bytes) {
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = ctx->cur->stream;
   if (nseg <= 0) return LISREG_OK;
   const int nblk = std::max(1, (max_n + RS_TILE - 1) / RS_TILE);
   const int pblk = std::max(1, std::min(64, (max_n + 1023) / 1024));
@@ -806,15 +831,15 @@ int32_t lisreg_voxel_grid(lisreg_ctx* ctx, const float* pts, int32_t n, float le
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   CK(ctx->d_stage.reserve(sizeof(float4) * (size_t)n));
-  CK(ctx->d_vox.reserve(vox_seg_bytes(n)));
-  CK(ctx->d_vox_segs.reserve(sizeof(VoxSeg)));
+  CK(ctx->cur->d_vox.reserve(vox_seg_bytes(n)));
+  CK(ctx->cur->d_vox_segs.reserve(sizeof(VoxSeg)));
   CK(cudaMemcpyAsync(ctx->d_stage.p, pts, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
   VoxSeg s{};
-  vox_carve((char*)ctx->d_vox.p, n, &s);
+  vox_carve((char*)ctx->cur->d_vox.p, n, &s);
   s.src = (const float4*)ctx->d_stage.p; s.gather = nullptr; s.n_ptr = nullptr; s.n = n; s.leaf = leaf;
-  CK(cudaMemcpyAsync(ctx->d_vox_segs.p, &s, sizeof(s), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->cur->d_vox_segs.p, &s, sizeof(s), cudaMemcpyHostToDevice, st));
   CK(cudaStreamSynchronize(st));
-  int rc = run_voxel(ctx, (VoxSeg*)ctx->d_vox_segs.p, 1, n, 32.0 * n);
+  int rc = run_voxel(ctx, (VoxSeg*)ctx->cur->d_vox_segs.p, 1, n, 32.0 * n);
   if (rc) return rc;
   int cnt = 0;
   CK(cudaMemcpyAsync(&cnt, s.out_n, 4, cudaMemcpyDeviceToHost, st));
@@ -843,7 +868,7 @@ static size_t frame_desc_bytes(int F) {
 static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, const char* d_arena, uint64_t arena_bytes,
                       float* d_pose, const lisreg_frame_params* prm, lisreg_lm_result* d_res, char* h_pinned = nullptr,
                       int tiling_B = 0) {
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = ctx->cur->stream;
   const lisreg_feat_params* fp = &prm->feat;
   if (fp->n_scan <= 0 || fp->horizon <= 0 || fp->horizon > 2048 || fp->n_scan * 6 > 1024 || fp->downsample_rate <= 0)
     return fail(ctx, LISREG_ERR_ARG, "frame pipeline: unsupported n_scan/horizon/downsample_rate");
@@ -854,9 +879,9 @@ static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, co
   if (rc) return rc;
   const size_t feat_per = feat_frame_bytes(cells, fp->n_scan) + 4096;
   const size_t vc_per = vox_seg_bytes(ccap), vs_per = vox_seg_bytes(cells);
-  CK(ctx->d_vox.reserve((vc_per + vs_per) * (size_t)F));
-  CK(ctx->d_vox_segs.reserve(sizeof(VoxSeg) * 2 * (size_t)F));
-  CK(ctx->d_descs.reserve(sizeof(RegDesc) * (size_t)F));
+  CK(ctx->cur->d_vox.reserve((vc_per + vs_per) * (size_t)F));
+  CK(ctx->cur->d_vox_segs.reserve(sizeof(VoxSeg) * 2 * (size_t)F));
+  CK(ctx->cur->d_descs.reserve(sizeof(RegDesc) * (size_t)F));
   std::vector<FeatFrame> vf; std::vector<VoxSeg> vv; std::vector<RegDesc> vd;
   FeatFrame* hf; VoxSeg* hv; RegDesc* hd;
   if (h_pinned) {
@@ -878,10 +903,10 @@ static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, co
       pts = (const float4*)(d_arena + op); ring = (const uint16_t*)(d_arena + orr);
     } else { pts = (const float4*)it.pts; ring = it.ring; }
     FeatFrame& f = hf[i];
-    feat_carve((char*)ctx->d_feat.p + feat_per * (size_t)i, cells, fp->n_scan, &f);
+    feat_carve((char*)ctx->cur->d_feat.p + feat_per * (size_t)i, cells, fp->n_scan, &f);
     f.pts = pts; f.ring = ring; f.n = it.n;
     VoxSeg& vc = hv[2 * i]; VoxSeg& vs = hv[2 * i + 1];
-    char* vb = (char*)ctx->d_vox.p + (vc_per + vs_per) * (size_t)i;
+    char* vb = (char*)ctx->cur->d_vox.p + (vc_per + vs_per) * (size_t)i;
     vox_carve(vb, ccap, &vc); vox_carve(vb + vc_per, cells, &vs);
     vc.src = f.ext_pts; vc.gather = f.corner_idx; vc.n_ptr = f.counts + 0; vc.n = 0; vc.leaf = prm->corner_leaf;
     vs.src = f.ext_pts; vs.gather = f.surf_idx;   vs.n_ptr = f.counts + 3; vs.n = 0; vs.leaf = prm->surf_leaf;
@@ -891,18 +916,18 @@ static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, co
     max_n = std::max(max_n, it.n); feat_bytes += 17.0 * it.n;
   }
   // pageable sources: cudaMemcpyAsync returns once they are consumed
-  CK(cudaMemcpyAsync(ctx->d_feat_frames.p, hf, sizeof(FeatFrame) * (size_t)F, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(ctx->d_vox_segs.p, hv, sizeof(VoxSeg) * 2 * (size_t)F, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(ctx->d_descs.p, hd, sizeof(RegDesc) * (size_t)F, cudaMemcpyHostToDevice, st));
-  rc = run_features(ctx, (FeatFrame*)ctx->d_feat_frames.p, F, fp, max_n, feat_bytes);
+  CK(cudaMemcpyAsync(ctx->cur->d_feat_frames.p, hf, sizeof(FeatFrame) * (size_t)F, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->cur->d_vox_segs.p, hv, sizeof(VoxSeg) * 2 * (size_t)F, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->cur->d_descs.p, hd, sizeof(RegDesc) * (size_t)F, cudaMemcpyHostToDevice, st));
+  rc = run_features(ctx, (FeatFrame*)ctx->cur->d_feat_frames.p, F, fp, max_n, feat_bytes);
   if (rc) return rc;
-  rc = run_voxel(ctx, (VoxSeg*)ctx->d_vox_segs.p, 2 * F, std::min(max_n, cells), 2.0 * feat_bytes);
+  rc = run_voxel(ctx, (VoxSeg*)ctx->cur->d_vox_segs.p, 2 * F, std::min(max_n, cells), 2.0 * feat_bytes);
   if (rc) return rc;
   // the per-frame query counts live on the device; size the LM grid for the largest possible tile count
   // of this batch (blocks beyond a frame's real tile count exit immediately).  Voxel output never exceeds
   // its input, and the input never exceeds the sweep size.
   const int lm_max_n = std::min(max_n, cells);
-  return run_lm(ctx, F, (const RegDesc*)ctx->d_descs.p, lm_max_n, 0.0, d_pose, &prm->lm, d_res, nullptr, tiling_B);
+  return run_lm(ctx, F, (const RegDesc*)ctx->cur->d_descs.p, lm_max_n, 0.0, d_pose, &prm->lm, d_res, nullptr, tiling_B);
 }
 
 int32_t lisreg_frames_batch_dev(lisreg_ctx* ctx, int32_t F, const lisreg_frame_item* items, float* d_pose6xF,
@@ -959,24 +984,42 @@ int32_t lisreg_frames_batch_arena(lisreg_ctx* ctx, int32_t F, const lisreg_frame
     if (rc) return rc;
   } else {
     if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    while ((int)ctx->chunk_ev.size() < nchunk + 1) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
+    for (int i = 1; i < 3; i++) if (!ctx->ws[i].stream) CK(cudaStreamCreateWithFlags(&ctx->ws[i].stream, cudaStreamNonBlocking));
+    while ((int)ctx->chunk_ev.size() < nchunk + 3) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
     const size_t desc_per = frame_desc_bytes(C);
     CK(ctx->h_desc.reserve(desc_per * (size_t)nchunk));
-    // the copy stream must not overwrite the arena while earlier work of this context still reads it
-    CK(cudaEventRecord(ctx->chunk_ev[nchunk], st));
-    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[nchunk], 0));
+    int rc = sync_maps(ctx);
+    if (rc) return rc;
+    // neither the copy stream nor the two chunk streams may touch the staging buffers while earlier work of this
+    // context (incl. the pose upload above) is still in flight on the context stream
+    cudaEvent_t ev_start = ctx->chunk_ev[nchunk];
+    CK(cudaEventRecord(ev_start, st));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ev_start, 0));
+    CK(cudaStreamWaitEvent(ctx->ws[1].stream, ev_start, 0));
+    CK(cudaStreamWaitEvent(ctx->ws[2].stream, ev_start, 0));
     for (int c = 0; c < nchunk; c++) {
       if (hi[c] > lo[c])
         CK(cudaMemcpyAsync(d_arena + lo[c], (const char*)host_arena + lo[c], (size_t)(hi[c] - lo[c]), cudaMemcpyHostToDevice, ctx->copy_stream));
       CK(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
     }
-    for (int c = 0; c < nchunk; c++) {
+    // chunks alternate between two work sets with private streams: while one chunk sits in a latency-bound phase
+    // (segment selection, the 6x6 solves, launch gaps) the other one keeps the SMs busy
+    rc = LISREG_OK;
+    for (int c = 0; c < nchunk && rc == LISREG_OK; c++) {
       const int f0 = c * C, fc = std::min(C, F - f0);
-      CK(cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0));
-      int rc = run_frames(ctx, fc, items + f0, d_arena, arena_bytes, d_pose + 6 * (size_t)f0, prm, d_res + f0,
-                          (char*)ctx->h_desc.p + desc_per * (size_t)c, F);
-      if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(st); return rc; }
+      ctx->cur = &ctx->ws[1 + (c & 1)];
+      cudaError_t e = cudaStreamWaitEvent(ctx->cur->stream, ctx->chunk_ev[c], 0);
+      if (e != cudaSuccess) rc = fail(ctx, LISREG_ERR_CUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
+      else rc = run_frames(ctx, fc, items + f0, d_arena, arena_bytes, d_pose + 6 * (size_t)f0, prm, d_res + f0,
+                           (char*)ctx->h_desc.p + desc_per * (size_t)c, F);
     }
+    ctx->cur = &ctx->ws[0];
+    // join: the context stream continues after both chunk streams
+    for (int i = 1; i < 3; i++) {
+      cudaEventRecord(ctx->chunk_ev[nchunk + i], ctx->ws[i].stream);
+      cudaStreamWaitEvent(st, ctx->chunk_ev[nchunk + i], 0);
+    }
+    if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(st); return rc; }
   }
   CK(ctx->h_out.reserve(sizeof(lisreg_lm_result) * (size_t)F));
   CK(cudaMemcpyAsync(ctx->h_out.p, d_res, sizeof(lisreg_lm_result) * (size_t)F, cudaMemcpyDeviceToHost, st));

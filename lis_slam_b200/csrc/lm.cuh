@@ -242,31 +242,34 @@ __device__ __forceinline__ void lm_pair_of_lane(int lane, int& r, int& c) {
 constexpr int LM_MAX_TILE = 512;
 
 // ---------------------------------------------------------------------------------------------------------
-// One Gauss-Newton iteration = k_lm_knn (5-NN search: few registers, latency bound -> many resident warps)
-// + k_lm_resid (coefficients + 27-term reduction: many registers) + k_lm_solve.  The 5 neighbour positions of
-// every query cross through global memory (20 B per query).
+// One Gauss-Newton iteration = the 5-NN stage (k_knn_check -> k_knn_scan -> k_knn_shell: few registers, latency
+// bound -> many resident warps) + k_lm_resid (coefficients + 27-term reduction: many registers) + k_lm_solve.
+// The 5 neighbour positions of every query cross through global memory (20 B per query).
 //
-// k_lm_knn exploits the temporal coherence of the iteration: between two iterations a query moves by
+// The 5-NN stage exploits the temporal coherence of the iteration: between two iterations a query moves by
 // centimetres or less, so its 5 nearest neighbours almost never change.  Every real search also records the
 // SAFE RADIUS s of the query = a lower bound on the distance from the searched position q_ref to every map
 // point that is NOT one of the 5 neighbours (the 6th best candidate visited, and the bound of everything not
 // visited).  At the next iteration the query sits at q with |q - q_ref| = delta: by the triangle inequality
 // every non-neighbour is farther than s - delta, so if (s - delta)^2 exceeds the largest of the 5 re-evaluated
 // neighbour distances the old set IS the exact 5-NN set of q - proved, not assumed - and only its order is
-// refreshed (CHECK path: 5 gathers instead of ~25 candidates).  Queries that fail the test are searched again.
+// refreshed (5 gathers instead of ~25 candidates).  Queries that fail the test are searched again.
 // Results are bit-identical to searching every query from scratch (LISREG_KNN_NOSKIP=1 does exactly that;
 // tests/test_lm_parity.py compares the two).
 //
-// Work decomposition: a block owns a tile of tile_pts queries, each WARP a quarter of it, and nothing in the
-// tile loop synchronises the block.  A warp runs three dense phases, compacting the work of the next phase
-// into a shared-memory list with ballots so that the lanes stay busy:
-//   1. CHECK   every query of the sub-tile (coalesced state loads, 5 gathers)
-//   2. SCAN    queries that failed the check: flattened 3x3x3 block scan - the nine row streaks of a query are
-//              staged in shared memory and walked as ONE candidate list, so a warp iterates max(total) times
-//              instead of sum(max per row) times - with a one-candidate-ahead prefetch
-//   3. SHELLS  the few queries whose 5th neighbour may lie outside the block: full search with outer shells
+// Three kernels, each with dense warps; the work of the next one is compacted into a global list (one slot id per
+// query, appended with one warp-aggregated atomic per 32 queries; results do not depend on the list order):
+//   k_knn_check  every query: coalesced state loads, 5 gathers, the proof; failures -> scan list
+//   k_knn_scan   listed queries: flattened 3x3x3 block scan - the nine row streaks of a query are staged in shared
+//                memory and walked as ONE candidate list, so a warp iterates max(total) times instead of
+//                sum(max per row) times - with a two-candidates-ahead prefetch; queries whose 5th neighbour may
+//                lie outside the block -> shell list
+//   k_knn_search<SHELL>  listed queries: ball walk (grid.cuh knn_ball_walk) with row / cell pruning; also gives
+//                rejected queries a bound so that they are not searched again either
 // ---------------------------------------------------------------------------------------------------------
-struct KnnState { float x, y, z, s; };   // searched position q_ref and safe radius (0 = none: search again)
+struct KnnState { float x, y, z, s; };   // searched position q_ref and safe radius: > 0 accepted (bound of every non-neighbour),
+                                         // < 0 rejected (-bound of the 5th-nearest distance), 0 = none: search again
+constexpr float KNN_PAD = 0.1f;          // proof margin (m) the ball walk of sparse queries leaves around its result
 
 #define KNN_INF __int_as_float(0x7f800000)   // +inf
 
@@ -289,8 +292,9 @@ __device__ __forceinline__ float knn_dist2(float qx, float qy, float qz, float4 
   return d;
 }
 
-// flattened 3x3x3 block scan; rng = this thread's column of the shared range table (stride LM_THREADS).
-// Returns true when the outer shells are needed; lb = lower bound of everything outside the block.
+// flattened 3x3x3 block scan; rng = this thread's column of the shared range table (stride LM_THREADS, 10 rows:
+// up to nine non-empty row streaks and a terminator).  Returns true when the outer shells are needed; lb = lower
+// bound of everything outside the block.
 __device__ __forceinline__ bool knn6_block_flat(const GridDev& g, float qx, float qy, float qz, float gate,
                                                 float (&bd)[6], unsigned (&bp)[6], uint2* rng, float& lb) {
 #pragma unroll
@@ -301,32 +305,44 @@ __device__ __forceinline__ bool knn6_block_flat(const GridDev& g, float qx, floa
   const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
   const float rx = fx - (float)cx, ry = fy - (float)cy, rz = fz - (float)cz;
   const float minf = fminf(fminf(fminf(rx, 1.f - rx), fminf(ry, 1.f - ry)), fminf(rz, 1.f - rz));
+  // the x extent is the same for the nine rows; a row is ONE contiguous streak of the sorted point array
+  const int xa = cx - 1 > 0 ? cx - 1 : 0, xb = cx + 1 < g.nx - 1 ? cx + 1 : g.nx - 1;
   int nr = 0;
+  if (xa <= xb) {
+    const uint32_t* __restrict__ cs = g.cell_start;
 #pragma unroll
-  for (int r = 0; r < 9; r++) {
-    uint32_t b, e;
-    knn_row_range(g, cx - 1, cx + 1, cy + (r % 3) - 1, cz + (r / 3) - 1, b, e);
-    if (e > b) { rng[nr * LM_THREADS] = make_uint2(b, e); nr++; }
+    for (int r = 0; r < 9; r++) {
+      const int y = cy + (r % 3) - 1, z = cz + (r / 3) - 1;
+      if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
+        const int rowbase = (z * g.ny + y) * g.nx;
+        const uint32_t b = __ldg(&cs[rowbase + xa]), e = __ldg(&cs[rowbase + xb + 1]);
+        if (e > b) { rng[nr * LM_THREADS] = make_uint2(b, e); nr++; }
+      }
+    }
   }
   const float4* __restrict__ pts = g.pts;
   if (nr > 0) {
+    // software pipeline: c0 is processed while c1 and c2 are in flight.  adv() steps the cursor (p, e, k) to the
+    // next candidate of the flattened list; past the end it keeps returning the last valid position (harmless
+    // re-load) and `left` counts what is really there.
+    int left = 0;
+    for (int k = 0; k < nr; k++) { const uint2 r = rng[k * LM_THREADS]; left += (int)(r.y - r.x); }
     uint2 r0 = rng[0];
-    uint32_t p = r0.x, e = r0.y;
-    int k = 1;
-    float4 cur = __ldg(&pts[p]);
-    bool have = true;
-    while (have) {
-      const unsigned pc = p;
-      p++;
-      if (p == e) {
-        if (k < nr) { const uint2 r = rng[k * LM_THREADS]; k++; p = r.x; e = r.y; }
-        else have = false;
-      }
-      float4 nxt = cur;
-      if (have) nxt = __ldg(&pts[p]);      // prefetch the next candidate while this one is processed
-      const float d = knn_dist2(qx, qy, qz, cur);
-      if (d < bd[5]) knn6_insert_mono(bd, bp, d, pc);
-      cur = nxt;
+    unsigned p = r0.x, e = r0.y; int k = 1;
+    auto adv = [&]() {
+      unsigned np = p + 1;
+      if (np == e && k < nr) { const uint2 r = rng[k * LM_THREADS]; k++; np = r.x; e = r.y; }
+      else if (np == e) { np = p; e = p + 1; }     // stay on the last candidate
+      p = np;
+    };
+    unsigned p0 = p; float4 c0 = __ldg(&pts[p]); adv();
+    unsigned p1 = p; float4 c1 = __ldg(&pts[p]); adv();
+    while (left > 0) {
+      const unsigned p2 = p; const float4 c2 = __ldg(&pts[p]); adv();
+      const float d = knn_dist2(qx, qy, qz, c0);
+      if (d < bd[5]) knn6_insert_mono(bd, bp, d, p0);
+      c0 = c1; p0 = p1; c1 = c2; p1 = p2;
+      left--;
     }
   }
   lb = knn_block_lb(g, minf);
@@ -346,50 +362,66 @@ __device__ __forceinline__ void knn_commit(int* __restrict__ tnbr, KnnState* __r
     // fp32 rounding of the distance evaluation and of the square root
     st.s = fminf(sqrtf(d6), lbu) * 0.99999f;
   } else {
+    // rejected (5th neighbour outside the gate): -s = lower bound of the 5th-nearest distance, so that the next
+    // iteration can prove "still rejected" without searching
     tnbr[l] = -1;
+    st.s = -(fminf(sqrtf(d5), lbu) * 0.99999f);
   }
   tstate[l] = st;
 }
 
-#ifndef LM_KNN_MIN_BLOCKS
-#define LM_KNN_MIN_BLOCKS 8
-#endif
-__global__ void __launch_bounds__(LM_THREADS, LM_KNN_MIN_BLOCKS)
-k_lm_knn(const RegDesc* __restrict__ descs, const RegState* __restrict__ states, const MapDev* __restrict__ maps,
-         float gate, int* __restrict__ nbr, KnnState* __restrict__ kstate, int max_tiles, int tile_pts, int use_state) {
-  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+// appends the slots of the lanes with `need` to a global list: one atomic per warp
+__device__ __forceinline__ void knn_list_append(bool need, unsigned slot, unsigned* __restrict__ list, int* __restrict__ counter) {
+  const unsigned m = __ballot_sync(0xffffffffu, need);
+  if (m == 0u) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (need) list[base + __popc(m & ((1u << lane) - 1u))] = slot;
+}
+
+// slot id of a query = position in the [B][max_tiles][tile_pts] slot space (tile_pts = 1 << tile_shift)
+struct KnnSlot { int b, tile, l, q; };
+__device__ __forceinline__ KnnSlot knn_slot_decode(unsigned slot, int max_tiles, int tile_shift) {
+  KnnSlot s;
+  const unsigned bt = slot >> tile_shift;
+  s.l = (int)(slot & ((1u << tile_shift) - 1u));
+  s.b = (int)(bt / (unsigned)max_tiles); s.tile = (int)(bt - (unsigned)s.b * (unsigned)max_tiles);
+  s.q = (s.tile << tile_shift) + s.l;
+  return s;
+}
+
+// ---- k_knn_check: grid (tiles, B), one thread per query ----
+__global__ void __launch_bounds__(LM_THREADS)
+k_knn_check(const RegDesc* __restrict__ descs, const RegState* __restrict__ states, const MapDev* __restrict__ maps,
+            float gate, int* __restrict__ nbr, KnnState* __restrict__ kstate, unsigned* __restrict__ scan_list,
+            int* __restrict__ counter, int max_tiles, int tile_shift, int use_state) {
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int tile_pts = 1 << tile_shift;
   __shared__ RegDesc sd;
   __shared__ float sT[12];
   __shared__ int sdone;
-  __shared__ uint2 s_rng[9 * LM_THREADS];
-  __shared__ unsigned char s_scan[LM_THREADS / 32][LM_MAX_TILE / 4];
-  __shared__ unsigned char s_shell[LM_THREADS / 32][LM_MAX_TILE / 4];
   if (tid == 0) { sd = descs[b]; sd.nc = states[b].nc; sd.ns = states[b].ns; sdone = states[b].done; }
   if (tid < 12) sT[tid] = states[b].T[tid];
   __syncthreads();
   if (sdone) return;
   const int n = sd.nc + sd.ns;
-  const int ntiles = (n + tile_pts - 1) / tile_pts;
+  const int ntiles = (n + tile_pts - 1) >> tile_shift;
   const MapDev& mp = maps[sd.map_slot];
-  const int sub = tile_pts / (LM_THREADS / 32);        // queries per warp per tile (32 or 128)
-  const unsigned lt_mask = (1u << lane) - 1u;
-  uint2* rng = s_rng + tid;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int q0 = tile * tile_pts;
+    const int q0 = tile << tile_shift;
     const int qn = min(n - q0, tile_pts);
-    int* tnbr = nbr + ((size_t)b * max_tiles + tile) * 5 * tile_pts;         // [5][tile_pts]
-    KnnState* tstate = kstate + ((size_t)b * max_tiles + tile) * tile_pts;   // [tile_pts]
-    const int l0 = wid * sub;
-    int n_scan = 0, n_shell = 0;
-    // ---------------- phase 1: CHECK ----------------
-    for (int o = 0; o < sub; o += 32) {
-      const int l = l0 + o + lane;
+    const size_t bt = (size_t)b * max_tiles + tile;
+    int* tnbr = nbr + bt * 5 * tile_pts;         // [5][tile_pts]
+    KnnState* tstate = kstate + bt * tile_pts;   // [tile_pts]
+    for (int l = tid; l < tile_pts; l += LM_THREADS) {   // tile_pts is a multiple of LM_THREADS: warps stay whole
       bool need = false;
       if (l < qn) {
         need = true;
         if (use_state) {
-          const float4 ref = __ldg(reinterpret_cast<const float4*>(&tstate[l]));
-          if (ref.w > 0.f) {
+          const float4 ref = *reinterpret_cast<const float4*>(&tstate[l]);
+          if (ref.w != 0.f) {
             const int q = q0 + l;
             const bool is_corner = q < sd.nc;
             const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
@@ -398,8 +430,11 @@ k_lm_knn(const RegDesc* __restrict__ descs, const RegState* __restrict__ states,
             const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
             const float mx = x0 - ref.x, my = y0 - ref.y, mz = z0 - ref.z;
             const float delta = sqrtf(mx * mx + my * my + mz * mz) * 1.00001f + 1e-6f;   // upper bound of the move
-            const float r = ref.w - delta;
-            if (r > 0.f) {
+            const float r = fabsf(ref.w) - delta;
+            if (r > 0.f && ref.w < 0.f) {
+              // rejected last time: the 5th-nearest point was farther than |s|, so it is still farther than r
+              if (r * r * 0.99999f > gate) need = false;          // still rejected; nbr[l] is already -1
+            } else if (r > 0.f) {
               const float4* __restrict__ pts = is_corner ? mp.corner.pts : mp.surf.pts;
               int pos[5]; knn_key key[5];
               float bmax = 0.f;
@@ -426,65 +461,74 @@ k_lm_knn(const RegDesc* __restrict__ descs, const RegState* __restrict__ states,
 #pragma unroll
                     for (int j = 0; j < 5; j++) tnbr[j * tile_pts + l] = knn_key_pos(key[j]);
                   }
-                } else {                          // the 5th neighbour left the gate: rejected; search again next time
+                } else {
+                  // the 5th neighbour left the gate: rejected now.  Its distance (>= sqrt(gate), and the neighbours are
+                  // the exact 5-NN) is the bound of the 5th-nearest distance from HERE
                   tnbr[l] = -1;
-                  tstate[l].s = 0.f;
+                  KnnState ns; ns.x = x0; ns.y = y0; ns.z = z0; ns.s = -(sqrtf(bmax) * 0.99999f);
+                  tstate[l] = ns;
                 }
               }
             }
           }
         }
       }
-      const unsigned m = __ballot_sync(0xffffffffu, need);
-      if (need) s_scan[wid][n_scan + __popc(m & lt_mask)] = (unsigned char)(o + lane);
-      n_scan += __popc(m);
+      knn_list_append(need, (unsigned)(bt * tile_pts + l), scan_list, counter);
     }
-    __syncwarp();
-    // ---------------- phase 2: SCAN ----------------
-    for (int base = 0; base < n_scan; base += 32) {
-      const int i = base + lane;
-      bool need_shell = false;
-      int ll = 0;
-      if (i < n_scan) {
-        ll = s_scan[wid][i];
-        const int l = l0 + ll;
-        const int q = q0 + l;
-        const bool is_corner = q < sd.nc;
-        const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
-        // pointAssociateToMap (:243-258)
-        const float x0 = sT[0] * p.x + sT[1] * p.y + sT[2] * p.z + sT[3];
-        const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
-        const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
-        const GridDev& g = is_corner ? mp.corner : mp.surf;
+  }
+}
+
+// ---- k_knn_scan / k_knn_shell: grid-stride over a slot list, one thread per listed query ----
+#ifndef LM_KNN_MIN_BLOCKS
+#define LM_KNN_MIN_BLOCKS 8
+#endif
+template <bool SHELL>
+__global__ void __launch_bounds__(LM_THREADS, LM_KNN_MIN_BLOCKS)
+k_knn_search(const RegDesc* __restrict__ descs, const RegState* __restrict__ states, const MapDev* __restrict__ maps,
+             float gate, int* __restrict__ nbr, KnnState* __restrict__ kstate, const unsigned* __restrict__ list,
+             const int* __restrict__ counter, unsigned* __restrict__ shell_list, int* __restrict__ shell_counter,
+             int max_tiles, int tile_shift) {
+  __shared__ uint2 s_rng[SHELL ? 1 : 10 * LM_THREADS];
+  const int tile_pts = 1 << tile_shift;
+  const int total = *counter;
+  const int lane = threadIdx.x & 31;
+  for (int base = (blockIdx.x * LM_THREADS + threadIdx.x) - lane; base < total; base += gridDim.x * LM_THREADS) {
+    const int i = base + lane;
+    bool need_shell = false;
+    unsigned slot = 0u;
+    if (i < total) {
+      slot = list[i];
+      const KnnSlot ks = knn_slot_decode(slot, max_tiles, tile_shift);
+      const RegDesc* __restrict__ d = &descs[ks.b];
+      const RegState* __restrict__ st = &states[ks.b];
+      const int nc = st->nc;
+      const bool is_corner = ks.q < nc;
+      const float4 p = is_corner ? __ldg(&d->corner[ks.q]) : __ldg(&d->surf[ks.q - nc]);
+      // pointAssociateToMap (:243-258)
+      const float x0 = st->T[0] * p.x + st->T[1] * p.y + st->T[2] * p.z + st->T[3];
+      const float y0 = st->T[4] * p.x + st->T[5] * p.y + st->T[6] * p.z + st->T[7];
+      const float z0 = st->T[8] * p.x + st->T[9] * p.y + st->T[10] * p.z + st->T[11];
+      const MapDev& mp = maps[d->map_slot];
+      const GridDev& g = is_corner ? mp.corner : mp.surf;
+      const size_t bt = (size_t)ks.b * max_tiles + ks.tile;
+      int* tnbr = nbr + bt * 5 * tile_pts;
+      KnnState* tstate = kstate + bt * tile_pts;
+      if (SHELL) {
+        knn_key best[6];
+        const float lbu = knn_ball_walk<6, 4>(g, x0, y0, z0, gate, KNN_PAD, best);
+        const unsigned pos[5] = {(unsigned)knn_key_pos(best[0]), (unsigned)knn_key_pos(best[1]), (unsigned)knn_key_pos(best[2]),
+                                 (unsigned)knn_key_pos(best[3]), (unsigned)knn_key_pos(best[4])};
+        knn_commit(tnbr, tstate, tile_pts, ks.l, x0, y0, z0, gate, knn_key_d(best[4]), knn_key_d(best[5]), lbu, pos);
+      } else {
         float bd[6]; unsigned bp[6]; float lb;
-        need_shell = knn6_block_flat(g, x0, y0, z0, gate, bd, bp, rng, lb);
+        need_shell = knn6_block_flat(g, x0, y0, z0, gate, bd, bp, s_rng + threadIdx.x, lb);
         if (!need_shell) {
           const unsigned pos[5] = {bp[0], bp[1], bp[2], bp[3], bp[4]};
-          knn_commit(tnbr, tstate, tile_pts, l, x0, y0, z0, gate, bd[4], bd[5], lb, pos);
+          knn_commit(tnbr, tstate, tile_pts, ks.l, x0, y0, z0, gate, bd[4], bd[5], lb, pos);
         }
       }
-      const unsigned m = __ballot_sync(0xffffffffu, need_shell);
-      if (need_shell) s_shell[wid][n_shell + __popc(m & lt_mask)] = (unsigned char)ll;
-      n_shell += __popc(m);
     }
-    __syncwarp();
-    // ---------------- phase 3: SHELLS ----------------
-    for (int i = lane; i < n_shell; i += 32) {
-      const int l = l0 + s_shell[wid][i];
-      const int q = q0 + l;
-      const bool is_corner = q < sd.nc;
-      const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
-      const float x0 = sT[0] * p.x + sT[1] * p.y + sT[2] * p.z + sT[3];
-      const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
-      const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
-      const GridDev& g = is_corner ? mp.corner : mp.surf;
-      knn_key best[6];
-      const float lbu = knn_grid_tracked<6, 4>(g, x0, y0, z0, gate, best);
-      const unsigned pos[5] = {(unsigned)knn_key_pos(best[0]), (unsigned)knn_key_pos(best[1]), (unsigned)knn_key_pos(best[2]),
-                               (unsigned)knn_key_pos(best[3]), (unsigned)knn_key_pos(best[4])};
-      knn_commit(tnbr, tstate, tile_pts, l, x0, y0, z0, gate, knn_key_d(best[4]), knn_key_d(best[5]), lbu, pos);
-    }
-    __syncwarp();
+    if (!SHELL) knn_list_append(need_shell, slot, shell_list, shell_counter);
   }
 }
 
@@ -638,18 +682,18 @@ __global__ void k_selftest_smallmat(const float* __restrict__ A36, const float* 
   for (int i = 0; i < 9; i++) out[89 + i] = V3[i];
 }
 
-// stand-alone exact 5-NN (tests / lisreg_knn5): the same flattened block scan + tracked shells as k_lm_knn.
-// safe (nullable, nq): the safe radius k_lm_knn would record for the query.
+// stand-alone exact 5-NN (tests / lisreg_knn5): the same flattened block scan + tracked shells as k_knn_search.
+// safe (nullable, nq): the safe radius the search would record for the query.
 __global__ void __launch_bounds__(LM_THREADS)
 k_knn5(GridDev g, const float4* __restrict__ q, int nq, float gate, int* __restrict__ idx, float* __restrict__ sqd, float* __restrict__ safe) {
-  __shared__ uint2 s_rng[9 * LM_THREADS];
+  __shared__ uint2 s_rng[10 * LM_THREADS];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   float4 p = q[i];
   float bd[6]; unsigned bp[6]; float lb;
   if (knn6_block_flat(g, p.x, p.y, p.z, gate, bd, bp, s_rng + threadIdx.x, lb)) {
     knn_key best[6];
-    lb = knn_grid_tracked<6, 4>(g, p.x, p.y, p.z, gate, best);
+    lb = knn_ball_walk<6, 4>(g, p.x, p.y, p.z, gate, KNN_PAD, best);
 #pragma unroll
     for (int j = 0; j < 6; j++) { bd[j] = knn_key_d(best[j]); bp[j] = (unsigned)knn_key_pos(best[j]); }
   }

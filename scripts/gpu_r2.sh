@@ -18,4 +18,4 @@ run b128 "LISREG_E2E_CHUNK=0" --batch 128 --no-cpu
 run b32 "LISREG_E2E_CHUNK=0" --batch 32 --no-cpu
 run b8 "LISREG_E2E_CHUNK=0" --batch 8 --no-cpu
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/${T}_ncu_launch.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_lm_knn|k_feat_segments' -s 2 -c 5 -o gpurun_out/${T}_prof python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/${T}_ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_knn_search|k_knn_check|k_feat_segments|k_lm_resid' -s 0 -c 9 -o gpurun_out/${T}_prof python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/${T}_ncu_full.log 2>&1

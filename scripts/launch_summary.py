@@ -11,8 +11,13 @@ for x in csv.DictReader(lines):
     v = v / 1000 if u == 'ns' else v * 1000 if u == 'ms' else v
     rows.append((x['Kernel Name'].split('(')[0].replace('lisreg::', ''), v))
 fin = [i for i, r in enumerate(rows) if r[0] == 'k_lm_finish']
-k = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-a, b = fin[-k - 1] + 1, fin[-k] + 1
+# steps = launch ranges between consecutive k_lm_finish; default: the longest one (a full device-resident batch,
+# not one chunk of the pipelined e2e path)
+steps = [(fin[i] + 1, fin[i + 1] + 1) for i in range(len(fin) - 1)]
+if len(sys.argv) > 2:
+    a, b = steps[-int(sys.argv[2])]
+else:
+    a, b = max(steps, key=lambda ab: sum(v for _, v in rows[ab[0]:ab[1]]))
 agg = collections.OrderedDict()
 for n, v in rows[a:b]:
     d = agg.setdefault(n[:60], [0, 0.0]); d[0] += 1; d[1] += v
@@ -21,3 +26,5 @@ print("| kernel | launches | total us | share | avg us |\n|---|---|---|---|---|"
 for n, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print("| %s | %d | %.1f | %.3f | %.1f |" % (n, v[0], v[1], v[1] / tot, v[1] / v[0]))
 print("| total | %d | %.1f | 1 | |" % (sum(v[0] for v in agg.values()), tot))
+for kn in ("k_lm_knn", "k_lm_resid"):
+    print("%s per iteration (us): %s" % (kn, [round(v) for n, v in rows[a:b] if n == kn]))
