@@ -217,6 +217,17 @@ int32_t lisreg_frames_batch_arena(lisreg_ctx* ctx, int32_t F, const lisreg_frame
                                   const void* host_arena, uint64_t arena_bytes,
                                   float* pose6xF, const lisreg_frame_params* prm, lisreg_lm_result* resxF);
 
+/* Pipelined form of lisreg_frames_batch_arena for a continuous stream of batches (a node that receives sweeps
+ * while the previous ones are still being registered): submit() enqueues the upload of the arena, the whole
+ * pipeline and the download of the results on a private stream and returns a ticket at once; wait() blocks
+ * until that batch is done and hands out its poses / results.  Two tickets can be in flight, so the PCIe upload
+ * of batch k+1 overlaps the compute of batch k.  host_arena must stay valid (and should be pinned) until wait();
+ * pose6xF is consumed before submit() returns.  Results are bit-identical to lisreg_frames_batch_arena. */
+int32_t lisreg_frames_batch_submit(lisreg_ctx* ctx, int32_t F, const lisreg_frame_item* items,
+                                   const void* host_arena, uint64_t arena_bytes, const float* pose6xF,
+                                   const lisreg_frame_params* prm, int32_t* ticket);
+int32_t lisreg_frames_batch_wait(lisreg_ctx* ctx, int32_t ticket, float* pose6xF, lisreg_lm_result* resxF);
+
 /* ---- EPSC loop-closure descriptors and scoring (B3 pieces) ----
  * lisreg_epsc_describe replaces EPSCGeneration::calculateEPSC / calculateSEPSC / calculateFEPSC
  * (epscGeneration.cpp:478-607) for n submaps/keyframes at once; using_map is the 256-entry label -> class
@@ -237,6 +248,40 @@ int32_t lisreg_epsc_score_all(lisreg_ctx* ctx, const uint8_t* desc, int32_t N, i
 /* same with descriptors and outputs resident in HBM; asynchronous */
 int32_t lisreg_epsc_score_all_dev(lisreg_ctx* ctx, const uint8_t* d_desc, int32_t N, int32_t topk,
                                   int32_t* d_idx, float* d_score, int8_t* d_shift);
+
+/* ---- EPSC loop detector (B3) ----
+ * Replaces EPSCGeneration::loopDetection(corner, surf, semantic, odom) (epscGeneration.h:155-158,
+ * epscGeneration.cpp:663-992) together with project() (:84-120) and globalICP() (:258-401): one stateful,
+ * append-only detector per EPSCGeneration instance.  Every call gates the stored keyframes by travelled distance
+ * (SKIP_NEIBOUR_DISTANCE, INFLATION_COVARIANCE), aligns the current 360-sector projection to every gated
+ * candidate (shift search + default-parameter 2-D ICP), re-describes the moved clouds (EPSC / SEPSC / FEPSC),
+ * scores them against the stored descriptors, then appends the current keyframe.  Clouds are in the sensor
+ * frame; odom is the row-major 4x4 world pose.  The result mirrors the public members current_frame_id,
+ * matched_frame_id[] and matched_frame_transform[] (:121-123) in the reference push order
+ * (EPSC, SEPSC, FEPSC, POSE); ISC / SC / SSC descriptors are not part of this path. */
+typedef struct lisreg_loop_params {
+  int32_t use_epsc, use_sepsc, use_fepsc, use_pose;   /* UsingEPSCFlag .. UsingPoseFlag (config/params.yaml:22-28) */
+  float skip_neighbour_distance;                      /* 20   */
+  float inflation_covariance;                         /* 0.01 */
+  float distance_threshold;                           /* 0.75 */
+  int32_t reserved;
+} lisreg_loop_params;
+typedef struct lisreg_loop_match {
+  int32_t kind;        /* 0 EPSC, 1 SEPSC, 2 FEPSC, 3 POSE */
+  int32_t frame_id;    /* matched_frame_id */
+  double score;        /* descriptor score (POSE: the position distance) */
+  float T[16];         /* matched_frame_transform, row-major 4x4 */
+} lisreg_loop_match;
+typedef struct lisreg_loop_result {
+  int32_t current_frame_id, n_candidates, n_matched, reserved;
+  lisreg_loop_match match[4];
+} lisreg_loop_result;
+void lisreg_loop_params_default(lisreg_loop_params* p);
+int32_t lisreg_loop_create(lisreg_ctx* ctx, const lisreg_loop_params* prm, const uint8_t using_map[256], int32_t* det_id);
+int32_t lisreg_loop_destroy(lisreg_ctx* ctx, int32_t det_id);
+int32_t lisreg_loop_detect(lisreg_ctx* ctx, int32_t det_id, const float* corner, int32_t nc, const float* surf, int32_t ns,
+                           const float* sem, const uint16_t* sem_label, int32_t nsem, const float odom[16],
+                           lisreg_loop_result* res);
 
 /* ---- loop-closure ICP verification (B4) ----
  * Replaces the pcl::IterativeClosestPoint block of SubMapOdometryNode::detectLoopClosureForSubMap

@@ -38,18 +38,31 @@ __device__ __forceinline__ bool epsc_bin(float x, float y, int& bin) {
   return true;
 }
 
-// grid = nsubmaps, block = 256.  out: [n][3][1600] = epsc, sepsc, fepsc
-__global__ void k_epsc_describe(const EpscCloud* __restrict__ clouds, const uint8_t* __restrict__ using_map, uint8_t* __restrict__ out) {
-  const EpscCloud c = clouds[blockIdx.x];
+// grid = nsubmaps, block = 256.  out: [n][3][1600] = epsc, sepsc, fepsc.
+// xf (nullable): one row-major 4x4 transform per BLOCK (stride xf_stride floats) applied to every point before
+// binning - the fused pcl::transformPointCloud of loopDetection (epscGeneration.cpp:764-770), fp32, left to right;
+// block b then describes cloud b * cloud_stride (cloud_stride 0: every block re-describes cloud 0 under its own
+// transform, one block per loop candidate).
+__global__ void k_epsc_describe(const EpscCloud* __restrict__ clouds, const uint8_t* __restrict__ using_map, uint8_t* __restrict__ out,
+                                const float* __restrict__ xf, int xf_stride, int cloud_stride) {
+  const EpscCloud c = clouds[(size_t)blockIdx.x * cloud_stride];
   __shared__ unsigned esc[EPSC_SIZE], psc[EPSC_SIZE];
   __shared__ uint8_t s_epsc[EPSC_SIZE];
   __shared__ uint8_t s_lut[256];
+  __shared__ float sT[8];
+  if (threadIdx.x < 8) sT[threadIdx.x] = xf ? xf[(size_t)blockIdx.x * xf_stride + threadIdx.x] : (threadIdx.x == 0 || threadIdx.x == 5 ? 1.f : 0.f);
   s_lut[threadIdx.x & 255] = using_map[threadIdx.x & 255];
   for (int i = threadIdx.x; i < EPSC_SIZE; i += blockDim.x) { esc[i] = 0u; psc[i] = 0u; }
   __syncthreads();
+  const bool moved = xf != nullptr;
+  auto bin_of = [&](float4 p, int& bin) -> bool {
+    float x = p.x, y = p.y;
+    if (moved) { x = ((sT[0] * p.x + sT[1] * p.y) + sT[2] * p.z) + sT[3]; y = ((sT[4] * p.x + sT[5] * p.y) + sT[6] * p.z) + sT[7]; }
+    return epsc_bin(x, y, bin);
+  };
   int bin;
-  for (int i = threadIdx.x; i < c.nc; i += blockDim.x) { const float4 p = __ldg(&c.corner[i]); if (epsc_bin(p.x, p.y, bin)) atomicAdd(&esc[bin], 1u); }
-  for (int i = threadIdx.x; i < c.ns; i += blockDim.x) { const float4 p = __ldg(&c.surf[i]); if (epsc_bin(p.x, p.y, bin)) atomicAdd(&psc[bin], 1u); }
+  for (int i = threadIdx.x; i < c.nc; i += blockDim.x) { if (bin_of(__ldg(&c.corner[i]), bin)) atomicAdd(&esc[bin], 1u); }
+  for (int i = threadIdx.x; i < c.ns; i += blockDim.x) { if (bin_of(__ldg(&c.surf[i]), bin)) atomicAdd(&psc[bin], 1u); }
   __syncthreads();
   uint8_t* o = out + (size_t)blockIdx.x * 3 * EPSC_SIZE;
   for (int i = threadIdx.x; i < EPSC_SIZE; i += blockDim.x) {
@@ -61,8 +74,7 @@ __global__ void k_epsc_describe(const EpscCloud* __restrict__ clouds, const uint
   for (int i = threadIdx.x; i < EPSC_SIZE; i += blockDim.x) { esc[i] = 0u; psc[i] = 0u; }
   __syncthreads();
   for (int i = threadIdx.x; i < c.nsem; i += blockDim.x) {
-    const float4 p = __ldg(&c.sem[i]);
-    if (!epsc_bin(p.x, p.y, bin)) continue;
+    if (!bin_of(__ldg(&c.sem[i]), bin)) continue;
     const unsigned l = c.sem_label[i];
     const int cls = l < 256u ? s_lut[l] : 0;
     if (cls == 40 || cls == 50) atomicAdd(&psc[bin], 1u);

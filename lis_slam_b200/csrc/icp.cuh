@@ -135,6 +135,38 @@ __device__ inline void icp_jacobi4(double* A, double* W, double* V) {
 
 struct IcpScratch { double sums[ICP_NSUM]; double N[16], W[4], V[16]; };
 
+// rigid fit of (source -> target) from the 17 correspondence sums (sum p, sum q, sum q p^T, sum d^2, n):
+// means, cross-covariance, optimal rotation by Horn's quaternion form (4x4 fp64 Jacobi == Umeyama/SVD with the
+// determinant fix), rounded to fp32 like PCL's Matrix4f.  T = row-major 4x4.
+__device__ inline void icp_rigid_from_sums(IcpScratch& sc, double n, float* T) {
+  double mp[3], mq[3], H[9];
+  for (int a = 0; a < 3; a++) { mp[a] = sc.sums[a] / n; mq[a] = sc.sums[3 + a] / n; }
+  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) H[a * 3 + b] = sc.sums[6 + a * 3 + b] / n - mq[a] * mp[b];   // dst x src^T
+  {
+    const double Sxx = H[0], Sxy = H[3], Sxz = H[6], Syx = H[1], Syy = H[4], Syz = H[7], Szx = H[2], Szy = H[5], Szz = H[8];
+    const double N[16] = {Sxx + Syy + Szz, Syz - Szy, Szx - Sxz, Sxy - Syx,
+                          Syz - Szy, Sxx - Syy - Szz, Sxy + Syx, Szx + Sxz,
+                          Szx - Sxz, Sxy + Syx, -Sxx + Syy - Szz, Syz + Szy,
+                          Sxy - Syx, Szx + Sxz, Syz + Szy, -Sxx - Syy + Szz};
+    for (int i = 0; i < 16; i++) sc.N[i] = N[i];
+  }
+  icp_jacobi4(sc.N, sc.W, sc.V);
+  int b = 0; for (int i = 1; i < 4; i++) if (sc.W[i] > sc.W[b]) b = i;
+  double q0 = sc.V[0 * 4 + b], q1 = sc.V[1 * 4 + b], q2 = sc.V[2 * 4 + b], q3 = sc.V[3 * 4 + b];
+  const double nq = sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+  q0 /= nq; q1 /= nq; q2 /= nq; q3 /= nq;
+  double R[9];
+  R[0] = q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3; R[1] = 2 * (q1 * q2 - q0 * q3); R[2] = 2 * (q1 * q3 + q0 * q2);
+  R[3] = 2 * (q1 * q2 + q0 * q3); R[4] = q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3; R[5] = 2 * (q2 * q3 - q0 * q1);
+  R[6] = 2 * (q1 * q3 - q0 * q2); R[7] = 2 * (q2 * q3 + q0 * q1); R[8] = q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3;
+  for (int i = 0; i < 16; i++) T[i] = 0.f;
+  for (int a = 0; a < 3; a++) {
+    for (int c = 0; c < 3; c++) T[a * 4 + c] = (float)R[a * 3 + c];
+    T[a * 4 + 3] = (float)(mq[a] - (R[a * 3] * mp[0] + R[a * 3 + 1] * mp[1] + R[a * 3 + 2] * mp[2]));
+  }
+  T[15] = 1.f;
+}
+
 // one warp per pair.  FITNESS: only finalises the fitness score.
 template <bool FITNESS>
 __global__ void k_icp_solve(IcpState* __restrict__ states, IcpParamsDev prm, const double* __restrict__ partials, int nblk, int P) {
@@ -156,33 +188,8 @@ __global__ void k_icp_solve(IcpState* __restrict__ states, IcpParamsDev prm, con
   if (FITNESS) { st.fitness = n > 0 ? sc.sums[15] / n : 1.7976931348623157e308; states[p] = st; return; }
   st.n_corr = (int)n;
   if (n < 3) { st.converged = 0; st.done = 1; st.pending = 0; states[p] = st; return; }   // min_number_correspondences_ = 3
-  double mp[3], mq[3], H[9];
-  for (int a = 0; a < 3; a++) { mp[a] = sc.sums[a] / n; mq[a] = sc.sums[3 + a] / n; }
-  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) H[a * 3 + b] = sc.sums[6 + a * 3 + b] / n - mq[a] * mp[b];   // dst x src^T
-  {
-    const double Sxx = H[0], Sxy = H[3], Sxz = H[6], Syx = H[1], Syy = H[4], Syz = H[7], Szx = H[2], Szy = H[5], Szz = H[8];
-    const double N[16] = {Sxx + Syy + Szz, Syz - Szy, Szx - Sxz, Sxy - Syx,
-                          Syz - Szy, Sxx - Syy - Szz, Sxy + Syx, Szx + Sxz,
-                          Szx - Sxz, Sxy + Syx, -Sxx + Syy - Szz, Syz + Szy,
-                          Sxy - Syx, Szx + Sxz, Syz + Szy, -Sxx - Syy + Szz};
-    for (int i = 0; i < 16; i++) sc.N[i] = N[i];
-  }
-  icp_jacobi4(sc.N, sc.W, sc.V);
-  int b = 0; for (int i = 1; i < 4; i++) if (sc.W[i] > sc.W[b]) b = i;
-  double q0 = sc.V[0 * 4 + b], q1 = sc.V[1 * 4 + b], q2 = sc.V[2 * 4 + b], q3 = sc.V[3 * 4 + b];
-  const double nq = sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
-  q0 /= nq; q1 /= nq; q2 /= nq; q3 /= nq;
-  double R[9];
-  R[0] = q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3; R[1] = 2 * (q1 * q2 - q0 * q3); R[2] = 2 * (q1 * q3 + q0 * q2);
-  R[3] = 2 * (q1 * q2 + q0 * q3); R[4] = q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3; R[5] = 2 * (q2 * q3 - q0 * q1);
-  R[6] = 2 * (q1 * q3 - q0 * q2); R[7] = 2 * (q2 * q3 + q0 * q1); R[8] = q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3;
   float T[16];
-  for (int i = 0; i < 16; i++) T[i] = 0.f;
-  for (int a = 0; a < 3; a++) {
-    for (int c = 0; c < 3; c++) T[a * 4 + c] = (float)R[a * 3 + c];
-    T[a * 4 + 3] = (float)(mq[a] - (R[a * 3] * mp[0] + R[a * 3 + 1] * mp[1] + R[a * 3 + 2] * mp[2]));
-  }
-  T[15] = 1.f;
+  icp_rigid_from_sums(sc, n, T);
   float F[16];
   for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { float s = 0.f; for (int k = 0; k < 4; k++) s += T[i * 4 + k] * st.Tfinal[k * 4 + j]; F[i * 4 + j] = s; }
   for (int i = 0; i < 16; i++) { st.Tfinal[i] = F[i]; st.Tpend[i] = T[i]; }

@@ -16,6 +16,7 @@
 #include "voxel.cuh"
 #include "epsc.cuh"
 #include "icp.cuh"
+#include "loop.cuh"
 
 using namespace lisreg;
 
@@ -93,8 +94,25 @@ struct lisreg_ctx {
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_ev;
   PinBuf h_desc;       // pinned descriptor staging of the arena entry points (one slice per chunk)
-  int e2e_chunk = 32;  // frames per chunk (LISREG_E2E_CHUNK; 0 = one copy, no overlap)
+  int e2e_chunk = 128; // frames per chunk (LISREG_E2E_CHUNK; 0 = one copy, no overlap)
+  // asynchronous submit / wait pipeline: two slots, each with its own staging arena, result buffers and work set
+  // (ws[1 + slot]); the upload of one batch overlaps the compute of the other
+  struct AsyncSlot { DevBuf d_stage, d_res; PinBuf h_out, h_desc; cudaEvent_t done = nullptr; bool busy = false; int F = 0; };
+  AsyncSlot slot[2];
+  int next_slot = 0;
   int n_sm = 148;
+  struct LoopDet {
+    bool used = false;
+    lisreg_loop_params prm{};
+    int n = 0, cap = 0;                    // keyframes stored / capacity of the device history
+    float4* d_proj = nullptr;              // [cap][360] sector projections
+    uint8_t* d_desc = nullptr;             // [cap][3][1600] EPSC / SEPSC / FEPSC
+    uint8_t* d_lut = nullptr;              // 256-entry using_label LUT
+    std::vector<double> travel, px, py;    // travelDistanceArr, posArr (host bookkeeping, a few scalars per keyframe)
+    std::vector<float> yaw;                // yawArr
+  };
+  std::vector<LoopDet> loops;
+  DevBuf d_loop;                           // per-call scratch of lisreg_loop_detect
   int knn_noskip = 0;   // LISREG_KNN_NOSKIP=1: search every query from scratch at every iteration (parity check of the CHECK path)
   // profiling
   bool prof_on = false;
@@ -353,7 +371,10 @@ void lisreg_destroy(lisreg_ctx* ctx) {
   for (DevBuf* b : {&ctx->d_stage, &ctx->d_logs, &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox, &ctx->d_epsc, &ctx->d_epsc2, &ctx->d_icp}) b->release();
   for (int i = 0; i < 3; i++) { if (i > 0 && ctx->ws[i].stream) { cudaStreamSynchronize(ctx->ws[i].stream); cudaStreamDestroy(ctx->ws[i].stream); } ctx->ws[i].release(); }
   ctx->h_stage.release(); ctx->h_out.release(); ctx->h_desc.release();
+  for (auto& L : ctx->loops) if (L.used) { cudaFree(L.d_proj); cudaFree(L.d_desc); cudaFree(L.d_lut); }
+  ctx->d_loop.release();
   for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
+  for (auto& sl : ctx->slot) { sl.d_stage.release(); sl.d_res.release(); sl.h_out.release(); sl.h_desc.release(); if (sl.done) cudaEventDestroy(sl.done); }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& p : ctx->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : ctx->ev_free) cudaEventDestroy(e);
@@ -816,7 +837,7 @@ static int run_voxel(lisreg_ctx* ctx, VoxSeg* d_segs, int nseg, int max_n, doubl
   k_vox_keys<<<dim3(pblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
   for (int pass = 0; pass < 4; pass++) {
     k_rs_hist<<<dim3(nblk, nseg), RS_THREADS, 0, st>>>(d_segs, 8 * pass, pass & 1); LAUNCH_CK();
-    k_rs_scan<<<nseg, 1024, 0, st>>>(d_segs); LAUNCH_CK();
+    k_rs_scan<<<nseg, 1024, 0, st>>>(d_segs, 8 * pass); LAUNCH_CK();
     k_rs_scatter<<<dim3(nblk, nseg), RS_THREADS, 0, st>>>(d_segs, 8 * pass, pass & 1); LAUNCH_CK();
   }
   k_vox_heads<<<nseg, 1024, 0, st>>>(d_segs); LAUNCH_CK();
@@ -1034,6 +1055,59 @@ int32_t lisreg_frames_batch_arena(lisreg_ctx* ctx, int32_t F, const lisreg_frame
   return worst;
 }
 
+int32_t lisreg_frames_batch_submit(lisreg_ctx* ctx, int32_t F, const lisreg_frame_item* items, const void* host_arena,
+                                   uint64_t arena_bytes, const float* pose6xF, const lisreg_frame_params* prm, int32_t* ticket) {
+  if (!ctx || F <= 0 || !items || !host_arena || !pose6xF || !prm || !ticket) return fail(ctx, LISREG_ERR_ARG, "lisreg_frames_batch_submit: bad argument");
+  if (prm->lm.max_iters <= 0 || prm->lm.max_iters > LISREG_MAX_ITERS) return fail(ctx, LISREG_ERR_ARG, "max_iters must be in 1..%d", LISREG_MAX_ITERS);
+  CK(cudaSetDevice(ctx->device));
+  const int si = ctx->next_slot;
+  lisreg_ctx::AsyncSlot& sl = ctx->slot[si];
+  if (sl.busy) return fail(ctx, LISREG_ERR_ARG, "lisreg_frames_batch_submit: both pipeline slots are in flight, wait for a ticket first");
+  WorkSet& w = ctx->ws[1 + si];
+  if (!w.stream) CK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+  if (!sl.done) CK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  int rc = sync_maps(ctx);
+  if (rc) return rc;
+  const size_t head = (sizeof(float) * 6 * (size_t)F + 255) & ~size_t(255);
+  CK(sl.d_stage.reserve(head + (size_t)arena_bytes + 16));
+  CK(sl.d_res.reserve(sizeof(lisreg_lm_result) * (size_t)F));
+  CK(sl.h_out.reserve(sizeof(lisreg_lm_result) * (size_t)F + head));
+  CK(sl.h_desc.reserve(frame_desc_bytes(F)));
+  char* d = (char*)sl.d_stage.p;
+  // the guesses go through the slot's pinned buffer: the caller may reuse its array as soon as this call returns
+  float* h_pose = (float*)((char*)sl.h_out.p + sizeof(lisreg_lm_result) * (size_t)F);
+  memcpy(h_pose, pose6xF, sizeof(float) * 6 * (size_t)F);
+  CK(cudaMemcpyAsync(d, h_pose, sizeof(float) * 6 * (size_t)F, cudaMemcpyHostToDevice, w.stream));
+  CK(cudaMemcpyAsync(d + head, host_arena, (size_t)arena_bytes, cudaMemcpyHostToDevice, w.stream));
+  ctx->cur = &w;
+  rc = run_frames(ctx, F, items, d + head, arena_bytes, (float*)d, prm, (lisreg_lm_result*)sl.d_res.p, (char*)sl.h_desc.p);
+  ctx->cur = &ctx->ws[0];
+  if (rc) { cudaStreamSynchronize(w.stream); return rc; }
+  CK(cudaMemcpyAsync(sl.h_out.p, sl.d_res.p, sizeof(lisreg_lm_result) * (size_t)F, cudaMemcpyDeviceToHost, w.stream));
+  CK(cudaEventRecord(sl.done, w.stream));
+  sl.busy = true; sl.F = F;
+  *ticket = si;
+  ctx->next_slot = si ^ 1;
+  return LISREG_OK;
+}
+
+int32_t lisreg_frames_batch_wait(lisreg_ctx* ctx, int32_t ticket, float* pose6xF, lisreg_lm_result* resxF) {
+  if (!ctx || ticket < 0 || ticket > 1 || !pose6xF || !resxF) return fail(ctx, LISREG_ERR_ARG, "lisreg_frames_batch_wait: bad argument");
+  lisreg_ctx::AsyncSlot& sl = ctx->slot[ticket];
+  if (!sl.busy) return fail(ctx, LISREG_ERR_ARG, "lisreg_frames_batch_wait: ticket %d is not in flight", ticket);
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventSynchronize(sl.done));
+  sl.busy = false;
+  const lisreg_lm_result* hr = (const lisreg_lm_result*)sl.h_out.p;
+  int worst = LISREG_OK;
+  for (int b = 0; b < sl.F; b++) {
+    resxF[b] = hr[b];
+    memcpy(pose6xF + 6 * (size_t)b, hr[b].pose, sizeof(float) * 6);
+    worst = std::max(worst, hr[b].status);
+  }
+  return worst;
+}
+
 // ------------------------------------------------------------------------------------------------
 // EPSC
 // ------------------------------------------------------------------------------------------------
@@ -1069,7 +1143,7 @@ int32_t lisreg_epsc_describe(lisreg_ctx* ctx, int32_t n, const lisreg_epsc_cloud
     hc[i] = e;
   }
   CK(cudaMemcpyAsync(d, h, off, cudaMemcpyHostToDevice, st));
-  k_epsc_describe<<<n, 256, 0, st>>>((const EpscCloud*)(d + o_desc), (const uint8_t*)d, (uint8_t*)ctx->d_epsc.p); LAUNCH_CK();
+  k_epsc_describe<<<n, 256, 0, st>>>((const EpscCloud*)(d + o_desc), (const uint8_t*)d, (uint8_t*)ctx->d_epsc.p, nullptr, 0, 1); LAUNCH_CK();
   CK(ctx->h_out.reserve(3 * (size_t)EPSC_SIZE * n));
   CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_epsc.p, 3 * (size_t)EPSC_SIZE * n, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -1110,6 +1184,169 @@ int32_t lisreg_epsc_score_all(lisreg_ctx* ctx, const uint8_t* desc, int32_t N, i
   CK(cudaMemcpyAsync(score, d + bd + bi, bs, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(shift, d + bd + bi + bs, bh, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return LISREG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// EPSC loop detector (B3)
+// ------------------------------------------------------------------------------------------------
+void lisreg_loop_params_default(lisreg_loop_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->use_fepsc = 1;                          // config/params.yaml:22-28: only UsingFEPSCFlag is true
+  p->skip_neighbour_distance = 20.0f;        // SKIP_NEIBOUR_DISTANCE  (epscGeneration.h:9)
+  p->inflation_covariance = 0.01f;           // INFLATION_COVARIANCE   (:11)
+  p->distance_threshold = 0.75f;             // DISTANCE_THRESHOLD     (:16)
+}
+
+int32_t lisreg_loop_create(lisreg_ctx* ctx, const lisreg_loop_params* prm, const uint8_t using_map[256], int32_t* det_id) {
+  if (!ctx || !prm || !using_map || !det_id) return fail(ctx, LISREG_ERR_ARG, "lisreg_loop_create: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  int slot = -1;
+  for (size_t i = 0; i < ctx->loops.size(); i++) if (!ctx->loops[i].used) { slot = (int)i; break; }
+  if (slot < 0) { ctx->loops.emplace_back(); slot = (int)ctx->loops.size() - 1; }
+  lisreg_ctx::LoopDet& L = ctx->loops[slot];
+  L = lisreg_ctx::LoopDet();
+  L.prm = *prm;
+  CK(cudaMalloc(&L.d_lut, 256));
+  CK(cudaMemcpyAsync(L.d_lut, using_map, 256, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  L.used = true;
+  *det_id = slot;
+  return LISREG_OK;
+}
+
+int32_t lisreg_loop_destroy(lisreg_ctx* ctx, int32_t det_id) {
+  if (!ctx || det_id < 0 || det_id >= (int)ctx->loops.size() || !ctx->loops[det_id].used) return fail(ctx, LISREG_ERR_ARG, "lisreg_loop_destroy: bad detector id");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  lisreg_ctx::LoopDet& L = ctx->loops[det_id];
+  cudaFree(L.d_proj); cudaFree(L.d_desc); cudaFree(L.d_lut);
+  L = lisreg_ctx::LoopDet();
+  return LISREG_OK;
+}
+
+static inline float f_sin64(float a) { return (float)sin((double)a); }
+static inline float f_cos64(float a) { return (float)cos((double)a); }
+
+// Identity; translation << dx, dy, 0; rotate(AngleAxisf(angle, UnitZ))  (epscGeneration.cpp:822-826)
+static void loop_planar_transform(float dx, float dy, float angle, float* T) {
+  const float c = f_cos64(angle), s = f_sin64(angle);
+  for (int i = 0; i < 16; i++) T[i] = (i % 5 == 0) ? 1.f : 0.f;
+  T[0] = c; T[1] = -s; T[4] = s; T[5] = c; T[10] = (1.f - c) + c;
+  T[3] = dx; T[7] = dy; T[11] = 0.f;
+}
+
+int32_t lisreg_loop_detect(lisreg_ctx* ctx, int32_t det_id, const float* corner, int32_t nc, const float* surf, int32_t ns,
+                           const float* sem, const uint16_t* sem_label, int32_t nsem, const float odom[16], lisreg_loop_result* res) {
+  if (!ctx || det_id < 0 || det_id >= (int)ctx->loops.size() || !ctx->loops[det_id].used || !odom || !res ||
+      nc < 0 || ns < 0 || nsem < 0 || (nc && !corner) || (ns && !surf) || (nsem && (!sem || !sem_label)))
+    return fail(ctx, LISREG_ERR_ARG, "lisreg_loop_detect: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  lisreg_ctx::LoopDet& L = ctx->loops[det_id];
+  memset(res, 0, sizeof(*res));
+  // ---- pose bookkeeping (:687-701): pcl::getTranslationAndEulerAngles, travelled distance ----
+  const float x_t = odom[3], y_t = odom[7];
+  const float yaw_t = (float)atan2((double)odom[4], (double)odom[0]);
+  const double cx = x_t, cy = y_t;
+  if (L.travel.empty()) L.travel.push_back(0);
+  else { const double ex = L.px.back() - cx, ey = L.py.back() - cy; L.travel.push_back(L.travel.back() + sqrt(ex * ex + ey * ey + 0.0)); }
+  const int cur = L.n;
+  res->current_frame_id = cur;
+  // ---- travel gate (:736-741); posArr.back() is still the PREVIOUS keyframe here ----
+  std::vector<int> cand; std::vector<float> cand_yaw; std::vector<double> cand_pos;
+  for (int i = 0; i < cur; i++) {
+    const double delta_travel = L.travel.back() - L.travel[i];
+    const double qx = L.px[i] - L.px.back(), qy = L.py[i] - L.py.back();
+    const double pos_distance = sqrt(qx * qx + qy * qy + 0.0);
+    if (delta_travel > (double)L.prm.skip_neighbour_distance && pos_distance < delta_travel * (double)L.prm.inflation_covariance) {
+      cand.push_back(i); cand_yaw.push_back(yaw_t - L.yaw[i]); cand_pos.push_back(pos_distance);
+    }
+  }
+  const int P = (int)cand.size();
+  res->n_candidates = P;
+  // ---- stage the three clouds (one pinned buffer -> one H2D copy) ----
+  auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+  const size_t o_c = 0, o_s = o_c + al(16 * (size_t)nc), o_m = o_s + al(16 * (size_t)ns), o_l = o_m + al(16 * (size_t)nsem),
+               o_desc = o_l + al(2 * (size_t)nsem), o_cid = o_desc + al(sizeof(EpscCloud)), o_cyaw = o_cid + al(4 * (size_t)std::max(P, 1)),
+               in_total = o_cyaw + al(4 * (size_t)std::max(P, 1));
+  CK(ctx->h_stage.reserve(in_total));
+  CK(ctx->d_stage.reserve(in_total));
+  char* h = (char*)ctx->h_stage.p; char* d = (char*)ctx->d_stage.p;
+  if (nc) memcpy(h + o_c, corner, 16 * (size_t)nc);
+  if (ns) memcpy(h + o_s, surf, 16 * (size_t)ns);
+  if (nsem) { memcpy(h + o_m, sem, 16 * (size_t)nsem); memcpy(h + o_l, sem_label, 2 * (size_t)nsem); }
+  EpscCloud ec{};
+  ec.corner = (const float4*)(d + o_c); ec.surf = (const float4*)(d + o_s); ec.sem = (const float4*)(d + o_m);
+  ec.sem_label = (const uint16_t*)(d + o_l); ec.nc = nc; ec.ns = ns; ec.nsem = nsem;
+  memcpy(h + o_desc, &ec, sizeof(ec));
+  if (P) { memcpy(h + o_cid, cand.data(), 4 * (size_t)P); memcpy(h + o_cyaw, cand_yaw.data(), 4 * (size_t)P); }
+  CK(cudaMemcpyAsync(d, h, in_total, cudaMemcpyHostToDevice, st));
+  // scratch: current projection, per-candidate align / score results, per-candidate descriptors of the moved cloud
+  const size_t s_proj = 0, s_align = s_proj + al(sizeof(float4) * LOOP_SECT), s_score = s_align + al(sizeof(LoopAlignOut) * (size_t)std::max(P, 1)),
+               s_cdesc = s_score + al(sizeof(LoopScoreOut) * (size_t)std::max(P, 1)), s_total = s_cdesc + al(3 * (size_t)EPSC_SIZE * std::max(P, 1));
+  CK(ctx->d_loop.reserve(s_total));
+  char* sc = (char*)ctx->d_loop.p;
+  float4* d_curproj = (float4*)(sc + s_proj);
+  k_loop_project<<<1, 256, 0, st>>>((const float4*)(d + o_m), (const uint16_t*)(d + o_l), nsem, d_curproj); LAUNCH_CK();
+  std::vector<LoopAlignOut> ha((size_t)P); std::vector<LoopScoreOut> hs((size_t)P);
+  if (P) {
+    k_loop_align<<<P, LOOP_THREADS, 0, st>>>(L.d_proj, d_curproj, (const int*)(d + o_cid), (const float*)(d + o_cyaw), (LoopAlignOut*)(sc + s_align)); LAUNCH_CK();
+    k_epsc_describe<<<P, 256, 0, st>>>((const EpscCloud*)(d + o_desc), L.d_lut, (uint8_t*)(sc + s_cdesc),
+                                       (const float*)(sc + s_align), (int)(sizeof(LoopAlignOut) / sizeof(float)), 0); LAUNCH_CK();
+    k_loop_score<<<P, 64, 0, st>>>((const uint8_t*)(sc + s_cdesc), L.d_desc, (const int*)(d + o_cid), (LoopScoreOut*)(sc + s_score)); LAUNCH_CK();
+    CK(cudaMemcpyAsync(ha.data(), sc + s_align, sizeof(LoopAlignOut) * (size_t)P, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hs.data(), sc + s_score, sizeof(LoopScoreOut) * (size_t)P, cudaMemcpyDeviceToHost, st));
+  }
+  // ---- append the current keyframe to the device history (:899-967): projection + descriptors of the UNmoved clouds ----
+  if (L.n == L.cap) {
+    const int ncap = std::max(256, 2 * L.cap);
+    float4* np = nullptr; uint8_t* nd = nullptr;
+    CK(cudaMalloc(&np, sizeof(float4) * LOOP_SECT * (size_t)ncap));
+    CK(cudaMalloc(&nd, 3 * (size_t)EPSC_SIZE * ncap));
+    if (L.n) {
+      CK(cudaMemcpyAsync(np, L.d_proj, sizeof(float4) * LOOP_SECT * (size_t)L.n, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(nd, L.d_desc, 3 * (size_t)EPSC_SIZE * L.n, cudaMemcpyDeviceToDevice, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    cudaFree(L.d_proj); cudaFree(L.d_desc);
+    L.d_proj = np; L.d_desc = nd; L.cap = ncap;
+  }
+  CK(cudaMemcpyAsync(L.d_proj + (size_t)LOOP_SECT * L.n, d_curproj, sizeof(float4) * LOOP_SECT, cudaMemcpyDeviceToDevice, st));
+  k_epsc_describe<<<1, 256, 0, st>>>((const EpscCloud*)(d + o_desc), L.d_lut, L.d_desc + 3 * (size_t)EPSC_SIZE * L.n, nullptr, 0, 1); LAUNCH_CK();
+  CK(cudaStreamSynchronize(st));
+  L.px.push_back(cx); L.py.push_back(cy); L.yaw.push_back(yaw_t); L.n++;
+  // ---- best candidate per descriptor kind (:812-897): first maximum above the threshold wins ----
+  const int use[3] = {L.prm.use_epsc, L.prm.use_sepsc, L.prm.use_fepsc};
+  int best_id[3] = {-1, -1, -1}; double best_score[3] = {0, 0, 0}; float best_T[3][16];
+  double min_distance = 1000000; int best_pose = -1;
+  const double sector_step = 2 * 3.14159265358979323846 / 80;
+  for (int k = 0; k < P; k++) {
+    for (int kind = 0; kind < 3; kind++) {
+      if (!use[kind]) continue;
+      const int sad = hs[k].sad[kind];
+      const double score = sad >= 0 ? 1 - (double)sad / (80 * 20 * 255) : 1 - 1.0;
+      if (score > (double)L.prm.distance_threshold && score > best_score[kind]) {
+        best_score[kind] = score; best_id[kind] = cand[k];
+        // EPSC rotates by yaw_diff + shift (:816-829), SEPSC by the ICP yaw + shift (:837-850), FEPSC by the ICP yaw (:857-869)
+        double a = kind == 0 ? (double)cand_yaw[k] : (double)ha[k].yaw;
+        if (kind != 2 && sad >= 0) a = a + hs[k].shift[kind] * sector_step;
+        loop_planar_transform(ha[k].diff_x, ha[k].diff_y, (float)a, best_T[kind]);
+      }
+    }
+    if (L.prm.use_pose && cand_pos[k] < min_distance) { min_distance = cand_pos[k]; best_pose = k; }
+  }
+  int m = 0;
+  for (int kind = 0; kind < 3; kind++) {
+    if (!use[kind] || best_id[kind] < 0) continue;
+    res->match[m].kind = kind; res->match[m].frame_id = best_id[kind]; res->match[m].score = best_score[kind];
+    memcpy(res->match[m].T, best_T[kind], sizeof(float) * 16); m++;
+  }
+  if (L.prm.use_pose && best_pose >= 0) {
+    res->match[m].kind = 3; res->match[m].frame_id = cand[best_pose]; res->match[m].score = min_distance;
+    memcpy(res->match[m].T, ha[best_pose].T, sizeof(float) * 16); m++;
+  }
+  res->n_matched = m;
   return LISREG_OK;
 }
 

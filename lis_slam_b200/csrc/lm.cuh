@@ -264,7 +264,8 @@ constexpr int LM_MAX_TILE = 512;
 //                memory and walked as ONE candidate list, so a warp iterates max(total) times instead of
 //                sum(max per row) times - with a two-candidates-ahead prefetch; queries whose 5th neighbour may
 //                lie outside the block -> shell list
-//   k_knn_search<SHELL>  listed queries: ball walk (grid.cuh knn_ball_walk) with row / cell pruning; also gives
+//   k_knn_search<SHELL>  deferred queries: flattened scan of the row streaks inside the ball that can still hold a
+//                neighbour (knn6_wide_flat; sequential knn_ball_walk as the fallback for tiny cells); also gives
 //                rejected queries a bound so that they are not searched again either
 // ---------------------------------------------------------------------------------------------------------
 struct KnnState { float x, y, z, s; };   // searched position q_ref and safe radius: > 0 accepted (bound of every non-neighbour),
@@ -290,6 +291,35 @@ __device__ __forceinline__ float knn_dist2(float qx, float qy, float qz, float4 
   const float dx = qx - m.x, dy = qy - m.y, dz = qz - m.z;
   float d = dx * dx; d = d + dy * dy; d = d + dz * dz;   // FLANN L2 functor op order, no FMA
   return d;
+}
+
+// walks the nr candidate ranges staged in this thread's column of the shared range table (stride LM_THREADS) as ONE
+// list.  Software pipeline: c0 is processed while c1 and c2 are in flight.  adv() steps the cursor (p, e, k) to the
+// next candidate of the flattened list; past the end it keeps returning the last valid position (harmless
+// re-load) and `left` counts what is really there.  Ranges must be in ascending position order (see
+// knn6_insert_mono).
+__device__ __forceinline__ void knn6_scan_ranges(const float4* __restrict__ pts, const uint2* rng, int nr, float qx, float qy, float qz,
+                                                 float (&bd)[6], unsigned (&bp)[6]) {
+  if (nr <= 0) return;
+  int left = 0;
+  for (int k = 0; k < nr; k++) { const uint2 r = rng[k * LM_THREADS]; left += (int)(r.y - r.x); }
+  uint2 r0 = rng[0];
+  unsigned p = r0.x, e = r0.y; int k = 1;
+  auto adv = [&]() {
+    unsigned np = p + 1;
+    if (np == e && k < nr) { const uint2 r = rng[k * LM_THREADS]; k++; np = r.x; e = r.y; }
+    else if (np == e) { np = p; e = p + 1; }     // stay on the last candidate
+    p = np;
+  };
+  unsigned p0 = p; float4 c0 = __ldg(&pts[p]); adv();
+  unsigned p1 = p; float4 c1 = __ldg(&pts[p]); adv();
+  while (left > 0) {
+    const unsigned p2 = p; const float4 c2 = __ldg(&pts[p]); adv();
+    const float d = knn_dist2(qx, qy, qz, c0);
+    if (d < bd[5]) knn6_insert_mono(bd, bp, d, p0);
+    c0 = c1; p0 = p1; c1 = c2; p1 = p2;
+    left--;
+  }
 }
 
 // flattened 3x3x3 block scan; rng = this thread's column of the shared range table (stride LM_THREADS, 10 rows:
@@ -320,34 +350,62 @@ __device__ __forceinline__ bool knn6_block_flat(const GridDev& g, float qx, floa
       }
     }
   }
-  const float4* __restrict__ pts = g.pts;
-  if (nr > 0) {
-    // software pipeline: c0 is processed while c1 and c2 are in flight.  adv() steps the cursor (p, e, k) to the
-    // next candidate of the flattened list; past the end it keeps returning the last valid position (harmless
-    // re-load) and `left` counts what is really there.
-    int left = 0;
-    for (int k = 0; k < nr; k++) { const uint2 r = rng[k * LM_THREADS]; left += (int)(r.y - r.x); }
-    uint2 r0 = rng[0];
-    unsigned p = r0.x, e = r0.y; int k = 1;
-    auto adv = [&]() {
-      unsigned np = p + 1;
-      if (np == e && k < nr) { const uint2 r = rng[k * LM_THREADS]; k++; np = r.x; e = r.y; }
-      else if (np == e) { np = p; e = p + 1; }     // stay on the last candidate
-      p = np;
-    };
-    unsigned p0 = p; float4 c0 = __ldg(&pts[p]); adv();
-    unsigned p1 = p; float4 c1 = __ldg(&pts[p]); adv();
-    while (left > 0) {
-      const unsigned p2 = p; const float4 c2 = __ldg(&pts[p]); adv();
-      const float d = knn_dist2(qx, qy, qz, c0);
-      if (d < bd[5]) knn6_insert_mono(bd, bp, d, p0);
-      c0 = c1; p0 = p1; c1 = c2; p1 = p2;
-      left--;
-    }
-  }
+  knn6_scan_ranges(g.pts, rng, nr, qx, qy, qz, bd, bp);
   lb = knn_block_lb(g, minf);
   const float lb2 = lb * lb;
   return !(bd[4] < lb2 || lb2 >= gate);
+}
+
+// Deferred queries (the 5th neighbour may lie outside the 3x3x3 block): flattened scan of every row streak that
+// intersects the ball of radius Rn = min(sqrt(d5 of the block), sqrt(gate)) + KNN_PAD around the query - rows pruned
+// by their distance in y / z, streaks clipped in x - over the (2T+1)^2 rows of the Chebyshev-T block that contains the
+// ball.  Exact (the 5-NN of the block bound the true 5th distance; beyond the gate nothing matters) and every map
+// point NOT visited is farther than Rn, which the caller records as the bound.  KNN_WIDE_T = largest T staged in
+// shared memory (returns false beyond: the caller falls back to the sequential ball walk).
+constexpr int KNN_WIDE_T = 3;
+constexpr int KNN_WIDE_ROWS = 48;   // staged row streaks per query (48 KB of static shared memory per 128 threads); the 49 rows of T = 3
+                                    // never all intersect the ball (its corner rows are farther than any admissible radius)
+__device__ __forceinline__ bool knn6_wide_flat(const GridDev& g, float qx, float qy, float qz, float gate, float d5_block,
+                                               float (&bd)[6], unsigned (&bp)[6], uint2* rng, float& lbu) {
+#pragma unroll
+  for (int j = 0; j < 6; j++) { bd[j] = KNN_INF; bp[j] = 0xffffffffu; }
+  lbu = KNN_INF;
+  if (g.n <= 0) return true;
+  const float eps = 1e-3f;
+  const float fx = (qx - g.ox) * g.inv_h, fy = (qy - g.oy) * g.inv_h, fz = (qz - g.oz) * g.inv_h;
+  const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
+  const float rx = fx - (float)cx, ry = fy - (float)cy, rz = fz - (float)cz;
+  const float minf = fminf(fminf(fminf(rx, 1.f - rx), fminf(ry, 1.f - ry)), fminf(rz, 1.f - rz));
+  const float Rn = sqrtf(fminf(d5_block, gate)) + KNN_PAD;
+  // smallest T whose outside is farther than Rn: ((T + minf - eps) h >= Rn)
+  int T = (int)ceilf(Rn * g.inv_h - minf + eps);
+  if (T < 1) T = 1;
+  if (T > KNN_WIDE_T) return false;
+  int nr = 0;
+  const uint32_t* __restrict__ cs = g.cell_start;
+  for (int z = cz - T; z <= cz + T; z++) {
+    if (z < 0 || z >= g.nz) continue;
+    float dz = z < cz ? fz - (float)(z + 1) : (z > cz ? (float)z - fz : 0.f);
+    dz = dz - eps > 0.f ? dz - eps : 0.f;
+    for (int y = cy - T; y <= cy + T; y++) {
+      if (y < 0 || y >= g.ny) continue;
+      float dy = y < cy ? fy - (float)(y + 1) : (y > cy ? (float)y - fy : 0.f);
+      dy = dy - eps > 0.f ? dy - eps : 0.f;
+      const float rem = Rn * Rn - (dy * dy + dz * dz) * g.h * g.h;
+      if (rem < 0.f) continue;                                   // the whole row is out of reach
+      const float rad = sqrtf(rem) * g.inv_h + eps;              // reach along x, in cells
+      int xa = (int)floorf(fx - rad), xb = (int)floorf(fx + rad);
+      xa = xa > cx - T ? xa : cx - T; xb = xb < cx + T ? xb : cx + T;
+      xa = xa > 0 ? xa : 0; xb = xb < g.nx - 1 ? xb : g.nx - 1;
+      if (xa > xb) continue;
+      const int rowbase = (z * g.ny + y) * g.nx;
+      const uint32_t b = __ldg(&cs[rowbase + xa]), e = __ldg(&cs[rowbase + xb + 1]);
+      if (e > b) { if (nr == KNN_WIDE_ROWS) return false; rng[nr * LM_THREADS] = make_uint2(b, e); nr++; }
+    }
+  }
+  knn6_scan_ranges(g.pts, rng, nr, qx, qy, qz, bd, bp);
+  lbu = Rn;
+  return true;
 }
 
 // writes the result of a real search: neighbour positions (or -1 = rejected) and the refreshed state
@@ -488,7 +546,7 @@ k_knn_search(const RegDesc* __restrict__ descs, const RegState* __restrict__ sta
              float gate, int* __restrict__ nbr, KnnState* __restrict__ kstate, const unsigned* __restrict__ list,
              const int* __restrict__ counter, unsigned* __restrict__ shell_list, int* __restrict__ shell_counter,
              int max_tiles, int tile_shift) {
-  __shared__ uint2 s_rng[SHELL ? 1 : 10 * LM_THREADS];
+  __shared__ uint2 s_rng[(SHELL ? KNN_WIDE_ROWS : 9) * LM_THREADS];
   const int tile_pts = 1 << tile_shift;
   const int total = *counter;
   const int lane = threadIdx.x & 31;
@@ -514,17 +572,26 @@ k_knn_search(const RegDesc* __restrict__ descs, const RegState* __restrict__ sta
       int* tnbr = nbr + bt * 5 * tile_pts;
       KnnState* tstate = kstate + bt * tile_pts;
       if (SHELL) {
-        knn_key best[6];
-        const float lbu = knn_ball_walk<6, 4>(g, x0, y0, z0, gate, KNN_PAD, best);
-        const unsigned pos[5] = {(unsigned)knn_key_pos(best[0]), (unsigned)knn_key_pos(best[1]), (unsigned)knn_key_pos(best[2]),
-                                 (unsigned)knn_key_pos(best[3]), (unsigned)knn_key_pos(best[4])};
-        knn_commit(tnbr, tstate, tile_pts, ks.l, x0, y0, z0, gate, knn_key_d(best[4]), knn_key_d(best[5]), lbu, pos);
+        float bd[6]; unsigned bp[6]; float lbu;
+        const float d5_block = tstate[ks.l].s;      // left by the block scan that deferred this query
+        if (knn6_wide_flat(g, x0, y0, z0, gate, d5_block, bd, bp, s_rng + threadIdx.x, lbu)) {
+          const unsigned pos[5] = {bp[0], bp[1], bp[2], bp[3], bp[4]};
+          knn_commit(tnbr, tstate, tile_pts, ks.l, x0, y0, z0, gate, bd[4], bd[5], lbu, pos);
+        } else {                                     // ball too wide for the staged rows (tiny cells): sequential walk
+          knn_key best[6];
+          const float lb2 = knn_ball_walk<6, 4>(g, x0, y0, z0, gate, KNN_PAD, best);
+          const unsigned pos[5] = {(unsigned)knn_key_pos(best[0]), (unsigned)knn_key_pos(best[1]), (unsigned)knn_key_pos(best[2]),
+                                   (unsigned)knn_key_pos(best[3]), (unsigned)knn_key_pos(best[4])};
+          knn_commit(tnbr, tstate, tile_pts, ks.l, x0, y0, z0, gate, knn_key_d(best[4]), knn_key_d(best[5]), lb2, pos);
+        }
       } else {
         float bd[6]; unsigned bp[6]; float lb;
         need_shell = knn6_block_flat(g, x0, y0, z0, gate, bd, bp, s_rng + threadIdx.x, lb);
         if (!need_shell) {
           const unsigned pos[5] = {bp[0], bp[1], bp[2], bp[3], bp[4]};
           knn_commit(tnbr, tstate, tile_pts, ks.l, x0, y0, z0, gate, bd[4], bd[5], lb, pos);
+        } else {
+          tstate[ks.l].s = bd[4];                    // 5th best of the block: bounds the radius of the wide scan
         }
       }
     }
@@ -686,16 +753,20 @@ __global__ void k_selftest_smallmat(const float* __restrict__ A36, const float* 
 // safe (nullable, nq): the safe radius the search would record for the query.
 __global__ void __launch_bounds__(LM_THREADS)
 k_knn5(GridDev g, const float4* __restrict__ q, int nq, float gate, int* __restrict__ idx, float* __restrict__ sqd, float* __restrict__ safe) {
-  __shared__ uint2 s_rng[10 * LM_THREADS];
+  __shared__ uint2 s_rng[KNN_WIDE_ROWS * LM_THREADS];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   float4 p = q[i];
   float bd[6]; unsigned bp[6]; float lb;
   if (knn6_block_flat(g, p.x, p.y, p.z, gate, bd, bp, s_rng + threadIdx.x, lb)) {
-    knn_key best[6];
-    lb = knn_ball_walk<6, 4>(g, p.x, p.y, p.z, gate, KNN_PAD, best);
+    const float d5_block = bd[4];
+    // odd queries take the sequential ball walk so that the tests cover both deferred paths
+    if ((i & 1) || !knn6_wide_flat(g, p.x, p.y, p.z, gate, d5_block, bd, bp, s_rng + threadIdx.x, lb)) {
+      knn_key best[6];
+      lb = knn_ball_walk<6, 4>(g, p.x, p.y, p.z, gate, KNN_PAD, best);
 #pragma unroll
-    for (int j = 0; j < 6; j++) { bd[j] = knn_key_d(best[j]); bp[j] = (unsigned)knn_key_pos(best[j]); }
+      for (int j = 0; j < 6; j++) { bd[j] = knn_key_d(best[j]); bp[j] = (unsigned)knn_key_pos(best[j]); }
+    }
   }
   for (int j = 0; j < 5; j++) {
     const bool ok = bp[j] != 0xffffffffu && bd[j] < gate;

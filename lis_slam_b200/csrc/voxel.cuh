@@ -7,7 +7,7 @@
 // points of a voxel accumulated in ascending input index.
 //
 // Implementation: (1) per-cloud bounding box -> plan, (2) key = voxel index, value = point index,
-// (3) stable LSD radix sort (8-bit digits, 4 passes; per pass: tile histograms -> per-cloud scan ->
+// (3) stable LSD radix sort (8-bit digits, only the passes the largest voxel index needs; per pass: tile histograms -> per-cloud scan ->
 // stable scatter with warp match-any ranking), (4) head flags + per-cloud scan -> voxel starts,
 // (5) one thread per voxel sums its points in order.  The sorted order is also spatially coherent
 // (x fastest), which is what the kNN kernel wants from its query stream.
@@ -18,7 +18,7 @@
 
 namespace lisreg {
 
-struct VoxPlan { float inv; int minb[3]; int mul[3]; int overflow; };
+struct VoxPlan { float inv; int minb[3]; int mul[3]; int overflow; int npass; };   // npass: 8-bit radix passes the largest key needs
 
 struct VoxSeg {
   const float4* src;       // source cloud
@@ -99,8 +99,12 @@ __global__ void k_vox_plan(VoxSeg* segs, int nseg) {
       divb[d] = (int)floorf(mx[d] * p.inv) - p.minb[d] + 1;
     }
     p.mul[0] = 1; p.mul[1] = divb[0]; p.mul[2] = divb[0] * divb[1];
+    // keys are < divb0 * divb1 * divb2 (or < n in the overflow case): passes over all-zero high digits are skipped
+    const unsigned long long kmax = p.overflow ? (unsigned long long)n : (unsigned long long)divb[0] * (unsigned long long)divb[1] * (unsigned long long)divb[2];
+    p.npass = kmax > (1ull << 24) ? 4 : kmax > (1ull << 16) ? 3 : kmax > (1ull << 8) ? 2 : 1;
   } else {
     for (int d = 0; d < 3; d++) { p.minb[d] = 0; p.mul[d] = 0; }
+    p.npass = 0;
   }
   *s.plan = p;
 }
@@ -130,7 +134,7 @@ k_rs_hist(VoxSeg* segs, int shift, int flip) {
   const VoxSeg s = segs[blockIdx.y];
   const int n = vox_n(s);
   const int nblk = (n + RS_TILE - 1) / RS_TILE;
-  if ((int)blockIdx.x >= nblk) return;
+  if ((int)blockIdx.x >= nblk || shift >= 8 * s.plan->npass) return;
   const uint32_t* key = flip ? s.key_b : s.key_a;
   __shared__ uint32_t h[256];
   h[threadIdx.x] = 0;
@@ -145,8 +149,9 @@ k_rs_hist(VoxSeg* segs, int shift, int flip) {
 }
 
 // (3b) exclusive scan over the 256 * nblk counters of one cloud: one block per cloud
-__global__ void k_rs_scan(VoxSeg* segs) {
+__global__ void k_rs_scan(VoxSeg* segs, int shift) {
   const VoxSeg s = segs[blockIdx.x];
+  if (shift >= 8 * s.plan->npass) return;
   const int n = vox_n(s);
   const int nblk = (n + RS_TILE - 1) / RS_TILE;
   const int total = 256 * nblk;
@@ -178,7 +183,7 @@ k_rs_scatter(VoxSeg* segs, int shift, int flip) {
   const VoxSeg s = segs[blockIdx.y];
   const int n = vox_n(s);
   const int nblk = (n + RS_TILE - 1) / RS_TILE;
-  if ((int)blockIdx.x >= nblk) return;
+  if ((int)blockIdx.x >= nblk || shift >= 8 * s.plan->npass) return;
   const uint32_t* key = flip ? s.key_b : s.key_a;
   const uint32_t* val = flip ? s.val_b : s.val_a;
   uint32_t* okey = flip ? s.key_a : s.key_b;
@@ -232,28 +237,35 @@ k_rs_scatter(VoxSeg* segs, int shift, int flip) {
   }
 }
 
-// (4) voxel starts: one block (1024 threads) per cloud.  After 4 passes the sorted data is back in *_a.
+// (4) voxel starts: one block (1024 threads) per cloud.  After npass passes the sorted data is in *_a (even) or *_b (odd).
 __global__ void k_vox_heads(VoxSeg* segs) {
   const VoxSeg s = segs[blockIdx.x];
   const int n = vox_n(s);
-  __shared__ int sm[1024];
-  __shared__ int carry;
+  const uint32_t* skey = (s.plan->npass & 1) ? s.key_b : s.key_a;
+  __shared__ int s_w[32];
+  __shared__ int carry, s_tot;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   for (int base = 0; base < n; base += 1024) {
     const int i = base + threadIdx.x;
-    const int head = (i < n && (i == 0 || s.key_a[i] != s.key_a[i - 1])) ? 1 : 0;
-    sm[threadIdx.x] = head;
+    const int head = (i < n && (i == 0 || skey[i] != skey[i - 1])) ? 1 : 0;
+    // rank of a head = carry + heads before it: ballot inside the warp, the 32 warp totals scanned by warp 0
+    const unsigned m = __ballot_sync(0xffffffffu, head);
+    if (lane == 0) s_w[wid] = __popc(m);
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      const int t = threadIdx.x >= o ? sm[threadIdx.x - o] : 0;
-      __syncthreads();
-      sm[threadIdx.x] += t;
-      __syncthreads();
+    if (wid == 0) {
+      const int v = s_w[lane];
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      s_w[lane] = incl - v;                      // exclusive warp offsets
+      if (lane == 31) s_tot = incl;
     }
-    if (head) s.seg_start[carry + sm[threadIdx.x] - 1] = i;
     __syncthreads();
-    if (threadIdx.x == 1023) carry += sm[1023];
+    if (head) s.seg_start[carry + s_w[wid] + __popc(m & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += s_tot;
     __syncthreads();
   }
   if (threadIdx.x == 0) { s.seg_start[carry] = n; *s.out_n = carry; }
@@ -263,11 +275,22 @@ __global__ void k_vox_heads(VoxSeg* segs) {
 __global__ void k_vox_centroid(VoxSeg* segs) {
   const VoxSeg s = segs[blockIdx.y];
   const int m = *s.out_n;
+  const uint32_t* sval = (s.plan->npass & 1) ? s.val_b : s.val_a;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < m; v += gridDim.x * blockDim.x) {
     const int b = s.seg_start[v], e = s.seg_start[v + 1];
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-    for (int j = b; j < e; j++) {
-      const float4 p = vox_point(s, (int)s.val_a[j]);
+    int j = b;
+    // four gathers in flight; the fp32 accumulation keeps the ascending input order
+    for (; j + 4 <= e; j += 4) {
+      const float4 p0 = vox_point(s, (int)sval[j]), p1 = vox_point(s, (int)sval[j + 1]),
+                   p2 = vox_point(s, (int)sval[j + 2]), p3 = vox_point(s, (int)sval[j + 3]);
+      sx += p0.x; sy += p0.y; sz += p0.z; si += p0.w;
+      sx += p1.x; sy += p1.y; sz += p1.z; si += p1.w;
+      sx += p2.x; sy += p2.y; sz += p2.z; si += p2.w;
+      sx += p3.x; sy += p3.y; sz += p3.z; si += p3.w;
+    }
+    for (; j < e; j++) {
+      const float4 p = vox_point(s, (int)sval[j]);
       sx += p.x; sy += p.y; sz += p.z; si += p.w;
     }
     const float c = (float)(e - b);

@@ -87,6 +87,24 @@ class EpscCloud(C.Structure):
                 ("nc", C.c_int32), ("ns", C.c_int32), ("nsem", C.c_int32), ("reserved", C.c_int32)]
 
 
+class LoopParams(C.Structure):
+    _fields_ = [("use_epsc", C.c_int32), ("use_sepsc", C.c_int32), ("use_fepsc", C.c_int32), ("use_pose", C.c_int32),
+                ("skip_neighbour_distance", C.c_float), ("inflation_covariance", C.c_float), ("distance_threshold", C.c_float),
+                ("reserved", C.c_int32)]
+
+
+class LoopMatch(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("frame_id", C.c_int32), ("score", C.c_double), ("T", C.c_float * 16)]
+
+
+class LoopResult(C.Structure):
+    _fields_ = [("current_frame_id", C.c_int32), ("n_candidates", C.c_int32), ("n_matched", C.c_int32), ("reserved", C.c_int32),
+                ("match", LoopMatch * 4)]
+
+
+LOOP_KINDS = ("epsc", "sepsc", "fepsc", "pose")
+
+
 class IcpParams(C.Structure):
     _fields_ = [("max_corr_dist", C.c_float), ("max_iters", C.c_int32), ("trans_eps", C.c_double), ("fitness_eps", C.c_double)]
 
@@ -167,6 +185,10 @@ def lib():
         L.lisreg_frames_batch_dev.argtypes = [vp, i32, C.POINTER(FrameItem), vp, C.POINTER(FrameParams), vp]
         L.lisreg_frames_batch_arena.restype = i32
         L.lisreg_frames_batch_arena.argtypes = [vp, i32, C.POINTER(FrameItem), vp, C.c_uint64, fp, C.POINTER(FrameParams), C.POINTER(LmResult)]
+        L.lisreg_frames_batch_submit.restype = i32
+        L.lisreg_frames_batch_submit.argtypes = [vp, i32, C.POINTER(FrameItem), vp, C.c_uint64, fp, C.POINTER(FrameParams), C.POINTER(i32)]
+        L.lisreg_frames_batch_wait.restype = i32
+        L.lisreg_frames_batch_wait.argtypes = [vp, i32, fp, C.POINTER(LmResult)]
         L.lisreg_epsc_describe.restype = i32
         L.lisreg_epsc_describe.argtypes = [vp, i32, C.POINTER(EpscCloud), vp, vp, vp, vp]
         L.lisreg_epsc_score_all.restype = i32
@@ -174,6 +196,13 @@ def lib():
         L.lisreg_epsc_score_all_dev.restype = i32
         L.lisreg_epsc_score_all_dev.argtypes = [vp, vp, i32, i32, vp, vp, vp]
         L.lisreg_icp_params_default.argtypes = [C.POINTER(IcpParams)]
+        L.lisreg_loop_params_default.argtypes = [C.POINTER(LoopParams)]
+        L.lisreg_loop_create.restype = i32
+        L.lisreg_loop_create.argtypes = [vp, C.POINTER(LoopParams), C.POINTER(C.c_uint8), C.POINTER(i32)]
+        L.lisreg_loop_destroy.restype = i32
+        L.lisreg_loop_destroy.argtypes = [vp, i32]
+        L.lisreg_loop_detect.restype = i32
+        L.lisreg_loop_detect.argtypes = [vp, i32, fp, i32, fp, i32, fp, C.POINTER(C.c_uint16), i32, fp, C.POINTER(LoopResult)]
         L.lisreg_icp_verify_batch.restype = i32
         L.lisreg_icp_verify_batch.argtypes = [vp, i32, C.POINTER(IcpPair), C.POINTER(IcpParams), C.POINTER(IcpResult)]
         L.lisreg_selftest_smallmat.restype = i32
@@ -367,6 +396,16 @@ class Engine:
         return self._ck(lib().lisreg_frames_batch_arena(self._h, F, items, arena_ptr, arena_bytes,
                                                         pose.ctypes.data_as(C.POINTER(C.c_float)), C.byref(params), res))
 
+    def frames_batch_submit(self, items, F, arena_ptr, arena_bytes, pose, params):
+        """Asynchronous arena call: returns a ticket (two may be in flight); see lisreg_frames_batch_submit."""
+        t = C.c_int32(-1)
+        self._ck(lib().lisreg_frames_batch_submit(self._h, F, items, arena_ptr, arena_bytes,
+                                                  pose.ctypes.data_as(C.POINTER(C.c_float)), C.byref(params), C.byref(t)))
+        return t.value
+
+    def frames_batch_wait(self, ticket, pose, res):
+        return self._ck(lib().lisreg_frames_batch_wait(self._h, ticket, pose.ctypes.data_as(C.POINTER(C.c_float)), res))
+
     def frames_batch_dev(self, items, F, d_pose_ptr, params, d_res_ptr):
         return self._ck(lib().lisreg_frames_batch_dev(self._h, F, items, d_pose_ptr, C.byref(params), d_res_ptr))
 
@@ -393,6 +432,32 @@ class Engine:
     def target_create(self, pts):
         """Registers an ICP target cloud (stored as the 'surf' cloud of a map slot)."""
         return self.map_create(np.zeros((0, 4), np.float32), pts, gate_hint=1.0)
+
+    def loop_create(self, lut, use_epsc=False, use_sepsc=False, use_fepsc=True, use_pose=False):
+        """EPSCGeneration instance (loop detector) on the device; returns its id."""
+        prm = LoopParams()
+        lib().lisreg_loop_params_default(C.byref(prm))
+        prm.use_epsc, prm.use_sepsc, prm.use_fepsc, prm.use_pose = int(use_epsc), int(use_sepsc), int(use_fepsc), int(use_pose)
+        lut = np.ascontiguousarray(lut, np.uint8)
+        det = C.c_int32(-1)
+        self._ck(lib().lisreg_loop_create(self._h, C.byref(prm), lut.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(det)))
+        return det.value
+
+    def loop_destroy(self, det):
+        self._ck(lib().lisreg_loop_destroy(self._h, det))
+
+    def loop_detect(self, det, corner, surf, sem, sem_label, odom):
+        """EPSCGeneration::loopDetection. Returns (current_frame_id, n_candidates, [(kind, matched_id, score, T 4x4)])."""
+        c, s, m = _f4(corner), _f4(surf), _f4(sem)
+        lab = np.ascontiguousarray(sem_label, np.uint16)
+        od = np.ascontiguousarray(odom, np.float32).reshape(16)
+        res = LoopResult()
+        fpt = C.POINTER(C.c_float)
+        self._ck(lib().lisreg_loop_detect(self._h, det, c.ctypes.data_as(fpt), len(c), s.ctypes.data_as(fpt), len(s), m.ctypes.data_as(fpt),
+                                          lab.ctypes.data_as(C.POINTER(C.c_uint16)), len(m), od.ctypes.data_as(fpt), C.byref(res)))
+        out = [(LOOP_KINDS[res.match[i].kind], res.match[i].frame_id, res.match[i].score,
+                np.array(res.match[i].T, np.float32).reshape(4, 4)) for i in range(res.n_matched)]
+        return res.current_frame_id, res.n_candidates, out
 
     def icp_verify_batch(self, pairs, prm=None):
         """pairs: list of (src (n,4) already pre-transformed by the initial guess, target_id). Returns [IcpResult]."""

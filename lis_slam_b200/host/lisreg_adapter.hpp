@@ -17,6 +17,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <array>
 #include <vector>
 
 #include "../../include/lisreg.h"
@@ -127,6 +128,24 @@ class Registrar {
     check(lisreg_epsc_score_all(ctx_, desc, n, topk, idx.data(), score.data(), shift.data()));
   }
 
+  // pcl::IterativeClosestPoint block of detectLoopClosureForSubMap (subMapOptmizationNode.cpp:2763-2769, :2822-2855):
+  // `source` = current keyframe cloud already moved by the initial guess, `target` = candidate submap cloud.
+  // Returns hasConverged(); fitness = getFitnessScore(), T = getFinalTransformation() (row-major 4x4).
+  template <typename CloudS, typename CloudT>
+  bool icpVerify(const CloudS& source, const CloudT& target, float T[16], double& fitness) {
+    Packed s = pack_xyzi(source), t = pack_xyzi(target);
+    int32_t tid = -1;
+    check(lisreg_map_create(ctx_, nullptr, 0, t.xyzi.data(), t.n, 4.0f, &tid));
+    lisreg_icp_params ip; lisreg_icp_params_default(&ip);
+    lisreg_icp_pair pr; pr.src = s.xyzi.data(); pr.ns = s.n; pr.target_id = tid;
+    lisreg_icp_result r;
+    int rc = lisreg_icp_verify_batch(ctx_, 1, &pr, &ip, &r);
+    lisreg_map_destroy(ctx_, tid);
+    check(rc);
+    std::memcpy(T, r.T, sizeof(float) * 16); fitness = r.fitness;
+    return r.converged != 0;
+  }
+
   lisreg_ctx* ctx() { return ctx_; }
   float deltaR = 100.f, deltaT = 100.f;   // same members as the reference node (odomEstimationNode.cpp:70-71)
   bool isDegenerate() const { return is_degenerate_; }
@@ -147,6 +166,45 @@ class Registrar {
   lisreg_ctx* ctx_ = nullptr;
   int32_t map_id_ = -1;
   bool is_degenerate_ = false;
+};
+
+// Stand-in for the EPSCGeneration instance of loopClosureThread (subMapOptmizationNode.cpp:2332): same call, same
+// public members (epscGeneration.h:121-123, :155-158).  The history lives on the device.
+class LoopDetector {
+ public:
+  int current_frame_id = -1;
+  std::vector<int> matched_frame_id;
+  std::vector<std::array<float, 16>> matched_frame_transform;   // row-major 4x4 (Eigen::Affine3f::matrix() transposed)
+
+  LoopDetector(Registrar& reg, const uint8_t using_map[256], bool usingEPSC = false, bool usingSEPSC = false,
+               bool usingFEPSC = true, bool usingPose = false) : ctx_(reg.ctx()) {
+    lisreg_loop_params p; lisreg_loop_params_default(&p);
+    p.use_epsc = usingEPSC; p.use_sepsc = usingSEPSC; p.use_fepsc = usingFEPSC; p.use_pose = usingPose;
+    if (lisreg_loop_create(ctx_, &p, using_map, &id_) != LISREG_OK) throw std::runtime_error(std::string("lisreg: ") + lisreg_last_error(ctx_));
+  }
+  ~LoopDetector() { if (id_ >= 0) lisreg_loop_destroy(ctx_, id_); }
+  LoopDetector(const LoopDetector&) = delete;
+  LoopDetector& operator=(const LoopDetector&) = delete;
+
+  // void EPSCGeneration::loopDetection(corner_pc, surf_pc, semantic_pc, odom)  — odom = row-major 4x4 world pose
+  template <typename CloudI, typename CloudL>
+  void loopDetection(const CloudI& corner_pc, const CloudI& surf_pc, const CloudL& semantic_pc, const float odom[16]) {
+    Packed c = pack_xyzi(corner_pc), s = pack_xyzi(surf_pc), m = pack_xyzil(semantic_pc);
+    lisreg_loop_result r;
+    if (lisreg_loop_detect(ctx_, id_, c.xyzi.data(), c.n, s.xyzi.data(), s.n, m.xyzi.data(), m.aux.data(), m.n, odom, &r) < 0)
+      throw std::runtime_error(std::string("lisreg: ") + lisreg_last_error(ctx_));
+    current_frame_id = r.current_frame_id;
+    matched_frame_id.clear(); matched_frame_transform.clear();
+    for (int i = 0; i < r.n_matched; i++) {
+      matched_frame_id.push_back(r.match[i].frame_id);
+      std::array<float, 16> T; std::memcpy(T.data(), r.match[i].T, sizeof(float) * 16);
+      matched_frame_transform.push_back(T);
+    }
+  }
+
+ private:
+  lisreg_ctx* ctx_ = nullptr;
+  int32_t id_ = -1;
 };
 
 }  // namespace lisreg_host

@@ -17,7 +17,19 @@ int main(int argc, char** argv) {
     LISREG_CLOUD(PointXYZIL) lc, ls; lc.points.resize(4); ls.points.resize(4);
     r.scan2SubMapOptimizationLabelled(lc, ls, pose, 'B');
     int rc = r.scan2SubMapOptimization(sc, ss, pose);   // 10 surf points <= surfFeatureMinValidNum => "Not enough features"
-    std::printf("rc=%d\n", rc);
+    // loop detector stand-in: two empty keyframes, ids count up and nothing matches
+    uint8_t lut[256] = {0};
+    LoopDetector ld(r, lut);
+    float odom[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    ld.loopDetection(sc, ss, lc, odom); ld.loopDetection(sc, ss, lc, odom);
+    if (ld.current_frame_id != 1 || !ld.matched_frame_id.empty()) return 4;
+    float T[16]; double fit = 0;
+    LISREG_CLOUD(PointXYZI) a, b; a.points.resize(50); b.points.resize(60);
+    for (int i = 0; i < 50; i++) { a.points[i].x = 0.1f * i; a.points[i].y = 0.01f * (i % 7); }
+    for (int i = 0; i < 60; i++) { b.points[i].x = 0.1f * i + 0.02f; b.points[i].y = 0.01f * (i % 7); }
+    bool conv = r.icpVerify(a, b, T, fit);
+    std::printf("rc=%d icp conv=%d fitness=%g\n", rc, (int)conv, fit);
+    if (!conv || !(fit < 0.01)) return 5;
     return rc == LISREG_NOT_ENOUGH_FEATURES ? 0 : 3;
   }
   try { Registrar r(0); } catch (const std::exception& e) { std::printf("no device: %s\n", e.what()); return 0; }

@@ -91,3 +91,39 @@ def test_chunked_e2e_pipeline_is_bit_identical(monkeypatch):
     assert np.array_equal(out["0"][0], out["2"][0])
     assert out["0"][1] == out["2"][1]
     assert out["0"][1][2][0] == E.NOT_ENOUGH_FEATURES
+
+
+def test_submit_wait_pipeline_matches_blocking_call(engine):
+    """lisreg_frames_batch_submit / _wait (two batches in flight on private streams and work sets) must return exactly
+    what the blocking arena call returns, in ticket order, and refuse a third submit."""
+    import ctypes as C
+    m = local_map()
+    mid = engine.map_create(m["corner"], m["surf"], gate_hint=1.0)
+    s0, _, g0 = frame(0)
+    s1, _, g1 = frame(1)
+    prm = E.frame_params("A", early_exit=0, max_iters=5)
+    batches = [([s0, s1], [g0, g1]), ([s1, s0, s1], [g1, g0, g0])]
+    ref = [engine.frames_batch([(mid, s["pts"], s["ring"]) for s in sw], gs, prm) for sw, gs in batches]
+    packed = []
+    for sw, gs in batches:
+        chunks, off = [], 0
+        items = (E.FrameItem * len(sw))()
+        for i, s in enumerate(sw):
+            p = np.ascontiguousarray(s["pts"], np.float32); r = np.ascontiguousarray(s["ring"], np.uint16)
+            op = off; chunks.append(p.view(np.uint8).reshape(-1)); off += p.nbytes
+            orr = off; chunks.append(r.view(np.uint8).reshape(-1)); off += r.nbytes
+            pad = (-off) % 16
+            if pad:
+                chunks.append(np.zeros(pad, np.uint8)); off += pad
+            items[i] = E.FrameItem(op, orr, len(p), mid)
+        packed.append((items, np.concatenate(chunks), np.asarray(gs, np.float32).reshape(-1, 6).copy()))
+    tickets = [engine.frames_batch_submit(it, len(it), ar.ctypes.data, ar.nbytes, gs, prm) for it, ar, gs in packed]
+    assert sorted(tickets) == [0, 1]
+    with pytest.raises(Exception):
+        engine.frames_batch_submit(packed[0][0], 2, packed[0][1].ctypes.data, packed[0][1].nbytes, packed[0][2], prm)
+    for t, (it, ar, gs), (pose_ref, res_ref) in zip(tickets, packed, ref):
+        pose = np.zeros_like(gs); res = (E.LmResult * len(it))()
+        engine.frames_batch_wait(t, pose, res)
+        assert np.array_equal(pose, pose_ref)
+        assert [(r.status, r.iters, r.n_sel_last) for r in res] == [(r.status, r.iters, r.n_sel_last) for r in res_ref]
+    engine.map_destroy(mid)

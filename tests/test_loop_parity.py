@@ -1,0 +1,62 @@
+"""GPU parity: the device loop detector (lisreg_loop_detect: project + globalICP + per-candidate re-description +
+scoring + bookkeeping, epscGeneration.cpp:84-120, :258-401, :663-992) against the CPU restatement on the same
+there-and-back keyframe sequence.  Frame ids and candidate counts are exact; scores come from integer SADs (equal
+unless a point sits within fp32 rounding of a bin edge: tolerance 1e-3); transforms agree to 1e-4 (fp64 sums of the
+2-D ICP are reduced in a different - fixed - order on the device)."""
+import numpy as np
+import pytest
+
+from lis_slam_b200 import engine as E
+from oracle import orc
+
+from common import loop_keyframes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("flags", [dict(use_fepsc=True), dict(use_epsc=True, use_sepsc=True, use_fepsc=True, use_pose=True)])
+def test_loop_detect_matches_oracle(engine, flags):
+    kfs = loop_keyframes()
+    lut = orc.using_map_lut()
+    det_o = orc.LoopDetector(lut=lut, **flags)
+    det_g = engine.loop_create(lut, **flags)
+    n_match = 0
+    for k, (corner, surf, sem, lab, odom) in enumerate(kfs):
+        co, no, mo = det_o.detect(corner, surf, sem, lab, odom)
+        cg, ng, mg = engine.loop_detect(det_g, corner, surf, sem, lab, odom)
+        assert (cg, ng) == (co, no) == (k, no)
+        assert [(a, b) for a, b, _, _ in mg] == [(a, b) for a, b, _, _ in mo], (k, mg, mo)
+        for (kind, mid, so, To), (_, _, sg, Tg) in zip(mo, mg):
+            assert abs(so - sg) <= 1e-3, (k, kind, so, sg)
+            assert np.abs(To - Tg).max() <= 1e-4, (k, kind, To, Tg)
+            n_match += 1
+    assert n_match >= 8
+    det_o.close()
+    engine.loop_destroy(det_g)
+
+
+def test_loop_detect_edge_cases(engine):
+    """Empty clouds and a jumpy trajectory: the gate (which measures the distance to the PREVIOUS keyframe, since
+    posArr.back() is pushed after the loop, epscGeneration.cpp:740 / :899), the ids and the matches follow the oracle."""
+    lut = orc.using_map_lut()
+    det = engine.loop_create(lut, use_fepsc=True, use_pose=True)
+    od = orc.LoopDetector(lut=lut, use_fepsc=True, use_pose=True)
+    empty = np.zeros((0, 4), np.float32); nolab = np.zeros(0, np.uint16)
+    rng = np.random.default_rng(3)
+    few = np.zeros((40, 4), np.float32); few[:, 0] = rng.uniform(5, 20, 40); few[:, 1] = rng.uniform(-5, 5, 40)
+    fewlab = np.full(40, 18, np.uint16)
+    xs = [0.0, 30.0, 60.0, 0.0, 0.0, 30.2, 59.9, 0.1]
+    total_cand = 0
+    for k, x in enumerate(xs):
+        T = np.eye(4, dtype=np.float32); T[0, 3] = x
+        clouds = (empty, empty, empty, nolab) if k % 2 == 0 else (few[:10], few, few, fewlab)
+        cg, ng, mg = engine.loop_detect(det, *clouds, T)
+        co, no, mo = od.detect(*clouds, T)
+        assert (cg, ng) == (co, no) == (k, no)
+        assert [(a, b) for a, b, _, _ in mg] == [(a, b) for a, b, _, _ in mo], (k, mg, mo)
+        for (_, _, so, To), (_, _, sg, Tg) in zip(mo, mg):
+            assert abs(so - sg) <= 1e-3 and np.abs(To - Tg).max() <= 1e-4
+        total_cand += ng
+    assert total_cand > 0
+    od.close()
+    engine.loop_destroy(det)
