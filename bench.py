@@ -298,22 +298,27 @@ def run_ours(args, rank, world, local_rank):
     value = world * F * args.steps / (ms_total * 1e-3)
     e2e = world * F * args.steps / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel: k_lm_iter (kNN + residual + reduce) ----
+    # ---- roofline of the dominant stage: one Gauss-Newton iteration = kNN + residual + reduce + solve ----
+    # (five launches: k_knn_check, k_knn_search<scan>, k_knn_search<wide>, k_lm_resid, k_lm_solve; timed as a group with
+    # CUDA events on the engine's stream inside the timed region)
     peak, peak_src = load_peaks()
-    lm_launches = max(prof.lm_iter_launches, 1)
+    lm_launches = max(prof.lm_iter_launches, 1)          # = iterations timed
     alg_per_launch = 96.0 * n_query                      # (nc+ns) x (16 B query + 5 x 16 B neighbours), SURVEY.md 8d A_iter
-    avg_launch_ms = prof.lm_iter_ms / lm_launches        # event pair spans k_lm_iter + the tiny k_lm_solve
+    avg_launch_ms = prof.lm_iter_ms / lm_launches
     ach = alg_per_launch / (avg_launch_ms * 1e-3) / 1e9
     traffic = load_traffic()
     stage_ms = {"features": prof.feat_ms / args.steps, "voxel_grid": prof.voxel_ms / args.steps, "lm_iterations": prof.lm_iter_ms / args.steps}
-    roofline = {"bound": "hbm", "kernel": "k_lm_iter", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "peak_source": peak_src, "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+    roofline = {"bound": "hbm", "kernel": "GN iteration = k_knn_check + k_knn_search<scan> + k_knn_search<wide> + k_lm_resid + k_lm_solve",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "peak_source": peak_src, "traffic": (traffic or {}).get("dram_bytes_per_iteration"),
+                "traffic_source": (traffic or {}).get("source"),
                 "alg_bytes_per_launch": alg_per_launch, "avg_launch_ms": avg_launch_ms,
                 "kernel_share_of_step": prof.lm_iter_ms / ms_total, "stage_ms_per_step": stage_ms,
-                "regime": "maps are shared by many frames and stay L2-resident (8 x 3.2 MB); the kernel is latency/issue bound, "
-                          "not DRAM bound (see profiles/)",
-                "note": "algorithmic bytes = query points x (16 B query + 5 x 16 B neighbours) per launch (SURVEY.md 8d A_iter); "
-                        "index traversal traffic excluded"}
+                "regime": "maps are shared by many frames and stay L2-resident (8 x 3.2 MB); the stage is latency / issue bound, "
+                          "not DRAM bound (see profiles/); from iteration 2 on most queries PROVE that their neighbours are "
+                          "unchanged (5 gathers) instead of searching, so the algorithmic bytes are an upper bound of what moves",
+                "note": "algorithmic bytes = query points x (16 B query + 5 x 16 B neighbours) per iteration (SURVEY.md 8d A_iter); "
+                        "index traversal traffic excluded; launch = one iteration of the whole batch"}
     a_reg = (17.0 * n_raw / F if frame_stage else 0.0) + LM_ITERS * 96.0 * n_query / F + 16.0 * 200000
     roofline["a_reg_bytes_per_frame"] = a_reg
     roofline["a_reg_frac_of_peak"] = a_reg * (value / world) / 1e9 / peak

@@ -290,39 +290,47 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
   }
 }
 
-// compaction of the per-segment lists into the reference push order; one block per frame
-__global__ void k_feat_gather(FeatFrame* frames, FeatParamsDev prm) {
-  const FeatFrame f = frames[blockIdx.x];
+// compaction of the per-segment lists into the reference push order.  grid = (FEAT_GATHER_SPLIT, F): every block
+// rebuilds the (cheap) exclusive offsets over all segments of its frame and then copies its share of the segments,
+// one WARP per segment (ballot compaction keeps the index order of the surface list).
+constexpr int FEAT_GATHER_SPLIT = 8;
+__global__ void __launch_bounds__(256)
+k_feat_gather(FeatFrame* frames, FeatParamsDev prm) {
+  const FeatFrame f = frames[blockIdx.y];
   const int nseg = prm.n_scan * 6;
   __shared__ int s_c[1024], s_s[1024], s_f[1024], s_u[1024];   // exclusive offsets per segment (nseg <= 1024)
   for (int s = threadIdx.x; s < nseg; s += blockDim.x) {
-    const int nc = f.seg_valid[s] ? f.seg_ncorner[s] : 0;
+    const int valid = f.seg_valid[s];
+    const int nc = valid ? f.seg_ncorner[s] : 0;
     s_c[s] = nc; s_s[s] = nc < 4 ? nc : 4;
-    s_f[s] = f.seg_valid[s] ? f.seg_nflat[s] : 0;
+    s_f[s] = valid ? f.seg_nflat[s] : 0;
+    // surface points of a segment = label <= 0 over [sp, ep]; only this segment's corner picks carry label 1 there
+    s_u[s] = valid ? (f.seg_ep[s] - f.seg_sp[s] + 1) - nc : 0;
   }
   __syncthreads();
-  // surf count per segment: label <= 0 over [sp, ep]
-  for (int s = threadIdx.x; s < nseg; s += blockDim.x) {
-    int c = 0;
-    if (f.seg_valid[s]) for (int k = f.seg_sp[s]; k <= f.seg_ep[s]; k++) c += f.label[k] <= 0;
-    s_u[s] = c;
-  }
-  __syncthreads();
-  if (threadIdx.x < 4) {
-    int* a = threadIdx.x == 0 ? s_c : threadIdx.x == 1 ? s_s : threadIdx.x == 2 ? s_f : s_u;
+  if (threadIdx.x < 128 && (threadIdx.x & 31) == 0) {          // four warps, one array each
+    int* a = threadIdx.x == 0 ? s_c : threadIdx.x == 32 ? s_s : threadIdx.x == 64 ? s_f : s_u;
     int acc = 0;
     for (int s = 0; s < nseg; s++) { int t = a[s]; a[s] = acc; acc += t; }
-    f.counts[threadIdx.x] = acc;
+    if (blockIdx.x == 0) f.counts[threadIdx.x >> 5] = acc;
   }
   __syncthreads();
-  for (int s = threadIdx.x; s < nseg; s += blockDim.x) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int s = blockIdx.x * nw + wid; s < nseg; s += gridDim.x * nw) {
     if (!f.seg_valid[s]) continue;
     const int nc = f.seg_ncorner[s], nf = f.seg_nflat[s];
-    for (int i = 0; i < nc; i++) f.corner_idx[s_c[s] + i] = f.seg_corner[s * 20 + i];
-    for (int i = 0; i < (nc < 4 ? nc : 4); i++) f.sharp_idx[s_s[s] + i] = f.seg_corner[s * 20 + i];
-    for (int i = 0; i < nf; i++) f.flat_idx[s_f[s] + i] = f.seg_flat[s * 10 + i];
+    if (lane < nc) f.corner_idx[s_c[s] + lane] = f.seg_corner[s * 20 + lane];
+    if (lane < (nc < 4 ? nc : 4)) f.sharp_idx[s_s[s] + lane] = f.seg_corner[s * 20 + lane];
+    if (lane < nf) f.flat_idx[s_f[s] + lane] = f.seg_flat[s * 10 + lane];
     int o = s_u[s];
-    for (int k = f.seg_sp[s]; k <= f.seg_ep[s]; k++) if (f.label[k] <= 0) f.surf_idx[o++] = k;
+    const int sp = f.seg_sp[s], ep = f.seg_ep[s];
+    for (int base = sp; base <= ep; base += 32) {
+      const int k = base + lane;
+      const bool keep = k <= ep && f.label[k] <= 0;
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) f.surf_idx[o + __popc(m & ((1u << lane) - 1u))] = k;
+      o += __popc(m);
+    }
   }
 }
 

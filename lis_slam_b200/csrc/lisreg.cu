@@ -755,7 +755,7 @@ static int run_features(lisreg_ctx* ctx, FeatFrame* d_frames, int F, const lisre
   k_feat_curvature<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames); LAUNCH_CK();
   k_feat_occlusion<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames); LAUNCH_CK();
   k_feat_segments<<<dim3((prm->n_scan + FEAT_WARPS - 1) / FEAT_WARPS, F), 32 * FEAT_WARPS, 0, st>>>(d_frames, dp); LAUNCH_CK();
-  k_feat_gather<<<F, 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
+  k_feat_gather<<<dim3(FEAT_GATHER_SPLIT, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
   return LISREG_OK;
 }
 
