@@ -62,8 +62,18 @@ __device__ __forceinline__ bool feat_project(const FeatParamsDev& prm, float4 p,
   if (ring < 0 || ring >= prm.n_scan) return false;
   if (ring % prm.downsample != 0) return false;
   const float ang_res_x = (float)(360.0 / (double)(float)prm.horizon);
-  const float horizonAngle = (float)((double)(atan2f_cr(p.x, p.y) * 180) / 3.14159265358979323846);
-  int col = (int)(-round(((double)horizonAngle - 90.0) / (double)ang_res_x) + (double)(prm.horizon / 2));
+  // The column is the only consumer of the azimuth.  Fast path: fp32 atan2f (<= 2 ulp, i.e. < 1e-4 columns off);
+  // only when the column coordinate lands within 2e-3 of a rounding boundary is the reference expression
+  // evaluated (correctly rounded atan2 in fp64) - the result is identical, the fp64 atan2 runs for ~0.4 % of the points.
+  const double t_fast = ((double)atan2f(p.x, p.y) * (180.0 / 3.14159265358979323846) - 90.0) / (double)ang_res_x;
+  const double fr = t_fast - floor(t_fast);
+  int col;
+  if (fabs(fr - 0.5) > 2e-3) {
+    col = (int)(-round(t_fast) + (double)(prm.horizon / 2));
+  } else {
+    const float horizonAngle = (float)((double)(atan2f_cr(p.x, p.y) * 180) / 3.14159265358979323846);
+    col = (int)(-round(((double)horizonAngle - 90.0) / (double)ang_res_x) + (double)(prm.horizon / 2));
+  }
   if (col >= prm.horizon) col -= prm.horizon;
   if (col < 0 || col >= prm.horizon) return false;
   cell = ring * prm.horizon + col;
@@ -171,8 +181,7 @@ constexpr int FEAT_WARPS = 4;            // rings per block
 constexpr int FEAT_RING_MAX = 2048 + 16; // staged ring window (horizon <= 2048, +-6 apron)
 constexpr int FEAT_CH = 12;              // segment elements per lane: a segment holds <= 32 * 12 points (horizon <= 2048 -> <= 341)
 
-// Neighbour suppression of a pick (:648-661) on the ring window staged in shared memory; executed by the whole
-// warp on the same `ind` (uniform).  lo = global index of window slot 0; indices outside [0, M) or outside the
+// Neighbour suppression of a pick (:648-661) on the ring window staged in shared memory.  lo = global index of window slot 0; indices outside [0, M) or outside the
 // window end the walk (the window covers [first-6, last+6] of the ring, the only indices a pick of this ring can
 // reach).  Returns the marked index range [a0, b0].
 __device__ __forceinline__ void feat_mark_range(const unsigned short* scol, int lo, int wlen, int ind, int M, int& a0, int& b0) {
@@ -198,7 +207,7 @@ __device__ __forceinline__ void feat_mark_range(const unsigned short* scol, int 
 // suppressed yet and suppressing its +-5 neighbours (order-dependent greedy non-maximum suppression).  Only the
 // PICKS change state, so the walk is restated as a selection loop: "take the best not-yet-suppressed candidate,
 // pick it, suppress its neighbours", which visits exactly the same picks in exactly the same order without ever
-// sorting.  The segment lives in registers (element sp + 32 t + lane in slot t of a lane, an alive bit per slot);
+// sorting.  The segment's curvatures sit in shared memory (element sp + 32 t + lane = slot t of a lane, an alive bit per slot);
 // one step = per-lane best of the alive slots, two warp reductions (redux.sync) for the winning (curvature,
 // index) key, a uniform walk for the suppression range, and an O(1) alive-mask update per lane.  ~40 steps per
 // segment instead of a 512-key bitonic sort plus a 300-element sequential walk by one lane.
@@ -208,7 +217,9 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int ring = blockIdx.x * FEAT_WARPS + wid;
   __shared__ unsigned char s_pick[FEAT_WARPS][FEAT_RING_MAX];
+  __shared__ unsigned char s_reach[FEAT_WARPS][FEAT_RING_MAX];   // suppression reach of every point: right | left << 4
   __shared__ unsigned short s_col[FEAT_WARPS][FEAT_RING_MAX];
+  __shared__ float s_cv[FEAT_WARPS][32 * FEAT_CH];               // curvature of the current segment, slot-major
   if (ring >= prm.n_scan) return;
   const unsigned FULL = 0xffffffffu;
   const int M = *f.M;
@@ -219,7 +230,15 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
   const int lo = max(start - 4 - 6, 0);
   const int hi = min(end + 5 + 6, M - 1);
   const int wlen = max(hi - lo + 1, 0);
+  unsigned char* sreach = s_reach[wid];
   for (int t = lane; t < wlen; t += 32) { spick[t] = (unsigned char)f.picked[lo + t]; scol[t] = (unsigned short)f.col[lo + t]; }
+  __syncwarp();
+  // how far a pick of each point suppresses to the right / left depends on the column indices only: once per point
+  for (int t = lane; t < wlen; t += 32) {
+    int a0, b0;
+    feat_mark_range(scol, lo, wlen, lo + t, M, a0, b0);
+    sreach[t] = (unsigned char)((b0 - (lo + t)) | ((lo + t - a0) << 4));
+  }
   __syncwarp();
   for (int j = 0; j < 6; j++) {
     const int seg = ring * 6 + j;
@@ -230,23 +249,26 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
     if (ep - sp + 1 > 32 * FEAT_CH) continue;   // unreachable for horizon <= 2048 (checked by the host entry points)
     // elements sp .. ep (ep is NOT part of the reference's sorted range but is visited first in pass 1 and last
     // in pass 2, quirk Q3): slot t of this lane = sp + 32 t + lane
-    float cv[FEAT_CH];
+    float* scv = s_cv[wid];
+    unsigned alive = 0u, flat = 0u;
 #pragma unroll
-    for (int t = 0; t < FEAT_CH; t++) { const int idx = sp + 32 * t + lane; cv[t] = idx <= ep ? f.curv[idx] : 0.f; }
+    for (int t = 0; t < FEAT_CH; t++) {
+      const int idx = sp + 32 * t + lane;
+      const float c = idx <= ep ? f.curv[idx] : 0.f;
+      scv[32 * t + lane] = c;
+      if (idx <= ep && c > prm.edge_thr && spick[idx - lo] == 0) alive |= 1u << t;
+      if (idx <= ep && c < prm.surf_thr) flat |= 1u << t;
+    }
     // ---------------- pass 1: edges, largest curvature first (:633-663) ----------------
-    unsigned alive = 0u;
-#pragma unroll
-    for (int t = 0; t < FEAT_CH; t++) { const int idx = sp + 32 * t + lane; if (idx <= ep && cv[t] > prm.edge_thr && spick[idx - lo] == 0) alive |= 1u << t; }
     int nc = 0;
     for (;;) {
       // per-lane best: key = (curvature bits + 1, index), ep outranks everything; 0 = no candidate.  Slots of a lane
       // have ascending indices, so ">=" keeps the larger index on equal curvature (descending walk of an
       // ascending (value, index) order)
       unsigned bh = 0u, bl = 0u;
-#pragma unroll
-      for (int t = 0; t < FEAT_CH; t++) if (alive >> t & 1u) {
-        const int idx = sp + 32 * t + lane;
-        const unsigned h = idx == ep ? 0xffffffffu : __float_as_uint(cv[t]) + 1u;
+      for (unsigned mb = alive; mb; mb &= mb - 1u) {          // only the alive slots (few after the first picks)
+        const int t = __ffs(mb) - 1, idx = sp + 32 * t + lane;
+        const unsigned h = idx == ep ? 0xffffffffu : __float_as_uint(scv[32 * t + lane]) + 1u;
         if (h >= bh) { bh = h; bl = (unsigned)idx; }
       }
       const unsigned mh = __reduce_max_sync(FULL, bh);
@@ -255,24 +277,22 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
       if (nc == 20) break;                       // the 21st pick ends the pass without being marked (:640-645)
       if (lane == 0) { f.label[ind] = 1; f.seg_corner[seg * 20 + nc] = ind; }
       nc++;
-      int a0, b0;
-      feat_mark_range(scol, lo, wlen, ind, M, a0, b0);
+      const int rch = sreach[ind - lo];
+      const int a0 = ind - (rch >> 4), b0 = ind + (rch & 15);
       if (lane <= b0 - a0) spick[a0 + lane - lo] = 1;
       { const int o = a0 - sp - lane; const int t0 = o <= 0 ? 0 : (o + 31) >> 5; if (t0 < FEAT_CH && sp + 32 * t0 + lane <= b0) alive &= ~(1u << t0); }
     }
     __syncwarp();
     // ---------------- pass 2: flat points, smallest curvature first (:665-694) ----------------
     alive = 0u;
-#pragma unroll
-    for (int t = 0; t < FEAT_CH; t++) { const int idx = sp + 32 * t + lane; if (idx <= ep && cv[t] < prm.surf_thr && spick[idx - lo] == 0) alive |= 1u << t; }
+    for (unsigned mb = flat; mb; mb &= mb - 1u) { const int t = __ffs(mb) - 1; if (spick[sp + 32 * t + lane - lo] == 0) alive |= 1u << t; }
     int nf = 0;
     for (;;) {
       // key = (curvature bits, index) ascending, ep is visited last; 0xffffffff = no candidate
       unsigned bh = 0xffffffffu, bl = 0xffffffffu;
-#pragma unroll
-      for (int t = 0; t < FEAT_CH; t++) if (alive >> t & 1u) {
-        const int idx = sp + 32 * t + lane;
-        const unsigned h = idx == ep ? 0xfffffffeu : __float_as_uint(cv[t]);
+      for (unsigned mb = alive; mb; mb &= mb - 1u) {
+        const int t = __ffs(mb) - 1, idx = sp + 32 * t + lane;
+        const unsigned h = idx == ep ? 0xfffffffeu : __float_as_uint(scv[32 * t + lane]);
         if (h < bh) { bh = h; bl = (unsigned)idx; }
       }
       const unsigned mh = __reduce_min_sync(FULL, bh);
@@ -280,8 +300,8 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
       const int ind = (int)__reduce_min_sync(FULL, bh == mh ? bl : 0xffffffffu);
       if (lane == 0) { f.label[ind] = -1; if (nf < 10) f.seg_flat[seg * 10 + nf] = ind; }
       if (nf < 10) nf++;
-      int a0, b0;
-      feat_mark_range(scol, lo, wlen, ind, M, a0, b0);
+      const int rch = sreach[ind - lo];
+      const int a0 = ind - (rch >> 4), b0 = ind + (rch & 15);
       if (lane <= b0 - a0) spick[a0 + lane - lo] = 1;
       { const int o = a0 - sp - lane; const int t0 = o <= 0 ? 0 : (o + 31) >> 5; if (t0 < FEAT_CH && sp + 32 * t0 + lane <= b0) alive &= ~(1u << t0); }
     }

@@ -478,11 +478,15 @@ k_knn_check(const RegDesc* __restrict__ descs, const RegState* __restrict__ stat
       if (l < qn) {
         need = true;
         if (use_state) {
+          // state, query and neighbour ids are independent loads: issue them together (most queries take the proof path)
           const float4 ref = *reinterpret_cast<const float4*>(&tstate[l]);
+          const int q = q0 + l;
+          const bool is_corner = q < sd.nc;
+          const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
+          int pos[5];
+#pragma unroll
+          for (int j = 0; j < 5; j++) pos[j] = tnbr[j * tile_pts + l];
           if (ref.w != 0.f) {
-            const int q = q0 + l;
-            const bool is_corner = q < sd.nc;
-            const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
             const float x0 = sT[0] * p.x + sT[1] * p.y + sT[2] * p.z + sT[3];
             const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
             const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
@@ -494,10 +498,8 @@ k_knn_check(const RegDesc* __restrict__ descs, const RegState* __restrict__ stat
               if (r * r * 0.99999f > gate) need = false;          // still rejected; nbr[l] is already -1
             } else if (r > 0.f) {
               const float4* __restrict__ pts = is_corner ? mp.corner.pts : mp.surf.pts;
-              int pos[5]; knn_key key[5];
+              knn_key key[5];
               float bmax = 0.f;
-#pragma unroll
-              for (int j = 0; j < 5; j++) pos[j] = tnbr[j * tile_pts + l];
 #pragma unroll
               for (int j = 0; j < 5; j++) {
                 const float d = knn_dist2(x0, y0, z0, __ldg(&pts[pos[j]]));
