@@ -288,6 +288,34 @@ def run_ours(args, rank, world, local_rank):
     sampler.join(timeout=2)
     e2e_matches = bool(np.array_equal(pose_host, pose_gpu))
 
+    # ---- single-frame latency (BASELINE configs[1] / configs[4] shape: one sweep at a time, reference early exit) ----
+    latency = None
+    if frame_stage and rank == 0 and not args.no_latency:
+        latency = {}
+        for sensor, n_scan in (("hdl64", 64), ("vlp16", 16)):
+            sc = synth.Scene(seed=1001)
+            r0 = wl["regs"][0]
+            sw1 = wl["sweeps"][r0["sweep"]][0] if sensor == "hdl64" else sc.scan(r0["truth"], sensor=sensor, seed=2000)
+            p1 = torch.from_numpy(np.ascontiguousarray(sw1["pts"], np.float32)).to(dev)
+            g1 = torch.from_numpy(np.ascontiguousarray(sw1["ring"], np.uint16).view(np.int16)).to(dev)
+            it1 = (E.FrameItem * 1)(); it1[0] = E.FrameItem(p1.data_ptr(), g1.data_ptr(), len(sw1["pts"]), map_ids[r0["map"]])
+            prm1 = E.frame_params("A")                       # reference behaviour: <= 15 iterations, early exit
+            prm1.feat.n_scan = n_scan
+            g6 = torch.from_numpy(np.asarray(r0["guess"], np.float32).reshape(1, 6)).to(dev)
+            po1 = torch.empty_like(g6); re1 = torch.empty(C.sizeof(E.LmResult), dtype=torch.uint8, device=dev)
+            ts = []
+            for k in range(25):
+                po1.copy_(g6)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                eng.frames_batch_dev(it1, 1, po1.data_ptr(), prm1, re1.data_ptr())
+                b.record(stream)
+                torch.cuda.synchronize(dev)
+                if k >= 5:
+                    ts.append(a.elapsed_time(b))
+            r1 = E.LmResult.from_buffer_copy(re1.cpu().numpy().tobytes())
+            latency[sensor] = {"p50_ms": float(np.median(ts)), "max_ms": float(np.max(ts)), "iters": int(r1.iters), "points": int(len(sw1["pts"]))}
+
     # ---- max over ranks ----
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
@@ -354,6 +382,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "pose_err_vs_cpu": pose_err,
+        "single_frame_latency": latency,
     }
     print(json.dumps(line), flush=True)
 
@@ -372,6 +401,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16, help="frames timed on the CPU for cpu_baseline")
     ap.add_argument("--ref-sample", type=int, default=8, help="frames per step for --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-frame latency probe")
     ap.add_argument("--e2e-sync", action="store_true", help="time the blocking arena call for e2e instead of the submit/wait pipeline")
     args = ap.parse_args()
 

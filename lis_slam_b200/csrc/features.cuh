@@ -179,6 +179,7 @@ __global__ void k_feat_occlusion(FeatFrame* frames) {
 // ---- F5 ----
 constexpr int FEAT_WARPS = 4;            // rings per block
 constexpr int FEAT_RING_MAX = 2048 + 16; // staged ring window (horizon <= 2048, +-6 apron)
+#define KNN_SEG_INF __int_as_float(0x7f800000)
 constexpr int FEAT_CH = 12;              // segment elements per lane: a segment holds <= 32 * 12 points (horizon <= 2048 -> <= 341)
 
 // Neighbour suppression of a pick (:648-661) on the ring window staged in shared memory.  lo = global index of window slot 0; indices outside [0, M) or outside the
@@ -208,8 +209,9 @@ __device__ __forceinline__ void feat_mark_range(const unsigned short* scol, int 
 // PICKS change state, so the walk is restated as a selection loop: "take the best not-yet-suppressed candidate,
 // pick it, suppress its neighbours", which visits exactly the same picks in exactly the same order without ever
 // sorting.  The segment's curvatures sit in shared memory (element sp + 32 t + lane = slot t of a lane, an alive bit per slot);
-// one step = per-lane best of the alive slots, two warp reductions (redux.sync) for the winning (curvature,
-// index) key, a uniform walk for the suppression range, and an O(1) alive-mask update per lane.  ~40 steps per
+// one step = per-lane best (lowest / highest alive rank of the lane's pre-ranked slots: one ffs / clz), two warp
+// reductions (redux.sync) for the winning (curvature, index) key, the pre-computed suppression reach of the winner,
+// and an O(1) alive-mask update per lane.  ~40 steps per
 // segment instead of a 512-key bitonic sort plus a 300-element sequential walk by one lane.
 __global__ void __launch_bounds__(32 * FEAT_WARPS)
 k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
@@ -247,29 +249,56 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
     if (lane == 0) { f.seg_sp[seg] = sp; f.seg_ep[seg] = ep; f.seg_valid[seg] = (sp < ep) ? 1 : 0; f.seg_ncorner[seg] = 0; f.seg_nflat[seg] = 0; }
     if (sp >= ep) continue;
     if (ep - sp + 1 > 32 * FEAT_CH) continue;   // unreachable for horizon <= 2048 (checked by the host entry points)
-    // elements sp .. ep (ep is NOT part of the reference's sorted range but is visited first in pass 1 and last
-    // in pass 2, quirk Q3): slot t of this lane = sp + 32 t + lane
+    // elements sp .. ep - 1 are the reference's sorted range: slot t of this lane = sp + 32 t + lane.  Each lane ranks
+    // its own <= 12 slots by (curvature, index) once per segment; its best candidate is then the lowest / highest
+    // alive RANK (one ffs / clz), looked up through two 4-bit-per-entry permutations held in registers.
+    // Element ep is not sorted (quirk Q3): it is visited first in pass 1 and last in pass 2, handled apart.
     float* scv = s_cv[wid];
-    unsigned alive = 0u, flat = 0u;
+    float cv[FEAT_CH];
 #pragma unroll
     for (int t = 0; t < FEAT_CH; t++) {
       const int idx = sp + 32 * t + lane;
-      const float c = idx <= ep ? f.curv[idx] : 0.f;
-      scv[32 * t + lane] = c;
-      if (idx <= ep && c > prm.edge_thr && spick[idx - lo] == 0) alive |= 1u << t;
-      if (idx <= ep && c < prm.surf_thr) flat |= 1u << t;
+      cv[t] = idx < ep ? f.curv[idx] : KNN_SEG_INF;
+      scv[32 * t + lane] = cv[t];
     }
+    unsigned long long slot_of_rank = 0ull, rank_of_slot = 0ull;
+#pragma unroll
+    for (int t = 0; t < FEAT_CH; t++) {
+      int rk = 0;
+#pragma unroll
+      for (int u = 0; u < FEAT_CH; u++) if (u != t) rk += (cv[u] < cv[t] || (cv[u] == cv[t] && u < t)) ? 1 : 0;
+      slot_of_rank |= (unsigned long long)t << (4 * rk);
+      rank_of_slot |= (unsigned long long)rk << (4 * t);
+    }
+    const float cv_ep = f.curv[ep];
+    auto mark = [&](int ind, unsigned& alive_r) {
+      const int rch = sreach[ind - lo];
+      const int a0 = ind - (rch >> 4), b0 = ind + (rch & 15);
+      if (lane <= b0 - a0) spick[a0 + lane - lo] = 1;
+      const int o = a0 - sp - lane; const int t0 = o <= 0 ? 0 : (o + 31) >> 5;
+      if (t0 < FEAT_CH && sp + 32 * t0 + lane <= b0) alive_r &= ~(1u << (int)((rank_of_slot >> (4 * t0)) & 15ull));
+    };
     // ---------------- pass 1: edges, largest curvature first (:633-663) ----------------
+    unsigned alive = 0u;
+#pragma unroll
+    for (int t = 0; t < FEAT_CH; t++) {
+      const int idx = sp + 32 * t + lane;
+      if (idx < ep && cv[t] > prm.edge_thr && spick[idx - lo] == 0) alive |= 1u << (int)((rank_of_slot >> (4 * t)) & 15ull);
+    }
     int nc = 0;
+    if (cv_ep > prm.edge_thr && spick[ep - lo] == 0) {          // k = ep comes first
+      __syncwarp();
+      if (lane == 0) { f.label[ep] = 1; f.seg_corner[seg * 20 + nc] = ep; }
+      nc++;
+      mark(ep, alive);
+    }
     for (;;) {
-      // per-lane best: key = (curvature bits + 1, index), ep outranks everything; 0 = no candidate.  Slots of a lane
-      // have ascending indices, so ">=" keeps the larger index on equal curvature (descending walk of an
-      // ascending (value, index) order)
+      // per-lane best = highest alive rank; key = (curvature bits + 1, index); 0 = no candidate.  ">=" semantics of
+      // the descending walk (larger index first on equal curvature) are in the ranking
       unsigned bh = 0u, bl = 0u;
-      for (unsigned mb = alive; mb; mb &= mb - 1u) {          // only the alive slots (few after the first picks)
-        const int t = __ffs(mb) - 1, idx = sp + 32 * t + lane;
-        const unsigned h = idx == ep ? 0xffffffffu : __float_as_uint(scv[32 * t + lane]) + 1u;
-        if (h >= bh) { bh = h; bl = (unsigned)idx; }
+      if (alive) {
+        const int r = 31 - __clz(alive), slot = (int)((slot_of_rank >> (4 * r)) & 15ull);
+        bh = __float_as_uint(scv[32 * slot + lane]) + 1u; bl = (unsigned)(sp + 32 * slot + lane);
       }
       const unsigned mh = __reduce_max_sync(FULL, bh);
       if (mh == 0u) break;
@@ -277,34 +306,41 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
       if (nc == 20) break;                       // the 21st pick ends the pass without being marked (:640-645)
       if (lane == 0) { f.label[ind] = 1; f.seg_corner[seg * 20 + nc] = ind; }
       nc++;
-      const int rch = sreach[ind - lo];
-      const int a0 = ind - (rch >> 4), b0 = ind + (rch & 15);
-      if (lane <= b0 - a0) spick[a0 + lane - lo] = 1;
-      { const int o = a0 - sp - lane; const int t0 = o <= 0 ? 0 : (o + 31) >> 5; if (t0 < FEAT_CH && sp + 32 * t0 + lane <= b0) alive &= ~(1u << t0); }
+      mark(ind, alive);
     }
     __syncwarp();
     // ---------------- pass 2: flat points, smallest curvature first (:665-694) ----------------
     alive = 0u;
-    for (unsigned mb = flat; mb; mb &= mb - 1u) { const int t = __ffs(mb) - 1; if (spick[sp + 32 * t + lane - lo] == 0) alive |= 1u << t; }
-    int nf = 0;
+#pragma unroll
+    for (int t = 0; t < FEAT_CH; t++) {
+      const int idx = sp + 32 * t + lane;
+      if (idx < ep && cv[t] < prm.surf_thr && spick[idx - lo] == 0) alive |= 1u << (int)((rank_of_slot >> (4 * t)) & 15ull);
+    }
+    int nf = 0, npick2 = 0;
     for (;;) {
-      // key = (curvature bits, index) ascending, ep is visited last; 0xffffffff = no candidate
+      // per-lane best = lowest alive rank; key = (curvature bits, index) ascending; 0xffffffff = no candidate
       unsigned bh = 0xffffffffu, bl = 0xffffffffu;
-      for (unsigned mb = alive; mb; mb &= mb - 1u) {
-        const int t = __ffs(mb) - 1, idx = sp + 32 * t + lane;
-        const unsigned h = idx == ep ? 0xfffffffeu : __float_as_uint(scv[32 * t + lane]);
-        if (h < bh) { bh = h; bl = (unsigned)idx; }
+      if (alive) {
+        const int r = __ffs(alive) - 1, slot = (int)((slot_of_rank >> (4 * r)) & 15ull);
+        bh = __float_as_uint(scv[32 * slot + lane]); bl = (unsigned)(sp + 32 * slot + lane);
       }
       const unsigned mh = __reduce_min_sync(FULL, bh);
       if (mh == 0xffffffffu) break;
       const int ind = (int)__reduce_min_sync(FULL, bh == mh ? bl : 0xffffffffu);
       if (lane == 0) { f.label[ind] = -1; if (nf < 10) f.seg_flat[seg * 10 + nf] = ind; }
       if (nf < 10) nf++;
-      const int rch = sreach[ind - lo];
-      const int a0 = ind - (rch >> 4), b0 = ind + (rch & 15);
-      if (lane <= b0 - a0) spick[a0 + lane - lo] = 1;
-      { const int o = a0 - sp - lane; const int t0 = o <= 0 ? 0 : (o + 31) >> 5; if (t0 < FEAT_CH && sp + 32 * t0 + lane <= b0) alive &= ~(1u << t0); }
+      npick2++;
+      mark(ind, alive);
     }
+    __syncwarp();
+    if (cv_ep < prm.surf_thr && spick[ep - lo] == 0) {          // k = ep comes last
+      __syncwarp();
+      if (lane == 0) { f.label[ep] = -1; if (nf < 10) f.seg_flat[seg * 10 + nf] = ep; }
+      if (nf < 10) nf++;
+      unsigned dummy = 0u;
+      mark(ep, dummy);
+    }
+    (void)npick2;
     if (lane == 0) { f.seg_ncorner[seg] = nc; f.seg_nflat[seg] = nf; }
     __syncwarp();
   }

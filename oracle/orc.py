@@ -134,6 +134,7 @@ def lib():
         L.orc_epsc_score_all.argtypes = [u8p, C.c_int32, C.c_int32, ip, fp, C.POINTER(C.c_int8), C.c_int32]
         L.orc_icp.restype = C.c_int
         L.orc_icp.argtypes = [fp, C.c_int32, fp, C.c_int32, C.POINTER(IcpParams), C.POINTER(IcpResult)]
+        L.orc_deskew.argtypes = [fp, fp, ip, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32, C.c_double, fp]
         L.orc_loop_create.restype = C.c_void_p
         L.orc_loop_create.argtypes = [u8p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         L.orc_loop_free.argtypes = [C.c_void_p]
@@ -353,3 +354,16 @@ def loop_global_icp(proj1, proj2, yaw_diff):
     fp = C.POINTER(C.c_float)
     lib().orc_loop_global_icp(a.ctypes.data_as(fp), b.ctypes.data_as(fp), float(yaw_diff), T.ctypes.data_as(fp))
     return T.reshape(4, 4)
+
+
+def deskew(pts4, time, src_index, imu_time, imu_rot, time_scan_cur):
+    """deskewPoint over the extracted points (laserProcessing.cpp:427-462). imu_rot: (n,3) doubles. Returns (M,4)."""
+    p, pp = _f(pts4)
+    t = np.ascontiguousarray(time, np.float32)
+    si = np.ascontiguousarray(src_index, np.int32)
+    it = np.ascontiguousarray(imu_time, np.float64); ir = np.ascontiguousarray(imu_rot, np.float64).reshape(-1)
+    out = np.zeros((len(si), 4), np.float32)
+    dp = C.POINTER(C.c_double)
+    lib().orc_deskew(pp, t.ctypes.data_as(C.POINTER(C.c_float)), si.ctypes.data_as(C.POINTER(C.c_int32)), len(si),
+                     it.ctypes.data_as(dp), ir.ctypes.data_as(dp), len(it), float(time_scan_cur), out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out

@@ -102,6 +102,10 @@ typedef struct orc_icp_params { float max_corr_dist; int32_t max_iters; double t
 typedef struct orc_icp_result { float T[16]; double fitness; int32_t converged, iters, n_corr_last, pad; } orc_icp_result;
 int orc_icp(const float* src4, int32_t ns, const float* tgt4, int32_t nt, const orc_icp_params* prm, orc_icp_result* res);
 
+/* ---- motion de-skew of the extracted points (laserProcessing.cpp:368-462, :501) ---- */
+void orc_deskew(const float* pts4, const float* time, const int32_t* src_index, int32_t M,
+                const double* imu_time, const double* imu_rot3, int32_t n_imu, double time_scan_cur, float* out4);
+
 /* ---- EPSC loop detector (epscGeneration.cpp:84-120 project, :258-401 globalICP, :663-992 loopDetection) ---- */
 void* orc_loop_create(const uint8_t* using_map, int32_t use_epsc, int32_t use_sepsc, int32_t use_fepsc, int32_t use_pose);
 void orc_loop_free(void* h);
