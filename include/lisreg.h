@@ -184,6 +184,24 @@ void lisreg_feat_params_default(lisreg_feat_params* p);
 int32_t lisreg_extract_features(lisreg_ctx* ctx, const float* pts, const uint16_t* ring, int32_t n,
                                 const lisreg_feat_params* prm, lisreg_feat_out* out);
 
+/* Same with the per-point motion de-skew of projectPointCloud (SURVEY.md 8f "next" #3): replaces
+ * LaserProcessing::deskewPoint / findRotation / findPosition (laserProcessing.cpp:368-462, call site :501).
+ * imu_time / imu_rot are the rotation table that imuDeskewInfo integrates over the sweep (:213-262: imuTime[],
+ * imuRotX/Y/Z[] interleaved, n_imu = imuPointerCur + 1 entries), time_scan_cur = timeScanCur, time[i] =
+ * PointXYZIRT::time of input point i.  Range, column and every feature decision come from the ORIGINAL points
+ * (as upstream); ext_xyzi (nullable, n_scan*horizon x float4) receives the de-skewed extracted cloud the index
+ * lists refer to.  dsk == NULL or n_imu <= 0 = deskewFlag -1 / IMU unavailable (:429): points pass through. */
+typedef struct lisreg_deskew {
+  const double* imu_time;
+  const double* imu_rot;
+  int32_t n_imu;
+  int32_t reserved;
+  double time_scan_cur;
+} lisreg_deskew;
+int32_t lisreg_extract_features_deskew(lisreg_ctx* ctx, const float* pts, const uint16_t* ring, const float* time, int32_t n,
+                                       const lisreg_feat_params* prm, const lisreg_deskew* dsk, lisreg_feat_out* out,
+                                       float* ext_xyzi);
+
 /* ---- voxel-grid down-sampling (F6) ----
  * Replaces pcl::VoxelGrid<PointType>::filter as used by downSizeFilterCorner/Surf
  * (odomEstimationNode.cpp:110-111, :196-201, :272-277): centroid per occupied voxel, ascending voxel

@@ -42,6 +42,11 @@ struct FeatFrame {
   // compacted outputs, reference push order
   int* corner_idx; int* sharp_idx; int* flat_idx; int* surf_idx;
   int* counts;           // [4] n_corner, n_sharp, n_flat, n_surf
+  // optional motion de-skew (deskewPoint, laserProcessing.cpp:427-462): n_imu = 0 disables it
+  const float* time;     // per input point: PointXYZIRT::time
+  const double* imu_time; const double* imu_rot;   // imuTime[n_imu], imuRotX/Y/Z[n_imu] interleaved
+  int n_imu; double t_scan;                         // imuPointerCur + 1, timeScanCur
+  float* start_inv;      // [9] transStartInverse (linear part; the translation is identically zero)
 };
 
 __device__ __forceinline__ float atan2f_cr(float y, float x) { return (float)atan2((double)y, (double)x); }
@@ -87,6 +92,76 @@ __global__ void k_feat_project(FeatFrame* frames, FeatParamsDev prm) {
     float r; int cell;
     if (feat_project(prm, __ldg(&f.pts[i]), (int)f.ring[i], r, cell)) atomicMin(&f.owner[cell], i);
   }
+}
+
+// ---- motion de-skew: findRotation :368-400, deskewPoint :427-462 ----
+__device__ __forceinline__ void feat_rot_of(float roll, float pitch, float yaw, float* R) {   // pcl::getTransformation, linear part
+  const float A = (float)cos((double)yaw), B = (float)sin((double)yaw), C = (float)cos((double)pitch), D = (float)sin((double)pitch),
+              E = (float)cos((double)roll), F = (float)sin((double)roll);
+  const float DE = D * E, DF = D * F;
+  R[0] = A * C; R[1] = A * DF - B * E; R[2] = B * F + A * DE;
+  R[3] = B * C; R[4] = A * E + B * DF; R[5] = B * DE - A * F;
+  R[6] = -D;    R[7] = C * F;          R[8] = C * E;
+}
+__device__ __forceinline__ void feat_find_rotation(const FeatFrame& f, double pointTime, float* r) {
+  const int cur = f.n_imu - 1;
+  int front = 0;
+  while (front < cur) { if (pointTime < f.imu_time[front]) break; ++front; }
+  if (pointTime > f.imu_time[front] || front == 0) {
+    for (int a = 0; a < 3; a++) r[a] = (float)f.imu_rot[3 * front + a];
+  } else {
+    const int back = front - 1;
+    const double ratioFront = (pointTime - f.imu_time[back]) / (f.imu_time[front] - f.imu_time[back]);
+    const double ratioBack = (f.imu_time[front] - pointTime) / (f.imu_time[front] - f.imu_time[back]);
+    for (int a = 0; a < 3; a++) r[a] = (float)(f.imu_rot[3 * front + a] * ratioFront + f.imu_rot[3 * back + a] * ratioBack);
+  }
+}
+__device__ __forceinline__ float feat_cof(const float* m, int i, int j) {
+  const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+  return m[i1 * 3 + j1] * m[i2 * 3 + j2] - m[i1 * 3 + j2] * m[i2 * 3 + j1];
+}
+// transStartInverse: the first point processed by projectPointCloud (smallest input index that owns a cell) fixes the
+// reference orientation (:439-443).  grid = F, block = 256
+__global__ void k_feat_deskew_start(FeatFrame* frames, FeatParamsDev prm) {
+  const FeatFrame f = frames[blockIdx.x];
+  if (f.n_imu <= 0) return;
+  __shared__ int s_min[32];
+  int m = 0x7fffffff;
+  const int cells = prm.n_scan * prm.horizon;
+  for (int i = threadIdx.x; i < cells; i += blockDim.x) m = min(m, f.owner[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = min(m, s_min[w]);
+    float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+    if (m != 0x7fffffff) {
+      float r[3];
+      feat_find_rotation(f, f.t_scan + (double)f.time[m], r);
+      feat_rot_of(r[0], r[1], r[2], R);
+    }
+    // Eigen::Affine3f::inverse(): cofactor inverse of the linear part
+    const float c0 = feat_cof(R, 0, 0), c1 = feat_cof(R, 1, 0), c2 = feat_cof(R, 2, 0);
+    const float det = (c0 * R[0] + c1 * R[3]) + c2 * R[6];
+    const float invdet = 1.f / det;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) f.start_inv[i * 3 + j] = feat_cof(R, j, i) * invdet;
+  }
+}
+__device__ __forceinline__ float4 feat_deskew_point(const FeatFrame& f, const float* Sinv, float4 p, int src) {
+  float r[3], Rc[9], Bt[9];
+  feat_find_rotation(f, f.t_scan + (double)f.time[src], r);
+  feat_rot_of(r[0], r[1], r[2], Rc);
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) Bt[a * 3 + b] = (Sinv[a * 3] * Rc[b] + Sinv[a * 3 + 1] * Rc[3 + b]) + Sinv[a * 3 + 2] * Rc[6 + b];
+  float4 o;
+  o.x = Bt[0] * p.x + Bt[1] * p.y + Bt[2] * p.z + 0.f;
+  o.y = Bt[3] * p.x + Bt[4] * p.y + Bt[5] * p.z + 0.f;
+  o.z = Bt[6] * p.x + Bt[7] * p.y + Bt[8] * p.z + 0.f;
+  o.w = p.w;
+  return o;
 }
 
 // F2a: valid cells per ring.  grid = (n_scan, F), block = 256
@@ -137,7 +212,8 @@ __global__ void k_feat_compact(FeatFrame* frames, FeatParamsDev prm) {
     if (v) {
       const int pos = s_base + s_chunk[ch] + __popc(m & ((1u << lane) - 1u));
       const float4 p = __ldg(&f.pts[own]);
-      f.ext_pts[pos] = p;
+      // range (and the column) come from the ORIGINAL point; only the stored coordinates are de-skewed (:489-507)
+      f.ext_pts[pos] = f.n_imu > 0 ? feat_deskew_point(f, f.start_inv, p, own) : p;
       f.ext_src[pos] = own;
       f.col[pos] = j;
       f.range[pos] = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);

@@ -713,7 +713,7 @@ static size_t feat_frame_bytes(int cells, int nscan) {
   b += sizeof(int) * (size_t)nscan * 3;                 // ring_count, ring_start, ring_end
   b += sizeof(int) * (size_t)nscan * 6 * (20 + 1 + 10 + 1 + 1 + 1 + 1);   // seg_corner, ncorner, seg_flat, nflat, valid, sp, ep
   b += sizeof(int) * (size_t)nscan * (120 + 24 + 60);   // corner_idx, sharp_idx, flat_idx
-  b += sizeof(int) * 8;                                 // M, counts[4]
+  b += sizeof(int) * 8 + 64;                            // M, counts[4], start_inv[9]
   return (b + 255) & ~size_t(255);
 }
 
@@ -731,7 +731,8 @@ static void feat_carve(char* base, int cells, int nscan, FeatFrame* f) {
   f->seg_flat = (int*)take(4 * ns * 10); f->seg_nflat = (int*)take(4 * ns);
   f->seg_valid = (int*)take(4 * ns); f->seg_sp = (int*)take(4 * ns); f->seg_ep = (int*)take(4 * ns);
   f->corner_idx = (int*)take(4 * (size_t)nscan * 120); f->sharp_idx = (int*)take(4 * (size_t)nscan * 24); f->flat_idx = (int*)take(4 * (size_t)nscan * 60);
-  f->M = (int*)take(4); f->counts = (int*)take(16);
+  f->M = (int*)take(4); f->counts = (int*)take(16); f->start_inv = (float*)take(36);
+  f->time = nullptr; f->imu_time = nullptr; f->imu_rot = nullptr; f->n_imu = 0; f->t_scan = 0.0;
 }
 
 static int feat_reserve(lisreg_ctx* ctx, int F, int cells, int nscan) {
@@ -743,13 +744,15 @@ static int feat_reserve(lisreg_ctx* ctx, int F, int cells, int nscan) {
 }
 
 // runs F1-F5 for F frames whose FeatFrame descriptors (device) are ready
-static int run_features(lisreg_ctx* ctx, FeatFrame* d_frames, int F, const lisreg_feat_params* prm, int max_n, double alg_bytes) {
+static int run_features(lisreg_ctx* ctx, FeatFrame* d_frames, int F, const lisreg_feat_params* prm, int max_n, double alg_bytes,
+                        bool with_deskew = false) {
   cudaStream_t st = ctx->cur->stream;
   FeatParamsDev dp{prm->n_scan, prm->horizon, prm->downsample_rate, prm->min_range, prm->max_range, prm->edge_thr, prm->surf_thr};
   const int cells = prm->n_scan * prm->horizon;
   ProfScope ps(ctx, PROF_FEAT, alg_bytes, 7);
   k_feat_clear<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
   k_feat_project<<<dim3(std::max(1, (max_n + 255) / 256), F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
+  if (with_deskew) { k_feat_deskew_start<<<F, 256, 0, st>>>(d_frames, dp); LAUNCH_CK(); }
   k_feat_ring_count<<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
   k_feat_compact<<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
   k_feat_curvature<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames); LAUNCH_CK();
@@ -759,26 +762,39 @@ static int run_features(lisreg_ctx* ctx, FeatFrame* d_frames, int F, const lisre
   return LISREG_OK;
 }
 
-int32_t lisreg_extract_features(lisreg_ctx* ctx, const float* pts, const uint16_t* ring, int32_t n,
-                                const lisreg_feat_params* prm, lisreg_feat_out* out) {
+static int extract_features_impl(lisreg_ctx* ctx, const float* pts, const uint16_t* ring, const float* time, int32_t n,
+                                 const lisreg_feat_params* prm, const lisreg_deskew* dsk, lisreg_feat_out* out, float* ext_xyzi) {
   if (!ctx || n < 0 || (n > 0 && (!pts || !ring)) || !prm || !out) return fail(ctx, LISREG_ERR_ARG, "lisreg_extract_features: bad argument");
   if (prm->n_scan <= 0 || prm->horizon <= 0 || prm->horizon > 2048 || prm->n_scan * 6 > 1024 || prm->downsample_rate <= 0)
     return fail(ctx, LISREG_ERR_ARG, "lisreg_extract_features: unsupported n_scan/horizon/downsample_rate");
+  const bool deskew = dsk && dsk->n_imu > 0;
+  if (deskew && (!time || !dsk->imu_time || !dsk->imu_rot)) return fail(ctx, LISREG_ERR_ARG, "lisreg_extract_features_deskew: time / IMU table missing");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const int cells = prm->n_scan * prm->horizon;
   int rc = feat_reserve(ctx, 1, cells, prm->n_scan);
   if (rc) return rc;
-  const size_t bp = sizeof(float4) * (size_t)n, br = sizeof(uint16_t) * (size_t)n;
-  CK(ctx->d_stage.reserve(bp + br + 64));
+  const size_t bp = sizeof(float4) * (size_t)n, br = (sizeof(uint16_t) * (size_t)n + 15) & ~size_t(15);
+  const size_t bt = deskew ? sizeof(float) * (size_t)n : 0, bi = deskew ? sizeof(double) * 4 * (size_t)dsk->n_imu : 0;
+  CK(ctx->d_stage.reserve(bp + br + ((bt + 15) & ~size_t(15)) + bi + 64));
   char* d = (char*)ctx->d_stage.p;
-  if (n) { CK(cudaMemcpyAsync(d, pts, bp, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(d + bp, ring, br, cudaMemcpyHostToDevice, st)); }
+  char* d_time = d + bp + br; char* d_imu = d_time + ((bt + 15) & ~size_t(15));
+  if (n) { CK(cudaMemcpyAsync(d, pts, bp, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(d + bp, ring, sizeof(uint16_t) * (size_t)n, cudaMemcpyHostToDevice, st)); }
+  if (deskew) {
+    if (n) CK(cudaMemcpyAsync(d_time, time, bt, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_imu, dsk->imu_time, sizeof(double) * (size_t)dsk->n_imu, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_imu + sizeof(double) * (size_t)dsk->n_imu, dsk->imu_rot, sizeof(double) * 3 * (size_t)dsk->n_imu, cudaMemcpyHostToDevice, st));
+  }
   FeatFrame f{};
   feat_carve((char*)ctx->cur->d_feat.p, cells, prm->n_scan, &f);
   f.pts = (const float4*)d; f.ring = (const uint16_t*)(d + bp); f.n = n;
+  if (deskew) {
+    f.time = (const float*)d_time; f.imu_time = (const double*)d_imu; f.imu_rot = (const double*)(d_imu + sizeof(double) * (size_t)dsk->n_imu);
+    f.n_imu = dsk->n_imu; f.t_scan = dsk->time_scan_cur;
+  }
   CK(cudaMemcpyAsync(ctx->cur->d_feat_frames.p, &f, sizeof(f), cudaMemcpyHostToDevice, st));
   CK(cudaStreamSynchronize(st));   // f is a stack object
-  rc = run_features(ctx, (FeatFrame*)ctx->cur->d_feat_frames.p, 1, prm, n, 17.0 * n);
+  rc = run_features(ctx, (FeatFrame*)ctx->cur->d_feat_frames.p, 1, prm, n, 17.0 * n, deskew);
   if (rc) return rc;
   int h[5];
   CK(cudaMemcpyAsync(&h[0], f.M, 4, cudaMemcpyDeviceToHost, st));
@@ -793,8 +809,19 @@ int32_t lisreg_extract_features(lisreg_ctx* ctx, const float* pts, const uint16_
   CK(dl(out->corner_idx, f.corner_idx, 4 * (size_t)h[1])); CK(dl(out->sharp_idx, f.sharp_idx, 4 * (size_t)h[2]));
   CK(dl(out->flat_idx, f.flat_idx, 4 * (size_t)h[3])); CK(dl(out->surf_idx, f.surf_idx, 4 * (size_t)h[4]));
   CK(dl(out->curvature, f.curv, 4 * M)); CK(dl(out->label, f.label, 4 * M));
+  CK(dl(ext_xyzi, f.ext_pts, 16 * M));
   CK(cudaStreamSynchronize(st));
   return LISREG_OK;
+}
+
+int32_t lisreg_extract_features(lisreg_ctx* ctx, const float* pts, const uint16_t* ring, int32_t n,
+                                const lisreg_feat_params* prm, lisreg_feat_out* out) {
+  return extract_features_impl(ctx, pts, ring, nullptr, n, prm, nullptr, out, nullptr);
+}
+
+int32_t lisreg_extract_features_deskew(lisreg_ctx* ctx, const float* pts, const uint16_t* ring, const float* time, int32_t n,
+                                       const lisreg_feat_params* prm, const lisreg_deskew* dsk, lisreg_feat_out* out, float* ext_xyzi) {
+  return extract_features_impl(ctx, pts, ring, time, n, prm, dsk, out, ext_xyzi);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -87,6 +87,11 @@ class EpscCloud(C.Structure):
                 ("nc", C.c_int32), ("ns", C.c_int32), ("nsem", C.c_int32), ("reserved", C.c_int32)]
 
 
+class Deskew(C.Structure):
+    _fields_ = [("imu_time", C.c_void_p), ("imu_rot", C.c_void_p), ("n_imu", C.c_int32), ("reserved", C.c_int32),
+                ("time_scan_cur", C.c_double)]
+
+
 class LoopParams(C.Structure):
     _fields_ = [("use_epsc", C.c_int32), ("use_sepsc", C.c_int32), ("use_fepsc", C.c_int32), ("use_pose", C.c_int32),
                 ("skip_neighbour_distance", C.c_float), ("inflation_covariance", C.c_float), ("distance_threshold", C.c_float),
@@ -196,6 +201,8 @@ def lib():
         L.lisreg_epsc_score_all_dev.restype = i32
         L.lisreg_epsc_score_all_dev.argtypes = [vp, vp, i32, i32, vp, vp, vp]
         L.lisreg_icp_params_default.argtypes = [C.POINTER(IcpParams)]
+        L.lisreg_extract_features_deskew.restype = i32
+        L.lisreg_extract_features_deskew.argtypes = [vp, vp, vp, vp, i32, C.POINTER(FeatParams), C.POINTER(Deskew), C.POINTER(FeatOut), vp]
         L.lisreg_loop_params_default.argtypes = [C.POINTER(LoopParams)]
         L.lisreg_loop_create.restype = i32
         L.lisreg_loop_create.argtypes = [vp, C.POINTER(LoopParams), C.POINTER(C.c_uint8), C.POINTER(i32)]
@@ -343,10 +350,12 @@ class Engine:
         return self._ck(lib().lisreg_scan2map_batch_arena(self._h, B, items, arena_ptr, arena_bytes,
                                                           pose.ctypes.data_as(C.POINTER(C.c_float)), C.byref(params), res))
 
-    def extract_features(self, pts, ring, prm=None):
-        """F1-F5 on one raw sweep (host buffers). Returns a dict shaped like oracle.orc.extract_features."""
+    def extract_features(self, pts, ring, prm=None, time=None, imu_time=None, imu_rot=None, time_scan_cur=0.0):
+        """F1-F5 on one raw sweep (host buffers). Returns a dict shaped like oracle.orc.extract_features.
+        With time + IMU rotation table: motion de-skew (lisreg_extract_features_deskew); adds 'ext_pts' (M,4)."""
         prm = prm or feat_params()
         p = _f4(pts); r = np.ascontiguousarray(ring, dtype=np.uint16)
+        deskew = time is not None
         cap = prm.n_scan * prm.horizon
         a = {"src_index": np.zeros(cap, np.int32), "col_ind": np.zeros(cap, np.int32), "range": np.zeros(cap, np.float32),
              "start_ring": np.zeros(prm.n_scan, np.int32), "end_ring": np.zeros(prm.n_scan, np.int32),
@@ -356,9 +365,21 @@ class Engine:
         out = FeatOut()
         for k, v in a.items():
             setattr(out, k, v.ctypes.data)
-        self._ck(lib().lisreg_extract_features(self._h, p.ctypes.data, r.ctypes.data, len(p), C.byref(prm), C.byref(out)))
+        ext = None
+        if deskew:
+            t = np.ascontiguousarray(time, np.float32)
+            it = np.ascontiguousarray(imu_time if imu_time is not None else np.zeros(0), np.float64)
+            ir = np.ascontiguousarray(imu_rot if imu_rot is not None else np.zeros((0, 3)), np.float64).reshape(-1)
+            dsk = Deskew(it.ctypes.data, ir.ctypes.data, len(it), 0, float(time_scan_cur))
+            ext = np.zeros((cap, 4), np.float32)
+            self._ck(lib().lisreg_extract_features_deskew(self._h, p.ctypes.data, r.ctypes.data, t.ctypes.data, len(p), C.byref(prm),
+                                                          C.byref(dsk), C.byref(out), ext.ctypes.data))
+        else:
+            self._ck(lib().lisreg_extract_features(self._h, p.ctypes.data, r.ctypes.data, len(p), C.byref(prm), C.byref(out)))
         M = out.n_extracted
         res = {"M": M, "start_ring": a["start_ring"], "end_ring": a["end_ring"]}
+        if ext is not None:
+            res["ext_pts"] = ext[:M].copy()
         for k in ("src_index", "col_ind", "range", "curvature", "label"):
             res[k] = a[k][:M]
         res["corner_idx"] = a["corner_idx"][:out.n_corner]; res["sharp_idx"] = a["sharp_idx"][:out.n_sharp]

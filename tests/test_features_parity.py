@@ -73,3 +73,34 @@ def test_edge_cases(engine):
     # only two rings populated: the other rings have start > end (skipped segments)
     keep = (s["ring"] == 10) | (s["ring"] == 40)
     _compare(engine, s["pts"][keep], s["ring"][keep], po, pg)
+
+
+def test_deskew_matches_oracle(engine):
+    """Motion de-skew of the projection (deskewPoint, laserProcessing.cpp:427-462): the de-skewed extracted cloud is
+    bit-exact vs the oracle; range / column / every feature list are those of the ORIGINAL sweep (as upstream)."""
+    from common import scene
+    pose = np.array([0.01, -0.02, 0.7, 3.0, -1.0, 0.0], np.float32)
+    s = scene().scan(pose, seed=2100)
+    rng = np.random.default_rng(21)
+    t_scan = 1000.25
+    n_imu = 30
+    imu_time = t_scan - 0.008 + np.arange(n_imu) * 0.0045 + rng.uniform(0, 1e-4, n_imu)      # covers [t_scan, t_scan + 0.1]
+    rate = np.array([0.05, -0.03, 0.6])                                                      # rad/s: a turn
+    imu_rot = np.zeros((n_imu, 3))
+    for i in range(1, n_imu):
+        imu_rot[i] = imu_rot[i - 1] + (rate + 0.02 * rng.standard_normal(3)) * (imu_time[i] - imu_time[i - 1])
+    base = engine.extract_features(s["pts"], s["ring"])
+    g = engine.extract_features(s["pts"], s["ring"], time=s["time"], imu_time=imu_time, imu_rot=imu_rot, time_scan_cur=t_scan)
+    for k in ("src_index", "col_ind", "range", "curvature", "label", "corner_idx", "sharp_idx", "flat_idx", "surf_idx"):
+        assert np.array_equal(base[k], g[k]), k
+    o = orc.deskew(s["pts"], s["time"], g["src_index"], imu_time, imu_rot, t_scan)
+    assert np.array_equal(o, g["ext_pts"])
+    moved = np.linalg.norm(g["ext_pts"][:, :3] - s["pts"][g["src_index"], :3], axis=1)
+    assert moved.max() > 0.5 and moved.min() < 1e-3          # 0.06 rad over the sweep at up to 70 m; the first point does not move
+    # disabled table (deskewFlag -1 / IMU unavailable): points pass through
+    g0 = engine.extract_features(s["pts"], s["ring"], time=s["time"], imu_time=np.zeros(0), imu_rot=np.zeros((0, 3)), time_scan_cur=t_scan)
+    assert np.array_equal(g0["ext_pts"], s["pts"][g0["src_index"]])
+    # a single table entry and point times outside the table: clamped to the end entries like findRotation
+    g1 = engine.extract_features(s["pts"], s["ring"], time=s["time"], imu_time=imu_time[:3], imu_rot=imu_rot[:3], time_scan_cur=t_scan)
+    o1 = orc.deskew(s["pts"], s["time"], g1["src_index"], imu_time[:3], imu_rot[:3], t_scan)
+    assert np.array_equal(o1, g1["ext_pts"])
