@@ -54,39 +54,70 @@ def load_traffic():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock / throttle-reason samples DURING the timed regions: NVML every 5 ms (nvidia-smi every 200 ms as the
+    fallback when pynvml is unavailable)."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index):
         super().__init__(daemon=True)
         self.idx = device_index
-        self.samples = []
+        self.samples = []          # (sm_mhz, max_mhz, set(reasons))
         self.stop_flag = False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        reasons = set()
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if mask & bit:
+                reasons.add(name)
+        self.samples.append((sm, self.max_mhz, reasons))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if not out:
+            return
+        s = [x.strip() for x in out.split(",")]
+        reasons = set()
+        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
+            if v.lower().startswith("active"):
+                reasons.add(name)
+        self.samples.append((float(s[1]), float(s[2]), reasons))
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self.nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.005 if self.nvml else 0.2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for s in self.samples:
-            try:
-                sm.append(float(s[1])); mx.append(float(s[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        if not sm:
+        if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        reasons = set()
+        for s in self.samples:
+            reasons |= s[2]
+        return {"sm_mhz": float(np.median([s[0] for s in self.samples])), "sm_max_mhz": float(max(s[1] for s in self.samples)),
+                "reasons": sorted(reasons), "samples": len(self.samples), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -31,7 +31,6 @@ extern "C" {
 #define LISREG_ERR_ARG (-1)
 #define LISREG_ERR_CUDA (-2)
 #define LISREG_ERR_CAPACITY (-3)
-#define LISREG_ERR_NCCL (-4)
 
 #define LISREG_LUT_SIZE 64
 #define LISREG_MAX_ITERS 32
@@ -125,6 +124,15 @@ int32_t lisreg_map_destroy(lisreg_ctx* ctx, int32_t map_id);
  * idx/sqd are nq x 5, sorted ascending; entries beyond the gate are idx=-1, sqd=FLT_MAX. */
 int32_t lisreg_knn5(lisreg_ctx* ctx, int32_t map_id, int32_t which, const float* queries,
                     int32_t nq, float sqdist_gate, int32_t* idx, float* sqd);
+
+/* map-based dynamic-object removal of the local-map update (SURVEY.md 8f "next" #2, kernel part): replaces
+ * map_scan_feature_pts_distance_removal (subMap.h:1063-1098; call site update_local_map :886-905, defaults
+ * center_radius 30, dyn_min 0.3, dyn_max 3.0, near 0.03).  feat = n x float4 in the map frame; keep[i] = 1 when the
+ * point survives (outside the centre disc, or nearest-map-point distance in (near, dyn_min) or beyond dyn_max);
+ * survivors keep their order.  The map is the cloud `which` (0 corner, 1 surf) of a lisreg_map_create'd map. */
+int32_t lisreg_map_distance_filter(lisreg_ctx* ctx, int32_t map_id, int32_t which, const float* feat, int32_t n,
+                                   float center_radius, float dyn_min, float dyn_max, float near_thre,
+                                   uint8_t* keep, int32_t* n_kept);
 
 /* ---- scan-to-map registration (B2) ----
  * Replaces OdomEstimationNode::scan2SubMapOptimization() (odomEstimationNode.cpp:596-626)

@@ -67,11 +67,11 @@ struct MapSlot {
 // alternate between the chunks of the pipelined e2e path, so that two chunks are in flight while a third uploads.
 struct WorkSet {
   cudaStream_t stream = nullptr;
-  DevBuf d_descs, d_states, d_partials, d_tickets, d_nbr, d_kstate, d_klist;
+  DevBuf d_descs, d_states, d_partials, d_nbr, d_kstate, d_klist;
   DevBuf d_feat, d_feat_frames, d_vox, d_vox_segs;
   int feat_cap_frames = 0, feat_cells = 0, feat_nscan = 0;
   void release() {
-    for (DevBuf* b : {&d_descs, &d_states, &d_partials, &d_tickets, &d_nbr, &d_kstate, &d_klist, &d_feat, &d_feat_frames, &d_vox, &d_vox_segs}) b->release();
+    for (DevBuf* b : {&d_descs, &d_states, &d_partials, &d_nbr, &d_kstate, &d_klist, &d_feat, &d_feat_frames, &d_vox, &d_vox_segs}) b->release();
   }
 };
 
@@ -487,6 +487,31 @@ int32_t lisreg_knn5(lisreg_ctx* ctx, int32_t map_id, int32_t which, const float*
   return LISREG_OK;
 }
 
+int32_t lisreg_map_distance_filter(lisreg_ctx* ctx, int32_t map_id, int32_t which, const float* feat, int32_t n, float center_radius,
+                                   float dyn_min, float dyn_max, float near_thre, uint8_t* keep, int32_t* n_kept) {
+  if (!ctx || map_id < 0 || map_id >= (int)ctx->maps.size() || !ctx->maps[map_id].used || n < 0 || (n > 0 && (!feat || !keep)))
+    return fail(ctx, LISREG_ERR_ARG, "lisreg_map_distance_filter: bad argument");
+  if (n_kept) *n_kept = n;
+  if (n <= 10) { for (int i = 0; i < n; i++) keep[i] = 1; return LISREG_OK; }     // subMap.h:1069-1070: small clouds are left alone
+  CK(cudaSetDevice(ctx->device));
+  const GridDev g = which == 0 ? ctx->maps[map_id].corner.g : ctx->maps[map_id].surf.g;
+  const size_t bq = sizeof(float4) * (size_t)n;
+  CK(ctx->d_stage.reserve(bq + (size_t)n + 64));
+  char* d = (char*)ctx->d_stage.p;
+  CK(cudaMemcpyAsync(d, feat, bq, cudaMemcpyHostToDevice, ctx->stream));
+  const float near2 = near_thre * near_thre, dmin2 = dyn_min * dyn_min, dmax2 = dyn_max * dyn_max;   // fp32 squares, like upstream
+  float top = dmin2;
+  if (std::isfinite(dmax2) && dmax2 > top) top = dmax2;
+  if (near2 > top) top = near2;
+  const float gate = top * 1.000001f + 1e-12f;
+  k_map_distance_filter<<<(n + 127) / 128, 128, 0, ctx->stream>>>(g, (const float4*)d, n, center_radius * center_radius, near2, dmin2, dmax2,
+                                                                     gate, (unsigned char*)(d + bq)); LAUNCH_CK();
+  CK(cudaMemcpyAsync(keep, d + bq, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (n_kept) { int c = 0; for (int i = 0; i < n; i++) c += keep[i] != 0; *n_kept = c; }
+  return LISREG_OK;
+}
+
 static void to_dev_params(const lisreg_lm_params* p, LmParamsDev* d) {
   d->max_iters = std::min(p->max_iters, (int)LISREG_MAX_ITERS); d->early_exit = p->early_exit;
   d->gate = p->sqdist_gate; d->conv_rot = p->conv_rot_deg; d->conv_trans = p->conv_trans_cm;
@@ -512,11 +537,9 @@ static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, dou
   const int max_tiles = std::max(1, (max_n + tile_pts - 1) / tile_pts);
   CK(ctx->cur->d_states.reserve(sizeof(RegState) * (size_t)B));
   CK(ctx->cur->d_partials.reserve(sizeof(double) * LM_NSUM * (size_t)B * max_tiles));
-  CK(ctx->cur->d_tickets.reserve(sizeof(int) * (size_t)B));
   RegState* states = (RegState*)ctx->cur->d_states.p;
   double* partials = (double*)ctx->cur->d_partials.p;
-  int* tickets = (int*)ctx->cur->d_tickets.p;
-  k_lm_init<<<(B + 127) / 128, 128, 0, st>>>(d_descs, states, d_pose, dp, tickets, B); LAUNCH_CK();
+  k_lm_init<<<(B + 127) / 128, 128, 0, st>>>(d_descs, states, d_pose, dp, B); LAUNCH_CK();
   // a block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...: batches get 32 blocks per registration
   // (the real tile count is only known on the device in the frame pipeline), a lone registration gets
   // one block per tile so that it spreads over the whole GPU

@@ -202,7 +202,7 @@ LISREG_HD inline void lm_solve_tail(RegState& st, const LmParamsDev& prm, const 
 }
 
 __global__ void k_lm_init(const RegDesc* __restrict__ descs, RegState* __restrict__ states, const float* __restrict__ pose_in,
-                          LmParamsDev prm, int* __restrict__ tickets, int B) {
+                          LmParamsDev prm, int B) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   RegState s;
@@ -214,7 +214,6 @@ __global__ void k_lm_init(const RegDesc* __restrict__ descs, RegState* __restric
   if (!(s.nc > prm.edge_min && s.ns > prm.surf_min)) { s.done = 1; s.status = LISREG_NOT_ENOUGH_FEATURES; }   // :598
   state_refresh(s);
   states[b] = s;
-  tickets[b] = 0;
 }
 
 __global__ void k_lm_finish(const RegState* __restrict__ states, float* __restrict__ pose_out, lisreg_lm_result* __restrict__ res, int B) {
@@ -601,7 +600,10 @@ k_knn_search(const RegDesc* __restrict__ descs, const RegState* __restrict__ sta
   }
 }
 
-__global__ void __launch_bounds__(LM_THREADS, 5)
+#ifndef LM_RESID_MIN_BLOCKS
+#define LM_RESID_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(LM_THREADS, LM_RESID_MIN_BLOCKS)
 k_lm_resid(const RegDesc* __restrict__ descs, const RegState* __restrict__ states, const MapDev* __restrict__ maps,
            LmParamsDev prm, const int* __restrict__ nbr, double* __restrict__ partials, int max_tiles, int tile_pts) {
   const int b = blockIdx.y, tid = threadIdx.x;
@@ -749,6 +751,27 @@ __global__ void k_selftest_smallmat(const float* __restrict__ A36, const float* 
   jacobi_eigen3(A36[0], A36[1], A36[2], A36[7], A36[8], A36[14], W3, V3);
   for (int i = 0; i < 3; i++) out[86 + i] = W3[i];
   for (int i = 0; i < 9; i++) out[89 + i] = V3[i];
+}
+
+// map-based dynamic-object removal (map_scan_feature_pts_distance_removal, subMap.h:1063-1098): a feature point
+// survives outside the centre disc, or when its squared distance d2 to the nearest map point satisfies
+// (d2 > near^2 && d2 < dyn_min^2) || d2 > dyn_max^2.  The 1-NN search is gated just above the largest finite
+// threshold: a miss means d2 exceeds every threshold, which decides the test without knowing d2.
+__global__ void k_map_distance_filter(GridDev g, const float4* __restrict__ feat, int n, float center_r2, float near2, float dmin2,
+                                      float dmax2, float gate, unsigned char* __restrict__ keep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(&feat[i]);
+  bool k;
+  if (p.x * p.x + p.y * p.y > center_r2) k = true;
+  else if (g.n <= 0) k = true;
+  else {
+    knn_key best[1];
+    knn_grid<1>(g, p.x, p.y, p.z, gate, best);
+    const float d2 = knn_key_pos(best[0]) >= 0 && knn_key_d(best[0]) < gate ? knn_key_d(best[0]) : KNN_INF;
+    k = (d2 > near2 && d2 < dmin2) || d2 > dmax2;
+  }
+  keep[i] = k ? 1 : 0;
 }
 
 // stand-alone exact 5-NN (tests / lisreg_knn5): the same flattened block scan + tracked shells as k_knn_search.

@@ -201,6 +201,8 @@ def lib():
         L.lisreg_epsc_score_all_dev.restype = i32
         L.lisreg_epsc_score_all_dev.argtypes = [vp, vp, i32, i32, vp, vp, vp]
         L.lisreg_icp_params_default.argtypes = [C.POINTER(IcpParams)]
+        L.lisreg_map_distance_filter.restype = i32
+        L.lisreg_map_distance_filter.argtypes = [vp, i32, i32, vp, i32, C.c_float, C.c_float, C.c_float, C.c_float, vp, C.POINTER(i32)]
         L.lisreg_extract_features_deskew.restype = i32
         L.lisreg_extract_features_deskew.argtypes = [vp, vp, vp, vp, i32, C.POINTER(FeatParams), C.POINTER(Deskew), C.POINTER(FeatOut), vp]
         L.lisreg_loop_params_default.argtypes = [C.POINTER(LoopParams)]
@@ -453,6 +455,15 @@ class Engine:
     def target_create(self, pts):
         """Registers an ICP target cloud (stored as the 'surf' cloud of a map slot)."""
         return self.map_create(np.zeros((0, 4), np.float32), pts, gate_hint=1.0)
+
+    def map_distance_filter(self, map_id, which, feat, center_radius=30.0, dyn_min=0.3, dyn_max=3.0, near=0.03):
+        """map_scan_feature_pts_distance_removal (subMap.h:1063-1098). Returns the keep mask (n,) bool."""
+        f = _f4(feat)
+        keep = np.zeros(max(len(f), 1), np.uint8)
+        nk = C.c_int32(0)
+        self._ck(lib().lisreg_map_distance_filter(self._h, map_id, which, f.ctypes.data, len(f), center_radius, dyn_min, dyn_max, near,
+                                                  keep.ctypes.data, C.byref(nk)))
+        return keep[:len(f)].astype(bool)
 
     def loop_create(self, lut, use_epsc=False, use_sepsc=False, use_fepsc=True, use_pose=False):
         """EPSCGeneration instance (loop detector) on the device; returns its id."""

@@ -135,6 +135,8 @@ def lib():
         L.orc_icp.restype = C.c_int
         L.orc_icp.argtypes = [fp, C.c_int32, fp, C.c_int32, C.POINTER(IcpParams), C.POINTER(IcpResult)]
         L.orc_deskew.argtypes = [fp, fp, ip, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32, C.c_double, fp]
+        L.orc_map_distance_filter.restype = C.c_int32
+        L.orc_map_distance_filter.argtypes = [fp, C.c_int32, fp, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, u8p]
         L.orc_loop_create.restype = C.c_void_p
         L.orc_loop_create.argtypes = [u8p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         L.orc_loop_free.argtypes = [C.c_void_p]
@@ -367,3 +369,11 @@ def deskew(pts4, time, src_index, imu_time, imu_rot, time_scan_cur):
     lib().orc_deskew(pp, t.ctypes.data_as(C.POINTER(C.c_float)), si.ctypes.data_as(C.POINTER(C.c_int32)), len(si),
                      it.ctypes.data_as(dp), ir.ctypes.data_as(dp), len(it), float(time_scan_cur), out.ctypes.data_as(C.POINTER(C.c_float)))
     return out
+
+
+def map_distance_filter(feat4, map4, center_radius=30.0, dyn_min=0.3, dyn_max=3.0, near=0.03):
+    """map_scan_feature_pts_distance_removal (subMap.h:1063-1098). Returns the keep mask (n,) bool."""
+    f, fp_ = _f(feat4); m, mp = _f(map4)
+    keep = np.zeros(len(f), np.uint8)
+    lib().orc_map_distance_filter(fp_, len(f), mp, len(m), center_radius, dyn_min, dyn_max, near, keep.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return keep.astype(bool)

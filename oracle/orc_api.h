@@ -106,6 +106,10 @@ int orc_icp(const float* src4, int32_t ns, const float* tgt4, int32_t nt, const 
 void orc_deskew(const float* pts4, const float* time, const int32_t* src_index, int32_t M,
                 const double* imu_time, const double* imu_rot3, int32_t n_imu, double time_scan_cur, float* out4);
 
+/* ---- map-based dynamic removal (subMap.h:1063-1098) ---- */
+int32_t orc_map_distance_filter(const float* feat4, int32_t n, const float* map4, int32_t m, float center_radius,
+                                float dyn_min, float dyn_max, float near_thre, uint8_t* keep);
+
 /* ---- EPSC loop detector (epscGeneration.cpp:84-120 project, :258-401 globalICP, :663-992 loopDetection) ---- */
 void* orc_loop_create(const uint8_t* using_map, int32_t use_epsc, int32_t use_sepsc, int32_t use_fepsc, int32_t use_pose);
 void orc_loop_free(void* h);

@@ -209,3 +209,20 @@ def test_knn_check_path_is_bit_identical_to_full_search(monkeypatch, variant):
         logs[noskip] = out
         eng.close()
     assert logs["0"] == logs["1"]
+
+
+def test_map_distance_filter_matches_oracle(engine, gpu_map):
+    """Map-based dynamic removal (map_scan_feature_pts_distance_removal, subMap.h:1063-1098): keep mask bit-exact."""
+    mid, m = gpu_map
+    rng = np.random.default_rng(11)
+    base = m["surf"][rng.choice(len(m["surf"]), 4000, replace=False)].copy()
+    # displacements spanning every branch: on the map (< near), inside the dynamic band, beyond dyn_max, outside the disc
+    disp = rng.choice([0.0, 0.01, 0.1, 0.5, 1.5, 4.0, 8.0], len(base))[:, None] * rng.standard_normal((len(base), 3))
+    feat = base.copy(); feat[:, :3] += disp.astype(np.float32)
+    for args in (dict(), dict(center_radius=15.0, dyn_min=0.5, dyn_max=2.0, near=0.05), dict(dyn_max=float(np.finfo(np.float32).max))):
+        ko = orc.map_distance_filter(feat, m["surf"], **args)
+        kg = engine.map_distance_filter(mid, 1, feat, **args)
+        assert np.array_equal(ko, kg), args
+        assert 0 < kg.sum() < len(kg)
+    small = feat[:10]
+    assert engine.map_distance_filter(mid, 1, small).all() and orc.map_distance_filter(small, m["surf"]).all()
