@@ -97,7 +97,7 @@ struct lisreg_ctx {
   int e2e_chunk = 128; // frames per chunk (LISREG_E2E_CHUNK; 0 = one copy, no overlap)
   // asynchronous submit / wait pipeline: two slots, each with its own staging arena, result buffers and work set
   // (ws[1 + slot]); the upload of one batch overlaps the compute of the other
-  struct AsyncSlot { DevBuf d_stage, d_res; PinBuf h_out, h_desc; cudaEvent_t done = nullptr; bool busy = false; int F = 0; };
+  struct AsyncSlot { DevBuf d_stage, d_res; PinBuf h_out, h_desc; cudaEvent_t done = nullptr, fence = nullptr; bool busy = false; int F = 0; };
   AsyncSlot slot[2];
   int next_slot = 0;
   int n_sm = 148;
@@ -374,7 +374,7 @@ void lisreg_destroy(lisreg_ctx* ctx) {
   for (auto& L : ctx->loops) if (L.used) { cudaFree(L.d_proj); cudaFree(L.d_desc); cudaFree(L.d_lut); }
   ctx->d_loop.release();
   for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
-  for (auto& sl : ctx->slot) { sl.d_stage.release(); sl.d_res.release(); sl.h_out.release(); sl.h_desc.release(); if (sl.done) cudaEventDestroy(sl.done); }
+  for (auto& sl : ctx->slot) { sl.d_stage.release(); sl.d_res.release(); sl.h_out.release(); sl.h_desc.release(); if (sl.done) cudaEventDestroy(sl.done); if (sl.fence) cudaEventDestroy(sl.fence); }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& p : ctx->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : ctx->ev_free) cudaEventDestroy(e);
@@ -445,6 +445,7 @@ int32_t lisreg_map_destroy(lisreg_ctx* ctx, int32_t map_id) {
   if (!ctx || map_id < 0 || map_id >= (int)ctx->maps.size() || !ctx->maps[map_id].used) return fail(ctx, LISREG_ERR_ARG, "lisreg_map_destroy: bad map id");
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 1; i < 3; i++) if (ctx->ws[i].stream) CK(cudaStreamSynchronize(ctx->ws[i].stream));   // batches still in flight may read the map
   MapSlot& m = ctx->maps[map_id];
   cudaFree(m.corner.sorted); cudaFree(m.corner.cell_start); cudaFree(m.surf.sorted); cudaFree(m.surf.cell_start);
   m = MapSlot();
@@ -891,7 +892,7 @@ static int run_voxel(lisreg_ctx* ctx, VoxSeg* d_segs, int nseg, int max_n, doubl
     k_rs_scatter<<<dim3(nblk, nseg), RS_THREADS, 0, st>>>(d_segs, 8 * pass, pass & 1); LAUNCH_CK();
   }
   k_vox_heads<<<nseg, 1024, 0, st>>>(d_segs); LAUNCH_CK();
-  k_vox_centroid<<<dim3(pblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
+  k_vox_centroid<<<dim3(std::max(1, (max_n + VC_CHUNK - 1) / VC_CHUNK), nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
   return LISREG_OK;
 }
 
@@ -1031,7 +1032,8 @@ int32_t lisreg_frames_batch_arena(lisreg_ctx* ctx, int32_t F, const lisreg_frame
   const int C = ctx->e2e_chunk;
   const int nchunk = (C > 0 && F > C) ? (F + C - 1) / C : 1;
   std::vector<uint64_t> lo((size_t)nchunk, ~0ull), hi((size_t)nchunk, 0ull);
-  bool pipelined = nchunk > 1;
+  // work sets 1 / 2 are shared with the submit / wait pipeline: while a ticket is in flight this call stays on set 0
+  bool pipelined = nchunk > 1 && !ctx->slot[0].busy && !ctx->slot[1].busy;
   if (pipelined) {
     for (int i = 0; i < F; i++) {
       const lisreg_frame_item& it = items[i];
@@ -1118,6 +1120,10 @@ int32_t lisreg_frames_batch_submit(lisreg_ctx* ctx, int32_t F, const lisreg_fram
   if (!sl.done) CK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
   int rc = sync_maps(ctx);
   if (rc) return rc;
+  // the slot's stream must see everything already enqueued on the context stream (e.g. a map index still being built)
+  if (!sl.fence) CK(cudaEventCreateWithFlags(&sl.fence, cudaEventDisableTiming));
+  CK(cudaEventRecord(sl.fence, ctx->stream));
+  CK(cudaStreamWaitEvent(w.stream, sl.fence, 0));
   const size_t head = (sizeof(float) * 6 * (size_t)F + 255) & ~size_t(255);
   CK(sl.d_stage.reserve(head + (size_t)arena_bytes + 16));
   CK(sl.d_res.reserve(sizeof(lisreg_lm_result) * (size_t)F));

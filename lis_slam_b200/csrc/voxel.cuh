@@ -271,28 +271,38 @@ __global__ void k_vox_heads(VoxSeg* segs) {
   if (threadIdx.x == 0) { s.seg_start[carry] = n; *s.out_n = carry; }
 }
 
-// (5) centroids: one thread per voxel, fp32 accumulation in ascending input index
-__global__ void k_vox_centroid(VoxSeg* segs) {
+// (5) centroids, fp32 accumulation in ascending input index (= sorted order inside a voxel: the sort is stable).
+// A block owns a chunk of VC_CHUNK sorted entries: all threads gather the chunk's points into shared memory with
+// coalesced index loads and VC_CHUNK / 256 independent gathers in flight per thread; then one thread per voxel that
+// STARTS in the chunk sums its entries in order out of shared memory (entries past the chunk end - a voxel that
+// straddles the boundary - come from global memory).  grid = (chunks_max, nseg)
+constexpr int VC_CHUNK = 2048;
+__global__ void __launch_bounds__(256)
+k_vox_centroid(VoxSeg* segs) {
   const VoxSeg s = segs[blockIdx.y];
+  const int n = vox_n(s);
+  const int c0 = blockIdx.x * VC_CHUNK;
+  if (c0 >= n) return;
+  const int c1 = min(c0 + VC_CHUNK, n);
   const int m = *s.out_n;
   const uint32_t* sval = (s.plan->npass & 1) ? s.val_b : s.val_a;
-  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < m; v += gridDim.x * blockDim.x) {
+  __shared__ float4 s_pts[VC_CHUNK];
+  __shared__ int s_vlo, s_vhi;
+  for (int j = c0 + threadIdx.x; j < c1; j += blockDim.x) s_pts[j - c0] = vox_point(s, (int)sval[j]);
+  if (threadIdx.x < 2) {
+    // first voxel whose start is >= c0 (thread 0) / >= c1 (thread 1): binary search over seg_start[0..m]
+    const int target = threadIdx.x == 0 ? c0 : c1;
+    int lo = 0, hi = m;                       // seg_start[m] = n >= target
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s.seg_start[mid] >= target) hi = mid; else lo = mid + 1; }
+    if (threadIdx.x == 0) s_vlo = lo; else s_vhi = lo;
+  }
+  __syncthreads();
+  for (int v = s_vlo + threadIdx.x; v < s_vhi; v += blockDim.x) {
     const int b = s.seg_start[v], e = s.seg_start[v + 1];
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-    int j = b;
-    // four gathers in flight; the fp32 accumulation keeps the ascending input order
-    for (; j + 4 <= e; j += 4) {
-      const float4 p0 = vox_point(s, (int)sval[j]), p1 = vox_point(s, (int)sval[j + 1]),
-                   p2 = vox_point(s, (int)sval[j + 2]), p3 = vox_point(s, (int)sval[j + 3]);
-      sx += p0.x; sy += p0.y; sz += p0.z; si += p0.w;
-      sx += p1.x; sy += p1.y; sz += p1.z; si += p1.w;
-      sx += p2.x; sy += p2.y; sz += p2.z; si += p2.w;
-      sx += p3.x; sy += p3.y; sz += p3.z; si += p3.w;
-    }
-    for (; j < e; j++) {
-      const float4 p = vox_point(s, (int)sval[j]);
-      sx += p.x; sy += p.y; sz += p.z; si += p.w;
-    }
+    const int e_in = min(e, c1);
+    for (int j = b; j < e_in; j++) { const float4 p = s_pts[j - c0]; sx += p.x; sy += p.y; sz += p.z; si += p.w; }
+    for (int j = e_in; j < e; j++) { const float4 p = vox_point(s, (int)sval[j]); sx += p.x; sy += p.y; sz += p.z; si += p.w; }
     const float c = (float)(e - b);
     s.out[v] = make_float4(sx / c, sy / c, sz / c, si / c);
   }
