@@ -67,11 +67,11 @@ struct MapSlot {
 // alternate between the chunks of the pipelined e2e path, so that two chunks are in flight while a third uploads.
 struct WorkSet {
   cudaStream_t stream = nullptr;
-  DevBuf d_descs, d_states, d_partials, d_nbr, d_kstate, d_klist;
+  DevBuf d_descs, d_states, d_partials, d_nbr, d_kstate, d_klist, d_geom;
   DevBuf d_feat, d_feat_frames, d_vox, d_vox_segs;
   int feat_cap_frames = 0, feat_cells = 0, feat_nscan = 0;
   void release() {
-    for (DevBuf* b : {&d_descs, &d_states, &d_partials, &d_nbr, &d_kstate, &d_klist, &d_feat, &d_feat_frames, &d_vox, &d_vox_segs}) b->release();
+    for (DevBuf* b : {&d_descs, &d_states, &d_partials, &d_nbr, &d_kstate, &d_klist, &d_geom, &d_feat, &d_feat_frames, &d_vox, &d_vox_segs}) b->release();
   }
 };
 
@@ -551,9 +551,11 @@ static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, dou
     if (slots >= (size_t)0xffffffffu) return fail(ctx, LISREG_ERR_CAPACITY, "batch too large: %zu query slots (split the batch)", slots);
     CK(ctx->cur->d_nbr.reserve(sizeof(int) * 5 * slots));
     CK(ctx->cur->d_kstate.reserve(sizeof(KnnState) * slots));
+    CK(ctx->cur->d_geom.reserve(sizeof(GeomCache) * slots));
     CK(ctx->cur->d_klist.reserve(sizeof(unsigned) * 2 * slots + sizeof(int) * 2 * LISREG_MAX_ITERS));
     int* nbr = (int*)ctx->cur->d_nbr.p;
     KnnState* kstate = (KnnState*)ctx->cur->d_kstate.p;
+    GeomCache* geom = (GeomCache*)ctx->cur->d_geom.p;
     unsigned* scan_list = (unsigned*)ctx->cur->d_klist.p;
     unsigned* shell_list = scan_list + slots;
     int* counters = (int*)(shell_list + slots);          // [it][2]: scan / shell list lengths of iteration it
@@ -562,13 +564,13 @@ static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, dou
     static_assert(LM_MAX_TILE == 512 && LM_THREADS == 128, "tile_shift assumes 512 / 128 query tiles");
     for (int it = 0; it < dp.max_iters; it++) {
       // iteration 0 searches every query; later iterations first try to PROVE that the neighbours did not change
-      k_knn_check<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, kstate, scan_list, counters + 2 * it,
+      k_knn_check<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, kstate, geom, scan_list, counters + 2 * it,
                                                max_tiles, tile_shift, (it > 0 && !ctx->knn_noskip) ? 1 : 0); LAUNCH_CK();
-      k_knn_search<false><<<ctx->n_sm * LM_KNN_MIN_BLOCKS, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, kstate, scan_list,
+      k_knn_search<false><<<ctx->n_sm * LM_KNN_MIN_BLOCKS, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, kstate, geom, scan_list,
                                                counters + 2 * it, shell_list, counters + 2 * it + 1, max_tiles, tile_shift); LAUNCH_CK();
-      k_knn_search<true><<<ctx->n_sm * 4, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, kstate, shell_list,
+      k_knn_search<true><<<ctx->n_sm * 4, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, kstate, geom, shell_list,
                                                counters + 2 * it + 1, nullptr, nullptr, max_tiles, tile_shift); LAUNCH_CK();
-      k_lm_resid<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp, nbr, partials, max_tiles, tile_pts); LAUNCH_CK();
+      k_lm_resid<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp, nbr, geom, partials, max_tiles, tile_pts); LAUNCH_CK();
       k_lm_solve<<<(B + LM_SOLVE_THREADS / 32 - 1) / (LM_SOLVE_THREADS / 32), LM_SOLVE_THREADS, 0, st>>>(
           d_descs, states, dp, partials, d_logs, max_tiles, tile_pts, B); LAUNCH_CK();
     }

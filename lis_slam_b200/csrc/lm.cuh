@@ -66,8 +66,15 @@ LISREG_HD inline void state_refresh(RegState& s) {
   s.trig[4] = F; s.trig[5] = E;   // srz crz <- roll
 }
 
-// cornerOptimization body after the kNN (:657-742). nb = 5 neighbours. raw = {la,lb,lc,ld2,s}
-LISREG_HD __forceinline__ bool corner_coeff(float x0, float y0, float z0, const float4 (&nb)[5], float (&raw)[5]) {
+// The coefficient of a correspondence splits into a part that depends on the 5 neighbours ONLY (the fitted line /
+// plane and its validity test) and a part that depends on the query position.  The first part is what costs (3x3
+// Jacobi eigen-decomposition, 5x3 column-pivoting QR) and it does not change while a query keeps its neighbours, so
+// k_lm_resid caches it per query (GeomCache) and k_knn_* invalidate it whenever the neighbour list changes.
+struct GeomCache { float4 a, b; };   // corner: a = {x1,y1,z1,x2}, b = {y2,z2,-,state}; surf: a = {pa,pb,pc,pd}, b = {-,-,-,state}
+constexpr float GEOM_INVALID = 0.f, GEOM_OK = 1.f, GEOM_REJECTED = 2.f;   // state (b.w)
+
+// cornerOptimization, neighbour part (:657-702): centroid, covariance, cv::eigen, line test, the two line points
+LISREG_HD __forceinline__ bool corner_geom(const float4 (&nb)[5], float (&ln)[6]) {
   float cx = 0, cy = 0, cz = 0;
 #pragma unroll
   for (int j = 0; j < 5; j++) { cx += nb[j].x; cy += nb[j].y; cz += nb[j].z; }
@@ -82,8 +89,13 @@ LISREG_HD __forceinline__ bool corner_coeff(float x0, float y0, float z0, const 
   float W[3], V[9];
   jacobi_eigen3(a11, a12, a13, a22, a23, a33, W, V);
   if (!(W[0] > 3 * W[1])) return false;
-  float x1 = (float)((double)cx + 0.1 * (double)V[0]), y1 = (float)((double)cy + 0.1 * (double)V[1]), z1 = (float)((double)cz + 0.1 * (double)V[2]);
-  float x2 = (float)((double)cx - 0.1 * (double)V[0]), y2 = (float)((double)cy - 0.1 * (double)V[1]), z2 = (float)((double)cz - 0.1 * (double)V[2]);
+  ln[0] = (float)((double)cx + 0.1 * (double)V[0]); ln[1] = (float)((double)cy + 0.1 * (double)V[1]); ln[2] = (float)((double)cz + 0.1 * (double)V[2]);
+  ln[3] = (float)((double)cx - 0.1 * (double)V[0]); ln[4] = (float)((double)cy - 0.1 * (double)V[1]); ln[5] = (float)((double)cz - 0.1 * (double)V[2]);
+  return true;
+}
+// cornerOptimization, query part (:704-742). raw = {la,lb,lc,ld2,s}
+LISREG_HD __forceinline__ bool corner_query(float x0, float y0, float z0, const float (&ln)[6], float (&raw)[5]) {
+  const float x1 = ln[0], y1 = ln[1], z1 = ln[2], x2 = ln[3], y2 = ln[4], z2 = ln[5];
   float a012 = sqrtf(((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1)) * ((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1)) +
                      ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1)) * ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1)) +
                      ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1)) * ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1)));
@@ -99,9 +111,15 @@ LISREG_HD __forceinline__ bool corner_coeff(float x0, float y0, float z0, const 
   raw[0] = la; raw[1] = lb; raw[2] = lc; raw[3] = ld2; raw[4] = s;
   return (double)s > 0.1;
 }
+// cornerOptimization body after the kNN (:657-742). nb = 5 neighbours. raw = {la,lb,lc,ld2,s}
+LISREG_HD __forceinline__ bool corner_coeff(float x0, float y0, float z0, const float4 (&nb)[5], float (&raw)[5]) {
+  float ln[6];
+  if (!corner_geom(nb, ln)) return false;
+  return corner_query(x0, y0, z0, ln, raw);
+}
 
-// surfOptimization body after the kNN (:776-821). raw = {pa,pb,pc,pd2,s}
-LISREG_HD __forceinline__ bool surf_coeff(float x0, float y0, float z0, const float4 (&nb)[5], float (&raw)[5]) {
+// surfOptimization, neighbour part (:776-806): plane fit A0 x = -1 (Eigen colPivHouseholderQr), normalisation, 5-point test
+LISREG_HD __forceinline__ bool surf_geom(const float4 (&nb)[5], float (&pl)[4]) {
   float A0[15], X0[3];
   const float B0[5] = {-1.f, -1.f, -1.f, -1.f, -1.f};
 #pragma unroll
@@ -114,11 +132,22 @@ LISREG_HD __forceinline__ bool surf_coeff(float x0, float y0, float z0, const fl
 #pragma unroll
   for (int j = 0; j < 5; j++)
     if ((double)fabsf(pa * nb[j].x + pb * nb[j].y + pc * nb[j].z + pd) > 0.2) valid = false;
-  if (!valid) return false;
+  pl[0] = pa; pl[1] = pb; pl[2] = pc; pl[3] = pd;
+  return valid;
+}
+// surfOptimization, query part (:808-821). raw = {pa,pb,pc,pd2,s}
+LISREG_HD __forceinline__ bool surf_query(float x0, float y0, float z0, const float (&pl)[4], float (&raw)[5]) {
+  const float pa = pl[0], pb = pl[1], pc = pl[2], pd = pl[3];
   float pd2 = pa * x0 + pb * y0 + pc * z0 + pd;
   float s = (float)(1.0 - 0.9 * (double)fabsf(pd2) / (double)sqrtf(sqrtf(x0 * x0 + y0 * y0 + z0 * z0)));
   raw[0] = pa; raw[1] = pb; raw[2] = pc; raw[3] = pd2; raw[4] = s;
   return (double)s > 0.1;
+}
+// surfOptimization body after the kNN (:776-821). raw = {pa,pb,pc,pd2,s}
+LISREG_HD __forceinline__ bool surf_coeff(float x0, float y0, float z0, const float4 (&nb)[5], float (&raw)[5]) {
+  float pl[4];
+  if (!surf_geom(nb, pl)) return false;
+  return surf_query(x0, y0, z0, pl, raw);
 }
 
 // scratch of the 6x6 solve; lives in SHARED memory on the device (one per solving warp)
@@ -408,10 +437,11 @@ __device__ __forceinline__ bool knn6_wide_flat(const GridDev& g, float qx, float
 }
 
 // writes the result of a real search: neighbour positions (or -1 = rejected) and the refreshed state
-__device__ __forceinline__ void knn_commit(int* __restrict__ tnbr, KnnState* __restrict__ tstate, int tile_pts, int l,
+__device__ __forceinline__ void knn_commit(int* __restrict__ tnbr, KnnState* __restrict__ tstate, GeomCache* __restrict__ tgeom, int tile_pts, int l,
                                            float qx, float qy, float qz, float gate,
                                            float d5, float d6, float lbu, const unsigned (&pos)[5]) {
   KnnState st; st.x = qx; st.y = qy; st.z = qz; st.s = 0.f;
+  tgeom[l].b.w = GEOM_INVALID;                 // new neighbour list: the cached line / plane is stale
   if (d5 < gate) {
 #pragma unroll
     for (int j = 0; j < 5; j++) tnbr[j * tile_pts + l] = (int)pos[j];
@@ -452,7 +482,7 @@ __device__ __forceinline__ KnnSlot knn_slot_decode(unsigned slot, int max_tiles,
 // ---- k_knn_check: grid (tiles, B), one thread per query ----
 __global__ void __launch_bounds__(LM_THREADS)
 k_knn_check(const RegDesc* __restrict__ descs, const RegState* __restrict__ states, const MapDev* __restrict__ maps,
-            float gate, int* __restrict__ nbr, KnnState* __restrict__ kstate, unsigned* __restrict__ scan_list,
+            float gate, int* __restrict__ nbr, KnnState* __restrict__ kstate, GeomCache* __restrict__ geom, unsigned* __restrict__ scan_list,
             int* __restrict__ counter, int max_tiles, int tile_shift, int use_state) {
   const int b = blockIdx.y, tid = threadIdx.x;
   const int tile_pts = 1 << tile_shift;
@@ -472,6 +502,7 @@ k_knn_check(const RegDesc* __restrict__ descs, const RegState* __restrict__ stat
     const size_t bt = (size_t)b * max_tiles + tile;
     int* tnbr = nbr + bt * 5 * tile_pts;         // [5][tile_pts]
     KnnState* tstate = kstate + bt * tile_pts;   // [tile_pts]
+    GeomCache* tgeom = geom + bt * tile_pts;
     for (int l = tid; l < tile_pts; l += LM_THREADS) {   // tile_pts is a multiple of LM_THREADS: warps stay whole
       bool need = false;
       if (l < qn) {
@@ -519,6 +550,7 @@ k_knn_check(const RegDesc* __restrict__ descs, const RegState* __restrict__ stat
                   if (changed) {
 #pragma unroll
                     for (int j = 0; j < 5; j++) tnbr[j * tile_pts + l] = knn_key_pos(key[j]);
+                    tgeom[l].b.w = GEOM_INVALID;   // same set, new order: the fits round differently
                   }
                 } else {
                   // the 5th neighbour left the gate: rejected now.  Its distance (>= sqrt(gate), and the neighbours are
@@ -544,7 +576,7 @@ k_knn_check(const RegDesc* __restrict__ descs, const RegState* __restrict__ stat
 template <bool SHELL>
 __global__ void __launch_bounds__(LM_THREADS, LM_KNN_MIN_BLOCKS)
 k_knn_search(const RegDesc* __restrict__ descs, const RegState* __restrict__ states, const MapDev* __restrict__ maps,
-             float gate, int* __restrict__ nbr, KnnState* __restrict__ kstate, const unsigned* __restrict__ list,
+             float gate, int* __restrict__ nbr, KnnState* __restrict__ kstate, GeomCache* __restrict__ geom, const unsigned* __restrict__ list,
              const int* __restrict__ counter, unsigned* __restrict__ shell_list, int* __restrict__ shell_counter,
              int max_tiles, int tile_shift) {
   __shared__ uint2 s_rng[(SHELL ? KNN_WIDE_ROWS : 9) * LM_THREADS];
@@ -572,25 +604,26 @@ k_knn_search(const RegDesc* __restrict__ descs, const RegState* __restrict__ sta
       const size_t bt = (size_t)ks.b * max_tiles + ks.tile;
       int* tnbr = nbr + bt * 5 * tile_pts;
       KnnState* tstate = kstate + bt * tile_pts;
+      GeomCache* tgeom = geom + bt * tile_pts;
       if (SHELL) {
         float bd[6]; unsigned bp[6]; float lbu;
         const float d5_block = tstate[ks.l].s;      // left by the block scan that deferred this query
         if (knn6_wide_flat(g, x0, y0, z0, gate, d5_block, bd, bp, s_rng + threadIdx.x, lbu)) {
           const unsigned pos[5] = {bp[0], bp[1], bp[2], bp[3], bp[4]};
-          knn_commit(tnbr, tstate, tile_pts, ks.l, x0, y0, z0, gate, bd[4], bd[5], lbu, pos);
+          knn_commit(tnbr, tstate, tgeom, tile_pts, ks.l, x0, y0, z0, gate, bd[4], bd[5], lbu, pos);
         } else {                                     // ball too wide for the staged rows (tiny cells): sequential walk
           knn_key best[6];
           const float lb2 = knn_ball_walk<6, 4>(g, x0, y0, z0, gate, KNN_PAD, best);
           const unsigned pos[5] = {(unsigned)knn_key_pos(best[0]), (unsigned)knn_key_pos(best[1]), (unsigned)knn_key_pos(best[2]),
                                    (unsigned)knn_key_pos(best[3]), (unsigned)knn_key_pos(best[4])};
-          knn_commit(tnbr, tstate, tile_pts, ks.l, x0, y0, z0, gate, knn_key_d(best[4]), knn_key_d(best[5]), lb2, pos);
+          knn_commit(tnbr, tstate, tgeom, tile_pts, ks.l, x0, y0, z0, gate, knn_key_d(best[4]), knn_key_d(best[5]), lb2, pos);
         }
       } else {
         float bd[6]; unsigned bp[6]; float lb;
         need_shell = knn6_block_flat(g, x0, y0, z0, gate, bd, bp, s_rng + threadIdx.x, lb);
         if (!need_shell) {
           const unsigned pos[5] = {bp[0], bp[1], bp[2], bp[3], bp[4]};
-          knn_commit(tnbr, tstate, tile_pts, ks.l, x0, y0, z0, gate, bd[4], bd[5], lb, pos);
+          knn_commit(tnbr, tstate, tgeom, tile_pts, ks.l, x0, y0, z0, gate, bd[4], bd[5], lb, pos);
         } else {
           tstate[ks.l].s = bd[4];                    // 5th best of the block: bounds the radius of the wide scan
         }
@@ -605,7 +638,7 @@ k_knn_search(const RegDesc* __restrict__ descs, const RegState* __restrict__ sta
 #endif
 __global__ void __launch_bounds__(LM_THREADS, LM_RESID_MIN_BLOCKS)
 k_lm_resid(const RegDesc* __restrict__ descs, const RegState* __restrict__ states, const MapDev* __restrict__ maps,
-           LmParamsDev prm, const int* __restrict__ nbr, double* __restrict__ partials, int max_tiles, int tile_pts) {
+           LmParamsDev prm, const int* __restrict__ nbr, GeomCache* __restrict__ geom, double* __restrict__ partials, int max_tiles, int tile_pts) {
   const int b = blockIdx.y, tid = threadIdx.x;
   __shared__ RegDesc sd;
   __shared__ float sT[12], sTrig[6];
@@ -626,6 +659,7 @@ k_lm_resid(const RegDesc* __restrict__ descs, const RegState* __restrict__ state
     const int q0 = tile * tile_pts;
     const int qn = min(n - q0, tile_pts);
     const int* tnbr = nbr + ((size_t)b * max_tiles + tile) * 5 * tile_pts;
+    GeomCache* tgeom = geom + ((size_t)b * max_tiles + tile) * tile_pts;
     int cntC = 0, cntS = 0;
     for (int l = tid; l < tile_pts; l += LM_THREADS) {
       float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -634,16 +668,34 @@ k_lm_resid(const RegDesc* __restrict__ descs, const RegState* __restrict__ state
         const int q = q0 + l;
         const bool is_corner = q < sd.nc;
         const float4 p = is_corner ? __ldg(&sd.corner[q]) : __ldg(&sd.surf[q - sd.nc]);
+        GeomCache gc = tgeom[l];
         const float x0 = sT[0] * p.x + sT[1] * p.y + sT[2] * p.z + sT[3];
         const float y0 = sT[4] * p.x + sT[5] * p.y + sT[6] * p.z + sT[7];
         const float z0 = sT[8] * p.x + sT[9] * p.y + sT[10] * p.z + sT[11];
-        const float4* __restrict__ pts = is_corner ? mp.corner.pts : mp.surf.pts;
-        float4 nb[5];
-        nb[0] = __ldg(&pts[pos0]);
+        if (gc.b.w == GEOM_INVALID) {
+          // the neighbour list changed since the fit was cached: gather, fit the line / plane, cache it
+          const float4* __restrict__ pts = is_corner ? mp.corner.pts : mp.surf.pts;
+          float4 nb[5];
+          nb[0] = __ldg(&pts[pos0]);
 #pragma unroll
-        for (int j = 1; j < 5; j++) nb[j] = __ldg(&pts[tnbr[j * tile_pts + l]]);
+          for (int j = 1; j < 5; j++) nb[j] = __ldg(&pts[tnbr[j * tile_pts + l]]);
+          if (is_corner) {
+            float ln[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const bool okg = corner_geom(nb, ln);
+            gc.a = make_float4(ln[0], ln[1], ln[2], ln[3]); gc.b = make_float4(ln[4], ln[5], 0.f, okg ? GEOM_OK : GEOM_REJECTED);
+          } else {
+            float pl[4];
+            const bool okg = surf_geom(nb, pl);
+            gc.a = make_float4(pl[0], pl[1], pl[2], pl[3]); gc.b = make_float4(0.f, 0.f, 0.f, okg ? GEOM_OK : GEOM_REJECTED);
+          }
+          tgeom[l] = gc;
+        }
         float raw[5];
-        const bool ok = is_corner ? corner_coeff(x0, y0, z0, nb, raw) : surf_coeff(x0, y0, z0, nb, raw);
+        bool ok = false;
+        if (gc.b.w == GEOM_OK) {
+          if (is_corner) { const float ln[6] = {gc.a.x, gc.a.y, gc.a.z, gc.a.w, gc.b.x, gc.b.y}; ok = corner_query(x0, y0, z0, ln, raw); }
+          else { const float pl[4] = {gc.a.x, gc.a.y, gc.a.z, gc.a.w}; ok = surf_query(x0, y0, z0, pl, raw); }
+        }
         if (ok) {
           float w = 1.0f;
           if (prm.use_w) {
