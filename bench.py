@@ -358,7 +358,7 @@ def run_ours(args, rank, world, local_rank):
     e2e = world * F * args.steps / (ms_e2e * 1e-3)
 
     # ---- roofline of the dominant stage: one Gauss-Newton iteration = kNN + residual + reduce + solve ----
-    # (five launches: k_knn_check, k_knn_search<scan>, k_knn_search<wide>, k_lm_resid, k_lm_solve; timed as a group with
+    # (six launches: k_knn_check, k_knn_coop, k_knn_search<scan>, k_knn_search<wide>, k_lm_resid, k_lm_solve; timed as a group with
     # CUDA events on the engine's stream inside the timed region)
     peak, peak_src = load_peaks()
     lm_launches = max(prof.lm_iter_launches, 1)          # = iterations timed
@@ -367,7 +367,7 @@ def run_ours(args, rank, world, local_rank):
     ach = alg_per_launch / (avg_launch_ms * 1e-3) / 1e9
     traffic = load_traffic()
     stage_ms = {"features": prof.feat_ms / args.steps, "voxel_grid": prof.voxel_ms / args.steps, "lm_iterations": prof.lm_iter_ms / args.steps}
-    roofline = {"bound": "hbm", "kernel": "GN iteration = k_knn_check + k_knn_search<scan> + k_knn_search<wide> + k_lm_resid + k_lm_solve",
+    roofline = {"bound": "hbm", "kernel": "GN iteration = k_knn_check + k_knn_coop + k_knn_search<scan> + k_knn_search<wide> + k_lm_resid + k_lm_solve",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "peak_source": peak_src, "traffic": (traffic or {}).get("dram_bytes_per_iteration"),
                 "traffic_source": (traffic or {}).get("source"),

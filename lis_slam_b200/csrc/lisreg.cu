@@ -113,6 +113,7 @@ struct lisreg_ctx {
   };
   std::vector<LoopDet> loops;
   DevBuf d_loop;                           // per-call scratch of lisreg_loop_detect
+  int knn_coop_max = 16384;   // scan lists shorter than this are searched warp-per-query (LISREG_KNN_COOP_MAX; 0 = never)
   int knn_noskip = 0;   // LISREG_KNN_NOSKIP=1: search every query from scratch at every iteration (parity check of the CHECK path)
   // profiling
   bool prof_on = false;
@@ -355,6 +356,7 @@ int32_t lisreg_create(const lisreg_config* cfg, lisreg_ctx** out) {
   if (cfg && cfg->max_grid_cells > 0) ctx->max_cells = cfg->max_grid_cells;
   { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, ctx->device) == cudaSuccess && v > 0) ctx->n_sm = v; }
   if (const char* e2 = getenv("LISREG_KNN_NOSKIP")) ctx->knn_noskip = atoi(e2) ? 1 : 0;
+  if (const char* e4 = getenv("LISREG_KNN_COOP_MAX")) ctx->knn_coop_max = std::max(0, atoi(e4));
   if (const char* e3 = getenv("LISREG_E2E_CHUNK")) ctx->e2e_chunk = std::max(0, atoi(e3));
   *out = ctx;
   return LISREG_OK;
@@ -566,10 +568,13 @@ static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, dou
       // iteration 0 searches every query; later iterations first try to PROVE that the neighbours did not change
       k_knn_check<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, kstate, geom, scan_list, counters + 2 * it,
                                                max_tiles, tile_shift, (it > 0 && !ctx->knn_noskip) ? 1 : 0); LAUNCH_CK();
+      // short scan lists (late iterations) go to the warp-per-query kernel, long ones to the thread-per-query scan
+      k_knn_coop<<<ctx->n_sm * 8, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, kstate, geom, scan_list, counters + 2 * it,
+                                               ctx->knn_coop_max, max_tiles, tile_shift); LAUNCH_CK();
       k_knn_search<false><<<ctx->n_sm * LM_KNN_MIN_BLOCKS, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, kstate, geom, scan_list,
-                                               counters + 2 * it, shell_list, counters + 2 * it + 1, max_tiles, tile_shift); LAUNCH_CK();
+                                               counters + 2 * it, shell_list, counters + 2 * it + 1, ctx->knn_coop_max, max_tiles, tile_shift); LAUNCH_CK();
       k_knn_search<true><<<ctx->n_sm * 4, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, kstate, geom, shell_list,
-                                               counters + 2 * it + 1, nullptr, nullptr, max_tiles, tile_shift); LAUNCH_CK();
+                                               counters + 2 * it + 1, nullptr, nullptr, 0, max_tiles, tile_shift); LAUNCH_CK();
       k_lm_resid<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp, nbr, geom, partials, max_tiles, tile_pts); LAUNCH_CK();
       k_lm_solve<<<(B + LM_SOLVE_THREADS / 32 - 1) / (LM_SOLVE_THREADS / 32), LM_SOLVE_THREADS, 0, st>>>(
           d_descs, states, dp, partials, d_logs, max_tiles, tile_pts, B); LAUNCH_CK();

@@ -268,6 +268,7 @@ __device__ __forceinline__ void lm_pair_of_lane(int lane, int& r, int& c) {
 }
 
 constexpr int LM_MAX_TILE = 512;
+constexpr int LM_ROW_STRIDE = LM_MAX_TILE + 1;   // shared-memory stride of a Jacobian row (doubles): odd => conflict-free column reads
 
 // ---------------------------------------------------------------------------------------------------------
 // One Gauss-Newton iteration = the 5-NN stage (k_knn_check -> k_knn_scan -> k_knn_shell: few registers, latency
@@ -578,10 +579,11 @@ __global__ void __launch_bounds__(LM_THREADS, LM_KNN_MIN_BLOCKS)
 k_knn_search(const RegDesc* __restrict__ descs, const RegState* __restrict__ states, const MapDev* __restrict__ maps,
              float gate, int* __restrict__ nbr, KnnState* __restrict__ kstate, GeomCache* __restrict__ geom, const unsigned* __restrict__ list,
              const int* __restrict__ counter, unsigned* __restrict__ shell_list, int* __restrict__ shell_counter,
-             int max_tiles, int tile_shift) {
+             int min_list, int max_tiles, int tile_shift) {
   __shared__ uint2 s_rng[(SHELL ? KNN_WIDE_ROWS : 9) * LM_THREADS];
   const int tile_pts = 1 << tile_shift;
   const int total = *counter;
+  if (total < min_list) return;             // short lists are searched by k_knn_coop
   const int lane = threadIdx.x & 31;
   for (int base = (blockIdx.x * LM_THREADS + threadIdx.x) - lane; base < total; base += gridDim.x * LM_THREADS) {
     const int i = base + lane;
@@ -633,6 +635,115 @@ k_knn_search(const RegDesc* __restrict__ descs, const RegState* __restrict__ sta
   }
 }
 
+// ---- k_knn_coop: WARP per query, for SHORT scan lists (late iterations: a few hundred queries whose proof failed).
+// A thread-per-query search of a short list is pure latency (one thread walks ~50-100 dependent candidates while the
+// GPU idles); here the 32 lanes split the row streaks of the ball of radius sqrt(gate) + KNN_PAD (same pruning / clipping
+// as knn6_wide_flat), each keeps a private top-6 (positions ascend inside a lane), and six warp arg-min rounds on
+// (d^2, position) keys merge them - exact, complete (no deferral), ~10x shorter dependent chain.
+// Runs only when the list is shorter than `max_list`; k_knn_search<false> runs only when it is not.
+__global__ void __launch_bounds__(LM_THREADS)
+k_knn_coop(const RegDesc* __restrict__ descs, const RegState* __restrict__ states, const MapDev* __restrict__ maps,
+           float gate, int* __restrict__ nbr, KnnState* __restrict__ kstate, GeomCache* __restrict__ geom, const unsigned* __restrict__ list,
+           const int* __restrict__ counter, int max_list, int max_tiles, int tile_shift) {
+  const int total = *counter;
+  if (total >= max_list) return;
+  const int tile_pts = 1 << tile_shift;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * LM_THREADS + threadIdx.x) >> 5, nwarps = (gridDim.x * LM_THREADS) >> 5;
+  const unsigned FULL = 0xffffffffu;
+  for (int i = warp; i < total; i += nwarps) {
+    const unsigned slot = list[i];
+    const KnnSlot ks = knn_slot_decode(slot, max_tiles, tile_shift);
+    const RegDesc* __restrict__ d = &descs[ks.b];
+    const RegState* __restrict__ st = &states[ks.b];
+    const int nc = st->nc;
+    const bool is_corner = ks.q < nc;
+    const float4 p = is_corner ? __ldg(&d->corner[ks.q]) : __ldg(&d->surf[ks.q - nc]);
+    const float x0 = st->T[0] * p.x + st->T[1] * p.y + st->T[2] * p.z + st->T[3];
+    const float y0 = st->T[4] * p.x + st->T[5] * p.y + st->T[6] * p.z + st->T[7];
+    const float z0 = st->T[8] * p.x + st->T[9] * p.y + st->T[10] * p.z + st->T[11];
+    const MapDev& mp = maps[d->map_slot];
+    const GridDev& g = is_corner ? mp.corner : mp.surf;
+    const size_t bt = (size_t)ks.b * max_tiles + ks.tile;
+    int* tnbr = nbr + bt * 5 * tile_pts;
+    KnnState* tstate = kstate + bt * tile_pts;
+    GeomCache* tgeom = geom + bt * tile_pts;
+    float bd[6]; unsigned bp[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) { bd[j] = KNN_INF; bp[j] = 0xffffffffu; }
+    float lbu = KNN_INF;
+    bool fallback = false;
+    if (g.n > 0) {
+      const float eps = 1e-3f;
+      const float fx = (x0 - g.ox) * g.inv_h, fy = (y0 - g.oy) * g.inv_h, fz = (z0 - g.oz) * g.inv_h;
+      const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
+      const float rx = fx - (float)cx, ry = fy - (float)cy, rz = fz - (float)cz;
+      const float minf = fminf(fminf(fminf(rx, 1.f - rx), fminf(ry, 1.f - ry)), fminf(rz, 1.f - rz));
+      const float Rn = sqrtf(gate) + KNN_PAD;
+      int T = (int)ceilf(Rn * g.inv_h - minf + eps);
+      if (T < 1) T = 1;
+      const int side = 2 * T + 1, nrows = side * side;
+      if (nrows > 64) fallback = true;                         // tiny cells: lane 0 walks the ball sequentially
+      else {
+        // rows r = lane and lane + 32 (ascending (z, y) order inside a lane => ascending positions)
+#pragma unroll 1
+        for (int rr = 0; rr < 2; rr++) {
+          const int r = lane + 32 * rr;
+          if (r >= nrows) break;
+          const int z = cz - T + r / side, y = cy - T + r % side;
+          if (z < 0 || z >= g.nz || y < 0 || y >= g.ny) continue;
+          float dz = z < cz ? fz - (float)(z + 1) : (z > cz ? (float)z - fz : 0.f);
+          dz = dz - eps > 0.f ? dz - eps : 0.f;
+          float dy = y < cy ? fy - (float)(y + 1) : (y > cy ? (float)y - fy : 0.f);
+          dy = dy - eps > 0.f ? dy - eps : 0.f;
+          const float rem = Rn * Rn - (dy * dy + dz * dz) * g.h * g.h;
+          if (rem < 0.f) continue;
+          const float rad = sqrtf(rem) * g.inv_h + eps;
+          int xa = (int)floorf(fx - rad), xb = (int)floorf(fx + rad);
+          xa = xa > cx - T ? xa : cx - T; xb = xb < cx + T ? xb : cx + T;
+          xa = xa > 0 ? xa : 0; xb = xb < g.nx - 1 ? xb : g.nx - 1;
+          if (xa > xb) continue;
+          const int rowbase = (z * g.ny + y) * g.nx;
+          const uint32_t b = __ldg(&g.cell_start[rowbase + xa]), e = __ldg(&g.cell_start[rowbase + xb + 1]);
+          for (uint32_t c = b; c < e; c++) {
+            const float dd = knn_dist2(x0, y0, z0, __ldg(&g.pts[c]));
+            if (dd < bd[5]) knn6_insert_mono(bd, bp, dd, c);
+          }
+        }
+        lbu = Rn;
+      }
+    }
+    unsigned pos[5] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    float d5 = KNN_INF, d6 = KNN_INF;
+    if (fallback) {
+      if (lane == 0) {
+        knn_key best[6];
+        lbu = knn_ball_walk<6, 4>(g, x0, y0, z0, gate, KNN_PAD, best);
+#pragma unroll
+        for (int j = 0; j < 5; j++) pos[j] = (unsigned)knn_key_pos(best[j]);
+        d5 = knn_key_d(best[4]); d6 = knn_key_d(best[5]);
+      }
+    } else {
+      // merge the 32 private ascending lists: six rounds of warp arg-min on (d^2 bits, position)
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const unsigned hd = __float_as_uint(bd[0]);                       // d^2 >= 0: bit order == value order; +inf = empty
+        const unsigned md = __reduce_min_sync(FULL, hd);
+        const unsigned mpos = __reduce_min_sync(FULL, hd == md ? bp[0] : 0xffffffffu);
+        if (hd == md && bp[0] == mpos && mpos != 0xffffffffu) {           // the owning lane pops its head
+#pragma unroll
+          for (int j = 0; j < 5; j++) { bd[j] = bd[j + 1]; bp[j] = bp[j + 1]; }
+          bd[5] = KNN_INF; bp[5] = 0xffffffffu;
+        }
+        if (k < 5) pos[k] = mpos;
+        if (k == 4) d5 = __uint_as_float(md);
+        if (k == 5) d6 = __uint_as_float(md);
+      }
+    }
+    if (lane == 0) knn_commit(tnbr, tstate, tgeom, tile_pts, ks.l, x0, y0, z0, gate, d5, d6, lbu, pos);
+  }
+}
+
 #ifndef LM_RESID_MIN_BLOCKS
 #define LM_RESID_MIN_BLOCKS 5
 #endif
@@ -643,7 +754,9 @@ k_lm_resid(const RegDesc* __restrict__ descs, const RegState* __restrict__ state
   __shared__ RegDesc sd;
   __shared__ float sT[12], sTrig[6];
   __shared__ int sdone;
-  __shared__ float s_row[7 * LM_MAX_TILE];
+  // Jacobian rows as doubles (converted once per element instead of once per product), row stride LM_ROW_STRIDE: the 27
+  // lanes of the reduction read up to 7 different rows at the same column, the odd stride puts them in different banks
+  __shared__ double s_row[7 * LM_ROW_STRIDE];
   __shared__ double swarp[LM_THREADS / 32][LM_NSUM];
   if (tid == 0) { sd = descs[b]; sd.nc = states[b].nc; sd.ns = states[b].ns; sdone = states[b].done; }
   if (tid < 12) sT[tid] = states[b].T[tid];
@@ -721,17 +834,17 @@ k_lm_resid(const RegDesc* __restrict__ descs, const RegState* __restrict__ state
         }
       }
 #pragma unroll
-      for (int k = 0; k < 7; k++) s_row[k * LM_MAX_TILE + l] = row[k];
+      for (int k = 0; k < 7; k++) s_row[k * LM_ROW_STRIDE + l] = (double)row[k];
     }
     __syncthreads();
     {
       int r, c;
       lm_pair_of_lane(lane < 27 ? lane : 0, r, c);
       const int per_warp = tile_pts / (LM_THREADS / 32);
-      const float* __restrict__ ra = s_row + r * LM_MAX_TILE + wid * per_warp;
-      const float* __restrict__ rc = s_row + c * LM_MAX_TILE + wid * per_warp;
+      const double* __restrict__ ra = s_row + r * LM_ROW_STRIDE + wid * per_warp;
+      const double* __restrict__ rc = s_row + c * LM_ROW_STRIDE + wid * per_warp;
       double v = 0.0;
-      for (int i = 0; i < per_warp; i++) v += (double)ra[i] * (double)rc[i];
+      for (int i = 0; i < per_warp; i++) v += ra[i] * rc[i];
       if (lane < 27) swarp[wid][lane] = v;
       int cc = cntC, s2 = cntS;
 #pragma unroll
