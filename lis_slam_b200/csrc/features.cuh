@@ -297,7 +297,8 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
   __shared__ unsigned char s_pick[FEAT_WARPS][FEAT_RING_MAX];
   __shared__ unsigned char s_reach[FEAT_WARPS][FEAT_RING_MAX];   // suppression reach of every point: right | left << 4
   __shared__ unsigned short s_col[FEAT_WARPS][FEAT_RING_MAX];
-  __shared__ float s_cv[FEAT_WARPS][32 * FEAT_CH];               // curvature of the current segment, slot-major
+  __shared__ float s_cv[FEAT_WARPS][32 * FEAT_CH];
+  __shared__ unsigned s_gap[FEAT_WARPS][FEAT_RING_MAX / 32 + 3];  // column-gap bits of the ring window               // curvature of the current segment, slot-major
   if (ring >= prm.n_scan) return;
   const unsigned FULL = 0xffffffffu;
   const int M = *f.M;
@@ -311,11 +312,25 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
   unsigned char* sreach = s_reach[wid];
   for (int t = lane; t < wlen; t += 32) { spick[t] = (unsigned char)f.picked[lo + t]; scol[t] = (unsigned short)f.col[lo + t]; }
   __syncwarp();
-  // how far a pick of each point suppresses to the right / left depends on the column indices only: once per point
+  // How far a pick of each point suppresses to the right / left (:648-661) depends on the column indices only:
+  // gap bit t = "the walk cannot step from t to t+1" (column jump > 10, or t+1 outside the window / the cloud); the
+  // reach of a point is the run of clear gap bits next to it, capped at 5 - one ffs / clz per point.
+  unsigned* sgap = s_gap[wid];
+  for (int base = 0; base < wlen + 32; base += 32) {
+    const int t = base + lane;
+    const bool gap = (t + 1 >= wlen) || abs((int)scol[t + 1] - (int)scol[t]) > 10;
+    const unsigned m = __ballot_sync(FULL, gap);
+    if (lane == 0) sgap[base >> 5] = m;
+  }
+  __syncwarp();
   for (int t = lane; t < wlen; t += 32) {
-    int a0, b0;
-    feat_mark_range(scol, lo, wlen, lo + t, M, a0, b0);
-    sreach[t] = (unsigned char)((b0 - (lo + t)) | ((lo + t - a0) << 4));
+    const int w = t >> 5, b = t & 31;
+    const unsigned right = __funnelshift_r(sgap[w], sgap[w + 1], b);                 // bit k = gap[t + k]
+    const unsigned below = w > 0 ? sgap[w - 1] : 0xffffffffu;                         // before the window: gaps
+    const unsigned left = b ? __funnelshift_l(below, sgap[w], 32 - b) : below;        // bit 31 - k = gap[t - 1 - k]
+    const int rr = min(5, __ffs(right | 0x20u) - 1);
+    const int rl = min(5, __clz(left));
+    sreach[t] = (unsigned char)(rr | (rl << 4));
   }
   __syncwarp();
   for (int j = 0; j < 6; j++) {

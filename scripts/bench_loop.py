@@ -53,6 +53,10 @@ def main():
     # ---- F17/F18: online detector ----
     from common import loop_keyframes
     kfs = loop_keyframes()
+    warm = eng.loop_create(orc.using_map_lut(), use_fepsc=True)      # first pass: staging buffers, history allocation
+    for (c, s, sem, lab, od) in kfs:
+        eng.loop_detect(warm, c, s, sem, lab, od)
+    eng.loop_destroy(warm)
     det = eng.loop_create(orc.using_map_lut(), use_fepsc=True)
     odet = orc.LoopDetector(use_fepsc=True)
     tg, tc, ncand = 0.0, 0.0, 0
