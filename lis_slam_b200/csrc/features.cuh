@@ -377,8 +377,9 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
       if (idx < ep && cv[t] > prm.edge_thr && spick[idx - lo] == 0) alive |= 1u << (int)((rank_of_slot >> (4 * t)) & 15ull);
     }
     int nc = 0;
-    if (cv_ep > prm.edge_thr && spick[ep - lo] == 0) {          // k = ep comes first
-      __syncwarp();
+    const bool ep_edge = cv_ep > prm.edge_thr && spick[ep - lo] == 0;
+    __syncwarp();                                               // every lane has read the flags before any pick rewrites them
+    if (ep_edge) {                                              // k = ep comes first
       if (lane == 0) { f.label[ep] = 1; f.seg_corner[seg * 20 + nc] = ep; }
       nc++;
       mark(ep, alive);
@@ -407,7 +408,8 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
       const int idx = sp + 32 * t + lane;
       if (idx < ep && cv[t] < prm.surf_thr && spick[idx - lo] == 0) alive |= 1u << (int)((rank_of_slot >> (4 * t)) & 15ull);
     }
-    int nf = 0, npick2 = 0;
+    int nf = 0;
+    __syncwarp();                                               // flags read, picks may rewrite them
     for (;;) {
       // per-lane best = lowest alive rank; key = (curvature bits, index) ascending; 0xffffffff = no candidate
       unsigned bh = 0xffffffffu, bl = 0xffffffffu;
@@ -420,18 +422,17 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
       const int ind = (int)__reduce_min_sync(FULL, bh == mh ? bl : 0xffffffffu);
       if (lane == 0) { f.label[ind] = -1; if (nf < 10) f.seg_flat[seg * 10 + nf] = ind; }
       if (nf < 10) nf++;
-      npick2++;
       mark(ind, alive);
     }
     __syncwarp();
-    if (cv_ep < prm.surf_thr && spick[ep - lo] == 0) {          // k = ep comes last
-      __syncwarp();
+    const bool ep_flat = cv_ep < prm.surf_thr && spick[ep - lo] == 0;
+    __syncwarp();
+    if (ep_flat) {                                              // k = ep comes last
       if (lane == 0) { f.label[ep] = -1; if (nf < 10) f.seg_flat[seg * 10 + nf] = ep; }
       if (nf < 10) nf++;
       unsigned dummy = 0u;
       mark(ep, dummy);
     }
-    (void)npick2;
     if (lane == 0) { f.seg_ncorner[seg] = nc; f.seg_nflat[seg] = nf; }
     __syncwarp();
   }
