@@ -39,6 +39,26 @@ counts differ between the queries of a warp: flattened-scan lane efficiency ≈ 
 straight-line fp32 computation at 96 registers (29 % warps active); `k_feat_segments` is the selection loop (latency of
 the per-pick `redux.sync` chain at 28 % warps active).  `k_vox_centroid` (gathers of 16 B points), `k_feat_compact` and
 `k_rs_scatter` are the DRAM-heavy ones.""")
+print("""
+## What moved the number this round (each row = a committed state measured with `python bench.py` on a pool B200)
+
+| state | `value` frames/s | `e2e` frames/s | stage ms per 256-frame step (features / voxel grid / 10 GN iterations) |
+|---|---|---|---|
+| start: one kNN kernel + one residual kernel per iteration, sort-based feature selection, blocking e2e call | 16 630 | 10 430 | 5.79 / 2.47 / 6.99 |
+| kNN: proof of unchanged neighbours (safe radius), flattened block scan | 18 970 | 11 310 | 5.84 / 2.51 / 5.02 |
+| feature selection as a warp-wide selection loop (no sort); check / scan / deferred kernels over dense global lists; bounds for rejected queries | 26 100 | 13 530 | 2.98 / 2.47 / 4.23 |
+| e2e through `lisreg_frames_batch_submit / _wait` (upload of step k+1 overlaps compute of step k) | 26 080 | 22 170 | |
+| deferred queries: flattened scan of the pruned ball instead of a sequential shell walk | 28 110 | 24 900 | 2.98 / 2.47 / 3.54 |
+| parallel `k_feat_gather`, ballot head scan, radix passes only over the digits the largest voxel index needs | 29 780 | 25 440 | 2.73 / 2.22 / 3.52 |
+| per-lane pre-ranked slots in the selection loop | 30 560 | 25 520 | 2.50 / 2.22 / 3.52 |
+| block-cooperative voxel centroids | 31 210 | 25 530 | 2.54 / 2.03 / 3.52 |
+| warp-per-query search for short lists, fp64 reduction on padded double rows (no bank conflicts, no per-product conversions), cached line / plane fits | 34 010 | 25 730 | 2.54 / 2.03 / 2.84 |
+| suppression reach from gap bits | 34 640 | 25 730 | 2.40 / 2.03 / 2.84 |
+
+`e2e` stopped moving at ≈ 25.7 k frames/s because it is PCIe-bound: 510 MB of sweeps per step at ≈ 55 GB/s is 9.2 ms, the step takes 9.95 ms.
+Tried and dropped (measured, no gain): 6 / 8 resident blocks for `k_lm_resid`, 10 / 12 for the scan kernel (±1 %); a separate fit kernel over the
+changed-query lists (slower in iterations 0-2, equal afterwards); grid cells of 0.45 / 0.5 / 0.55 / 0.7 m (0.6 m stays best); chunked upload inside the
+blocking call (each chunk pays the ~2.5 ms latency floor of the pipeline, so only 2 chunks break even).""")
 if loop:
     d = json.load(open(loop))
     print("\n## Loop-closure side (`scripts/bench_loop.py`, one B200; wall clock incl. H2D / D2H of the call)\n")
