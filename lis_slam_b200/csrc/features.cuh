@@ -54,10 +54,9 @@ __device__ __forceinline__ float atan2f_cr(float y, float x) { return (float)ata
 __global__ void k_feat_clear(FeatFrame* frames, FeatParamsDev prm) {
   const FeatFrame f = frames[blockIdx.y];
   const int cells = prm.n_scan * prm.horizon;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += gridDim.x * blockDim.x) {
-    f.owner[i] = 0x7fffffff;
-    f.picked[i] = 0; f.label[i] = 0; f.curv[i] = 0.f; f.col[i] = 0; f.range[i] = 0.f;
-  }
+  // only the range-image owners need a value in EVERY cell; the per-point arrays are initialised for the M extracted
+  // slots by k_feat_compact (nothing reads them beyond M)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += gridDim.x * blockDim.x) f.owner[i] = 0x7fffffff;
   if (blockIdx.x == 0 && threadIdx.x < 4) f.counts[threadIdx.x] = 0;
 }
 
@@ -217,37 +216,33 @@ __global__ void k_feat_compact(FeatFrame* frames, FeatParamsDev prm) {
       f.ext_src[pos] = own;
       f.col[pos] = j;
       f.range[pos] = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+      f.picked[pos] = 0; f.label[pos] = 0; f.curv[pos] = 0.f;     // resetParameters (:61-75): cleared per extracted slot
     }
   }
 }
 
-// F3 + F4.  grid = (blocks, F)
-__global__ void k_feat_curvature(FeatFrame* frames) {
+// F3 + F4 in one pass over the extracted ranges.  grid = (blocks, F).  F4's writes are idempotent ORs of 1 into
+// flags that k_feat_compact cleared, F3 writes only its own slot: no ordering between the two is needed.
+__global__ void k_feat_curv_occl(FeatFrame* frames) {
   const FeatFrame f = frames[blockIdx.y];
   const int M = *f.M;
+  const float* __restrict__ r = f.range;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
     if (i >= 5 && i < M - 5) {
-      const float* r = f.range;
       const float d = r[i - 5] + r[i - 4] + r[i - 3] + r[i - 2] + r[i - 1] - r[i] * 10 +
                       r[i + 1] + r[i + 2] + r[i + 3] + r[i + 4] + r[i + 5];   // exact op order (:549-553)
       f.curv[i] = d * d;
     }
-  }
-}
-__global__ void k_feat_occlusion(FeatFrame* frames) {
-  const FeatFrame f = frames[blockIdx.y];
-  const int M = *f.M;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
     if (i >= 5 && i < M - 6) {
-      const float depth1 = f.range[i], depth2 = f.range[i + 1];
+      const float depth1 = r[i], depth2 = r[i + 1];
       const int columnDiff = abs(f.col[i + 1] - f.col[i]);
       if (columnDiff < 10) {
         if ((double)(depth1 - depth2) > 0.3) { for (int k = -5; k <= 0; k++) f.picked[i + k] = 1; }
         else if ((double)(depth2 - depth1) > 0.3) { for (int k = 1; k <= 6; k++) f.picked[i + k] = 1; }
       }
-      const float diff1 = fabsf(f.range[i - 1] - f.range[i]);
-      const float diff2 = fabsf(f.range[i + 1] - f.range[i]);
-      if ((double)diff1 > 0.02 * (double)f.range[i] && (double)diff2 > 0.02 * (double)f.range[i]) f.picked[i] = 1;
+      const float diff1 = fabsf(r[i - 1] - r[i]);
+      const float diff2 = fabsf(r[i + 1] - r[i]);
+      if ((double)diff1 > 0.02 * (double)r[i] && (double)diff2 > 0.02 * (double)r[i]) f.picked[i] = 1;
     }
   }
 }

@@ -786,8 +786,7 @@ static int run_features(lisreg_ctx* ctx, FeatFrame* d_frames, int F, const lisre
   if (with_deskew) { k_feat_deskew_start<<<F, 256, 0, st>>>(d_frames, dp); LAUNCH_CK(); }
   k_feat_ring_count<<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
   k_feat_compact<<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
-  k_feat_curvature<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames); LAUNCH_CK();
-  k_feat_occlusion<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames); LAUNCH_CK();
+  k_feat_curv_occl<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames); LAUNCH_CK();
   k_feat_segments<<<dim3((prm->n_scan + FEAT_WARPS - 1) / FEAT_WARPS, F), 32 * FEAT_WARPS, 0, st>>>(d_frames, dp); LAUNCH_CK();
   k_feat_gather<<<dim3(FEAT_GATHER_SPLIT, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
   return LISREG_OK;
@@ -893,7 +892,7 @@ static int run_voxel(lisreg_ctx* ctx, VoxSeg* d_segs, int nseg, int max_n, doubl
   k_vox_bbox<<<dim3(pblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
   k_vox_plan<<<(nseg + 127) / 128, 128, 0, st>>>(d_segs, nseg); LAUNCH_CK();
   k_vox_keys<<<dim3(pblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
-  for (int pass = 0; pass < 4; pass++) {
+  for (int pass = 0; pass < 4; pass++) {                  // passes beyond a cloud's plan->npass return at once
     k_rs_hist<<<dim3(nblk, nseg), RS_THREADS, 0, st>>>(d_segs, 8 * pass, pass & 1); LAUNCH_CK();
     k_rs_scan<<<nseg, 1024, 0, st>>>(d_segs, 8 * pass); LAUNCH_CK();
     k_rs_scatter<<<dim3(nblk, nseg), RS_THREADS, 0, st>>>(d_segs, 8 * pass, pass & 1); LAUNCH_CK();

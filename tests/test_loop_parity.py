@@ -60,3 +60,32 @@ def test_loop_detect_edge_cases(engine):
     assert total_cand > 0
     od.close()
     engine.loop_destroy(det)
+
+
+def test_loop_history_grows_past_its_first_allocation(engine):
+    """300 keyframes (first device allocation = 256): the history survives the re-allocation - a revisit of keyframe 0
+    after the growth still matches it with the same score as the oracle."""
+    lut = orc.using_map_lut()
+    det = engine.loop_create(lut, use_fepsc=True)
+    od = orc.LoopDetector(lut=lut, use_fepsc=True)
+    rng = np.random.default_rng(9)
+    few = np.zeros((60, 4), np.float32); few[:, 0] = rng.uniform(5, 40, 60); few[:, 1] = rng.uniform(-20, 20, 60)
+    lab = np.where(np.arange(60) % 2 == 0, 13, 18).astype(np.uint16)
+    last = None
+    for k in range(300):
+        T = np.eye(4, dtype=np.float32); T[0, 3] = 0.5 * k
+        pts = few.copy(); pts[:, 1] += 0.01 * (k % 7)
+        a = engine.loop_detect(det, pts[:20], pts, pts, lab, T)
+        b = od.detect(pts[:20], pts, pts, lab, T)
+        assert a[:2] == b[:2]
+    for rep in range(2):                               # jump back to the start: the second call sees the start gated
+        T = np.eye(4, dtype=np.float32); T[0, 3] = 0.01 * rep
+        cg, ng, mg = engine.loop_detect(det, few[:20], few, few, lab, T)
+        co, no, mo = od.detect(few[:20], few, few, lab, T)
+        assert (cg, ng) == (co, no)
+        assert [(x[0], x[1]) for x in mg] == [(x[0], x[1]) for x in mo]
+        for (_, _, so, To), (_, _, sg, Tg) in zip(mo, mg):
+            assert abs(so - sg) <= 1e-3 and np.abs(To - Tg).max() <= 1e-4
+        last = (ng, mg)
+    assert last[0] > 0
+    od.close(); engine.loop_destroy(det)

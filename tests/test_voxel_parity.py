@@ -58,3 +58,17 @@ def test_properties_at_full_size(engine):
     div = mx - mn + 1
     lin = (ijk[:, 0] - mn[0]) + (ijk[:, 1] - mn[1]) * div[0] + (ijk[:, 2] - mn[2]) * div[0] * div[1]
     assert np.all(np.diff(lin) >= 0)
+
+
+@pytest.mark.parametrize("spread,leaf", [(0.5, 0.2), (3.0, 0.2), (20.0, 0.2), (400.0, 0.2)])
+def test_every_radix_pass_count(engine, spread, leaf):
+    """The sort only runs the 8-bit passes the largest voxel index needs (1 .. 4): tiny, small, medium and very large
+    extents, with voxels that straddle the 2048-entry chunks of the centroid kernel."""
+    rng = np.random.default_rng(int(spread * 10))
+    p = np.zeros((30000, 4), np.float32)
+    p[:, :3] = rng.uniform(-spread, spread, (30000, 3))
+    p[:5000, :3] = rng.uniform(-0.05, 0.05, (5000, 3))            # one crowded voxel neighbourhood (> 2048 points in a voxel)
+    p[:, 3] = rng.uniform(0, 255, 30000)
+    o = orc.voxel_grid(p, leaf)
+    g = engine.voxel_grid(p, leaf)
+    assert np.array_equal(o, g)
