@@ -271,6 +271,11 @@ int32_t lisreg_epsc_describe(lisreg_ctx* ctx, int32_t n, const lisreg_epsc_cloud
  * best first (idx = -1 when fewer qualify); shift = winning i in [-10, 10) (yaw offset = i * 2*pi/80). */
 int32_t lisreg_epsc_score_all(lisreg_ctx* ctx, const uint8_t* desc, int32_t N, int32_t topk,
                               int32_t* idx, float* score, int8_t* shift);
+/* the shard of one rank of a multi-GPU run: only the query rows q = row_begin + r * row_stride are
+ * scored (row q costs q pairs, so ranks take the cyclic rows rank, rank + world, ...); outputs are n_rows x topk with
+ * n_rows = ceil((N - row_begin) / row_stride), row r describing query q.  (0, 1) == lisreg_epsc_score_all. */
+int32_t lisreg_epsc_score_rows(lisreg_ctx* ctx, const uint8_t* desc, int32_t N, int32_t row_begin, int32_t row_stride,
+                               int32_t topk, int32_t* idx, float* score, int8_t* shift);
 /* same with descriptors and outputs resident in HBM; asynchronous */
 int32_t lisreg_epsc_score_all_dev(lisreg_ctx* ctx, const uint8_t* d_desc, int32_t N, int32_t topk,
                                   int32_t* d_idx, float* d_score, int8_t* d_shift);

@@ -94,17 +94,20 @@ __global__ void k_epsc_describe(const EpscCloud* __restrict__ clouds, const uint
 constexpr int EPSC_QT = 8, EPSC_JT = 16, EPSC_THREADS = EPSC_QT * EPSC_JT;
 constexpr int EPSC_STRIDE_W = 401;   // words per descriptor in smem (+1 pad => conflict-free across descriptors)
 
-// sad_out[q * N + j] = min over shifts of the SAD (int32), shift_out = winning i in [-10, 10)
+// Query rows are q = q_begin + r * q_stride for local rows r in [0, n_rows): the whole matrix is (0, 1, N); a rank
+// of a multi-GPU run owns the cyclic rows (rank, world, ...) (triangular load => cyclic assignment).
+// sad_out[r * N + j] = min over shifts of the SAD (int32), shift_out = winning i in [-10, 10)
 __global__ void __launch_bounds__(EPSC_THREADS)
-k_epsc_score(const uint8_t* __restrict__ desc, int N, int* __restrict__ sad_out, int8_t* __restrict__ shift_out) {
-  const int q0 = blockIdx.y * EPSC_QT, j0 = blockIdx.x * EPSC_JT;
-  if (j0 >= q0 + EPSC_QT - 1) return;   // whole tile on/above the diagonal (needs j < q): nothing to do
+k_epsc_score(const uint8_t* __restrict__ desc, int N, int q_begin, int q_stride, int n_rows, int* __restrict__ sad_out, int8_t* __restrict__ shift_out) {
+  const int r0 = blockIdx.y * EPSC_QT, j0 = blockIdx.x * EPSC_JT;
+  const int r_last = min(r0 + EPSC_QT, n_rows) - 1;
+  if (r_last < r0 || j0 >= q_begin + r_last * q_stride) return;   // whole tile on/above the diagonal (needs j < q): nothing to do
   __shared__ unsigned s_q[EPSC_QT * EPSC_STRIDE_W];
   __shared__ unsigned s_j[EPSC_JT * EPSC_STRIDE_W];
   const unsigned* dw = (const unsigned*)desc;
   for (int t = threadIdx.x; t < EPSC_QT * 400; t += EPSC_THREADS) {
     const int d = t / 400, w = t % 400;
-    s_q[d * EPSC_STRIDE_W + w] = (q0 + d < N) ? __ldg(&dw[(size_t)(q0 + d) * 400 + w]) : 0u;
+    s_q[d * EPSC_STRIDE_W + w] = (r0 + d < n_rows) ? __ldg(&dw[(size_t)(q_begin + (r0 + d) * q_stride) * 400 + w]) : 0u;
   }
   for (int t = threadIdx.x; t < EPSC_JT * 400; t += EPSC_THREADS) {
     const int d = t / 400, w = t % 400;
@@ -112,8 +115,8 @@ k_epsc_score(const uint8_t* __restrict__ desc, int N, int* __restrict__ sad_out,
   }
   __syncthreads();
   const int ql = threadIdx.x / EPSC_JT, jl = threadIdx.x % EPSC_JT;
-  const int q = q0 + ql, j = j0 + jl;
-  if (q >= N || j >= q) return;
+  const int r = r0 + ql, q = q_begin + r * q_stride, j = j0 + jl;
+  if (r >= n_rows || j >= q) return;
   const unsigned* dq = s_q + ql * EPSC_STRIDE_W;   // desc2 = current/query  (shifted columns)
   const unsigned* dj = s_j + jl * EPSC_STRIDE_W;   // desc1 = history
   unsigned sad[20];
@@ -152,22 +155,23 @@ k_epsc_score(const uint8_t* __restrict__ desc, int N, int* __restrict__ sad_out,
   unsigned best = sad[0]; int bs = 0;
 #pragma unroll
   for (int s = 1; s < 20; s++) if (sad[s] < best) { best = sad[s]; bs = s; }
-  sad_out[(size_t)q * N + j] = (int)best;
-  shift_out[(size_t)q * N + j] = (int8_t)(bs - 10);
+  sad_out[(size_t)r * N + j] = (int)best;
+  shift_out[(size_t)r * N + j] = (int8_t)(bs - 10);
 }
 
-// per-query top-k among history j < q with score > 0.75 (<=> SAD < 102000): one warp per query
-__global__ void k_epsc_topk(const int* __restrict__ sad, const int8_t* __restrict__ shiftm, int N, int topk,
+// per-query top-k among history j < q with score > 0.75 (<=> SAD < 102000): one warp per (local) query row
+__global__ void k_epsc_topk(const int* __restrict__ sad, const int8_t* __restrict__ shiftm, int N, int q_begin, int q_stride, int n_rows, int topk,
                             int* __restrict__ idx, float* __restrict__ score, int8_t* __restrict__ shift) {
-  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (q >= N) return;
+  if (r >= n_rows) return;
+  const int q = q_begin + r * q_stride;
   // each lane keeps its own sorted top-k (k <= 8) of keys (sad << 32 | j), then a warp merge by repeated min
   unsigned long long best[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) best[k] = ~0ull;
   for (int j = lane; j < q; j += 32) {
-    const int s = sad[(size_t)q * N + j];
+    const int s = sad[(size_t)r * N + j];
     if (s >= 102000) continue;
     unsigned long long key = ((unsigned long long)(unsigned)s << 32) | (unsigned)j;
 #pragma unroll
@@ -186,10 +190,10 @@ __global__ void k_epsc_topk(const int* __restrict__ sad, const int8_t* __restric
     if (lane == 0) {
       if (h != ~0ull) {
         const int j = (int)(unsigned)(h & 0xffffffffull), s = (int)(unsigned)(h >> 32);
-        idx[(size_t)q * topk + k] = j;
-        score[(size_t)q * topk + k] = (float)(1.0 - (double)s / (80 * 20 * 255));
-        shift[(size_t)q * topk + k] = shiftm[(size_t)q * N + j];
-      } else { idx[(size_t)q * topk + k] = -1; score[(size_t)q * topk + k] = 0.f; shift[(size_t)q * topk + k] = 0; }
+        idx[(size_t)r * topk + k] = j;
+        score[(size_t)r * topk + k] = (float)(1.0 - (double)s / (80 * 20 * 255));
+        shift[(size_t)r * topk + k] = shiftm[(size_t)r * N + j];
+      } else { idx[(size_t)r * topk + k] = -1; score[(size_t)r * topk + k] = 0.f; shift[(size_t)r * topk + k] = 0; }
     }
   }
 }

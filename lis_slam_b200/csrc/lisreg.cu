@@ -1218,35 +1218,51 @@ int32_t lisreg_epsc_describe(lisreg_ctx* ctx, int32_t n, const lisreg_epsc_cloud
   return LISREG_OK;
 }
 
+static int epsc_score_rows_dev(lisreg_ctx* ctx, const uint8_t* d_desc, int32_t N, int32_t row_begin, int32_t row_stride, int32_t topk,
+                               int32_t* d_idx, float* d_score, int8_t* d_shift) {
+  cudaStream_t st = ctx->stream;
+  const int n_rows = row_begin < N ? (N - row_begin + row_stride - 1) / row_stride : 0;
+  if (n_rows == 0) return LISREG_OK;
+  CK(ctx->d_epsc2.reserve((size_t)n_rows * N * 5 + 64));
+  int* sad = (int*)ctx->d_epsc2.p;
+  int8_t* shm = (int8_t*)(sad + (size_t)n_rows * N);
+  dim3 grid((N + EPSC_JT - 1) / EPSC_JT, (n_rows + EPSC_QT - 1) / EPSC_QT);
+  k_epsc_score<<<grid, EPSC_THREADS, 0, st>>>(d_desc, N, row_begin, row_stride, n_rows, sad, shm); LAUNCH_CK();
+  k_epsc_topk<<<(n_rows + 3) / 4, 128, 0, st>>>(sad, shm, N, row_begin, row_stride, n_rows, topk, d_idx, d_score, d_shift); LAUNCH_CK();
+  return LISREG_OK;
+}
+
 int32_t lisreg_epsc_score_all_dev(lisreg_ctx* ctx, const uint8_t* d_desc, int32_t N, int32_t topk,
                                   int32_t* d_idx, float* d_score, int8_t* d_shift) {
   if (!ctx || N <= 0 || !d_desc || topk <= 0 || topk > 8 || !d_idx || !d_score || !d_shift) return fail(ctx, LISREG_ERR_ARG, "lisreg_epsc_score_all: bad argument");
   CK(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  CK(ctx->d_epsc2.reserve((size_t)N * N * 5 + 64));
-  int* sad = (int*)ctx->d_epsc2.p;
-  int8_t* shm = (int8_t*)(sad + (size_t)N * N);
-  dim3 grid((N + EPSC_JT - 1) / EPSC_JT, (N + EPSC_QT - 1) / EPSC_QT);
-  k_epsc_score<<<grid, EPSC_THREADS, 0, st>>>(d_desc, N, sad, shm); LAUNCH_CK();
-  k_epsc_topk<<<(N + 3) / 4, 128, 0, st>>>(sad, shm, N, topk, d_idx, d_score, d_shift); LAUNCH_CK();
-  return LISREG_OK;
+  return epsc_score_rows_dev(ctx, d_desc, N, 0, 1, topk, d_idx, d_score, d_shift);
 }
 
-int32_t lisreg_epsc_score_all(lisreg_ctx* ctx, const uint8_t* desc, int32_t N, int32_t topk, int32_t* idx, float* score, int8_t* shift) {
-  if (!ctx || N <= 0 || !desc || topk <= 0 || topk > 8 || !idx || !score || !shift) return fail(ctx, LISREG_ERR_ARG, "lisreg_epsc_score_all: bad argument");
+// host buffers; rows q = row_begin + r * row_stride (the whole matrix: 0, 1); outputs n_rows x topk
+int32_t lisreg_epsc_score_rows(lisreg_ctx* ctx, const uint8_t* desc, int32_t N, int32_t row_begin, int32_t row_stride, int32_t topk,
+                               int32_t* idx, float* score, int8_t* shift) {
+  if (!ctx || N <= 0 || !desc || row_begin < 0 || row_stride <= 0 || topk <= 0 || topk > 8 || !idx || !score || !shift)
+    return fail(ctx, LISREG_ERR_ARG, "lisreg_epsc_score_rows: bad argument");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  const size_t bd = (size_t)N * EPSC_SIZE, bi = 4 * (size_t)N * topk, bs = 4 * (size_t)N * topk, bh = (size_t)N * topk;
+  const int n_rows = row_begin < N ? (N - row_begin + row_stride - 1) / row_stride : 0;
+  if (n_rows == 0) return LISREG_OK;
+  const size_t bd = (size_t)N * EPSC_SIZE, bi = 4 * (size_t)n_rows * topk, bs = 4 * (size_t)n_rows * topk, bh = (size_t)n_rows * topk;
   CK(ctx->d_epsc.reserve(bd + bi + bs + bh + 64));
   char* d = (char*)ctx->d_epsc.p;
   CK(cudaMemcpyAsync(d, desc, bd, cudaMemcpyHostToDevice, st));
-  int rc = lisreg_epsc_score_all_dev(ctx, (const uint8_t*)d, N, topk, (int32_t*)(d + bd), (float*)(d + bd + bi), (int8_t*)(d + bd + bi + bs));
+  int rc = epsc_score_rows_dev(ctx, (const uint8_t*)d, N, row_begin, row_stride, topk, (int32_t*)(d + bd), (float*)(d + bd + bi), (int8_t*)(d + bd + bi + bs));
   if (rc) return rc;
   CK(cudaMemcpyAsync(idx, d + bd, bi, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(score, d + bd + bi, bs, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(shift, d + bd + bi + bs, bh, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return LISREG_OK;
+}
+
+int32_t lisreg_epsc_score_all(lisreg_ctx* ctx, const uint8_t* desc, int32_t N, int32_t topk, int32_t* idx, float* score, int8_t* shift) {
+  return lisreg_epsc_score_rows(ctx, desc, N, 0, 1, topk, idx, score, shift);
 }
 
 // ------------------------------------------------------------------------------------------------

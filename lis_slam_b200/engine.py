@@ -205,6 +205,8 @@ def lib():
         L.lisreg_map_distance_filter.argtypes = [vp, i32, i32, vp, i32, C.c_float, C.c_float, C.c_float, C.c_float, vp, C.POINTER(i32)]
         L.lisreg_extract_features_deskew.restype = i32
         L.lisreg_extract_features_deskew.argtypes = [vp, vp, vp, vp, i32, C.POINTER(FeatParams), C.POINTER(Deskew), C.POINTER(FeatOut), vp]
+        L.lisreg_epsc_score_rows.restype = i32
+        L.lisreg_epsc_score_rows.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp]
         L.lisreg_loop_params_default.argtypes = [C.POINTER(LoopParams)]
         L.lisreg_loop_create.restype = i32
         L.lisreg_loop_create.argtypes = [vp, C.POINTER(LoopParams), C.POINTER(C.c_uint8), C.POINTER(i32)]
@@ -444,6 +446,15 @@ class Engine:
         out = [np.zeros((n, 20, 80), np.uint8) for _ in range(3)]
         self._ck(lib().lisreg_epsc_describe(self._h, n, arr, lut.ctypes.data, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data))
         return {"epsc": out[0], "sepsc": out[1], "fepsc": out[2]}
+
+    def epsc_score_rows(self, desc, row_begin, row_stride, topk=5):
+        """One rank's cyclic shard of the all-pairs scoring: rows row_begin, row_begin + row_stride, ..."""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 1600)
+        N = len(d)
+        n_rows = max(0, (N - row_begin + row_stride - 1) // row_stride)
+        idx = np.zeros((n_rows, topk), np.int32); score = np.zeros((n_rows, topk), np.float32); shift = np.zeros((n_rows, topk), np.int8)
+        self._ck(lib().lisreg_epsc_score_rows(self._h, d.ctypes.data, N, row_begin, row_stride, topk, idx.ctypes.data, score.ctypes.data, shift.ctypes.data))
+        return idx, score, shift
 
     def epsc_score_all(self, desc, topk=5):
         d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 1600)

@@ -78,3 +78,24 @@ def test_score_all_tile_edges(engine):
         io, so, ho = orc.epsc_score_all(desc, topk=3)
         ig, sg, hg = engine.epsc_score_all(desc, topk=3)
         assert np.array_equal(io, ig) and np.array_equal(ho, hg) and np.array_equal(so, sg), n
+
+
+def test_cyclic_row_shards_reassemble_the_full_result(engine):
+    """Multi-GPU sharding of the loop-closure scoring: every rank scores the cyclic query rows rank,
+    rank + world, ...; interleaving the shards gives exactly the single-GPU all-pairs result (ragged shards included)."""
+    from lis_slam_b200 import shard
+    rng = np.random.default_rng(12)
+    base = [rng.integers(0, 256, (20, 80), dtype=np.uint8) for _ in range(6)]
+    desc = np.stack([np.roll(base[rng.integers(0, 6)], int(rng.integers(-9, 10)), axis=1) for _ in range(101)])
+    full = engine.epsc_score_all(desc, topk=4)
+    for world in (2, 3, 8):
+        got = [np.zeros_like(a) for a in full]
+        for rank in range(world):
+            rows = shard.cyclic_rows(len(desc), rank, world)
+            part = engine.epsc_score_rows(desc, rank, world, topk=4)
+            assert len(part[0]) == len(rows)
+            for a, b in zip(got, part):
+                a[rows] = b
+        for a, b in zip(got, full):
+            assert np.array_equal(a, b), world
+    assert engine.epsc_score_rows(desc, 500, 2, topk=4)[0].shape == (0, 4)      # a rank beyond the rows owns nothing
