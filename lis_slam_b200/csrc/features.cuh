@@ -31,7 +31,8 @@ struct FeatFrame {
   int* owner;            // n_scan*horizon  : input index owning each range-image cell (INT_MAX = empty)
   float4* ext_pts;       // extracted cloud (capacity n_scan*horizon)
   int* ext_src;          // index of the input point in each extracted slot
-  int* col; float* range; float* curv; int* picked; int* label;
+  unsigned short* col; float* range; float* curv;   // column index (horizon <= 2048), range, curvature per extracted point
+  unsigned char* picked; signed char* label;         // cloudNeighborPicked flag, cloudLabel (-1 / 0 / 1): bytes (the stage is DRAM-bound)
   int* ring_count;       // n_scan
   int* ring_start; int* ring_end;   // n_scan (startRingIndex / endRingIndex)
   int* M;                // number of extracted points
@@ -66,14 +67,15 @@ __device__ __forceinline__ bool feat_project(const FeatParamsDev& prm, float4 p,
   if (ring < 0 || ring >= prm.n_scan) return false;
   if (ring % prm.downsample != 0) return false;
   const float ang_res_x = (float)(360.0 / (double)(float)prm.horizon);
-  // The column is the only consumer of the azimuth.  Fast path: fp32 atan2f (<= 2 ulp, i.e. < 1e-4 columns off);
-  // only when the column coordinate lands within 2e-3 of a rounding boundary is the reference expression
-  // evaluated (correctly rounded atan2 in fp64) - the result is identical, the fp64 atan2 runs for ~0.4 % of the points.
-  const double t_fast = ((double)atan2f(p.x, p.y) * (180.0 / 3.14159265358979323846) - 90.0) / (double)ang_res_x;
-  const double fr = t_fast - floor(t_fast);
+  // The column is the only consumer of the azimuth.  Fast path: fp32 atan2f (<= 2 ulp) and fp32 arithmetic, together
+  // < 5e-4 columns off; only when the column coordinate lands within 4e-3 of a rounding boundary is the reference
+  // expression evaluated (correctly rounded atan2 in fp64) - the result is identical, the fp64 path runs for ~0.8 %
+  // of the points.
+  const float t_fast = (atan2f(p.x, p.y) * 57.29577951f - 90.0f) / ang_res_x;    // fp32 end to end: < 5e-4 columns off
+  const float fr = t_fast - floorf(t_fast);
   int col;
-  if (fabs(fr - 0.5) > 2e-3) {
-    col = (int)(-round(t_fast) + (double)(prm.horizon / 2));
+  if (fabsf(fr - 0.5f) > 4e-3f) {
+    col = (int)(-roundf(t_fast)) + prm.horizon / 2;
   } else {
     const float horizonAngle = (float)((double)(atan2f_cr(p.x, p.y) * 180) / 3.14159265358979323846);
     col = (int)(-round(((double)horizonAngle - 90.0) / (double)ang_res_x) + (double)(prm.horizon / 2));
@@ -214,7 +216,7 @@ __global__ void k_feat_compact(FeatFrame* frames, FeatParamsDev prm) {
       // range (and the column) come from the ORIGINAL point; only the stored coordinates are de-skewed (:489-507)
       f.ext_pts[pos] = f.n_imu > 0 ? feat_deskew_point(f, f.start_inv, p, own) : p;
       f.ext_src[pos] = own;
-      f.col[pos] = j;
+      f.col[pos] = (unsigned short)j;
       f.range[pos] = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
       f.picked[pos] = 0; f.label[pos] = 0; f.curv[pos] = 0.f;     // resetParameters (:61-75): cleared per extracted slot
     }
@@ -235,7 +237,7 @@ __global__ void k_feat_curv_occl(FeatFrame* frames) {
     }
     if (i >= 5 && i < M - 6) {
       const float depth1 = r[i], depth2 = r[i + 1];
-      const int columnDiff = abs(f.col[i + 1] - f.col[i]);
+      const int columnDiff = abs((int)f.col[i + 1] - (int)f.col[i]);
       if (columnDiff < 10) {
         if ((double)(depth1 - depth2) > 0.3) { for (int k = -5; k <= 0; k++) f.picked[i + k] = 1; }
         else if ((double)(depth2 - depth1) > 0.3) { for (int k = 1; k <= 6; k++) f.picked[i + k] = 1; }
@@ -305,7 +307,7 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
   const int hi = min(end + 5 + 6, M - 1);
   const int wlen = max(hi - lo + 1, 0);
   unsigned char* sreach = s_reach[wid];
-  for (int t = lane; t < wlen; t += 32) { spick[t] = (unsigned char)f.picked[lo + t]; scol[t] = (unsigned short)f.col[lo + t]; }
+  for (int t = lane; t < wlen; t += 32) { spick[t] = f.picked[lo + t]; scol[t] = f.col[lo + t]; }
   __syncwarp();
   // How far a pick of each point suppresses to the right / left (:648-661) depends on the column indices only:
   // gap bit t = "the walk cannot step from t to t+1" (column jump > 10, or t+1 outside the window / the cloud); the

@@ -753,9 +753,9 @@ static void feat_carve(char* base, int cells, int nscan, FeatFrame* f) {
   char* p = base;
   auto take = [&](size_t bytes) { char* r = p; p += (bytes + 15) & ~size_t(15); return r; };
   f->ext_pts = (float4*)take(sizeof(float4) * (size_t)cells);
-  f->owner = (int*)take(4 * (size_t)cells); f->ext_src = (int*)take(4 * (size_t)cells); f->col = (int*)take(4 * (size_t)cells);
+  f->owner = (int*)take(4 * (size_t)cells); f->ext_src = (int*)take(4 * (size_t)cells); f->col = (unsigned short*)take(4 * (size_t)cells);
   f->range = (float*)take(4 * (size_t)cells); f->curv = (float*)take(4 * (size_t)cells);
-  f->picked = (int*)take(4 * (size_t)cells); f->label = (int*)take(4 * (size_t)cells); f->surf_idx = (int*)take(4 * (size_t)cells);
+  f->picked = (unsigned char*)take(4 * (size_t)cells); f->label = (signed char*)take(4 * (size_t)cells); f->surf_idx = (int*)take(4 * (size_t)cells);
   f->ring_count = (int*)take(4 * (size_t)nscan); f->ring_start = (int*)take(4 * (size_t)nscan); f->ring_end = (int*)take(4 * (size_t)nscan);
   const size_t ns = (size_t)nscan * 6;
   f->seg_corner = (int*)take(4 * ns * 20); f->seg_ncorner = (int*)take(4 * ns);
@@ -834,13 +834,17 @@ static int extract_features_impl(lisreg_ctx* ctx, const float* pts, const uint16
   auto dl = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
     return (dst && bytes) ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess; };
   const size_t M = (size_t)h[0];
-  CK(dl(out->src_index, f.ext_src, 4 * M)); CK(dl(out->col_ind, f.col, 4 * M)); CK(dl(out->range, f.range, 4 * M));
+  // column indices and labels live as 16-bit / 8-bit arrays on the device: widened to the int32 of the interface here
+  std::vector<unsigned short> h_col(out->col_ind ? M : 0); std::vector<signed char> h_label(out->label ? M : 0);
+  CK(dl(out->src_index, f.ext_src, 4 * M)); CK(dl(h_col.data(), f.col, 2 * h_col.size())); CK(dl(out->range, f.range, 4 * M));
   CK(dl(out->start_ring, f.ring_start, 4 * (size_t)prm->n_scan)); CK(dl(out->end_ring, f.ring_end, 4 * (size_t)prm->n_scan));
   CK(dl(out->corner_idx, f.corner_idx, 4 * (size_t)h[1])); CK(dl(out->sharp_idx, f.sharp_idx, 4 * (size_t)h[2]));
   CK(dl(out->flat_idx, f.flat_idx, 4 * (size_t)h[3])); CK(dl(out->surf_idx, f.surf_idx, 4 * (size_t)h[4]));
-  CK(dl(out->curvature, f.curv, 4 * M)); CK(dl(out->label, f.label, 4 * M));
+  CK(dl(out->curvature, f.curv, 4 * M)); CK(dl(h_label.data(), f.label, h_label.size()));
   CK(dl(ext_xyzi, f.ext_pts, 16 * M));
   CK(cudaStreamSynchronize(st));
+  for (size_t i = 0; i < h_col.size(); i++) out->col_ind[i] = h_col[i];
+  for (size_t i = 0; i < h_label.size(); i++) out->label[i] = h_label[i];
   return LISREG_OK;
 }
 
