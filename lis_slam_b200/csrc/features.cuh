@@ -255,26 +255,6 @@ constexpr int FEAT_RING_MAX = 2048 + 16; // staged ring window (horizon <= 2048,
 #define KNN_SEG_INF __int_as_float(0x7f800000)
 constexpr int FEAT_CH = 12;              // segment elements per lane: a segment holds <= 32 * 12 points (horizon <= 2048 -> <= 341)
 
-// Neighbour suppression of a pick (:648-661) on the ring window staged in shared memory.  lo = global index of window slot 0; indices outside [0, M) or outside the
-// window end the walk (the window covers [first-6, last+6] of the ring, the only indices a pick of this ring can
-// reach).  Returns the marked index range [a0, b0].
-__device__ __forceinline__ void feat_mark_range(const unsigned short* scol, int lo, int wlen, int ind, int M, int& a0, int& b0) {
-  int rr = 0, rl = 0;
-  for (int l = 1; l <= 5; l++) {
-    const int a = ind + l, b = ind + l - 1;
-    if (a >= M || a - lo >= wlen || b - lo < 0) break;
-    if (abs((int)scol[a - lo] - (int)scol[b - lo]) > 10) break;
-    rr = l;
-  }
-  for (int l = 1; l <= 5; l++) {
-    const int a = ind - l, b = ind - l + 1;
-    if (a < 0 || a - lo < 0 || b - lo >= wlen) break;
-    if (abs((int)scol[a - lo] - (int)scol[b - lo]) > 10) break;
-    rl = l;
-  }
-  a0 = ind - rl; b0 = ind + rr;
-}
-
 // one warp per (frame, ring).  grid = (ceil(n_scan / FEAT_WARPS), F), block = 32 * FEAT_WARPS.
 //
 // The reference sorts every segment by curvature and walks it twice, picking a point when it has not been
@@ -286,14 +266,13 @@ __device__ __forceinline__ void feat_mark_range(const unsigned short* scol, int 
 // reductions (redux.sync) for the winning (curvature, index) key, the pre-computed suppression reach of the winner,
 // and an O(1) alive-mask update per lane.  ~40 steps per
 // segment instead of a 512-key bitonic sort plus a 300-element sequential walk by one lane.
-__global__ void __launch_bounds__(32 * FEAT_WARPS)
+__global__ void __launch_bounds__(32 * FEAT_WARPS, 7)
 k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
   const FeatFrame f = frames[blockIdx.y];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int ring = blockIdx.x * FEAT_WARPS + wid;
   __shared__ unsigned char s_pick[FEAT_WARPS][FEAT_RING_MAX];
   __shared__ unsigned char s_reach[FEAT_WARPS][FEAT_RING_MAX];   // suppression reach of every point: right | left << 4
-  __shared__ unsigned short s_col[FEAT_WARPS][FEAT_RING_MAX];
   __shared__ float s_cv[FEAT_WARPS][32 * FEAT_CH];
   __shared__ unsigned s_gap[FEAT_WARPS][FEAT_RING_MAX / 32 + 3];  // column-gap bits of the ring window               // curvature of the current segment, slot-major
   if (ring >= prm.n_scan) return;
@@ -301,13 +280,12 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
   const int M = *f.M;
   const int start = f.ring_start[ring], end = f.ring_end[ring];
   unsigned char* spick = s_pick[wid];
-  unsigned short* scol = s_col[wid];
   // ring = extracted indices [first, last] with first = start - 4, last = end + 5; window adds a +-6 apron
   const int lo = max(start - 4 - 6, 0);
   const int hi = min(end + 5 + 6, M - 1);
   const int wlen = max(hi - lo + 1, 0);
   unsigned char* sreach = s_reach[wid];
-  for (int t = lane; t < wlen; t += 32) { spick[t] = f.picked[lo + t]; scol[t] = f.col[lo + t]; }
+  for (int t = lane; t < wlen; t += 32) spick[t] = f.picked[lo + t];
   __syncwarp();
   // How far a pick of each point suppresses to the right / left (:648-661) depends on the column indices only:
   // gap bit t = "the walk cannot step from t to t+1" (column jump > 10, or t+1 outside the window / the cloud); the
@@ -315,7 +293,7 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
   unsigned* sgap = s_gap[wid];
   for (int base = 0; base < wlen + 32; base += 32) {
     const int t = base + lane;
-    const bool gap = (t + 1 >= wlen) || abs((int)scol[t + 1] - (int)scol[t]) > 10;
+    const bool gap = (t + 1 >= wlen) || abs((int)f.col[lo + t + 1] - (int)f.col[lo + t]) > 10;   // column indices straight from global memory
     const unsigned m = __ballot_sync(FULL, gap);
     if (lane == 0) sgap[base >> 5] = m;
   }
