@@ -31,13 +31,13 @@ print("\nPer-iteration device times of one step (µs) — the proof path (DESIGN
 for kn in ("k_knn_check", "k_knn_coop", "k_knn_search<0>", "k_knn_search<1>", "k_lm_resid", "k_lm_solve"):
     print("%-18s" % kn, [round(v) for n, v in rows[a:b] if n == kn])
 print("```\n")
-print("## `ncu --set full` of the top kernels (first launches of one step, captured before the last two feature-kernel changes (8 / 16-bit flag arrays, 7 resident blocks for `k_feat_segments`: 919 → 622 µs); table by `scripts/ncu_table.py`)\n")
+print("## `ncu --set full` of the top kernels (first launches of one step; table by `scripts/ncu_table.py`)\n")
 print(run(os.path.join(HERE, "ncu_table.py"), raw))
 print("""Reading: no kernel of the registration stage is DRAM-bound (dram % ≤ 25, the search / residual kernels ≤ 13 %): maps
 (8 × 3.2 MB) and partial sums live in L2.  `k_knn_search<0>` issues ~67 % of the cycles with 17 of 32 lanes active (candidate
 counts differ between the queries of a warp: flattened-scan lane efficiency ≈ 0.5 on this scene); `k_lm_resid` is a long
-straight-line fp32 computation at 96 registers (29 % warps active); `k_feat_segments` is the selection loop (latency of
-the per-pick `redux.sync` chain at 28 % warps active).  `k_vox_centroid` (gathers of 16 B points), `k_feat_compact` and
+straight-line fp32 computation at 96 registers (29 % warps active); `k_feat_segments` is the selection loop (issue 60 %,
+the per-pick `redux.sync` chain at 39 % warps active).  `k_vox_centroid` (gathers of 16 B points), `k_feat_compact` and
 `k_rs_scatter` are the DRAM-heavy ones.""")
 print("""
 ## What moved the number this round (each row = a committed state measured with `python bench.py` on a pool B200)
