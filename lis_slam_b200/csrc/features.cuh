@@ -180,6 +180,7 @@ __global__ void k_feat_ring_count(FeatFrame* frames, FeatParamsDev prm) {
 }
 
 // F2b: row-major compaction.  grid = (n_scan, F), block = 256 (8 warps); every warp scans chunks of 32 cells
+template <bool DESKEW>   // the de-skew path (fp64 trigonometry) is compiled out of the common instantiation: it costs registers
 __global__ void k_feat_compact(FeatFrame* frames, FeatParamsDev prm) {
   const FeatFrame f = frames[blockIdx.y];
   const int ring = blockIdx.x;
@@ -214,7 +215,7 @@ __global__ void k_feat_compact(FeatFrame* frames, FeatParamsDev prm) {
       const int pos = s_base + s_chunk[ch] + __popc(m & ((1u << lane) - 1u));
       const float4 p = __ldg(&f.pts[own]);
       // range (and the column) come from the ORIGINAL point; only the stored coordinates are de-skewed (:489-507)
-      f.ext_pts[pos] = f.n_imu > 0 ? feat_deskew_point(f, f.start_inv, p, own) : p;
+      f.ext_pts[pos] = (DESKEW && f.n_imu > 0) ? feat_deskew_point(f, f.start_inv, p, own) : p;
       f.ext_src[pos] = own;
       f.col[pos] = (unsigned short)j;
       f.range[pos] = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);

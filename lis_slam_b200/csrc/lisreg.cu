@@ -785,7 +785,8 @@ static int run_features(lisreg_ctx* ctx, FeatFrame* d_frames, int F, const lisre
   k_feat_project<<<dim3(std::max(1, (max_n + 255) / 256), F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
   if (with_deskew) { k_feat_deskew_start<<<F, 256, 0, st>>>(d_frames, dp); LAUNCH_CK(); }
   k_feat_ring_count<<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
-  k_feat_compact<<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
+  if (with_deskew) { k_feat_compact<true><<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK(); }
+  else { k_feat_compact<false><<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK(); }
   k_feat_curv_occl<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames); LAUNCH_CK();
   k_feat_segments<<<dim3((prm->n_scan + FEAT_WARPS - 1) / FEAT_WARPS, F), 32 * FEAT_WARPS, 0, st>>>(d_frames, dp); LAUNCH_CK();
   k_feat_gather<<<dim3(FEAT_GATHER_SPLIT, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();

@@ -31,7 +31,7 @@ print("\nPer-iteration device times of one step (µs) — the proof path (DESIGN
 for kn in ("k_knn_check", "k_knn_coop", "k_knn_search<0>", "k_knn_search<1>", "k_lm_resid", "k_lm_solve"):
     print("%-18s" % kn, [round(v) for n, v in rows[a:b] if n == kn])
 print("```\n")
-print("## `ncu --set full` of the top kernels (first launches of one step; table by `scripts/ncu_table.py`)\n")
+print("## `ncu --set full` of the top kernels (first launches of one step, captured one commit before `k_feat_compact` was split into <DESKEW> instantiations; table by `scripts/ncu_table.py`)\n")
 print(run(os.path.join(HERE, "ncu_table.py"), raw))
 print("""Reading: no kernel of the registration stage is DRAM-bound (dram % ≤ 25, the search / residual kernels ≤ 13 %): maps
 (8 × 3.2 MB) and partial sums live in L2.  `k_knn_search<0>` issues ~67 % of the cycles with 17 of 32 lanes active (candidate
@@ -56,6 +56,7 @@ print("""
 | suppression reach from gap bits | 34 640 | 25 730 | 2.40 / 2.03 / 2.84 |
 | fused curvature + occlusion kernel, 8 / 16-bit flag and column arrays | 35 930 | 25 810 | 2.14 / 2.03 / 2.84 |
 | `k_feat_segments` at 7 resident blocks per SM (no column staging, 72 registers) | 36 860 | 25 880 | 1.95 / 2.03 / 2.84 |
+| de-skew path compiled out of the common `k_feat_compact` instantiation (68 → 40 registers, 500 → 333 µs) | 37 820 | 25 920 | 1.79 / 2.03 / 2.83 |
 
 `e2e` stopped moving at ≈ 25.7 k frames/s because it is PCIe-bound: 510 MB of sweeps per step at ≈ 55 GB/s is 9.2 ms, the step takes 9.95 ms.
 Tried and dropped (measured, no gain): 6 / 8 resident blocks for `k_lm_resid`, 10 / 12 for the scan kernel (±1 %); a separate fit kernel over the
