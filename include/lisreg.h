@@ -238,7 +238,9 @@ void lisreg_frame_params_default(lisreg_frame_params* p);
 /* everything resident in HBM; asynchronous on the context stream */
 int32_t lisreg_frames_batch_dev(lisreg_ctx* ctx, int32_t F, const lisreg_frame_item* items,
                                 float* d_pose6xF, const lisreg_frame_params* prm, lisreg_lm_result* d_resxF);
-/* raw sweeps packed in one (pinned) host arena; items hold byte offsets (pts 16-byte aligned, ring 2-byte) */
+/* raw sweeps packed in one (pinned) host arena; items hold byte offsets (pts 16-byte aligned, ring 2-byte).  Blocking.
+ * Batches larger than 128 frames whose sweeps are packed in frame order are uploaded in chunks on a copy stream while
+ * the earlier chunks already run (LISREG_E2E_CHUNK frames per chunk, 0 = one copy); results do not depend on it. */
 int32_t lisreg_frames_batch_arena(lisreg_ctx* ctx, int32_t F, const lisreg_frame_item* items,
                                   const void* host_arena, uint64_t arena_bytes,
                                   float* pose6xF, const lisreg_frame_params* prm, lisreg_lm_result* resxF);
@@ -340,8 +342,8 @@ int32_t lisreg_selftest_smallmat(lisreg_ctx* ctx, const float* A36, const float*
 
 /* ---- profiling (CUDA events on the context stream around the dominant kernels) ---- */
 typedef struct lisreg_profile {
-  double lm_iter_ms;        /* total device time of k_lm_iter launches */
-  int64_t lm_iter_launches;
+  double lm_iter_ms;        /* total device time of the Gauss-Newton iterations (kNN check / search, residual, solve kernels) */
+  int64_t lm_iter_launches; /* iterations timed */
   double lm_alg_bytes;      /* algorithmic bytes of those launches: sum (nc+ns) * 96 B (SURVEY.md 8d A_iter) */
   double feat_ms;  int64_t feat_launches;  double feat_alg_bytes;
   double voxel_ms; int64_t voxel_launches; double voxel_alg_bytes;

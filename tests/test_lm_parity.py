@@ -186,7 +186,7 @@ def test_degenerate_corridor_quirk_q1(engine):
 
 @pytest.mark.parametrize("variant", ["A", "B"])
 def test_knn_check_path_is_bit_identical_to_full_search(monkeypatch, variant):
-    """k_lm_knn re-uses the previous iteration's neighbours when it can PROVE (safe radius vs movement) that they
+    """k_knn_check re-uses the previous iteration's neighbours when it can PROVE (safe radius vs movement) that they
     are still the exact 5-NN; LISREG_KNN_NOSKIP=1 searches every query from scratch.  Every per-iteration record
     (selection counts, A^T A, A^T b, step, pose) must be identical bit for bit, single and batched."""
     m = local_map()
