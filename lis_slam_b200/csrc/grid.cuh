@@ -16,8 +16,9 @@
 // everything not yet visited (or the bound reaches the gate).
 //
 // The running best-5 is kept as five 64-bit keys (float bits of d^2 << 32 | position in the
-// sorted array): d^2 >= 0 so the integer order of the key is the lexicographic (d^2, position)
-// order, and a sorted insert is five branch-free min/max stages held entirely in registers.
+// sorted array): d^2 >= 0 so the integer order of the key is the order of d^2, and a sorted insert is
+// five min/max stages held entirely in registers.  Bit-equal distances are ordered by the ORIGINAL point
+// index (knn_key_less), like the CPU oracle.
 #pragma once
 #include <cstdint>
 #include <cfloat>
@@ -68,12 +69,29 @@ LISREG_HD __forceinline__ int cell_coord(float v, float o, float inv_h) {
   return (int)floorf((v - o) * inv_h);
 }
 
+// original (caller-side) index of the point stored at `pos` of the cell-sorted array
+LISREG_HD __forceinline__ int knn_orig(const float4* __restrict__ pts, unsigned pos) { return f2i(LISREG_LDG(&pts[pos].w)); }
+
+// Total order of the candidates of one query: (d^2, ORIGINAL index) - the order of the CPU oracle's kd-tree
+// (oracle/orc_lm.cpp KdTree::insert), so that maps with exactly equidistant points (lattices, duplicated voxel
+// centroids) give the same neighbour set and the same neighbour order on both sides.  Keys carry the POSITION in
+// the sorted array (what the gathers need); the original index is only fetched when two squared distances are
+// bit-equal, which real clouds almost never produce.
+LISREG_HD __forceinline__ bool knn_key_less(const float4* __restrict__ pts, knn_key a, knn_key b) {
+  const unsigned da = (unsigned)(a >> 32), db = (unsigned)(b >> 32);
+  if (da != db) return da < db;
+  const unsigned pa = (unsigned)a, pb = (unsigned)b;
+  if (pa == 0xffffffffu || pb == 0xffffffffu) return pa < pb;      // sentinel: after every real candidate
+  return knn_orig(pts, pa) < knn_orig(pts, pb);
+}
+
 // keeps the K smallest keys, ascending
 template <int K>
-LISREG_HD __forceinline__ void knn_insert(knn_key (&b)[K], knn_key k) {
+LISREG_HD __forceinline__ void knn_insert(const float4* __restrict__ pts, knn_key (&b)[K], knn_key k) {
 #pragma unroll
   for (int j = 0; j < K; j++) {
-    const bool lt = b[j] < k;
+    bool lt = b[j] < k;
+    if ((unsigned)(b[j] >> 32) == (unsigned)(k >> 32)) lt = knn_key_less(pts, b[j], k);
     const knn_key lo = lt ? b[j] : k;
     k = lt ? k : b[j];
     b[j] = lo;
@@ -88,7 +106,7 @@ LISREG_HD __forceinline__ void knn_scan_range(const float4* __restrict__ pts, ui
     const float dx = qx - m.x, dy = qy - m.y, dz = qz - m.z;
     float d = dx * dx; d = d + dy * dy; d = d + dz * dz;   // FLANN L2 functor op order, no FMA
     const knn_key k = ((knn_key)(unsigned)f2i(d) << 32) | (knn_key)p;
-    if (k < best[K - 1]) knn_insert<K>(best, k);
+    if ((unsigned)f2i(d) <= (unsigned)(best[K - 1] >> 32)) knn_insert<K>(pts, best, k);   // "<=": a tie is decided inside
   }
 }
 

@@ -139,6 +139,9 @@ struct ProfScope {   // records an event pair around a group of launches when pr
   ~ProfScope() { if (on) { cudaEventRecord(p.b, ctx->cur->stream); ctx->ev_pending.push_back(p); } }
 };
 
+// [off, off + bytes) inside an arena of `total` bytes, without wrapping for offsets near 2^64
+static inline bool in_arena(uint64_t off, uint64_t bytes, uint64_t total) { return off <= total && bytes <= total - off; }
+
 static int fail(lisreg_ctx* c, int code, const char* fmt, ...) {
   char buf[512];
   va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
@@ -185,8 +188,8 @@ __global__ void k_grid_plan(const unsigned* __restrict__ bb, float h_req, int ma
   for (int d = 0; d < 3; d++) { mn[d] = ord2f(bb[d]); mx[d] = ord2f(bb[3 + d]); }
   if (n <= 0) { for (int d = 0; d < 3; d++) { mn[d] = 0.f; mx[d] = 0.f; } }
   float h = h_req;
-  int nx, ny, nz;
-  for (;;) {
+  int nx = 0, ny = 0, nz = 0;
+  for (int grow = 0; grow < 400; grow++) {   // bounded: non-finite boxes never satisfy the test (the host rejects the plan)
     nx = (int)floorf((mx[0] - mn[0]) / h) + 2; ny = (int)floorf((mx[1] - mn[1]) / h) + 2; nz = (int)floorf((mx[2] - mn[2]) / h) + 2;
     if ((double)nx * (double)ny * (double)nz <= (double)max_cells) break;
     h *= 1.25f;
@@ -294,9 +297,14 @@ static int build_cloud_index(lisreg_ctx* ctx, const float4* d_pts, int n, float 
   GridDev g;
   CK(cudaMemcpyAsync(&g, d_g, sizeof(g), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  // a NaN / Inf coordinate makes the planned dimensions meaningless (overflowed or negative): reject the cloud
+  if (!(g.nx > 0 && g.ny > 0 && g.nz > 0) || !std::isfinite(g.ox) || !std::isfinite(g.oy) || !std::isfinite(g.oz) || !std::isfinite(g.h) ||
+      (double)g.nx * (double)g.ny * (double)g.nz > (double)ctx->max_cells || g.ncells != g.nx * g.ny * g.nz)
+    return fail(ctx, LISREG_ERR_ARG, "map cloud has non-finite coordinates (grid %d x %d x %d)", g.nx, g.ny, g.nz);
   const int ncells = g.ncells;
   CK(cudaMalloc(&ci->sorted, sizeof(float4) * (size_t)std::max(n, 1)));
-  CK(cudaMalloc(&ci->cell_start, sizeof(uint32_t) * ((size_t)ncells + 1)));
+  { cudaError_t e2 = cudaMalloc(&ci->cell_start, sizeof(uint32_t) * ((size_t)ncells + 1));
+    if (e2 != cudaSuccess) { cudaFree(ci->sorted); ci->sorted = nullptr; return fail(ctx, LISREG_ERR_CUDA, "cudaMalloc(cell_start) failed: %s", cudaGetErrorString(e2)); } }
   const int nblk = (ncells + 1 + SCAN_BLOCK - 1) / SCAN_BLOCK;
   CK(ctx->d_tmp.reserve(sizeof(int) * (size_t)std::max(n, 1) + sizeof(uint32_t) * ((size_t)ncells + 1) + sizeof(uint32_t) * (size_t)(nblk + 1)));
   int* cell_id = (int*)ctx->d_tmp.p;
@@ -421,10 +429,11 @@ int32_t lisreg_map_create_dev(lisreg_ctx* ctx, const float* d_corner, int32_t mc
   const int slot = map_alloc_slot(ctx);
   MapSlot& m = ctx->maps[slot];
   const float h = cell_size_for_gate(gate_hint);
+  auto drop = [](CloudIndex& ci) { cudaFree(ci.sorted); cudaFree(ci.cell_start); ci = CloudIndex(); };
   int rc = build_cloud_index(ctx, (const float4*)d_corner, mc, h, &m.corner);
-  if (rc) return rc;
+  if (rc) { cudaStreamSynchronize(ctx->stream); drop(m.corner); return rc; }
   rc = build_cloud_index(ctx, (const float4*)d_surf, ms, h, &m.surf);
-  if (rc) return rc;
+  if (rc) { cudaStreamSynchronize(ctx->stream); drop(m.corner); drop(m.surf); return rc; }
   m.used = true;
   ctx->maps_dirty = true;
   *map_id = slot;
@@ -701,8 +710,8 @@ int32_t lisreg_scan2map_batch_arena(lisreg_ctx* ctx, int32_t B, const lisreg_bat
     const lisreg_batch_item& it = items[b];
     const size_t oc = (size_t)it.corner, os = (size_t)it.surf, ocl = (size_t)it.clabel, osl = (size_t)it.slabel;
     if (it.nc < 0 || it.ns < 0 || it.map_id < 0 || it.map_id >= (int)ctx->maps.size() || !ctx->maps[it.map_id].used ||
-        (oc & 15) || (os & 15) || oc + 16ull * it.nc > arena_bytes || os + 16ull * it.ns > arena_bytes ||
-        (ocl != (size_t)-1 && ocl + 2ull * it.nc > arena_bytes) || (osl != (size_t)-1 && osl + 2ull * it.ns > arena_bytes))
+        (oc & 15) || (os & 15) || !in_arena(oc, 16ull * it.nc, arena_bytes) || !in_arena(os, 16ull * it.ns, arena_bytes) ||
+        (ocl != (size_t)-1 && !in_arena(ocl, 2ull * it.nc, arena_bytes)) || (osl != (size_t)-1 && !in_arena(osl, 2ull * it.ns, arena_bytes)))
       return fail(ctx, LISREG_ERR_ARG, "arena item %d: bad sizes, offsets or map id", b);
     hd[b].corner = (const float4*)(d_arena + oc); hd[b].surf = (const float4*)(d_arena + os);
     hd[b].clabel = ocl != (size_t)-1 ? (const uint16_t*)(d_arena + ocl) : nullptr;
@@ -981,7 +990,7 @@ static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, co
     const float4* pts; const uint16_t* ring;
     if (d_arena) {
       const size_t op = (size_t)it.pts, orr = (size_t)it.ring;
-      if ((op & 15) || (orr & 1) || op + 16ull * it.n > arena_bytes || orr + 2ull * it.n > arena_bytes)
+      if ((op & 15) || (orr & 1) || !in_arena(op, 16ull * it.n, arena_bytes) || !in_arena(orr, 2ull * it.n, arena_bytes))
         return fail(ctx, LISREG_ERR_ARG, "frame item %d: bad arena offsets", i);
       pts = (const float4*)(d_arena + op); ring = (const uint16_t*)(d_arena + orr);
     } else { pts = (const float4*)it.pts; ring = it.ring; }
@@ -1051,6 +1060,7 @@ int32_t lisreg_frames_batch_arena(lisreg_ctx* ctx, int32_t F, const lisreg_frame
       if (it.n <= 0) continue;
       const int c = i / C;
       const uint64_t op = (uint64_t)(size_t)it.pts, orr = (uint64_t)(size_t)it.ring;
+      if (!in_arena(op, 16ull * it.n, arena_bytes) || !in_arena(orr, 2ull * it.n, arena_bytes)) { pipelined = false; break; }   // run_frames reports it
       lo[c] = std::min(lo[c], std::min(op, orr));
       hi[c] = std::max(hi[c], std::max(op + (uint64_t)16 * (uint64_t)it.n, orr + (uint64_t)2 * (uint64_t)it.n));
     }
@@ -1332,14 +1342,16 @@ int32_t lisreg_loop_detect(lisreg_ctx* ctx, int32_t det_id, const float* corner,
   const float x_t = odom[3], y_t = odom[7];
   const float yaw_t = (float)atan2((double)odom[4], (double)odom[0]);
   const double cx = x_t, cy = y_t;
-  if (L.travel.empty()) L.travel.push_back(0);
-  else { const double ex = L.px.back() - cx, ey = L.py.back() - cy; L.travel.push_back(L.travel.back() + sqrt(ex * ex + ey * ey + 0.0)); }
+  // travelDistanceArr entry of THIS keyframe; committed together with posArr / yawArr / the device history only after
+  // every fallible step below has succeeded, so an error return leaves the detector exactly as it was
+  double travel_cur = 0;
+  if (!L.travel.empty()) { const double ex = L.px.back() - cx, ey = L.py.back() - cy; travel_cur = L.travel.back() + sqrt(ex * ex + ey * ey + 0.0); }
   const int cur = L.n;
   res->current_frame_id = cur;
   // ---- travel gate (:736-741); posArr.back() is still the PREVIOUS keyframe here ----
   std::vector<int> cand; std::vector<float> cand_yaw; std::vector<double> cand_pos;
   for (int i = 0; i < cur; i++) {
-    const double delta_travel = L.travel.back() - L.travel[i];
+    const double delta_travel = travel_cur - L.travel[i];
     const double qx = L.px[i] - L.px.back(), qy = L.py[i] - L.py.back();
     const double pos_distance = sqrt(qx * qx + qy * qy + 0.0);
     if (delta_travel > (double)L.prm.skip_neighbour_distance && pos_distance < delta_travel * (double)L.prm.inflation_covariance) {
@@ -1385,20 +1397,22 @@ int32_t lisreg_loop_detect(lisreg_ctx* ctx, int32_t det_id, const float* corner,
   if (L.n == L.cap) {
     const int ncap = std::max(256, 2 * L.cap);
     float4* np = nullptr; uint8_t* nd = nullptr;
-    CK(cudaMalloc(&np, sizeof(float4) * LOOP_SECT * (size_t)ncap));
-    CK(cudaMalloc(&nd, 3 * (size_t)EPSC_SIZE * ncap));
-    if (L.n) {
-      CK(cudaMemcpyAsync(np, L.d_proj, sizeof(float4) * LOOP_SECT * (size_t)L.n, cudaMemcpyDeviceToDevice, st));
-      CK(cudaMemcpyAsync(nd, L.d_desc, 3 * (size_t)EPSC_SIZE * L.n, cudaMemcpyDeviceToDevice, st));
+    cudaError_t ge = cudaMalloc(&np, sizeof(float4) * LOOP_SECT * (size_t)ncap);
+    if (ge == cudaSuccess) ge = cudaMalloc(&nd, 3 * (size_t)EPSC_SIZE * ncap);
+    if (ge == cudaSuccess && L.n) ge = cudaMemcpyAsync(np, L.d_proj, sizeof(float4) * LOOP_SECT * (size_t)L.n, cudaMemcpyDeviceToDevice, st);
+    if (ge == cudaSuccess && L.n) ge = cudaMemcpyAsync(nd, L.d_desc, 3 * (size_t)EPSC_SIZE * L.n, cudaMemcpyDeviceToDevice, st);
+    if (ge == cudaSuccess) ge = cudaStreamSynchronize(st);
+    if (ge != cudaSuccess) {                     // the old history stays valid and owned; nothing leaks
+      cudaFree(np); cudaFree(nd);
+      return fail(ctx, LISREG_ERR_CUDA, "lisreg_loop_detect: growing the history failed: %s", cudaGetErrorString(ge));
     }
-    CK(cudaStreamSynchronize(st));
     cudaFree(L.d_proj); cudaFree(L.d_desc);
     L.d_proj = np; L.d_desc = nd; L.cap = ncap;
   }
   CK(cudaMemcpyAsync(L.d_proj + (size_t)LOOP_SECT * L.n, d_curproj, sizeof(float4) * LOOP_SECT, cudaMemcpyDeviceToDevice, st));
   k_epsc_describe<<<1, 256, 0, st>>>((const EpscCloud*)(d + o_desc), L.d_lut, L.d_desc + 3 * (size_t)EPSC_SIZE * L.n, nullptr, 0, 1); LAUNCH_CK();
   CK(cudaStreamSynchronize(st));
-  L.px.push_back(cx); L.py.push_back(cy); L.yaw.push_back(yaw_t); L.n++;
+  L.travel.push_back(travel_cur); L.px.push_back(cx); L.py.push_back(cy); L.yaw.push_back(yaw_t); L.n++;
   // ---- best candidate per descriptor kind (:812-897): first maximum above the threshold wins ----
   const int use[3] = {L.prm.use_epsc, L.prm.use_sepsc, L.prm.use_fepsc};
   int best_id[3] = {-1, -1, -1}; double best_score[3] = {0, 0, 0}; float best_T[3][16];

@@ -303,13 +303,14 @@ constexpr float KNN_PAD = 0.1f;          // proof margin (m) the ball walk of sp
 
 #define KNN_INF __int_as_float(0x7f800000)   // +inf
 
-// candidates arrive in ascending position order (rows in ascending cell order, points ascending inside a
-// streak), so on equal distance the resident entry - smaller position - stays ahead: float compares suffice
-// for the lexicographic (d^2, position) order of the 64-bit keys used elsewhere
-__device__ __forceinline__ void knn6_insert_mono(float (&bd)[6], unsigned (&bp)[6], float d, unsigned p) {
+// sorted insert into the running top-6 (distances + positions).  Bit-equal distances are ordered by the ORIGINAL
+// point index (grid.cuh knn_key_less: the oracle's order); the index is fetched only on such a tie, so the common
+// path is one float compare per stage.
+__device__ __forceinline__ void knn6_insert_mono(const float4* __restrict__ pts, float (&bd)[6], unsigned (&bp)[6], float d, unsigned p) {
 #pragma unroll
   for (int j = 0; j < 6; j++) {
-    const bool keep = bd[j] <= d;
+    bool keep = bd[j] <= d;
+    if (bd[j] == d && d < KNN_INF) keep = knn_orig(pts, bp[j]) < knn_orig(pts, p);   // (a displaced +inf sentinel bubbles down past its peers)
     const float lo_d = keep ? bd[j] : d; const unsigned lo_p = keep ? bp[j] : p;
     d = keep ? d : bd[j]; p = keep ? p : bp[j];
     bd[j] = lo_d; bp[j] = lo_p;
@@ -325,8 +326,7 @@ __device__ __forceinline__ float knn_dist2(float qx, float qy, float qz, float4 
 // walks the nr candidate ranges staged in this thread's column of the shared range table (stride LM_THREADS) as ONE
 // list.  Software pipeline: c0 is processed while c1 and c2 are in flight.  adv() steps the cursor (p, e, k) to the
 // next candidate of the flattened list; past the end it keeps returning the last valid position (harmless
-// re-load) and `left` counts what is really there.  Ranges must be in ascending position order (see
-// knn6_insert_mono).
+// re-load) and `left` counts what is really there.
 __device__ __forceinline__ void knn6_scan_ranges(const float4* __restrict__ pts, const uint2* rng, int nr, float qx, float qy, float qz,
                                                  float (&bd)[6], unsigned (&bp)[6]) {
   if (nr <= 0) return;
@@ -345,7 +345,7 @@ __device__ __forceinline__ void knn6_scan_ranges(const float4* __restrict__ pts,
   while (left > 0) {
     const unsigned p2 = p; const float4 c2 = __ldg(&pts[p]); adv();
     const float d = knn_dist2(qx, qy, qz, c0);
-    if (d < bd[5]) knn6_insert_mono(bd, bp, d, p0);
+    if (d <= bd[5]) knn6_insert_mono(pts, bd, bp, d, p0);   // "<=": a tie with the 6th is decided inside
     c0 = c1; p0 = p1; c1 = c2; p1 = p2;
     left--;
   }
@@ -540,11 +540,22 @@ k_knn_check(const RegDesc* __restrict__ descs, const RegState* __restrict__ stat
               if (r * r * 0.99999f > bmax) {     // no other map point can be as close as the farthest neighbour
                 need = false;
                 if (bmax < gate) {
-                  // refresh the (d^2, position) order: 9-comparator network
+                  // refresh the (d^2, original index) order: 9-comparator network on (d^2, position) keys, then - only when
+                  // two of the five distances are bit-equal - an insertion sort with the full order
 #define LISREG_CSWAP(i, j) { const knn_key a_ = key[i], b_ = key[j]; const bool sw_ = b_ < a_; key[i] = sw_ ? b_ : a_; key[j] = sw_ ? a_ : b_; }
                   LISREG_CSWAP(0, 1) LISREG_CSWAP(3, 4) LISREG_CSWAP(2, 4) LISREG_CSWAP(2, 3) LISREG_CSWAP(1, 4)
                   LISREG_CSWAP(0, 3) LISREG_CSWAP(0, 2) LISREG_CSWAP(1, 3) LISREG_CSWAP(1, 2)
 #undef LISREG_CSWAP
+                  bool tie = false;
+#pragma unroll
+                  for (int j = 0; j < 4; j++) tie |= (unsigned)(key[j] >> 32) == (unsigned)(key[j + 1] >> 32);
+                  if (tie) {
+#pragma unroll
+                    for (int j = 1; j < 5; j++)
+#pragma unroll
+                      for (int k = j; k > 0; k--)
+                        if (knn_key_less(pts, key[k], key[k - 1])) { const knn_key t_ = key[k]; key[k] = key[k - 1]; key[k - 1] = t_; }
+                  }
                   bool changed = false;
 #pragma unroll
                   for (int j = 0; j < 5; j++) changed |= knn_key_pos(key[j]) != pos[j];
@@ -707,7 +718,7 @@ k_knn_coop(const RegDesc* __restrict__ descs, const RegState* __restrict__ state
           const uint32_t b = __ldg(&g.cell_start[rowbase + xa]), e = __ldg(&g.cell_start[rowbase + xb + 1]);
           for (uint32_t c = b; c < e; c++) {
             const float dd = knn_dist2(x0, y0, z0, __ldg(&g.pts[c]));
-            if (dd < bd[5]) knn6_insert_mono(bd, bp, dd, c);
+            if (dd <= bd[5]) knn6_insert_mono(g.pts, bd, bp, dd, c);
           }
         }
         lbu = Rn;
@@ -729,8 +740,15 @@ k_knn_coop(const RegDesc* __restrict__ descs, const RegState* __restrict__ state
       for (int k = 0; k < 6; k++) {
         const unsigned hd = __float_as_uint(bd[0]);                       // d^2 >= 0: bit order == value order; +inf = empty
         const unsigned md = __reduce_min_sync(FULL, hd);
-        const unsigned mpos = __reduce_min_sync(FULL, hd == md ? bp[0] : 0xffffffffu);
-        if (hd == md && bp[0] == mpos && mpos != 0xffffffffu) {           // the owning lane pops its head
+        const bool cand = hd == md && bp[0] != 0xffffffffu;
+        unsigned mpos;
+        if (__popc(__ballot_sync(FULL, cand)) <= 1) mpos = __reduce_min_sync(FULL, cand ? bp[0] : 0xffffffffu);
+        else {                                                            // bit-equal heads: the smaller ORIGINAL index wins
+          const unsigned o = cand ? (unsigned)knn_orig(g.pts, bp[0]) : 0xffffffffu;
+          const unsigned mo = __reduce_min_sync(FULL, o);
+          mpos = __reduce_min_sync(FULL, (cand && o == mo) ? bp[0] : 0xffffffffu);
+        }
+        if (cand && bp[0] == mpos) {                                      // the owning lane pops its head
 #pragma unroll
           for (int j = 0; j < 5; j++) { bd[j] = bd[j + 1]; bp[j] = bp[j + 1]; }
           bd[5] = KNN_INF; bp[5] = 0xffffffffu;

@@ -7,7 +7,8 @@
 //   k_loop_project  360-sector {count, last x, last y, last label} projection of the semantic cloud (one block)
 //   k_loop_align    per candidate: sector-count shift search (60 shifts), rotation of the current sector points,
 //                   PCL-default point-to-point ICP on <= 360 planar points (brute-force 1-NN in shared memory,
-//                   fp64 correspondence sums in a fixed order, Horn rigid fit) -> T = T_icp * Rz(angle)
+//                   fp64 correspondence sums in source-index order = the oracle's order, Horn rigid fit)
+//                   -> T = T_icp * Rz(angle), bit-identical to the oracle
 //   k_epsc_describe (epsc.cuh) with the per-candidate transform -> EPSC / SEPSC / FEPSC of the moved cloud
 //   k_loop_score    per candidate: 20-shift byte SAD against the stored descriptors of that history keyframe
 // The travel-distance gate, the best-candidate selection and the history bookkeeping are a few scalars per
@@ -57,14 +58,15 @@ struct LoopAlignOut { float T[16]; float diff_x, diff_y, yaw; int icp_iters; };
 __global__ void __launch_bounds__(LOOP_THREADS)
 k_loop_align(const float4* __restrict__ hist, const float4* __restrict__ cur, const int* __restrict__ cand_id,
              const float* __restrict__ cand_yaw, LoopAlignOut* __restrict__ out) {
-  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int c = blockIdx.x, tid = threadIdx.x;
   const float4* h = hist + (size_t)cand_id[c] * LOOP_SECT;
   __shared__ float4 s1[LOOP_SECT], s2[LOOP_SECT];
   __shared__ float s_dis[64];
   __shared__ float s_tx[LOOP_SECT], s_ty[LOOP_SECT], s_sx[LOOP_SECT], s_sy[LOOP_SECT], s_sz[LOOP_SECT];   // target (cloud1), source (cloud2, moving)
   __shared__ int s_nt, s_ns, s_tmp_id, s_state;
   __shared__ float s_angle, s_T[16], s_F[16];
-  __shared__ double s_part[LOOP_THREADS / 32][ICP_NSUM];
+  __shared__ int s_bj[LOOP_SECT];
+  __shared__ float s_bd[LOOP_SECT];
   __shared__ IcpScratch s_sc;
   __shared__ double s_prev_mse;
   for (int i = tid; i < LOOP_SECT; i += LOOP_THREADS) { s1[i] = __ldg(&h[i]); s2[i] = __ldg(&cur[i]); }
@@ -113,9 +115,7 @@ k_loop_align(const float4* __restrict__ hist, const float4* __restrict__ cur, co
   int iters = 0;
   if (nt > 0 && ns > 0) {
     for (;;) {
-      double acc[17];
-#pragma unroll
-      for (int i = 0; i < 17; i++) acc[i] = 0.0;
+      // correspondences: every thread its own source points (brute-force 1-NN, first minimum = smallest target index)
       for (int i = tid; i < ns; i += LOOP_THREADS) {
         const float x = s_sx[i], y = s_sy[i], z = s_sz[i];
         float bd = 3.0e38f; int bj = -1;
@@ -124,25 +124,33 @@ k_loop_align(const float4* __restrict__ hist, const float4* __restrict__ cur, co
           float d = dx * dx; d = d + dy * dy; d = d + dz * dz;
           if (d < bd) { bd = d; bj = j; }
         }
-        if (bj < 0) continue;
-        const float qx = s_tx[bj], qy = s_ty[bj], qz = 0.f;
-        acc[0] += x; acc[1] += y; acc[2] += z;
-        acc[3] += qx; acc[4] += qy; acc[5] += qz;
-        acc[6] += (double)qx * x; acc[7] += (double)qx * y; acc[8] += (double)qx * z;
-        acc[9] += (double)qy * x; acc[10] += (double)qy * y; acc[11] += (double)qy * z;
-        acc[12] += (double)qz * x; acc[13] += (double)qz * y; acc[14] += (double)qz * z;
-        acc[15] += (double)bd; acc[16] += 1.0;
+        s_bj[i] = bj; s_bd[i] = bd;
       }
-#pragma unroll
-      for (int i = 0; i < 17; i++) {
-        double v = acc[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) s_part[wid][i] = v;
+      __syncthreads();
+      // the 17 fp64 sums, each accumulated by ONE thread over the source points in index order: the summation order of
+      // the CPU oracle (oracle/orc_icp.cpp), so the fitted transform - and every descriptor byte binned after it - is
+      // bit-identical to it.  <= 360 terms per sum.
+      if (tid < 17) {
+        // sum tid: 0-2 source x y z, 3-5 target x y z, 6-14 target_a * source_b (row-major), 15 d^2, 16 count
+        const int a = tid < 6 ? tid % 3 : (tid - 6) / 3, b = (tid - 6) % 3;
+        const float* src_b = (tid < 3 ? tid : b) == 0 ? s_sx : (tid < 3 ? tid : b) == 1 ? s_sy : s_sz;
+        double v = 0.0;
+        for (int i = 0; i < ns; i++) {
+          const int bj = s_bj[i];
+          if (bj < 0) continue;
+          const float qa = a == 0 ? s_tx[bj] : a == 1 ? s_ty[bj] : 0.f;
+          double t;
+          if (tid < 3) t = (double)src_b[i];
+          else if (tid < 6) t = (double)qa;
+          else if (tid < 15) t = (double)qa * (double)src_b[i];
+          else if (tid == 15) t = (double)s_bd[i];
+          else t = 1.0;
+          v += t;
+        }
+        s_sc.sums[tid] = v;
       }
       __syncthreads();
       if (tid == 0) {
-        for (int i = 0; i < 17; i++) { double v = 0.0; for (int w = 0; w < LOOP_THREADS / 32; w++) v += s_part[w][i]; s_sc.sums[i] = v; }
         const double n = s_sc.sums[16];
         if (n < 3) s_state = 1;                                   // min_number_correspondences_: not converged, stop
         else {

@@ -11,7 +11,7 @@ import pytest
 from lis_slam_b200 import synth
 from oracle import orc
 
-from common import local_map, reg_case
+from common import lattice_map, lattice_queries, local_map, reg_case
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -83,6 +83,22 @@ def test_grid_knn_exact_for_any_cell_size(H):
         mp = np.ascontiguousarray(m[key])
         io, so = orc.knn(mp, q, 5)
         for gate, h in ((1.0, 0.6), (1.0, 1.003), (2.0, 0.6), (1.0, 0.31)):
+            idx = np.empty((len(q), 5), np.int32); sqd = np.empty((len(q), 5), np.float32)
+            H.hc_knn5(mp.ctypes.data_as(C.c_void_p), len(mp), q.ctypes.data_as(C.c_void_p), len(q), C.c_float(h), C.c_float(gate),
+                      idx.ctypes.data_as(C.c_void_p), sqd.ctypes.data_as(C.c_void_p))
+            inside = so < gate
+            assert np.array_equal(np.where(inside, io, -1), idx) and np.array_equal(so[inside], sqd[inside])
+
+
+def test_grid_knn_tie_order_matches_oracle_on_lattice(H):
+    """Maps with exactly equidistant / duplicated points: neighbour INDICES (not only distances) equal the oracle's,
+    i.e. bit-equal distances are ordered by original index on both sides (grid.cuh knn_key_less)."""
+    m = lattice_map()
+    for which, key in ((0, "corner"), (1, "surf")):
+        mp = np.ascontiguousarray(m[key]); q = lattice_queries(m, which, n=1500)
+        io, so = orc.knn(mp, q, 5)
+        assert (so[:, 0] == so[:, 1]).mean() > 0.1 and (so[:, 3] == so[:, 4]).mean() > 0.1     # ties are the rule here
+        for gate, h in ((1.0, 0.6), (2.0, 0.6), (1.0, 0.31)):
             idx = np.empty((len(q), 5), np.int32); sqd = np.empty((len(q), 5), np.float32)
             H.hc_knn5(mp.ctypes.data_as(C.c_void_p), len(mp), q.ctypes.data_as(C.c_void_p), len(q), C.c_float(h), C.c_float(gate),
                       idx.ctypes.data_as(C.c_void_p), sqd.ctypes.data_as(C.c_void_p))

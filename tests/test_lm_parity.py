@@ -8,7 +8,7 @@ from lis_slam_b200 import engine as E
 from lis_slam_b200 import synth
 from oracle import orc
 
-from common import local_map, reg_case, scene
+from common import lattice_map, lattice_queries, local_map, reg_case, scene
 
 pytestmark = pytest.mark.gpu
 
@@ -226,3 +226,97 @@ def test_map_distance_filter_matches_oracle(engine, gpu_map):
         assert 0 < kg.sum() < len(kg)
     small = feat[:10]
     assert engine.map_distance_filter(mid, 1, small).all() and orc.map_distance_filter(small, m["surf"]).all()
+
+
+@pytest.mark.parametrize("which", [0, 1])
+@pytest.mark.parametrize("gate", [1.0, 2.0])
+def test_knn5_tie_order_on_lattice_map(engine, which, gate):
+    """Exactly equidistant and duplicated map points (lattice + coinciding centroids, shuffled): the neighbour INDICES
+    equal the oracle's - bit-equal distances are ordered by original index on both sides - through the block scan, the
+    wide scan and the ball walk (k_knn5 alternates the deferred paths)."""
+    m = lattice_map()
+    mid = engine.map_create(m["corner"], m["surf"], gate_hint=gate)
+    cloud = m["corner"] if which == 0 else m["surf"]
+    q = lattice_queries(m, which)
+    idx_o, sqd_o = orc.knn(cloud, q, 5)
+    idx_g, sqd_g = engine.knn5(mid, which, q, gate)
+    engine.map_destroy(mid)
+    inside = sqd_o < gate
+    assert (sqd_o[:, 3] == sqd_o[:, 4]).mean() > 0.1          # ties at the 5th place are the rule here
+    assert np.array_equal(np.where(inside, idx_o, -1), idx_g)
+    assert np.array_equal(sqd_o[inside], sqd_g[inside])
+
+
+@pytest.mark.parametrize("variant", ["A", "B"])
+def test_registration_on_lattice_map_matches_oracle(engine, variant):
+    """Whole Gauss-Newton loop against a map full of ties: every search path (check / proof refresh, block scan, wide
+    scan, warp-cooperative merge) must pick the oracle's neighbours, otherwise the fits - and the selection counts -
+    drift.  Selection counts equal per iteration, pose within the north_star tolerance."""
+    m = lattice_map()
+    rng = np.random.default_rng(31)
+    truth = np.array([0.004, -0.003, 0.3, 1.0, -0.5, 0.02], np.float32)
+    T = synth.pose_to_T(truth)
+    def scan_of(cloud, n):
+        sel = np.sort(rng.choice(len(cloud), n, replace=False))
+        w = cloud[sel, :3].astype(np.float64) + rng.normal(0, 0.004, (n, 3))
+        out = np.zeros((n, 4), np.float32); out[:, :3] = ((w - T[:3, 3]) @ T[:3, :3]).astype(np.float32)
+        return out
+    corner = scan_of(m["corner"], 400); surf = scan_of(m["surf"], 4000)
+    guess = synth.perturb_pose(truth, rng, rot=0.01, trans=0.1)
+    gate = 1.0 if variant == "A" else 2.0
+    mid = engine.map_create(m["corner"], m["surf"], gate_hint=gate)
+    kw = dict(early_exit=0, max_iters=8)
+    pose_o, res_o, log_o = orc.scan2map(corner, surf, m["corner"], m["surf"], guess, orc.lm_params(variant, **kw))
+    pose_g, res_g, log_g = engine.scan2map(mid, corner, surf, guess, E.lm_params(variant, **kw), log=True)
+    # batched path (512-query tiles, warp-cooperative late iterations)
+    poses_b, res_b, _ = engine.scan2map_batch([(mid, corner, surf, None, None)] * 40, [guess] * 40, E.lm_params(variant, **kw))
+    engine.map_destroy(mid)
+    for lo, lg in zip(log_o, log_g):
+        assert (lo.n_corner_sel, lo.n_surf_sel) == (lg.n_corner_sel, lg.n_surf_sel), (lo.n_corner_sel, lo.n_surf_sel, lg.n_corner_sel, lg.n_surf_sel)
+        A_o, A_g = np.array(lo.AtA), np.array(lg.AtA)
+        assert np.abs(A_o - A_g).max() <= 2e-4 * np.abs(A_o).max()
+    assert log_o[0].n_sel > 2000
+    er, et = synth.pose_error(pose_o, pose_g)
+    assert er <= ROT_TOL and et <= TRANS_TOL, (er, et)
+    for pb, rb in zip(poses_b, res_b):
+        eb = synth.pose_error(pose_o, pb)
+        assert eb[0] <= ROT_TOL and eb[1] <= TRANS_TOL and rb.n_sel_last == res_o.n_sel_last
+
+
+def test_lattice_ties_at_iteration_zero(engine):
+    """Guess = identity on scan points that sit on binary-exact offsets of the lattice: at iteration 0 most queries have
+    several bit-equal neighbour distances (also at the 5th / 6th place), so the line / plane fits depend on the
+    tie-break.  Selection counts equal, A^T A within the usual 2e-4 at every iteration, single and batched."""
+    m = lattice_map()
+    corner = lattice_queries(m, 0, n=400, seed=5); surf = lattice_queries(m, 1, n=4000, seed=6)
+    corner[:, 0] += np.float32(1 / 128); surf[:, 2] += np.float32(1 / 128); surf[:, 1] += np.float32(1 / 256)   # off the lines / planes: no 0 / 0
+    guess = np.zeros(6, np.float32)
+    mid = engine.map_create(m["corner"], m["surf"], gate_hint=1.0)
+    kw = dict(early_exit=0, max_iters=4)
+    pose_o, res_o, log_o = orc.scan2map(corner, surf, m["corner"], m["surf"], guess, orc.lm_params("A", **kw))
+    pose_g, res_g, log_g = engine.scan2map(mid, corner, surf, guess, E.lm_params("A", **kw), log=True)
+    poses_b, res_b, _ = engine.scan2map_batch([(mid, corner, surf, None, None)] * 40, [guess] * 40, E.lm_params("A", **kw))
+    engine.map_destroy(mid)
+    for lo, lg in zip(log_o, log_g):
+        assert (lo.n_corner_sel, lo.n_surf_sel) == (lg.n_corner_sel, lg.n_surf_sel)
+        A_o, A_g = np.array(lo.AtA), np.array(lg.AtA)
+        assert np.abs(A_o - A_g).max() <= 2e-4 * np.abs(A_o).max()
+    er, et = synth.pose_error(pose_o, pose_g)
+    assert er <= 1e-6 and et <= 1e-5, (er, et)
+    for pb in poses_b:
+        eb = synth.pose_error(pose_o, pb)
+        assert eb[0] <= 1e-6 and eb[1] <= 1e-5
+
+
+def test_non_finite_map_is_rejected(engine):
+    """A NaN / Inf coordinate in a map cloud must fail loudly (LISREG_ERR_ARG) instead of planning a garbage grid; the
+    context stays usable afterwards."""
+    m = local_map()
+    bad = m["surf"][:5000].copy(); bad[17, 0] = np.inf
+    with pytest.raises(E.LisregError):
+        engine.map_create(m["corner"][:1000], bad, gate_hint=1.0)
+    bad[17, 0] = -np.inf
+    with pytest.raises(E.LisregError):
+        engine.map_create(bad, m["surf"][:1000], gate_hint=1.0)
+    mid = engine.map_create(m["corner"][:1000], m["surf"][:5000], gate_hint=1.0)
+    engine.map_destroy(mid)

@@ -1,0 +1,128 @@
+"""Pins the C++ oracle (oracle/orc_*.cpp, the checker of every GPU parity test) to an INDEPENDENT restatement of the
+reference written in Python on top of library routines (oracle/pyref.py: scipy cKDTree, cv2.eigen, cv2.solve(QR),
+cv2.gemm, cv2.invert, numpy fp32) - SURVEY.md 8c (1)-(2).  A misreading of the reference shared by the C++ oracle and
+the CUDA kernels (same author) would show up here.  Tolerances: pose <= 1e-6, selection counts equal,
+A^T A <= 1e-6 relative, per iteration.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import orc, pyref
+
+from common import lattice_map, local_map, reg_case
+
+
+def _compare(f, m, guess, variant, labels=False, **kw):
+    po = orc.lm_params(variant, **kw)
+    pkw = dict(kw)
+    if "early_exit" in pkw:
+        pkw["early_exit"] = bool(pkw["early_exit"])
+    pp = pyref.params(variant, **pkw)
+    cl = f.get("corner_label") if labels else None
+    sl = f.get("surf_label") if labels else None
+    pose_c, res_c, log_c = orc.scan2map(f["corner"], f["surf"], m["corner"], m["surf"], guess, po, clabel=cl, slabel=sl)
+    pose_p, info_p, log_p = pyref.scan2map(f["corner"], f["surf"], m["corner"], m["surf"], guess, pp, clabel=cl, slabel=sl)
+    assert res_c.iters == info_p["iters"], (res_c.iters, info_p["iters"])
+    assert bool(res_c.converged) == info_p["converged"] and bool(res_c.is_degenerate) == info_p["degenerate"]
+    assert res_c.status == info_p["status"]
+    for lc, lp in zip(log_c, log_p):
+        assert (lc.n_corner_sel, lc.n_surf_sel) == (lp["n_corner_sel"], lp["n_surf_sel"])
+        if not lp["solved"]:
+            assert lc.solved == 0
+            continue
+        A_c = np.array(lc.AtA, np.float64).reshape(6, 6); A_p = lp["AtA"].astype(np.float64)
+        assert np.abs(A_c - A_p).max() <= 1e-6 * np.abs(A_p).max()
+        b_c = np.array(lc.AtB, np.float64); b_p = lp["AtB"].astype(np.float64)
+        # A^T b sums signed residuals (pd2 = n.q + pd cancels ~40 m down to ~1 cm, so the two plane-fit solvers' fp32
+        # rounding shows): bounded by 1e-6 of the Cauchy-Schwarz scale sqrt(AtA_ii * n_sel * mean b^2) ~ |row_i| |b|
+        scale = np.sqrt(np.diag(A_p) * lp["n_sel"]) * 0.05
+        assert (np.abs(b_c - b_p) <= 1e-6 * scale + 1e-9).all(), (b_c, b_p, scale)
+        assert np.abs(np.array(lc.X) - lp["X"]).max() <= 1e-6
+        assert np.abs(np.array(lc.pose) - lp["pose"]).max() <= 1e-6
+    assert np.abs(np.asarray(pose_c) - pose_p).max() <= 1e-6
+    return res_c, log_c
+
+
+@pytest.mark.parametrize("seed,nc,ns", [(0, 4000, 12000), (1, 1500, 5000), (2, 1500, 5000)])
+def test_cpp_oracle_matches_python_oracle_variant_a(seed, nc, ns):
+    m = local_map()
+    f, truth, guess = reg_case(seed, n_corner=nc, n_surf=ns)
+    res, log = _compare(f, m, guess, "A")
+    assert res.iters >= 3 and log[0].n_sel > 0.5 * (nc + ns)
+
+
+def test_cpp_oracle_matches_python_oracle_variant_b_labels():
+    m = local_map()
+    f, truth, guess = reg_case(4, n_corner=1500, n_surf=5000)
+    _compare(f, m, guess, "B", labels=True)
+
+
+def test_cpp_oracle_matches_python_oracle_fixed_iterations():
+    m = local_map(n_edge=10000, n_surf=40000, seed=3002)
+    f, truth, guess = reg_case(3, n_corner=800, n_surf=2500)
+    res, _ = _compare(f, m, guess, "A", early_exit=0, max_iters=10)
+    assert res.iters == 10
+
+
+def test_degenerate_corridor_q1_both_oracles():
+    """Ground plane only: isDegenerate at iteration 0, zeroed local matP afterwards (quirk Q1) - same story in both."""
+    rng = np.random.default_rng(5)
+    g = np.arange(-30, 30, 0.4, dtype=np.float32)
+    gx, gy = np.meshgrid(g, g, indexing="ij")
+    ms = np.zeros((gx.size, 4), np.float32); ms[:, 0] = gx.ravel(); ms[:, 1] = gy.ravel(); ms[:, 2] = -1.73
+    ms[:, :3] += rng.normal(0, 0.005, (len(ms), 3)).astype(np.float32)
+    mc = ms[:10].copy()
+    surf = np.zeros((3000, 4), np.float32)
+    surf[:, :2] = rng.uniform(-20, 20, (3000, 2)); surf[:, 2] = -1.73 + rng.normal(0, 0.01, 3000)
+    f = {"corner": surf[:20].copy(), "surf": surf}
+    guess = np.array([0.003, -0.002, 0.01, 0.1, -0.1, 0.05], np.float32)
+    res, log = _compare(f, {"corner": mc, "surf": ms}, guess, "A")
+    assert res.is_degenerate == 1 and res.iters == 2
+
+
+def test_not_enough_features_and_few_correspondences():
+    m = local_map(n_edge=10000, n_surf=40000, seed=3002)
+    f, truth, guess = reg_case(5, n_corner=800, n_surf=2500)
+    few = {"corner": f["corner"], "surf": f["surf"][:100]}
+    _compare(few, m, guess, "A")
+    far = np.array(guess, np.float32); far[3] += 500.0
+    res, _ = _compare(f, m, far, "A")
+    assert res.status == 2 and res.iters == 15
+
+
+def test_plane_fit_against_lstsq():
+    rng = np.random.default_rng(0)
+    n = rng.normal(size=(500, 3)); n /= np.linalg.norm(n, axis=1)[:, None]
+    A = np.zeros((500, 5, 3), np.float32)
+    for i in range(500):
+        base = rng.normal(size=(5, 3)) * 0.3
+        base -= np.outer(base @ n[i], n[i])
+        A[i] = (base + n[i] * rng.uniform(5, 40) + rng.normal(0, 0.01, (5, 3))).astype(np.float32)
+    X = pyref.plane_fit_colpiv_qr(A)
+    for i in range(0, 500, 7):
+        ref = np.linalg.lstsq(A[i].astype(np.float64), -np.ones(5), rcond=None)[0]
+        assert np.abs(X[i] - ref).max() <= 2e-4 * np.abs(ref).max()
+        assert np.array_equal(orc.plane_fit(A[i]), orc.plane_fit(A[i]))
+        assert np.abs(orc.plane_fit(A[i]) - X[i]).max() <= 2e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("leaf", [0.2, 0.4, 1.0])
+def test_voxel_grid_cpp_equals_python(leaf):
+    m = local_map(n_edge=10000, n_surf=40000, seed=3002)
+    rng = np.random.default_rng(int(leaf * 10))
+    for cloud in (m["surf"], m["corner"], lattice_map()["surf"], m["surf"][:1], m["surf"][:0]):
+        cloud = np.ascontiguousarray(cloud).copy()
+        if len(cloud):
+            cloud[:, 3] = rng.uniform(0, 255, len(cloud)).astype(np.float32)
+        a = orc.voxel_grid(cloud, leaf); b = pyref.voxel_grid(cloud, leaf)
+        assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_descriptor_distance_cpp_equals_python():
+    rng = np.random.default_rng(3)
+    base = rng.integers(0, 256, (20, 80)).astype(np.uint8)
+    sparse = (base * (rng.random((20, 80)) < 0.3)).astype(np.uint8)
+    for d1, d2 in ((base, np.roll(base, 3, 1)), (base, np.roll(base, -9, 1)), (sparse, np.roll(sparse, 10, 1)),
+                   (base, 255 - base), (np.zeros((20, 80), np.uint8), np.full((20, 80), 255, np.uint8)), (base, base)):
+        sc, sh, sad = orc.epsc_distance(d1, d2)
+        sp, shp = pyref.calculate_distance(d1, d2)
+        assert sc == sp and (shp is None or shp == sh)
