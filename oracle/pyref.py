@@ -17,8 +17,8 @@ An INDEPENDENT restatement of the scan-to-map loop in Python, written from the r
 Per-point arithmetic is numpy float32 in the reference's expression order; the double-literal sub-expressions
 (`cx + 0.1 * v`, `1 - 0.9 * fabs(d)`, `> 0.2`) are promoted to float64 exactly where C++ promotes them.
 sin / cos follow the repo-wide resolution (DESIGN.md numerics): correctly rounded float of the double routine.
-tests/test_pyref_oracle.py checks the C++ oracle against this file: pose <= 1e-6, selection counts equal,
-A^T A <= 1e-6 relative, per iteration.  PARITY UNPINNED by the reference itself (it ships no vectors and cannot be
+tests/test_pyref_oracle.py checks the C++ oracle against this file: pose and step <= 1e-6, selection counts equal,
+A^T A <= 5e-6 relative (1e-6 typical), per iteration.  PARITY UNPINNED by the reference itself (it ships no vectors and cannot be
 built here); this file pins the C++ oracle to an independent reading plus the reference's own library calls.
 """
 import numpy as np
