@@ -256,6 +256,44 @@ int32_t lisreg_frames_batch_submit(lisreg_ctx* ctx, int32_t F, const lisreg_fram
                                    const lisreg_frame_params* prm, int32_t* ticket);
 int32_t lisreg_frames_batch_wait(lisreg_ctx* ctx, int32_t ticket, float* pose6xF, lisreg_lm_result* resxF);
 
+/* ---- streaming odometry: device-resident sliding-window local map (SURVEY.md 8f "next" #1; BASELINE configs[1], [4]) ----
+ * One lisreg_odom = the state OdomEstimationNode keeps between frames (odomEstimationNode.cpp:56-71, 80-100):
+ * transformTobeMapped, lastTransformTobeMapped, transformPriFrame, keyFrameId, deltaR / deltaT and the vectors
+ * laserCloudCornerVec / laserCloudSurfVec of the last <= window key-frame clouds (already in the map frame) - the
+ * latter resident in HBM.  lisreg_odom_push = laserCloudInfoHandler (:163-239) for one sweep without IMU / odometry
+ * input (cloudInfo.odomAvailable == false): updateInitialGuess (constant-velocity model, :353-391) -> map = the
+ * window concatenated newest first + VoxelGrid (:185-207; rebuilt only when a key frame was added - the reference
+ * rebuilds the identical map every frame) -> projectPointCloud .. extractFeatures (laserProcessing.cpp:467-713) ->
+ * currentCloudInit (:260-281) -> scan2SubMapOptimization (:596-626) -> key-frame rule (:216-229) -> saveKeyFrames
+ * (:421-478).  Nothing but the sweep goes to the device and nothing but the pose / result record comes back.
+ * use_graph = 1 replays the per-frame kernel sequence as ONE CUDA graph (needs a context with a non-default stream:
+ * lisreg_config.own_stream = 1 or an explicit stream; ignored otherwise); results are identical.
+ * Frame t needs the pose and the map of frame t-1: this mode does not shard (multi-GPU = independent replicas). */
+typedef struct lisreg_odom_params {
+  lisreg_frame_params frame;        /* feature extraction, leaf sizes 0.2 / 0.4, loop constants (variant A) */
+  float keyframe_min_distance;      /* keyFrameMiniDistance 1.4 (config/params.yaml:140) */
+  float keyframe_min_yaw;           /* keyFrameMiniYaw 0.5 (:141) */
+  int32_t window;                   /* 19: while (laserCloudSurfVec.size() >= 20) erase(begin) (:463-467) */
+  int32_t use_graph;
+} lisreg_odom_params;
+typedef struct lisreg_odom_result {
+  lisreg_lm_result lm;              /* status / iterations / deltaR / deltaT of this frame's loop (zeros for the first frame) */
+  int32_t frame_id, keyframe_id;    /* frames pushed so far, keyFrameId after this frame */
+  int32_t keyframe_saved, map_rebuilt;
+  int32_t n_map_corner, n_map_surf; /* laserCloudCornerFromMapDSNum / SurfFromMapDSNum of the map this frame was registered to */
+  float guess[6];                   /* transformTobeMapped after updateInitialGuess */
+} lisreg_odom_result;
+void lisreg_odom_params_default(lisreg_odom_params* p);
+int32_t lisreg_odom_create(lisreg_ctx* ctx, const lisreg_odom_params* prm, int32_t* odom_id);
+int32_t lisreg_odom_destroy(lisreg_ctx* ctx, int32_t odom_id);
+/* host buffers (pinned memory makes the upload asynchronous); init_pose6 (nullable) = the pose of the FIRST frame
+ * (imuRollInit / PitchInit / YawInit + origin upstream), ignored afterwards */
+int32_t lisreg_odom_push(lisreg_ctx* ctx, int32_t odom_id, const float* pts, const uint16_t* ring, int32_t n,
+                         const float* init_pose6, float pose6[6], lisreg_odom_result* res);
+/* same with the sweep already resident in HBM */
+int32_t lisreg_odom_push_dev(lisreg_ctx* ctx, int32_t odom_id, const float* d_pts, const uint16_t* d_ring, int32_t n,
+                             const float* init_pose6, float pose6[6], lisreg_odom_result* res);
+
 /* ---- EPSC loop-closure descriptors and scoring (B3 pieces) ----
  * lisreg_epsc_describe replaces EPSCGeneration::calculateEPSC / calculateSEPSC / calculateFEPSC
  * (epscGeneration.cpp:478-607) for n submaps/keyframes at once; using_map is the 256-entry label -> class
@@ -334,6 +372,25 @@ typedef struct lisreg_icp_result { float T[16]; double fitness; int32_t converge
 void lisreg_icp_params_default(lisreg_icp_params* p);
 int32_t lisreg_icp_verify_batch(lisreg_ctx* ctx, int32_t P, const lisreg_icp_pair* pairs, const lisreg_icp_params* prm,
                                 lisreg_icp_result* out);
+
+/* ---- multi-GPU exchange: one NCCL all-gather of fixed-size result records ----
+ * Frames and loop-closure candidate pairs are independent units sharded one process per GPU; the ONLY exchange step
+ * of the path is an all-gather of the per-rank result blocks (6-DoF poses + status: 40 B per frame).  NCCL is bound
+ * at run time (dlopen of libnccl.so.2 - the copy already loaded in the process when there is one), so liblisreg.so
+ * has no link-time NCCL dependency.  Either adopt an existing ncclComm_t of the host program or let the context
+ * create its own: rank 0 calls lisreg_comm_unique_id(), the 128 bytes travel out of band (ROS parameter, file,
+ * MPI, torch.distributed ...), every rank calls lisreg_comm_init().
+ * lisreg_allgather_results enqueues ncclAllGather(d_send -> d_recv, bytes_per_rank per rank) on a private stream
+ * that first waits for everything enqueued so far on the context stream, and returns at once: the kernels of the
+ * next batch do not wait for the collective.  lisreg_allgather_wait blocks the host until the last gather has
+ * landed (d_send may be overwritten and d_recv read after it). */
+#define LISREG_NCCL_ID_BYTES 128
+int32_t lisreg_comm_unique_id(uint8_t id[LISREG_NCCL_ID_BYTES]);
+int32_t lisreg_comm_init(lisreg_ctx* ctx, int32_t world, int32_t rank, const uint8_t id[LISREG_NCCL_ID_BYTES]);
+int32_t lisreg_comm_adopt(lisreg_ctx* ctx, void* nccl_comm /* ncclComm_t */, int32_t world, int32_t rank);
+int32_t lisreg_comm_destroy(lisreg_ctx* ctx);
+int32_t lisreg_allgather_results(lisreg_ctx* ctx, const void* d_send, void* d_recv, uint64_t bytes_per_rank);
+int32_t lisreg_allgather_wait(lisreg_ctx* ctx);
 
 /* device self-test of the small dense routines (cv::eigen / cv::solve(QR) / cv::Mat::inv restatements):
  * out98 = E[6], V[36] (eigenvectors in rows), X[6] (QR solve of A x = b), ok, Ainv[36] (LU), ok,

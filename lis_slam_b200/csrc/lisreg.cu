@@ -1,6 +1,7 @@
 // lisreg C-ABI implementation (include/lisreg.h): context, map index build, LM driver.
 // sm_100a only; there is no CPU fallback — every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -17,6 +18,7 @@
 #include "epsc.cuh"
 #include "icp.cuh"
 #include "loop.cuh"
+#include "odom.cuh"
 
 using namespace lisreg;
 
@@ -54,6 +56,7 @@ struct PinBuf {
 struct CloudIndex {   // one cloud of a map
   float4* sorted = nullptr;
   uint32_t* cell_start = nullptr;
+  size_t cap_pts = 0, cap_cells = 0;   // allocated capacities: an index rebuilt in place (streaming odometry) only grows
   GridDev g{};
 };
 
@@ -113,6 +116,26 @@ struct lisreg_ctx {
   };
   std::vector<LoopDet> loops;
   DevBuf d_loop;                           // per-call scratch of lisreg_loop_detect
+  struct Odom {                            // streaming odometry state (lisreg_odom_*)
+    bool used = false;
+    lisreg_odom_params prm{};
+    float pose[6] = {0, 0, 0, 0, 0, 0}, last_pose[6] = {0, 0, 0, 0, 0, 0}, key_pose[6] = {0, 0, 0, 0, 0, 0};   // transformTobeMapped, lastTransformTobeMapped, transformPriFrame
+    bool first_trans = false, have_last = false, first_flag = true;
+    float deltaR = 100.f, deltaT = 100.f;
+    int keyframe_id = 0, frame_id = 0;
+    int slots = 0, ccap = 0, scap = 0;     // ring of key-frame slots: capacities per slot (corner / surface points)
+    float4* d_win_c = nullptr; float4* d_win_s = nullptr;
+    std::vector<int> order, nc, ns;        // slot ids oldest .. newest; points per slot
+    int map_id = -1; bool map_dirty = true; int n_map_c = 0, n_map_s = 0;
+    DevBuf d_cat, d_mapvox, d_mapseg, d_in, d_io;
+    PinBuf h_io, h_desc;
+    int64_t graph_kernels = 0;
+    cudaGraphExec_t gexec = nullptr; std::vector<const void*> gkey;   // captured per-frame graph + the buffer addresses it was captured with
+  };
+  std::vector<Odom> odoms;
+  // multi-GPU exchange: NCCL communicator (own or adopted), private stream, fence / done events
+  void* comm = nullptr; bool comm_owned = false; int comm_world = 1, comm_rank = 0;
+  cudaStream_t comm_stream = nullptr; cudaEvent_t comm_fence = nullptr, comm_done = nullptr; bool comm_pending = false;
   int knn_coop_max = 16384;   // scan lists shorter than this are searched warp-per-query (LISREG_KNN_COOP_MAX; 0 = never)
   int knn_noskip = 0;   // LISREG_KNN_NOSKIP=1: search every query from scratch at every iteration (parity check of the CHECK path)
   // profiling
@@ -161,7 +184,8 @@ __device__ __forceinline__ float ord2f(unsigned u) { return __uint_as_float((u &
 
 __global__ void k_bbox_init(unsigned* bb) { if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffu; else if (threadIdx.x < 6) bb[threadIdx.x] = 0u; }
 
-__global__ void k_bbox(const float4* __restrict__ pts, int n, unsigned* __restrict__ bb) {
+__global__ void k_bbox(const float4* __restrict__ pts, int n, const int* __restrict__ n_ptr, unsigned* __restrict__ bb) {
+  if (n_ptr) n = *n_ptr;
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 p = __ldg(&pts[i]);
@@ -182,8 +206,9 @@ __global__ void k_bbox(const float4* __restrict__ pts, int n, unsigned* __restri
 }
 
 // one thread: choose the cell size (>= h_req, grown until the grid fits max_cells) and dims
-__global__ void k_grid_plan(const unsigned* __restrict__ bb, float h_req, int max_cells, int n, GridDev* __restrict__ out) {
+__global__ void k_grid_plan(const unsigned* __restrict__ bb, float h_req, int max_cells, int n, const int* __restrict__ n_ptr, GridDev* __restrict__ out) {
   GridDev g;
+  if (n_ptr) n = *n_ptr;
   float mn[3], mx[3];
   for (int d = 0; d < 3; d++) { mn[d] = ord2f(bb[d]); mx[d] = ord2f(bb[3 + d]); }
   if (n <= 0) { for (int d = 0; d < 3; d++) { mn[d] = 0.f; mx[d] = 0.f; } }
@@ -285,26 +310,42 @@ __global__ void k_cell_order(float4* __restrict__ sorted, const uint32_t* __rest
   }
 }
 
-// builds one cloud index from device-resident points
-static int build_cloud_index(lisreg_ctx* ctx, const float4* d_pts, int n, float h_req, CloudIndex* ci) {
-  cudaStream_t st = ctx->stream;
+// builds one cloud index from device-resident points.  d_n (nullable): the point count lives on the device (output of a
+// voxel grid); n is then only the capacity bound used to size launches and buffers.  The buffers of *ci are re-used
+// when large enough (in-place rebuild).
+static int build_cloud_index(lisreg_ctx* ctx, const float4* d_pts, int n, float h_req, CloudIndex* ci, const int* d_n = nullptr) {
+  cudaStream_t st = ctx->cur->stream;
   CK(ctx->d_bbox.reserve(6 * sizeof(unsigned) + sizeof(GridDev)));
   unsigned* bb = (unsigned*)ctx->d_bbox.p;
   GridDev* d_g = (GridDev*)((char*)ctx->d_bbox.p + 32);
   k_bbox_init<<<1, 32, 0, st>>>(bb); LAUNCH_CK();
-  if (n > 0) { k_bbox<<<std::min(1184, (n + 255) / 256), 256, 0, st>>>(d_pts, n, bb); LAUNCH_CK(); }
-  k_grid_plan<<<1, 1, 0, st>>>(bb, h_req, ctx->max_cells, n, d_g); LAUNCH_CK();
+  if (n > 0) { k_bbox<<<std::min(1184, (n + 255) / 256), 256, 0, st>>>(d_pts, n, d_n, bb); LAUNCH_CK(); }
+  k_grid_plan<<<1, 1, 0, st>>>(bb, h_req, ctx->max_cells, n, d_n, d_g); LAUNCH_CK();
   GridDev g;
   CK(cudaMemcpyAsync(&g, d_g, sizeof(g), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   // a NaN / Inf coordinate makes the planned dimensions meaningless (overflowed or negative): reject the cloud
   if (!(g.nx > 0 && g.ny > 0 && g.nz > 0) || !std::isfinite(g.ox) || !std::isfinite(g.oy) || !std::isfinite(g.oz) || !std::isfinite(g.h) ||
-      (double)g.nx * (double)g.ny * (double)g.nz > (double)ctx->max_cells || g.ncells != g.nx * g.ny * g.nz)
+      (double)g.nx * (double)g.ny * (double)g.nz > (double)ctx->max_cells || g.ncells != g.nx * g.ny * g.nz || g.n < 0 || g.n > n)
     return fail(ctx, LISREG_ERR_ARG, "map cloud has non-finite coordinates (grid %d x %d x %d)", g.nx, g.ny, g.nz);
+  n = g.n;
   const int ncells = g.ncells;
-  CK(cudaMalloc(&ci->sorted, sizeof(float4) * (size_t)std::max(n, 1)));
-  { cudaError_t e2 = cudaMalloc(&ci->cell_start, sizeof(uint32_t) * ((size_t)ncells + 1));
-    if (e2 != cudaSuccess) { cudaFree(ci->sorted); ci->sorted = nullptr; return fail(ctx, LISREG_ERR_CUDA, "cudaMalloc(cell_start) failed: %s", cudaGetErrorString(e2)); } }
+  if ((size_t)std::max(n, 1) > ci->cap_pts) {
+    if (ci->sorted) cudaFree(ci->sorted);
+    ci->sorted = nullptr; ci->cap_pts = 0;
+    const size_t want = (size_t)std::max(n, 1) + (ci->cap_cells ? (size_t)n / 4 : 0);   // in-place rebuilds grow with slack
+    CK(cudaMalloc(&ci->sorted, sizeof(float4) * want));
+    ci->cap_pts = want;
+  }
+  if ((size_t)ncells + 1 > ci->cap_cells) {
+    const bool regrow = ci->cap_cells != 0;
+    if (ci->cell_start) cudaFree(ci->cell_start);
+    ci->cell_start = nullptr; ci->cap_cells = 0;
+    const size_t want = (size_t)ncells + 1 + (regrow ? (size_t)ncells / 4 : 0);
+    cudaError_t e2 = cudaMalloc(&ci->cell_start, sizeof(uint32_t) * want);
+    if (e2 != cudaSuccess) return fail(ctx, LISREG_ERR_CUDA, "cudaMalloc(cell_start) failed: %s", cudaGetErrorString(e2));
+    ci->cap_cells = want;
+  }
   const int nblk = (ncells + 1 + SCAN_BLOCK - 1) / SCAN_BLOCK;
   CK(ctx->d_tmp.reserve(sizeof(int) * (size_t)std::max(n, 1) + sizeof(uint32_t) * ((size_t)ncells + 1) + sizeof(uint32_t) * (size_t)(nblk + 1)));
   int* cell_id = (int*)ctx->d_tmp.p;
@@ -382,6 +423,13 @@ void lisreg_destroy(lisreg_ctx* ctx) {
   for (int i = 0; i < 3; i++) { if (i > 0 && ctx->ws[i].stream) { cudaStreamSynchronize(ctx->ws[i].stream); cudaStreamDestroy(ctx->ws[i].stream); } ctx->ws[i].release(); }
   ctx->h_stage.release(); ctx->h_out.release(); ctx->h_desc.release();
   for (auto& L : ctx->loops) if (L.used) { cudaFree(L.d_proj); cudaFree(L.d_desc); cudaFree(L.d_lut); }
+  lisreg_comm_destroy(ctx);
+  for (auto& O : ctx->odoms) if (O.used) {
+    if (O.gexec) cudaGraphExecDestroy(O.gexec);
+    cudaFree(O.d_win_c); cudaFree(O.d_win_s);
+    for (DevBuf* b : {&O.d_cat, &O.d_mapvox, &O.d_mapseg, &O.d_in, &O.d_io}) b->release();
+    O.h_io.release(); O.h_desc.release();
+  }
   ctx->d_loop.release();
   for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
   for (auto& sl : ctx->slot) { sl.d_stage.release(); sl.d_res.release(); sl.h_out.release(); sl.h_desc.release(); if (sl.done) cudaEventDestroy(sl.done); if (sl.fence) cudaEventDestroy(sl.fence); }
@@ -957,9 +1005,12 @@ void lisreg_frame_params_default(lisreg_frame_params* p) {
 static size_t frame_desc_bytes(int F) {
   return ((sizeof(FeatFrame) + 2 * sizeof(VoxSeg) + sizeof(RegDesc)) * (size_t)F + 255) & ~size_t(255);
 }
+// launch_n > 0: size every launch / buffer for sweeps of up to launch_n points whatever the items say (the per-frame CUDA
+// graph of the streaming odometry is captured once and must fit every later frame; all kernels bound themselves by the
+// device-resident counts, so the results do not depend on it)
 static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, const char* d_arena, uint64_t arena_bytes,
                       float* d_pose, const lisreg_frame_params* prm, lisreg_lm_result* d_res, char* h_pinned = nullptr,
-                      int tiling_B = 0) {
+                      int tiling_B = 0, int launch_n = 0) {
   cudaStream_t st = ctx->cur->stream;
   const lisreg_feat_params* fp = &prm->feat;
   if (fp->n_scan <= 0 || fp->horizon <= 0 || fp->horizon > 2048 || fp->n_scan * 6 > 1024 || fp->downsample_rate <= 0)
@@ -1007,6 +1058,7 @@ static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, co
     d.map_slot = it.map_id; d.pad = 0; d.nc_ptr = vc.out_n; d.ns_ptr = vs.out_n;
     max_n = std::max(max_n, it.n); feat_bytes += 17.0 * it.n;
   }
+  if (launch_n > 0) max_n = std::max(max_n, launch_n);
   // pageable sources: cudaMemcpyAsync returns once they are consumed
   CK(cudaMemcpyAsync(ctx->cur->d_feat_frames.p, hf, sizeof(FeatFrame) * (size_t)F, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->cur->d_vox_segs.p, hv, sizeof(VoxSeg) * 2 * (size_t)F, cudaMemcpyHostToDevice, st));
@@ -1540,6 +1592,414 @@ int32_t lisreg_profile_get(lisreg_ctx* ctx, lisreg_profile* out, int32_t reset) 
   *out = ctx->prof;
   if (reset) ctx->prof = lisreg_profile{};
   return LISREG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU exchange: NCCL bound at run time
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct NcclId { char b[LISREG_NCCL_ID_BYTES]; };                          // ncclUniqueId: 128 opaque bytes, passed by value
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;                                   // ncclResult_t ncclGetUniqueId(ncclUniqueId*)
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+typedef decltype(NcclApi::CommInitRank) nccl_init_fn;
+NcclApi g_nccl;
+bool nccl_load(std::string* why) {
+  if (g_nccl.h) return true;
+  void* h = nullptr;
+  for (const char* name : {"libnccl.so.2", "libnccl.so"}) { h = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+  if (!h) { if (why) *why = std::string("dlopen(libnccl.so.2) failed: ") + (dlerror() ? dlerror() : "?"); return false; }
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (nccl_init_fn)dlsym(h, "ncclCommInitRank");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) { if (why) *why = "libnccl lacks a required symbol"; return false; }
+  g_nccl.h = h;
+  return true;
+}
+const char* nccl_err(int rc) { return g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "nccl error"; }
+}  // namespace
+
+int32_t lisreg_comm_unique_id(uint8_t id[LISREG_NCCL_ID_BYTES]) {
+  if (!id || !nccl_load(nullptr)) return LISREG_ERR_CUDA;
+  return g_nccl.GetUniqueId(id) == 0 ? LISREG_OK : LISREG_ERR_CUDA;
+}
+
+static int comm_streams(lisreg_ctx* ctx) {
+  if (!ctx->comm_stream) CK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  if (!ctx->comm_fence) CK(cudaEventCreateWithFlags(&ctx->comm_fence, cudaEventDisableTiming));
+  if (!ctx->comm_done) CK(cudaEventCreateWithFlags(&ctx->comm_done, cudaEventDisableTiming));
+  return LISREG_OK;
+}
+
+int32_t lisreg_comm_init(lisreg_ctx* ctx, int32_t world, int32_t rank, const uint8_t id[LISREG_NCCL_ID_BYTES]) {
+  if (!ctx || world < 1 || rank < 0 || rank >= world || !id) return fail(ctx, LISREG_ERR_ARG, "lisreg_comm_init: bad argument");
+  std::string why;
+  if (!nccl_load(&why)) return fail(ctx, LISREG_ERR_CUDA, "lisreg_comm_init: %s", why.c_str());
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->comm) lisreg_comm_destroy(ctx);
+  NcclId uid; memcpy(uid.b, id, LISREG_NCCL_ID_BYTES);
+  void* comm = nullptr;
+  const int rc = g_nccl.CommInitRank(&comm, world, uid, rank);
+  if (rc != 0) return fail(ctx, LISREG_ERR_CUDA, "ncclCommInitRank failed: %s", nccl_err(rc));
+  ctx->comm = comm; ctx->comm_owned = true; ctx->comm_world = world; ctx->comm_rank = rank;
+  return comm_streams(ctx);
+}
+
+int32_t lisreg_comm_adopt(lisreg_ctx* ctx, void* nccl_comm, int32_t world, int32_t rank) {
+  if (!ctx || !nccl_comm || world < 1 || rank < 0 || rank >= world) return fail(ctx, LISREG_ERR_ARG, "lisreg_comm_adopt: bad argument");
+  std::string why;
+  if (!nccl_load(&why)) return fail(ctx, LISREG_ERR_CUDA, "lisreg_comm_adopt: %s", why.c_str());
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->comm) lisreg_comm_destroy(ctx);
+  ctx->comm = nccl_comm; ctx->comm_owned = false; ctx->comm_world = world; ctx->comm_rank = rank;
+  return comm_streams(ctx);
+}
+
+int32_t lisreg_comm_destroy(lisreg_ctx* ctx) {
+  if (!ctx) return LISREG_ERR_ARG;
+  if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
+  if (ctx->comm && ctx->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  ctx->comm = nullptr; ctx->comm_owned = false; ctx->comm_world = 1; ctx->comm_rank = 0; ctx->comm_pending = false;
+  if (ctx->comm_stream) { cudaStreamDestroy(ctx->comm_stream); ctx->comm_stream = nullptr; }
+  if (ctx->comm_fence) { cudaEventDestroy(ctx->comm_fence); ctx->comm_fence = nullptr; }
+  if (ctx->comm_done) { cudaEventDestroy(ctx->comm_done); ctx->comm_done = nullptr; }
+  return LISREG_OK;
+}
+
+int32_t lisreg_allgather_results(lisreg_ctx* ctx, const void* d_send, void* d_recv, uint64_t bytes_per_rank) {
+  if (!ctx || !d_send || !d_recv || bytes_per_rank == 0) return fail(ctx, LISREG_ERR_ARG, "lisreg_allgather_results: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->comm) {                                  // a single-process run: the gather is a copy
+    if (d_send != d_recv) CK(cudaMemcpyAsync(d_recv, d_send, (size_t)bytes_per_rank, cudaMemcpyDeviceToDevice, ctx->stream));
+    return LISREG_OK;
+  }
+  CK(cudaEventRecord(ctx->comm_fence, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->comm_fence, 0));
+  const int rc = g_nccl.AllGather(d_send, d_recv, (size_t)bytes_per_rank, /* ncclInt8 */ 0, ctx->comm, ctx->comm_stream);
+  if (rc != 0) return fail(ctx, LISREG_ERR_CUDA, "ncclAllGather failed: %s", nccl_err(rc));
+  CK(cudaEventRecord(ctx->comm_done, ctx->comm_stream));
+  ctx->comm_pending = true;
+  return LISREG_OK;
+}
+
+int32_t lisreg_allgather_wait(lisreg_ctx* ctx) {
+  if (!ctx) return LISREG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->comm_pending) { CK(cudaEventSynchronize(ctx->comm_done)); ctx->comm_pending = false; }
+  else CK(cudaStreamSynchronize(ctx->stream));
+  return LISREG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming odometry (device-resident sliding-window map)
+// ------------------------------------------------------------------------------------------------
+// Host-side pose arithmetic of updateInitialGuess / calculateTranslation (odomEstimationNode.cpp:284-391):
+// Eigen::Affine3f products and inverses in fp32.  Eigen's vectorised evaluation order is not pinnable; the natural
+// order is used (row times column, k ascending; cofactor inverse of the linear part) - mirrored by
+// lis_slam_b200/stream.py, which drives the CPU oracle through the same flow for the parity tests.
+static void odom_T16(const float pose[6], float T[16]) {       // pcl::getTransformation(x, y, z, roll, pitch, yaw)
+  RegState s; for (int i = 0; i < 6; i++) s.pose[i] = pose[i];
+  state_refresh(s);
+  for (int i = 0; i < 12; i++) T[i] = s.T[i];
+  T[12] = 0.f; T[13] = 0.f; T[14] = 0.f; T[15] = 1.f;
+}
+static inline float odom_cof(const float* T, int i, int j) {    // cofactor (i, j) of the 3x3 linear part of a row-major 4x4
+  const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+  return T[i1 * 4 + j1] * T[i2 * 4 + j2] - T[i1 * 4 + j2] * T[i2 * 4 + j1];
+}
+static void odom_inv(const float T[16], float R[16]) {          // Eigen::Affine3f::inverse(): linear^-1, -linear^-1 * t
+  const float c0 = odom_cof(T, 0, 0), c1 = odom_cof(T, 1, 0), c2 = odom_cof(T, 2, 0);
+  const float det = (c0 * T[0] + c1 * T[4]) + c2 * T[8];
+  const float invdet = 1.f / det;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R[i * 4 + j] = odom_cof(T, j, i) * invdet;
+  for (int i = 0; i < 3; i++) R[i * 4 + 3] = ((-R[i * 4 + 0]) * T[3] + (-R[i * 4 + 1]) * T[7]) + (-R[i * 4 + 2]) * T[11];
+  R[12] = 0.f; R[13] = 0.f; R[14] = 0.f; R[15] = 1.f;
+}
+static void odom_mul(const float A[16], const float B[16], float Cm[16]) {
+  float r[16];
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { float a = 0.f; for (int k = 0; k < 4; k++) a += A[i * 4 + k] * B[k * 4 + j]; r[i * 4 + j] = a; }
+  memcpy(Cm, r, sizeof(r));
+}
+static void odom_euler(const float T[16], float pose[6]) {      // pcl::getTranslationAndEulerAngles
+  pose[3] = T[3]; pose[4] = T[7]; pose[5] = T[11];
+  pose[0] = (float)atan2((double)T[9], (double)T[10]);
+  pose[1] = (float)asin((double)-T[8]);
+  pose[2] = (float)atan2((double)T[4], (double)T[0]);
+}
+
+void lisreg_odom_params_default(lisreg_odom_params* p) {
+  memset(p, 0, sizeof(*p));
+  lisreg_frame_params_default(&p->frame);
+  p->keyframe_min_distance = 1.4f; p->keyframe_min_yaw = 0.5f;   // config/params.yaml:140-141
+  p->window = 19;                                                 // odomEstimationNode.cpp:463
+  p->use_graph = 1;
+}
+
+int32_t lisreg_odom_create(lisreg_ctx* ctx, const lisreg_odom_params* prm, int32_t* odom_id) {
+  if (!ctx || !prm || !odom_id) return fail(ctx, LISREG_ERR_ARG, "lisreg_odom_create: bad argument");
+  const lisreg_feat_params& fp = prm->frame.feat;
+  if (fp.n_scan <= 0 || fp.horizon <= 0 || fp.horizon > 2048 || fp.n_scan * 6 > 1024 || fp.downsample_rate <= 0 ||
+      prm->window < 1 || prm->window + 1 > ODOM_MAX_SLOTS || !(prm->frame.corner_leaf > 0.f) || !(prm->frame.surf_leaf > 0.f) ||
+      prm->frame.lm.max_iters <= 0 || prm->frame.lm.max_iters > LISREG_MAX_ITERS)
+    return fail(ctx, LISREG_ERR_ARG, "lisreg_odom_create: unsupported parameters");
+  CK(cudaSetDevice(ctx->device));
+  int slot = -1;
+  for (size_t i = 0; i < ctx->odoms.size(); i++) if (!ctx->odoms[i].used) { slot = (int)i; break; }
+  if (slot < 0) { ctx->odoms.emplace_back(); slot = (int)ctx->odoms.size() - 1; }
+  lisreg_ctx::Odom& O = ctx->odoms[slot];
+  O = lisreg_ctx::Odom();
+  O.prm = *prm;
+  O.slots = prm->window + 1;
+  O.ccap = fp.n_scan * 120; O.scap = fp.n_scan * fp.horizon;
+  CK(cudaMalloc(&O.d_win_c, sizeof(float4) * (size_t)O.ccap * O.slots));
+  { cudaError_t e = cudaMalloc(&O.d_win_s, sizeof(float4) * (size_t)O.scap * O.slots);
+    if (e != cudaSuccess) { cudaFree(O.d_win_c); O.d_win_c = nullptr; return fail(ctx, LISREG_ERR_CUDA, "lisreg_odom_create: window allocation failed: %s", cudaGetErrorString(e)); } }
+  O.nc.assign(O.slots, 0); O.ns.assign(O.slots, 0);
+  O.used = true;
+  *odom_id = slot;
+  return LISREG_OK;
+}
+
+int32_t lisreg_odom_destroy(lisreg_ctx* ctx, int32_t odom_id) {
+  if (!ctx || odom_id < 0 || odom_id >= (int)ctx->odoms.size() || !ctx->odoms[odom_id].used) return fail(ctx, LISREG_ERR_ARG, "lisreg_odom_destroy: bad id");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  lisreg_ctx::Odom& O = ctx->odoms[odom_id];
+  if (O.gexec) cudaGraphExecDestroy(O.gexec);
+  if (O.map_id >= 0) lisreg_map_destroy(ctx, O.map_id);
+  cudaFree(O.d_win_c); cudaFree(O.d_win_s);
+  for (DevBuf* b : {&O.d_cat, &O.d_mapvox, &O.d_mapseg, &O.d_in, &O.d_io}) b->release();
+  O.h_io.release(); O.h_desc.release();
+  O = lisreg_ctx::Odom();
+  return LISREG_OK;
+}
+
+// updateInitialGuess, cloudInfo.odomAvailable == false branch (:298-313, :343-383)
+static void odom_update_initial_guess(lisreg_ctx::Odom& O, const float* init_pose6) {
+  if (!O.first_trans) {
+    for (int i = 0; i < 6; i++) O.pose[i] = init_pose6 ? init_pose6[i] : 0.f;
+    O.first_trans = true;
+    return;
+  }
+  if (!O.have_last) { memcpy(O.last_pose, O.pose, sizeof(O.pose)); O.have_last = true; return; }
+  float Tb[16], Tl[16], Tli[16], Ti[16], Tf[16];
+  odom_T16(O.pose, Tb); odom_T16(O.last_pose, Tl);
+  memcpy(O.last_pose, O.pose, sizeof(O.pose));
+  odom_inv(Tl, Tli); odom_mul(Tli, Tb, Ti);       // transIncre = transLast.inverse() * transBack
+  odom_mul(Tb, Ti, Tf);                           // transFinal = transTobe * transIncre
+  odom_euler(Tf, O.pose);
+}
+
+// saveKeyFrames (:421-478): the frame's full corner / surface clouds, moved by the refined pose, enter the window
+static int odom_save_keyframe(lisreg_ctx* ctx, lisreg_ctx::Odom& O, const FeatFrame& f, int n_corner, int n_surf) {
+  cudaStream_t st = ctx->cur->stream;
+  // a free slot: the ring holds window + 1 slots and at most `window` are live after the trim below
+  std::vector<char> live((size_t)O.slots, 0);
+  for (int s : O.order) live[s] = 1;
+  int slot = 0; while (slot < O.slots && live[slot]) slot++;
+  if (slot >= O.slots) return fail(ctx, LISREG_ERR_CAPACITY, "odom window ring is full");
+  float T[16]; odom_T16(O.pose, T);
+  OdomT12 t12; for (int i = 0; i < 12; i++) t12.m[i] = T[i];
+  const int nc = std::min(n_corner, O.ccap), ns = std::min(n_surf, O.scap);
+  if (nc > 0) { k_odom_append<<<std::min(296, (nc + 255) / 256), 256, 0, st>>>(f.ext_pts, f.corner_idx, f.counts + 0, t12, O.d_win_c + (size_t)slot * O.ccap, O.ccap); LAUNCH_CK(); }
+  if (ns > 0) { k_odom_append<<<std::min(592, (ns + 255) / 256), 256, 0, st>>>(f.ext_pts, f.surf_idx, f.counts + 3, t12, O.d_win_s + (size_t)slot * O.scap, O.scap); LAUNCH_CK(); }
+  O.nc[slot] = nc; O.ns[slot] = ns;
+  O.order.push_back(slot);
+  while ((int)O.order.size() >= O.prm.window + 1) O.order.erase(O.order.begin());
+  memcpy(O.key_pose, O.pose, sizeof(O.pose));
+  O.keyframe_id++;
+  O.map_dirty = true;
+  return LISREG_OK;
+}
+
+// map = window concatenated newest first (:190-193) -> VoxelGrid (:196-201) -> spatial index (:602-603)
+static int odom_rebuild_map(lisreg_ctx* ctx, lisreg_ctx::Odom& O) {
+  cudaStream_t st = ctx->cur->stream;
+  OdomConcat tc{}, ts{};
+  int total_c = 0, total_s = 0, k = 0, max_c = 0, max_s = 0;
+  for (int i = (int)O.order.size() - 1; i >= 0; i--, k++) {
+    const int s = O.order[i];
+    tc.src[k] = O.d_win_c + (size_t)s * O.ccap; tc.n[k] = O.nc[s]; tc.off[k] = total_c; total_c += O.nc[s]; max_c = std::max(max_c, O.nc[s]);
+    ts.src[k] = O.d_win_s + (size_t)s * O.scap; ts.n[k] = O.ns[s]; ts.off[k] = total_s; total_s += O.ns[s]; max_s = std::max(max_s, O.ns[s]);
+  }
+  tc.count = ts.count = k;
+  const size_t cat_c = (sizeof(float4) * (size_t)std::max(total_c, 1) + 255) & ~size_t(255);
+  CK(O.d_cat.reserve(cat_c + sizeof(float4) * (size_t)std::max(total_s, 1)));
+  float4* d_cc = (float4*)O.d_cat.p; float4* d_cs = (float4*)((char*)O.d_cat.p + cat_c);
+  if (total_c > 0) { k_odom_concat<<<dim3(std::max(1, std::min(64, (max_c + 255) / 256)), k), 256, 0, st>>>(tc, d_cc); LAUNCH_CK(); }
+  if (total_s > 0) { k_odom_concat<<<dim3(std::max(1, std::min(148, (max_s + 255) / 256)), k), 256, 0, st>>>(ts, d_cs); LAUNCH_CK(); }
+  const size_t vc_per = vox_seg_bytes(std::max(total_c, 1)), vs_per = vox_seg_bytes(std::max(total_s, 1));
+  CK(O.d_mapvox.reserve(vc_per + vs_per));
+  CK(O.d_mapseg.reserve(sizeof(VoxSeg) * 2));
+  VoxSeg seg[2];
+  memset(seg, 0, sizeof(seg));
+  vox_carve((char*)O.d_mapvox.p, std::max(total_c, 1), &seg[0]); vox_carve((char*)O.d_mapvox.p + vc_per, std::max(total_s, 1), &seg[1]);
+  seg[0].src = d_cc; seg[0].gather = nullptr; seg[0].n_ptr = nullptr; seg[0].n = total_c; seg[0].leaf = O.prm.frame.corner_leaf;
+  seg[1].src = d_cs; seg[1].gather = nullptr; seg[1].n_ptr = nullptr; seg[1].n = total_s; seg[1].leaf = O.prm.frame.surf_leaf;
+  CK(cudaMemcpyAsync(O.d_mapseg.p, seg, sizeof(seg), cudaMemcpyHostToDevice, st));   // pageable source: consumed on return
+  CK(cudaMemsetAsync(seg[0].out_n, 0, 4, st)); CK(cudaMemsetAsync(seg[1].out_n, 0, 4, st));
+  int rc = run_voxel(ctx, (VoxSeg*)O.d_mapseg.p, 2, std::max(std::max(total_c, total_s), 1), 32.0 * (total_c + total_s));
+  if (rc) return rc;
+  if (O.map_id < 0) { O.map_id = map_alloc_slot(ctx); ctx->maps[O.map_id] = MapSlot(); }
+  MapSlot& m = ctx->maps[O.map_id];
+  const float h = cell_size_for_gate(O.prm.frame.lm.sqdist_gate);
+  rc = build_cloud_index(ctx, seg[0].out, total_c, h, &m.corner, seg[0].out_n);
+  if (rc) return rc;
+  rc = build_cloud_index(ctx, seg[1].out, total_s, h, &m.surf, seg[1].out_n);
+  if (rc) return rc;
+  m.used = true;
+  ctx->maps_dirty = true;
+  O.n_map_c = m.corner.g.n; O.n_map_s = m.surf.g.n;
+  O.map_dirty = false;
+  return sync_maps(ctx);
+}
+
+// addresses a captured frame graph depends on: when one of them moves the graph is dropped and captured again
+static std::vector<const void*> odom_graph_key(lisreg_ctx* ctx, lisreg_ctx::Odom& O) {
+  WorkSet& w = *ctx->cur;
+  return {w.d_descs.p, w.d_states.p, w.d_partials.p, w.d_nbr.p, w.d_kstate.p, w.d_klist.p, w.d_geom.p, w.d_feat.p, w.d_feat_frames.p,
+          w.d_vox.p, w.d_vox_segs.p, ctx->d_maps, O.d_io.p, O.h_desc.p};
+}
+
+static int odom_push_impl(lisreg_ctx* ctx, int32_t odom_id, const float* pts, const uint16_t* ring, int32_t n, bool on_device,
+                          const float* init_pose6, float pose6[6], lisreg_odom_result* res) {
+  if (!ctx || odom_id < 0 || odom_id >= (int)ctx->odoms.size() || !ctx->odoms[odom_id].used || n < 0 || (n > 0 && (!pts || !ring)) || !pose6 || !res)
+    return fail(ctx, LISREG_ERR_ARG, "lisreg_odom_push: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  lisreg_ctx::Odom& O = ctx->odoms[odom_id];
+  cudaStream_t st = ctx->cur->stream;
+  const lisreg_feat_params& fp = O.prm.frame.feat;
+  const int cells = fp.n_scan * fp.horizon;
+  memset(res, 0, sizeof(*res));
+  // ---- the sweep ----
+  const float4* d_pts = (const float4*)pts; const uint16_t* d_ring = ring;
+  if (!on_device) {
+    const size_t bp = (sizeof(float4) * (size_t)n + 255) & ~size_t(255);
+    CK(O.d_in.reserve(bp + sizeof(uint16_t) * (size_t)n + 64));
+    if (n) {
+      CK(cudaMemcpyAsync(O.d_in.p, pts, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync((char*)O.d_in.p + bp, ring, sizeof(uint16_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    d_pts = (const float4*)O.d_in.p; d_ring = (const uint16_t*)((char*)O.d_in.p + bp);
+  }
+  odom_update_initial_guess(O, init_pose6);
+  O.frame_id++;
+  memcpy(res->guess, O.pose, sizeof(O.pose));
+  // io block: [pose6 in/out][lm result][4 feature counts], device + pinned mirror
+  const size_t o_res = 32, o_cnt = o_res + ((sizeof(lisreg_lm_result) + 15) & ~size_t(15)), io_bytes = o_cnt + 16;
+  CK(O.d_io.reserve(io_bytes)); CK(O.h_io.reserve(io_bytes));
+  CK(O.h_desc.reserve(frame_desc_bytes(1)));
+  char* dio = (char*)O.d_io.p; char* hio = (char*)O.h_io.p;
+  int rc = feat_reserve(ctx, 1, cells, fp.n_scan);
+  if (rc) return rc;
+  FeatFrame f{};
+  feat_carve((char*)ctx->cur->d_feat.p, cells, fp.n_scan, &f);        // frame 0 of the work set: where run_frames puts it
+  if (O.first_flag) {
+    // FirstFlag (:175-183): features and the first key frame only, no registration
+    f.pts = d_pts; f.ring = d_ring; f.n = n;
+    CK(cudaMemcpyAsync(ctx->cur->d_feat_frames.p, &f, sizeof(f), cudaMemcpyHostToDevice, st));   // pageable: consumed on return
+    rc = run_features(ctx, (FeatFrame*)ctx->cur->d_feat_frames.p, 1, &fp, n, 17.0 * n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(hio + o_cnt, f.counts, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int* cnt = (const int*)(hio + o_cnt);
+    rc = odom_save_keyframe(ctx, O, f, cnt[0], cnt[3]);
+    if (rc) return rc;
+    O.first_flag = false;
+    res->keyframe_saved = 1;
+  } else {
+    if (O.map_dirty) { rc = odom_rebuild_map(ctx, O); if (rc) return rc; res->map_rebuilt = 1; }
+    res->n_map_corner = O.n_map_c; res->n_map_surf = O.n_map_s;
+    memcpy(hio, O.pose, sizeof(O.pose));
+    CK(cudaMemcpyAsync(dio, hio, sizeof(O.pose), cudaMemcpyHostToDevice, st));
+    lisreg_frame_item it; it.pts = (const float*)d_pts; it.ring = d_ring; it.n = n; it.map_id = O.map_id;
+    const bool graph_ok = O.prm.use_graph && st != nullptr && !ctx->prof_on && n <= cells;
+    bool launched = false;
+    if (graph_ok && O.gexec && O.gkey == odom_graph_key(ctx, O)) {
+      // replay: the sweep (address, size) reaches the kernels through the frame descriptor, which the graph uploads from
+      // the pinned block - only that block's CONTENT changes; every address the graph itself holds is the captured one
+      FeatFrame* hf = (FeatFrame*)O.h_desc.p;
+      hf->pts = d_pts; hf->ring = d_ring; hf->n = n;
+      cudaError_t e = cudaGraphLaunch(O.gexec, st);
+      if (e != cudaSuccess) return fail(ctx, LISREG_ERR_CUDA, "cudaGraphLaunch failed: %s", cudaGetErrorString(e));
+      ctx->launches += O.graph_kernels;
+      launched = true;
+    }
+    if (!launched) {
+      if (O.gexec) { cudaGraphExecDestroy(O.gexec); O.gexec = nullptr; }
+      // capture needs every buffer at its final size: the first registered frame runs eagerly (sized for a full sweep),
+      // the graph is captured on a later frame once nothing would have to be allocated inside the capture
+      const bool sized = graph_ok && ctx->cur->feat_cap_frames >= 1 && O.gkey.size() && O.gkey == odom_graph_key(ctx, O);
+      if (sized) {
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int64_t l0 = ctx->launches;
+        rc = run_frames(ctx, 1, &it, nullptr, 0, (float*)dio, &O.prm.frame, (lisreg_lm_result*)(dio + o_res), (char*)O.h_desc.p, 0, cells);
+        cudaError_t e = cudaStreamEndCapture(st, &g);
+        O.graph_kernels = ctx->launches - l0;                              // kernels one replay launches
+        ctx->launches = l0;
+        if (rc != LISREG_OK || e != cudaSuccess || !g) {
+          if (g) cudaGraphDestroy(g);
+          cudaGetLastError();
+          O.prm.use_graph = 0;                                             // fall back to eager launches for good
+          if (rc == LISREG_OK) rc = run_frames(ctx, 1, &it, nullptr, 0, (float*)dio, &O.prm.frame, (lisreg_lm_result*)(dio + o_res), (char*)O.h_desc.p, 0, cells);
+          if (rc) return rc;
+        } else {
+          e = cudaGraphInstantiate(&O.gexec, g, 0);
+          cudaGraphDestroy(g);
+          if (e != cudaSuccess) { O.gexec = nullptr; return fail(ctx, LISREG_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+          e = cudaGraphLaunch(O.gexec, st);
+          if (e != cudaSuccess) return fail(ctx, LISREG_ERR_CUDA, "cudaGraphLaunch failed: %s", cudaGetErrorString(e));
+          ctx->launches += O.graph_kernels;
+        }
+      } else {
+        rc = run_frames(ctx, 1, &it, nullptr, 0, (float*)dio, &O.prm.frame, (lisreg_lm_result*)(dio + o_res), (char*)O.h_desc.p, 0, cells);
+        if (rc) return rc;
+        O.gkey = odom_graph_key(ctx, O);
+      }
+    }
+    CK(cudaMemcpyAsync(hio + o_res, dio + o_res, sizeof(lisreg_lm_result), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hio + o_cnt, f.counts, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const lisreg_lm_result* lr = (const lisreg_lm_result*)(hio + o_res);
+    const int* cnt = (const int*)(hio + o_cnt);
+    res->lm = *lr;
+    if (lr->status != LISREG_NOT_ENOUGH_FEATURES) {
+      memcpy(O.pose, lr->pose, sizeof(O.pose));
+      if (!(lr->deltaR == 100.f && lr->deltaT == 100.f)) { O.deltaR = lr->deltaR; O.deltaT = lr->deltaT; }   // members (:70-71) keep the last solved step
+    }
+    // key-frame rule (:216-229)
+    if ((double)O.deltaR < 0.005 || (double)O.deltaT < 0.05) {
+      float Tk[16], Tki[16], Tc[16], Ti[16], inc[6];
+      odom_T16(O.key_pose, Tk); odom_T16(O.pose, Tc);
+      odom_inv(Tk, Tki); odom_mul(Tki, Tc, Ti); odom_euler(Ti, inc);       // calculateTranslation (:284-295)
+      if (O.keyframe_id <= 5 || fabsf(inc[2]) >= O.prm.keyframe_min_yaw || fabsf(inc[3]) >= O.prm.keyframe_min_distance ||
+          fabsf(inc[4]) >= O.prm.keyframe_min_distance) {
+        rc = odom_save_keyframe(ctx, O, f, cnt[0], cnt[3]);
+        if (rc) return rc;
+        res->keyframe_saved = 1;
+      }
+    }
+  }
+  memcpy(pose6, O.pose, sizeof(O.pose));
+  res->frame_id = O.frame_id; res->keyframe_id = O.keyframe_id;
+  return res->lm.status > 0 ? res->lm.status : LISREG_OK;
+}
+
+int32_t lisreg_odom_push(lisreg_ctx* ctx, int32_t odom_id, const float* pts, const uint16_t* ring, int32_t n,
+                         const float* init_pose6, float pose6[6], lisreg_odom_result* res) {
+  return odom_push_impl(ctx, odom_id, pts, ring, n, false, init_pose6, pose6, res);
+}
+int32_t lisreg_odom_push_dev(lisreg_ctx* ctx, int32_t odom_id, const float* d_pts, const uint16_t* d_ring, int32_t n,
+                             const float* init_pose6, float pose6[6], lisreg_odom_result* res) {
+  return odom_push_impl(ctx, odom_id, d_pts, d_ring, n, true, init_pose6, pose6, res);
 }
 
 int32_t lisreg_scan2map(lisreg_ctx* ctx, int32_t map_id, const float* corner, const uint16_t* clabel, int32_t nc,

@@ -82,6 +82,16 @@ class FrameItem(C.Structure):
     _fields_ = [("pts", C.c_void_p), ("ring", C.c_void_p), ("n", C.c_int32), ("map_id", C.c_int32)]
 
 
+class OdomParams(C.Structure):
+    _fields_ = [("frame", FrameParams), ("keyframe_min_distance", C.c_float), ("keyframe_min_yaw", C.c_float),
+                ("window", C.c_int32), ("use_graph", C.c_int32)]
+
+
+class OdomResult(C.Structure):
+    _fields_ = [("lm", LmResult), ("frame_id", C.c_int32), ("keyframe_id", C.c_int32), ("keyframe_saved", C.c_int32),
+                ("map_rebuilt", C.c_int32), ("n_map_corner", C.c_int32), ("n_map_surf", C.c_int32), ("guess", C.c_float * 6)]
+
+
 class EpscCloud(C.Structure):
     _fields_ = [("corner", C.c_void_p), ("surf", C.c_void_p), ("sem", C.c_void_p), ("sem_label", C.c_void_p),
                 ("nc", C.c_int32), ("ns", C.c_int32), ("nsem", C.c_int32), ("reserved", C.c_int32)]
@@ -216,6 +226,15 @@ def lib():
         L.lisreg_loop_detect.argtypes = [vp, i32, fp, i32, fp, i32, fp, C.POINTER(C.c_uint16), i32, fp, C.POINTER(LoopResult)]
         L.lisreg_icp_verify_batch.restype = i32
         L.lisreg_icp_verify_batch.argtypes = [vp, i32, C.POINTER(IcpPair), C.POINTER(IcpParams), C.POINTER(IcpResult)]
+        L.lisreg_odom_params_default.argtypes = [C.POINTER(OdomParams)]
+        L.lisreg_odom_create.restype = i32
+        L.lisreg_odom_create.argtypes = [vp, C.POINTER(OdomParams), C.POINTER(i32)]
+        L.lisreg_odom_destroy.restype = i32
+        L.lisreg_odom_destroy.argtypes = [vp, i32]
+        L.lisreg_odom_push.restype = i32
+        L.lisreg_odom_push.argtypes = [vp, i32, vp, vp, i32, vp, fp, C.POINTER(OdomResult)]
+        L.lisreg_odom_push_dev.restype = i32
+        L.lisreg_odom_push_dev.argtypes = [vp, i32, vp, vp, i32, vp, fp, C.POINTER(OdomResult)]
         L.lisreg_selftest_smallmat.restype = i32
         L.lisreg_selftest_smallmat.argtypes = [vp, fp, fp, fp]
         L.lisreg_profile_enable.restype = i32
@@ -248,6 +267,17 @@ def frame_params(variant="A", **lm_kw):
     lib().lisreg_lm_params_preset(C.byref(p.lm), variant.encode())
     for k, v in lm_kw.items():
         setattr(p.lm, k, v)
+    return p
+
+
+def odom_params(variant="A", n_scan=64, use_graph=1, **lm_kw):
+    p = OdomParams()
+    lib().lisreg_odom_params_default(C.byref(p))
+    lib().lisreg_lm_params_preset(C.byref(p.frame.lm), variant.encode())
+    p.frame.feat.n_scan = n_scan
+    p.use_graph = use_graph
+    for k, v in lm_kw.items():
+        setattr(p.frame.lm, k, v)
     return p
 
 
@@ -433,6 +463,32 @@ class Engine:
 
     def frames_batch_dev(self, items, F, d_pose_ptr, params, d_res_ptr):
         return self._ck(lib().lisreg_frames_batch_dev(self._h, F, items, d_pose_ptr, C.byref(params), d_res_ptr))
+
+    # ---- streaming odometry (device-resident sliding-window map) ----
+    def odom_create(self, prm=None):
+        prm = prm or odom_params()
+        oid = C.c_int32(-1)
+        self._ck(lib().lisreg_odom_create(self._h, C.byref(prm), C.byref(oid)))
+        return oid.value
+
+    def odom_destroy(self, oid):
+        self._ck(lib().lisreg_odom_destroy(self._h, oid))
+
+    def odom_push(self, oid, pts, ring, init_pose=None):
+        """One sweep (host arrays) -> (pose6, OdomResult)."""
+        p = _f4(pts); g = _u16(ring)
+        pose = np.zeros(6, np.float32); res = OdomResult()
+        ip = None if init_pose is None else np.ascontiguousarray(init_pose, np.float32)
+        self.last_status = self._ck(lib().lisreg_odom_push(self._h, oid, p.ctypes.data, g.ctypes.data, len(p), _ptr(ip),
+                                                           pose.ctypes.data_as(C.POINTER(C.c_float)), C.byref(res)))
+        return pose, res
+
+    def odom_push_dev(self, oid, d_pts_ptr, d_ring_ptr, n, init_pose=None):
+        pose = np.zeros(6, np.float32); res = OdomResult()
+        ip = None if init_pose is None else np.ascontiguousarray(init_pose, np.float32)
+        self.last_status = self._ck(lib().lisreg_odom_push_dev(self._h, oid, d_pts_ptr, d_ring_ptr, n, _ptr(ip),
+                                                               pose.ctypes.data_as(C.POINTER(C.c_float)), C.byref(res)))
+        return pose, res
 
     def epsc_describe(self, clouds, using_map):
         """clouds: list of (corner (n,4), surf (n,4), sem (n,4), sem_label (n,)). Returns dict of (n,20,80) u8 arrays."""

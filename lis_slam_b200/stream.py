@@ -20,9 +20,64 @@ KEYFRAME_MIN_YAW = 0.5        # keyFrameMiniYaw
 WINDOW = 19                   # while (laserCloudSurfVec.size() >= 20) erase(begin)  (:463-467)
 
 
+f32 = np.float32
+
+
+def _T16(pose6):
+    """pcl::getTransformation in fp32 (same closed form as csrc/lm.cuh state_refresh / lisreg.cu odom_T16)."""
+    p = np.asarray(pose6, f32)
+    c = lambda a: f32(np.cos(np.float64(a)))
+    s_ = lambda a: f32(np.sin(np.float64(a)))
+    A, B, Cc, D, E, F = c(p[2]), s_(p[2]), c(p[1]), s_(p[1]), c(p[0]), s_(p[0])
+    DE, DF = f32(D * E), f32(D * F)
+    T = np.zeros((4, 4), f32)
+    T[0] = [f32(A * Cc), f32(f32(A * DF) - f32(B * E)), f32(f32(B * F) + f32(A * DE)), p[3]]
+    T[1] = [f32(B * Cc), f32(f32(A * E) + f32(B * DF)), f32(f32(B * DE) - f32(A * F)), p[4]]
+    T[2] = [f32(-D), f32(Cc * F), f32(Cc * E), p[5]]
+    T[3, 3] = 1
+    return T
+
+
+def _cof(T, i, j):
+    i1, i2, j1, j2 = (i + 1) % 3, (i + 2) % 3, (j + 1) % 3, (j + 2) % 3
+    return f32(f32(T[i1, j1] * T[i2, j2]) - f32(T[i1, j2] * T[i2, j1]))
+
+
+def _inv(T):
+    """Eigen::Affine3f::inverse(): cofactor inverse of the linear part, -linear^-1 * t (lisreg.cu odom_inv)."""
+    c0, c1, c2 = _cof(T, 0, 0), _cof(T, 1, 0), _cof(T, 2, 0)
+    det = f32(f32(f32(c0 * T[0, 0]) + f32(c1 * T[1, 0])) + f32(c2 * T[2, 0]))
+    invdet = f32(f32(1) / det)
+    R = np.zeros((4, 4), f32)
+    for i in range(3):
+        for j in range(3):
+            R[i, j] = f32(_cof(T, j, i) * invdet)
+    for i in range(3):
+        R[i, 3] = f32(f32(f32(f32(-R[i, 0]) * T[0, 3]) + f32(f32(-R[i, 1]) * T[1, 3])) + f32(f32(-R[i, 2]) * T[2, 3]))
+    R[3, 3] = 1
+    return R
+
+
+def _mul(A, B):
+    Cm = np.zeros((4, 4), f32)
+    for i in range(4):
+        for j in range(4):
+            a = f32(0)
+            for k in range(4):
+                a = f32(a + f32(A[i, k] * B[k, j]))
+            Cm[i, j] = a
+    return Cm
+
+
+def _euler(T):
+    """pcl::getTranslationAndEulerAngles -> [roll, pitch, yaw, x, y, z] fp32."""
+    return np.array([f32(np.arctan2(np.float64(T[2, 1]), np.float64(T[2, 2]))), f32(np.arcsin(np.float64(-T[2, 0]))),
+                     f32(np.arctan2(np.float64(T[1, 0]), np.float64(T[0, 0]))), T[0, 3], T[1, 3], T[2, 3]], f32)
+
+
 def transform_cloud(pts4, pose6):
     """common.cpp:113-150 transformPointCloud(cloudIn, PointTypePose*): q = R p + t in fp32, intensity kept."""
-    T = synth.pose_to_T(pose6).astype(np.float32)
+    T = _T16(pose6)
     out = np.array(pts4, dtype=np.float32, copy=True)
     x, y, z = pts4[:, 0], pts4[:, 1], pts4[:, 2]
     out[:, 0] = T[0, 0] * x + T[0, 1] * y + T[0, 2] * z + T[0, 3]
@@ -41,16 +96,23 @@ class OdometryStream:
         self.kf_corner, self.kf_surf = [], []
         self.keyframe_id = 0
         self.first = True
+        self.first_trans = False
+        self.deltaR, self.deltaT = f32(100), f32(100)     # members (:70-71): keep the last solved step across frames
         self.trajectory, self.results = [], []
 
-    def _update_initial_guess(self):
+    def _update_initial_guess(self, initial_pose):
+        """updateInitialGuess, cloudInfo.odomAvailable == false (:298-313, :343-383), Affine3f arithmetic in fp32."""
+        if not self.first_trans:
+            self.pose = np.zeros(6, f32) if initial_pose is None else np.asarray(initial_pose, f32).copy()
+            self.first_trans = True
+            return
         if self.last_pose is None:
             self.last_pose = self.pose.copy()
             return
-        T_back, T_last = synth.pose_to_T(self.pose), synth.pose_to_T(self.last_pose)
+        T_back, T_last = _T16(self.pose), _T16(self.last_pose)
         self.last_pose = self.pose.copy()
-        incre = np.linalg.inv(T_last) @ T_back
-        self.pose = synth.T_to_pose(T_back @ incre)
+        incre = _mul(_inv(T_last), T_back)
+        self.pose = _euler(_mul(T_back, incre))
 
     def _save_keyframe(self, corner_full, surf_full):
         self.kf_corner.append(transform_cloud(corner_full, self.pose))
@@ -62,9 +124,7 @@ class OdometryStream:
 
     def push(self, pts, ring, initial_pose=None):
         """One LiDAR frame.  Returns the pose estimate [roll, pitch, yaw, x, y, z]."""
-        if self.first and initial_pose is not None:
-            self.pose = np.asarray(initial_pose, np.float32).copy()
-        self._update_initial_guess()
+        self._update_initial_guess(initial_pose)
         f = self.be.extract_features(pts, ring, self.fprm) if self.fprm is not None else self.be.extract_features(pts, ring)
         ext = np.ascontiguousarray(pts[f["src_index"]], np.float32)
         corner_full = np.ascontiguousarray(ext[f["corner_idx"]]); surf_full = np.ascontiguousarray(ext[f["surf_idx"]])
@@ -80,9 +140,12 @@ class OdometryStream:
         surf = self.be.voxel_grid(surf_full, self.surf_leaf)
         pose, res = self.be.scan2map(mid, corner, surf, self.pose, self.prm)
         self.be.map_destroy(mid)
-        self.pose = np.asarray(pose, np.float32).copy()
-        if res.deltaR < 0.005 or res.deltaT < 0.05:
-            inc = synth.T_to_pose(np.linalg.inv(synth.pose_to_T(self.key_pose)) @ synth.pose_to_T(self.pose))
+        if res.status != 1:                                   # "Not enough features": pose left at the prediction (:623-625)
+            self.pose = np.asarray(pose, np.float32).copy()
+            if not (res.deltaR == 100.0 and res.deltaT == 100.0):
+                self.deltaR, self.deltaT = f32(res.deltaR), f32(res.deltaT)
+        if float(self.deltaR) < 0.005 or float(self.deltaT) < 0.05:
+            inc = _euler(_mul(_inv(_T16(self.key_pose)), _T16(self.pose)))     # calculateTranslation (:284-295)
             if self.keyframe_id <= 5 or abs(inc[2]) >= KEYFRAME_MIN_YAW or abs(inc[3]) >= KEYFRAME_MIN_DISTANCE or abs(inc[4]) >= KEYFRAME_MIN_DISTANCE:
                 self._save_keyframe(corner_full, surf_full)
         self.trajectory.append(self.pose.copy()); self.results.append(res)

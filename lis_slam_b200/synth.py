@@ -5,9 +5,32 @@ There is no dataset access in this environment, so every benchmark/test input is
 generated here from `numpy.random.default_rng(seed)`; identical bytes feed the CPU
 oracle and the GPU engine.  Shapes follow KITTI HDL-64 (64 x 1800, 10 Hz).
 """
+import ctypes as C
+import os
+import subprocess
+
 import numpy as np
 
 GROUND_Z = -1.73
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SYNTH_LIB = None
+
+
+def build_synth_lib(force=False):
+    """gcc -O2 -fopenmp -shared tools/synth_raycast.c -> libsynth.so (in-tree, next to liblisreg.so)."""
+    src = os.path.join(_HERE, "tools", "synth_raycast.c"); out = os.path.join(_HERE, "libsynth.so")
+    if force or not os.path.exists(out) or os.path.getmtime(src) > os.path.getmtime(out):
+        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off", "-o", out, src, "-lm"])
+    return out
+
+
+def _synth_lib():
+    global _SYNTH_LIB
+    if _SYNTH_LIB is None:
+        _SYNTH_LIB = C.CDLL(build_synth_lib())
+        _SYNTH_LIB.synth_raycast.restype = None
+    return _SYNTH_LIB
 
 
 def euler_to_R(roll, pitch, yaw):
@@ -138,7 +161,24 @@ class Scene:
                 best[hit] = t[ok]; lab[hit] = 18
         return best, lab
 
-    def scan(self, pose6, sensor="hdl64", seed=2000, noise=0.01, max_range=70.0):
+    def raycast_fast(self, origin, dirs):
+        """Same as raycast() through the C generator (tools/synth_raycast.c, libsynth.so): ~100x faster; used for the
+        long synthetic streams.  Ranges agree with raycast() to rounding (the pole test skips numpy's azimuth
+        pre-cull, which only removes rays that cannot hit)."""
+        lib = _synth_lib()
+        o = np.ascontiguousarray(origin, np.float64); d = np.ascontiguousarray(dirs, np.float64)
+        n = len(d)
+        rng_out = np.empty(n, np.float64); lab = np.empty(n, np.uint16)
+        boxes = np.ascontiguousarray(self.boxes, np.float64); bl = np.ascontiguousarray(self.box_labels, np.uint16)
+        poles = np.ascontiguousarray(self.poles, np.float64)
+        vp = C.c_void_p
+        lib.synth_raycast(o.ctypes.data_as(vp), d.ctypes.data_as(vp), C.c_int64(n), boxes.ctypes.data_as(vp), bl.ctypes.data_as(vp),
+                          C.c_int32(len(boxes)), poles.ctypes.data_as(vp), C.c_int32(len(poles)), C.c_double(self.pole_r),
+                          C.c_double(self.pole_h), C.c_double(GROUND_Z), C.c_double(self.extent), rng_out.ctypes.data_as(vp),
+                          lab.ctypes.data_as(vp))
+        return rng_out, lab
+
+    def scan(self, pose6, sensor="hdl64", seed=2000, noise=0.01, max_range=70.0, fast=False):
         """Raw sweep in firing order (column-major).  Returns dict with
         pts (N,4) f32 {x,y,z,intensity} in the SENSOR frame, ring u16, time f32, label u16."""
         if sensor == "hdl64":
@@ -155,7 +195,7 @@ class Scene:
         azg, elg = np.meshgrid(az, elev, indexing="ij")  # (H, n_ring): column-major firing order
         d_s = np.stack([np.cos(elg) * np.cos(azg), np.cos(elg) * np.sin(azg), np.sin(elg)], -1).reshape(-1, 3)
         T = pose_to_T(pose6)
-        rngs, lab = self.raycast(T[:3, 3], d_s @ T[:3, :3].T)
+        rngs, lab = (self.raycast_fast if fast else self.raycast)(T[:3, 3], d_s @ T[:3, :3].T)
         rngs = rngs + rng.normal(0.0, noise, rngs.shape)
         keep = np.isfinite(rngs) & (rngs < max_range) & (rngs > 1.0)
         ring = np.tile(np.arange(n_ring, dtype=np.uint16), H)

@@ -35,17 +35,19 @@ def test_struct_layouts_match_header():
     #include <stdio.h>
     #include "lisreg.h"
     int main(void) {
-      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(lisreg_config), sizeof(lisreg_lm_params), sizeof(lisreg_lm_iter),
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(lisreg_config), sizeof(lisreg_lm_params), sizeof(lisreg_lm_iter),
              sizeof(lisreg_lm_result), sizeof(lisreg_batch_item), sizeof(lisreg_feat_params), sizeof(lisreg_feat_out),
              sizeof(lisreg_frame_params), sizeof(lisreg_frame_item), sizeof(lisreg_epsc_cloud), sizeof(lisreg_profile),
-             sizeof(lisreg_icp_params), sizeof(lisreg_icp_pair), sizeof(lisreg_icp_result));
+             sizeof(lisreg_icp_params), sizeof(lisreg_icp_pair), sizeof(lisreg_icp_result), sizeof(lisreg_odom_params),
+             sizeof(lisreg_odom_result), sizeof(lisreg_loop_params), sizeof(lisreg_loop_result), sizeof(lisreg_deskew));
       return 0;
     }'''
     exe = "/tmp/lisreg_sizes"
     subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=prog.encode(), check=True)
     sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     mirrors = [E.Config, E.LmParams, E.LmIter, E.LmResult, E.BatchItem, E.FeatParams, E.FeatOut, E.FrameParams, E.FrameItem,
-               E.EpscCloud, E.Profile, E.IcpParams, E.IcpPair, E.IcpResult]
+               E.EpscCloud, E.Profile, E.IcpParams, E.IcpPair, E.IcpResult, E.OdomParams, E.OdomResult, E.LoopParams, E.LoopResult,
+               E.Deskew]
     assert sizes == [C.sizeof(m) for m in mirrors]
 
 

@@ -54,3 +54,67 @@ def test_vlp16_stream_matches_oracle(engine):
     er, et = synth.pose_error(truth[-1], sg.trajectory[-1])
     assert et < 0.3 and er < 0.03, (er, et)
     assert all((a is None) == (b is None) and (a is None or a.iters == b.iters) for a, b in zip(sg.results, so.results))
+
+
+def _stream_traj(t, x0=-30.0):
+    """8 m/s along x with a yaw wobble."""
+    return np.array([0.0, 0.0, 0.02 * np.sin(0.05 * t), x0 + 0.8 * t, 0.3 * np.sin(0.02 * t), 0.0], np.float32)
+
+
+def _run_device_vs_oracle_flow(eng, sensor, n_scan, n_frames, use_graph):
+    """lisreg_odom_push (device-resident window, C-ABI) against stream.OdometryStream driving the CPU oracle."""
+    sc = scene()
+    oid = eng.odom_create(E.odom_params("A", n_scan=n_scan, use_graph=use_graph))
+    so = stream.OdometryStream(OracleBackend(), orc.lm_params("A"), orc.feat_params(n_scan=n_scan))
+    worst = (0.0, 0.0)
+    n_kf_saved = 0
+    for t in range(n_frames):
+        sw = sc.scan(_stream_traj(t), sensor=sensor, seed=7000 + t, fast=True)
+        pg, rg = eng.odom_push(oid, sw["pts"], sw["ring"], init_pose=_stream_traj(0))
+        po = so.push(sw["pts"], sw["ring"], initial_pose=_stream_traj(0))
+        er, et = synth.pose_error(po, pg)
+        assert er <= 1e-4 and et <= 1e-3, (t, er, et)
+        worst = (max(worst[0], er), max(worst[1], et))
+        ro = so.results[-1]
+        assert rg.keyframe_id == so.keyframe_id, (t, rg.keyframe_id, so.keyframe_id)
+        if ro is not None:
+            assert rg.lm.iters == ro.iters and rg.lm.status == ro.status, (t, rg.lm.iters, ro.iters)
+        n_kf_saved += rg.keyframe_saved
+    er, et = synth.pose_error(_stream_traj(n_frames - 1), pg)
+    eng.odom_destroy(oid)
+    assert n_kf_saved == so.keyframe_id >= 4
+    return worst, (er, et)
+
+
+@pytest.mark.parametrize("use_graph", [0, 1])
+def test_odom_device_window_vlp16_matches_oracle_flow(use_graph):
+    eng = E.Engine(device=0, own_stream=True)      # a non-default stream: the per-frame CUDA graph needs one
+    worst, drift = _run_device_vs_oracle_flow(eng, "vlp16", 16, 14, use_graph)
+    eng.close()
+    assert drift[1] < 0.3 and drift[0] < 0.03
+
+
+def test_odom_device_window_hdl64_64_frames_matches_oracle_flow():
+    """BASELINE configs[1] shape: 64 HDL-64 frames (64 x 1800) through the device-resident sliding-window flow; every
+    frame's pose within 1e-4 rad / 1e-3 m of the CPU oracle flow on identical input, same key-frame decisions and
+    iteration counts.  The window fills up (>= 20 key frames would need more frames; 64 frames save ~35)."""
+    eng = E.Engine(device=0, own_stream=True)
+    worst, drift = _run_device_vs_oracle_flow(eng, "hdl64", 64, 64, 1)
+    eng.close()
+    assert drift[1] < 0.1 and drift[0] < 0.01
+
+
+def test_odom_graph_replay_is_bit_identical_to_eager_launches():
+    sc = scene()
+    out = []
+    for use_graph in (0, 1):
+        eng = E.Engine(device=0, own_stream=True)
+        oid = eng.odom_create(E.odom_params("A", n_scan=16, use_graph=use_graph))
+        poses = []
+        for t in range(10):
+            sw = sc.scan(_stream_traj(t), sensor="vlp16", seed=7000 + t, fast=True)
+            p, r = eng.odom_push(oid, sw["pts"], sw["ring"], init_pose=_stream_traj(0))
+            poses.append(p.tobytes() + bytes([r.lm.iters, r.keyframe_saved]))
+        out.append(poses)
+        eng.odom_destroy(oid); eng.close()
+    assert out[0] == out[1]
