@@ -174,11 +174,33 @@ int32_t lisreg_scan2map_batch_arena(lisreg_ctx* ctx, int32_t B, const lisreg_bat
  * caller-allocated and optional (NULL = not wanted); capacities: src_index/col_ind/range/surf_idx/
  * curvature/label n_scan*horizon, start_ring/end_ring n_scan, corner_idx n_scan*120, sharp_idx n_scan*24,
  * flat_idx n_scan*60. */
+/* Memory layout of a raw sweep, sensor_msgs/PointCloud2 style (SURVEY.md 8f "next" #4, rows T1 / T3): the engine reads
+ * the caller's records in place - the 32-byte PCL PointXYZIRT records of cloud_info.cloud_deskewed (common.h:12-23:
+ * x 0, y 4, z 8, intensity 16, ring 20 (uint16), time 24; laserProcessing.cpp:729-747), a bare xyz stream, ... - so no
+ * adapter has to repack them.  point_step == 0 (the zero-initialised default) = packed float4 {x, y, z, intensity}
+ * records (16 B) with the ring ids in the separate uint16 array of the call.
+ * off_ring: >= 0 byte offset of a uint16 ring field inside the record; -1 separate ring array; -2 no ring input:
+ * scanID is synthesised from the elevation angle exactly as laserPretreatmentNode.cpp:95-126 does for N_SCAN 16 / 32 /
+ * 64 (points it would drop are dropped).  Offsets and point_step must be multiples of 4 (ring: of 2). */
+typedef struct lisreg_cloud_layout {
+  int32_t point_step;
+  int32_t off_x, off_y, off_z;
+  int32_t off_intensity;                      /* < 0: absent (intensity = 0) */
+  int32_t off_ring;
+  int32_t off_time;                           /* >= 0: float32 time field (de-skew entry point); < 0: separate array / absent */
+  int32_t reserved;
+} lisreg_cloud_layout;
+
 typedef struct lisreg_feat_params {
   int32_t n_scan, horizon, downsample_rate;   /* N_SCAN 64, Horizon_SCAN 1800, downsampleRate */
   float min_range, max_range;                 /* lidarMinRange, lidarMaxRange */
   float edge_thr, surf_thr;                   /* edgeThreshold 1.0, surfThreshold 0.1 */
+  int32_t reserved;
+  lisreg_cloud_layout layout;                 /* how `pts` is laid out (all-zero = packed float4 + ring array) */
 } lisreg_feat_params;
+/* presets: 0 packed float4 + ring array (16 + 2 B), 1 xyz float3 + ring array (12 + 2 B), 2 PCL PointXYZIRT records
+ * (32 B, ring and time inside), 3 xyz float3 only, ring synthesised (12 B) */
+void lisreg_cloud_layout_preset(lisreg_cloud_layout* l, int32_t which);
 
 typedef struct lisreg_feat_out {
   int32_t n_extracted, n_corner, n_sharp, n_flat, n_surf;
@@ -396,6 +418,11 @@ int32_t lisreg_allgather_wait(lisreg_ctx* ctx);
  * out98 = E[6], V[36] (eigenvectors in rows), X[6] (QR solve of A x = b), ok, Ainv[36] (LU), ok,
  * then W3[3], V3[9] of the register-only 3x3 Jacobi applied to the leading 3x3 block of A */
 int32_t lisreg_selftest_smallmat(lisreg_ctx* ctx, const float* A36, const float* b6, float* out98);
+
+/* integer-ALU roofline of lisreg_epsc_score_* (the all-pairs SAD is bound by VABSDIFF4 + funnel-shift
+ * issue, not by HBM): measured rate of the kernel's inner-loop instruction mix on registers only, in 1e9 VABSDIFF4
+ * instructions per second (one instruction = 4 byte abs-diff-accumulates). */
+int32_t lisreg_selftest_alu_peak(lisreg_ctx* ctx, double* gsad_per_s);
 
 /* ---- profiling (CUDA events on the context stream around the dominant kernels) ---- */
 typedef struct lisreg_profile {

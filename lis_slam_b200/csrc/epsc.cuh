@@ -96,9 +96,18 @@ constexpr int EPSC_STRIDE_W = 401;   // words per descriptor in smem (+1 pad => 
 
 // Query rows are q = q_begin + r * q_stride for local rows r in [0, n_rows): the whole matrix is (0, 1, N); a rank
 // of a multi-GPU run owns the cyclic rows (rank, world, ...) (triangular load => cyclic assignment).
-// sad_out[r * N + j] = min over shifts of the SAD (int32), shift_out = winning i in [-10, 10)
+//
+// The per-query top-k is FUSED into the scoring kernel: a pair whose best SAD passes the reference gate
+// (score > 0.75 <=> SAD < 102000, rare) is pushed into the 8-slot sorted list of its query row with an atomicMin
+// cascade on 64-bit keys (slot k keeps the smaller of (resident, incoming) and hands the larger one to slot k + 1).
+// min / max conserve the multiset, so whatever the arrival order the 8 slots end up holding the 8 smallest keys in
+// ascending order - deterministic - and the N x N SAD / shift matrices (125 MB at N = 5000) never exist.
+// key = SAD (< 2^17) << 40 | history index j (< 2^24) << 8 | shift + 10: ordered by (SAD, j) like the reference loop
+// (first best candidate wins), the shift rides along.
+constexpr int EPSC_TOPK_SLOTS = 8;
+constexpr unsigned EPSC_SAD_GATE = 102000u;     // 1 - SAD / (80 * 20 * 255) > DISTANCE_THRESHOLD 0.75
 __global__ void __launch_bounds__(EPSC_THREADS)
-k_epsc_score(const uint8_t* __restrict__ desc, int N, int q_begin, int q_stride, int n_rows, int* __restrict__ sad_out, int8_t* __restrict__ shift_out) {
+k_epsc_score(const uint8_t* __restrict__ desc, int N, int q_begin, int q_stride, int n_rows, unsigned long long* __restrict__ row_top) {
   const int r0 = blockIdx.y * EPSC_QT, j0 = blockIdx.x * EPSC_JT;
   const int r_last = min(r0 + EPSC_QT, n_rows) - 1;
   if (r_last < r0 || j0 >= q_begin + r_last * q_stride) return;   // whole tile on/above the diagonal (needs j < q): nothing to do
@@ -155,47 +164,49 @@ k_epsc_score(const uint8_t* __restrict__ desc, int N, int q_begin, int q_stride,
   unsigned best = sad[0]; int bs = 0;
 #pragma unroll
   for (int s = 1; s < 20; s++) if (sad[s] < best) { best = sad[s]; bs = s; }
-  sad_out[(size_t)r * N + j] = (int)best;
-  shift_out[(size_t)r * N + j] = (int8_t)(bs - 10);
+  if (best < EPSC_SAD_GATE) {
+    unsigned long long key = ((unsigned long long)best << 40) | ((unsigned long long)(unsigned)j << 8) | (unsigned long long)(unsigned)bs;
+    unsigned long long* top = row_top + (size_t)r * EPSC_TOPK_SLOTS;
+#pragma unroll 1
+    for (int k = 0; k < EPSC_TOPK_SLOTS; k++) {
+      const unsigned long long old = atomicMin(&top[k], key);
+      key = old > key ? old : key;                 // the larger one moves on
+      if (key == ~0ull) break;                      // displaced an empty slot: done
+    }
+  }
 }
 
-// per-query top-k among history j < q with score > 0.75 (<=> SAD < 102000): one warp per (local) query row
-__global__ void k_epsc_topk(const int* __restrict__ sad, const int8_t* __restrict__ shiftm, int N, int q_begin, int q_stride, int n_rows, int topk,
+// row_top -> the interface arrays: per query the topk (<= 8) best candidates, best first (idx -1 when fewer qualify)
+__global__ void k_epsc_topk(const unsigned long long* __restrict__ row_top, int n_rows, int topk,
                             int* __restrict__ idx, float* __restrict__ score, int8_t* __restrict__ shift) {
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (r >= n_rows) return;
-  const int q = q_begin + r * q_stride;
-  // each lane keeps its own sorted top-k (k <= 8) of keys (sad << 32 | j), then a warp merge by repeated min
-  unsigned long long best[8];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_rows * topk) return;
+  const int r = t / topk, k = t % topk;
+  const unsigned long long key = row_top[(size_t)r * EPSC_TOPK_SLOTS + k];
+  if (key != ~0ull) {
+    const int s = (int)(key >> 40), j = (int)((key >> 8) & 0xffffffull), bs = (int)(key & 0xffull);
+    idx[t] = j; score[t] = (float)(1.0 - (double)s / (80 * 20 * 255)); shift[t] = (int8_t)(bs - 10);
+  } else { idx[t] = -1; score[t] = 0.f; shift[t] = 0; }
+}
+
+// integer-ALU roofline of the pair scoring: a register-only chain of the kernel's inner-loop mix
+// (one funnel shift + one VABSDIFF4.ACC per 4 byte-pairs) with no memory traffic; out[blockIdx] keeps the result live.
+// grid = SMs * 8, block = 256; every thread issues iters * 64 SAD instructions on 8 independent accumulators.
+__global__ void __launch_bounds__(256)
+k_epsc_alu_peak(unsigned* __restrict__ out, int iters, unsigned seed) {
+  unsigned a0 = seed + threadIdx.x, a1 = a0 * 3u, a2 = a0 * 5u, a3 = a0 * 7u, x0 = a0 ^ 0x9e3779b9u, x1 = a1 ^ 0x7f4a7c15u;
+  unsigned s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
 #pragma unroll
-  for (int k = 0; k < 8; k++) best[k] = ~0ull;
-  for (int j = lane; j < q; j += 32) {
-    const int s = sad[(size_t)r * N + j];
-    if (s >= 102000) continue;
-    unsigned long long key = ((unsigned long long)(unsigned)s << 32) | (unsigned)j;
-#pragma unroll
-    for (int k = 0; k < 8; k++) { const bool lt = best[k] < key; const unsigned long long lo = lt ? best[k] : key; key = lt ? key : best[k]; best[k] = lo; }
-  }
-  for (int k = 0; k < topk; k++) {
-    // warp-wide minimum of the lanes' current heads
-    unsigned long long h = best[0];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, h, o); h = t < h ? t : h; }
-    if (best[0] == h && h != ~0ull) {   // the owning lane pops it (keys are unique: j is unique)
-#pragma unroll
-      for (int t = 0; t < 7; t++) best[t] = best[t + 1];
-      best[7] = ~0ull;
-    }
-    if (lane == 0) {
-      if (h != ~0ull) {
-        const int j = (int)(unsigned)(h & 0xffffffffull), s = (int)(unsigned)(h >> 32);
-        idx[(size_t)r * topk + k] = j;
-        score[(size_t)r * topk + k] = (float)(1.0 - (double)s / (80 * 20 * 255));
-        shift[(size_t)r * topk + k] = shiftm[(size_t)r * N + j];
-      } else { idx[(size_t)r * topk + k] = -1; score[(size_t)r * topk + k] = 0.f; shift[(size_t)r * topk + k] = 0; }
+    for (int u = 0; u < 8; u++) {
+      const unsigned y0 = __funnelshift_r(x0, x1, 8), y1 = __funnelshift_r(x1, x0, 16);
+      s0 = __vsadu4(a0, y0) + s0; s1 = __vsadu4(a1, y1) + s1; s2 = __vsadu4(a2, y0) + s2; s3 = __vsadu4(a3, y1) + s3;
+      s4 = __vsadu4(a0, y1) + s4; s5 = __vsadu4(a1, y0) + s5; s6 = __vsadu4(a2, y1) + s6; s7 = __vsadu4(a3, y0) + s7;
+      x0 += s0; x1 ^= s4;
     }
   }
+  if (((s0 ^ s1) + (s2 ^ s3) + (s4 ^ s5) + (s6 ^ s7)) == 0x12345u) out[blockIdx.x] = x0;   // practically never: keeps the chain alive
 }
 
 }  // namespace lisreg

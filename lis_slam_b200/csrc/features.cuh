@@ -23,6 +23,7 @@ namespace lisreg {
 struct FeatParamsDev {
   int n_scan, horizon, downsample;
   float min_range, max_range, edge_thr, surf_thr;
+  lisreg_cloud_layout lay;     // point_step == 0: packed float4 records + ring array
 };
 
 // Per-frame views into the batch work buffers (all device pointers).
@@ -51,6 +52,44 @@ struct FeatFrame {
 };
 
 __device__ __forceinline__ float atan2f_cr(float y, float x) { return (float)atan2((double)y, (double)x); }
+
+// raw point i of a sweep in the caller's layout (lisreg_cloud_layout): {x, y, z, intensity}
+__device__ __forceinline__ float4 feat_load_point(const float4* __restrict__ pts, const lisreg_cloud_layout& lay, int i) {
+  if (lay.point_step == 0) return __ldg(&pts[i]);
+  const char* r = reinterpret_cast<const char*>(pts) + (size_t)i * (size_t)lay.point_step;
+  float4 p;
+  p.x = __ldg(reinterpret_cast<const float*>(r + lay.off_x));
+  p.y = __ldg(reinterpret_cast<const float*>(r + lay.off_y));
+  p.z = __ldg(reinterpret_cast<const float*>(r + lay.off_z));
+  p.w = lay.off_intensity >= 0 ? __ldg(reinterpret_cast<const float*>(r + lay.off_intensity)) : 0.f;
+  return p;
+}
+__device__ __forceinline__ float feat_load_time(const float4* __restrict__ pts, const float* __restrict__ time, const lisreg_cloud_layout& lay, int i) {
+  if (lay.point_step != 0 && lay.off_time >= 0)
+    return __ldg(reinterpret_cast<const float*>(reinterpret_cast<const char*>(pts) + (size_t)i * (size_t)lay.point_step + lay.off_time));
+  return time[i];
+}
+// scanID from the elevation angle (laserPretreatmentNode.cpp:95-126); -1 = the reference drops the point
+__device__ __forceinline__ int feat_synth_ring(float4 p, int n_scan) {
+  const float angle = (float)((double)(float)atan((double)(p.z / sqrtf(p.x * p.x + p.y * p.y))) * 180 / 3.14159265358979323846);
+  int id;
+  if (n_scan == 16) id = (int)((double)((angle + 15) / 2) + 0.5);
+  else if (n_scan == 32) id = (int)(((double)angle + 92.0 / 3.0) * 3.0 / 4.0);
+  else if (n_scan == 64) {
+    if ((double)angle >= -8.83) id = (int)((double)(2 - angle) * 3.0 + 0.5);
+    else id = n_scan / 2 + (int)((-8.83 - (double)angle) * 2.0 + 0.5);
+    if ((double)angle > 2 || (double)angle < -24.33 || id > 50 || id < 0) return -1;
+    return id;
+  } else return -1;
+  if (id > n_scan - 1 || id < 0) return -1;
+  return id;
+}
+__device__ __forceinline__ int feat_load_ring(const float4* __restrict__ pts, const uint16_t* __restrict__ ring, const lisreg_cloud_layout& lay,
+                                              int n_scan, int i, float4 p) {
+  if (lay.point_step == 0 || lay.off_ring == -1) return (int)ring[i];
+  if (lay.off_ring >= 0) return (int)__ldg(reinterpret_cast<const unsigned short*>(reinterpret_cast<const char*>(pts) + (size_t)i * (size_t)lay.point_step + lay.off_ring));
+  return feat_synth_ring(p, n_scan);
+}
 
 __global__ void k_feat_clear(FeatFrame* frames, FeatParamsDev prm) {
   const FeatFrame f = frames[blockIdx.y];
@@ -91,7 +130,8 @@ __global__ void k_feat_project(FeatFrame* frames, FeatParamsDev prm) {
   const FeatFrame f = frames[blockIdx.y];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < f.n; i += gridDim.x * blockDim.x) {
     float r; int cell;
-    if (feat_project(prm, __ldg(&f.pts[i]), (int)f.ring[i], r, cell)) atomicMin(&f.owner[cell], i);
+    const float4 p = feat_load_point(f.pts, prm.lay, i);
+    if (feat_project(prm, p, feat_load_ring(f.pts, f.ring, prm.lay, prm.n_scan, i, p), r, cell)) atomicMin(&f.owner[cell], i);
   }
 }
 
@@ -139,7 +179,7 @@ __global__ void k_feat_deskew_start(FeatFrame* frames, FeatParamsDev prm) {
     float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
     if (m != 0x7fffffff) {
       float r[3];
-      feat_find_rotation(f, f.t_scan + (double)f.time[m], r);
+      feat_find_rotation(f, f.t_scan + (double)feat_load_time(f.pts, f.time, prm.lay, m), r);
       feat_rot_of(r[0], r[1], r[2], R);
     }
     // Eigen::Affine3f::inverse(): cofactor inverse of the linear part
@@ -149,9 +189,9 @@ __global__ void k_feat_deskew_start(FeatFrame* frames, FeatParamsDev prm) {
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) f.start_inv[i * 3 + j] = feat_cof(R, j, i) * invdet;
   }
 }
-__device__ __forceinline__ float4 feat_deskew_point(const FeatFrame& f, const float* Sinv, float4 p, int src) {
+__device__ __forceinline__ float4 feat_deskew_point(const FeatFrame& f, const float* Sinv, float4 p, float t_rel) {
   float r[3], Rc[9], Bt[9];
-  feat_find_rotation(f, f.t_scan + (double)f.time[src], r);
+  feat_find_rotation(f, f.t_scan + (double)t_rel, r);
   feat_rot_of(r[0], r[1], r[2], Rc);
 #pragma unroll
   for (int a = 0; a < 3; a++)
@@ -213,9 +253,9 @@ __global__ void k_feat_compact(FeatFrame* frames, FeatParamsDev prm) {
     const unsigned m = __ballot_sync(0xffffffffu, v);
     if (v) {
       const int pos = s_base + s_chunk[ch] + __popc(m & ((1u << lane) - 1u));
-      const float4 p = __ldg(&f.pts[own]);
+      const float4 p = feat_load_point(f.pts, prm.lay, own);
       // range (and the column) come from the ORIGINAL point; only the stored coordinates are de-skewed (:489-507)
-      f.ext_pts[pos] = (DESKEW && f.n_imu > 0) ? feat_deskew_point(f, f.start_inv, p, own) : p;
+      f.ext_pts[pos] = (DESKEW && f.n_imu > 0) ? feat_deskew_point(f, f.start_inv, p, feat_load_time(f.pts, f.time, prm.lay, own)) : p;
       f.ext_src[pos] = own;
       f.col[pos] = (unsigned short)j;
       f.range[pos] = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);

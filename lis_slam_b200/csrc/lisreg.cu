@@ -315,6 +315,7 @@ __global__ void k_cell_order(float4* __restrict__ sorted, const uint32_t* __rest
 // when large enough (in-place rebuild).
 static int build_cloud_index(lisreg_ctx* ctx, const float4* d_pts, int n, float h_req, CloudIndex* ci, const int* d_n = nullptr) {
   cudaStream_t st = ctx->cur->stream;
+  ProfScope ps(ctx, PROF_INDEX, 16.0 * n, 1);
   CK(ctx->d_bbox.reserve(6 * sizeof(unsigned) + sizeof(GridDev)));
   unsigned* bb = (unsigned*)ctx->d_bbox.p;
   GridDev* d_g = (GridDev*)((char*)ctx->d_bbox.p + 32);
@@ -789,7 +790,34 @@ int32_t lisreg_scan2map_batch_arena(lisreg_ctx* ctx, int32_t B, const lisreg_bat
 // ------------------------------------------------------------------------------------------------
 // feature extraction
 // ------------------------------------------------------------------------------------------------
+void lisreg_cloud_layout_preset(lisreg_cloud_layout* l, int32_t which) {
+  memset(l, 0, sizeof(*l));
+  l->off_intensity = -1; l->off_ring = -1; l->off_time = -1;
+  switch (which) {
+    case 1: l->point_step = 12; l->off_x = 0; l->off_y = 4; l->off_z = 8; break;                                   // xyz + ring array
+    case 2: l->point_step = 32; l->off_x = 0; l->off_y = 4; l->off_z = 8; l->off_intensity = 16; l->off_ring = 20; l->off_time = 24; break;   // PointXYZIRT
+    case 3: l->point_step = 12; l->off_x = 0; l->off_y = 4; l->off_z = 8; l->off_ring = -2; break;                  // xyz only, ring synthesised
+    default: memset(l, 0, sizeof(*l)); break;                                                                       // packed float4 + ring array
+  }
+}
+
+// bytes per record and validity of a layout
+static inline int layout_step(const lisreg_cloud_layout& l) { return l.point_step == 0 ? 16 : l.point_step; }
+static bool layout_ok(const lisreg_cloud_layout& l, int n_scan) {
+  if (l.point_step == 0) return true;
+  if (l.point_step < 12 || (l.point_step & 3)) return false;
+  for (int o : {l.off_x, l.off_y, l.off_z}) if (o < 0 || (o & 3) || o + 4 > l.point_step) return false;
+  if (l.off_intensity >= 0 && ((l.off_intensity & 3) || l.off_intensity + 4 > l.point_step)) return false;
+  if (l.off_ring >= 0 && ((l.off_ring & 1) || l.off_ring + 2 > l.point_step)) return false;
+  if (l.off_ring < -2) return false;
+  if (l.off_ring == -2 && !(n_scan == 16 || n_scan == 32 || n_scan == 64)) return false;   // the formulas upstream knows
+  if (l.off_time >= 0 && ((l.off_time & 3) || l.off_time + 4 > l.point_step)) return false;
+  return true;
+}
+static inline bool layout_needs_ring_array(const lisreg_cloud_layout& l) { return l.point_step == 0 || l.off_ring == -1; }
+
 void lisreg_feat_params_default(lisreg_feat_params* p) {
+  memset(p, 0, sizeof(*p));
   p->n_scan = 64; p->horizon = 1800; p->downsample_rate = 1;   // benchmark pins downsampleRate = 1
   p->min_range = 0.0f; p->max_range = 70.0f;                    // config/params.yaml:73-74
   p->edge_thr = 1.0f; p->surf_thr = 0.1f;                       // config/params.yaml:117-118
@@ -835,7 +863,7 @@ static int feat_reserve(lisreg_ctx* ctx, int F, int cells, int nscan) {
 static int run_features(lisreg_ctx* ctx, FeatFrame* d_frames, int F, const lisreg_feat_params* prm, int max_n, double alg_bytes,
                         bool with_deskew = false) {
   cudaStream_t st = ctx->cur->stream;
-  FeatParamsDev dp{prm->n_scan, prm->horizon, prm->downsample_rate, prm->min_range, prm->max_range, prm->edge_thr, prm->surf_thr};
+  FeatParamsDev dp{prm->n_scan, prm->horizon, prm->downsample_rate, prm->min_range, prm->max_range, prm->edge_thr, prm->surf_thr, prm->layout};
   const int cells = prm->n_scan * prm->horizon;
   ProfScope ps(ctx, PROF_FEAT, alg_bytes, 7);
   k_feat_clear<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
@@ -852,24 +880,31 @@ static int run_features(lisreg_ctx* ctx, FeatFrame* d_frames, int F, const lisre
 
 static int extract_features_impl(lisreg_ctx* ctx, const float* pts, const uint16_t* ring, const float* time, int32_t n,
                                  const lisreg_feat_params* prm, const lisreg_deskew* dsk, lisreg_feat_out* out, float* ext_xyzi) {
-  if (!ctx || n < 0 || (n > 0 && (!pts || !ring)) || !prm || !out) return fail(ctx, LISREG_ERR_ARG, "lisreg_extract_features: bad argument");
+  if (!ctx || n < 0 || (n > 0 && !pts) || !prm || !out) return fail(ctx, LISREG_ERR_ARG, "lisreg_extract_features: bad argument");
   if (prm->n_scan <= 0 || prm->horizon <= 0 || prm->horizon > 2048 || prm->n_scan * 6 > 1024 || prm->downsample_rate <= 0)
     return fail(ctx, LISREG_ERR_ARG, "lisreg_extract_features: unsupported n_scan/horizon/downsample_rate");
+  if (!layout_ok(prm->layout, prm->n_scan)) return fail(ctx, LISREG_ERR_ARG, "lisreg_extract_features: bad cloud layout");
+  if (n > 0 && layout_needs_ring_array(prm->layout) && !ring) return fail(ctx, LISREG_ERR_ARG, "lisreg_extract_features: ring array missing");
   const bool deskew = dsk && dsk->n_imu > 0;
-  if (deskew && (!time || !dsk->imu_time || !dsk->imu_rot)) return fail(ctx, LISREG_ERR_ARG, "lisreg_extract_features_deskew: time / IMU table missing");
+  const bool time_in_rec = prm->layout.point_step != 0 && prm->layout.off_time >= 0;
+  if (deskew && ((!time && !time_in_rec) || !dsk->imu_time || !dsk->imu_rot)) return fail(ctx, LISREG_ERR_ARG, "lisreg_extract_features_deskew: time / IMU table missing");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const int cells = prm->n_scan * prm->horizon;
   int rc = feat_reserve(ctx, 1, cells, prm->n_scan);
   if (rc) return rc;
-  const size_t bp = sizeof(float4) * (size_t)n, br = (sizeof(uint16_t) * (size_t)n + 15) & ~size_t(15);
+  const bool ring_arr = layout_needs_ring_array(prm->layout);
+  const size_t bp = ((size_t)layout_step(prm->layout) * (size_t)n + 15) & ~size_t(15), br = (sizeof(uint16_t) * (size_t)n + 15) & ~size_t(15);
   const size_t bt = deskew ? sizeof(float) * (size_t)n : 0, bi = deskew ? sizeof(double) * 4 * (size_t)dsk->n_imu : 0;
   CK(ctx->d_stage.reserve(bp + br + ((bt + 15) & ~size_t(15)) + bi + 64));
   char* d = (char*)ctx->d_stage.p;
   char* d_time = d + bp + br; char* d_imu = d_time + ((bt + 15) & ~size_t(15));
-  if (n) { CK(cudaMemcpyAsync(d, pts, bp, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(d + bp, ring, sizeof(uint16_t) * (size_t)n, cudaMemcpyHostToDevice, st)); }
+  if (n) {
+    CK(cudaMemcpyAsync(d, pts, (size_t)layout_step(prm->layout) * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (ring_arr) CK(cudaMemcpyAsync(d + bp, ring, sizeof(uint16_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+  }
   if (deskew) {
-    if (n) CK(cudaMemcpyAsync(d_time, time, bt, cudaMemcpyHostToDevice, st));
+    if (n && time) CK(cudaMemcpyAsync(d_time, time, bt, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_imu, dsk->imu_time, sizeof(double) * (size_t)dsk->n_imu, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_imu + sizeof(double) * (size_t)dsk->n_imu, dsk->imu_rot, sizeof(double) * 3 * (size_t)dsk->n_imu, cudaMemcpyHostToDevice, st));
   }
@@ -1016,6 +1051,10 @@ static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, co
   if (fp->n_scan <= 0 || fp->horizon <= 0 || fp->horizon > 2048 || fp->n_scan * 6 > 1024 || fp->downsample_rate <= 0)
     return fail(ctx, LISREG_ERR_ARG, "frame pipeline: unsupported n_scan/horizon/downsample_rate");
   if (!(prm->corner_leaf > 0.f) || !(prm->surf_leaf > 0.f)) return fail(ctx, LISREG_ERR_ARG, "frame pipeline: leaf sizes must be > 0");
+  if (!layout_ok(fp->layout, fp->n_scan)) return fail(ctx, LISREG_ERR_ARG, "frame pipeline: bad cloud layout");
+  const uint64_t rec = (uint64_t)layout_step(fp->layout);
+  const bool ring_arr = layout_needs_ring_array(fp->layout);
+  const size_t pts_align = fp->layout.point_step == 0 ? 15 : 3;
   const int cells = fp->n_scan * fp->horizon;
   const int ccap = fp->n_scan * 120;
   int rc = feat_reserve(ctx, F, cells, fp->n_scan);
@@ -1041,9 +1080,9 @@ static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, co
     const float4* pts; const uint16_t* ring;
     if (d_arena) {
       const size_t op = (size_t)it.pts, orr = (size_t)it.ring;
-      if ((op & 15) || (orr & 1) || !in_arena(op, 16ull * it.n, arena_bytes) || !in_arena(orr, 2ull * it.n, arena_bytes))
+      if ((op & pts_align) || !in_arena(op, rec * it.n, arena_bytes) || (ring_arr && ((orr & 1) || !in_arena(orr, 2ull * it.n, arena_bytes))))
         return fail(ctx, LISREG_ERR_ARG, "frame item %d: bad arena offsets", i);
-      pts = (const float4*)(d_arena + op); ring = (const uint16_t*)(d_arena + orr);
+      pts = (const float4*)(d_arena + op); ring = ring_arr ? (const uint16_t*)(d_arena + orr) : nullptr;
     } else { pts = (const float4*)it.pts; ring = it.ring; }
     FeatFrame& f = hf[i];
     feat_carve((char*)ctx->cur->d_feat.p + feat_per * (size_t)i, cells, fp->n_scan, &f);
@@ -1111,10 +1150,12 @@ int32_t lisreg_frames_batch_arena(lisreg_ctx* ctx, int32_t F, const lisreg_frame
       const lisreg_frame_item& it = items[i];
       if (it.n <= 0) continue;
       const int c = i / C;
-      const uint64_t op = (uint64_t)(size_t)it.pts, orr = (uint64_t)(size_t)it.ring;
-      if (!in_arena(op, 16ull * it.n, arena_bytes) || !in_arena(orr, 2ull * it.n, arena_bytes)) { pipelined = false; break; }   // run_frames reports it
+      const uint64_t recb = (uint64_t)layout_step(prm->feat.layout);
+      const bool rarr = layout_needs_ring_array(prm->feat.layout);
+      const uint64_t op = (uint64_t)(size_t)it.pts, orr = rarr ? (uint64_t)(size_t)it.ring : op;
+      if (!in_arena(op, recb * it.n, arena_bytes) || (rarr && !in_arena(orr, 2ull * it.n, arena_bytes))) { pipelined = false; break; }   // run_frames reports it
       lo[c] = std::min(lo[c], std::min(op, orr));
-      hi[c] = std::max(hi[c], std::max(op + (uint64_t)16 * (uint64_t)it.n, orr + (uint64_t)2 * (uint64_t)it.n));
+      hi[c] = std::max(hi[c], std::max(op + recb * (uint64_t)it.n, rarr ? orr + (uint64_t)2 * (uint64_t)it.n : op));
     }
     uint64_t prev = 0;
     for (int c = 0; c < nchunk && pipelined; c++) {
@@ -1290,18 +1331,18 @@ static int epsc_score_rows_dev(lisreg_ctx* ctx, const uint8_t* d_desc, int32_t N
   cudaStream_t st = ctx->stream;
   const int n_rows = row_begin < N ? (N - row_begin + row_stride - 1) / row_stride : 0;
   if (n_rows == 0) return LISREG_OK;
-  CK(ctx->d_epsc2.reserve((size_t)n_rows * N * 5 + 64));
-  int* sad = (int*)ctx->d_epsc2.p;
-  int8_t* shm = (int8_t*)(sad + (size_t)n_rows * N);
+  CK(ctx->d_epsc2.reserve(sizeof(unsigned long long) * EPSC_TOPK_SLOTS * (size_t)n_rows));
+  unsigned long long* row_top = (unsigned long long*)ctx->d_epsc2.p;
+  CK(cudaMemsetAsync(row_top, 0xff, sizeof(unsigned long long) * EPSC_TOPK_SLOTS * (size_t)n_rows, st));
   dim3 grid((N + EPSC_JT - 1) / EPSC_JT, (n_rows + EPSC_QT - 1) / EPSC_QT);
-  k_epsc_score<<<grid, EPSC_THREADS, 0, st>>>(d_desc, N, row_begin, row_stride, n_rows, sad, shm); LAUNCH_CK();
-  k_epsc_topk<<<(n_rows + 3) / 4, 128, 0, st>>>(sad, shm, N, row_begin, row_stride, n_rows, topk, d_idx, d_score, d_shift); LAUNCH_CK();
+  k_epsc_score<<<grid, EPSC_THREADS, 0, st>>>(d_desc, N, row_begin, row_stride, n_rows, row_top); LAUNCH_CK();
+  k_epsc_topk<<<(n_rows * topk + 127) / 128, 128, 0, st>>>(row_top, n_rows, topk, d_idx, d_score, d_shift); LAUNCH_CK();
   return LISREG_OK;
 }
 
 int32_t lisreg_epsc_score_all_dev(lisreg_ctx* ctx, const uint8_t* d_desc, int32_t N, int32_t topk,
                                   int32_t* d_idx, float* d_score, int8_t* d_shift) {
-  if (!ctx || N <= 0 || !d_desc || topk <= 0 || topk > 8 || !d_idx || !d_score || !d_shift) return fail(ctx, LISREG_ERR_ARG, "lisreg_epsc_score_all: bad argument");
+  if (!ctx || N <= 0 || N >= (1 << 24) || !d_desc || topk <= 0 || topk > 8 || !d_idx || !d_score || !d_shift) return fail(ctx, LISREG_ERR_ARG, "lisreg_epsc_score_all: bad argument");
   CK(cudaSetDevice(ctx->device));
   return epsc_score_rows_dev(ctx, d_desc, N, 0, 1, topk, d_idx, d_score, d_shift);
 }
@@ -1309,7 +1350,7 @@ int32_t lisreg_epsc_score_all_dev(lisreg_ctx* ctx, const uint8_t* d_desc, int32_
 // host buffers; rows q = row_begin + r * row_stride (the whole matrix: 0, 1); outputs n_rows x topk
 int32_t lisreg_epsc_score_rows(lisreg_ctx* ctx, const uint8_t* desc, int32_t N, int32_t row_begin, int32_t row_stride, int32_t topk,
                                int32_t* idx, float* score, int8_t* shift) {
-  if (!ctx || N <= 0 || !desc || row_begin < 0 || row_stride <= 0 || topk <= 0 || topk > 8 || !idx || !score || !shift)
+  if (!ctx || N <= 0 || N >= (1 << 24) || !desc || row_begin < 0 || row_stride <= 0 || topk <= 0 || topk > 8 || !idx || !score || !shift)
     return fail(ctx, LISREG_ERR_ARG, "lisreg_epsc_score_rows: bad argument");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
@@ -1563,6 +1604,29 @@ int32_t lisreg_selftest_smallmat(lisreg_ctx* ctx, const float* A36, const float*
   k_selftest_smallmat<<<1, 32, 0, ctx->stream>>>(d, d + 36, d + 42); LAUNCH_CK();
   CK(cudaMemcpyAsync(out98, d + 42, sizeof(float) * 98, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return LISREG_OK;
+}
+
+int32_t lisreg_selftest_alu_peak(lisreg_ctx* ctx, double* gsad_per_s) {
+  if (!ctx || !gsad_per_s) return LISREG_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->d_stage.reserve(4 * 4096));
+  cudaStream_t st = ctx->stream;
+  cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  const int blocks = ctx->n_sm * 8, iters = 4096;
+  k_epsc_alu_peak<<<blocks, 256, 0, st>>>((unsigned*)ctx->d_stage.p, 64, 1u); LAUNCH_CK();     // warm-up
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    CK(cudaEventRecord(a, st));
+    k_epsc_alu_peak<<<blocks, 256, 0, st>>>((unsigned*)ctx->d_stage.p, iters, 2u + rep); LAUNCH_CK();
+    CK(cudaEventRecord(b, st));
+    CK(cudaEventSynchronize(b));
+    float ms = 0.f; CK(cudaEventElapsedTime(&ms, a, b));
+    const double ops = (double)blocks * 256.0 * iters * 64.0;            // VABSDIFF4 instructions (4 byte-SADs each)
+    best = std::max(best, ops / (ms * 1e-3) / 1e9);
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  *gsad_per_s = best;
   return LISREG_OK;
 }
 

@@ -303,18 +303,29 @@ constexpr float KNN_PAD = 0.1f;          // proof margin (m) the ball walk of sp
 
 #define KNN_INF __int_as_float(0x7f800000)   // +inf
 
-// sorted insert into the running top-6 (distances + positions).  Bit-equal distances are ordered by the ORIGINAL
-// point index (grid.cuh knn_key_less: the oracle's order); the index is fetched only on such a tie, so the common
-// path is one float compare per stage.
+// Sorted insert into the running top-6 (distances + positions).
+// TIE = false (the hot path): candidates arrive in ascending position order, so on equal distance the resident entry
+// - smaller position - stays ahead and ONE float compare per stage suffices.  The order of bit-equal distances that the
+// oracle uses is (d^2, ORIGINAL index) though (grid.cuh knn_key_less); the searches therefore check their final list
+// for equal neighbouring distances (knn6_has_tie) and, only then, run again with TIE = true, which fetches the original
+// indices on equality.  Real clouds almost never tie, so the common path pays five compares per query.
+template <bool TIE>
 __device__ __forceinline__ void knn6_insert_mono(const float4* __restrict__ pts, float (&bd)[6], unsigned (&bp)[6], float d, unsigned p) {
 #pragma unroll
   for (int j = 0; j < 6; j++) {
     bool keep = bd[j] <= d;
-    if (bd[j] == d && d < KNN_INF) keep = knn_orig(pts, bp[j]) < knn_orig(pts, p);   // (a displaced +inf sentinel bubbles down past its peers)
+    if (TIE) { if (bd[j] == d && d < __int_as_float(0x7f800000)) keep = knn_orig(pts, bp[j]) < knn_orig(pts, p); }   // (a displaced +inf sentinel bubbles past its peers)
     const float lo_d = keep ? bd[j] : d; const unsigned lo_p = keep ? bp[j] : p;
     d = keep ? d : bd[j]; p = keep ? p : bp[j];
     bd[j] = lo_d; bp[j] = lo_p;
   }
+}
+// a tie that can change the 5-NN set or its order shows up as two equal neighbouring distances in the final top-6
+__device__ __forceinline__ bool knn6_has_tie(const float (&bd)[6]) {
+  bool t = false;
+#pragma unroll
+  for (int j = 0; j < 5; j++) t |= (bd[j] == bd[j + 1]) && (bd[j] < __int_as_float(0x7f800000));
+  return t;
 }
 
 __device__ __forceinline__ float knn_dist2(float qx, float qy, float qz, float4 m) {
@@ -327,6 +338,7 @@ __device__ __forceinline__ float knn_dist2(float qx, float qy, float qz, float4 
 // list.  Software pipeline: c0 is processed while c1 and c2 are in flight.  adv() steps the cursor (p, e, k) to the
 // next candidate of the flattened list; past the end it keeps returning the last valid position (harmless
 // re-load) and `left` counts what is really there.
+template <bool TIE>
 __device__ __forceinline__ void knn6_scan_ranges(const float4* __restrict__ pts, const uint2* rng, int nr, float qx, float qy, float qz,
                                                  float (&bd)[6], unsigned (&bp)[6]) {
   if (nr <= 0) return;
@@ -345,7 +357,7 @@ __device__ __forceinline__ void knn6_scan_ranges(const float4* __restrict__ pts,
   while (left > 0) {
     const unsigned p2 = p; const float4 c2 = __ldg(&pts[p]); adv();
     const float d = knn_dist2(qx, qy, qz, c0);
-    if (d <= bd[5]) knn6_insert_mono(pts, bd, bp, d, p0);   // "<=": a tie with the 6th is decided inside
+    if (TIE ? d <= bd[5] : d < bd[5]) knn6_insert_mono<TIE>(pts, bd, bp, d, p0);
     c0 = c1; p0 = p1; c1 = c2; p1 = p2;
     left--;
   }
@@ -379,7 +391,12 @@ __device__ __forceinline__ bool knn6_block_flat(const GridDev& g, float qx, floa
       }
     }
   }
-  knn6_scan_ranges(g.pts, rng, nr, qx, qy, qz, bd, bp);
+  knn6_scan_ranges<false>(g.pts, rng, nr, qx, qy, qz, bd, bp);
+  if (knn6_has_tie(bd)) {                                        // rare: order the equal distances by original index
+#pragma unroll
+    for (int j = 0; j < 6; j++) { bd[j] = KNN_INF; bp[j] = 0xffffffffu; }
+    knn6_scan_ranges<true>(g.pts, rng, nr, qx, qy, qz, bd, bp);
+  }
   lb = knn_block_lb(g, minf);
   const float lb2 = lb * lb;
   return !(bd[4] < lb2 || lb2 >= gate);
@@ -432,7 +449,12 @@ __device__ __forceinline__ bool knn6_wide_flat(const GridDev& g, float qx, float
       if (e > b) { if (nr == KNN_WIDE_ROWS) return false; rng[nr * LM_THREADS] = make_uint2(b, e); nr++; }
     }
   }
-  knn6_scan_ranges(g.pts, rng, nr, qx, qy, qz, bd, bp);
+  knn6_scan_ranges<false>(g.pts, rng, nr, qx, qy, qz, bd, bp);
+  if (knn6_has_tie(bd)) {
+#pragma unroll
+    for (int j = 0; j < 6; j++) { bd[j] = KNN_INF; bp[j] = 0xffffffffu; }
+    knn6_scan_ranges<true>(g.pts, rng, nr, qx, qy, qz, bd, bp);
+  }
   lbu = Rn;
   return true;
 }
@@ -718,7 +740,7 @@ k_knn_coop(const RegDesc* __restrict__ descs, const RegState* __restrict__ state
           const uint32_t b = __ldg(&g.cell_start[rowbase + xa]), e = __ldg(&g.cell_start[rowbase + xb + 1]);
           for (uint32_t c = b; c < e; c++) {
             const float dd = knn_dist2(x0, y0, z0, __ldg(&g.pts[c]));
-            if (dd <= bd[5]) knn6_insert_mono(g.pts, bd, bp, dd, c);
+            if (dd <= bd[5]) knn6_insert_mono<true>(g.pts, bd, bp, dd, c);     // short lists only: always tie-aware
           }
         }
         lbu = Rn;

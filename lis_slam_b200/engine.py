@@ -61,9 +61,24 @@ class BatchItem(C.Structure):
     ]
 
 
+class CloudLayout(C.Structure):
+    _fields_ = [("point_step", C.c_int32), ("off_x", C.c_int32), ("off_y", C.c_int32), ("off_z", C.c_int32),
+                ("off_intensity", C.c_int32), ("off_ring", C.c_int32), ("off_time", C.c_int32), ("reserved", C.c_int32)]
+
+
+LAYOUT_FLOAT4_RING, LAYOUT_XYZ_RING, LAYOUT_PCL_XYZIRT, LAYOUT_XYZ_SYNTH_RING = 0, 1, 2, 3
+
+
+def cloud_layout(which):
+    l = CloudLayout()
+    lib().lisreg_cloud_layout_preset(C.byref(l), which)
+    return l
+
+
 class FeatParams(C.Structure):
     _fields_ = [("n_scan", C.c_int32), ("horizon", C.c_int32), ("downsample_rate", C.c_int32),
-                ("min_range", C.c_float), ("max_range", C.c_float), ("edge_thr", C.c_float), ("surf_thr", C.c_float)]
+                ("min_range", C.c_float), ("max_range", C.c_float), ("edge_thr", C.c_float), ("surf_thr", C.c_float),
+                ("reserved", C.c_int32), ("layout", CloudLayout)]
 
 
 class FeatOut(C.Structure):
@@ -191,6 +206,7 @@ def lib():
         L.lisreg_scan2map_batch_arena.restype = i32
         L.lisreg_scan2map_batch_arena.argtypes = [vp, i32, C.POINTER(BatchItem), vp, C.c_uint64, fp, C.POINTER(LmParams), C.POINTER(LmResult)]
         L.lisreg_feat_params_default.argtypes = [C.POINTER(FeatParams)]
+        L.lisreg_cloud_layout_preset.argtypes = [C.POINTER(CloudLayout), i32]
         L.lisreg_extract_features.restype = i32
         L.lisreg_extract_features.argtypes = [vp, vp, vp, i32, C.POINTER(FeatParams), C.POINTER(FeatOut)]
         L.lisreg_voxel_grid.restype = i32
@@ -237,6 +253,19 @@ def lib():
         L.lisreg_odom_push_dev.argtypes = [vp, i32, vp, vp, i32, vp, fp, C.POINTER(OdomResult)]
         L.lisreg_selftest_smallmat.restype = i32
         L.lisreg_selftest_smallmat.argtypes = [vp, fp, fp, fp]
+        L.lisreg_selftest_alu_peak.restype = i32
+        L.lisreg_selftest_alu_peak.argtypes = [vp, C.POINTER(C.c_double)]
+        for name in ("lisreg_comm_unique_id",):
+            getattr(L, name).restype = i32
+        L.lisreg_comm_unique_id.argtypes = [vp]
+        L.lisreg_comm_init.restype = i32
+        L.lisreg_comm_init.argtypes = [vp, i32, i32, vp]
+        L.lisreg_comm_destroy.restype = i32
+        L.lisreg_comm_destroy.argtypes = [vp]
+        L.lisreg_allgather_results.restype = i32
+        L.lisreg_allgather_results.argtypes = [vp, vp, vp, C.c_uint64]
+        L.lisreg_allgather_wait.restype = i32
+        L.lisreg_allgather_wait.argtypes = [vp]
         L.lisreg_profile_enable.restype = i32
         L.lisreg_profile_enable.argtypes = [vp, i32]
         L.lisreg_profile_get.restype = i32
@@ -388,7 +417,13 @@ class Engine:
         """F1-F5 on one raw sweep (host buffers). Returns a dict shaped like oracle.orc.extract_features.
         With time + IMU rotation table: motion de-skew (lisreg_extract_features_deskew); adds 'ext_pts' (M,4)."""
         prm = prm or feat_params()
-        p = _f4(pts); r = np.ascontiguousarray(ring, dtype=np.uint16)
+        if prm.layout.point_step:      # caller-defined records (lisreg_cloud_layout): any contiguous array of n * point_step bytes
+            p = np.ascontiguousarray(pts)
+            assert p.nbytes % prm.layout.point_step == 0
+            n_pts = p.nbytes // prm.layout.point_step
+        else:
+            p = _f4(pts); n_pts = len(p)
+        r = None if ring is None else np.ascontiguousarray(ring, dtype=np.uint16)
         deskew = time is not None
         cap = prm.n_scan * prm.horizon
         a = {"src_index": np.zeros(cap, np.int32), "col_ind": np.zeros(cap, np.int32), "range": np.zeros(cap, np.float32),
@@ -406,10 +441,10 @@ class Engine:
             ir = np.ascontiguousarray(imu_rot if imu_rot is not None else np.zeros((0, 3)), np.float64).reshape(-1)
             dsk = Deskew(it.ctypes.data, ir.ctypes.data, len(it), 0, float(time_scan_cur))
             ext = np.zeros((cap, 4), np.float32)
-            self._ck(lib().lisreg_extract_features_deskew(self._h, p.ctypes.data, r.ctypes.data, t.ctypes.data, len(p), C.byref(prm),
+            self._ck(lib().lisreg_extract_features_deskew(self._h, p.ctypes.data, _ptr(r), t.ctypes.data, n_pts, C.byref(prm),
                                                           C.byref(dsk), C.byref(out), ext.ctypes.data))
         else:
-            self._ck(lib().lisreg_extract_features(self._h, p.ctypes.data, r.ctypes.data, len(p), C.byref(prm), C.byref(out)))
+            self._ck(lib().lisreg_extract_features(self._h, p.ctypes.data, _ptr(r), n_pts, C.byref(prm), C.byref(out)))
         M = out.n_extracted
         res = {"M": M, "start_ring": a["start_ring"], "end_ring": a["end_ring"]}
         if ext is not None:
@@ -578,6 +613,32 @@ class Engine:
                                                 out.ctypes.data_as(C.POINTER(C.c_float))))
         return {"E": out[:6], "V": out[6:42].reshape(6, 6), "X": out[42:48], "qr_ok": int(out[48]),
                 "inv": out[49:85].reshape(6, 6), "lu_ok": int(out[85]), "W3": out[86:89], "V3": out[89:98].reshape(3, 3)}
+
+    def alu_peak(self):
+        v = C.c_double(0)
+        self._ck(lib().lisreg_selftest_alu_peak(self._h, C.byref(v)))
+        return v.value
+
+    # ---- multi-GPU exchange (NCCL behind the C-ABI) ----
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_uint8 * 128)()
+        if lib().lisreg_comm_unique_id(buf) != 0:
+            raise LisregError("lisreg_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return bytes(buf)
+
+    def comm_init(self, world, rank, uid):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._ck(lib().lisreg_comm_init(self._h, world, rank, buf))
+
+    def comm_destroy(self):
+        self._ck(lib().lisreg_comm_destroy(self._h))
+
+    def allgather_results(self, d_send_ptr, d_recv_ptr, bytes_per_rank):
+        self._ck(lib().lisreg_allgather_results(self._h, d_send_ptr, d_recv_ptr, bytes_per_rank))
+
+    def allgather_wait(self):
+        self._ck(lib().lisreg_allgather_wait(self._h))
 
     def profile_enable(self, on=True):
         self._ck(lib().lisreg_profile_enable(self._h, 1 if on else 0))

@@ -80,13 +80,14 @@ def frame_batch(F=256, n_maps=8, n_sweeps=8, map_edge=40000, map_surf=160000, se
     return {"maps": maps, "sweeps": sweeps, "regs": regs}
 
 
-def pack_frame_arena(wl):
+def pack_frame_arena(wl, xyz_only=False):
     """One private copy of the raw sweep (points + ring ids) PER FRAME in a contiguous byte arena.
+    xyz_only: 12-byte xyz records instead of packed float4 (lisreg_cloud_layout preset 1: 14 B / point with the ring).
     Returns (arena uint8, [(pts_off, ring_off, n)])."""
     chunks, offs, off = [], [], 0
     for r in wl["regs"]:
         sw, _ = wl["sweeps"][r["sweep"]]
-        p = np.ascontiguousarray(sw["pts"], np.float32); g = np.ascontiguousarray(sw["ring"], np.uint16)
+        p = np.ascontiguousarray(sw["pts"][:, :3] if xyz_only else sw["pts"], np.float32); g = np.ascontiguousarray(sw["ring"], np.uint16)
         op = off; chunks.append(p.view(np.uint8).reshape(-1)); off += p.nbytes
         og = off; chunks.append(g.view(np.uint8).reshape(-1)); off += g.nbytes
         pad = (-off) % 16

@@ -104,3 +104,38 @@ def test_deskew_matches_oracle(engine):
     g1 = engine.extract_features(s["pts"], s["ring"], time=s["time"], imu_time=imu_time[:3], imu_rot=imu_rot[:3], time_scan_cur=t_scan)
     o1 = orc.deskew(s["pts"], s["time"], g1["src_index"], imu_time[:3], imu_rot[:3], t_scan)
     assert np.array_equal(o1, g1["ext_pts"])
+
+
+def _pack_layout(sw, which):
+    """The same sweep in another memory layout (lisreg_cloud_layout presets)."""
+    pts, ring, t = sw["pts"], sw["ring"], sw["time"]
+    if which == E.LAYOUT_XYZ_RING or which == E.LAYOUT_XYZ_SYNTH_RING:
+        return np.ascontiguousarray(pts[:, :3]), (ring if which == E.LAYOUT_XYZ_RING else None)
+    rec = np.zeros(len(pts), dtype=np.dtype({"names": ["x", "y", "z", "intensity", "ring", "time"],
+                                             "formats": ["<f4", "<f4", "<f4", "<f4", "<u2", "<f4"],
+                                             "offsets": [0, 4, 8, 16, 20, 24], "itemsize": 32}))    # PCL PointXYZIRT (common.h:12-23)
+    rec["x"], rec["y"], rec["z"], rec["intensity"], rec["ring"], rec["time"] = pts[:, 0], pts[:, 1], pts[:, 2], pts[:, 3], ring, t
+    return rec, None
+
+
+@pytest.mark.parametrize("sensor,n_scan", [("hdl64", 64), ("vlp16", 16)])
+def test_cloud_layouts_give_identical_features(engine, sensor, n_scan):
+    """PointCloud2-style layouts (32-byte PCL PointXYZIRT records read in place, bare xyz + ring array, xyz with the
+    ring synthesised from the elevation angle as laserPretreatmentNode.cpp:95-126) produce exactly the index lists of the
+    packed float4 + ring-array input (and therefore of the oracle).  Ring synthesis is checked on the VLP-16 shape, whose
+    2 degree spacing is the one the upstream formula encodes (the synthetic HDL-64 uses a linear elevation table)."""
+    sw = scene().scan(np.array([0.01, -0.01, 0.4, 3.0, 0.5, 0.0], np.float32), sensor=sensor, seed=123, fast=True)
+    base = engine.extract_features(sw["pts"], sw["ring"], E.feat_params(n_scan=n_scan))
+    ref = orc.extract_features(sw["pts"], sw["ring"], orc.feat_params(n_scan=n_scan))
+    assert np.array_equal(base["surf_idx"], ref["surf_idx"]) and np.array_equal(base["corner_idx"], ref["corner_idx"])
+    layouts = [E.LAYOUT_XYZ_RING, E.LAYOUT_PCL_XYZIRT] + ([E.LAYOUT_XYZ_SYNTH_RING] if sensor == "vlp16" else [])
+    for which in layouts:
+        prm = E.feat_params(n_scan=n_scan); prm.layout = E.cloud_layout(which)
+        data, ring = _pack_layout(sw, which)
+        out = engine.extract_features(data, ring, prm)
+        for k in ("src_index", "col_ind", "range", "corner_idx", "sharp_idx", "flat_idx", "surf_idx", "curvature", "label", "start_ring", "end_ring"):
+            assert np.array_equal(out[k], base[k]), (which, k)
+    # bad layouts fail loudly
+    prm = E.feat_params(n_scan=n_scan); prm.layout = E.cloud_layout(E.LAYOUT_XYZ_RING); prm.layout.off_y = 5
+    with pytest.raises(E.LisregError):
+        engine.extract_features(np.ascontiguousarray(sw["pts"][:, :3]), sw["ring"], prm)
