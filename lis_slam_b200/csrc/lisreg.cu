@@ -1811,6 +1811,7 @@ int32_t lisreg_odom_create(lisreg_ctx* ctx, const lisreg_odom_params* prm, int32
   const lisreg_feat_params& fp = prm->frame.feat;
   if (fp.n_scan <= 0 || fp.horizon <= 0 || fp.horizon > 2048 || fp.n_scan * 6 > 1024 || fp.downsample_rate <= 0 ||
       prm->window < 1 || prm->window + 1 > ODOM_MAX_SLOTS || !(prm->frame.corner_leaf > 0.f) || !(prm->frame.surf_leaf > 0.f) ||
+      !layout_ok(fp.layout, fp.n_scan) ||
       prm->frame.lm.max_iters <= 0 || prm->frame.lm.max_iters > LISREG_MAX_ITERS)
     return fail(ctx, LISREG_ERR_ARG, "lisreg_odom_create: unsupported parameters");
   CK(cudaSetDevice(ctx->device));
@@ -1934,10 +1935,12 @@ static std::vector<const void*> odom_graph_key(lisreg_ctx* ctx, lisreg_ctx::Odom
 
 static int odom_push_impl(lisreg_ctx* ctx, int32_t odom_id, const float* pts, const uint16_t* ring, int32_t n, bool on_device,
                           const float* init_pose6, float pose6[6], lisreg_odom_result* res) {
-  if (!ctx || odom_id < 0 || odom_id >= (int)ctx->odoms.size() || !ctx->odoms[odom_id].used || n < 0 || (n > 0 && (!pts || !ring)) || !pose6 || !res)
+  if (!ctx || odom_id < 0 || odom_id >= (int)ctx->odoms.size() || !ctx->odoms[odom_id].used || n < 0 || (n > 0 && !pts) || !pose6 || !res)
     return fail(ctx, LISREG_ERR_ARG, "lisreg_odom_push: bad argument");
   CK(cudaSetDevice(ctx->device));
   lisreg_ctx::Odom& O = ctx->odoms[odom_id];
+  const bool ring_arr = layout_needs_ring_array(O.prm.frame.feat.layout);
+  if (n > 0 && ring_arr && !ring) return fail(ctx, LISREG_ERR_ARG, "lisreg_odom_push: ring array missing");
   cudaStream_t st = ctx->cur->stream;
   const lisreg_feat_params& fp = O.prm.frame.feat;
   const int cells = fp.n_scan * fp.horizon;
@@ -1945,13 +1948,14 @@ static int odom_push_impl(lisreg_ctx* ctx, int32_t odom_id, const float* pts, co
   // ---- the sweep ----
   const float4* d_pts = (const float4*)pts; const uint16_t* d_ring = ring;
   if (!on_device) {
-    const size_t bp = (sizeof(float4) * (size_t)n + 255) & ~size_t(255);
+    const size_t rec = (size_t)layout_step(O.prm.frame.feat.layout);
+    const size_t bp = (rec * (size_t)n + 255) & ~size_t(255);
     CK(O.d_in.reserve(bp + sizeof(uint16_t) * (size_t)n + 64));
     if (n) {
-      CK(cudaMemcpyAsync(O.d_in.p, pts, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync((char*)O.d_in.p + bp, ring, sizeof(uint16_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(O.d_in.p, pts, rec * (size_t)n, cudaMemcpyHostToDevice, st));
+      if (ring_arr) CK(cudaMemcpyAsync((char*)O.d_in.p + bp, ring, sizeof(uint16_t) * (size_t)n, cudaMemcpyHostToDevice, st));
     }
-    d_pts = (const float4*)O.d_in.p; d_ring = (const uint16_t*)((char*)O.d_in.p + bp);
+    d_pts = (const float4*)O.d_in.p; d_ring = ring_arr ? (const uint16_t*)((char*)O.d_in.p + bp) : nullptr;
   }
   odom_update_initial_guess(O, init_pose6);
   O.frame_id++;

@@ -9,9 +9,14 @@
 //   pcl::VoxelGrid::filter                        odomEstimationNode.cpp:196-201, :272-277  -> Registrar::voxelGrid
 //   EPSCGeneration::calculateFEPSC / calculateDistance  src/core/epscGeneration.cpp:591, :633 -> Registrar::describe / scoreAll
 //
+//   OdomEstimationNode::laserCloudInfoHandler     odomEstimationNode.cpp:163-239            -> Odometry::push (device-resident window)
+//
 // The only thing it needs from PCL is the record layout: PCL points are 32-byte records
-// {x, y, z, 1.0f pad, intensity, ...} (common.h:9-35); they are repacked to packed float4 + uint16 here.
-// Define LISREG_ADAPTER_MOCK_PCL to compile it without PCL (unit tests in this repo do that).
+// {x, y, z, 1.0f pad, intensity, ...} (common.h:9-35).  Raw sweeps - the big clouds - are handed to the engine IN
+// PLACE through a lisreg_cloud_layout (PointXYZIRT records, or the `data` blob of a sensor_msgs/PointCloud2 such as
+// cloud_info.cloud_deskewed with the offsets of its `fields`, msg/cloud_info.msg:17-25): no repacking.  The small
+// down-sampled feature / map clouds of the scan2SubMapOptimization call are repacked to float4 + uint16.
+// Define LISREG_ADAPTER_MOCK_PCL to compile it without PCL / ROS (unit tests in this repo do that).
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -28,12 +33,18 @@ struct alignas(16) PointXYZI { float x, y, z, pad; float intensity; float pad2[3
 struct alignas(16) PointXYZIL { float x, y, z, pad; float intensity; uint32_t label; float pad2[2]; };
 struct alignas(16) PointXYZIRT { float x, y, z, pad; float intensity; uint16_t ring; float time; float pad2; };
 template <typename P> struct PointCloud { std::vector<P> points; size_t size() const { return points.size(); } };
+// sensor_msgs/PointField + PointCloud2, the members the adapter reads (datatype 7 = FLOAT32, 4 = UINT16)
+struct PointField { std::string name; uint32_t offset; uint8_t datatype; uint32_t count; };
+struct PointCloud2 { uint32_t height = 1, width = 0; std::vector<PointField> fields; uint32_t point_step = 0, row_step = 0; std::vector<uint8_t> data; };
 }  // namespace lisreg_mock
+#define LISREG_POINTCLOUD2 lisreg_mock::PointCloud2
 #define LISREG_CLOUD(P) lisreg_mock::PointCloud<lisreg_mock::P>
 #else
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
+#include <sensor_msgs/PointCloud2.h>
 #define LISREG_CLOUD(P) pcl::PointCloud<P>
+#define LISREG_POINTCLOUD2 sensor_msgs::PointCloud2
 #endif
 
 namespace lisreg_host {
@@ -58,6 +69,27 @@ template <typename CloudT> inline Packed pack_xyzirt(const CloudT& c) {
   Packed p = pack_xyzi(c); p.aux.resize(p.n);
   for (int32_t i = 0; i < p.n; i++) p.aux[i] = (uint16_t)c.points[i].ring;
   return p;
+}
+
+// lisreg_cloud_layout of an in-memory PCL PointXYZIRT cloud (32-byte records: x 0, y 4, z 8, intensity 16, ring 20, time 24)
+inline lisreg_cloud_layout layout_xyzirt() { lisreg_cloud_layout l; lisreg_cloud_layout_preset(&l, 2); return l; }
+
+// lisreg_cloud_layout of a sensor_msgs/PointCloud2 (e.g. cloud_info.cloud_deskewed, laserProcessing.cpp:729-747) from its
+// `fields`: x / y / z / intensity must be FLOAT32, ring UINT16, time FLOAT32.  The engine then reads msg.data in place.
+template <typename Msg> inline lisreg_cloud_layout layout_of(const Msg& msg) {
+  lisreg_cloud_layout l; std::memset(&l, 0, sizeof(l));
+  l.point_step = (int32_t)msg.point_step; l.off_x = l.off_y = l.off_z = -1; l.off_intensity = -1; l.off_ring = -2; l.off_time = -1;
+  for (const auto& f : msg.fields) {
+    const bool f32 = f.datatype == 7, u16 = f.datatype == 4;
+    if (f.name == "x" && f32) l.off_x = (int32_t)f.offset;
+    else if (f.name == "y" && f32) l.off_y = (int32_t)f.offset;
+    else if (f.name == "z" && f32) l.off_z = (int32_t)f.offset;
+    else if ((f.name == "intensity" || f.name == "i") && f32) l.off_intensity = (int32_t)f.offset;
+    else if (f.name == "ring" && u16) l.off_ring = (int32_t)f.offset;
+    else if ((f.name == "time" || f.name == "t") && f32) l.off_time = (int32_t)f.offset;
+  }
+  if (l.off_x < 0 || l.off_y < 0 || l.off_z < 0) throw std::runtime_error("PointCloud2 without float32 x / y / z fields");
+  return l;   // off_ring == -2 (no ring field): scanID is synthesised from the elevation angle, like laserPretreatmentNode.cpp:95-126
 }
 
 // One engine context per node process (not re-entrant, exactly like the member scratch buffers it replaces).
@@ -96,13 +128,25 @@ class Registrar {
   template <typename CloudT>
   void featureExtraction(const CloudT& laserCloudIn, const lisreg_feat_params& prm, std::vector<int32_t>& extracted_src,
                          std::vector<int32_t>& corner, std::vector<int32_t>& surface, std::vector<int32_t>& sharpCorner, std::vector<int32_t>& sharpSurface) {
-    Packed p = pack_xyzirt(laserCloudIn);
+    static_assert(sizeof(laserCloudIn.points[0]) == 32, "PointXYZIRT is a 32-byte record");
+    lisreg_feat_params q = prm; q.layout = layout_xyzirt();            // the records are read where they are: no repack
+    featureExtractionRaw(laserCloudIn.points.data(), (int32_t)laserCloudIn.points.size(), q, extracted_src, corner, surface, sharpCorner, sharpSurface);
+  }
+  // the same on the `data` blob of a sensor_msgs/PointCloud2 (cloud_info.cloud_deskewed): zero-copy
+  template <typename Msg>
+  void featureExtractionMsg(const Msg& msg, const lisreg_feat_params& prm, std::vector<int32_t>& extracted_src,
+                            std::vector<int32_t>& corner, std::vector<int32_t>& surface, std::vector<int32_t>& sharpCorner, std::vector<int32_t>& sharpSurface) {
+    lisreg_feat_params q = prm; q.layout = layout_of(msg);
+    featureExtractionRaw(msg.data.data(), (int32_t)(msg.point_step ? msg.data.size() / msg.point_step : 0), q, extracted_src, corner, surface, sharpCorner, sharpSurface);
+  }
+  void featureExtractionRaw(const void* records, int32_t n, const lisreg_feat_params& prm, std::vector<int32_t>& extracted_src,
+                            std::vector<int32_t>& corner, std::vector<int32_t>& surface, std::vector<int32_t>& sharpCorner, std::vector<int32_t>& sharpSurface) {
     const size_t cells = (size_t)prm.n_scan * prm.horizon;
     extracted_src.assign(cells, 0); corner.assign((size_t)prm.n_scan * 120, 0); surface.assign(cells, 0);
     sharpCorner.assign((size_t)prm.n_scan * 24, 0); sharpSurface.assign((size_t)prm.n_scan * 60, 0);
     lisreg_feat_out o; std::memset(&o, 0, sizeof(o));
     o.src_index = extracted_src.data(); o.corner_idx = corner.data(); o.surf_idx = surface.data(); o.sharp_idx = sharpCorner.data(); o.flat_idx = sharpSurface.data();
-    check(lisreg_extract_features(ctx_, p.xyzi.data(), p.aux.data(), p.n, &prm, &o));
+    check(lisreg_extract_features(ctx_, (const float*)records, nullptr, n, &prm, &o));
     extracted_src.resize(o.n_extracted); corner.resize(o.n_corner); surface.resize(o.n_surf); sharpCorner.resize(o.n_sharp); sharpSurface.resize(o.n_flat);
   }
 
@@ -166,6 +210,41 @@ class Registrar {
   lisreg_ctx* ctx_ = nullptr;
   int32_t map_id_ = -1;
   bool is_degenerate_ = false;
+};
+
+// Stand-in for the per-frame body of OdomEstimationNode::laserCloudInfoHandler (odomEstimationNode.cpp:163-239) when
+// laserProcessing and odomEstimation run in one process: the sweep goes in (in place, any PointCloud2 layout), the
+// refined transformTobeMapped comes out; the key-frame window, the local map and its index stay in HBM.
+class Odometry {
+ public:
+  float transformTobeMapped[6] = {0, 0, 0, 0, 0, 0};
+  int keyFrameId = 0;
+  float deltaR = 100.f, deltaT = 100.f;
+  lisreg_odom_result last;
+
+  Odometry(Registrar& reg, const lisreg_odom_params& prm) : ctx_(reg.ctx()), prm_(prm) {
+    if (lisreg_odom_create(ctx_, &prm_, &id_) != LISREG_OK) throw std::runtime_error(std::string("lisreg: ") + lisreg_last_error(ctx_));
+  }
+  ~Odometry() { if (id_ >= 0) lisreg_odom_destroy(ctx_, id_); }
+  Odometry(const Odometry&) = delete;
+  Odometry& operator=(const Odometry&) = delete;
+
+  // one sweep as 32-byte PointXYZIRT records (the layout must be the one given in prm.frame.feat.layout at construction)
+  template <typename CloudT> int push(const CloudT& laserCloudIn, const float* init_pose6 = nullptr) {
+    return pushRaw(laserCloudIn.points.data(), (int32_t)laserCloudIn.points.size(), init_pose6);
+  }
+  int pushRaw(const void* records, int32_t n, const float* init_pose6 = nullptr) {
+    const int rc = lisreg_odom_push(ctx_, id_, (const float*)records, nullptr, n, init_pose6, transformTobeMapped, &last);
+    if (rc < 0) throw std::runtime_error(std::string("lisreg: ") + lisreg_last_error(ctx_));
+    keyFrameId = last.keyframe_id;
+    if (last.frame_id > 1 && !(last.lm.deltaR == 100.f && last.lm.deltaT == 100.f)) { deltaR = last.lm.deltaR; deltaT = last.lm.deltaT; }
+    return rc;
+  }
+
+ private:
+  lisreg_ctx* ctx_ = nullptr;
+  lisreg_odom_params prm_;
+  int32_t id_ = -1;
 };
 
 // Stand-in for the EPSCGeneration instance of loopClosureThread (subMapOptmizationNode.cpp:2332): same call, same

@@ -89,3 +89,48 @@ def test_cpp_adapter_runs_on_gpu():
     if not os.path.exists(exe):
         test_cpp_adapter_compiles_and_links()
     assert subprocess.call([exe, "run"]) == 0
+
+
+@pytest.mark.gpu
+def test_cpp_adapter_on_real_data_matches_oracle(tmp_path):
+    """The header-only C++ adapter (host/lisreg_adapter.hpp) driven with REAL clouds: Registrar::setMap +
+    scan2SubMapOptimization (pose vs the CPU oracle, 1e-4 rad / 1e-3 m), featureExtraction on 32-byte PCL PointXYZIRT
+    records read in place and on a sensor_msgs/PointCloud2 blob with its own field order (index lists == oracle),
+    Odometry::push over a short stream (trajectory vs the oracle flow)."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import local_map, reg_case, scene
+    from lis_slam_b200 import stream, synth
+    from oracle import orc
+    from test_stream_parity import OracleBackend, _stream_traj
+    d = str(tmp_path)
+    m = local_map(); f, truth, guess = reg_case(1, n_corner=2000, n_surf=6000)
+    for name, arr in (("map_corner", m["corner"]), ("map_surf", m["surf"]), ("scan_corner", f["corner"]), ("scan_surf", f["surf"]),
+                      ("guess", np.asarray(guess, np.float32))):
+        np.ascontiguousarray(arr, np.float32).tofile(os.path.join(d, name + ".bin"))
+    sw = scene().scan(np.array([0.0, 0.0, 0.3, 2.0, 0.4, 0.0], np.float32), sensor="vlp16", seed=321, fast=True)
+    np.ascontiguousarray(sw["pts"], np.float32).tofile(os.path.join(d, "sweep_pts.bin")); np.ascontiguousarray(sw["ring"], np.uint16).tofile(os.path.join(d, "sweep_ring.bin"))
+    sweeps = [scene().scan(_stream_traj(t), sensor="vlp16", seed=7000 + t, fast=True) for t in range(8)]
+    for t, s in enumerate(sweeps):
+        np.ascontiguousarray(s["pts"], np.float32).tofile(os.path.join(d, "stream_%03d_pts.bin" % t))
+        np.ascontiguousarray(s["ring"], np.uint16).tofile(os.path.join(d, "stream_%03d_ring.bin" % t))
+    np.asarray(_stream_traj(0), np.float32).tofile(os.path.join(d, "stream_init.bin"))
+    exe = "/tmp/lisreg_adapter_check"
+    test_cpp_adapter_compiles_and_links()
+    assert subprocess.call([exe, "data", d]) == 0
+    out = np.fromfile(os.path.join(d, "out_pose.bin"), np.float32)
+    pose_o, res_o, _ = orc.scan2map(f["corner"], f["surf"], m["corner"], m["surf"], guess, orc.lm_params("A"), log=False)
+    er, et = synth.pose_error(pose_o, out[:6])
+    assert er <= 1e-4 and et <= 1e-3 and int(out[6]) == res_o.iters and int(out[7]) == res_o.status
+    fo = orc.extract_features(sw["pts"], sw["ring"], orc.feat_params(n_scan=16))
+    assert np.array_equal(np.fromfile(os.path.join(d, "out_corner_idx.bin"), np.int32), fo["corner_idx"])
+    assert np.array_equal(np.fromfile(os.path.join(d, "out_surf_idx.bin"), np.int32), fo["surf_idx"])
+    assert np.array_equal(np.fromfile(os.path.join(d, "out_src.bin"), np.int32), fo["src_index"])
+    traj = np.fromfile(os.path.join(d, "out_traj.bin"), np.float32).reshape(-1, 7)
+    so = stream.OdometryStream(OracleBackend(), orc.lm_params("A"), orc.feat_params(n_scan=16))
+    for t, s in enumerate(sweeps):
+        po = so.push(s["pts"], s["ring"], initial_pose=_stream_traj(0))
+        er, et = synth.pose_error(po, traj[t, :6])
+        assert er <= 1e-4 and et <= 1e-3, (t, er, et)
+    assert int(traj[-1, 6]) == so.keyframe_id
