@@ -316,6 +316,44 @@ int32_t lisreg_odom_push(lisreg_ctx* ctx, int32_t odom_id, const float* pts, con
 int32_t lisreg_odom_push_dev(lisreg_ctx* ctx, int32_t odom_id, const float* d_pts, const uint16_t* d_ring, int32_t n,
                              const float* init_pose6, float pose6[6], lisreg_odom_result* res);
 
+/* ---- device-resident local map / submap (rows T4 + 8f "next" #2) ----
+ * One lisreg_submap = the five class clouds of localMap_t / submap_t (subMap.h:435-777: submap_dynamic, _pole, _ground,
+ * _building, _outlier; class index 0..4 in that order) kept in HBM together with their bounding box.
+ * lisreg_submap_insert = SubMapManager::insert_local_map / insert_submap / fisrt_submap (subMap.h:785-1055): the key
+ * frame's class clouds are moved by its pose (transformPointCloud, common.cpp:134-160: optimized_pose for the local map,
+ * relative_pose for a submap), the DYNAMIC class optionally goes through the map-based dynamic-object removal against the
+ * map's current dynamic cloud (map_scan_feature_pts_distance_removal, :1001-1017, only when feature_point_num >
+ * max_num_pts / 5), everything is appended (append_feature :742-753) and the box of all five clouds is refreshed
+ * (get_cloud_bbx_cpt :131-171).
+ * lisreg_submap_extract = SubMapOdometryNode::extractSlidingCloud (subMapOptmizationNode.cpp:1369-1432; the submap copy
+ * :3976-4081): every class is voxel-filtered IN PLACE (leaf 0.1 / 0.05 / 0.4 / 0.2 / 0.6), box-filtered IN PLACE with the
+ * sensor box (+-70, +-70, -10..20 moved by cur_pose6) intersected with the map box padded by 2 m (strict inequalities,
+ * subMap.h:1125-1150), then laserCloudCornerFromSubMap = pole and laserCloudSurfFromSubMap = ground + building + dynamic
+ * become a registration map (*map_id, usable with lisreg_scan2map variant 'B' / 'C'; pass the previous id to rebuild
+ * that map in place, -1 for a new one).  Map-side labels are not kept: the loop reads the label of the query point only. */
+#define LISREG_SUBMAP_CLASSES 5
+typedef struct lisreg_submap_insert_params {
+  int32_t dynamic_removal_on;       /* map_based_dynamic_removal_on */
+  int32_t max_num_pts;              /* 20000 */
+  float center_radius, dist_min, dist_max, near_dist;   /* 30, 0.3, 3.0, 0.03 */
+} lisreg_submap_insert_params;
+typedef struct lisreg_submap_info {
+  int32_t n[LISREG_SUBMAP_CLASSES]; /* points per class after the call */
+  int32_t feature_point_num;
+  double bound_min[3], bound_max[3];/* localMap->bound */
+  int32_t n_map_corner, n_map_surf; /* extract: size of the registration map */
+} lisreg_submap_info;
+int32_t lisreg_submap_create(lisreg_ctx* ctx, int32_t* submap_id);
+int32_t lisreg_submap_destroy(lisreg_ctx* ctx, int32_t submap_id);
+int32_t lisreg_submap_clear(lisreg_ctx* ctx, int32_t submap_id);                     /* localMap_t::free() */
+int32_t lisreg_submap_insert(lisreg_ctx* ctx, int32_t submap_id, const float* const pts[LISREG_SUBMAP_CLASSES],
+                             const int32_t n[LISREG_SUBMAP_CLASSES], const float pose6[6],
+                             const lisreg_submap_insert_params* prm /* NULL = no dynamic removal */, lisreg_submap_info* info);
+int32_t lisreg_submap_extract(lisreg_ctx* ctx, int32_t submap_id, const float cur_pose6[6], const float leaf[LISREG_SUBMAP_CLASSES] /* NULL = reference */,
+                              float gate_hint, int32_t* map_id, lisreg_submap_info* info);
+/* copies class cloud `cls` to the host (parity tests / visualisation); *n = its size (may exceed cap: nothing is copied then) */
+int32_t lisreg_submap_download(lisreg_ctx* ctx, int32_t submap_id, int32_t cls, float* out, int32_t cap, int32_t* n);
+
 /* ---- EPSC loop-closure descriptors and scoring (B3 pieces) ----
  * lisreg_epsc_describe replaces EPSCGeneration::calculateEPSC / calculateSEPSC / calculateFEPSC
  * (epscGeneration.cpp:478-607) for n submaps/keyframes at once; using_map is the 256-entry label -> class

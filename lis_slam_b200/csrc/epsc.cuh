@@ -14,6 +14,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "tma.cuh"
 
 namespace lisreg {
 
@@ -92,37 +93,50 @@ __global__ void k_epsc_describe(const EpscCloud* __restrict__ clouds, const uint
 // Pair scoring.  Work item = (query q, history j < q).  Pairs are enumerated over a [Q_TILE x J_TILE] tile
 // per block; thread t handles query (t / J_TILE), history (t % J_TILE) of the tile.
 constexpr int EPSC_QT = 8, EPSC_JT = 16, EPSC_THREADS = EPSC_QT * EPSC_JT;
-constexpr int EPSC_STRIDE_W = 401;   // words per descriptor in smem (+1 pad => conflict-free across descriptors)
+// words per descriptor row in shared memory: 400 payload words + 4 pad = 1616 B, a multiple of 16 B so that every row is
+// a legal bulk-copy destination (16 threads with different rows and the same word then touch 8 banks: 2-way conflicts on
+// 40 LDS per ring against 600 ALU instructions - negligible)
+constexpr int EPSC_STRIDE_W = 404;
+constexpr int EPSC_CLUSTER = 4;      // CTAs per cluster along the history axis: they share the tile's query rows (multicast)
 
 // Query rows are q = q_begin + r * q_stride for local rows r in [0, n_rows): the whole matrix is (0, 1, N); a rank
 // of a multi-GPU run owns the cyclic rows (rank, world, ...) (triangular load => cyclic assignment).
 //
-// The per-query top-k is FUSED into the scoring kernel: a pair whose best SAD passes the reference gate
-// (score > 0.75 <=> SAD < 102000, rare) is pushed into the 8-slot sorted list of its query row with an atomicMin
-// cascade on 64-bit keys (slot k keeps the smaller of (resident, incoming) and hands the larger one to slot k + 1).
-// min / max conserve the multiset, so whatever the arrival order the 8 slots end up holding the 8 smallest keys in
-// ascending order - deterministic - and the N x N SAD / shift matrices (125 MB at N = 5000) never exist.
-// key = SAD (< 2^17) << 40 | history index j (< 2^24) << 8 | shift + 10: ordered by (SAD, j) like the reference loop
-// (first best candidate wins), the shift rides along.
+// Staging: the 8 query rows + 16 history rows of a tile (24 x 1600 B) are copied by the bulk-copy engine
+// (cp.async.bulk, one 1600-byte transaction per descriptor row, completion counted on an mbarrier) - no registers, no
+// LSU instructions.  The EPSC_CLUSTER CTAs of a cluster sit next to each other on the history axis and need the SAME
+// query rows: the cluster leader fetches them once and multicasts them into every CTA's shared memory.
+//
 constexpr int EPSC_TOPK_SLOTS = 8;
 constexpr unsigned EPSC_SAD_GATE = 102000u;     // 1 - SAD / (80 * 20 * 255) > DISTANCE_THRESHOLD 0.75
 __global__ void __launch_bounds__(EPSC_THREADS)
 k_epsc_score(const uint8_t* __restrict__ desc, int N, int q_begin, int q_stride, int n_rows, unsigned long long* __restrict__ row_top) {
   const int r0 = blockIdx.y * EPSC_QT, j0 = blockIdx.x * EPSC_JT;
   const int r_last = min(r0 + EPSC_QT, n_rows) - 1;
-  if (r_last < r0 || j0 >= q_begin + r_last * q_stride) return;   // whole tile on/above the diagonal (needs j < q): nothing to do
-  __shared__ unsigned s_q[EPSC_QT * EPSC_STRIDE_W];
-  __shared__ unsigned s_j[EPSC_JT * EPSC_STRIDE_W];
-  const unsigned* dw = (const unsigned*)desc;
-  for (int t = threadIdx.x; t < EPSC_QT * 400; t += EPSC_THREADS) {
-    const int d = t / 400, w = t % 400;
-    s_q[d * EPSC_STRIDE_W + w] = (r0 + d < n_rows) ? __ldg(&dw[(size_t)(q_begin + (r0 + d) * q_stride) * 400 + w]) : 0u;
+  // the cluster's first history tile decides for the whole cluster (j0 ascends inside it): on / above the diagonal
+  // (needs j < q) nobody has work and everybody leaves before any barrier exists
+  const unsigned crank = tma::cluster_ctarank(), csize = tma::cluster_nctarank();
+  const int j0_first = ((int)blockIdx.x - (int)crank) * EPSC_JT;
+  if (r_last < r0 || j0_first >= q_begin + r_last * q_stride) return;
+  __shared__ __align__(16) unsigned s_q[EPSC_QT * EPSC_STRIDE_W];
+  __shared__ __align__(16) unsigned s_j[EPSC_JT * EPSC_STRIDE_W];
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int nq = r_last - r0 + 1;                                   // valid query rows of the tile (same for the cluster)
+  const int nj = max(0, min(EPSC_JT, N - j0));                      // valid history rows of this CTA
+  if (threadIdx.x == 0) { tma::mbar_init(&s_bar, 1); tma::fence_barrier_init(); }
+  if (csize > 1) tma::cluster_sync(); else __syncthreads();        // every CTA's barrier exists before the leader multicasts into it
+  if (threadIdx.x == 0) {
+    tma::mbar_arrive_expect_tx(&s_bar, (unsigned)(nq + nj) * EPSC_SIZE);
+    for (int d = 0; d < nj; d++) tma::bulk_g2s(&s_j[d * EPSC_STRIDE_W], desc + (size_t)(j0 + d) * EPSC_SIZE, EPSC_SIZE, &s_bar);
+    if (csize == 1)
+      for (int d = 0; d < nq; d++) tma::bulk_g2s(&s_q[d * EPSC_STRIDE_W], desc + (size_t)(q_begin + (r0 + d) * q_stride) * EPSC_SIZE, EPSC_SIZE, &s_bar);
+    else if (crank == 0)
+      for (int d = 0; d < nq; d++)
+        tma::bulk_g2s_multicast(&s_q[d * EPSC_STRIDE_W], desc + (size_t)(q_begin + (r0 + d) * q_stride) * EPSC_SIZE, EPSC_SIZE, &s_bar,
+                                (unsigned short)((1u << csize) - 1u));
   }
-  for (int t = threadIdx.x; t < EPSC_JT * 400; t += EPSC_THREADS) {
-    const int d = t / 400, w = t % 400;
-    s_j[d * EPSC_STRIDE_W + w] = (j0 + d < N) ? __ldg(&dw[(size_t)(j0 + d) * 400 + w]) : 0u;
-  }
-  __syncthreads();
+  tma::mbar_wait(&s_bar, 0);
+  if (csize > 1) tma::cluster_sync();                               // nobody exits while copies into its shared memory may be in flight
   const int ql = threadIdx.x / EPSC_JT, jl = threadIdx.x % EPSC_JT;
   const int r = r0 + ql, q = q_begin + r * q_stride, j = j0 + jl;
   if (r >= n_rows || j >= q) return;

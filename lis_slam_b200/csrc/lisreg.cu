@@ -133,6 +133,14 @@ struct lisreg_ctx {
     cudaGraphExec_t gexec = nullptr; std::vector<const void*> gkey;   // captured per-frame graph + the buffer addresses it was captured with
   };
   std::vector<Odom> odoms;
+  struct Submap {                          // localMap_t / submap_t class clouds in HBM (lisreg_submap_*)
+    bool used = false;
+    DevBuf cls[5]; int n[5] = {0, 0, 0, 0, 0};
+    double bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
+    CloudIndex dyn_index;                  // scratch index of the dynamic cloud (map-based dynamic removal)
+  };
+  std::vector<Submap> submaps;
+  DevBuf d_smvox, d_smcat;
   // multi-GPU exchange: NCCL communicator (own or adopted), private stream, fence / done events
   void* comm = nullptr; bool comm_owned = false; int comm_world = 1, comm_rank = 0;
   cudaStream_t comm_stream = nullptr; cudaEvent_t comm_fence = nullptr, comm_done = nullptr; bool comm_pending = false;
@@ -425,6 +433,8 @@ void lisreg_destroy(lisreg_ctx* ctx) {
   ctx->h_stage.release(); ctx->h_out.release(); ctx->h_desc.release();
   for (auto& L : ctx->loops) if (L.used) { cudaFree(L.d_proj); cudaFree(L.d_desc); cudaFree(L.d_lut); }
   lisreg_comm_destroy(ctx);
+  for (auto& S : ctx->submaps) if (S.used) { for (auto& b : S.cls) b.release(); cudaFree(S.dyn_index.sorted); cudaFree(S.dyn_index.cell_start); }
+  ctx->d_smvox.release(); ctx->d_smcat.release();
   for (auto& O : ctx->odoms) if (O.used) {
     if (O.gexec) cudaGraphExecDestroy(O.gexec);
     cudaFree(O.d_win_c); cudaFree(O.d_win_s);
@@ -957,7 +967,7 @@ int32_t lisreg_extract_features_deskew(lisreg_ctx* ctx, const float* pts, const 
 static size_t vox_seg_bytes(int cap) {
   const int nblk = (cap + RS_TILE - 1) / RS_TILE + 1;
   size_t b = 4 * (size_t)cap * 4;                 // key_a, val_a, key_b, val_b
-  b += 4 * 256 * (size_t)nblk;                    // hist
+  b += 4 * 256 * (size_t)(nblk + 1);              // hist + the 256 digit bases behind it
   b += 4 * ((size_t)cap + 1);                     // seg_start
   b += sizeof(VoxPlan) + 16 + 32;                 // plan, out_n, bbox
   b += sizeof(float4) * (size_t)cap;              // out
@@ -970,7 +980,7 @@ static void vox_carve(char* base, int cap, VoxSeg* s) {
   s->out = (float4*)take(sizeof(float4) * (size_t)cap);
   s->key_a = (uint32_t*)take(4 * (size_t)cap); s->val_a = (uint32_t*)take(4 * (size_t)cap);
   s->key_b = (uint32_t*)take(4 * (size_t)cap); s->val_b = (uint32_t*)take(4 * (size_t)cap);
-  s->hist = (uint32_t*)take(4 * 256 * (size_t)nblk);
+  s->hist = (uint32_t*)take(4 * 256 * (size_t)(nblk + 1));
   s->seg_start = (int*)take(4 * ((size_t)cap + 1));
   s->plan = (VoxPlan*)take(sizeof(VoxPlan));
   s->bbox = (unsigned*)take(24);
@@ -985,16 +995,30 @@ static int run_voxel(lisreg_ctx* ctx, VoxSeg* d_segs, int nseg, int max_n, doubl
   const int nblk = std::max(1, (max_n + RS_TILE - 1) / RS_TILE);
   const int pblk = std::max(1, std::min(64, (max_n + 1023) / 1024));
   ProfScope ps(ctx, PROF_VOXEL, alg_bytes, 16);
+  // single-block scans are the cheaper choice when there are many clouds to keep the GPU busy; with a handful of clouds
+  // (streaming odometry: one frame's two clouds, the 2 M-point window map) they serialise, so those take the parallel forms
+  const bool big = nseg < 64;
   k_vox_bbox_init<<<(nseg * 6 + 255) / 256, 256, 0, st>>>(d_segs, nseg); LAUNCH_CK();
   k_vox_bbox<<<dim3(pblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
   k_vox_plan<<<(nseg + 127) / 128, 128, 0, st>>>(d_segs, nseg); LAUNCH_CK();
   k_vox_keys<<<dim3(pblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
   for (int pass = 0; pass < 4; pass++) {                  // passes beyond a cloud's plan->npass return at once
     k_rs_hist<<<dim3(nblk, nseg), RS_THREADS, 0, st>>>(d_segs, 8 * pass, pass & 1); LAUNCH_CK();
-    k_rs_scan<<<nseg, 1024, 0, st>>>(d_segs, 8 * pass); LAUNCH_CK();
+    if (big) {      // a few large clouds (sliding-window map, submap classes): scan with 256 warps per cloud
+      k_rs_scan_digit<<<dim3(32, nseg), 256, 0, st>>>(d_segs, 8 * pass); LAUNCH_CK();
+      k_rs_scan_base<<<(nseg + 7) / 8, 256, 0, st>>>(d_segs, nseg, 8 * pass); LAUNCH_CK();
+    } else {        // many small clouds (batched frames): one block per cloud is the cheaper launch
+      k_rs_scan<<<nseg, 1024, 0, st>>>(d_segs, 8 * pass); LAUNCH_CK();
+    }
     k_rs_scatter<<<dim3(nblk, nseg), RS_THREADS, 0, st>>>(d_segs, 8 * pass, pass & 1); LAUNCH_CK();
   }
-  k_vox_heads<<<nseg, 1024, 0, st>>>(d_segs); LAUNCH_CK();
+  if (big) {
+    k_vox_head_count<<<dim3(nblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
+    k_vox_head_scan<<<(nseg + 7) / 8, 256, 0, st>>>(d_segs, nseg); LAUNCH_CK();
+    k_vox_head_write<<<dim3(nblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
+  } else {
+    k_vox_heads<<<nseg, 1024, 0, st>>>(d_segs); LAUNCH_CK();
+  }
   k_vox_centroid<<<dim3(std::max(1, (max_n + VC_CHUNK - 1) / VC_CHUNK), nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
   return LISREG_OK;
 }
@@ -1334,8 +1358,17 @@ static int epsc_score_rows_dev(lisreg_ctx* ctx, const uint8_t* d_desc, int32_t N
   CK(ctx->d_epsc2.reserve(sizeof(unsigned long long) * EPSC_TOPK_SLOTS * (size_t)n_rows));
   unsigned long long* row_top = (unsigned long long*)ctx->d_epsc2.p;
   CK(cudaMemsetAsync(row_top, 0xff, sizeof(unsigned long long) * EPSC_TOPK_SLOTS * (size_t)n_rows, st));
-  dim3 grid((N + EPSC_JT - 1) / EPSC_JT, (n_rows + EPSC_QT - 1) / EPSC_QT);
-  k_epsc_score<<<grid, EPSC_THREADS, 0, st>>>(d_desc, N, row_begin, row_stride, n_rows, row_top); LAUNCH_CK();
+  {
+    // clusters of EPSC_CLUSTER CTAs along the history axis share the tile's query rows (bulk-copy multicast)
+    const int gx = (((N + EPSC_JT - 1) / EPSC_JT) + EPSC_CLUSTER - 1) / EPSC_CLUSTER * EPSC_CLUSTER;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(gx, (n_rows + EPSC_QT - 1) / EPSC_QT); lc.blockDim = dim3(EPSC_THREADS); lc.dynamicSmemBytes = 0; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = EPSC_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&lc, k_epsc_score, d_desc, (int)N, (int)row_begin, (int)row_stride, (int)n_rows, row_top));
+    ctx->launches++;
+  }
   k_epsc_topk<<<(n_rows * topk + 127) / 128, 128, 0, st>>>(row_top, n_rows, topk, d_idx, d_score, d_shift); LAUNCH_CK();
   return LISREG_OK;
 }
@@ -1343,6 +1376,7 @@ static int epsc_score_rows_dev(lisreg_ctx* ctx, const uint8_t* d_desc, int32_t N
 int32_t lisreg_epsc_score_all_dev(lisreg_ctx* ctx, const uint8_t* d_desc, int32_t N, int32_t topk,
                                   int32_t* d_idx, float* d_score, int8_t* d_shift) {
   if (!ctx || N <= 0 || N >= (1 << 24) || !d_desc || topk <= 0 || topk > 8 || !d_idx || !d_score || !d_shift) return fail(ctx, LISREG_ERR_ARG, "lisreg_epsc_score_all: bad argument");
+  if (((size_t)d_desc & 15) != 0) return fail(ctx, LISREG_ERR_ARG, "lisreg_epsc_score_all_dev: descriptors must be 16-byte aligned (bulk-copy source)");
   CK(cudaSetDevice(ctx->device));
   return epsc_score_rows_dev(ctx, d_desc, N, 0, 1, topk, d_idx, d_score, d_shift);
 }
@@ -2068,6 +2102,239 @@ int32_t lisreg_odom_push(lisreg_ctx* ctx, int32_t odom_id, const float* pts, con
 int32_t lisreg_odom_push_dev(lisreg_ctx* ctx, int32_t odom_id, const float* d_pts, const uint16_t* d_ring, int32_t n,
                              const float* init_pose6, float pose6[6], lisreg_odom_result* res) {
   return odom_push_impl(ctx, odom_id, d_pts, d_ring, n, true, init_pose6, pose6, res);
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident local map / submap (T4, SURVEY.md 8f "next" #2)
+// ------------------------------------------------------------------------------------------------
+// exclusive scan in place over n_entries uint32 (three-phase block scan of the grid build)
+static int scan_u32(lisreg_ctx* ctx, uint32_t* d_data, int n_entries, uint32_t* d_bsums) {
+  cudaStream_t st = ctx->cur->stream;
+  const int nblk = (n_entries + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  k_scan_local<<<nblk, SCAN_BLOCK, 0, st>>>(d_data, n_entries, d_bsums); LAUNCH_CK();
+  k_scan_sums<<<1, SCAN_BLOCK, 0, st>>>(d_bsums, nblk); LAUNCH_CK();
+  k_scan_add<<<nblk, SCAN_BLOCK, 0, st>>>(d_data, n_entries, d_bsums); LAUNCH_CK();
+  return LISREG_OK;
+}
+// order-preserving compaction of d_in (n points) by d_flags (n + 1 entries, last 0; scanned in place) into d_out; *kept on the host
+static int compact_points(lisreg_ctx* ctx, const float4* d_in, int n, uint32_t* d_flags, uint32_t* d_bsums, float4* d_out, int* kept) {
+  cudaStream_t st = ctx->cur->stream;
+  *kept = 0;
+  if (n <= 0) return LISREG_OK;
+  int rc = scan_u32(ctx, d_flags, n + 1, d_bsums);
+  if (rc) return rc;
+  k_sm_scatter<<<(n + 255) / 256, 256, 0, st>>>(d_in, n, d_flags, d_out); LAUNCH_CK();
+  uint32_t total = 0;
+  CK(cudaMemcpyAsync(&total, d_flags + n, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *kept = (int)total;
+  return LISREG_OK;
+}
+static size_t sm_flag_bytes(int n) { return ((sizeof(uint32_t) * ((size_t)n + 1) + 255) & ~size_t(255)) + sizeof(uint32_t) * ((size_t)(n + 1) / SCAN_BLOCK + 2); }
+
+int32_t lisreg_submap_create(lisreg_ctx* ctx, int32_t* submap_id) {
+  if (!ctx || !submap_id) return fail(ctx, LISREG_ERR_ARG, "lisreg_submap_create: bad argument");
+  int slot = -1;
+  for (size_t i = 0; i < ctx->submaps.size(); i++) if (!ctx->submaps[i].used) { slot = (int)i; break; }
+  if (slot < 0) { ctx->submaps.emplace_back(); slot = (int)ctx->submaps.size() - 1; }
+  ctx->submaps[slot] = lisreg_ctx::Submap();
+  ctx->submaps[slot].used = true;
+  *submap_id = slot;
+  return LISREG_OK;
+}
+#define SUBMAP_CK(name) if (!ctx || submap_id < 0 || submap_id >= (int)ctx->submaps.size() || !ctx->submaps[submap_id].used) \
+  return fail(ctx, LISREG_ERR_ARG, name ": bad submap id")
+int32_t lisreg_submap_destroy(lisreg_ctx* ctx, int32_t submap_id) {
+  SUBMAP_CK("lisreg_submap_destroy");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (auto& b : ctx->submaps[submap_id].cls) b.release();
+  cudaFree(ctx->submaps[submap_id].dyn_index.sorted); cudaFree(ctx->submaps[submap_id].dyn_index.cell_start);
+  ctx->submaps[submap_id] = lisreg_ctx::Submap();
+  return LISREG_OK;
+}
+int32_t lisreg_submap_clear(lisreg_ctx* ctx, int32_t submap_id) {
+  SUBMAP_CK("lisreg_submap_clear");
+  lisreg_ctx::Submap& S = ctx->submaps[submap_id];
+  for (int c = 0; c < 5; c++) S.n[c] = 0;
+  for (int d = 0; d < 3; d++) { S.bmin[d] = 0; S.bmax[d] = 0; }
+  return LISREG_OK;
+}
+static void submap_fill_info(const lisreg_ctx::Submap& S, lisreg_submap_info* info) {
+  if (!info) return;
+  memset(info, 0, sizeof(*info));
+  for (int c = 0; c < 5; c++) { info->n[c] = S.n[c]; info->feature_point_num += S.n[c]; }
+  for (int d = 0; d < 3; d++) { info->bound_min[d] = S.bmin[d]; info->bound_max[d] = S.bmax[d]; }
+}
+// grows a class buffer to hold `want` points, keeping its content
+static int submap_reserve(lisreg_ctx* ctx, lisreg_ctx::Submap& S, int c, size_t want) {
+  if (sizeof(float4) * want <= S.cls[c].cap) return LISREG_OK;
+  DevBuf nb;
+  CK(nb.reserve(sizeof(float4) * (want + want / 2 + 1024)));
+  if (S.n[c] > 0) {
+    CK(cudaMemcpyAsync(nb.p, S.cls[c].p, sizeof(float4) * (size_t)S.n[c], cudaMemcpyDeviceToDevice, ctx->cur->stream));
+    CK(cudaStreamSynchronize(ctx->cur->stream));
+  }
+  S.cls[c].release();
+  S.cls[c] = nb;
+  return LISREG_OK;
+}
+
+int32_t lisreg_submap_insert(lisreg_ctx* ctx, int32_t submap_id, const float* const pts[LISREG_SUBMAP_CLASSES], const int32_t n[LISREG_SUBMAP_CLASSES],
+                             const float pose6[6], const lisreg_submap_insert_params* prm, lisreg_submap_info* info) {
+  SUBMAP_CK("lisreg_submap_insert");
+  if (!pts || !n || !pose6) return fail(ctx, LISREG_ERR_ARG, "lisreg_submap_insert: bad argument");
+  for (int c = 0; c < 5; c++) if (n[c] < 0 || (n[c] > 0 && !pts[c])) return fail(ctx, LISREG_ERR_ARG, "lisreg_submap_insert: class %d bad", c);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->cur->stream;
+  lisreg_ctx::Submap& S = ctx->submaps[submap_id];
+  float T[16]; odom_T16(pose6, T);
+  OdomT12 t12; for (int i = 0; i < 12; i++) t12.m[i] = T[i];
+  int feature_point_num = 0;
+  for (int c = 0; c < 5; c++) feature_point_num += S.n[c];
+  for (int c = 0; c < 5; c++) {
+    if (n[c] == 0) continue;
+    const size_t bytes = sizeof(float4) * (size_t)n[c];
+    const size_t o_moved = (bytes + 255) & ~size_t(255), o_keep = 2 * o_moved, o_flags = o_keep + (((size_t)n[c] + 255) & ~size_t(255));
+    CK(ctx->d_stage.reserve(o_flags + sm_flag_bytes(n[c])));
+    char* d = (char*)ctx->d_stage.p;
+    CK(cudaMemcpyAsync(d, pts[c], bytes, cudaMemcpyHostToDevice, st));
+    int rc = submap_reserve(ctx, S, c, (size_t)S.n[c] + n[c]);
+    if (rc) return rc;
+    float4* dst = (float4*)S.cls[c].p + S.n[c];
+    const bool filter = c == 0 && prm && prm->dynamic_removal_on && feature_point_num > prm->max_num_pts / 5 && n[c] > 10;   // subMap.h:980, :1069
+    if (!filter) {
+      k_sm_transform<<<std::min(592, (n[c] + 255) / 256), 256, 0, st>>>((const float4*)d, n[c], t12, dst); LAUNCH_CK();
+      S.n[c] += n[c];
+      continue;
+    }
+    // dynamic class: transform -> 1-NN distance test against the map's current dynamic cloud -> append the survivors
+    float4* moved = (float4*)(d + o_moved);
+    k_sm_transform<<<std::min(592, (n[c] + 255) / 256), 256, 0, st>>>((const float4*)d, n[c], t12, moved); LAUNCH_CK();
+    CloudIndex& ci = S.dyn_index;
+    rc = build_cloud_index(ctx, (const float4*)S.cls[0].p, S.n[0], cell_size_for_gate(1.0f), &ci);
+    if (rc) return rc;
+    const float dist_max = std::max(prm->dist_max, (float)((double)prm->dist_min + 0.1));             // :979
+    const float near2 = prm->near_dist * prm->near_dist, dmin2 = prm->dist_min * prm->dist_min, dmax2 = dist_max * dist_max;
+    float top = dmin2;
+    if (std::isfinite(dmax2) && dmax2 > top) top = dmax2;
+    if (near2 > top) top = near2;
+    const float gate = top * 1.000001f + 1e-12f;
+    unsigned char* keep = (unsigned char*)(d + o_keep);
+    uint32_t* flags = (uint32_t*)(d + o_flags);
+    uint32_t* bsums = (uint32_t*)(d + o_flags + ((sizeof(uint32_t) * ((size_t)n[c] + 1) + 255) & ~size_t(255)));
+    k_map_distance_filter<<<(n[c] + 127) / 128, 128, 0, st>>>(ci.g, moved, n[c], prm->center_radius * prm->center_radius, near2, dmin2, dmax2, gate, keep); LAUNCH_CK();
+    k_sm_widen_flags<<<(n[c] + 256) / 256, 256, 0, st>>>(keep, n[c], flags); LAUNCH_CK();
+    int kept = 0;
+    rc = compact_points(ctx, moved, n[c], flags, bsums, dst, &kept);
+    if (rc) return rc;
+    S.n[c] += kept;
+  }
+  // get_cloud_bbx over the five clouds (coordinates are floats: the double bounds upstream hold exactly these values)
+  CK(ctx->d_bbox.reserve(6 * sizeof(unsigned) + sizeof(GridDev)));
+  unsigned* bb = (unsigned*)ctx->d_bbox.p;
+  k_bbox_init<<<1, 32, 0, st>>>(bb); LAUNCH_CK();
+  bool any = false;
+  for (int c = 0; c < 5; c++) if (S.n[c] > 0) { k_bbox<<<std::min(1184, (S.n[c] + 255) / 256), 256, 0, st>>>((const float4*)S.cls[c].p, S.n[c], nullptr, bb); LAUNCH_CK(); any = true; }
+  unsigned hb[6];
+  CK(cudaMemcpyAsync(hb, bb, sizeof(hb), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int dd = 0; dd < 3; dd++) {
+    auto ord2f_h = [](unsigned u) { unsigned v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; float f; memcpy(&f, &v, 4); return f; };
+    S.bmin[dd] = any ? (double)ord2f_h(hb[dd]) : 1.7976931348623157e308;       // DBL_MAX / -DBL_MAX for an empty map, as upstream
+    S.bmax[dd] = any ? (double)ord2f_h(hb[3 + dd]) : -1.7976931348623157e308;
+  }
+  submap_fill_info(S, info);
+  return LISREG_OK;
+}
+
+int32_t lisreg_submap_extract(lisreg_ctx* ctx, int32_t submap_id, const float cur_pose6[6], const float leaf[LISREG_SUBMAP_CLASSES], float gate_hint,
+                              int32_t* map_id, lisreg_submap_info* info) {
+  SUBMAP_CK("lisreg_submap_extract");
+  if (!cur_pose6 || !map_id) return fail(ctx, LISREG_ERR_ARG, "lisreg_submap_extract: bad argument");
+  if (*map_id >= 0 && (*map_id >= (int)ctx->maps.size() || !ctx->maps[*map_id].used)) return fail(ctx, LISREG_ERR_ARG, "lisreg_submap_extract: bad map id");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->cur->stream;
+  lisreg_ctx::Submap& S = ctx->submaps[submap_id];
+  static const float kLeaf[5] = {0.1f, 0.05f, 0.4f, 0.2f, 0.6f};                      // subMapOptmizationNode.cpp:1393-1397
+  const float* lf = leaf ? leaf : kLeaf;
+  for (int c = 0; c < 5; c++) if (!(lf[c] > 0.f)) return fail(ctx, LISREG_ERR_ARG, "lisreg_submap_extract: leaf sizes must be > 0");
+  // sensor box moved by the current pose (transform_bbx: float matrix entries, double coordinates), intersected with the map box
+  float T[16]; odom_T16(cur_pose6, T);
+  const double bmin[3] = {-70.0, -70.0, -10.0}, bmax[3] = {70.0, 70.0, 20.0};
+  double cp[3], cpo[3];
+  for (int d = 0; d < 3; d++) cp[d] = 0.5 * (bmin[d] + bmax[d]);
+  for (int d = 0; d < 3; d++) cpo[d] = (double)T[4 * d] * cp[0] + (double)T[4 * d + 1] * cp[1] + (double)T[4 * d + 2] * cp[2] + (double)T[4 * d + 3];
+  SmBox box;
+  const float pad = 2.0f;
+  for (int d = 0; d < 3; d++) {
+    const double hi = bmax[d] - cp[d] + cpo[d], lo = bmin[d] - cp[d] + cpo[d];
+    box.lo[d] = std::max(lo, S.bmin[d]) - pad; box.hi[d] = std::min(hi, S.bmax[d]) + pad;
+  }
+  // ---- voxel filter of every class (one batched call), then the box filter back into the class buffers ----
+  int max_n = 0; size_t vox_total = 0; size_t vox_off[5];
+  for (int c = 0; c < 5; c++) { vox_off[c] = vox_total; vox_total += vox_seg_bytes(std::max(S.n[c], 1)); max_n = std::max(max_n, S.n[c]); }
+  CK(ctx->d_smvox.reserve(vox_total + sizeof(VoxSeg) * 5 + 256));
+  VoxSeg seg[5];
+  memset(seg, 0, sizeof(seg));
+  for (int c = 0; c < 5; c++) {
+    vox_carve((char*)ctx->d_smvox.p + vox_off[c], std::max(S.n[c], 1), &seg[c]);
+    seg[c].src = (const float4*)S.cls[c].p; seg[c].gather = nullptr; seg[c].n_ptr = nullptr; seg[c].n = S.n[c]; seg[c].leaf = lf[c];
+  }
+  VoxSeg* d_seg = (VoxSeg*)((char*)ctx->d_smvox.p + ((vox_total + 255) & ~size_t(255)));
+  CK(cudaMemcpyAsync(d_seg, seg, sizeof(seg), cudaMemcpyHostToDevice, st));
+  for (int c = 0; c < 5; c++) CK(cudaMemsetAsync(seg[c].out_n, 0, 4, st));
+  int rc = run_voxel(ctx, d_seg, 5, std::max(max_n, 1), 32.0 * (S.n[0] + S.n[1] + S.n[2] + S.n[3] + S.n[4]));
+  if (rc) return rc;
+  int vn[5];
+  for (int c = 0; c < 5; c++) CK(cudaMemcpyAsync(&vn[c], seg[c].out_n, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int c = 0; c < 5; c++) {
+    if (S.n[c] == 0) continue;                                                        // voxel_downsample_pcl leaves empty clouds alone
+    const int m = vn[c];
+    CK(ctx->d_stage.reserve(sm_flag_bytes(m) + 256));
+    uint32_t* flags = (uint32_t*)ctx->d_stage.p;
+    uint32_t* bsums = (uint32_t*)((char*)ctx->d_stage.p + ((sizeof(uint32_t) * ((size_t)m + 1) + 255) & ~size_t(255)));
+    k_sm_box_flags<<<(m + 256) / 256, 256, 0, st>>>(seg[c].out, m, box, flags); LAUNCH_CK();
+    int kept = 0;
+    rc = compact_points(ctx, seg[c].out, m, flags, bsums, (float4*)S.cls[c].p, &kept);
+    if (rc) return rc;
+    S.n[c] = kept;
+  }
+  // ---- registration map: corner = pole, surf = ground + building + dynamic ----
+  const int ns = S.n[2] + S.n[3] + S.n[0];
+  CK(ctx->d_smcat.reserve(sizeof(float4) * (size_t)std::max(ns, 1)));
+  size_t o = 0;
+  for (int c : {2, 3, 0}) {
+    if (S.n[c] > 0) CK(cudaMemcpyAsync((float4*)ctx->d_smcat.p + o, S.cls[c].p, sizeof(float4) * (size_t)S.n[c], cudaMemcpyDeviceToDevice, st));
+    o += (size_t)S.n[c];
+  }
+  int slot = *map_id;
+  if (slot < 0) { slot = map_alloc_slot(ctx); ctx->maps[slot] = MapSlot(); }
+  MapSlot& m = ctx->maps[slot];
+  const float h = cell_size_for_gate(gate_hint);
+  rc = build_cloud_index(ctx, (const float4*)S.cls[1].p, S.n[1], h, &m.corner);
+  if (rc) return rc;
+  rc = build_cloud_index(ctx, (const float4*)ctx->d_smcat.p, ns, h, &m.surf);
+  if (rc) return rc;
+  m.used = true;
+  ctx->maps_dirty = true;
+  *map_id = slot;
+  submap_fill_info(S, info);
+  if (info) { info->n_map_corner = S.n[1]; info->n_map_surf = ns; }
+  return sync_maps(ctx);
+}
+
+int32_t lisreg_submap_download(lisreg_ctx* ctx, int32_t submap_id, int32_t cls, float* out, int32_t cap, int32_t* n) {
+  SUBMAP_CK("lisreg_submap_download");
+  if (cls < 0 || cls >= 5 || !n) return fail(ctx, LISREG_ERR_ARG, "lisreg_submap_download: bad argument");
+  lisreg_ctx::Submap& S = ctx->submaps[submap_id];
+  *n = S.n[cls];
+  if (!out || cap < S.n[cls] || S.n[cls] == 0) return LISREG_OK;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(out, S.cls[cls].p, sizeof(float4) * (size_t)S.n[cls], cudaMemcpyDeviceToHost, ctx->cur->stream));
+  CK(cudaStreamSynchronize(ctx->cur->stream));
+  return LISREG_OK;
 }
 
 int32_t lisreg_scan2map(lisreg_ctx* ctx, int32_t map_id, const float* corner, const uint16_t* clabel, int32_t nc,

@@ -148,7 +148,55 @@ k_rs_hist(VoxSeg* segs, int shift, int flip) {
   s.hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
 }
 
-// (3b) exclusive scan over the 256 * nblk counters of one cloud: one block per cloud
+// (3b) exclusive scan over the 256 * nblk counters of one cloud (digit-major: hist[digit * nblk + tile]), in two steps so
+// that one 2 M-point cloud (the sliding-window map of the streaming odometry: 1000 tiles) is scanned by 256 warps instead
+// of one block:  k_rs_scan_digit - one WARP per digit: exclusive scan over the tiles of its digit, digit total -> dbase;
+// k_rs_scan_base - one warp per cloud: exclusive scan of the 256 digit totals.  k_rs_scatter adds dbase[digit].
+// dbase lives behind the histogram matrix: hist[256 * nblk_cap .. + 256).
+__device__ __forceinline__ int rs_nblk_cap(const VoxSeg& s) { return (s.cap + RS_TILE - 1) / RS_TILE + 1; }
+
+// grid = (32, nseg), block = 256 (8 warps = 8 digits per block)
+__global__ void __launch_bounds__(256)
+k_rs_scan_digit(VoxSeg* segs, int shift) {
+  const VoxSeg s = segs[blockIdx.y];
+  if (shift >= 8 * s.plan->npass) return;
+  const int n = vox_n(s);
+  const int nblk = (n + RS_TILE - 1) / RS_TILE;
+  const int lane = threadIdx.x & 31, d = blockIdx.x * 8 + (threadIdx.x >> 5);
+  uint32_t* __restrict__ h = s.hist + (size_t)d * nblk;
+  uint32_t carry = 0u;
+  for (int base = 0; base < nblk; base += 32) {
+    const int i = base + lane;
+    const uint32_t v = i < nblk ? h[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (i < nblk) h[i] = carry + incl - v;
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) s.hist[(size_t)256 * rs_nblk_cap(s) + d] = carry;
+}
+// grid = ceil(nseg / 8), block = 256: one warp per cloud
+__global__ void __launch_bounds__(256)
+k_rs_scan_base(VoxSeg* segs, int nseg, int shift) {
+  const int si = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (si >= nseg) return;
+  const VoxSeg s = segs[si];
+  if (shift >= 8 * s.plan->npass) return;
+  uint32_t* __restrict__ db = s.hist + (size_t)256 * rs_nblk_cap(s);
+  uint32_t carry = 0u;
+  for (int base = 0; base < 256; base += 32) {
+    const uint32_t v = db[base + lane];
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    db[base + lane] = carry + incl - v;
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+// (3b, many small clouds - the batched frame pipeline) exclusive scan over the 256 * nblk counters of one cloud by ONE block;
+// zeroes the digit bases so that k_rs_scatter can add them unconditionally
 __global__ void k_rs_scan(VoxSeg* segs, int shift) {
   const VoxSeg s = segs[blockIdx.x];
   if (shift >= 8 * s.plan->npass) return;
@@ -157,6 +205,7 @@ __global__ void k_rs_scan(VoxSeg* segs, int shift) {
   const int total = 256 * nblk;
   __shared__ uint32_t sm[1024];
   __shared__ uint32_t carry;
+  if (threadIdx.x < 256) s.hist[(size_t)256 * rs_nblk_cap(s) + threadIdx.x] = 0u;
   if (threadIdx.x == 0) carry = 0u;
   __syncthreads();
   for (int base = 0; base < total; base += 1024) {
@@ -212,7 +261,7 @@ k_rs_scatter(VoxSeg* segs, int shift, int flip) {
   // exclusive prefix over warps per digit + global base of this (digit, tile)
   {
     const int d = threadIdx.x;   // 256 threads == 256 digits
-    uint32_t acc = s.hist[d * nblk + blockIdx.x];
+    uint32_t acc = s.hist[d * nblk + blockIdx.x] + s.hist[(size_t)256 * rs_nblk_cap(s) + d];   // tile prefix inside the digit + digit base
 #pragma unroll
     for (int w = 0; w < NW; w++) { const uint32_t t = wh[w][d]; wh[w][d] = acc; acc += t; }
   }
@@ -237,7 +286,78 @@ k_rs_scatter(VoxSeg* segs, int shift, int flip) {
   }
 }
 
-// (4) voxel starts: one block (1024 threads) per cloud.  After npass passes the sorted data is in *_a (even) or *_b (odd).
+// (4) voxel starts (positions of the first entry of every voxel in the sorted arrays).  After npass passes the sorted
+// data is in *_a (even) or *_b (odd).  Three fully parallel steps (a 2 M-point map has 1000 chunks):
+//   k_vox_head_count  grid (chunks, nseg): heads per chunk of VH_CHUNK sorted keys -> hist[chunk] (the histogram matrix is free now)
+//   k_vox_head_scan   one warp per cloud: exclusive scan of the chunk counts, out_n, seg_start[out_n] = n
+//   k_vox_head_write  grid (chunks, nseg): rank of every head inside its chunk (ballot) + chunk offset -> seg_start
+constexpr int VH_CHUNK = RS_TILE;      // same tiling as the sort: (cap + RS_TILE - 1) / RS_TILE + 1 counters fit the histogram area
+__device__ __forceinline__ const uint32_t* vox_sorted_keys(const VoxSeg& s) { return (s.plan->npass & 1) ? s.key_b : s.key_a; }
+
+__global__ void __launch_bounds__(256)
+k_vox_head_count(VoxSeg* segs) {
+  const VoxSeg s = segs[blockIdx.y];
+  const int n = vox_n(s);
+  const int c0 = blockIdx.x * VH_CHUNK;
+  if (c0 >= n) return;
+  const uint32_t* __restrict__ skey = vox_sorted_keys(s);
+  int cnt = 0;
+  for (int i = c0 + threadIdx.x; i < min(c0 + VH_CHUNK, n); i += blockDim.x) cnt += (i == 0 || skey[i] != skey[i - 1]) ? 1 : 0;
+  __shared__ int s_w[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) t += s_w[w]; s.hist[blockIdx.x] = (uint32_t)t; }
+}
+// grid = ceil(nseg / 8), block = 256: one warp per cloud
+__global__ void __launch_bounds__(256)
+k_vox_head_scan(VoxSeg* segs, int nseg) {
+  const int si = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (si >= nseg) return;
+  const VoxSeg s = segs[si];
+  const int n = vox_n(s);
+  const int nchunk = (n + VH_CHUNK - 1) / VH_CHUNK;
+  uint32_t carry = 0u;
+  for (int base = 0; base < nchunk; base += 32) {
+    const int i = base + lane;
+    const uint32_t v = i < nchunk ? s.hist[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (i < nchunk) s.hist[i] = carry + incl - v;
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) { s.seg_start[carry] = n; *s.out_n = (int)carry; }
+}
+__global__ void __launch_bounds__(256)
+k_vox_head_write(VoxSeg* segs) {
+  const VoxSeg s = segs[blockIdx.y];
+  const int n = vox_n(s);
+  const int c0 = blockIdx.x * VH_CHUNK;
+  if (c0 >= n) return;
+  const uint32_t* __restrict__ skey = vox_sorted_keys(s);
+  __shared__ int s_w[8];
+  __shared__ int s_carry;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = (int)s.hist[blockIdx.x];
+  __syncthreads();
+  for (int base = c0; base < min(c0 + VH_CHUNK, n); base += 256) {
+    const int i = base + threadIdx.x;
+    const int head = (i < n && i < c0 + VH_CHUNK && (i == 0 || skey[i] != skey[i - 1])) ? 1 : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, head);
+    if (lane == 0) s_w[wid] = __popc(m);
+    __syncthreads();
+    int off = s_carry;
+    for (int w = 0; w < wid; w++) off += s_w[w];
+    if (head) s.seg_start[off + __popc(m & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) t += s_w[w]; s_carry += t; }
+    __syncthreads();
+  }
+}
+
+// (4, many small clouds) voxel starts: one block (1024 threads) per cloud.  After npass passes the sorted data is in *_a (even) or *_b (odd).
 __global__ void k_vox_heads(VoxSeg* segs) {
   const VoxSeg s = segs[blockIdx.x];
   const int n = vox_n(s);

@@ -107,6 +107,16 @@ class OdomResult(C.Structure):
                 ("map_rebuilt", C.c_int32), ("n_map_corner", C.c_int32), ("n_map_surf", C.c_int32), ("guess", C.c_float * 6)]
 
 
+class SubmapInsertParams(C.Structure):
+    _fields_ = [("dynamic_removal_on", C.c_int32), ("max_num_pts", C.c_int32), ("center_radius", C.c_float), ("dist_min", C.c_float),
+                ("dist_max", C.c_float), ("near_dist", C.c_float)]
+
+
+class SubmapInfo(C.Structure):
+    _fields_ = [("n", C.c_int32 * 5), ("feature_point_num", C.c_int32), ("bound_min", C.c_double * 3), ("bound_max", C.c_double * 3),
+                ("n_map_corner", C.c_int32), ("n_map_surf", C.c_int32)]
+
+
 class EpscCloud(C.Structure):
     _fields_ = [("corner", C.c_void_p), ("surf", C.c_void_p), ("sem", C.c_void_p), ("sem_label", C.c_void_p),
                 ("nc", C.c_int32), ("ns", C.c_int32), ("nsem", C.c_int32), ("reserved", C.c_int32)]
@@ -251,6 +261,18 @@ def lib():
         L.lisreg_odom_push.argtypes = [vp, i32, vp, vp, i32, vp, fp, C.POINTER(OdomResult)]
         L.lisreg_odom_push_dev.restype = i32
         L.lisreg_odom_push_dev.argtypes = [vp, i32, vp, vp, i32, vp, fp, C.POINTER(OdomResult)]
+        L.lisreg_submap_create.restype = i32
+        L.lisreg_submap_create.argtypes = [vp, C.POINTER(i32)]
+        L.lisreg_submap_destroy.restype = i32
+        L.lisreg_submap_destroy.argtypes = [vp, i32]
+        L.lisreg_submap_clear.restype = i32
+        L.lisreg_submap_clear.argtypes = [vp, i32]
+        L.lisreg_submap_insert.restype = i32
+        L.lisreg_submap_insert.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i32), fp, C.POINTER(SubmapInsertParams), C.POINTER(SubmapInfo)]
+        L.lisreg_submap_extract.restype = i32
+        L.lisreg_submap_extract.argtypes = [vp, i32, fp, fp, C.c_float, C.POINTER(i32), C.POINTER(SubmapInfo)]
+        L.lisreg_submap_download.restype = i32
+        L.lisreg_submap_download.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]
         L.lisreg_selftest_smallmat.restype = i32
         L.lisreg_selftest_smallmat.argtypes = [vp, fp, fp, fp]
         L.lisreg_selftest_alu_peak.restype = i32
@@ -524,6 +546,46 @@ class Engine:
         self.last_status = self._ck(lib().lisreg_odom_push_dev(self._h, oid, d_pts_ptr, d_ring_ptr, n, _ptr(ip),
                                                                pose.ctypes.data_as(C.POINTER(C.c_float)), C.byref(res)))
         return pose, res
+
+    # ---- device-resident local map / submap ----
+    def submap_create(self):
+        sid = C.c_int32(-1)
+        self._ck(lib().lisreg_submap_create(self._h, C.byref(sid)))
+        return sid.value
+
+    def submap_destroy(self, sid):
+        self._ck(lib().lisreg_submap_destroy(self._h, sid))
+
+    def submap_clear(self, sid):
+        self._ck(lib().lisreg_submap_clear(self._h, sid))
+
+    def submap_insert(self, sid, clouds5, pose6, dynrem=None, max_num_pts=20000):
+        """clouds5: five (n,4) arrays (dynamic, pole, ground, building, outlier); dynrem = None or
+        (center_radius, dist_min, dist_max, near).  Returns SubmapInfo."""
+        arrs = [_f4(np.asarray(c, np.float32).reshape(-1, 4)) for c in clouds5]
+        ptrs = (C.c_void_p * 5)(*[a.ctypes.data for a in arrs]); n = (C.c_int32 * 5)(*[len(a) for a in arrs])
+        pose = np.ascontiguousarray(pose6, np.float32); info = SubmapInfo()
+        prm = None
+        if dynrem:
+            prm = SubmapInsertParams(1, max_num_pts, dynrem[0], dynrem[1], dynrem[2], dynrem[3])
+        self._ck(lib().lisreg_submap_insert(self._h, sid, ptrs, n, pose.ctypes.data_as(C.POINTER(C.c_float)),
+                                            C.byref(prm) if prm else None, C.byref(info)))
+        return info
+
+    def submap_extract(self, sid, cur_pose6, leaf=None, gate_hint=2.0, map_id=-1):
+        pose = np.ascontiguousarray(cur_pose6, np.float32); info = SubmapInfo(); mid = C.c_int32(map_id)
+        lf = None if leaf is None else np.ascontiguousarray(leaf, np.float32)
+        self._ck(lib().lisreg_submap_extract(self._h, sid, pose.ctypes.data_as(C.POINTER(C.c_float)),
+                                             None if lf is None else lf.ctypes.data_as(C.POINTER(C.c_float)), gate_hint, C.byref(mid), C.byref(info)))
+        return mid.value, info
+
+    def submap_download(self, sid, cls):
+        n = C.c_int32(0)
+        self._ck(lib().lisreg_submap_download(self._h, sid, cls, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 4), np.float32)
+        if n.value:
+            self._ck(lib().lisreg_submap_download(self._h, sid, cls, out.ctypes.data, n.value, C.byref(n)))
+        return out
 
     def epsc_describe(self, clouds, using_map):
         """clouds: list of (corner (n,4), surf (n,4), sem (n,4), sem_label (n,)). Returns dict of (n,20,80) u8 arrays."""

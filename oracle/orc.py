@@ -377,3 +377,52 @@ def map_distance_filter(feat4, map4, center_radius=30.0, dyn_min=0.3, dyn_max=3.
     keep = np.zeros(len(f), np.uint8)
     lib().orc_map_distance_filter(fp_, len(f), mp, len(m), center_radius, dyn_min, dyn_max, near, keep.ctypes.data_as(C.POINTER(C.c_uint8)))
     return keep.astype(bool)
+
+
+class Submap:
+    """localMap_t / submap_t class clouds + insert_local_map + extractSlidingCloud (oracle/orc_submap.cpp)."""
+    LEAF = (0.1, 0.05, 0.4, 0.2, 0.6)          # dynamic, pole, ground, building, outlier (subMapOptmizationNode.cpp:1393-1397)
+
+    def __init__(self):
+        L = lib()
+        L.orc_submap_create.restype = C.c_void_p
+        L.orc_submap_free.argtypes = [C.c_void_p]; L.orc_submap_clear.argtypes = [C.c_void_p]
+        L.orc_submap_get.restype = C.c_int32
+        self.h = C.c_void_p(L.orc_submap_create())
+        self.bound = np.zeros(6, np.float64)
+
+    def close(self):
+        if self.h:
+            lib().orc_submap_free(self.h); self.h = None
+
+    def clear(self):
+        lib().orc_submap_clear(self.h)
+
+    def insert(self, clouds5, pose6, dynrem=None, max_num_pts=20000):
+        """clouds5: five (n,4) arrays; dynrem = None or (center_radius, dist_min, dist_max, near). Returns counts[5]."""
+        arrs = [np.ascontiguousarray(c, np.float32).reshape(-1, 4) for c in clouds5]
+        ptrs = (C.c_void_p * 5)(*[a.ctypes.data for a in arrs]); n = (C.c_int32 * 5)(*[len(a) for a in arrs])
+        pose = np.ascontiguousarray(pose6, np.float32); counts = (C.c_int32 * 5)()
+        dr = dynrem or (30.0, 0.3, 3.0, 0.03)
+        lib().orc_submap_insert(self.h, ptrs, n, pose.ctypes.data_as(C.c_void_p), C.c_int32(1 if dynrem else 0), C.c_int32(max_num_pts),
+                                C.c_float(dr[0]), C.c_float(dr[1]), C.c_float(dr[2]), C.c_float(dr[3]), counts, self.bound.ctypes.data_as(C.c_void_p))
+        return list(counts)
+
+    def extract(self, cur_pose6, leaf=None):
+        leaf = np.ascontiguousarray(leaf or self.LEAF, np.float32)
+        cap = sum(self.count(c) for c in range(5)) + 1
+        corner = np.zeros((cap, 4), np.float32); surf = np.zeros((cap, 4), np.float32)
+        nc, ns = C.c_int32(0), C.c_int32(0); counts = (C.c_int32 * 5)()
+        pose = np.ascontiguousarray(cur_pose6, np.float32)
+        lib().orc_submap_extract(self.h, pose.ctypes.data_as(C.c_void_p), leaf.ctypes.data_as(C.c_void_p), self.bound.ctypes.data_as(C.c_void_p),
+                                 corner.ctypes.data_as(C.c_void_p), C.byref(nc), surf.ctypes.data_as(C.c_void_p), C.byref(ns), counts)
+        return corner[:nc.value].copy(), surf[:ns.value].copy(), list(counts)
+
+    def count(self, c):
+        return lib().orc_submap_get(self.h, C.c_int32(c), None, C.c_int32(0))
+
+    def get(self, c):
+        n = self.count(c)
+        out = np.zeros((n, 4), np.float32)
+        lib().orc_submap_get(self.h, C.c_int32(c), out.ctypes.data_as(C.c_void_p), C.c_int32(n))
+        return out

@@ -119,6 +119,16 @@ int32_t orc_loop_detect(void* h, const float* corner4, int32_t nc, const float* 
 void orc_loop_project(const float* sem4, const uint16_t* label, int32_t n, float* out1440);
 void orc_loop_global_icp(const float* proj1, const float* proj2, float yaw_diff, float* T16);
 
+/* ---- local-map / submap assembly (subMap.h:435-777, :957-1055; subMapOptmizationNode.cpp:1369-1432) ---- */
+void* orc_submap_create();
+void orc_submap_free(void* h);
+void orc_submap_clear(void* h);
+void orc_submap_insert(void* h, const float* const* pts, const int32_t* n, const float* pose6, int32_t dynrem_on, int32_t max_num_pts,
+                       float center_radius, float dist_min, float dist_max, float near_dist, int32_t* counts, double* bound);
+void orc_submap_extract(void* h, const float* cur_pose6, const float* leaf5, const double* map_bound, float* corner_out, int32_t* nc,
+                        float* surf_out, int32_t* ns, int32_t* counts);
+int32_t orc_submap_get(void* h, int32_t c, float* out, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif
