@@ -198,6 +198,13 @@ typedef struct lisreg_feat_params {
   int32_t reserved;
   lisreg_cloud_layout layout;                 /* how `pts` is laid out (all-zero = packed float4 + ring array) */
 } lisreg_feat_params;
+typedef struct lisreg_deskew {
+  const double* imu_time;
+  const double* imu_rot;
+  int32_t n_imu;
+  int32_t reserved;
+  double time_scan_cur;
+} lisreg_deskew;
 /* presets: 0 packed float4 + ring array (16 + 2 B), 1 xyz float3 + ring array (12 + 2 B), 2 PCL PointXYZIRT records
  * (32 B, ring and time inside), 3 xyz float3 only, ring synthesised (12 B) */
 void lisreg_cloud_layout_preset(lisreg_cloud_layout* l, int32_t which);
@@ -221,16 +228,23 @@ int32_t lisreg_extract_features(lisreg_ctx* ctx, const float* pts, const uint16_
  * PointXYZIRT::time of input point i.  Range, column and every feature decision come from the ORIGINAL points
  * (as upstream); ext_xyzi (nullable, n_scan*horizon x float4) receives the de-skewed extracted cloud the index
  * lists refer to.  dsk == NULL or n_imu <= 0 = deskewFlag -1 / IMU unavailable (:429): points pass through. */
-typedef struct lisreg_deskew {
-  const double* imu_time;
-  const double* imu_rot;
-  int32_t n_imu;
-  int32_t reserved;
-  double time_scan_cur;
-} lisreg_deskew;
+/* (lisreg_deskew is declared with the feature parameters above) */
 int32_t lisreg_extract_features_deskew(lisreg_ctx* ctx, const float* pts, const uint16_t* ring, const float* time, int32_t n,
                                        const lisreg_feat_params* prm, const lisreg_deskew* dsk, lisreg_feat_out* out,
                                        float* ext_xyzi);
+
+/* ---- sweep pre-treatment in front of the feature extractor (SURVEY.md 8f "next" #3) ----
+ * lisreg_pretreat replaces the body of LaserPretreatment's cloud handler (laserPretreatmentNode.cpp:60-230, dup
+ * src/core/laserPretreatment.cpp:20-160) for sensors that deliver bare x, y, z, intensity: removeNaNFromPointCloud,
+ * removeClosedPointCloud(lidarMinRange, lidarMaxRange) (:244-272), PointXYZIRT::ring from the elevation angle (N_SCAN 16 /
+ * 32 / 64, :95-126) and PointXYZIRT::time = scanPeriod * relTime from the azimuth (:128-141; the sequential halfPassed
+ * flag is resolved with one atomicMin).  Outputs (capacity n each) keep the input order; *n_out = points kept.
+ * lisreg_deskew_constant_velocity replaces DistortionAdjust::AdjustCloud (distortionAdjust.cpp:419-479): every point but
+ * the first is moved by R(angular_rate * t) p + velocity * t with t = time - scan_period / 2; out holds n - 1 points. */
+int32_t lisreg_pretreat(lisreg_ctx* ctx, const float* pts, int32_t n, int32_t n_scan, double scan_period, float min_range, float max_range,
+                        float* pts_out, uint16_t* ring_out, float* time_out, int32_t* n_out);
+int32_t lisreg_deskew_constant_velocity(lisreg_ctx* ctx, const float* pts, const float* time, int32_t n, float scan_period,
+                                        const float lin_vel[3], const float ang_vel[3], float* out);
 
 /* ---- voxel-grid down-sampling (F6) ----
  * Replaces pcl::VoxelGrid<PointType>::filter as used by downSizeFilterCorner/Surf
@@ -247,6 +261,10 @@ typedef struct lisreg_frame_params {
   lisreg_feat_params feat;
   float corner_leaf, surf_leaf;     /* mappingCornerLeafSize 0.2, mappingSurfLeafSize 0.4 */
   lisreg_lm_params lm;
+  /* NULL, or one entry per frame of the batch: motion de-skew of projectPointCloud (laserProcessing.cpp:427-462, :501) with
+   * the frame's IMU rotation table (host pointers), exactly as lisreg_extract_features_deskew; the per-point time is read from
+   * the records (feat.layout.off_time >= 0, e.g. PointXYZIRT).  Not used by lisreg_odom_* (leave NULL there). */
+  const lisreg_deskew* deskew;
 } lisreg_frame_params;
 
 typedef struct lisreg_frame_item {

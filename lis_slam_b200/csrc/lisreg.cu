@@ -19,6 +19,7 @@
 #include "icp.cuh"
 #include "loop.cuh"
 #include "odom.cuh"
+#include "pretreat.cuh"
 
 using namespace lisreg;
 
@@ -71,10 +72,10 @@ struct MapSlot {
 struct WorkSet {
   cudaStream_t stream = nullptr;
   DevBuf d_descs, d_states, d_partials, d_nbr, d_kstate, d_klist, d_geom;
-  DevBuf d_feat, d_feat_frames, d_vox, d_vox_segs;
+  DevBuf d_feat, d_feat_frames, d_vox, d_vox_segs, d_imu;
   int feat_cap_frames = 0, feat_cells = 0, feat_nscan = 0;
   void release() {
-    for (DevBuf* b : {&d_descs, &d_states, &d_partials, &d_nbr, &d_kstate, &d_klist, &d_geom, &d_feat, &d_feat_frames, &d_vox, &d_vox_segs}) b->release();
+    for (DevBuf* b : {&d_descs, &d_states, &d_partials, &d_nbr, &d_kstate, &d_klist, &d_geom, &d_feat, &d_feat_frames, &d_vox, &d_vox_segs, &d_imu}) b->release();
   }
 };
 
@@ -1056,6 +1057,7 @@ void lisreg_frame_params_default(lisreg_frame_params* p) {
   lisreg_feat_params_default(&p->feat);
   p->corner_leaf = 0.2f; p->surf_leaf = 0.4f;       // config/params.yaml:132-133
   lisreg_lm_params_preset(&p->lm, 'A');
+  p->deskew = nullptr;
 }
 
 // d_pts_base/d_ring_base: if arena != nullptr the item pointers are byte offsets into it
@@ -1069,13 +1071,28 @@ static size_t frame_desc_bytes(int F) {
 // device-resident counts, so the results do not depend on it)
 static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, const char* d_arena, uint64_t arena_bytes,
                       float* d_pose, const lisreg_frame_params* prm, lisreg_lm_result* d_res, char* h_pinned = nullptr,
-                      int tiling_B = 0, int launch_n = 0) {
+                      int tiling_B = 0, int launch_n = 0, int frame_offset = 0) {
   cudaStream_t st = ctx->cur->stream;
   const lisreg_feat_params* fp = &prm->feat;
   if (fp->n_scan <= 0 || fp->horizon <= 0 || fp->horizon > 2048 || fp->n_scan * 6 > 1024 || fp->downsample_rate <= 0)
     return fail(ctx, LISREG_ERR_ARG, "frame pipeline: unsupported n_scan/horizon/downsample_rate");
   if (!(prm->corner_leaf > 0.f) || !(prm->surf_leaf > 0.f)) return fail(ctx, LISREG_ERR_ARG, "frame pipeline: leaf sizes must be > 0");
   if (!layout_ok(fp->layout, fp->n_scan)) return fail(ctx, LISREG_ERR_ARG, "frame pipeline: bad cloud layout");
+  // optional motion de-skew (projectPointCloud's deskewPoint, laserProcessing.cpp:427-462, :501): one IMU rotation table per
+  // frame, the per-point time read from the records
+  const lisreg_deskew* dsk = prm->deskew ? prm->deskew + frame_offset : nullptr;
+  size_t imu_doubles = 0;
+  if (dsk) {
+    if (!(fp->layout.point_step != 0 && fp->layout.off_time >= 0))
+      return fail(ctx, LISREG_ERR_ARG, "frame pipeline: de-skew needs the per-point time inside the records (layout.off_time)");
+    for (int i = 0; i < F; i++) {
+      if (dsk[i].n_imu < 0 || (dsk[i].n_imu > 0 && (!dsk[i].imu_time || !dsk[i].imu_rot))) return fail(ctx, LISREG_ERR_ARG, "frame %d: bad IMU table", i);
+      imu_doubles += 4 * (size_t)dsk[i].n_imu;
+    }
+    CK(ctx->cur->d_imu.reserve(sizeof(double) * std::max<size_t>(imu_doubles, 1)));
+  }
+  std::vector<double> h_imu(imu_doubles);
+  size_t imu_off = 0;
   const uint64_t rec = (uint64_t)layout_step(fp->layout);
   const bool ring_arr = layout_needs_ring_array(fp->layout);
   const size_t pts_align = fp->layout.point_step == 0 ? 15 : 3;
@@ -1111,6 +1128,13 @@ static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, co
     FeatFrame& f = hf[i];
     feat_carve((char*)ctx->cur->d_feat.p + feat_per * (size_t)i, cells, fp->n_scan, &f);
     f.pts = pts; f.ring = ring; f.n = it.n;
+    if (dsk && dsk[i].n_imu > 0) {
+      double* hd_t = h_imu.data() + imu_off; double* dd_t = (double*)ctx->cur->d_imu.p + imu_off;
+      memcpy(hd_t, dsk[i].imu_time, sizeof(double) * (size_t)dsk[i].n_imu);
+      memcpy(hd_t + dsk[i].n_imu, dsk[i].imu_rot, sizeof(double) * 3 * (size_t)dsk[i].n_imu);
+      f.imu_time = dd_t; f.imu_rot = dd_t + dsk[i].n_imu; f.n_imu = dsk[i].n_imu; f.t_scan = dsk[i].time_scan_cur;
+      imu_off += 4 * (size_t)dsk[i].n_imu;
+    }
     VoxSeg& vc = hv[2 * i]; VoxSeg& vs = hv[2 * i + 1];
     char* vb = (char*)ctx->cur->d_vox.p + (vc_per + vs_per) * (size_t)i;
     vox_carve(vb, ccap, &vc); vox_carve(vb + vc_per, cells, &vs);
@@ -1126,7 +1150,8 @@ static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, co
   CK(cudaMemcpyAsync(ctx->cur->d_feat_frames.p, hf, sizeof(FeatFrame) * (size_t)F, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->cur->d_vox_segs.p, hv, sizeof(VoxSeg) * 2 * (size_t)F, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->cur->d_descs.p, hd, sizeof(RegDesc) * (size_t)F, cudaMemcpyHostToDevice, st));
-  rc = run_features(ctx, (FeatFrame*)ctx->cur->d_feat_frames.p, F, fp, max_n, feat_bytes);
+  if (imu_doubles) CK(cudaMemcpyAsync(ctx->cur->d_imu.p, h_imu.data(), sizeof(double) * imu_doubles, cudaMemcpyHostToDevice, st));   // pageable: consumed on return
+  rc = run_features(ctx, (FeatFrame*)ctx->cur->d_feat_frames.p, F, fp, max_n, feat_bytes, dsk != nullptr);
   if (rc) return rc;
   rc = run_voxel(ctx, (VoxSeg*)ctx->cur->d_vox_segs.p, 2 * F, std::min(max_n, cells), 2.0 * feat_bytes);
   if (rc) return rc;
@@ -1222,7 +1247,7 @@ int32_t lisreg_frames_batch_arena(lisreg_ctx* ctx, int32_t F, const lisreg_frame
       cudaError_t e = cudaStreamWaitEvent(ctx->cur->stream, ctx->chunk_ev[c], 0);
       if (e != cudaSuccess) rc = fail(ctx, LISREG_ERR_CUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
       else rc = run_frames(ctx, fc, items + f0, d_arena, arena_bytes, d_pose + 6 * (size_t)f0, prm, d_res + f0,
-                           (char*)ctx->h_desc.p + desc_per * (size_t)c, F);
+                           (char*)ctx->h_desc.p + desc_per * (size_t)c, F, 0, f0);
     }
     ctx->cur = &ctx->ws[0];
     // join: the context stream continues after both chunk streams
@@ -2334,6 +2359,67 @@ int32_t lisreg_submap_download(lisreg_ctx* ctx, int32_t submap_id, int32_t cls, 
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpyAsync(out, S.cls[cls].p, sizeof(float4) * (size_t)S.n[cls], cudaMemcpyDeviceToHost, ctx->cur->stream));
   CK(cudaStreamSynchronize(ctx->cur->stream));
+  return LISREG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sweep pre-treatment (SURVEY.md 8f "next" #3)
+// ------------------------------------------------------------------------------------------------
+int32_t lisreg_pretreat(lisreg_ctx* ctx, const float* pts, int32_t n, int32_t n_scan, double scan_period, float min_range, float max_range,
+                        float* pts_out, uint16_t* ring_out, float* time_out, int32_t* n_out) {
+  if (!ctx || n < 0 || (n > 0 && (!pts || !pts_out || !ring_out || !time_out)) || !n_out) return fail(ctx, LISREG_ERR_ARG, "lisreg_pretreat: bad argument");
+  if (!(n_scan == 16 || n_scan == 32 || n_scan == 64)) return fail(ctx, LISREG_ERR_ARG, "lisreg_pretreat: N_SCAN must be 16, 32 or 64 (laserPretreatmentNode.cpp:98-126)");
+  *n_out = 0;
+  if (n == 0) return LISREG_OK;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->cur->stream;
+  const size_t bp = (sizeof(float4) * (size_t)n + 255) & ~size_t(255), bf = (sizeof(uint32_t) * ((size_t)n + 1) + 255) & ~size_t(255);
+  const size_t o_cloud = bp, o_out = 2 * bp, o_flags = 3 * bp, o_bs = o_flags + bf, o_ring = o_bs + sm_flag_bytes(n), o_time = o_ring + ((2 * (size_t)n + 255) & ~size_t(255)),
+               o_ori = o_time + ((4 * (size_t)n + 255) & ~size_t(255)), total = o_ori + 256;
+  CK(ctx->d_stage.reserve(total));
+  char* d = (char*)ctx->d_stage.p;
+  CK(cudaMemcpyAsync(d, pts, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
+  uint32_t* flags = (uint32_t*)(d + o_flags); uint32_t* bsums = (uint32_t*)(d + o_bs);
+  float4* cloud = (float4*)(d + o_cloud); float4* out = (float4*)(d + o_out);
+  k_pt_flags_range<<<(n + 256) / 256, 256, 0, st>>>((const float4*)d, n, min_range, max_range, flags); LAUNCH_CK();
+  int m = 0;
+  int rc = compact_points(ctx, (const float4*)d, n, flags, bsums, cloud, &m);
+  if (rc) return rc;
+  if (m == 0) return LISREG_OK;
+  PtOri* ori = (PtOri*)(d + o_ori);
+  k_pt_ori<<<1, 1, 0, st>>>(cloud, m, ori); LAUNCH_CK();
+  k_pt_ring_cond<<<(m + 256) / 256, 256, 0, st>>>(cloud, m, n_scan, ori, flags); LAUNCH_CK();
+  rc = scan_u32(ctx, flags, m + 1, bsums);
+  if (rc) return rc;
+  k_pt_emit<<<(m + 255) / 256, 256, 0, st>>>(cloud, m, n_scan, scan_period, ori, flags, out, (uint16_t*)(d + o_ring), (float*)(d + o_time)); LAUNCH_CK();
+  uint32_t cnt = 0;
+  CK(cudaMemcpyAsync(&cnt, flags + m, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (cnt) {
+    CK(cudaMemcpyAsync(pts_out, out, sizeof(float4) * (size_t)cnt, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ring_out, d + o_ring, sizeof(uint16_t) * (size_t)cnt, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(time_out, d + o_time, sizeof(float) * (size_t)cnt, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  *n_out = (int32_t)cnt;
+  return LISREG_OK;
+}
+
+int32_t lisreg_deskew_constant_velocity(lisreg_ctx* ctx, const float* pts, const float* time, int32_t n, float scan_period,
+                                        const float lin_vel[3], const float ang_vel[3], float* out) {
+  if (!ctx || n < 0 || (n > 1 && (!pts || !time || !out)) || !lin_vel || !ang_vel) return fail(ctx, LISREG_ERR_ARG, "lisreg_deskew_constant_velocity: bad argument");
+  if (n <= 1) return LISREG_OK;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->cur->stream;
+  const size_t bp = (sizeof(float4) * (size_t)n + 255) & ~size_t(255), bt = (sizeof(float) * (size_t)n + 255) & ~size_t(255);
+  CK(ctx->d_stage.reserve(2 * bp + bt));
+  char* d = (char*)ctx->d_stage.p;
+  CK(cudaMemcpyAsync(d, pts, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + bp, time, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+  PtMotion mo; for (int k = 0; k < 3; k++) { mo.v[k] = lin_vel[k]; mo.w[k] = ang_vel[k]; } mo.scan_period = scan_period;
+  k_deskew_cv<<<(n - 1 + 255) / 256, 256, 0, st>>>((const float4*)d, (const float*)(d + bp), n, mo, (float4*)(d + bp + bt)); LAUNCH_CK();
+  CK(cudaMemcpyAsync(out, d + bp + bt, sizeof(float4) * (size_t)(n - 1), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return LISREG_OK;
 }
 

@@ -90,7 +90,7 @@ class FeatOut(C.Structure):
 
 
 class FrameParams(C.Structure):
-    _fields_ = [("feat", FeatParams), ("corner_leaf", C.c_float), ("surf_leaf", C.c_float), ("lm", LmParams)]
+    _fields_ = [("feat", FeatParams), ("corner_leaf", C.c_float), ("surf_leaf", C.c_float), ("lm", LmParams), ("deskew", C.c_void_p)]
 
 
 class FrameItem(C.Structure):
@@ -273,6 +273,10 @@ def lib():
         L.lisreg_submap_extract.argtypes = [vp, i32, fp, fp, C.c_float, C.POINTER(i32), C.POINTER(SubmapInfo)]
         L.lisreg_submap_download.restype = i32
         L.lisreg_submap_download.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]
+        L.lisreg_pretreat.restype = i32
+        L.lisreg_pretreat.argtypes = [vp, vp, i32, i32, C.c_double, C.c_float, C.c_float, vp, vp, vp, C.POINTER(i32)]
+        L.lisreg_deskew_constant_velocity.restype = i32
+        L.lisreg_deskew_constant_velocity.argtypes = [vp, vp, vp, i32, C.c_float, fp, fp, vp]
         L.lisreg_selftest_smallmat.restype = i32
         L.lisreg_selftest_smallmat.argtypes = [vp, fp, fp, fp]
         L.lisreg_selftest_alu_peak.restype = i32
@@ -476,6 +480,23 @@ class Engine:
         res["corner_idx"] = a["corner_idx"][:out.n_corner]; res["sharp_idx"] = a["sharp_idx"][:out.n_sharp]
         res["flat_idx"] = a["flat_idx"][:out.n_flat]; res["surf_idx"] = a["surf_idx"][:out.n_surf]
         return res
+
+    def pretreat(self, pts, n_scan, scan_period=0.1, min_range=0.0, max_range=70.0):
+        """Ring / time synthesis (lisreg_pretreat). Returns (pts (m,4), ring (m,) u16, time (m,) f32)."""
+        p = _f4(pts); n = len(p)
+        out = np.zeros((n, 4), np.float32); ring = np.zeros(n, np.uint16); t = np.zeros(n, np.float32); m = C.c_int32(0)
+        self._ck(lib().lisreg_pretreat(self._h, p.ctypes.data, n, n_scan, scan_period, min_range, max_range, out.ctypes.data, ring.ctypes.data,
+                                       t.ctypes.data, C.byref(m)))
+        return out[:m.value].copy(), ring[:m.value].copy(), t[:m.value].copy()
+
+    def deskew_cv(self, pts, time, scan_period, lin_vel, ang_vel):
+        p = _f4(pts); t = np.ascontiguousarray(time, np.float32)
+        lv = np.ascontiguousarray(lin_vel, np.float32); av = np.ascontiguousarray(ang_vel, np.float32)
+        out = np.zeros((max(len(p) - 1, 0), 4), np.float32)
+        f = C.POINTER(C.c_float)
+        self._ck(lib().lisreg_deskew_constant_velocity(self._h, p.ctypes.data, t.ctypes.data, len(p), scan_period, lv.ctypes.data_as(f),
+                                                       av.ctypes.data_as(f), out.ctypes.data))
+        return out
 
     def voxel_grid(self, pts, leaf):
         p = _f4(pts)

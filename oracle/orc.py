@@ -426,3 +426,24 @@ class Submap:
         out = np.zeros((n, 4), np.float32)
         lib().orc_submap_get(self.h, C.c_int32(c), out.ctypes.data_as(C.c_void_p), C.c_int32(n))
         return out
+
+
+def pretreat(pts4, n_scan, scan_period=0.1, min_range=0.0, max_range=70.0):
+    """Ring / time synthesis (laserPretreatmentNode.cpp:60-230). Returns (pts (m,4), ring (m,) u16, time (m,) f32)."""
+    p, pp = _f(pts4)
+    out = np.zeros((len(p), 4), np.float32); ring = np.zeros(len(p), np.uint16); t = np.zeros(len(p), np.float32)
+    L = lib(); L.orc_pretreat.restype = C.c_int32
+    m = L.orc_pretreat(pp, C.c_int32(len(p)), C.c_int32(n_scan), C.c_double(scan_period), C.c_float(min_range), C.c_float(max_range),
+                       out.ctypes.data_as(C.c_void_p), ring.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p))
+    return out[:m].copy(), ring[:m].copy(), t[:m].copy()
+
+
+def deskew_cv(pts4, time, scan_period, lin_vel, ang_vel):
+    """DistortionAdjust::AdjustCloud (distortionAdjust.cpp:419-479). Returns (n - 1, 4)."""
+    p, pp = _f(pts4)
+    t = np.ascontiguousarray(time, np.float32); lv = np.ascontiguousarray(lin_vel, np.float32); av = np.ascontiguousarray(ang_vel, np.float32)
+    out = np.zeros((max(len(p) - 1, 0), 4), np.float32)
+    L = lib(); L.orc_deskew_cv.restype = C.c_int32
+    m = L.orc_deskew_cv(pp, t.ctypes.data_as(C.c_void_p), C.c_int32(len(p)), C.c_float(scan_period), lv.ctypes.data_as(C.c_void_p),
+                        av.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out[:m]

@@ -119,6 +119,11 @@ int32_t orc_loop_detect(void* h, const float* corner4, int32_t nc, const float* 
 void orc_loop_project(const float* sem4, const uint16_t* label, int32_t n, float* out1440);
 void orc_loop_global_icp(const float* proj1, const float* proj2, float yaw_diff, float* T16);
 
+/* ---- sweep pre-treatment: ring / time synthesis (laserPretreatmentNode.cpp:60-230), constant-velocity de-skew (distortionAdjust.cpp:419-479) ---- */
+int32_t orc_pretreat(const float* pts4, int32_t n, int32_t n_scan, double scan_period, float min_range, float max_range,
+                     float* out4, uint16_t* ring_out, float* time_out);
+int32_t orc_deskew_cv(const float* pts4, const float* time, int32_t n, float scan_period, const float* lin_vel3, const float* ang_vel3, float* out4);
+
 /* ---- local-map / submap assembly (subMap.h:435-777, :957-1055; subMapOptmizationNode.cpp:1369-1432) ---- */
 void* orc_submap_create();
 void orc_submap_free(void* h);
