@@ -470,6 +470,37 @@ int32_t lisreg_comm_destroy(lisreg_ctx* ctx);
 int32_t lisreg_allgather_results(lisreg_ctx* ctx, const void* d_send, void* d_recv, uint64_t bytes_per_rank);
 int32_t lisreg_allgather_wait(lisreg_ctx* ctx);
 
+/* ---- loop-closure verification against candidate submaps (B4: the whole of detectLoopClosureForSubMap) ----
+ * Replaces SubMapOdometryNode::detectLoopClosureForSubMap (subMapOptmizationNode.cpp:2739-2916) on top of the
+ * device-resident submaps: for every candidate submap i the initial alignment key2PreSubMapTrans is composed
+ * (EPSC: T(keyframe_poses_6D_map[loopKeyPreLast[i]]) * curKey2PreKeyInitTrans[i], :2797-2803; pose-based:
+ * T(submap_pose_6D_optimized)^-1 * T(cur_keyframe->optimized_pose), :2807-2809), the key-frame cloud (dynamic + pole +
+ * ground + building, sensor frame) is moved by it (transformPointCloud, :2822-2824) and ICP-aligned to the candidate's
+ * dynamic + pole + ground + building cloud (:2785-2790, settings :2763-2769) - all candidates in one batch; the best
+ * converged candidate by getFitnessScore wins (:2835-2842) and is accepted iff its score <= fitness_threshold
+ * (historyKeyframeFitnessScore, :2855); the loop constraint tCorrect = correctionLidarFrame * key2PreSubMapTrans *
+ * T(cur_keyframe->relative_pose)^-1 and its X, Y, Z, ROLL, PITCH, YAW (:2874-2878) are returned (poseFrom of the GTSAM
+ * between-factor; GTSAM itself stays upstream).  The ICP target index of a submap is cached until the submap changes. */
+typedef struct lisreg_loop_candidate {
+  int32_t submap_id;            /* lisreg_submap of loopSubMapPre[i] */
+  int32_t use_epsc_init;        /* 1: EPSC initial pose (:2797-2803); 0: pose-based (:2807-2809) */
+  float prekey_pose6[6];        /* keyframe_poses_6D_map[loopKeyPreLast[i]]  [roll, pitch, yaw, x, y, z] */
+  float epsc_T[16];             /* curKey2PreKeyInitTrans[i], row-major 4x4 (lisreg_loop_match.T) */
+  float submap_pose6[6];        /* submap_pose_6D_optimized */
+} lisreg_loop_candidate;
+typedef struct lisreg_loop_verify_result {
+  int32_t found;                /* the reference's return value */
+  int32_t best;                 /* bestID: index into the candidate array, -1 = no candidate converged */
+  double best_score;            /* bestScore */
+  float correction[16];         /* correctionLidarFrame (getFinalTransformation of the best candidate) */
+  float key2pre[16];            /* key2PreSubMapTrans of the best candidate */
+  float t_correct[16];          /* tCorrect */
+  float constraint6[6];         /* X, Y, Z, ROLL, PITCH, YAW of tCorrect */
+} lisreg_loop_verify_result;
+int32_t lisreg_loop_verify(lisreg_ctx* ctx, const float* key_cloud, int32_t n, const float key_pose6[6], const float key_rel_pose6[6],
+                           int32_t P, const lisreg_loop_candidate* cand, float fitness_threshold, const lisreg_icp_params* prm,
+                           lisreg_loop_verify_result* out, lisreg_icp_result* per_candidate /* nullable, P entries */);
+
 /* device self-test of the small dense routines (cv::eigen / cv::solve(QR) / cv::Mat::inv restatements):
  * out98 = E[6], V[36] (eigenvectors in rows), X[6] (QR solve of A x = b), ok, Ainv[36] (LU), ok,
  * then W3[3], V3[9] of the register-only 3x3 Jacobi applied to the leading 3x3 block of A */

@@ -139,6 +139,7 @@ struct lisreg_ctx {
     DevBuf cls[5]; int n[5] = {0, 0, 0, 0, 0};
     double bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
     CloudIndex dyn_index;                  // scratch index of the dynamic cloud (map-based dynamic removal)
+    int icp_slot = -1; bool icp_dirty = true;   // cached ICP target (map slot) of lisreg_loop_verify
   };
   std::vector<Submap> submaps;
   DevBuf d_smvox, d_smcat;
@@ -1604,38 +1605,24 @@ int32_t lisreg_loop_detect(lisreg_ctx* ctx, int32_t det_id, const float* corner,
 // ------------------------------------------------------------------------------------------------
 void lisreg_icp_params_default(lisreg_icp_params* p) { p->max_corr_dist = 10.f; p->max_iters = 30; p->trans_eps = 1e-4; p->fitness_eps = 1e-4; }
 
-int32_t lisreg_icp_verify_batch(lisreg_ctx* ctx, int32_t P, const lisreg_icp_pair* pairs, const lisreg_icp_params* prm,
-                                lisreg_icp_result* out) {
-  if (!ctx || P <= 0 || !pairs || !prm || !out || prm->max_iters <= 0) return fail(ctx, LISREG_ERR_ARG, "lisreg_icp_verify_batch: bad argument");
-  CK(cudaSetDevice(ctx->device));
+// ICP of P pairs whose (pre-transformed) sources already sit in ctx->d_stage at byte offsets off[i] (256-byte aligned slots of
+// a region of src_bytes bytes): work copies, per-iteration correspondence + solve launches, results to the host
+static int icp_run_dev(lisreg_ctx* ctx, int P, const std::vector<size_t>& off, const std::vector<int>& ns, const std::vector<int>& tgt,
+                       size_t src_bytes, const lisreg_icp_params* prm, lisreg_icp_result* out) {
   cudaStream_t st = ctx->stream;
   int rc = sync_maps(ctx);
   if (rc) return rc;
   auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
-  size_t src_bytes = 0; int max_ns = 0;
-  for (int i = 0; i < P; i++) {
-    const lisreg_icp_pair& pr = pairs[i];
-    if (pr.ns < 0 || (pr.ns > 0 && !pr.src) || pr.target_id < 0 || pr.target_id >= (int)ctx->maps.size() || !ctx->maps[pr.target_id].used)
-      return fail(ctx, LISREG_ERR_ARG, "icp pair %d: bad size, pointer or target id", i);
-    src_bytes += al(16 * (size_t)pr.ns); max_ns = std::max(max_ns, pr.ns);
-  }
+  int max_ns = 0;
+  for (int i = 0; i < P; i++) max_ns = std::max(max_ns, ns[i]);
   const int nblk = std::max(1, std::min(64, (max_ns + ICP_THREADS - 1) / ICP_THREADS));
   const size_t o_pairs = 0, o_states = al(sizeof(IcpPair) * (size_t)P), o_part = o_states + al(sizeof(IcpState) * (size_t)P),
                o_res = o_part + al(sizeof(double) * ICP_NSUM * (size_t)P * nblk), o_cur = o_res + al(sizeof(lisreg_icp_result) * (size_t)P);
   CK(ctx->d_icp.reserve(o_cur + src_bytes));
-  CK(ctx->h_stage.reserve(src_bytes + al(sizeof(IcpPair) * (size_t)P)));
-  CK(ctx->d_stage.reserve(src_bytes + 256));
-  char* h = (char*)ctx->h_stage.p; char* dsrc = (char*)ctx->d_stage.p; char* d = (char*)ctx->d_icp.p;
-  IcpPair* hp = (IcpPair*)(h + src_bytes);
-  size_t off = 0;
-  for (int i = 0; i < P; i++) {
-    const lisreg_icp_pair& pr = pairs[i];
-    if (pr.ns) memcpy(h + off, pr.src, 16 * (size_t)pr.ns);
-    hp[i].src = (const float4*)(dsrc + off); hp[i].ns = pr.ns; hp[i].cur = (float4*)(d + o_cur + off); hp[i].tgt_slot = pr.target_id; hp[i].pad = 0;
-    off += al(16 * (size_t)pr.ns);
-  }
-  if (src_bytes) CK(cudaMemcpyAsync(dsrc, h, src_bytes, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d + o_pairs, hp, sizeof(IcpPair) * (size_t)P, cudaMemcpyHostToDevice, st));
+  char* dsrc = (char*)ctx->d_stage.p; char* d = (char*)ctx->d_icp.p;
+  std::vector<IcpPair> hp((size_t)P);
+  for (int i = 0; i < P; i++) { hp[i].src = (const float4*)(dsrc + off[i]); hp[i].ns = ns[i]; hp[i].cur = (float4*)(d + o_cur + off[i]); hp[i].tgt_slot = tgt[i]; hp[i].pad = 0; }
+  CK(cudaMemcpyAsync(d + o_pairs, hp.data(), sizeof(IcpPair) * (size_t)P, cudaMemcpyHostToDevice, st));   // pageable: consumed on return
   IcpPair* dp = (IcpPair*)(d + o_pairs); IcpState* ds = (IcpState*)(d + o_states); double* part = (double*)(d + o_part);
   lisreg_icp_result* dres = (lisreg_icp_result*)(d + o_res);
   IcpParamsDev kp{prm->max_corr_dist * prm->max_corr_dist, prm->max_iters, 1.0 - prm->trans_eps, prm->trans_eps, prm->fitness_eps};
@@ -1651,6 +1638,29 @@ int32_t lisreg_icp_verify_batch(lisreg_ctx* ctx, int32_t P, const lisreg_icp_pai
   CK(cudaMemcpyAsync(out, dres, sizeof(lisreg_icp_result) * (size_t)P, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return LISREG_OK;
+}
+
+int32_t lisreg_icp_verify_batch(lisreg_ctx* ctx, int32_t P, const lisreg_icp_pair* pairs, const lisreg_icp_params* prm,
+                                lisreg_icp_result* out) {
+  if (!ctx || P <= 0 || !pairs || !prm || !out || prm->max_iters <= 0) return fail(ctx, LISREG_ERR_ARG, "lisreg_icp_verify_batch: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+  size_t src_bytes = 0;
+  std::vector<size_t> off((size_t)P); std::vector<int> ns((size_t)P), tgt((size_t)P);
+  for (int i = 0; i < P; i++) {
+    const lisreg_icp_pair& pr = pairs[i];
+    if (pr.ns < 0 || (pr.ns > 0 && !pr.src) || pr.target_id < 0 || pr.target_id >= (int)ctx->maps.size() || !ctx->maps[pr.target_id].used)
+      return fail(ctx, LISREG_ERR_ARG, "icp pair %d: bad size, pointer or target id", i);
+    off[i] = src_bytes; ns[i] = pr.ns; tgt[i] = pr.target_id;
+    src_bytes += al(16 * (size_t)pr.ns);
+  }
+  CK(ctx->h_stage.reserve(src_bytes + 256));
+  CK(ctx->d_stage.reserve(src_bytes + 256));
+  char* h = (char*)ctx->h_stage.p;
+  for (int i = 0; i < P; i++) if (pairs[i].ns) memcpy(h + off[i], pairs[i].src, 16 * (size_t)pairs[i].ns);
+  if (src_bytes) CK(cudaMemcpyAsync(ctx->d_stage.p, h, src_bytes, cudaMemcpyHostToDevice, st));
+  return icp_run_dev(ctx, P, off, ns, tgt, src_bytes, prm, out);
 }
 
 int32_t lisreg_selftest_smallmat(lisreg_ctx* ctx, const float* A36, const float* b6, float* out98) {
@@ -2174,6 +2184,7 @@ int32_t lisreg_submap_destroy(lisreg_ctx* ctx, int32_t submap_id) {
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   for (auto& b : ctx->submaps[submap_id].cls) b.release();
+  if (ctx->submaps[submap_id].icp_slot >= 0) lisreg_map_destroy(ctx, ctx->submaps[submap_id].icp_slot);
   cudaFree(ctx->submaps[submap_id].dyn_index.sorted); cudaFree(ctx->submaps[submap_id].dyn_index.cell_start);
   ctx->submaps[submap_id] = lisreg_ctx::Submap();
   return LISREG_OK;
@@ -2183,6 +2194,7 @@ int32_t lisreg_submap_clear(lisreg_ctx* ctx, int32_t submap_id) {
   lisreg_ctx::Submap& S = ctx->submaps[submap_id];
   for (int c = 0; c < 5; c++) S.n[c] = 0;
   for (int d = 0; d < 3; d++) { S.bmin[d] = 0; S.bmax[d] = 0; }
+  S.icp_dirty = true;
   return LISREG_OK;
 }
 static void submap_fill_info(const lisreg_ctx::Submap& S, lisreg_submap_info* info) {
@@ -2213,6 +2225,7 @@ int32_t lisreg_submap_insert(lisreg_ctx* ctx, int32_t submap_id, const float* co
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->cur->stream;
   lisreg_ctx::Submap& S = ctx->submaps[submap_id];
+  S.icp_dirty = true;
   float T[16]; odom_T16(pose6, T);
   OdomT12 t12; for (int i = 0; i < 12; i++) t12.m[i] = T[i];
   int feature_point_num = 0;
@@ -2281,6 +2294,7 @@ int32_t lisreg_submap_extract(lisreg_ctx* ctx, int32_t submap_id, const float cu
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->cur->stream;
   lisreg_ctx::Submap& S = ctx->submaps[submap_id];
+  S.icp_dirty = true;
   static const float kLeaf[5] = {0.1f, 0.05f, 0.4f, 0.2f, 0.6f};                      // subMapOptmizationNode.cpp:1393-1397
   const float* lf = leaf ? leaf : kLeaf;
   for (int c = 0; c < 5; c++) if (!(lf[c] > 0.f)) return fail(ctx, LISREG_ERR_ARG, "lisreg_submap_extract: leaf sizes must be > 0");
@@ -2420,6 +2434,86 @@ int32_t lisreg_deskew_constant_velocity(lisreg_ctx* ctx, const float* pts, const
   k_deskew_cv<<<(n - 1 + 255) / 256, 256, 0, st>>>((const float4*)d, (const float*)(d + bp), n, mo, (float4*)(d + bp + bt)); LAUNCH_CK();
   CK(cudaMemcpyAsync(out, d + bp + bt, sizeof(float4) * (size_t)(n - 1), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return LISREG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// loop-closure verification against candidate submaps (B4)
+// ------------------------------------------------------------------------------------------------
+// ICP target of a submap = dynamic + pole + ground + building (subMapOptmizationNode.cpp:2785-2790), indexed once per change
+static int submap_icp_target(lisreg_ctx* ctx, lisreg_ctx::Submap& S, int* slot_out) {
+  cudaStream_t st = ctx->cur->stream;
+  if (S.icp_slot >= 0 && !S.icp_dirty) { *slot_out = S.icp_slot; return LISREG_OK; }
+  const int nt = S.n[0] + S.n[1] + S.n[2] + S.n[3];
+  CK(ctx->d_smcat.reserve(sizeof(float4) * (size_t)std::max(nt, 1)));
+  size_t o = 0;
+  for (int c = 0; c < 4; c++) {
+    if (S.n[c] > 0) CK(cudaMemcpyAsync((float4*)ctx->d_smcat.p + o, S.cls[c].p, sizeof(float4) * (size_t)S.n[c], cudaMemcpyDeviceToDevice, st));
+    o += (size_t)S.n[c];
+  }
+  if (S.icp_slot < 0) { S.icp_slot = map_alloc_slot(ctx); ctx->maps[S.icp_slot] = MapSlot(); ctx->maps[S.icp_slot].used = true; }
+  MapSlot& m = ctx->maps[S.icp_slot];
+  int rc = build_cloud_index(ctx, nullptr, 0, 1.0f, &m.corner);
+  if (rc) return rc;
+  rc = build_cloud_index(ctx, (const float4*)ctx->d_smcat.p, nt, cell_size_for_gate(4.0f), &m.surf);
+  if (rc) return rc;
+  m.used = true; ctx->maps_dirty = true; S.icp_dirty = false;
+  *slot_out = S.icp_slot;
+  return LISREG_OK;
+}
+
+int32_t lisreg_loop_verify(lisreg_ctx* ctx, const float* key_cloud, int32_t n, const float key_pose6[6], const float key_rel_pose6[6],
+                           int32_t P, const lisreg_loop_candidate* cand, float fitness_threshold, const lisreg_icp_params* prm,
+                           lisreg_loop_verify_result* out, lisreg_icp_result* per_candidate) {
+  if (!ctx || n < 0 || (n > 0 && !key_cloud) || !key_pose6 || !key_rel_pose6 || P < 0 || (P > 0 && !cand) || !prm || !out || prm->max_iters <= 0)
+    return fail(ctx, LISREG_ERR_ARG, "lisreg_loop_verify: bad argument");
+  memset(out, 0, sizeof(*out));
+  out->best = -1; out->best_score = 1.7976931348623157e308;
+  if (P == 0) return LISREG_OK;
+  for (int i = 0; i < P; i++)
+    if (cand[i].submap_id < 0 || cand[i].submap_id >= (int)ctx->submaps.size() || !ctx->submaps[cand[i].submap_id].used)
+      return fail(ctx, LISREG_ERR_ARG, "lisreg_loop_verify: candidate %d: bad submap id", i);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+  // targets first (they use the staging buffers themselves)
+  std::vector<int> tgt((size_t)P), ns((size_t)P, n);
+  for (int i = 0; i < P; i++) { int rc = submap_icp_target(ctx, ctx->submaps[cand[i].submap_id], &tgt[i]); if (rc) return rc; }
+  // sources: the key-frame cloud moved by each candidate's initial alignment, written straight into the ICP staging slots
+  const size_t slot = al(sizeof(float4) * (size_t)std::max(n, 1));
+  CK(ctx->d_stage.reserve(slot * ((size_t)P + 1) + 256));
+  char* d = (char*)ctx->d_stage.p;
+  float4* d_key = (float4*)(d + slot * (size_t)P);
+  if (n) CK(cudaMemcpyAsync(d_key, key_cloud, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
+  std::vector<size_t> off((size_t)P);
+  std::vector<float> K((size_t)P * 16);
+  for (int i = 0; i < P; i++) {
+    float* T = &K[16 * (size_t)i];
+    if (cand[i].use_epsc_init) { float A[16]; odom_T16(cand[i].prekey_pose6, A); odom_mul(A, cand[i].epsc_T, T); }            // :2801-2802
+    else { float A[16], Ai[16], B[16]; odom_T16(cand[i].submap_pose6, A); odom_T16(key_pose6, B); odom_inv(A, Ai); odom_mul(Ai, B, T); }   // :2807-2809
+    OdomT12 t12; for (int k = 0; k < 12; k++) t12.m[k] = T[k];
+    off[i] = slot * (size_t)i;
+    if (n) { k_sm_transform<<<std::min(592, (n + 255) / 256), 256, 0, st>>>(d_key, n, t12, (float4*)(d + off[i])); LAUNCH_CK(); }
+  }
+  std::vector<lisreg_icp_result> res((size_t)P);
+  int rc = icp_run_dev(ctx, P, off, ns, tgt, slot * (size_t)P, prm, res.data());
+  if (rc) return rc;
+  if (per_candidate) memcpy(per_candidate, res.data(), sizeof(lisreg_icp_result) * (size_t)P);
+  for (int i = 0; i < P; i++) {                                        // :2835-2842
+    if (!res[i].converged || res[i].fitness > out->best_score) continue;
+    out->best_score = res[i].fitness; out->best = i;
+  }
+  if (out->best < 0) return LISREG_OK;
+  memcpy(out->correction, res[out->best].T, sizeof(float) * 16);
+  memcpy(out->key2pre, &K[16 * (size_t)out->best], sizeof(float) * 16);
+  if (out->best_score > (double)fitness_threshold) return LISREG_OK;  // "loop not found" (:2855)
+  float R[16], Ri[16], M[16];
+  odom_T16(key_rel_pose6, R); odom_inv(R, Ri);                          // curSubMap2KeyTrans
+  odom_mul(out->correction, out->key2pre, M); odom_mul(M, Ri, out->t_correct);   // tCorrect (:2876)
+  float e[6]; odom_euler(out->t_correct, e);
+  out->constraint6[0] = e[3]; out->constraint6[1] = e[4]; out->constraint6[2] = e[5];
+  out->constraint6[3] = e[0]; out->constraint6[4] = e[1]; out->constraint6[5] = e[2];
+  out->found = 1;
   return LISREG_OK;
 }
 

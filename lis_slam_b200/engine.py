@@ -117,6 +117,16 @@ class SubmapInfo(C.Structure):
                 ("n_map_corner", C.c_int32), ("n_map_surf", C.c_int32)]
 
 
+class LoopCandidate(C.Structure):
+    _fields_ = [("submap_id", C.c_int32), ("use_epsc_init", C.c_int32), ("prekey_pose6", C.c_float * 6), ("epsc_T", C.c_float * 16),
+                ("submap_pose6", C.c_float * 6)]
+
+
+class LoopVerifyResult(C.Structure):
+    _fields_ = [("found", C.c_int32), ("best", C.c_int32), ("best_score", C.c_double), ("correction", C.c_float * 16),
+                ("key2pre", C.c_float * 16), ("t_correct", C.c_float * 16), ("constraint6", C.c_float * 6)]
+
+
 class EpscCloud(C.Structure):
     _fields_ = [("corner", C.c_void_p), ("surf", C.c_void_p), ("sem", C.c_void_p), ("sem_label", C.c_void_p),
                 ("nc", C.c_int32), ("ns", C.c_int32), ("nsem", C.c_int32), ("reserved", C.c_int32)]
@@ -277,6 +287,9 @@ def lib():
         L.lisreg_pretreat.argtypes = [vp, vp, i32, i32, C.c_double, C.c_float, C.c_float, vp, vp, vp, C.POINTER(i32)]
         L.lisreg_deskew_constant_velocity.restype = i32
         L.lisreg_deskew_constant_velocity.argtypes = [vp, vp, vp, i32, C.c_float, fp, fp, vp]
+        L.lisreg_loop_verify.restype = i32
+        L.lisreg_loop_verify.argtypes = [vp, vp, i32, fp, fp, i32, C.POINTER(LoopCandidate), C.c_float, C.POINTER(IcpParams),
+                                         C.POINTER(LoopVerifyResult), C.POINTER(IcpResult)]
         L.lisreg_selftest_smallmat.restype = i32
         L.lisreg_selftest_smallmat.argtypes = [vp, fp, fp, fp]
         L.lisreg_selftest_alu_peak.restype = i32
@@ -607,6 +620,25 @@ class Engine:
         if n.value:
             self._ck(lib().lisreg_submap_download(self._h, sid, cls, out.ctypes.data, n.value, C.byref(n)))
         return out
+
+    def loop_verify(self, key_cloud, key_pose6, key_rel_pose6, cands, fitness_threshold=0.5, prm=None):
+        """detectLoopClosureForSubMap on device-resident submaps. cands: list of dicts {submap_id, use_epsc, prekey_pose6,
+        epsc_T (4,4), submap_pose6}.  Returns (LoopVerifyResult, [IcpResult per candidate])."""
+        k = _f4(key_cloud); P = len(cands)
+        arr = (LoopCandidate * max(P, 1))()
+        for i, c in enumerate(cands):
+            arr[i].submap_id = c["submap_id"]; arr[i].use_epsc_init = 1 if c["use_epsc"] else 0
+            arr[i].prekey_pose6 = (C.c_float * 6)(*[float(v) for v in c["prekey_pose6"]])
+            arr[i].epsc_T = (C.c_float * 16)(*[float(v) for v in np.asarray(c["epsc_T"], np.float32).reshape(16)])
+            arr[i].submap_pose6 = (C.c_float * 6)(*[float(v) for v in c["submap_pose6"]])
+        if prm is None:
+            prm = IcpParams(); lib().lisreg_icp_params_default(C.byref(prm))
+        out = LoopVerifyResult(); per = (IcpResult * max(P, 1))()
+        f = C.POINTER(C.c_float)
+        a = np.ascontiguousarray(key_pose6, np.float32); b = np.ascontiguousarray(key_rel_pose6, np.float32)
+        self._ck(lib().lisreg_loop_verify(self._h, k.ctypes.data, len(k), a.ctypes.data_as(f), b.ctypes.data_as(f), P, arr, fitness_threshold,
+                                          C.byref(prm), C.byref(out), per))
+        return out, list(per)[:P]
 
     def epsc_describe(self, clouds, using_map):
         """clouds: list of (corner (n,4), surf (n,4), sem (n,4), sem_label (n,)). Returns dict of (n,20,80) u8 arrays."""

@@ -447,3 +447,28 @@ def deskew_cv(pts4, time, scan_period, lin_vel, ang_vel):
     m = L.orc_deskew_cv(pp, t.ctypes.data_as(C.c_void_p), C.c_int32(len(p)), C.c_float(scan_period), lv.ctypes.data_as(C.c_void_p),
                         av.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
     return out[:m]
+
+
+def loop_verify(key_cloud, key_pose6, key_rel_pose6, cands, fitness_threshold=0.5, prm=None):
+    """detectLoopClosureForSubMap. cands: list of dicts {submap: Submap, use_epsc, prekey_pose6, epsc_T (4,4), submap_pose6}.
+    Returns dict(found, best, best_score, correction, key2pre, t_correct, constraint6, fitness[], converged[])."""
+    k, kp = _f(key_cloud)
+    P = len(cands)
+    cp = np.zeros((max(P, 1), 29), np.float32)
+    hs = (C.c_void_p * max(P, 1))()
+    for i, c in enumerate(cands):
+        cp[i, 0] = 1.0 if c["use_epsc"] else 0.0
+        cp[i, 1:7] = c["prekey_pose6"]; cp[i, 7:23] = np.asarray(c["epsc_T"], np.float32).reshape(16); cp[i, 23:29] = c["submap_pose6"]
+        hs[i] = c["submap"].h
+    prm = prm or icp_params()
+    best = C.c_int32(-1); score = C.c_double(0)
+    corr = np.zeros(16, np.float32); k2p = np.zeros(16, np.float32); tc = np.zeros(16, np.float32); c6 = np.zeros(6, np.float32)
+    fit = np.zeros(max(P, 1), np.float64); conv = np.zeros(max(P, 1), np.int32)
+    a = np.ascontiguousarray(key_pose6, np.float32); b = np.ascontiguousarray(key_rel_pose6, np.float32)
+    vp = C.c_void_p
+    L = lib(); L.orc_loop_verify.restype = C.c_int32
+    found = L.orc_loop_verify(kp, C.c_int32(len(k)), a.ctypes.data_as(vp), b.ctypes.data_as(vp), C.c_int32(P), hs, cp.ctypes.data_as(vp),
+                              C.c_float(fitness_threshold), C.byref(prm), C.byref(best), C.byref(score), corr.ctypes.data_as(vp),
+                              k2p.ctypes.data_as(vp), tc.ctypes.data_as(vp), c6.ctypes.data_as(vp), fit.ctypes.data_as(vp), conv.ctypes.data_as(vp))
+    return dict(found=found, best=best.value, best_score=score.value, correction=corr.reshape(4, 4), key2pre=k2p.reshape(4, 4),
+                t_correct=tc.reshape(4, 4), constraint6=c6, fitness=fit[:P], converged=conv[:P])

@@ -133,6 +133,10 @@ void orc_submap_insert(void* h, const float* const* pts, const int32_t* n, const
 void orc_submap_extract(void* h, const float* cur_pose6, const float* leaf5, const double* map_bound, float* corner_out, int32_t* nc,
                         float* surf_out, int32_t* ns, int32_t* counts);
 int32_t orc_submap_get(void* h, int32_t c, float* out, int32_t cap);
+/* detectLoopClosureForSubMap (subMapOptmizationNode.cpp:2739-2916); orc_icp_params / orc_icp_result are declared above */
+int32_t orc_loop_verify(const float* key4, int32_t n, const float* key_pose6, const float* key_rel_pose6, int32_t P, void* const* submaps,
+                        const float* cand_pose, float fitness_threshold, const orc_icp_params* prm, int32_t* best, double* best_score,
+                        float* correction16, float* key2pre16, float* t_correct16, float* constraint6, double* fitness_out, int32_t* conv_out);
 
 #ifdef __cplusplus
 }

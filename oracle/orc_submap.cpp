@@ -15,6 +15,7 @@
 #include "orc_api.h"
 #include <algorithm>
 #include <cfloat>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -104,6 +105,69 @@ void orc_submap_extract(void* h, const float* cur_pose6, const float* leaf5, con
   size_t o = 0;
   for (int c : {2, 3, 0}) { if (!S.cls[c].empty()) memcpy(surf_out + o, S.cls[c].data(), sizeof(float) * S.cls[c].size()); o += S.cls[c].size(); }
   *ns = (int32_t)(o / 4);
+}
+
+// SubMapOdometryNode::detectLoopClosureForSubMap (subMapOptmizationNode.cpp:2739-2916).  Pose arithmetic: Eigen::Affine3f
+// products / inverse in fp32, natural order (same resolution as the streaming odometry flow, lis_slam_b200/stream.py).
+namespace {
+void T16_of(const float* pose6, float* T) { float t12[12]; orc_pose_to_affine(pose6, t12); memcpy(T, t12, sizeof(t12)); T[12] = T[13] = T[14] = 0.f; T[15] = 1.f; }
+float cof(const float* T, int i, int j) { const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3; return T[i1 * 4 + j1] * T[i2 * 4 + j2] - T[i1 * 4 + j2] * T[i2 * 4 + j1]; }
+void inv16(const float* T, float* R) {
+  const float c0 = cof(T, 0, 0), c1 = cof(T, 1, 0), c2 = cof(T, 2, 0);
+  const float det = (c0 * T[0] + c1 * T[4]) + c2 * T[8];
+  const float invdet = 1.f / det;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R[i * 4 + j] = cof(T, j, i) * invdet;
+  for (int i = 0; i < 3; i++) R[i * 4 + 3] = ((-R[i * 4 + 0]) * T[3] + (-R[i * 4 + 1]) * T[7]) + (-R[i * 4 + 2]) * T[11];
+  R[12] = R[13] = R[14] = 0.f; R[15] = 1.f;
+}
+void mul16(const float* A, const float* B, float* Cm) {
+  float r[16];
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { float a = 0.f; for (int k = 0; k < 4; k++) a += A[i * 4 + k] * B[k * 4 + j]; r[i * 4 + j] = a; }
+  memcpy(Cm, r, sizeof(r));
+}
+}  // namespace
+
+// cand_pose: per candidate [use_epsc, prekey_pose6 (6), epsc_T (16), submap_pose6 (6)] = 29 floats; submaps: P handles.
+// out: found, best, best_score, correction[16], key2pre[16], t_correct[16], constraint6; per-candidate fitness / converged / iters.
+int32_t orc_loop_verify(const float* key4, int32_t n, const float* key_pose6, const float* key_rel_pose6, int32_t P, void* const* submaps,
+                        const float* cand_pose, float fitness_threshold, const orc_icp_params* prm, int32_t* best, double* best_score,
+                        float* correction16, float* key2pre16, float* t_correct16, float* constraint6, double* fitness_out, int32_t* conv_out) {
+  *best = -1; *best_score = DBL_MAX;
+  std::vector<float> K((size_t)std::max(P, 1) * 16);
+  std::vector<orc_icp_result> res((size_t)std::max(P, 1));
+  for (int i = 0; i < P; i++) {
+    const float* c = cand_pose + 29 * (size_t)i;
+    float* T = &K[16 * (size_t)i];
+    if (c[0] != 0.f) { float A[16]; T16_of(c + 1, A); mul16(A, c + 7, T); }
+    else { float A[16], Ai[16], B[16]; T16_of(c + 23, A); T16_of(key_pose6, B); inv16(A, Ai); mul16(Ai, B, T); }
+    const Submap& S = *(const Submap*)submaps[i];
+    std::vector<float> tgt;
+    for (int cl = 0; cl < 4; cl++) tgt.insert(tgt.end(), S.cls[cl].begin(), S.cls[cl].end());
+    std::vector<float> src(4 * (size_t)n);
+    for (int k = 0; k < n; k++) {
+      const float* p = key4 + 4 * (size_t)k; float* q = &src[4 * (size_t)k];
+      q[0] = T[0] * p[0] + T[1] * p[1] + T[2] * p[2] + T[3];
+      q[1] = T[4] * p[0] + T[5] * p[1] + T[6] * p[2] + T[7];
+      q[2] = T[8] * p[0] + T[9] * p[1] + T[10] * p[2] + T[11];
+      q[3] = p[3];
+    }
+    orc_icp(src.data(), n, tgt.data(), (int)(tgt.size() / 4), prm, &res[i]);
+    fitness_out[i] = res[i].fitness; conv_out[i] = res[i].converged;
+    if (!res[i].converged || res[i].fitness > *best_score) continue;
+    *best_score = res[i].fitness; *best = i;
+  }
+  if (*best < 0) return 0;
+  memcpy(correction16, res[*best].T, sizeof(float) * 16);
+  memcpy(key2pre16, &K[16 * (size_t)*best], sizeof(float) * 16);
+  if (*best_score > (double)fitness_threshold) return 0;
+  float R[16], Ri[16], M[16];
+  T16_of(key_rel_pose6, R); inv16(R, Ri);
+  mul16(correction16, key2pre16, M); mul16(M, Ri, t_correct16);
+  constraint6[0] = t_correct16[3]; constraint6[1] = t_correct16[7]; constraint6[2] = t_correct16[11];
+  constraint6[3] = (float)std::atan2((double)t_correct16[9], (double)t_correct16[10]);
+  constraint6[4] = (float)std::asin((double)-t_correct16[8]);
+  constraint6[5] = (float)std::atan2((double)t_correct16[4], (double)t_correct16[0]);
+  return 1;
 }
 
 int32_t orc_submap_get(void* h, int32_t c, float* out, int32_t cap) {

@@ -81,3 +81,63 @@ def test_submap_empty_and_clear(engine):
     engine.submap_clear(sid)
     assert engine.submap_download(sid, 2).shape == (0, 4)
     engine.map_destroy(mid); engine.submap_destroy(sid); so.close()
+
+
+def test_loop_verify_on_submaps_matches_oracle(engine):
+    """B4 glue: detectLoopClosureForSubMap (subMapOptmizationNode.cpp:2739-2916) on device-resident submaps - initial
+    alignment composed from the EPSC transform or from the poses, key-frame cloud moved and ICP-aligned to every candidate
+    submap in one batch, best converged candidate, acceptance threshold, loop constraint tCorrect and its 6-DoF.  Same
+    winner and decision as the oracle; transforms / scores within the ICP tolerance (fp64 sums are reduced per block on
+    the device, sequentially in the oracle: tests/test_icp_parity.py)."""
+    m = local_map()
+    rng = np.random.default_rng(23)
+    sub_pose = [np.array([0.0, 0.0, 0.3 * k, 4.0 * k, 1.0 * k, 0.0], np.float32) for k in range(3)]
+    subs_o, subs_g = [], []
+    for k in range(3):
+        so = orc.Submap(); sid = engine.submap_create()
+        # submap clouds live in the SUBMAP frame: map points expressed relative to the submap pose
+        T = synth.pose_to_T(sub_pose[k])
+        def local(src, n):
+            w = src[rng.choice(len(src), n, replace=False)].copy()
+            w[:, :3] = ((w[:, :3].astype(np.float64) - T[:3, 3]) @ T[:3, :3]).astype(np.float32)
+            return w
+        clouds = [local(m["surf"], 2000), local(m["corner"], 3000), local(m["surf"], 30000), local(m["surf"], 20000), local(m["surf"], 500)]
+        so.insert(clouds, np.zeros(6, np.float32)); engine.submap_insert(sid, clouds, np.zeros(6, np.float32))
+        subs_o.append(so); subs_g.append(sid)
+    # current key frame: a world pose close to submap 1, cloud in its own frame
+    key_pose = np.array([0.01, -0.01, 0.32, 4.3, 1.2, 0.02], np.float32)
+    Tk = synth.pose_to_T(key_pose)
+    kc = np.concatenate([m["surf"][rng.choice(len(m["surf"]), 8000, replace=False)], m["corner"][rng.choice(len(m["corner"]), 1500, replace=False)]]).copy()
+    kc[:, :3] = ((kc[:, :3].astype(np.float64) - Tk[:3, 3]) @ Tk[:3, :3]).astype(np.float32)
+    kc[:, :3] += rng.normal(0, 0.01, (len(kc), 3)).astype(np.float32)
+    key_rel = np.array([0.0, 0.0, 0.05, 0.8, 0.1, 0.0], np.float32)
+    # candidate 1 gets an EPSC-style initial pose (prekey pose * planar transform), the others the pose-based one
+    prekey = np.array([0.0, 0.0, 0.02, 0.2, 0.1, 0.0], np.float32)
+    want = np.linalg.inv(synth.pose_to_T(sub_pose[1])) @ Tk                     # true key -> submap 1
+    epsc_T = (np.linalg.inv(synth.pose_to_T(prekey)) @ want @ synth.pose_to_T(np.array([0, 0, 0.02, 0.15, -0.1, 0.0]))).astype(np.float32)
+    cands_o, cands_g = [], []
+    for k in range(3):
+        c = dict(use_epsc=(k == 1), prekey_pose6=prekey, epsc_T=epsc_T, submap_pose6=sub_pose[k])
+        cands_o.append(dict(c, submap=subs_o[k])); cands_g.append(dict(c, submap_id=subs_g[k]))
+    ro = orc.loop_verify(kc, key_pose, key_rel, cands_o)
+    rg, per = engine.loop_verify(kc, key_pose, key_rel, cands_g)
+    assert rg.found == ro["found"] == 1 and rg.best == ro["best"]
+    assert [p.converged for p in per] == list(ro["converged"])
+    for p, fo in zip(per, ro["fitness"]):
+        assert abs(p.fitness - fo) <= 1e-4 * max(1.0, fo)
+    assert abs(rg.best_score - ro["best_score"]) <= 1e-5
+    assert np.array_equal(np.array(rg.key2pre).reshape(4, 4), ro["key2pre"])            # pure fp32 pose arithmetic: identical
+    assert np.abs(np.array(rg.correction).reshape(4, 4) - ro["correction"]).max() <= 1e-4
+    assert np.abs(np.array(rg.t_correct).reshape(4, 4) - ro["t_correct"]).max() <= 1e-4
+    assert np.abs(np.array(rg.constraint6) - ro["constraint6"]).max() <= 1e-4
+    # a threshold nobody passes -> "loop not found", best candidate still reported
+    rg2, _ = engine.loop_verify(kc, key_pose, key_rel, cands_g, fitness_threshold=1e-9)
+    ro2 = orc.loop_verify(kc, key_pose, key_rel, cands_o, fitness_threshold=1e-9)
+    assert rg2.found == ro2["found"] == 0 and rg2.best == ro2["best"]
+    # the cached target index is rebuilt after the submap changes
+    extra = [m["surf"][:500].copy()] * 5
+    subs_o[0].insert(extra, np.zeros(6, np.float32)); engine.submap_insert(subs_g[0], extra, np.zeros(6, np.float32))
+    rg3, per3 = engine.loop_verify(kc, key_pose, key_rel, cands_g); ro3 = orc.loop_verify(kc, key_pose, key_rel, cands_o)
+    assert rg3.best == ro3["best"] and abs(per3[0].fitness - ro3["fitness"][0]) <= 1e-4 * max(1.0, ro3["fitness"][0])
+    for so, sid in zip(subs_o, subs_g):
+        so.close(); engine.submap_destroy(sid)
