@@ -597,8 +597,11 @@ static void to_dev_params(const lisreg_lm_params* p, LmParamsDev* d) {
 // core driver: descs already on the device. max_n = largest nc+ns of the batch.
 // tiling_B: batch size that decides the tile size (a chunk of a larger batch must tile like the whole batch so
 // that the fixed summation order - hence every bit of the result - does not depend on the chunking); 0 = B
+// it0 / it1: run only the iterations [it0, it1) of the loop (it1 < 0 = all): the streaming odometry launches the loop in
+// slices and looks at the convergence flag in between instead of launching 15 x 6 kernels that mostly find `done` set;
+// it0 == 0 includes k_lm_init and the counter reset, every slice ends with k_lm_finish (the result is valid after each)
 static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, double alg_bytes_per_iter, float* d_pose,
-                  const lisreg_lm_params* prm, lisreg_lm_result* d_res, lisreg_lm_iter* d_logs, int tiling_B = 0) {
+                  const lisreg_lm_params* prm, lisreg_lm_result* d_res, lisreg_lm_iter* d_logs, int tiling_B = 0, int it0 = 0, int it1 = -1) {
   cudaStream_t st = ctx->cur->stream;
   int rc = sync_maps(ctx);
   if (rc) return rc;
@@ -612,13 +615,14 @@ static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, dou
   CK(ctx->cur->d_partials.reserve(sizeof(double) * LM_NSUM * (size_t)B * max_tiles));
   RegState* states = (RegState*)ctx->cur->d_states.p;
   double* partials = (double*)ctx->cur->d_partials.p;
-  k_lm_init<<<(B + 127) / 128, 128, 0, st>>>(d_descs, states, d_pose, dp, B); LAUNCH_CK();
+  if (it1 < 0 || it1 > dp.max_iters) it1 = dp.max_iters;
+  if (it0 == 0) { k_lm_init<<<(B + 127) / 128, 128, 0, st>>>(d_descs, states, d_pose, dp, B); LAUNCH_CK(); }
   // a block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...: batches get 32 blocks per registration
   // (the real tile count is only known on the device in the frame pipeline), a lone registration gets
   // one block per tile so that it spreads over the whole GPU
   dim3 grid(std::min(max_tiles, tiling_B >= 32 ? 32 : 1024), B);
   {
-    ProfScope ps(ctx, PROF_LM, alg_bytes_per_iter * dp.max_iters, dp.max_iters);
+    ProfScope ps(ctx, PROF_LM, alg_bytes_per_iter * (it1 - it0), it1 - it0);
     const size_t slots = (size_t)tile_pts * max_tiles * B;
     if (slots >= (size_t)0xffffffffu) return fail(ctx, LISREG_ERR_CAPACITY, "batch too large: %zu query slots (split the batch)", slots);
     CK(ctx->cur->d_nbr.reserve(sizeof(int) * 5 * slots));
@@ -631,10 +635,10 @@ static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, dou
     unsigned* scan_list = (unsigned*)ctx->cur->d_klist.p;
     unsigned* shell_list = scan_list + slots;
     int* counters = (int*)(shell_list + slots);          // [it][2]: scan / shell list lengths of iteration it
-    CK(cudaMemsetAsync(counters, 0, sizeof(int) * 2 * LISREG_MAX_ITERS, st));
+    if (it0 == 0) CK(cudaMemsetAsync(counters, 0, sizeof(int) * 2 * LISREG_MAX_ITERS, st));
     const int tile_shift = tile_pts == LM_MAX_TILE ? 9 : 7;
     static_assert(LM_MAX_TILE == 512 && LM_THREADS == 128, "tile_shift assumes 512 / 128 query tiles");
-    for (int it = 0; it < dp.max_iters; it++) {
+    for (int it = it0; it < it1; it++) {
       // iteration 0 searches every query; later iterations first try to PROVE that the neighbours did not change
       k_knn_check<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, kstate, geom, scan_list, counters + 2 * it,
                                                max_tiles, tile_shift, (it > 0 && !ctx->knn_noskip) ? 1 : 0); LAUNCH_CK();
@@ -1072,7 +1076,7 @@ static size_t frame_desc_bytes(int F) {
 // device-resident counts, so the results do not depend on it)
 static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, const char* d_arena, uint64_t arena_bytes,
                       float* d_pose, const lisreg_frame_params* prm, lisreg_lm_result* d_res, char* h_pinned = nullptr,
-                      int tiling_B = 0, int launch_n = 0, int frame_offset = 0) {
+                      int tiling_B = 0, int launch_n = 0, int frame_offset = 0, int lm_it1 = -1) {
   cudaStream_t st = ctx->cur->stream;
   const lisreg_feat_params* fp = &prm->feat;
   if (fp->n_scan <= 0 || fp->horizon <= 0 || fp->horizon > 2048 || fp->n_scan * 6 > 1024 || fp->downsample_rate <= 0)
@@ -1160,7 +1164,7 @@ static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, co
   // of this batch (blocks beyond a frame's real tile count exit immediately).  Voxel output never exceeds
   // its input, and the input never exceeds the sweep size.
   const int lm_max_n = std::min(max_n, cells);
-  return run_lm(ctx, F, (const RegDesc*)ctx->cur->d_descs.p, lm_max_n, 0.0, d_pose, &prm->lm, d_res, nullptr, tiling_B);
+  return run_lm(ctx, F, (const RegDesc*)ctx->cur->d_descs.p, lm_max_n, 0.0, d_pose, &prm->lm, d_res, nullptr, tiling_B, 0, lm_it1);
 }
 
 int32_t lisreg_frames_batch_dev(lisreg_ctx* ctx, int32_t F, const lisreg_frame_item* items, float* d_pose6xF,
@@ -1897,6 +1901,28 @@ int32_t lisreg_odom_create(lisreg_ctx* ctx, const lisreg_odom_params* prm, int32
     if (e != cudaSuccess) { cudaFree(O.d_win_c); O.d_win_c = nullptr; return fail(ctx, LISREG_ERR_CUDA, "lisreg_odom_create: window allocation failed: %s", cudaGetErrorString(e)); } }
   O.nc.assign(O.slots, 0); O.ns.assign(O.slots, 0);
   O.used = true;
+  // every buffer the stream will need, sized for a full window now: no cudaMalloc / cudaFree (a device-wide synchronisation)
+  // while frames are flowing
+  {
+    const size_t tot_c = (size_t)O.ccap * prm->window, tot_s = (size_t)O.scap * prm->window;
+    const size_t cat_c = (sizeof(float4) * tot_c + 255) & ~size_t(255);
+    cudaError_t e = O.d_cat.reserve(cat_c + sizeof(float4) * tot_s);
+    if (e == cudaSuccess) e = O.d_mapvox.reserve(vox_seg_bytes((int)tot_c) + vox_seg_bytes((int)tot_s));
+    if (e == cudaSuccess) e = O.d_mapseg.reserve(sizeof(VoxSeg) * 2);
+    if (e == cudaSuccess) e = O.d_in.reserve(((size_t)layout_step(fp.layout) * O.scap + 255) + sizeof(uint16_t) * (size_t)O.scap + 64);
+    if (e != cudaSuccess) { lisreg_odom_destroy(ctx, slot); return fail(ctx, LISREG_ERR_CUDA, "lisreg_odom_create: buffer allocation failed: %s", cudaGetErrorString(e)); }
+    O.map_id = map_alloc_slot(ctx);
+    ctx->maps[O.map_id] = MapSlot();
+    MapSlot& m = ctx->maps[O.map_id];
+    m.used = true;                                  // reserved (empty) until the first rebuild
+    const size_t cells = (size_t)ctx->max_cells + 1;
+    for (CloudIndex* ci : {&m.corner, &m.surf}) {
+      const size_t npts = ci == &m.corner ? tot_c : tot_s;
+      if (cudaMalloc(&ci->sorted, sizeof(float4) * npts) == cudaSuccess) ci->cap_pts = npts; else ci->sorted = nullptr;
+      if (cudaMalloc(&ci->cell_start, sizeof(uint32_t) * cells) == cudaSuccess) ci->cap_cells = cells; else ci->cell_start = nullptr;
+    }
+    ctx->maps_dirty = true;
+  }
   *odom_id = slot;
   return LISREG_OK;
 }
@@ -1995,6 +2021,8 @@ static int odom_rebuild_map(lisreg_ctx* ctx, lisreg_ctx::Odom& O) {
   return sync_maps(ctx);
 }
 
+constexpr int ODOM_LM_SLICE = 4;   // Gauss-Newton iterations per launch slice of the streaming odometry
+
 // addresses a captured frame graph depends on: when one of them moves the graph is dropped and captured again
 static std::vector<const void*> odom_graph_key(lisreg_ctx* ctx, lisreg_ctx::Odom& O) {
   WorkSet& w = *ctx->cur;
@@ -2078,7 +2106,7 @@ static int odom_push_impl(lisreg_ctx* ctx, int32_t odom_id, const float* pts, co
         cudaGraph_t g = nullptr;
         CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         const int64_t l0 = ctx->launches;
-        rc = run_frames(ctx, 1, &it, nullptr, 0, (float*)dio, &O.prm.frame, (lisreg_lm_result*)(dio + o_res), (char*)O.h_desc.p, 0, cells);
+        rc = run_frames(ctx, 1, &it, nullptr, 0, (float*)dio, &O.prm.frame, (lisreg_lm_result*)(dio + o_res), (char*)O.h_desc.p, 0, cells, 0, ODOM_LM_SLICE);
         cudaError_t e = cudaStreamEndCapture(st, &g);
         O.graph_kernels = ctx->launches - l0;                              // kernels one replay launches
         ctx->launches = l0;
@@ -2086,7 +2114,7 @@ static int odom_push_impl(lisreg_ctx* ctx, int32_t odom_id, const float* pts, co
           if (g) cudaGraphDestroy(g);
           cudaGetLastError();
           O.prm.use_graph = 0;                                             // fall back to eager launches for good
-          if (rc == LISREG_OK) rc = run_frames(ctx, 1, &it, nullptr, 0, (float*)dio, &O.prm.frame, (lisreg_lm_result*)(dio + o_res), (char*)O.h_desc.p, 0, cells);
+          if (rc == LISREG_OK) rc = run_frames(ctx, 1, &it, nullptr, 0, (float*)dio, &O.prm.frame, (lisreg_lm_result*)(dio + o_res), (char*)O.h_desc.p, 0, cells, 0, ODOM_LM_SLICE);
           if (rc) return rc;
         } else {
           e = cudaGraphInstantiate(&O.gexec, g, 0);
@@ -2097,7 +2125,7 @@ static int odom_push_impl(lisreg_ctx* ctx, int32_t odom_id, const float* pts, co
           ctx->launches += O.graph_kernels;
         }
       } else {
-        rc = run_frames(ctx, 1, &it, nullptr, 0, (float*)dio, &O.prm.frame, (lisreg_lm_result*)(dio + o_res), (char*)O.h_desc.p, 0, cells);
+        rc = run_frames(ctx, 1, &it, nullptr, 0, (float*)dio, &O.prm.frame, (lisreg_lm_result*)(dio + o_res), (char*)O.h_desc.p, 0, cells, 0, ODOM_LM_SLICE);
         if (rc) return rc;
         O.gkey = odom_graph_key(ctx, O);
       }
@@ -2107,6 +2135,19 @@ static int odom_push_impl(lisreg_ctx* ctx, int32_t odom_id, const float* pts, co
     CK(cudaStreamSynchronize(st));
     const lisreg_lm_result* lr = (const lisreg_lm_result*)(hio + o_res);
     const int* cnt = (const int*)(hio + o_cnt);
+    // The frame graph holds the first ODOM_LM_SLICE iterations (a 10 Hz / 100 Hz stream converges in 2-3); the rare frame that
+    // needs more continues slice by slice with eager launches - same kernels, same order, so the result does not depend on it.
+    const lisreg_lm_params& lp = O.prm.frame.lm;
+    const int max_it = std::min(lp.max_iters, (int)LISREG_MAX_ITERS);
+    while (lr->status != LISREG_NOT_ENOUGH_FEATURES && lr->iters < max_it && !(lr->converged && lp.early_exit)) {
+      const int it0 = lr->iters;
+      rc = run_lm(ctx, 1, (const RegDesc*)ctx->cur->d_descs.p, cells, 0.0, (float*)dio, &lp, (lisreg_lm_result*)(dio + o_res), nullptr, 0, it0,
+                  it0 + ODOM_LM_SLICE);
+      if (rc) return rc;
+      CK(cudaMemcpyAsync(hio + o_res, dio + o_res, sizeof(lisreg_lm_result), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (lr->iters <= it0) break;                                   // no progress (cannot happen): never spin
+    }
     res->lm = *lr;
     if (lr->status != LISREG_NOT_ENOUGH_FEATURES) {
       memcpy(O.pose, lr->pose, sizeof(O.pose));
