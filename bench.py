@@ -498,9 +498,11 @@ def run_ours(args, rank, world, local_rank):
                 "traffic_source": (traffic or {}).get("source"),
                 "alg_bytes_per_launch": alg_per_launch, "avg_launch_ms": avg_launch_ms,
                 "kernel_share_of_step": prof.lm_iter_ms / ms_total, "stage_ms_per_step": stage_ms,
-                "regime": "maps are shared by many frames and stay L2-resident (8 x 3.2 MB); the stage is latency / issue bound, "
-                          "not DRAM bound (see profiles/); from iteration 2 on most queries PROVE that their neighbours are "
-                          "unchanged (5 gathers) instead of searching, so the algorithmic bytes are an upper bound of what moves",
+                "regime": ("every frame has a private 200k-point map (%d x 3.2 MB + index per GPU, far beyond the 126 MB L2): the map "
+                           "gathers stream from HBM - the regime the HBM roofline applies to (SURVEY.md 8d)" % F) if args.distinct_maps else
+                          ("maps are shared by many frames and stay L2-resident (8 x 3.2 MB); the stage is latency / issue bound, "
+                           "not DRAM bound (see profiles/); from iteration 2 on most queries PROVE that their neighbours are "
+                           "unchanged (5 gathers) instead of searching, so the algorithmic bytes are an upper bound of what moves"),
                 "note": "algorithmic bytes = query points x (16 B query + 5 x 16 B neighbours) per iteration (SURVEY.md 8d A_iter); "
                         "index traversal traffic excluded; launch = one iteration of the whole batch"}
     a_reg = (17.0 * n_raw / F if frame_stage else 0.0) + LM_ITERS * 96.0 * n_query / F + 16.0 * 200000
@@ -645,8 +647,7 @@ def run_stream(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def run(resident):
-        oid = eng.odom_create(prm)
+    def run(oid, resident):
         lat, poses, results = [], [], []
         for t in range(n_frames):
             t0 = time.perf_counter()
@@ -655,26 +656,32 @@ def run_stream(args, rank, world, local_rank):
             else:
                 p, r = eng.odom_push(oid, pin[t][0].numpy(), pin[t][1].numpy().view(np.uint16), init_pose=init)
             lat.append(1e3 * (time.perf_counter() - t0)); poses.append(p); results.append(r)
-        eng.odom_destroy(oid)
         return lat, poses, results
 
-    run(True)                                        # warm-up: allocations, graph capture, clocks (a whole stream >= 3 steps)
+    # one odometry object per run, created (window / map buffers, ~190 MB for HDL-64) outside the timed regions
+    oid = eng.odom_create(prm)
+    run(oid, True)                                   # warm-up: allocations, graph capture, clocks (a whole stream >= 3 steps)
+    eng.odom_destroy(oid)
+    oid = eng.odom_create(prm)
     barrier()
     sampler = ClockSampler(local_rank); sampler.start()
     l0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    lat_dev, poses_dev, res_dev = run(True)          # `value`: sweeps resident in HBM
+    lat_dev, poses_dev, res_dev = run(oid, True)     # `value`: sweeps resident in HBM
     e1.record(stream)
     barrier()
     ms_dev = e0.elapsed_time(e1)
     launches = eng.launches - l0
+    eng.odom_destroy(oid)
+    oid = eng.odom_create(prm)
     barrier()
     t0 = time.perf_counter()
-    lat_e2e, poses_e2e, res_e2e = run(False)         # `e2e`: lisreg_odom_push from pinned host memory, pose back every frame
+    lat_e2e, poses_e2e, res_e2e = run(oid, False)    # `e2e`: lisreg_odom_push from pinned host memory, pose back every frame
     torch.cuda.synchronize(dev)
     ms_e2e = 1e3 * (time.perf_counter() - t0)
+    eng.odom_destroy(oid)
     barrier()
     sampler.stop_flag = True; sampler.join(timeout=2)
     same = all(np.array_equal(a, b) for a, b in zip(poses_dev, poses_e2e))

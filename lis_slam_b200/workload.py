@@ -71,7 +71,7 @@ def frame_batch(F=256, n_maps=8, n_sweeps=8, map_edge=40000, map_surf=160000, se
     sweeps = []
     for s in range(n_sweeps):
         truth = synth.random_pose(rng)
-        sw = sc.scan(truth, sensor=sensor, seed=2000 + 1000 * seed + s)
+        sw = sc.scan(truth, sensor=sensor, seed=2000 + 1000 * seed + s, fast=True)      # C ray-caster: bit-identical to the numpy one
         sweeps.append((sw, truth))
     regs = []
     for b in range(F):
