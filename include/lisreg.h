@@ -460,15 +460,16 @@ int32_t lisreg_icp_verify_batch(lisreg_ctx* ctx, int32_t P, const lisreg_icp_pai
  * MPI, torch.distributed ...), every rank calls lisreg_comm_init().
  * lisreg_allgather_results enqueues ncclAllGather(d_send -> d_recv, bytes_per_rank per rank) on a private stream
  * that first waits for everything enqueued so far on the context stream, and returns at once: the kernels of the
- * next batch do not wait for the collective.  lisreg_allgather_wait blocks the host until the last gather has
- * landed (d_send may be overwritten and d_recv read after it). */
+ * next batch do not wait for the collective.  lisreg_allgather_wait(ctx, back) blocks the host until the gather issued
+ * `back` calls before the most recent one has landed (0 = the last one; with double-buffered send / receive blocks a
+ * producer waits with back = 1 before reusing a buffer, without draining the step still in flight). */
 #define LISREG_NCCL_ID_BYTES 128
 int32_t lisreg_comm_unique_id(uint8_t id[LISREG_NCCL_ID_BYTES]);
 int32_t lisreg_comm_init(lisreg_ctx* ctx, int32_t world, int32_t rank, const uint8_t id[LISREG_NCCL_ID_BYTES]);
 int32_t lisreg_comm_adopt(lisreg_ctx* ctx, void* nccl_comm /* ncclComm_t */, int32_t world, int32_t rank);
 int32_t lisreg_comm_destroy(lisreg_ctx* ctx);
 int32_t lisreg_allgather_results(lisreg_ctx* ctx, const void* d_send, void* d_recv, uint64_t bytes_per_rank);
-int32_t lisreg_allgather_wait(lisreg_ctx* ctx);
+int32_t lisreg_allgather_wait(lisreg_ctx* ctx, int32_t back);
 
 /* ---- loop-closure verification against candidate submaps (B4: the whole of detectLoopClosureForSubMap) ----
  * Replaces SubMapOdometryNode::detectLoopClosureForSubMap (subMapOptmizationNode.cpp:2739-2916) on top of the

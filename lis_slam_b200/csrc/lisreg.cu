@@ -145,7 +145,8 @@ struct lisreg_ctx {
   DevBuf d_smvox, d_smcat;
   // multi-GPU exchange: NCCL communicator (own or adopted), private stream, fence / done events
   void* comm = nullptr; bool comm_owned = false; int comm_world = 1, comm_rank = 0;
-  cudaStream_t comm_stream = nullptr; cudaEvent_t comm_fence = nullptr, comm_done = nullptr; bool comm_pending = false;
+  cudaStream_t comm_stream = nullptr; cudaEvent_t comm_fence = nullptr, comm_done[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t comm_seq = 0;                    // gathers issued so far; gather k signals comm_done[k % 4]
   int knn_coop_max = 16384;   // scan lists shorter than this are searched warp-per-query (LISREG_KNN_COOP_MAX; 0 = never)
   int knn_noskip = 0;   // LISREG_KNN_NOSKIP=1: search every query from scratch at every iteration (parity check of the CHECK path)
   // profiling
@@ -974,7 +975,7 @@ static size_t vox_seg_bytes(int cap) {
   const int nblk = (cap + RS_TILE - 1) / RS_TILE + 1;
   size_t b = 4 * (size_t)cap * 4;                 // key_a, val_a, key_b, val_b
   b += 4 * 256 * (size_t)(nblk + 1);              // hist + the 256 digit bases behind it
-  b += 4 * ((size_t)cap + 1);                     // seg_start
+  b += 2 * 4 * ((size_t)cap + 1) + 32;            // seg_start, run_start
   b += sizeof(VoxPlan) + 16 + 32;                 // plan, out_n, bbox
   b += sizeof(float4) * (size_t)cap;              // out
   return (b + 1024) & ~size_t(255);
@@ -988,6 +989,7 @@ static void vox_carve(char* base, int cap, VoxSeg* s) {
   s->key_b = (uint32_t*)take(4 * (size_t)cap); s->val_b = (uint32_t*)take(4 * (size_t)cap);
   s->hist = (uint32_t*)take(4 * 256 * (size_t)(nblk + 1));
   s->seg_start = (int*)take(4 * ((size_t)cap + 1));
+  s->run_start = (int*)take(4 * ((size_t)cap + 1));
   s->plan = (VoxPlan*)take(sizeof(VoxPlan));
   s->bbox = (unsigned*)take(24);
   s->out_n = (int*)take(4);
@@ -1008,6 +1010,14 @@ static int run_voxel(lisreg_ctx* ctx, VoxSeg* d_segs, int nseg, int max_n, doubl
   k_vox_bbox<<<dim3(pblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
   k_vox_plan<<<(nseg + 127) / 128, 128, 0, st>>>(d_segs, nseg); LAUNCH_CK();
   k_vox_keys<<<dim3(pblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
+  // runs of equal consecutive keys -> the entries the sort moves
+  if (big) {
+    k_vox_head_count<true><<<dim3(nblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
+    k_vox_head_scan<true><<<(nseg + 7) / 8, 256, 0, st>>>(d_segs, nseg); LAUNCH_CK();
+    k_vox_head_write<true><<<dim3(nblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
+  } else {
+    k_vox_heads<true><<<nseg, 1024, 0, st>>>(d_segs); LAUNCH_CK();
+  }
   for (int pass = 0; pass < 4; pass++) {                  // passes beyond a cloud's plan->npass return at once
     k_rs_hist<<<dim3(nblk, nseg), RS_THREADS, 0, st>>>(d_segs, 8 * pass, pass & 1); LAUNCH_CK();
     if (big) {      // a few large clouds (sliding-window map, submap classes): scan with 256 warps per cloud
@@ -1019,13 +1029,14 @@ static int run_voxel(lisreg_ctx* ctx, VoxSeg* d_segs, int nseg, int max_n, doubl
     k_rs_scatter<<<dim3(nblk, nseg), RS_THREADS, 0, st>>>(d_segs, 8 * pass, pass & 1); LAUNCH_CK();
   }
   if (big) {
-    k_vox_head_count<<<dim3(nblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
-    k_vox_head_scan<<<(nseg + 7) / 8, 256, 0, st>>>(d_segs, nseg); LAUNCH_CK();
-    k_vox_head_write<<<dim3(nblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
+    k_vox_head_count<false><<<dim3(nblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
+    k_vox_head_scan<false><<<(nseg + 7) / 8, 256, 0, st>>>(d_segs, nseg); LAUNCH_CK();
+    k_vox_head_write<false><<<dim3(nblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
   } else {
-    k_vox_heads<<<nseg, 1024, 0, st>>>(d_segs); LAUNCH_CK();
+    k_vox_heads<false><<<nseg, 1024, 0, st>>>(d_segs); LAUNCH_CK();
   }
-  k_vox_centroid<<<dim3(std::max(1, (max_n + VC_CHUNK - 1) / VC_CHUNK), nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
+  if (big) { k_vox_centroid_warp<<<dim3(std::max(1, std::min(2 * ctx->n_sm, (max_n + 255) / 256)), nseg), 256, 0, st>>>(d_segs); LAUNCH_CK(); }
+  else { k_vox_centroid<<<dim3(std::max(1, (max_n + VC_CHUNK - 1) / VC_CHUNK), nseg), 256, 0, st>>>(d_segs); LAUNCH_CK(); }
   return LISREG_OK;
 }
 
@@ -1771,7 +1782,7 @@ int32_t lisreg_comm_unique_id(uint8_t id[LISREG_NCCL_ID_BYTES]) {
 static int comm_streams(lisreg_ctx* ctx) {
   if (!ctx->comm_stream) CK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
   if (!ctx->comm_fence) CK(cudaEventCreateWithFlags(&ctx->comm_fence, cudaEventDisableTiming));
-  if (!ctx->comm_done) CK(cudaEventCreateWithFlags(&ctx->comm_done, cudaEventDisableTiming));
+  for (auto& e : ctx->comm_done) if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return LISREG_OK;
 }
 
@@ -1803,10 +1814,10 @@ int32_t lisreg_comm_destroy(lisreg_ctx* ctx) {
   if (!ctx) return LISREG_ERR_ARG;
   if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
   if (ctx->comm && ctx->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
-  ctx->comm = nullptr; ctx->comm_owned = false; ctx->comm_world = 1; ctx->comm_rank = 0; ctx->comm_pending = false;
+  ctx->comm = nullptr; ctx->comm_owned = false; ctx->comm_world = 1; ctx->comm_rank = 0; ctx->comm_seq = 0;
   if (ctx->comm_stream) { cudaStreamDestroy(ctx->comm_stream); ctx->comm_stream = nullptr; }
   if (ctx->comm_fence) { cudaEventDestroy(ctx->comm_fence); ctx->comm_fence = nullptr; }
-  if (ctx->comm_done) { cudaEventDestroy(ctx->comm_done); ctx->comm_done = nullptr; }
+  for (auto& e : ctx->comm_done) if (e) { cudaEventDestroy(e); e = nullptr; }
   return LISREG_OK;
 }
 
@@ -1821,16 +1832,17 @@ int32_t lisreg_allgather_results(lisreg_ctx* ctx, const void* d_send, void* d_re
   CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->comm_fence, 0));
   const int rc = g_nccl.AllGather(d_send, d_recv, (size_t)bytes_per_rank, /* ncclInt8 */ 0, ctx->comm, ctx->comm_stream);
   if (rc != 0) return fail(ctx, LISREG_ERR_CUDA, "ncclAllGather failed: %s", nccl_err(rc));
-  CK(cudaEventRecord(ctx->comm_done, ctx->comm_stream));
-  ctx->comm_pending = true;
+  CK(cudaEventRecord(ctx->comm_done[ctx->comm_seq % 4], ctx->comm_stream));
+  ctx->comm_seq++;
   return LISREG_OK;
 }
 
-int32_t lisreg_allgather_wait(lisreg_ctx* ctx) {
-  if (!ctx) return LISREG_ERR_ARG;
+int32_t lisreg_allgather_wait(lisreg_ctx* ctx, int32_t back) {
+  if (!ctx || back < 0 || back > 2) return fail(ctx, LISREG_ERR_ARG, "lisreg_allgather_wait: back must be 0..2");
   CK(cudaSetDevice(ctx->device));
-  if (ctx->comm_pending) { CK(cudaEventSynchronize(ctx->comm_done)); ctx->comm_pending = false; }
-  else CK(cudaStreamSynchronize(ctx->stream));
+  if (!ctx->comm) { if (back == 0) CK(cudaStreamSynchronize(ctx->stream)); return LISREG_OK; }
+  const int64_t k = ctx->comm_seq - 1 - back;          // the gather to wait for (and with it every earlier one)
+  if (k >= 0) CK(cudaEventSynchronize(ctx->comm_done[k % 4]));
   return LISREG_OK;
 }
 

@@ -6,11 +6,14 @@
 // point per occupied voxel in ASCENDING voxel index, value = fp32 centroid of x, y, z, intensity with the
 // points of a voxel accumulated in ascending input index.
 //
-// Implementation: (1) per-cloud bounding box -> plan, (2) key = voxel index, value = point index,
-// (3) stable LSD radix sort (8-bit digits, only the passes the largest voxel index needs; per pass: tile histograms -> per-cloud scan ->
-// stable scatter with warp match-any ranking), (4) head flags + per-cloud scan -> voxel starts,
-// (5) one thread per voxel sums its points in order.  The sorted order is also spatially coherent
-// (x fastest), which is what the kNN kernel wants from its query stream.
+// Implementation: (1) per-cloud bounding box -> plan, (2) key = voxel index per point, (2b) RUNS: consecutive input points
+// with the same key (a LiDAR ring crosses a 0.4 m voxel with ~5 consecutive returns) are collapsed into one (key, run id)
+// entry - the sort below then moves ~5x fewer elements and a voxel's points stay a handful of contiguous index ranges,
+// (3) stable LSD radix sort of the runs (8-bit digits, only the passes the largest voxel index needs; per pass: tile
+// histograms -> per-cloud scan -> stable scatter with warp match-any ranking), (4) head flags + per-cloud scan -> voxel
+// starts, (5) one thread per voxel walks its runs in order (= ascending input index: the sort is stable and runs are
+// index-ordered) and sums their points.  The sorted order is also spatially coherent (x fastest), which is what the kNN
+// kernel wants from its query stream.
 #pragma once
 #include <cstdint>
 #include <cfloat>
@@ -18,7 +21,7 @@
 
 namespace lisreg {
 
-struct VoxPlan { float inv; int minb[3]; int mul[3]; int overflow; int npass; };   // npass: 8-bit radix passes the largest key needs
+struct VoxPlan { float inv; int minb[3]; int mul[3]; int overflow; int npass; int n_runs; };   // npass: 8-bit radix passes the largest key needs; n_runs: entries to sort
 
 struct VoxSeg {
   const float4* src;       // source cloud
@@ -28,7 +31,8 @@ struct VoxSeg {
   float leaf;
   uint32_t* key_a; uint32_t* val_a; uint32_t* key_b; uint32_t* val_b;   // capacity cap each
   uint32_t* hist;          // 256 * nblk_cap
-  int* seg_start;          // cap + 1 : voxel starts (positions in the sorted arrays)
+  int* seg_start;          // cap + 1 : voxel starts (positions in the sorted run arrays)
+  int* run_start;          // cap + 1 : first input index of every run (run r = input points [run_start[r], run_start[r + 1]))
   VoxPlan* plan;
   unsigned* bbox;          // 6 order-preserving encoded floats (min xyz, max xyz)
   float4* out;             // cap
@@ -106,6 +110,7 @@ __global__ void k_vox_plan(VoxSeg* segs, int nseg) {
     for (int d = 0; d < 3; d++) { p.minb[d] = 0; p.mul[d] = 0; }
     p.npass = 0;
   }
+  p.n_runs = 0;
   *s.plan = p;
 }
 
@@ -124,7 +129,7 @@ __global__ void k_vox_keys(VoxSeg* segs) {
       const int i2 = (int)(floorf(q.z * p.inv) - (float)p.minb[2]);
       key = (uint32_t)(i0 * p.mul[0] + i1 * p.mul[1] + i2 * p.mul[2]);
     }
-    s.key_a[i] = key; s.val_a[i] = (uint32_t)i;
+    s.key_b[i] = key;          // per-point keys: input of the run detection, which fills key_a / val_a
   }
 }
 
@@ -132,7 +137,7 @@ __global__ void k_vox_keys(VoxSeg* segs) {
 __global__ void __launch_bounds__(RS_THREADS)
 k_rs_hist(VoxSeg* segs, int shift, int flip) {
   const VoxSeg s = segs[blockIdx.y];
-  const int n = vox_n(s);
+  const int n = s.plan->n_runs;
   const int nblk = (n + RS_TILE - 1) / RS_TILE;
   if ((int)blockIdx.x >= nblk || shift >= 8 * s.plan->npass) return;
   const uint32_t* key = flip ? s.key_b : s.key_a;
@@ -160,7 +165,7 @@ __global__ void __launch_bounds__(256)
 k_rs_scan_digit(VoxSeg* segs, int shift) {
   const VoxSeg s = segs[blockIdx.y];
   if (shift >= 8 * s.plan->npass) return;
-  const int n = vox_n(s);
+  const int n = s.plan->n_runs;
   const int nblk = (n + RS_TILE - 1) / RS_TILE;
   const int lane = threadIdx.x & 31, d = blockIdx.x * 8 + (threadIdx.x >> 5);
   uint32_t* __restrict__ h = s.hist + (size_t)d * nblk;
@@ -200,7 +205,7 @@ k_rs_scan_base(VoxSeg* segs, int nseg, int shift) {
 __global__ void k_rs_scan(VoxSeg* segs, int shift) {
   const VoxSeg s = segs[blockIdx.x];
   if (shift >= 8 * s.plan->npass) return;
-  const int n = vox_n(s);
+  const int n = s.plan->n_runs;
   const int nblk = (n + RS_TILE - 1) / RS_TILE;
   const int total = 256 * nblk;
   __shared__ uint32_t sm[1024];
@@ -230,7 +235,7 @@ __global__ void k_rs_scan(VoxSeg* segs, int shift) {
 __global__ void __launch_bounds__(RS_THREADS)
 k_rs_scatter(VoxSeg* segs, int shift, int flip) {
   const VoxSeg s = segs[blockIdx.y];
-  const int n = vox_n(s);
+  const int n = s.plan->n_runs;
   const int nblk = (n + RS_TILE - 1) / RS_TILE;
   if ((int)blockIdx.x >= nblk || shift >= 8 * s.plan->npass) return;
   const uint32_t* key = flip ? s.key_b : s.key_a;
@@ -294,13 +299,16 @@ k_rs_scatter(VoxSeg* segs, int shift, int flip) {
 constexpr int VH_CHUNK = RS_TILE;      // same tiling as the sort: (cap + RS_TILE - 1) / RS_TILE + 1 counters fit the histogram area
 __device__ __forceinline__ const uint32_t* vox_sorted_keys(const VoxSeg& s) { return (s.plan->npass & 1) ? s.key_b : s.key_a; }
 
+// RUNS = true: the same three steps on the UNSORTED per-point keys (key_b) detect the runs of equal consecutive keys and
+// fill the sort input: key_a[r] = key, val_a[r] = r, run_start[r] = first input index, plan->n_runs.
+template <bool RUNS>
 __global__ void __launch_bounds__(256)
 k_vox_head_count(VoxSeg* segs) {
   const VoxSeg s = segs[blockIdx.y];
-  const int n = vox_n(s);
+  const int n = RUNS ? vox_n(s) : s.plan->n_runs;
   const int c0 = blockIdx.x * VH_CHUNK;
   if (c0 >= n) return;
-  const uint32_t* __restrict__ skey = vox_sorted_keys(s);
+  const uint32_t* __restrict__ skey = RUNS ? s.key_b : vox_sorted_keys(s);
   int cnt = 0;
   for (int i = c0 + threadIdx.x; i < min(c0 + VH_CHUNK, n); i += blockDim.x) cnt += (i == 0 || skey[i] != skey[i - 1]) ? 1 : 0;
   __shared__ int s_w[8];
@@ -311,12 +319,13 @@ k_vox_head_count(VoxSeg* segs) {
   if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) t += s_w[w]; s.hist[blockIdx.x] = (uint32_t)t; }
 }
 // grid = ceil(nseg / 8), block = 256: one warp per cloud
+template <bool RUNS>
 __global__ void __launch_bounds__(256)
 k_vox_head_scan(VoxSeg* segs, int nseg) {
   const int si = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (si >= nseg) return;
   const VoxSeg s = segs[si];
-  const int n = vox_n(s);
+  const int n = RUNS ? vox_n(s) : s.plan->n_runs;
   const int nchunk = (n + VH_CHUNK - 1) / VH_CHUNK;
   uint32_t carry = 0u;
   for (int base = 0; base < nchunk; base += 32) {
@@ -328,15 +337,19 @@ k_vox_head_scan(VoxSeg* segs, int nseg) {
     if (i < nchunk) s.hist[i] = carry + incl - v;
     carry += __shfl_sync(0xffffffffu, incl, 31);
   }
-  if (lane == 0) { s.seg_start[carry] = n; *s.out_n = (int)carry; }
+  if (lane == 0) {
+    if (RUNS) { s.run_start[carry] = n; s.plan->n_runs = (int)carry; }
+    else { s.seg_start[carry] = n; *s.out_n = (int)carry; }
+  }
 }
+template <bool RUNS>
 __global__ void __launch_bounds__(256)
 k_vox_head_write(VoxSeg* segs) {
   const VoxSeg s = segs[blockIdx.y];
-  const int n = vox_n(s);
+  const int n = RUNS ? vox_n(s) : s.plan->n_runs;
   const int c0 = blockIdx.x * VH_CHUNK;
   if (c0 >= n) return;
-  const uint32_t* __restrict__ skey = vox_sorted_keys(s);
+  const uint32_t* __restrict__ skey = RUNS ? s.key_b : vox_sorted_keys(s);
   __shared__ int s_w[8];
   __shared__ int s_carry;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -350,7 +363,11 @@ k_vox_head_write(VoxSeg* segs) {
     __syncthreads();
     int off = s_carry;
     for (int w = 0; w < wid; w++) off += s_w[w];
-    if (head) s.seg_start[off + __popc(m & ((1u << lane) - 1u))] = i;
+    if (head) {
+      const int r = off + __popc(m & ((1u << lane) - 1u));
+      if (RUNS) { s.run_start[r] = i; s.key_a[r] = skey[i]; s.val_a[r] = (uint32_t)r; }
+      else s.seg_start[r] = i;
+    }
     __syncthreads();
     if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) t += s_w[w]; s_carry += t; }
     __syncthreads();
@@ -358,10 +375,11 @@ k_vox_head_write(VoxSeg* segs) {
 }
 
 // (4, many small clouds) voxel starts: one block (1024 threads) per cloud.  After npass passes the sorted data is in *_a (even) or *_b (odd).
+template <bool RUNS>
 __global__ void k_vox_heads(VoxSeg* segs) {
   const VoxSeg s = segs[blockIdx.x];
-  const int n = vox_n(s);
-  const uint32_t* skey = (s.plan->npass & 1) ? s.key_b : s.key_a;
+  const int n = RUNS ? vox_n(s) : s.plan->n_runs;
+  const uint32_t* skey = RUNS ? s.key_b : ((s.plan->npass & 1) ? s.key_b : s.key_a);
   __shared__ int s_w[32];
   __shared__ int carry, s_tot;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -383,48 +401,104 @@ __global__ void k_vox_heads(VoxSeg* segs) {
       if (lane == 31) s_tot = incl;
     }
     __syncthreads();
-    if (head) s.seg_start[carry + s_w[wid] + __popc(m & ((1u << lane) - 1u))] = i;
+    if (head) {
+      const int r = carry + s_w[wid] + __popc(m & ((1u << lane) - 1u));
+      if (RUNS) { s.run_start[r] = i; s.key_a[r] = skey[i]; s.val_a[r] = (uint32_t)r; }
+      else s.seg_start[r] = i;
+    }
     __syncthreads();
     if (threadIdx.x == 0) carry += s_tot;
     __syncthreads();
   }
-  if (threadIdx.x == 0) { s.seg_start[carry] = n; *s.out_n = carry; }
+  if (threadIdx.x == 0) {
+    if (RUNS) { s.run_start[carry] = n; s.plan->n_runs = carry; }
+    else { s.seg_start[carry] = n; *s.out_n = carry; }
+  }
 }
 
-// (5) centroids, fp32 accumulation in ascending input index (= sorted order inside a voxel: the sort is stable).
-// A block owns a chunk of VC_CHUNK sorted entries: all threads gather the chunk's points into shared memory with
-// coalesced index loads and VC_CHUNK / 256 independent gathers in flight per thread; then one thread per voxel that
-// STARTS in the chunk sums its entries in order out of shared memory (entries past the chunk end - a voxel that
-// straddles the boundary - come from global memory).  grid = (chunks_max, nseg)
-constexpr int VC_CHUNK = 2048;
+// (5) centroids, fp32 accumulation in ascending input index: the runs of a voxel are adjacent in the sorted arrays and -
+// the sort being stable - in ascending run id = ascending input index; inside a run the points are consecutive inputs.
+// One thread per voxel (grid-stride).  A thread's loads are a chain of dependent round trips (index list -> point), so the
+// points of a run are fetched four at a time (four index loads, then four point loads in flight) and added in order.
+// Two other decompositions were measured on the 256-frame batch and dropped (profiles/r02_summary.md): staging the chunk's
+// points in shared memory first (the barriers and the per-chunk binary search cost more than the loads they save) and the
+// round-1 kernel on a re-expanded point list.  grid = (blocks, nseg)
+constexpr int VC_CHUNK = 2048;     // host: blocks = ceil(max_n / VC_CHUNK) per cloud (voxels are dealt out grid-stride)
 __global__ void __launch_bounds__(256)
 k_vox_centroid(VoxSeg* segs) {
   const VoxSeg s = segs[blockIdx.y];
-  const int n = vox_n(s);
-  const int c0 = blockIdx.x * VC_CHUNK;
-  if (c0 >= n) return;
-  const int c1 = min(c0 + VC_CHUNK, n);
   const int m = *s.out_n;
-  const uint32_t* sval = (s.plan->npass & 1) ? s.val_b : s.val_a;
-  __shared__ float4 s_pts[VC_CHUNK];
-  __shared__ int s_vlo, s_vhi;
-  for (int j = c0 + threadIdx.x; j < c1; j += blockDim.x) s_pts[j - c0] = vox_point(s, (int)sval[j]);
-  if (threadIdx.x < 2) {
-    // first voxel whose start is >= c0 (thread 0) / >= c1 (thread 1): binary search over seg_start[0..m]
-    const int target = threadIdx.x == 0 ? c0 : c1;
-    int lo = 0, hi = m;                       // seg_start[m] = n >= target
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s.seg_start[mid] >= target) hi = mid; else lo = mid + 1; }
-    if (threadIdx.x == 0) s_vlo = lo; else s_vhi = lo;
-  }
-  __syncthreads();
-  for (int v = s_vlo + threadIdx.x; v < s_vhi; v += blockDim.x) {
-    const int b = s.seg_start[v], e = s.seg_start[v + 1];
+  const uint32_t* __restrict__ sval = (s.plan->npass & 1) ? s.val_b : s.val_a;
+  const float4* __restrict__ src = s.src;
+  const int* __restrict__ gat = s.gather;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < m; v += gridDim.x * blockDim.x) {
+    const int rb = s.seg_start[v], re = s.seg_start[v + 1];
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-    const int e_in = min(e, c1);
-    for (int j = b; j < e_in; j++) { const float4 p = s_pts[j - c0]; sx += p.x; sy += p.y; sz += p.z; si += p.w; }
-    for (int j = e_in; j < e; j++) { const float4 p = vox_point(s, (int)sval[j]); sx += p.x; sy += p.y; sz += p.z; si += p.w; }
-    const float c = (float)(e - b);
+    int cnt = 0;
+    for (int r = rb; r < re; r++) {
+      const int run = (int)sval[r];
+      const int a = s.run_start[run], e = s.run_start[run + 1];
+      int j = a;
+      for (; j + 4 <= e; j += 4) {
+        int i0 = j, i1 = j + 1, i2 = j + 2, i3 = j + 3;
+        if (gat) { i0 = gat[j]; i1 = gat[j + 1]; i2 = gat[j + 2]; i3 = gat[j + 3]; }
+        const float4 p0 = __ldg(&src[i0]), p1 = __ldg(&src[i1]), p2 = __ldg(&src[i2]), p3 = __ldg(&src[i3]);
+        sx += p0.x; sy += p0.y; sz += p0.z; si += p0.w;
+        sx += p1.x; sy += p1.y; sz += p1.z; si += p1.w;
+        sx += p2.x; sy += p2.y; sz += p2.z; si += p2.w;
+        sx += p3.x; sy += p3.y; sz += p3.z; si += p3.w;
+      }
+      for (; j < e; j++) { const float4 p = vox_point(s, j); sx += p.x; sy += p.y; sz += p.z; si += p.w; }
+      cnt += e - a;
+    }
+    const float c = (float)cnt;
     s.out[v] = make_float4(sx / c, sy / c, sz / c, si / c);
+  }
+}
+
+// (5, a few large clouds: the sliding-window map, submap classes) the same sums with one WARP per voxel.  A map voxel holds
+// ~100 points in ~20 runs (one or two per key frame); a single thread would walk them through ~50 dependent round trips.
+// Here the lanes fetch the points of up to 32 runs at a time in parallel into shared memory (flattened point list, the run
+// of a point found by comparing against the shuffled run offsets) and lane 0 adds them in order.  grid = (blocks, nseg)
+constexpr int VCW_PTS = 256;       // staged points per warp and pass
+__global__ void __launch_bounds__(256)
+k_vox_centroid_warp(VoxSeg* segs) {
+  const VoxSeg s = segs[blockIdx.y];
+  const int m = *s.out_n;
+  const uint32_t* __restrict__ sval = (s.plan->npass & 1) ? s.val_b : s.val_a;
+  __shared__ float4 s_pts[8][VCW_PTS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned FULL = 0xffffffffu;
+  for (int v = blockIdx.x * 8 + wid; v < m; v += gridDim.x * 8) {
+    const int rb = s.seg_start[v], re = s.seg_start[v + 1];
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    int cnt = 0;
+    for (int r0 = rb; r0 < re; r0 += 32) {                       // up to 32 runs per pass, in sorted (= input) order
+      const int nr = min(32, re - r0);
+      int a = 0, len = 0;
+      if (lane < nr) { const int run = (int)sval[r0 + lane]; a = s.run_start[run]; len = s.run_start[run + 1] - a; }
+      int incl = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+      const int off = incl - len;                                // exclusive offset of this lane's run
+      const int T = __shfl_sync(FULL, incl, 31);
+      for (int q0 = 0; q0 < T; q0 += VCW_PTS) {                  // batches of the flattened point list
+        const int qn = min(VCW_PTS, T - q0);
+        for (int q = q0 + lane; q < q0 + VCW_PTS; q += 32) {     // uniform trip count: the shuffles below need every lane
+          int rr = 0;                                            // run of point q = number of runs whose offset is <= q, minus 1
+#pragma unroll 1
+          for (int r = 1; r < nr; r++) rr += (__shfl_sync(FULL, off, r) <= q) ? 1 : 0;
+          const int ra = __shfl_sync(FULL, a, rr), ro = __shfl_sync(FULL, off, rr);
+          if (q < q0 + qn) s_pts[wid][q - q0] = vox_point(s, ra + (q - ro));
+        }
+        __syncwarp();
+        if (lane == 0)
+          for (int k = 0; k < qn; k++) { const float4 p = s_pts[wid][k]; sx += p.x; sy += p.y; sz += p.z; si += p.w; }
+        __syncwarp();
+      }
+      cnt += T;
+    }
+    if (lane == 0) { const float c = (float)cnt; s.out[v] = make_float4(sx / c, sy / c, sz / c, si / c); }
   }
 }
 

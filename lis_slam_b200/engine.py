@@ -304,7 +304,7 @@ def lib():
         L.lisreg_allgather_results.restype = i32
         L.lisreg_allgather_results.argtypes = [vp, vp, vp, C.c_uint64]
         L.lisreg_allgather_wait.restype = i32
-        L.lisreg_allgather_wait.argtypes = [vp]
+        L.lisreg_allgather_wait.argtypes = [vp, i32]
         L.lisreg_profile_enable.restype = i32
         L.lisreg_profile_enable.argtypes = [vp, i32]
         L.lisreg_profile_get.restype = i32
@@ -752,8 +752,8 @@ class Engine:
     def allgather_results(self, d_send_ptr, d_recv_ptr, bytes_per_rank):
         self._ck(lib().lisreg_allgather_results(self._h, d_send_ptr, d_recv_ptr, bytes_per_rank))
 
-    def allgather_wait(self):
-        self._ck(lib().lisreg_allgather_wait(self._h))
+    def allgather_wait(self, back=0):
+        self._ck(lib().lisreg_allgather_wait(self._h, back))
 
     def profile_enable(self, on=True):
         self._ck(lib().lisreg_profile_enable(self._h, 1 if on else 0))
