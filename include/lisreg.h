@@ -315,7 +315,16 @@ typedef struct lisreg_odom_params {
   float keyframe_min_yaw;           /* keyFrameMiniYaw 0.5 (:141) */
   int32_t window;                   /* 19: while (laserCloudSurfVec.size() >= 20) erase(begin) (:463-467) */
   int32_t use_graph;
+  int32_t use_imu_heading_initialization;   /* useImuHeadingInitialization (config/params.yaml:77): keep imuYawInit on the first frame */
+  float imu_rpy_weight;             /* imuRPYWeight 0.01 (utility.h:405): slerp weight of transformUpdate (:982-997) */
 } lisreg_odom_params;
+/* the scalar hints of lis_slam::cloud_info (msg/cloud_info.msg:4-19) that updateInitialGuess (:297-419) and transformUpdate
+ * (:976-999) read; the clouds of the message are what lisreg_odom_push extracts itself */
+typedef struct lisreg_cloud_info {
+  int32_t imu_available, odom_available;
+  float imu_roll_init, imu_pitch_init, imu_yaw_init;
+  float initial_guess[6];           /* initialGuessX, Y, Z, Roll, Pitch, Yaw (message order) */
+} lisreg_cloud_info;
 typedef struct lisreg_odom_result {
   lisreg_lm_result lm;              /* status / iterations / deltaR / deltaT of this frame's loop (zeros for the first frame) */
   int32_t frame_id, keyframe_id;    /* frames pushed so far, keyFrameId after this frame */
@@ -330,6 +339,19 @@ int32_t lisreg_odom_destroy(lisreg_ctx* ctx, int32_t odom_id);
  * (imuRollInit / PitchInit / YawInit + origin upstream), ignored afterwards */
 int32_t lisreg_odom_push(lisreg_ctx* ctx, int32_t odom_id, const float* pts, const uint16_t* ring, int32_t n,
                          const float* init_pose6, float pose6[6], lisreg_odom_result* res);
+/* the same frame step with the cloud_info hints (info != NULL): first frame = [imuRollInit, imuPitchInit, imuYawInit or 0];
+ * odomAvailable: pose *= lastImuPreTransformation^-1 * initialGuess (:322-349); otherwise the constant-velocity guess
+ * (:353-391); imuAvailable on the frame that first sees odomAvailable: rotation increment of the IMU attitude (:394-417);
+ * after the loop, imuAvailable and |imuPitchInit| < 1.4 pull roll / pitch toward the IMU by a tf slerp (transformUpdate).
+ * on_device != 0: pts / ring are device pointers.  info == NULL behaves as lisreg_odom_push with init_pose6 == NULL. */
+int32_t lisreg_odom_push_info(lisreg_ctx* ctx, int32_t odom_id, const float* pts, const uint16_t* ring, int32_t n, int32_t on_device,
+                              const lisreg_cloud_info* info, float pose6[6], lisreg_odom_result* res);
+/* transformUpdate on its own (odomEstimationNode.cpp:976-1006; the same body at subMapOptmizationNode.cpp:1969-1996 and
+ * :4968-4995 for a caller that drives lisreg_scan2map variant 'B' / 'C' itself): IMU roll / pitch slerp when
+ * info->imu_available and |imu_pitch_init| < 1.4, then the roll / pitch / z clamps (tolerance <= 0 disables).  Host arithmetic
+ * on six floats, no device work.  info may be NULL (clamps only). */
+void lisreg_transform_update(const lisreg_cloud_info* info, float imu_rpy_weight, float rot_tolerance, float z_tolerance,
+                             float pose6[6]);
 /* same with the sweep already resident in HBM */
 int32_t lisreg_odom_push_dev(lisreg_ctx* ctx, int32_t odom_id, const float* d_pts, const uint16_t* d_ring, int32_t n,
                              const float* init_pose6, float pose6[6], lisreg_odom_result* res);

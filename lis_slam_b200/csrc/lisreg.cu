@@ -122,6 +122,10 @@ struct lisreg_ctx {
     lisreg_odom_params prm{};
     float pose[6] = {0, 0, 0, 0, 0, 0}, last_pose[6] = {0, 0, 0, 0, 0, 0}, key_pose[6] = {0, 0, 0, 0, 0, 0};   // transformTobeMapped, lastTransformTobeMapped, transformPriFrame
     bool first_trans = false, have_last = false, first_flag = true;
+    float last_imu[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};      // lastImuTransformation
+    float last_imu_pre[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};  // lastImuPreTransformation
+    bool have_imu_pre = false;             // lastImuPreTransAvailable
+    float rot_tol = 0.f, z_tol = 0.f;      // transformUpdate clamps: applied on the host after the IMU slerp (the device loop runs without)
     float deltaR = 100.f, deltaT = 100.f;
     int keyframe_id = 0, frame_id = 0;
     int slots = 0, ccap = 0, scap = 0;     // ring of key-frame slots: capacities per slot (corner / surface points)
@@ -1889,6 +1893,8 @@ void lisreg_odom_params_default(lisreg_odom_params* p) {
   p->keyframe_min_distance = 1.4f; p->keyframe_min_yaw = 0.5f;   // config/params.yaml:140-141
   p->window = 19;                                                 // odomEstimationNode.cpp:463
   p->use_graph = 1;
+  p->use_imu_heading_initialization = 0;                          // config/params.yaml:77
+  p->imu_rpy_weight = 0.01f;                                      // utility.h:405 (the shipped yaml sets 0.1)
 }
 
 int32_t lisreg_odom_create(lisreg_ctx* ctx, const lisreg_odom_params* prm, int32_t* odom_id) {
@@ -1906,6 +1912,8 @@ int32_t lisreg_odom_create(lisreg_ctx* ctx, const lisreg_odom_params* prm, int32
   lisreg_ctx::Odom& O = ctx->odoms[slot];
   O = lisreg_ctx::Odom();
   O.prm = *prm;
+  O.rot_tol = prm->frame.lm.rot_tolerance; O.z_tol = prm->frame.lm.z_tolerance;
+  O.prm.frame.lm.rot_tolerance = 0.f; O.prm.frame.lm.z_tolerance = 0.f;   // see odom_transform_update
   O.slots = prm->window + 1;
   O.ccap = fp.n_scan * 120; O.scap = fp.n_scan * fp.horizon;
   CK(cudaMalloc(&O.d_win_c, sizeof(float4) * (size_t)O.ccap * O.slots));
@@ -1954,19 +1962,112 @@ int32_t lisreg_odom_destroy(lisreg_ctx* ctx, int32_t odom_id) {
 }
 
 // updateInitialGuess, cloudInfo.odomAvailable == false branch (:298-313, :343-383)
-static void odom_update_initial_guess(lisreg_ctx::Odom& O, const float* init_pose6) {
+static void odom_imu_T16(const lisreg_cloud_info* info, float T[16]) {
+  const float p[6] = {info->imu_roll_init, info->imu_pitch_init, info->imu_yaw_init, 0.f, 0.f, 0.f};
+  odom_T16(p, T);
+}
+// updateInitialGuess (:297-419).  info == NULL: no hints (odomAvailable = imuAvailable = false), first pose = init_pose6 or 0
+static void odom_update_initial_guess(lisreg_ctx::Odom& O, const float* init_pose6, const lisreg_cloud_info* info) {
   if (!O.first_trans) {
-    for (int i = 0; i < 6; i++) O.pose[i] = init_pose6 ? init_pose6[i] : 0.f;
+    if (info) {
+      O.pose[0] = info->imu_roll_init; O.pose[1] = info->imu_pitch_init;
+      O.pose[2] = O.prm.use_imu_heading_initialization ? info->imu_yaw_init : 0.f;
+      O.pose[3] = O.pose[4] = O.pose[5] = 0.f;
+      odom_imu_T16(info, O.last_imu);
+    } else {
+      for (int i = 0; i < 6; i++) O.pose[i] = init_pose6 ? init_pose6[i] : 0.f;
+    }
     O.first_trans = true;
     return;
   }
-  if (!O.have_last) { memcpy(O.last_pose, O.pose, sizeof(O.pose)); O.have_last = true; return; }
-  float Tb[16], Tl[16], Tli[16], Ti[16], Tf[16];
-  odom_T16(O.pose, Tb); odom_T16(O.last_pose, Tl);
-  memcpy(O.last_pose, O.pose, sizeof(O.pose));
-  odom_inv(Tl, Tli); odom_mul(Tli, Tb, Ti);       // transIncre = transLast.inverse() * transBack
-  odom_mul(Tb, Ti, Tf);                           // transFinal = transTobe * transIncre
-  odom_euler(Tf, O.pose);
+  float Tb[16], Tl[16], Tli[16], Ti[16], Tt[16], Tf[16];
+  if (info && info->odom_available) {
+    const float g[6] = {info->initial_guess[3], info->initial_guess[4], info->initial_guess[5],
+                        info->initial_guess[0], info->initial_guess[1], info->initial_guess[2]};
+    odom_T16(g, Tb);
+    if (!O.have_imu_pre) {
+      memcpy(O.last_imu_pre, Tb, sizeof(Tb)); O.have_imu_pre = true;     // falls through to the imuAvailable block (:327-330)
+    } else {
+      odom_inv(O.last_imu_pre, Tli); odom_mul(Tli, Tb, Ti);              // transIncre = lastImuPreTransformation.inverse() * transBack
+      odom_T16(O.pose, Tt); odom_mul(Tt, Ti, Tf);                        // transFinal = transTobe * transIncre
+      odom_euler(Tf, O.pose);
+      memcpy(O.last_imu_pre, Tb, sizeof(Tb));
+      odom_imu_T16(info, O.last_imu);
+      return;
+    }
+  }
+  if (!info || !info->odom_available) {
+    if (!O.have_last) { memcpy(O.last_pose, O.pose, sizeof(O.pose)); O.have_last = true; return; }
+    odom_T16(O.pose, Tb); odom_T16(O.last_pose, Tl);
+    memcpy(O.last_pose, O.pose, sizeof(O.pose));
+    odom_inv(Tl, Tli); odom_mul(Tli, Tb, Ti);       // transIncre = transLast.inverse() * transBack
+    odom_mul(Tb, Ti, Tf);                           // transFinal = transTobe * transIncre
+    odom_euler(Tf, O.pose);
+    return;
+  }
+  if (info->imu_available) {                        // rotation increment of the IMU attitude (:394-417)
+    odom_imu_T16(info, Tb);
+    odom_inv(O.last_imu, Tli); odom_mul(Tli, Tb, Ti);
+    odom_T16(O.pose, Tt); odom_mul(Tt, Ti, Tf);
+    odom_euler(Tf, O.pose);
+    memcpy(O.last_imu, Tb, sizeof(Tb));
+  }
+}
+
+// transformUpdate (:976-1006).  tf (ROS geometry LinearMath) is not part of the reference tree; its Quaternion::setRPY /
+// slerp / Matrix3x3::getRPY are written out here in double (tfScalar) for the two single-axis cases the function uses:
+// for a pure roll (or pure pitch) pair the quaternions are (sin h, 0, 0, cos h), and getRPY of the slerp result reads the
+// angle back through the rotation matrix exactly as tf does.
+struct OdomQuat { double x, y, z, w; };
+static OdomQuat odom_quat_rpy(double roll, double pitch, double yaw) {
+  const double hy = yaw * 0.5, hp = pitch * 0.5, hr = roll * 0.5;
+  const double cy = cos(hy), sy = sin(hy), cp = cos(hp), sp = sin(hp), cr = cos(hr), sr = sin(hr);
+  return {sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy};
+}
+static double odom_quat_dot(const OdomQuat& a, const OdomQuat& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+static OdomQuat odom_quat_slerp(const OdomQuat& a, const OdomQuat& b, double t) {
+  const double s = sqrt(odom_quat_dot(a, a) * odom_quat_dot(b, b)), d = odom_quat_dot(a, b);
+  const double theta = (d < 0 ? acos(-d / s) * 2.0 : acos(d / s) * 2.0) / 2.0;     // angleShortestPath(q) / 2
+  if (theta == 0.0) return a;
+  const double inv = 1.0 / sin(theta), s0 = sin((1.0 - t) * theta), s1 = sin(t * theta);
+  const double sg = d < 0 ? -1.0 : 1.0;
+  return {(a.x * s0 + sg * b.x * s1) * inv, (a.y * s0 + sg * b.y * s1) * inv, (a.z * s0 + sg * b.z * s1) * inv, (a.w * s0 + sg * b.w * s1) * inv};
+}
+static void odom_quat_get_rpy(const OdomQuat& q, double* roll, double* pitch, double* yaw) {
+  const double s = 2.0 / odom_quat_dot(q, q);
+  const double xs = q.x * s, ys = q.y * s, zs = q.z * s;
+  const double wx = q.w * xs, wy = q.w * ys, wz = q.w * zs, xx = q.x * xs, xy = q.x * ys, xz = q.x * zs, yy = q.y * ys, yz = q.y * zs, zz = q.z * zs;
+  const double m00 = 1.0 - (yy + zz), m10 = xy + wz, m20 = xz - wy, m21 = yz + wx, m22 = 1.0 - (xx + yy);
+  if (fabs(m20) >= 1) {                                                // gimbal lock branch of getEulerYPR
+    *yaw = 0; *roll = atan2(m21, m22); *pitch = m20 < 0 ? M_PI / 2.0 : -M_PI / 2.0;
+  } else {
+    *pitch = -asin(m20);
+    const double c = cos(*pitch);
+    *roll = atan2(m21 / c, m22 / c); *yaw = atan2(m10 / c, m00 / c);
+  }
+}
+static float odom_clamp(float v, float lim) {      // constraintTransformation (src/core/common.cpp:286-292); lim <= 0 disables
+  if (!(lim > 0.f)) return v;
+  if (v < -lim) v = -lim;
+  if (v > lim) v = lim;
+  return v;
+}
+void lisreg_transform_update(const lisreg_cloud_info* info, float imu_rpy_weight, float rot_tolerance, float z_tolerance, float pose6[6]) {
+  if (!pose6) return;
+  if (info && info->imu_available && std::abs(info->imu_pitch_init) < 1.4) {
+    const double w = imu_rpy_weight;
+    double r, p, y;
+    odom_quat_get_rpy(odom_quat_slerp(odom_quat_rpy(pose6[0], 0, 0), odom_quat_rpy(info->imu_roll_init, 0, 0), w), &r, &p, &y);
+    pose6[0] = (float)r;
+    odom_quat_get_rpy(odom_quat_slerp(odom_quat_rpy(0, pose6[1], 0), odom_quat_rpy(0, info->imu_pitch_init, 0), w), &r, &p, &y);
+    pose6[1] = (float)p;
+  }
+  pose6[0] = odom_clamp(pose6[0], rot_tolerance);
+  pose6[1] = odom_clamp(pose6[1], rot_tolerance);
+  pose6[5] = odom_clamp(pose6[5], z_tolerance);
+}
+static void odom_transform_update(lisreg_ctx::Odom& O, const lisreg_cloud_info* info) {
+  lisreg_transform_update(info, O.prm.imu_rpy_weight, O.rot_tol, O.z_tol, O.pose);
 }
 
 // saveKeyFrames (:421-478): the frame's full corner / surface clouds, moved by the refined pose, enter the window
@@ -2043,7 +2144,7 @@ static std::vector<const void*> odom_graph_key(lisreg_ctx* ctx, lisreg_ctx::Odom
 }
 
 static int odom_push_impl(lisreg_ctx* ctx, int32_t odom_id, const float* pts, const uint16_t* ring, int32_t n, bool on_device,
-                          const float* init_pose6, float pose6[6], lisreg_odom_result* res) {
+                          const float* init_pose6, const lisreg_cloud_info* info, float pose6[6], lisreg_odom_result* res) {
   if (!ctx || odom_id < 0 || odom_id >= (int)ctx->odoms.size() || !ctx->odoms[odom_id].used || n < 0 || (n > 0 && !pts) || !pose6 || !res)
     return fail(ctx, LISREG_ERR_ARG, "lisreg_odom_push: bad argument");
   CK(cudaSetDevice(ctx->device));
@@ -2066,7 +2167,7 @@ static int odom_push_impl(lisreg_ctx* ctx, int32_t odom_id, const float* pts, co
     }
     d_pts = (const float4*)O.d_in.p; d_ring = ring_arr ? (const uint16_t*)((char*)O.d_in.p + bp) : nullptr;
   }
-  odom_update_initial_guess(O, init_pose6);
+  odom_update_initial_guess(O, init_pose6, info);
   O.frame_id++;
   memcpy(res->guess, O.pose, sizeof(O.pose));
   // io block: [pose6 in/out][lm result][4 feature counts], device + pinned mirror
@@ -2163,6 +2264,8 @@ static int odom_push_impl(lisreg_ctx* ctx, int32_t odom_id, const float* pts, co
     res->lm = *lr;
     if (lr->status != LISREG_NOT_ENOUGH_FEATURES) {
       memcpy(O.pose, lr->pose, sizeof(O.pose));
+      odom_transform_update(O, info);
+      memcpy(res->lm.pose, O.pose, sizeof(O.pose));
       if (!(lr->deltaR == 100.f && lr->deltaT == 100.f)) { O.deltaR = lr->deltaR; O.deltaT = lr->deltaT; }   // members (:70-71) keep the last solved step
     }
     // key-frame rule (:216-229)
@@ -2185,11 +2288,15 @@ static int odom_push_impl(lisreg_ctx* ctx, int32_t odom_id, const float* pts, co
 
 int32_t lisreg_odom_push(lisreg_ctx* ctx, int32_t odom_id, const float* pts, const uint16_t* ring, int32_t n,
                          const float* init_pose6, float pose6[6], lisreg_odom_result* res) {
-  return odom_push_impl(ctx, odom_id, pts, ring, n, false, init_pose6, pose6, res);
+  return odom_push_impl(ctx, odom_id, pts, ring, n, false, init_pose6, nullptr, pose6, res);
 }
 int32_t lisreg_odom_push_dev(lisreg_ctx* ctx, int32_t odom_id, const float* d_pts, const uint16_t* d_ring, int32_t n,
                              const float* init_pose6, float pose6[6], lisreg_odom_result* res) {
-  return odom_push_impl(ctx, odom_id, d_pts, d_ring, n, true, init_pose6, pose6, res);
+  return odom_push_impl(ctx, odom_id, d_pts, d_ring, n, true, init_pose6, nullptr, pose6, res);
+}
+int32_t lisreg_odom_push_info(lisreg_ctx* ctx, int32_t odom_id, const float* pts, const uint16_t* ring, int32_t n, int32_t on_device,
+                              const lisreg_cloud_info* info, float pose6[6], lisreg_odom_result* res) {
+  return odom_push_impl(ctx, odom_id, pts, ring, n, on_device != 0, nullptr, info, pose6, res);
 }
 
 // ------------------------------------------------------------------------------------------------

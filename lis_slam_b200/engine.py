@@ -99,7 +99,14 @@ class FrameItem(C.Structure):
 
 class OdomParams(C.Structure):
     _fields_ = [("frame", FrameParams), ("keyframe_min_distance", C.c_float), ("keyframe_min_yaw", C.c_float),
-                ("window", C.c_int32), ("use_graph", C.c_int32)]
+                ("window", C.c_int32), ("use_graph", C.c_int32), ("use_imu_heading_initialization", C.c_int32),
+                ("imu_rpy_weight", C.c_float)]
+
+
+class CloudInfo(C.Structure):
+    """lisreg_cloud_info: the scalar hints of lis_slam::cloud_info (msg/cloud_info.msg:4-19)."""
+    _fields_ = [("imu_available", C.c_int32), ("odom_available", C.c_int32), ("imu_roll_init", C.c_float),
+                ("imu_pitch_init", C.c_float), ("imu_yaw_init", C.c_float), ("initial_guess", C.c_float * 6)]
 
 
 class OdomResult(C.Structure):
@@ -269,6 +276,10 @@ def lib():
         L.lisreg_odom_destroy.argtypes = [vp, i32]
         L.lisreg_odom_push.restype = i32
         L.lisreg_odom_push.argtypes = [vp, i32, vp, vp, i32, vp, fp, C.POINTER(OdomResult)]
+        L.lisreg_odom_push_info.restype = i32
+        L.lisreg_odom_push_info.argtypes = [vp, i32, vp, vp, i32, i32, C.POINTER(CloudInfo), fp, C.POINTER(OdomResult)]
+        L.lisreg_transform_update.restype = None
+        L.lisreg_transform_update.argtypes = [C.POINTER(CloudInfo), C.c_float, C.c_float, C.c_float, fp]
         L.lisreg_odom_push_dev.restype = i32
         L.lisreg_odom_push_dev.argtypes = [vp, i32, vp, vp, i32, vp, fp, C.POINTER(OdomResult)]
         L.lisreg_submap_create.restype = i32
@@ -335,6 +346,24 @@ def frame_params(variant="A", **lm_kw):
     lib().lisreg_lm_params_preset(C.byref(p.lm), variant.encode())
     for k, v in lm_kw.items():
         setattr(p.lm, k, v)
+    return p
+
+
+def cloud_info(imu_available=False, odom_available=False, imu_rpy=(0.0, 0.0, 0.0), initial_guess=(0, 0, 0, 0, 0, 0)):
+    """lisreg_cloud_info from the message's scalar fields; initial_guess = (x, y, z, roll, pitch, yaw)."""
+    ci = CloudInfo()
+    ci.imu_available, ci.odom_available = int(bool(imu_available)), int(bool(odom_available))
+    ci.imu_roll_init, ci.imu_pitch_init, ci.imu_yaw_init = (float(v) for v in imu_rpy)
+    for i, v in enumerate(initial_guess):
+        ci.initial_guess[i] = float(v)
+    return ci
+
+
+def transform_update(pose6, info, imu_rpy_weight=0.01, rot_tolerance=0.0, z_tolerance=0.0):
+    """lisreg_transform_update: host arithmetic only (no device).  Returns the new pose6."""
+    p = np.array(pose6, dtype=np.float32).copy()
+    lib().lisreg_transform_update(None if info is None else C.byref(info), imu_rpy_weight, rot_tolerance, z_tolerance,
+                                  p.ctypes.data_as(C.POINTER(C.c_float)))
     return p
 
 
@@ -572,6 +601,18 @@ class Engine:
         ip = None if init_pose is None else np.ascontiguousarray(init_pose, np.float32)
         self.last_status = self._ck(lib().lisreg_odom_push(self._h, oid, p.ctypes.data, g.ctypes.data, len(p), _ptr(ip),
                                                            pose.ctypes.data_as(C.POINTER(C.c_float)), C.byref(res)))
+        return pose, res
+
+    def odom_push_info(self, oid, pts, ring, info, on_device=False, n=None):
+        """One sweep with the cloud_info hints (CloudInfo or None).  on_device: pts / ring are device pointers, n given."""
+        pose = np.zeros(6, np.float32); res = OdomResult()
+        if on_device:
+            pp, gp, cnt = pts, ring, n
+        else:
+            p = _f4(pts); g = _u16(ring); pp, gp, cnt = p.ctypes.data, g.ctypes.data, len(p)
+        self.last_status = self._ck(lib().lisreg_odom_push_info(self._h, oid, pp, gp, cnt, 1 if on_device else 0,
+                                                                None if info is None else C.byref(info),
+                                                                pose.ctypes.data_as(C.POINTER(C.c_float)), C.byref(res)))
         return pose, res
 
     def odom_push_dev(self, oid, d_pts_ptr, d_ring_ptr, n, init_pose=None):

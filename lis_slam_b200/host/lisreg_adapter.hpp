@@ -240,6 +240,27 @@ class Odometry {
     if (last.frame_id > 1 && !(last.lm.deltaR == 100.f && last.lm.deltaT == 100.f)) { deltaR = last.lm.deltaR; deltaT = last.lm.deltaT; }
     return rc;
   }
+  // laserCloudInfoHandler (odomEstimationNode.cpp:163-239) with the message's hints: any type with the scalar members of
+  // lis_slam::cloud_info (imuAvailable, odomAvailable, imuRollInit .. initialGuessYaw) - the ROS message itself qualifies
+  template <typename InfoT> static lisreg_cloud_info hintsOf(const InfoT& m) {
+    lisreg_cloud_info ci;
+    ci.imu_available = m.imuAvailable ? 1 : 0; ci.odom_available = m.odomAvailable ? 1 : 0;
+    ci.imu_roll_init = m.imuRollInit; ci.imu_pitch_init = m.imuPitchInit; ci.imu_yaw_init = m.imuYawInit;
+    ci.initial_guess[0] = m.initialGuessX; ci.initial_guess[1] = m.initialGuessY; ci.initial_guess[2] = m.initialGuessZ;
+    ci.initial_guess[3] = m.initialGuessRoll; ci.initial_guess[4] = m.initialGuessPitch; ci.initial_guess[5] = m.initialGuessYaw;
+    return ci;
+  }
+  template <typename CloudT, typename InfoT> int pushInfo(const CloudT& laserCloudIn, const InfoT& cloudInfo) {
+    return pushRawInfo(laserCloudIn.points.data(), (int32_t)laserCloudIn.points.size(), cloudInfo);
+  }
+  template <typename InfoT> int pushRawInfo(const void* records, int32_t n, const InfoT& cloudInfo) {
+    const lisreg_cloud_info ci = hintsOf(cloudInfo);
+    const int rc = lisreg_odom_push_info(ctx_, id_, (const float*)records, nullptr, n, 0, &ci, transformTobeMapped, &last);
+    if (rc < 0) throw std::runtime_error(std::string("lisreg: ") + lisreg_last_error(ctx_));
+    keyFrameId = last.keyframe_id;
+    if (last.frame_id > 1 && !(last.lm.deltaR == 100.f && last.lm.deltaT == 100.f)) { deltaR = last.lm.deltaR; deltaT = last.lm.deltaT; }
+    return rc;
+  }
 
  private:
   lisreg_ctx* ctx_ = nullptr;

@@ -87,7 +87,8 @@ def transform_cloud(pts4, pose6):
 
 
 class OdometryStream:
-    def __init__(self, backend, lm_params, feat_params=None, corner_leaf=0.2, surf_leaf=0.4):
+    def __init__(self, backend, lm_params, feat_params=None, corner_leaf=0.2, surf_leaf=0.4, use_imu_heading=False,
+                 imu_rpy_weight=0.01, transform_update=None):
         self.be, self.prm, self.fprm = backend, lm_params, feat_params
         self.corner_leaf, self.surf_leaf = corner_leaf, surf_leaf
         self.pose = np.zeros(6, np.float32)          # transformTobeMapped
@@ -98,21 +99,54 @@ class OdometryStream:
         self.first = True
         self.first_trans = False
         self.deltaR, self.deltaT = f32(100), f32(100)     # members (:70-71): keep the last solved step across frames
+        self.use_imu_heading = use_imu_heading            # useImuHeadingInitialization
+        self.imu_rpy_weight = imu_rpy_weight              # imuRPYWeight
+        self.transform_update = transform_update          # callable(pose6, imu_available, imu_roll, imu_pitch, weight, rot_tol, z_tol) -> pose6
+        self.last_imu = np.eye(4, dtype=f32)              # lastImuTransformation
+        self.last_imu_pre = None                          # lastImuPreTransformation (None = lastImuPreTransAvailable false)
         self.trajectory, self.results = [], []
 
-    def _update_initial_guess(self, initial_pose):
-        """updateInitialGuess, cloudInfo.odomAvailable == false (:298-313, :343-383), Affine3f arithmetic in fp32."""
+    def _update_initial_guess(self, initial_pose, info=None):
+        """updateInitialGuess (:297-419), Affine3f arithmetic in fp32.  info = None: no hints (odomAvailable = imuAvailable =
+        false; first pose = initial_pose); else a dict with imu_available, odom_available, imu_rpy (3), initial_guess (x, y, z,
+        roll, pitch, yaw) - the scalar fields of lis_slam::cloud_info."""
         if not self.first_trans:
-            self.pose = np.zeros(6, f32) if initial_pose is None else np.asarray(initial_pose, f32).copy()
+            if info is not None:
+                r, p, y = (f32(v) for v in info["imu_rpy"])
+                self.pose = np.array([r, p, y if self.use_imu_heading else 0, 0, 0, 0], f32)
+                self.last_imu = _T16([r, p, y, 0, 0, 0])
+            else:
+                self.pose = np.zeros(6, f32) if initial_pose is None else np.asarray(initial_pose, f32).copy()
             self.first_trans = True
             return
-        if self.last_pose is None:
+        odom_av = info is not None and bool(info["odom_available"])
+        if odom_av:
+            g = np.asarray(info["initial_guess"], f32)
+            T_back = _T16([g[3], g[4], g[5], g[0], g[1], g[2]])
+            if self.last_imu_pre is None:
+                self.last_imu_pre = T_back                      # and fall through to the imuAvailable block (:327-330)
+            else:
+                incre = _mul(_inv(self.last_imu_pre), T_back)
+                self.pose = _euler(_mul(_T16(self.pose), incre))
+                self.last_imu_pre = T_back
+                r, p, y = (f32(v) for v in info["imu_rpy"])
+                self.last_imu = _T16([r, p, y, 0, 0, 0])
+                return
+        if not odom_av:
+            if self.last_pose is None:
+                self.last_pose = self.pose.copy()
+                return
+            T_back, T_last = _T16(self.pose), _T16(self.last_pose)
             self.last_pose = self.pose.copy()
+            incre = _mul(_inv(T_last), T_back)
+            self.pose = _euler(_mul(T_back, incre))
             return
-        T_back, T_last = _T16(self.pose), _T16(self.last_pose)
-        self.last_pose = self.pose.copy()
-        incre = _mul(_inv(T_last), T_back)
-        self.pose = _euler(_mul(T_back, incre))
+        if info["imu_available"]:
+            r, p, y = (f32(v) for v in info["imu_rpy"])
+            T_back = _T16([r, p, y, 0, 0, 0])
+            incre = _mul(_inv(self.last_imu), T_back)
+            self.pose = _euler(_mul(_T16(self.pose), incre))
+            self.last_imu = T_back
 
     def _save_keyframe(self, corner_full, surf_full):
         self.kf_corner.append(transform_cloud(corner_full, self.pose))
@@ -122,9 +156,11 @@ class OdometryStream:
         self.key_pose = self.pose.copy()
         self.keyframe_id += 1
 
-    def push(self, pts, ring, initial_pose=None):
-        """One LiDAR frame.  Returns the pose estimate [roll, pitch, yaw, x, y, z]."""
-        self._update_initial_guess(initial_pose)
+    def push(self, pts, ring, initial_pose=None, info=None):
+        """One LiDAR frame.  Returns the pose estimate [roll, pitch, yaw, x, y, z].  With `info` (cloud_info hints) the
+        loop must run with its clamps disabled (rot_tolerance = z_tolerance = 0 in lm_params): transformUpdate (:976-1006)
+        - IMU slerp, then the clamps - is applied here through `transform_update`."""
+        self._update_initial_guess(initial_pose, info)
         f = self.be.extract_features(pts, ring, self.fprm) if self.fprm is not None else self.be.extract_features(pts, ring)
         ext = np.ascontiguousarray(pts[f["src_index"]], np.float32)
         corner_full = np.ascontiguousarray(ext[f["corner_idx"]]); surf_full = np.ascontiguousarray(ext[f["surf_idx"]])
@@ -142,6 +178,10 @@ class OdometryStream:
         self.be.map_destroy(mid)
         if res.status != 1:                                   # "Not enough features": pose left at the prediction (:623-625)
             self.pose = np.asarray(pose, np.float32).copy()
+            if self.transform_update is not None:
+                imu_av = info is not None and bool(info["imu_available"])
+                rp = info["imu_rpy"] if info is not None else (0.0, 0.0, 0.0)
+                self.pose = self.transform_update(self.pose, imu_av, rp[0], rp[1], self.imu_rpy_weight)
             if not (res.deltaR == 100.0 and res.deltaT == 100.0):
                 self.deltaR, self.deltaT = f32(res.deltaR), f32(res.deltaT)
         if float(self.deltaR) < 0.005 or float(self.deltaT) < 0.05:

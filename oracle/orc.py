@@ -472,3 +472,14 @@ def loop_verify(key_cloud, key_pose6, key_rel_pose6, cands, fitness_threshold=0.
                               k2p.ctypes.data_as(vp), tc.ctypes.data_as(vp), c6.ctypes.data_as(vp), fit.ctypes.data_as(vp), conv.ctypes.data_as(vp))
     return dict(found=found, best=best.value, best_score=score.value, correction=corr.reshape(4, 4), key2pre=k2p.reshape(4, 4),
                 t_correct=tc.reshape(4, 4), constraint6=c6, fitness=fit[:P], converged=conv[:P])
+
+
+def transform_update(pose6, imu_available, imu_roll, imu_pitch, imu_rpy_weight, rot_tol=0.0, z_tol=0.0):
+    """transformUpdate (odomEstimationNode.cpp:976-1006): IMU roll / pitch slerp + clamps.  Returns the new pose6."""
+    L = lib()
+    L.orc_transform_update.restype = None
+    L.orc_transform_update.argtypes = [C.POINTER(C.c_float), C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]
+    p = np.array(pose6, dtype=np.float32).copy()
+    L.orc_transform_update(p.ctypes.data_as(C.POINTER(C.c_float)), int(bool(imu_available)), float(imu_roll), float(imu_pitch),
+                           float(imu_rpy_weight), float(rot_tol), float(z_tol))
+    return p

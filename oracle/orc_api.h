@@ -138,6 +138,10 @@ int32_t orc_loop_verify(const float* key4, int32_t n, const float* key_pose6, co
                         const float* cand_pose, float fitness_threshold, const orc_icp_params* prm, int32_t* best, double* best_score,
                         float* correction16, float* key2pre16, float* t_correct16, float* constraint6, double* fitness_out, int32_t* conv_out);
 
+/* ---- transformUpdate (odomEstimationNode.cpp:976-1006): IMU roll / pitch slerp (tf restated) + clamps ---- */
+void orc_transform_update(float pose6[6], int32_t imu_available, float imu_roll, float imu_pitch, float imu_rpy_weight,
+                          float rot_tol, float z_tol);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,15 @@ static int run_data(const std::string& dir) {
     traj.push_back((float)od.keyFrameId);
   }
   wr(dir + "/out_traj.bin", traj);
+  {   // the cloud_info overload: a message-shaped struct with no hints available behaves like the plain push (first pose = IMU attitude)
+    struct { bool imuAvailable = false, odomAvailable = false; float imuRollInit = 0, imuPitchInit = 0, imuYawInit = 0, initialGuessX = 0,
+             initialGuessY = 0, initialGuessZ = 0, initialGuessRoll = 0, initialGuessPitch = 0, initialGuessYaw = 0; } info;
+    info.imuRollInit = init[0]; info.imuPitchInit = init[1]; info.imuYawInit = init[2];
+    Odometry od2(r, op);
+    auto sw0 = sweep_of(rd<float>(dir + "/stream_000_pts.bin"), rd<uint16_t>(dir + "/stream_000_ring.bin"));
+    od2.pushInfo(sw0, info);
+    if (od2.keyFrameId != 1 || od2.transformTobeMapped[0] != init[0] || od2.transformTobeMapped[2] != 0.f) { std::printf("cloud_info push differs\n"); return 8; }
+  }
   std::printf("rc=%d iters=%d corner=%zu surf=%zu frames=%zu\n", rc, res.iters, corner.size(), surf.size(), traj.size() / 7);
   return 0;
 }

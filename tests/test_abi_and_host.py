@@ -6,6 +6,7 @@ import os
 import re
 import subprocess
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -35,11 +36,11 @@ def test_struct_layouts_match_header():
     #include <stdio.h>
     #include "lisreg.h"
     int main(void) {
-      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(lisreg_config), sizeof(lisreg_lm_params), sizeof(lisreg_lm_iter),
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(lisreg_config), sizeof(lisreg_lm_params), sizeof(lisreg_lm_iter),
              sizeof(lisreg_lm_result), sizeof(lisreg_batch_item), sizeof(lisreg_feat_params), sizeof(lisreg_feat_out),
              sizeof(lisreg_frame_params), sizeof(lisreg_frame_item), sizeof(lisreg_epsc_cloud), sizeof(lisreg_profile),
              sizeof(lisreg_icp_params), sizeof(lisreg_icp_pair), sizeof(lisreg_icp_result), sizeof(lisreg_odom_params),
-             sizeof(lisreg_odom_result), sizeof(lisreg_loop_params), sizeof(lisreg_loop_result), sizeof(lisreg_deskew));
+             sizeof(lisreg_odom_result), sizeof(lisreg_loop_params), sizeof(lisreg_loop_result), sizeof(lisreg_deskew), sizeof(lisreg_cloud_info));
       return 0;
     }'''
     exe = "/tmp/lisreg_sizes"
@@ -47,8 +48,42 @@ def test_struct_layouts_match_header():
     sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     mirrors = [E.Config, E.LmParams, E.LmIter, E.LmResult, E.BatchItem, E.FeatParams, E.FeatOut, E.FrameParams, E.FrameItem,
                E.EpscCloud, E.Profile, E.IcpParams, E.IcpPair, E.IcpResult, E.OdomParams, E.OdomResult, E.LoopParams, E.LoopResult,
-               E.Deskew]
+               E.Deskew, E.CloudInfo]
     assert sizes == [C.sizeof(m) for m in mirrors]
+
+
+def test_transform_update_matches_oracle_and_scipy():
+    """lisreg_transform_update (transformUpdate, odomEstimationNode.cpp:976-1006; host arithmetic, no device): bit-equal to the
+    oracle's restatement of the tf slerp, and both agree with scipy's Slerp (an independent quaternion implementation) to
+    float rounding; the clamps are constraintTransformation (common.cpp:286-292)."""
+    from lis_slam_b200 import engine as E
+    from oracle import orc
+    from scipy.spatial.transform import Rotation, Slerp
+    rng = np.random.default_rng(5)
+    for k in range(200):
+        pose = rng.uniform(-0.6, 0.6, 6).astype(np.float32)
+        imu = rng.uniform(-0.6, 0.6, 3)
+        if k % 7 == 0:
+            imu[1] = 1.45                                   # |imuPitchInit| >= 1.4: no slerp
+        if k % 11 == 0:
+            imu[0] = float(pose[0])                         # theta == 0 branch of slerp
+        w = float(rng.choice([0.01, 0.1, 0.5]))
+        tol = (0.0, 0.0) if k % 3 else (0.2, 0.3)
+        info = E.cloud_info(imu_available=(k % 5 != 0), imu_rpy=imu)
+        got = E.transform_update(pose, info, w, tol[0], tol[1])
+        ref = orc.transform_update(pose, k % 5 != 0, np.float32(imu[0]), np.float32(imu[1]), w, tol[0], tol[1])
+        assert np.array_equal(got, ref), (k, got, ref)
+        exp = pose.astype(np.float64).copy()
+        if k % 5 != 0 and abs(np.float32(imu[1])) < 1.4:
+            for ax, name in ((0, "x"), (1, "y")):
+                r = Rotation.from_euler(name, [[float(pose[ax])], [float(np.float32(imu[ax]))]])
+                exp[ax] = Slerp([0.0, 1.0], r)([w]).as_euler("xyz")[0][ax]
+        if tol[0] > 0:
+            exp[0] = np.clip(exp[0], -tol[0], tol[0]); exp[1] = np.clip(exp[1], -tol[0], tol[0]); exp[5] = np.clip(exp[5], -tol[1], tol[1])
+        assert np.allclose(got, exp, atol=2e-7, rtol=0), (k, got, exp)
+    # info = NULL: clamps only
+    p = E.transform_update(np.array([0.5, -0.5, 0.1, 1, 2, 3], np.float32), None, 0.01, 0.25, 2.0)
+    assert np.array_equal(p, np.array([0.25, -0.25, 0.1, 1, 2, 2.0], np.float32))
 
 
 def test_presets_match_reference_constants():

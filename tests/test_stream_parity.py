@@ -118,3 +118,53 @@ def test_odom_graph_replay_is_bit_identical_to_eager_launches():
         out.append(poses)
         eng.odom_destroy(oid); eng.close()
     assert out[0] == out[1]
+
+
+def _hint(t, rng, odom_on, imu_on):
+    """cloud_info scalars an IMU pre-integration front end would publish: attitude = truth + noise, initial guess = the truth
+    expressed from a drifting odom origin (only its increments matter, :331)."""
+    tr = _stream_traj(t)
+    imu_rpy = (tr[0] + 0.01 * rng.standard_normal(), tr[1] + 0.01 * rng.standard_normal(), tr[2] + 0.002 * rng.standard_normal())
+    guess = (tr[3] + 30.0 + 0.02 * rng.standard_normal(), tr[4] + 0.02 * rng.standard_normal(), tr[5] + 0.01 * rng.standard_normal(),
+             imu_rpy[0], imu_rpy[1], imu_rpy[2])
+    return dict(imu_available=imu_on, odom_available=odom_on, imu_rpy=imu_rpy, initial_guess=guess)
+
+
+@pytest.mark.parametrize("schedule", ["odom+imu", "imu_only", "odom_drops"])
+def test_odom_cloud_info_hints_match_oracle_flow(schedule):
+    """lisreg_odom_push_info: every branch of updateInitialGuess (:297-419 - first-frame IMU attitude, pre-integration
+    increment, the fall-through IMU rotation increment on the frame that first sees odomAvailable, constant velocity when
+    the odometry drops out) and the IMU slerp + clamps of transformUpdate (:976-1006), against the same flow in
+    stream.OdometryStream around the CPU oracle.  Clamps are live (rot 0.002 rad, inside the IMU noise) so their order after the slerp matters."""
+    eng = E.Engine(device=0, own_stream=True)
+    sc = scene()
+    prm = E.odom_params("A", n_scan=16, use_graph=1)
+    prm.frame.lm.rot_tolerance, prm.frame.lm.z_tolerance = 0.002, 1000.0
+    prm.imu_rpy_weight = 0.1                                                    # the shipped yaml value (params.yaml:88)
+    oid = eng.odom_create(prm)
+    tu = lambda pose, av, r, p, w: orc.transform_update(pose, av, np.float32(r), np.float32(p), w, 0.002, 1000.0)
+    so = stream.OdometryStream(OracleBackend(), orc.lm_params("A", rot_tolerance=0.0, z_tolerance=0.0), orc.feat_params(n_scan=16),
+                               imu_rpy_weight=0.1, transform_update=tu)
+    rng = np.random.default_rng(99)
+    used = set()
+    for t in range(12):
+        odom_on = {"odom+imu": t >= 1, "imu_only": False, "odom_drops": t in (2, 3, 4, 8, 9)}[schedule]
+        h = _hint(t, rng, odom_on, True)
+        sw = sc.scan(_stream_traj(t), sensor="vlp16", seed=7000 + t, fast=True)
+        ci = E.cloud_info(h["imu_available"], h["odom_available"], h["imu_rpy"], h["initial_guess"])
+        pg, rg = eng.odom_push_info(oid, sw["pts"], sw["ring"], ci)
+        po = so.push(sw["pts"], sw["ring"], info=h)
+        # the prediction itself (transformTobeMapped after updateInitialGuess) is host fp32 arithmetic: equal to rounding
+        er, et = synth.pose_error(po, pg)
+        assert er <= 1e-4 and et <= 1e-3, (schedule, t, er, et)
+        ro = so.results[-1]
+        assert rg.keyframe_id == so.keyframe_id
+        if ro is not None:
+            assert rg.lm.iters == ro.iters and rg.lm.status == ro.status, (t, rg.lm.iters, ro.iters)
+            assert np.array_equal(np.array(rg.lm.pose[:], np.float32), pg)       # the result carries the updated pose
+        if ro is not None and ro.status != 1:
+            assert abs(pg[0]) <= np.float32(0.002) and abs(pg[1]) <= np.float32(0.002)
+    expect = _stream_traj(11).copy(); expect[3] -= _stream_traj(0)[3]          # the hinted flow starts at the origin (:307-312)
+    er, et = synth.pose_error(expect, pg)
+    eng.odom_destroy(oid); eng.close()
+    assert et < 0.3 and er < 0.05, (er, et)
