@@ -97,7 +97,7 @@ constexpr int EPSC_QT = 8, EPSC_JT = 16, EPSC_THREADS = EPSC_QT * EPSC_JT;
 // a legal bulk-copy destination (16 threads with different rows and the same word then touch 8 banks: 2-way conflicts on
 // 40 LDS per ring against 600 ALU instructions - negligible)
 constexpr int EPSC_STRIDE_W = 404;
-constexpr int EPSC_CLUSTER = 4;      // CTAs per cluster along the history axis: they share the tile's query rows (multicast)
+constexpr int EPSC_CLUSTER = 2;      // CTAs per cluster along the history axis: they share the tile's query rows (multicast)
 
 // Query rows are q = q_begin + r * q_stride for local rows r in [0, n_rows): the whole matrix is (0, 1, N); a rank
 // of a multi-GPU run owns the cyclic rows (rank, world, ...) (triangular load => cyclic assignment).

@@ -264,6 +264,154 @@ __global__ void k_feat_compact(FeatFrame* frames, FeatParamsDev prm) {
   }
 }
 
+// ---- F1 + F2 fused: projection and row-major compaction without the range image ever leaving the SM ----
+// One block per (frame, group of R consecutive rings).  The group's slice of the range image (the input index owning each
+// cell) lives in SHARED memory: the block walks the ring ids of the whole sweep, projects the points of its own rings and
+// resolves "first point wins" (:499) with shared-memory atomicMin; then it counts / scans its valid cells, learns how many
+// cells the groups before it extracted (decoupled look-back over per-frame group totals: a block waits only for blocks
+// that took an EARLIER ticket, which are resident or finished and publish their total before waiting themselves - no
+// deadlock), and writes its rows of the extracted cloud at their final positions.  Replaces k_feat_clear, k_feat_project,
+// k_feat_ring_count and k_feat_compact<false>: 118 MB of owner-image clears, 28 M global atomics and two re-reads of the
+// owner image per 256-frame step stay on chip.
+// ctl = [ticket counter, finished counter, group totals (F * G, 0 = not published, else total + 1)]: the last block to
+// finish puts everything back to zero, so the kernel can be replayed (CUDA graph) without a host-side reset.
+constexpr int FEAT_FRONT_THREADS = 384;
+constexpr int FEAT_FRONT_SMEM_INTS = 15104;   // 59 KB of range-image slice + chunk offsets per block: three blocks per SM
+__global__ void __launch_bounds__(FEAT_FRONT_THREADS, 3)
+k_feat_front(FeatFrame* frames, FeatParamsDev prm, int R, int G, int F, int* ctl) {
+  extern __shared__ int s_dyn[];
+  __shared__ int s_ticket, s_base, s_last;
+  __shared__ int s_queue[FEAT_FRONT_THREADS / 32][64];
+  const int nchunk = (prm.horizon + 31) / 32;
+  int* s_owner = s_dyn;                       // [R * horizon]
+  int* s_chunk = s_dyn + R * prm.horizon;     // [R * nchunk + 1] valid cells per 32-cell chunk -> exclusive offsets
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&ctl[0], 1);
+  __syncthreads();
+  const int ticket = s_ticket, fi = ticket / G, g = ticket - fi * G;
+  const FeatFrame f = frames[fi];
+  const int r0 = g * R, r1 = min(r0 + R, prm.n_scan), nr = r1 - r0;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < nr * prm.horizon; i += blockDim.x) s_owner[i] = 0x7fffffff;
+  if (g == 0 && threadIdx.x < 4) f.counts[threadIdx.x] = 0;
+  __syncthreads();
+  // ---- F1 over the whole sweep, own rings only ----
+  // A sweep in firing order has its rings interleaved: only nr of n_scan consecutive points belong to this block.  Each warp
+  // therefore first collects the indices of its own points in a 64-entry queue and projects them 32 at a time with all
+  // lanes busy.
+  {
+    const uint16_t* __restrict__ ring = f.ring;
+    const int n = f.n;
+    int* q = s_queue[wid];
+    int qn = 0;                                                       // warp-uniform fill of the queue (< 32 between chunks)
+    auto project32 = [&](int cnt) {
+      if (lane < cnt) {
+        const int i = q[lane];
+        float r; int cell;
+        if (feat_project(prm, feat_load_point(f.pts, prm.lay, i), (int)__ldg(&ring[i]), r, cell)) atomicMin(&s_owner[cell - r0 * prm.horizon], i);
+      }
+    };
+    constexpr int U = 4;
+    const int stride = blockDim.x;
+    for (int i0 = threadIdx.x - lane; i0 < n; i0 += U * stride) {     // warp-uniform trip count
+      int rg[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) { const int i = i0 + lane + u * stride; rg[u] = i < n ? (int)__ldg(&ring[i]) : -1; }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const bool own = rg[u] >= r0 && rg[u] < r1;
+        const unsigned m = __ballot_sync(0xffffffffu, own);
+        if (m == 0u) continue;
+        if (own) q[qn + __popc(m & ((1u << lane) - 1u))] = i0 + lane + u * stride;
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) {
+          project32(32);
+          __syncwarp();
+          const int rest = qn - 32;
+          const int t = lane < rest ? q[32 + lane] : 0;
+          __syncwarp();
+          if (lane < rest) q[lane] = t;
+          qn = rest;
+          __syncwarp();
+        }
+      }
+    }
+    project32(qn);
+  }
+  __syncthreads();
+  // ---- F2: valid cells per chunk, exclusive scan over the group (row-major = extraction order) ----
+  const int nch = nr * nchunk;
+  for (int ch = wid; ch < nch; ch += nw) {
+    const int rr = ch / nchunk, j = (ch - rr * nchunk) * 32 + lane;
+    const bool v = j < prm.horizon && s_owner[rr * prm.horizon + j] != 0x7fffffff;
+    const unsigned m = __ballot_sync(0xffffffffu, v);
+    if (lane == 0) s_chunk[ch] = __popc(m);
+  }
+  __syncthreads();
+  if (wid == 0) {
+    int carry = 0;
+    for (int b0 = 0; b0 < nch; b0 += 32) {
+      const int v = b0 + lane < nch ? s_chunk[b0 + lane] : 0;
+      int x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+      if (b0 + lane < nch) s_chunk[b0 + lane] = carry + x - v;
+      carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane == 0) {
+      s_chunk[nch] = carry;
+      __threadfence();
+      atomicExch(&ctl[2 + ticket], carry + 1);                       // publish before waiting on anybody
+    }
+    // cells extracted by the groups before this one (same frame: tickets fi * G .. ticket - 1)
+    int before = 0;
+    for (int l0 = 0; l0 < g; l0 += 32) {
+      int v = 0;
+      if (l0 + lane < g) {
+        const volatile int* slot = &ctl[2 + fi * G + l0 + lane];
+        while ((v = *slot) == 0) __nanosleep(64);
+        v -= 1;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      before += v;
+    }
+    if (lane == 0) s_base = before;
+  }
+  __syncthreads();
+  const int base = s_base;
+  if (threadIdx.x < nr) {
+    const int b = base + s_chunk[threadIdx.x * nchunk], c = s_chunk[(threadIdx.x + 1) * nchunk] - s_chunk[threadIdx.x * nchunk];
+    f.ring_count[r0 + threadIdx.x] = c;
+    f.ring_start[r0 + threadIdx.x] = b - 1 + 5;                      // startRingIndex (:521)
+    f.ring_end[r0 + threadIdx.x] = b + c - 1 - 5;                    // endRingIndex   (:537)
+  }
+  if (g == G - 1 && threadIdx.x == 0) *f.M = base + s_chunk[nch];
+  for (int ch = wid; ch < nch; ch += nw) {
+    const int rr = ch / nchunk, j = (ch - rr * nchunk) * 32 + lane;
+    const int own = j < prm.horizon ? s_owner[rr * prm.horizon + j] : 0x7fffffff;
+    const bool v = own != 0x7fffffff;
+    const unsigned m = __ballot_sync(0xffffffffu, v);
+    if (v) {
+      const int pos = base + s_chunk[ch] + __popc(m & ((1u << lane) - 1u));
+      const float4 p = feat_load_point(f.pts, prm.lay, own);
+      f.ext_pts[pos] = p;
+      f.ext_src[pos] = own;
+      f.col[pos] = (unsigned short)j;
+      f.range[pos] = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+      f.picked[pos] = 0; f.label[pos] = 0; f.curv[pos] = 0.f;       // resetParameters (:61-75): cleared per extracted slot
+    }
+  }
+  // ---- replay safety: the last block to finish clears the control words ----
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(&ctl[1], 1) == F * G - 1; }
+  __syncthreads();
+  if (s_last) {
+    for (int i = threadIdx.x; i < F * G; i += blockDim.x) ctl[2 + i] = 0;
+    if (threadIdx.x == 0) { ctl[0] = 0; ctl[1] = 0; }
+  }
+}
+
 // F3 + F4 in one pass over the extracted ranges.  grid = (blocks, F).  F4's writes are idempotent ORs of 1 into
 // flags that k_feat_compact cleared, F3 writes only its own slot: no ordering between the two is needed.
 __global__ void k_feat_curv_occl(FeatFrame* frames) {

@@ -67,15 +67,16 @@ struct MapSlot {
 };
 
 // Everything one in-flight batch (or chunk of a batch) of the frame pipeline / LM loop needs.  A context owns three:
-// ws[0] runs on the context stream (every synchronous entry point); ws[1] and ws[2] have private streams and
+// ws[0] runs on the context stream (every synchronous entry point); ws[1..4] have private streams (created on first use); ws[1] and ws[2]
 // alternate between the chunks of the pipelined e2e path, so that two chunks are in flight while a third uploads.
 struct WorkSet {
   cudaStream_t stream = nullptr;
   DevBuf d_descs, d_states, d_partials, d_nbr, d_kstate, d_klist, d_geom;
   DevBuf d_feat, d_feat_frames, d_vox, d_vox_segs, d_imu;
+  DevBuf d_feat_ctl;                       // k_feat_front control words (ticket, finished, group totals): all zero between launches
   int feat_cap_frames = 0, feat_cells = 0, feat_nscan = 0;
   void release() {
-    for (DevBuf* b : {&d_descs, &d_states, &d_partials, &d_nbr, &d_kstate, &d_klist, &d_geom, &d_feat, &d_feat_frames, &d_vox, &d_vox_segs, &d_imu}) b->release();
+    for (DevBuf* b : {&d_descs, &d_states, &d_partials, &d_nbr, &d_kstate, &d_klist, &d_geom, &d_feat, &d_feat_frames, &d_vox, &d_vox_segs, &d_imu, &d_feat_ctl}) b->release();
   }
 };
 
@@ -91,7 +92,7 @@ struct lisreg_ctx {
   // scratch
   DevBuf d_stage, d_logs, d_pose, d_res, d_tmp, d_bbox;
   PinBuf h_stage, h_out;
-  WorkSet ws[3];
+  WorkSet ws[5];   // 0: context stream; 1, 2: private streams (e2e chunks, submit / wait slots); 1..4: sub-batches of lisreg_frames_batch_dev
   WorkSet* cur = &ws[0];   // work set (and stream) the run_* drivers use; only the pipelined e2e path switches it
   DevBuf d_epsc, d_epsc2, d_icp;
   // e2e pipeline: H2D of chunk c+1 on copy_stream overlaps the compute of chunk c on `stream`
@@ -99,6 +100,7 @@ struct lisreg_ctx {
   std::vector<cudaEvent_t> chunk_ev;
   PinBuf h_desc;       // pinned descriptor staging of the arena entry points (one slice per chunk)
   int e2e_chunk = 128; // frames per chunk (LISREG_E2E_CHUNK; 0 = one copy, no overlap)
+  int dev_split = 4;   // sub-batches lisreg_frames_batch_dev runs concurrently on private streams (LISREG_DEV_SPLIT; <= 1 = off)
   // asynchronous submit / wait pipeline: two slots, each with its own staging arena, result buffers and work set
   // (ws[1 + slot]); the upload of one batch overlaps the compute of the other
   struct AsyncSlot { DevBuf d_stage, d_res; PinBuf h_out, h_desc; cudaEvent_t done = nullptr, fence = nullptr; bool busy = false; int F = 0; };
@@ -152,6 +154,8 @@ struct lisreg_ctx {
   cudaStream_t comm_stream = nullptr; cudaEvent_t comm_fence = nullptr, comm_done[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t comm_seq = 0;                    // gathers issued so far; gather k signals comm_done[k % 4]
   int knn_coop_max = 16384;   // scan lists shorter than this are searched warp-per-query (LISREG_KNN_COOP_MAX; 0 = never)
+  int feat_fused = 0;     // LISREG_FEAT_FUSED=1: projection + compaction in one kernel with the range-image slice in shared memory (k_feat_front);
+                          // measured slower than the global range image on firing-order sweeps (8x redundant ring-id scans), so off by default
   int knn_noskip = 0;   // LISREG_KNN_NOSKIP=1: search every query from scratch at every iteration (parity check of the CHECK path)
   // profiling
   bool prof_on = false;
@@ -421,8 +425,10 @@ int32_t lisreg_create(const lisreg_config* cfg, lisreg_ctx** out) {
   if (cfg && cfg->max_grid_cells > 0) ctx->max_cells = cfg->max_grid_cells;
   { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, ctx->device) == cudaSuccess && v > 0) ctx->n_sm = v; }
   if (const char* e2 = getenv("LISREG_KNN_NOSKIP")) ctx->knn_noskip = atoi(e2) ? 1 : 0;
+  if (const char* e3 = getenv("LISREG_FEAT_FUSED")) ctx->feat_fused = atoi(e3) ? 1 : 0;
   if (const char* e4 = getenv("LISREG_KNN_COOP_MAX")) ctx->knn_coop_max = std::max(0, atoi(e4));
   if (const char* e3 = getenv("LISREG_E2E_CHUNK")) ctx->e2e_chunk = std::max(0, atoi(e3));
+  if (const char* e4 = getenv("LISREG_DEV_SPLIT")) ctx->dev_split = std::min(4, std::max(0, atoi(e4)));
   *out = ctx;
   return LISREG_OK;
 }
@@ -436,7 +442,7 @@ void lisreg_destroy(lisreg_ctx* ctx) {
   }
   if (ctx->d_maps) cudaFree(ctx->d_maps);
   for (DevBuf* b : {&ctx->d_stage, &ctx->d_logs, &ctx->d_pose, &ctx->d_res, &ctx->d_tmp, &ctx->d_bbox, &ctx->d_epsc, &ctx->d_epsc2, &ctx->d_icp}) b->release();
-  for (int i = 0; i < 3; i++) { if (i > 0 && ctx->ws[i].stream) { cudaStreamSynchronize(ctx->ws[i].stream); cudaStreamDestroy(ctx->ws[i].stream); } ctx->ws[i].release(); }
+  for (int i = 0; i < 5; i++) { if (i > 0 && ctx->ws[i].stream) { cudaStreamSynchronize(ctx->ws[i].stream); cudaStreamDestroy(ctx->ws[i].stream); } ctx->ws[i].release(); }
   ctx->h_stage.release(); ctx->h_out.release(); ctx->h_desc.release();
   for (auto& L : ctx->loops) if (L.used) { cudaFree(L.d_proj); cudaFree(L.d_desc); cudaFree(L.d_lut); }
   lisreg_comm_destroy(ctx);
@@ -522,7 +528,7 @@ int32_t lisreg_map_destroy(lisreg_ctx* ctx, int32_t map_id) {
   if (!ctx || map_id < 0 || map_id >= (int)ctx->maps.size() || !ctx->maps[map_id].used) return fail(ctx, LISREG_ERR_ARG, "lisreg_map_destroy: bad map id");
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
-  for (int i = 1; i < 3; i++) if (ctx->ws[i].stream) CK(cudaStreamSynchronize(ctx->ws[i].stream));   // batches still in flight may read the map
+  for (int i = 1; i < 5; i++) if (ctx->ws[i].stream) CK(cudaStreamSynchronize(ctx->ws[i].stream));   // batches still in flight may read the map
   MapSlot& m = ctx->maps[map_id];
   cudaFree(m.corner.sorted); cudaFree(m.corner.cell_start); cudaFree(m.surf.sorted); cudaFree(m.surf.cell_start);
   m = MapSlot();
@@ -876,6 +882,11 @@ static int feat_reserve(lisreg_ctx* ctx, int F, int cells, int nscan) {
   const size_t per = feat_frame_bytes(cells, nscan) + 4096;
   CK(ctx->cur->d_feat.reserve(per * (size_t)F));
   CK(ctx->cur->d_feat_frames.reserve(sizeof(FeatFrame) * (size_t)F));
+  {
+    const void* before = ctx->cur->d_feat_ctl.p;
+    CK(ctx->cur->d_feat_ctl.reserve(sizeof(int) * (2 + (size_t)F * (size_t)nscan)));
+    if (ctx->cur->d_feat_ctl.p != before) CK(cudaMemsetAsync(ctx->cur->d_feat_ctl.p, 0, ctx->cur->d_feat_ctl.cap, ctx->cur->stream));
+  }
   ctx->cur->feat_cap_frames = F; ctx->cur->feat_cells = cells; ctx->cur->feat_nscan = nscan;
   return LISREG_OK;
 }
@@ -887,12 +898,28 @@ static int run_features(lisreg_ctx* ctx, FeatFrame* d_frames, int F, const lisre
   FeatParamsDev dp{prm->n_scan, prm->horizon, prm->downsample_rate, prm->min_range, prm->max_range, prm->edge_thr, prm->surf_thr, prm->layout};
   const int cells = prm->n_scan * prm->horizon;
   ProfScope ps(ctx, PROF_FEAT, alg_bytes, 7);
-  k_feat_clear<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
-  k_feat_project<<<dim3(std::max(1, (max_n + 255) / 256), F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
-  if (with_deskew) { k_feat_deskew_start<<<F, 256, 0, st>>>(d_frames, dp); LAUNCH_CK(); }
-  k_feat_ring_count<<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
-  if (with_deskew) { k_feat_compact<true><<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK(); }
-  else { k_feat_compact<false><<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK(); }
+  // F1 + F2 on chip (k_feat_front, opt-in) when the ring ids come as their own array and no de-skew reference has to be found
+  // across the whole sweep first; otherwise (default) the range image goes through global memory
+  const bool fused = !with_deskew && ctx->feat_fused && layout_needs_ring_array(prm->layout) &&
+                     ctx->cur->d_feat_ctl.cap >= sizeof(int) * (2 + (size_t)F * (size_t)prm->n_scan);
+  if (fused) {
+    const int nchunk = (prm->horizon + 31) / 32;
+    const int rmax = std::max(1, std::min(prm->n_scan, FEAT_FRONT_SMEM_INTS / (prm->horizon + nchunk)));
+    int R = rmax;                                                 // rings per block: as many as fit, fewer when the batch is small
+    while (R > 1 && (long long)F * ((prm->n_scan + R - 1) / R) < 2 * 148) R--;
+    const int G = (prm->n_scan + R - 1) / R;
+    const size_t smem = sizeof(int) * ((size_t)R * (size_t)(prm->horizon + nchunk) + 1);
+    static bool attr_set = false;
+    if (!attr_set) { CK(cudaFuncSetAttribute(k_feat_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * (FEAT_FRONT_SMEM_INTS + 1)))); attr_set = true; }
+    k_feat_front<<<F * G, FEAT_FRONT_THREADS, smem, st>>>(d_frames, dp, R, G, F, (int*)ctx->cur->d_feat_ctl.p); LAUNCH_CK();
+  } else {
+    k_feat_clear<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
+    k_feat_project<<<dim3(std::max(1, (max_n + 255) / 256), F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
+    if (with_deskew) { k_feat_deskew_start<<<F, 256, 0, st>>>(d_frames, dp); LAUNCH_CK(); }
+    k_feat_ring_count<<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
+    if (with_deskew) { k_feat_compact<true><<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK(); }
+    else { k_feat_compact<false><<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK(); }
+  }
   k_feat_curv_occl<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames); LAUNCH_CK();
   k_feat_segments<<<dim3((prm->n_scan + FEAT_WARPS - 1) / FEAT_WARPS, F), 32 * FEAT_WARPS, 0, st>>>(d_frames, dp); LAUNCH_CK();
   k_feat_gather<<<dim3(FEAT_GATHER_SPLIT, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
@@ -1187,7 +1214,37 @@ int32_t lisreg_frames_batch_dev(lisreg_ctx* ctx, int32_t F, const lisreg_frame_i
   if (!ctx || F <= 0 || !items || !d_pose6xF || !prm || !d_resxF) return fail(ctx, LISREG_ERR_ARG, "lisreg_frames_batch_dev: bad argument");
   if (prm->lm.max_iters <= 0 || prm->lm.max_iters > LISREG_MAX_ITERS) return fail(ctx, LISREG_ERR_ARG, "max_iters must be in 1..%d", LISREG_MAX_ITERS);
   CK(cudaSetDevice(ctx->device));
-  return run_frames(ctx, F, items, nullptr, 0, d_pose6xF, prm, d_resxF);
+  // A large batch runs as up to four sub-batches on private streams: the stages of one frame pipeline are bound by different
+  // things (selection loop: issue; ordered centroids and the 6x6 solves: latency; launch gaps), so kernels of different
+  // sub-batches fill each other's idle SM time (measured: 6.65 -> 5.8 ms per 256 frames).  Every registration is reduced
+  // in the same fixed order, so the results do not depend on the split.  Profiling keeps the batch whole (stage times
+  // would overlap), and so does a submit / wait ticket in flight (it owns work sets 1 / 2).
+  const int S = (ctx->dev_split > 1 && !ctx->prof_on && !ctx->slot[0].busy && !ctx->slot[1].busy) ? std::min(ctx->dev_split, F / 32) : 1;
+  if (S <= 1) return run_frames(ctx, F, items, nullptr, 0, d_pose6xF, prm, d_resxF);
+  cudaStream_t st = ctx->stream;
+  for (int i = 1; i <= S; i++) if (!ctx->ws[i].stream) CK(cudaStreamCreateWithFlags(&ctx->ws[i].stream, cudaStreamNonBlocking));
+  while ((int)ctx->chunk_ev.size() < S + 1) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
+  const int C = (F + S - 1) / S;
+  int rc = sync_maps(ctx);
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->chunk_ev[S], st));                       // fork: everything the caller queued before this call
+  rc = LISREG_OK;
+  for (int c = 0; c < S && rc == LISREG_OK; c++) {
+    const int f0 = c * C, fc = std::min(C, F - f0);
+    if (fc <= 0) break;
+    ctx->cur = &ctx->ws[1 + c];
+    cudaError_t e = cudaStreamWaitEvent(ctx->cur->stream, ctx->chunk_ev[S], 0);
+    if (e != cudaSuccess) rc = fail(ctx, LISREG_ERR_CUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
+    // descriptors go through pageable staging (consumed before cudaMemcpyAsync returns): this call does not synchronise,
+    // so a pinned block could still be in use by the previous call's copies
+    else rc = run_frames(ctx, fc, items + f0, nullptr, 0, d_pose6xF + 6 * (size_t)f0, prm, d_resxF + f0, nullptr, F, 0, f0);
+  }
+  ctx->cur = &ctx->ws[0];
+  for (int c = 0; c < S; c++) {                                    // join
+    cudaEventRecord(ctx->chunk_ev[c], ctx->ws[1 + c].stream);
+    cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0);
+  }
+  return rc;
 }
 
 int32_t lisreg_frames_batch_arena(lisreg_ctx* ctx, int32_t F, const lisreg_frame_item* items, const void* host_arena,
@@ -2140,7 +2197,7 @@ constexpr int ODOM_LM_SLICE = 4;   // Gauss-Newton iterations per launch slice o
 static std::vector<const void*> odom_graph_key(lisreg_ctx* ctx, lisreg_ctx::Odom& O) {
   WorkSet& w = *ctx->cur;
   return {w.d_descs.p, w.d_states.p, w.d_partials.p, w.d_nbr.p, w.d_kstate.p, w.d_klist.p, w.d_geom.p, w.d_feat.p, w.d_feat_frames.p,
-          w.d_vox.p, w.d_vox_segs.p, ctx->d_maps, O.d_io.p, O.h_desc.p};
+          w.d_vox.p, w.d_vox_segs.p, w.d_feat_ctl.p, ctx->d_maps, O.d_io.p, O.h_desc.p};
 }
 
 static int odom_push_impl(lisreg_ctx* ctx, int32_t odom_id, const float* pts, const uint16_t* ring, int32_t n, bool on_device,

@@ -139,3 +139,26 @@ def test_cloud_layouts_give_identical_features(engine, sensor, n_scan):
     prm = E.feat_params(n_scan=n_scan); prm.layout = E.cloud_layout(E.LAYOUT_XYZ_RING); prm.layout.off_y = 5
     with pytest.raises(E.LisregError):
         engine.extract_features(np.ascontiguousarray(sw["pts"][:, :3]), sw["ring"], prm)
+
+
+def test_fused_front_end_equals_range_image_path():
+    """k_feat_front (projection + compaction with the range-image slice in shared memory, look-back over ring groups) writes
+    exactly what the global range-image kernels write: every output array of a single sweep (64 one-ring groups)
+    is identical with and without LISREG_FEAT_FUSED=1 (batches: tests/test_frames_parity.py and the all-frames pose check of bench.py)."""
+    import os
+    from common import scene
+    sc = scene()
+    sweeps = [sc.scan(np.array([0.01 * k, -0.02, 0.1 * k, 1.0 * k, -0.5 * k, 0.0], np.float32), seed=3100 + k, fast=True) for k in range(3)]
+    outs = {}
+    for mode in ("0", "1"):
+        os.environ["LISREG_FEAT_FUSED"] = mode
+        try:
+            eng = E.Engine(device=0)
+            outs[mode] = [eng.extract_features(s["pts"], s["ring"]) for s in sweeps]
+            eng.close()
+        finally:
+            os.environ.pop("LISREG_FEAT_FUSED", None)
+    for a, b in zip(outs["0"], outs["1"]):
+        assert set(a) == set(b)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k

@@ -127,3 +127,52 @@ def test_submit_wait_pipeline_matches_blocking_call(engine):
         assert np.array_equal(pose, pose_ref)
         assert [(r.status, r.iters, r.n_sel_last) for r in res] == [(r.status, r.iters, r.n_sel_last) for r in res_ref]
     engine.map_destroy(mid)
+
+
+def test_device_resident_sub_batches_are_bit_identical(monkeypatch):
+    """lisreg_frames_batch_dev runs a large batch as concurrent sub-batches on private streams (kernels of different
+    pipeline stages overlap); splitting must not change a bit: 70 frames (ragged and empty ones included) as 2 sub-batches
+    of 35 against the same batch kept whole (LISREG_DEV_SPLIT=0), twice in a row without a host sync in between."""
+    import ctypes as C
+    import torch
+    m = local_map()
+    s0, _, g0 = frame(0)
+    s1, _, g1 = frame(1)
+    third = {"pts": s1["pts"][: len(s1["pts"]) // 3], "ring": s1["ring"][: len(s1["pts"]) // 3]}
+    empty = {"pts": np.zeros((0, 4), np.float32), "ring": np.zeros(0, np.uint16)}
+    base = [s0, third, s1, empty, s0, s1, s0]
+    F = 70
+    rng = np.random.default_rng(8)
+    sweeps = [base[i % len(base)] for i in range(F)]
+    guesses = np.stack([(g0 if i % 2 else g1) + rng.normal(0, [0.002, 0.002, 0.005, 0.05, 0.05, 0.02]).astype(np.float32) for i in range(F)]).astype(np.float32)
+    prm = E.frame_params("A", early_exit=0, max_iters=5)
+    dev = torch.device("cuda", 0)
+    d_sw = {id(s): (torch.from_numpy(np.ascontiguousarray(s["pts"], np.float32)).to(dev), torch.from_numpy(s["ring"].astype(np.int16)).to(dev)) for s in base}
+    out = {}
+    for split, fused in (("0", "0"), ("4", "0"), ("0", "1"), ("4", "1")):      # fused: k_feat_front with 8-ring groups (opt-in)
+        monkeypatch.setenv("LISREG_DEV_SPLIT", split)
+        monkeypatch.setenv("LISREG_FEAT_FUSED", fused)
+        eng = E.Engine(device=0)
+        mid = eng.map_create(m["corner"], m["surf"], gate_hint=1.0)
+        items = (E.FrameItem * F)()
+        for i, s in enumerate(sweeps):
+            p, r = d_sw[id(s)]
+            items[i] = E.FrameItem(p.data_ptr() if len(s["pts"]) else None, r.data_ptr() if len(s["pts"]) else None, len(s["pts"]), mid)
+        runs = []
+        pose = [torch.from_numpy(guesses).to(dev) for _ in range(2)]
+        res = [torch.zeros(F * C.sizeof(E.LmResult), dtype=torch.uint8, device=dev) for _ in range(2)]
+        torch.cuda.synchronize()
+        for k in range(2):
+            eng.frames_batch_dev(items, F, pose[k].data_ptr(), prm, res[k].data_ptr())
+        eng.sync()
+        for k in range(2):
+            rr = (E.LmResult * F).from_buffer_copy(res[k].cpu().numpy().tobytes())
+            runs.append((pose[k].cpu().numpy().copy(), [(r.status, r.iters, r.n_corner, r.n_surf, r.n_sel_last) for r in rr]))
+        eng.close()
+        assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1] == runs[1][1]
+        out[(split, fused)] = runs[0]
+    ref = out[("0", "0")]
+    for k, v in out.items():
+        assert np.array_equal(ref[0], v[0]), k
+        assert ref[1] == v[1], k
+    assert not np.array_equal(ref[0], guesses)
