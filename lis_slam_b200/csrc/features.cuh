@@ -620,14 +620,21 @@ k_feat_gather(FeatFrame* frames, FeatParamsDev prm) {
     s_u[s] = valid ? (f.seg_ep[s] - f.seg_sp[s] + 1) - nc : 0;
   }
   __syncthreads();
-  if (threadIdx.x < 128 && (threadIdx.x & 31) == 0) {          // four warps, one array each
-    int* a = threadIdx.x == 0 ? s_c : threadIdx.x == 32 ? s_s : threadIdx.x == 64 ? s_f : s_u;
-    int acc = 0;
-    for (int s = 0; s < nseg; s++) { int t = a[s]; a[s] = acc; acc += t; }
-    if (blockIdx.x == 0) f.counts[threadIdx.x >> 5] = acc;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (wid < 4) {                                               // four warps, one array each: exclusive scan, 32 segments per round
+    int* a = wid == 0 ? s_c : wid == 1 ? s_s : wid == 2 ? s_f : s_u;
+    int carry = 0;
+    for (int b0 = 0; b0 < nseg; b0 += 32) {
+      const int v = b0 + lane < nseg ? a[b0 + lane] : 0;
+      int x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+      if (b0 + lane < nseg) a[b0 + lane] = carry + x - v;
+      carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (blockIdx.x == 0 && lane == 0) f.counts[wid] = carry;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int s = blockIdx.x * nw + wid; s < nseg; s += gridDim.x * nw) {
     if (!f.seg_valid[s]) continue;
     const int nc = f.seg_ncorner[s], nf = f.seg_nflat[s];

@@ -156,6 +156,7 @@ struct lisreg_ctx {
   int knn_coop_max = 16384;   // scan lists shorter than this are searched warp-per-query (LISREG_KNN_COOP_MAX; 0 = never)
   int feat_fused = 0;     // LISREG_FEAT_FUSED=1: projection + compaction in one kernel with the range-image slice in shared memory (k_feat_front);
                           // measured slower than the global range image on firing-order sweeps (8x redundant ring-id scans), so off by default
+  int vox_unfused = 0;    // LISREG_VOX_UNFUSED=1: frame-sized clouds take the multi-kernel voxel path too (parity check of k_vox_block)
   int knn_noskip = 0;   // LISREG_KNN_NOSKIP=1: search every query from scratch at every iteration (parity check of the CHECK path)
   // profiling
   bool prof_on = false;
@@ -426,6 +427,7 @@ int32_t lisreg_create(const lisreg_config* cfg, lisreg_ctx** out) {
   { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, ctx->device) == cudaSuccess && v > 0) ctx->n_sm = v; }
   if (const char* e2 = getenv("LISREG_KNN_NOSKIP")) ctx->knn_noskip = atoi(e2) ? 1 : 0;
   if (const char* e3 = getenv("LISREG_FEAT_FUSED")) ctx->feat_fused = atoi(e3) ? 1 : 0;
+  if (const char* e5 = getenv("LISREG_VOX_UNFUSED")) ctx->vox_unfused = atoi(e5) ? 1 : 0;
   if (const char* e4 = getenv("LISREG_KNN_COOP_MAX")) ctx->knn_coop_max = std::max(0, atoi(e4));
   if (const char* e3 = getenv("LISREG_E2E_CHUNK")) ctx->e2e_chunk = std::max(0, atoi(e3));
   if (const char* e4 = getenv("LISREG_DEV_SPLIT")) ctx->dev_split = std::min(4, std::max(0, atoi(e4)));
@@ -661,7 +663,7 @@ static int run_lm(lisreg_ctx* ctx, int B, const RegDesc* d_descs, int max_n, dou
       k_knn_search<true><<<ctx->n_sm * 4, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp.gate, nbr, kstate, geom, shell_list,
                                                counters + 2 * it + 1, nullptr, nullptr, 0, max_tiles, tile_shift); LAUNCH_CK();
       k_lm_resid<<<grid, LM_THREADS, 0, st>>>(d_descs, states, ctx->d_maps, dp, nbr, geom, partials, max_tiles, tile_pts); LAUNCH_CK();
-      k_lm_solve<<<(B + LM_SOLVE_THREADS / 32 - 1) / (LM_SOLVE_THREADS / 32), LM_SOLVE_THREADS, 0, st>>>(
+      k_lm_solve<<<B, LM_SOLVE_THREADS, 0, st>>>(
           d_descs, states, dp, partials, d_logs, max_tiles, tile_pts, B); LAUNCH_CK();
     }
   }
@@ -1025,6 +1027,7 @@ static void vox_carve(char* base, int cap, VoxSeg* s) {
   s->bbox = (unsigned*)take(24);
   s->out_n = (int*)take(4);
   s->cap = cap;
+  s->bound = 0.f;
 }
 
 // runs the voxel grid for nseg clouds whose VoxSeg descriptors (device) are ready; max_n bounds every n
@@ -1037,6 +1040,15 @@ static int run_voxel(lisreg_ctx* ctx, VoxSeg* d_segs, int nseg, int max_n, doubl
   // single-block scans are the cheaper choice when there are many clouds to keep the GPU busy; with a handful of clouds
   // (streaming odometry: one frame's two clouds, the 2 M-point window map) they serialise, so those take the parallel forms
   const bool big = nseg < 64;
+  if (max_n <= VOX_BLOCK_MAX_N && !ctx->vox_unfused) {
+    // clouds of frame size: bounding box -> keys -> runs -> sort -> voxel heads by ONE block per cloud, the sort in shared memory
+    static bool attr_set = false;
+    if (!attr_set) { CK(cudaFuncSetAttribute(k_vox_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VB_SMEM)); attr_set = true; }
+    k_vox_block<<<nseg, VB_THREADS, VB_SMEM, st>>>(d_segs); LAUNCH_CK();
+    if (big) { k_vox_centroid_warp<<<dim3(std::max(1, std::min(2 * ctx->n_sm, (max_n + 255) / 256)), nseg), 256, 0, st>>>(d_segs); LAUNCH_CK(); }
+    else { k_vox_centroid<<<dim3(std::max(1, (max_n + VC_CHUNK - 1) / VC_CHUNK), nseg), 256, 0, st>>>(d_segs); LAUNCH_CK(); }
+    return LISREG_OK;
+  }
   k_vox_bbox_init<<<(nseg * 6 + 255) / 256, 256, 0, st>>>(d_segs, nseg); LAUNCH_CK();
   k_vox_bbox<<<dim3(pblk, nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
   k_vox_plan<<<(nseg + 127) / 128, 128, 0, st>>>(d_segs, nseg); LAUNCH_CK();
@@ -1187,6 +1199,7 @@ static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, co
     vox_carve(vb, ccap, &vc); vox_carve(vb + vc_per, cells, &vs);
     vc.src = f.ext_pts; vc.gather = f.corner_idx; vc.n_ptr = f.counts + 0; vc.n = 0; vc.leaf = prm->corner_leaf;
     vs.src = f.ext_pts; vs.gather = f.surf_idx;   vs.n_ptr = f.counts + 3; vs.n = 0; vs.leaf = prm->surf_leaf;
+    vc.bound = vs.bound = fp->max_range + 1.0f;            // extracted points passed the range gate (the de-skew is a pure rotation)
     RegDesc& d = hd[i];
     d.corner = vc.out; d.surf = vs.out; d.clabel = nullptr; d.slabel = nullptr; d.nc = 0; d.ns = 0;
     d.map_slot = it.map_id; d.pad = 0; d.nc_ptr = vc.out_n; d.ns_ptr = vs.out_n;

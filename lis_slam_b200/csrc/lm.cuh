@@ -909,28 +909,36 @@ k_lm_resid(const RegDesc* __restrict__ descs, const RegState* __restrict__ state
 // last block of k_lm_resid run the solve costs 0.3 ms per 256-frame step - the 544-byte frame of the solve lands in the
 // hot kernel - and saves nothing on the single-frame path).
 constexpr int LM_SOLVE_THREADS = 128;
+constexpr int LM_SOLVE_CHUNK = 32;       // tiles staged per round
+// One block per registration: the tile partials are staged in shared memory by all threads (coalesced, every load in
+// flight at once - a lane that walks the tiles itself waits one L2 round trip per tile, 20 us for a 7 k-point frame), then 29
+// lanes add them up in tile order (fixed order => bit-reproducible) and lane 0 runs the 6x6 solve.
 __global__ void __launch_bounds__(LM_SOLVE_THREADS)
 k_lm_solve(const RegDesc* __restrict__ descs, RegState* __restrict__ states, LmParamsDev prm,
            const double* __restrict__ partials, lisreg_lm_iter* __restrict__ logs, int max_tiles, int tile_pts, int B) {
-  __shared__ double stot[LM_SOLVE_THREADS / 32][LM_NSUM];
-  __shared__ SolveScratch ssc[LM_SOLVE_THREADS / 32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int b = blockIdx.x * (LM_SOLVE_THREADS / 32) + wid;
+  __shared__ double s_part[LM_SOLVE_CHUNK * LM_NSUM];
+  __shared__ double stot[LM_NSUM];
+  __shared__ SolveScratch ssc;
+  const int b = blockIdx.x;
   if (b >= B) return;
   if (states[b].done) return;
   const int n = states[b].nc + states[b].ns;
   const int ntiles = (n + tile_pts - 1) / tile_pts;
-  if (lane < 29) {
-    double v = 0.0;
-    const double* base = partials + (size_t)b * max_tiles * LM_NSUM + lane;
-    for (int t = 0; t < ntiles; t++) v += base[(size_t)t * LM_NSUM];
-    stot[wid][lane] = v;
+  const double* base = partials + (size_t)b * max_tiles * LM_NSUM;
+  double v = 0.0;
+  for (int t0 = 0; t0 < ntiles; t0 += LM_SOLVE_CHUNK) {
+    const int cnt = min(LM_SOLVE_CHUNK, ntiles - t0) * LM_NSUM;
+    for (int i = threadIdx.x; i < cnt; i += LM_SOLVE_THREADS) s_part[i] = base[(size_t)t0 * LM_NSUM + i];
+    __syncthreads();
+    if (threadIdx.x < 29) for (int i = threadIdx.x; i < cnt; i += LM_NSUM) v += s_part[i];
+    __syncthreads();
   }
-  __syncwarp();
-  if (lane == 0) {
+  if (threadIdx.x < 29) stot[threadIdx.x] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
     RegState st = states[b];
     lisreg_lm_iter* lg = logs ? &logs[(size_t)b * LISREG_MAX_ITERS + st.iter] : nullptr;
-    lm_solve_tail(st, prm, stot[wid], lg, ssc[wid]);
+    lm_solve_tail(st, prm, stot, lg, ssc);
     states[b] = st;
   }
 }

@@ -38,6 +38,7 @@ struct VoxSeg {
   float4* out;             // cap
   int* out_n;              // number of voxels
   int cap;
+  float bound;             // > 0: every coordinate is known to lie in [-bound, bound] (range-gated sweep points): lets k_vox_block skip its bounding-box pass
 };
 
 constexpr int RS_TILE = 2048;      // keys per block per pass
@@ -414,6 +415,268 @@ __global__ void k_vox_heads(VoxSeg* segs) {
     if (RUNS) { s.run_start[carry] = n; s.plan->n_runs = carry; }
     else { s.seg_start[carry] = n; *s.out_n = carry; }
   }
+}
+
+// ---- steps (1)-(4) for ONE cloud in ONE block, with the sort in shared memory ----
+// A frame's feature cloud (<= ~130 k points, ~17 k runs) is small enough that everything between "points" and "voxel
+// starts" fits one SM: the block reads the points twice (bounding box, then keys + runs; the second read hits L2), keeps
+// the run keys and two 16-bit index arrays in shared memory (8 B per run), runs the stable LSD radix passes there (per-warp
+// digit counters, match-any ranking - the same scheme as k_rs_scatter without the histogram matrix in HBM) and finds
+// the voxel heads on the sorted keys.  HBM sees the points, run_start, the sorted run ids and the voxel starts - no
+// per-point key array, no ping-pong buffers, no histogram matrix, and 1 launch instead of 19.  A cloud with more than
+// VB_CAP runs sorts through its global scratch arrays (same code, 32-bit ids): slow, correct, rare.
+__device__ __forceinline__ VoxPlan vox_make_plan(const float* mn, const float* mx, int n, float leaf) {   // = k_vox_plan
+  VoxPlan p;
+  p.inv = 1.0f / leaf;
+  p.overflow = 0;
+  if (n > 0) {
+    const long long dx = (long long)((mx[0] - mn[0]) * p.inv) + 1, dy = (long long)((mx[1] - mn[1]) * p.inv) + 1,
+                    dz = (long long)((mx[2] - mn[2]) * p.inv) + 1;
+    if (dx * dy * dz > 2147483647LL) p.overflow = 1;   // PCL: "leaf size is too small" -> output = input
+    int divb[3];
+    for (int d = 0; d < 3; d++) {
+      p.minb[d] = (int)floorf(mn[d] * p.inv);
+      divb[d] = (int)floorf(mx[d] * p.inv) - p.minb[d] + 1;
+    }
+    p.mul[0] = 1; p.mul[1] = divb[0]; p.mul[2] = divb[0] * divb[1];
+    const unsigned long long kmax = p.overflow ? (unsigned long long)n : (unsigned long long)divb[0] * (unsigned long long)divb[1] * (unsigned long long)divb[2];
+    p.npass = kmax > (1ull << 24) ? 4 : kmax > (1ull << 16) ? 3 : kmax > (1ull << 8) ? 2 : 1;
+  } else {
+    for (int d = 0; d < 3; d++) { p.minb[d] = 0; p.mul[d] = 0; }
+    p.npass = 0;
+  }
+  p.n_runs = 0;
+  return p;
+}
+
+constexpr int VB_THREADS = 1024;
+constexpr int VB_PER = 4;                 // points per thread and round of the two passes over the cloud (loads in flight)
+constexpr int VB_CAP = 22528;              // runs sorted in shared memory: 8 B each + 32 KB of digit counters
+constexpr size_t VB_SMEM = (size_t)VB_CAP * 8 + 32 * 256 * 4;
+constexpr int VOX_BLOCK_MAX_N = 131072;    // larger clouds (the 2 M-point window map) take the multi-block kernels
+
+template <typename V>
+__device__ __forceinline__ void vb_sort(const uint32_t* key, V* va, V* vb, int n, int npass, uint32_t* cnt, uint32_t* s_dtot) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int chunk = (((n + 31) / 32) + 31) & ~31;            // contiguous range of a warp, a multiple of 32
+  const int e_begin = wid * chunk, e_end = min(n, e_begin + chunk);
+  for (int p = 0; p < npass; p++) {
+    const int shift = 8 * p;
+    const V* in = (p & 1) ? va : vb;                         // pass 0 reads the identity
+    V* out = (p & 1) ? vb : va;
+    for (int d = lane; d < 256; d += 32) cnt[wid * 256 + d] = 0u;
+    __syncwarp();
+    for (int e0 = e_begin; e0 < e_end; e0 += 32) {
+      const int e = e0 + lane;
+      const bool ok = e < e_end;
+      const uint32_t v = ok ? (p == 0 ? (uint32_t)e : (uint32_t)in[e]) : 0u;
+      const uint32_t dgt = ok ? (key[v] >> shift) & 255u : 0u;
+      const unsigned act = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const unsigned m = __match_any_sync(act, dgt);
+        if (lane == __ffs(m) - 1) cnt[wid * 256 + dgt] += __popc(m);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {                                   // exclusive prefix over the warps of one digit
+      uint32_t acc = 0u;
+#pragma unroll 8
+      for (int w = 0; w < VB_THREADS / 32; w++) { const uint32_t t = cnt[w * 256 + threadIdx.x]; cnt[w * 256 + threadIdx.x] = acc; acc += t; }
+      s_dtot[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    if (wid == 0) {                                            // exclusive scan of the 256 digit totals: 8 digits per lane
+      uint32_t loc[8], sum = 0u;
+#pragma unroll
+      for (int k = 0; k < 8; k++) { loc[k] = s_dtot[lane * 8 + k]; sum += loc[k]; }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      uint32_t acc = incl - sum;
+#pragma unroll
+      for (int k = 0; k < 8; k++) { s_dtot[lane * 8 + k] = acc; acc += loc[k]; }
+    }
+    __syncthreads();
+    for (int e0 = e_begin; e0 < e_end; e0 += 32) {
+      const int e = e0 + lane;
+      const bool ok = e < e_end;
+      const uint32_t v = ok ? (p == 0 ? (uint32_t)e : (uint32_t)in[e]) : 0u;
+      const uint32_t dgt = ok ? (key[v] >> shift) & 255u : 0u;
+      const unsigned act = __ballot_sync(0xffffffffu, ok);
+      unsigned m = 0u;
+      if (ok) {
+        m = __match_any_sync(act, dgt);
+        out[s_dtot[dgt] + cnt[wid * 256 + dgt] + __popc(m & ((1u << lane) - 1u))] = (V)v;
+      }
+      __syncwarp();
+      if (ok && lane == __ffs(m) - 1) cnt[wid * 256 + dgt] += __popc(m);
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+}
+
+// exclusive block scan of one small count per thread (1024 threads): returns the offset of this thread and the block total
+__device__ __forceinline__ int vb_rank(int count, int* s_w, int* s_tot, int& total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = count;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) s_w[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    const int v = s_w[lane];
+    int wi = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+    s_w[lane] = wi - v;
+    if (lane == 31) *s_tot = wi;
+  }
+  __syncthreads();
+  const int r = s_w[wid] + incl - count;
+  total = *s_tot;
+  __syncthreads();                                             // s_w / s_tot may be rewritten by the next call
+  return r;
+}
+
+__global__ void __launch_bounds__(VB_THREADS, 1)
+k_vox_block(VoxSeg* segs) {
+  extern __shared__ __align__(16) unsigned char vb_smem[];
+  uint32_t* s_key = reinterpret_cast<uint32_t*>(vb_smem);
+  uint16_t* s_va = reinterpret_cast<uint16_t*>(s_key + VB_CAP);
+  uint16_t* s_vb = s_va + VB_CAP;
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_vb + VB_CAP);   // [32][256]; the key exchange of the run detection before the sort
+  __shared__ float s_red[6][32];
+  __shared__ int s_w[32];
+  __shared__ int s_tot;
+  __shared__ uint32_t s_lastkey;
+  __shared__ uint32_t s_dtot[256];
+  __shared__ VoxPlan s_plan;
+  const VoxSeg s = segs[blockIdx.x];
+  const int n = vox_n(s);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // ---- (1) bounding box + plan (k_vox_bbox / k_vox_plan) ----
+  // Only the ORDER of the voxel indices and the voxel a point falls into reach the output, and both are the same for any
+  // box that contains the cloud (the index is lexicographic in (z, y, x) cells either way).  A caller that knows a bound
+  // (sweep points passed the range gate) saves the pass over the points - unless the bound is so loose that the index
+  // would overflow, where PCL's own check needs the real box.
+  bool planned = false;
+  if (s.bound > 0.f && n > 0) {
+    const float bn[3] = {-s.bound, -s.bound, -s.bound}, bx[3] = {s.bound, s.bound, s.bound};
+    const VoxPlan hp = vox_make_plan(bn, bx, n, s.leaf);
+    if (!hp.overflow) { planned = true; if (threadIdx.x == 0) s_plan = hp; __syncthreads(); }
+  }
+  if (!planned) {
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i0 = threadIdx.x; i0 < n; i0 += VB_PER * VB_THREADS) {      // VB_PER points in flight per thread
+      int idx[VB_PER]; float4 q[VB_PER];
+#pragma unroll
+      for (int k = 0; k < VB_PER; k++) { const int i = min(i0 + k * VB_THREADS, n - 1); idx[k] = s.gather ? __ldg(&s.gather[i]) : i; }
+#pragma unroll
+      for (int k = 0; k < VB_PER; k++) q[k] = __ldg(&s.src[idx[k]]);
+#pragma unroll
+      for (int k = 0; k < VB_PER; k++) {
+        mn[0] = fminf(mn[0], q[k].x); mn[1] = fminf(mn[1], q[k].y); mn[2] = fminf(mn[2], q[k].z);
+        mx[0] = fmaxf(mx[0], q[k].x); mx[1] = fmaxf(mx[1], q[k].y); mx[2] = fmaxf(mx[2], q[k].z);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+        mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+      }
+    if (lane == 0) { for (int d = 0; d < 3; d++) { s_red[d][wid] = mn[d]; s_red[3 + d][wid] = mx[d]; } }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float bn[3] = {0.f, 0.f, 0.f}, bx[3] = {0.f, 0.f, 0.f};
+      if (n > 0)
+        for (int d = 0; d < 3; d++) {
+          bn[d] = s_red[d][0]; bx[d] = s_red[3 + d][0];
+          for (int w = 1; w < VB_THREADS / 32; w++) { bn[d] = fminf(bn[d], s_red[d][w]); bx[d] = fmaxf(bx[d], s_red[3 + d][w]); }
+        }
+      s_plan = vox_make_plan(bn, bx, n, s.leaf);
+    }
+    __syncthreads();
+  }
+  const VoxPlan p = s_plan;
+  // ---- (2) keys (k_vox_keys) and runs of equal consecutive keys: VB_PER consecutive points per thread ----
+  int n_runs = 0;
+  int idx_next[VB_PER];                                         // the index list runs one round ahead of the points
+#pragma unroll
+  for (int k = 0; k < VB_PER; k++) { const int i = max(0, min(VB_PER * (int)threadIdx.x + k, n - 1)); idx_next[k] = (s.gather && n > 0) ? __ldg(&s.gather[i]) : i; }
+  for (int base = 0; base < n; base += VB_PER * VB_THREADS) {
+    const int i0 = base + VB_PER * threadIdx.x;
+    uint32_t key[VB_PER];
+    if (p.overflow) {
+#pragma unroll
+      for (int k = 0; k < VB_PER; k++) key[k] = (uint32_t)(i0 + k);
+    } else {
+      int idx[VB_PER]; float4 q[VB_PER];
+#pragma unroll
+      for (int k = 0; k < VB_PER; k++) idx[k] = idx_next[k];
+#pragma unroll
+      for (int k = 0; k < VB_PER; k++) q[k] = __ldg(&s.src[idx[k]]);
+#pragma unroll
+      for (int k = 0; k < VB_PER; k++) { const int i = min(i0 + VB_PER * VB_THREADS + k, n - 1); idx_next[k] = s.gather ? __ldg(&s.gather[i]) : i; }
+#pragma unroll
+      for (int k = 0; k < VB_PER; k++) {
+        const int c0 = (int)(floorf(q[k].x * p.inv) - (float)p.minb[0]);
+        const int c1 = (int)(floorf(q[k].y * p.inv) - (float)p.minb[1]);
+        const int c2 = (int)(floorf(q[k].z * p.inv) - (float)p.minb[2]);
+        key[k] = (uint32_t)(c0 * p.mul[0] + c1 * p.mul[1] + c2 * p.mul[2]);
+      }
+    }
+    s_cnt[threadIdx.x] = key[VB_PER - 1];                      // (a clamped index repeats the last valid point: same key)
+    __syncthreads();
+    uint32_t prev = threadIdx.x ? s_cnt[threadIdx.x - 1] : s_lastkey;
+    int head[VB_PER], cnt = 0;
+#pragma unroll
+    for (int k = 0; k < VB_PER; k++) {
+      const int i = i0 + k;
+      head[k] = (i < n && (i == 0 || key[k] != prev)) ? 1 : 0;
+      cnt += head[k];
+      prev = key[k];
+    }
+    int total;
+    int r = n_runs + vb_rank(cnt, s_w, &s_tot, total);          // (its barriers also order the exchange buffer)
+#pragma unroll
+    for (int k = 0; k < VB_PER; k++)
+      if (head[k]) { s.run_start[r] = i0 + k; s.key_a[r] = key[k]; if (r < VB_CAP) s_key[r] = key[k]; r++; }
+    if (threadIdx.x == VB_THREADS - 1) s_lastkey = key[VB_PER - 1];
+    n_runs += total;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { s.run_start[n_runs] = n; VoxPlan q = p; q.n_runs = n_runs; *s.plan = q; }
+  // ---- (3) stable LSD radix sort of the run ids by key; (4) voxel heads on the sorted order ----
+  uint32_t* sval_out = (p.npass & 1) ? s.val_b : s.val_a;       // where k_vox_centroid* expect the sorted run ids
+  const bool in_smem = n_runs <= VB_CAP;
+  if (in_smem) vb_sort<uint16_t>(s_key, s_va, s_vb, n_runs, p.npass, s_cnt, s_dtot);
+  else {
+    __syncthreads();                                           // key_a of this block's own writes
+    vb_sort<uint32_t>(s.key_a, s.val_b, s.val_a, n_runs, p.npass, s_cnt, s_dtot);   // pass 0 writes val_b: an odd pass count ends there
+  }
+  const uint16_t* fin16 = (p.npass & 1) ? s_va : s_vb;
+  int n_vox = 0;
+  for (int base = 0; base < n_runs; base += VB_THREADS) {
+    const int i = base + threadIdx.x;
+    int head = 0;
+    uint32_t v = 0u;
+    if (i < n_runs) {
+      uint32_t k, kp = 0u;
+      if (in_smem) { v = fin16[i]; k = s_key[v]; if (i) kp = s_key[fin16[i - 1]]; }
+      else { v = sval_out[i]; k = s.key_a[v]; if (i) kp = s.key_a[sval_out[i - 1]]; }
+      head = (i == 0 || k != kp) ? 1 : 0;
+      if (in_smem) sval_out[i] = v;
+    }
+    int total;
+    const int r = n_vox + vb_rank(head, s_w, &s_tot, total);
+    if (head) s.seg_start[r] = i;
+    n_vox += total;
+  }
+  if (threadIdx.x == 0) { s.seg_start[n_vox] = n_runs; *s.out_n = n_vox; }
 }
 
 // (5) centroids, fp32 accumulation in ascending input index: the runs of a voxel are adjacent in the sorted arrays and -

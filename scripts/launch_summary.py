@@ -14,7 +14,9 @@ fin = [i for i, r in enumerate(rows) if r[0] == 'k_lm_finish']
 # steps = launch ranges between consecutive k_lm_finish; default: the longest one (a full device-resident batch,
 # not one chunk of the pipelined e2e path)
 steps = [(fin[i] + 1, fin[i + 1] + 1) for i in range(len(fin) - 1)]
-if len(sys.argv) > 2:
+if len(sys.argv) > 2 and sys.argv[2] == "median":      # a typical step (streaming: a frame without a map rebuild)
+    a, b = sorted(steps, key=lambda ab: sum(v for _, v in rows[ab[0]:ab[1]]))[len(steps) // 2]
+elif len(sys.argv) > 2:
     a, b = steps[-int(sys.argv[2])]
 else:
     a, b = max(steps, key=lambda ab: sum(v for _, v in rows[ab[0]:ab[1]]))

@@ -72,3 +72,25 @@ def test_every_radix_pass_count(engine, spread, leaf):
     o = orc.voxel_grid(p, leaf)
     g = engine.voxel_grid(p, leaf)
     assert np.array_equal(o, g)
+
+
+def test_block_kernel_equals_multi_kernel_path(monkeypatch):
+    """k_vox_block (one block per cloud, the sort in shared memory; clouds of up to 131072 points) against the multi-kernel
+    path (LISREG_VOX_UNFUSED=1) on a feature cloud (runs -> shared-memory sort), a shuffled one (every point its own run ->
+    the in-kernel global-memory sort) and sizes around the 22528-run capacity."""
+    from lis_slam_b200 import engine as E
+    s = scene().scan(np.array([0, 0, 0.3, 5, 0.5, 0], np.float32))
+    f = orc.extract_features(s["pts"], s["ring"])
+    surf = np.ascontiguousarray(s["pts"][f["src_index"]][f["surf_idx"]])
+    rng = np.random.default_rng(3)
+    clouds = [(surf, 0.4), (surf[rng.permutation(len(surf))], 0.4), (_cloud(22528, 1), 0.2), (_cloud(22529, 2), 0.2), (_cloud(131072, 3), 0.4),
+              (surf[:1], 0.4)]
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("LISREG_VOX_UNFUSED", mode)
+        eng = E.Engine(device=0)
+        outs[mode] = [eng.voxel_grid(c, leaf) for c, leaf in clouds]
+        eng.close()
+    for a, b, (c, leaf) in zip(outs["0"], outs["1"], clouds):
+        assert np.array_equal(a, b)
+    assert np.array_equal(outs["0"][0], orc.voxel_grid(surf, 0.4))
