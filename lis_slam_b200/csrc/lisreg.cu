@@ -156,6 +156,7 @@ struct lisreg_ctx {
   int knn_coop_max = 16384;   // scan lists shorter than this are searched warp-per-query (LISREG_KNN_COOP_MAX; 0 = never)
   int feat_fused = 0;     // LISREG_FEAT_FUSED=1: projection + compaction in one kernel with the range-image slice in shared memory (k_feat_front);
                           // measured slower than the global range image on firing-order sweeps (8x redundant ring-id scans), so off by default
+  int vox_batch_form = 0; // LISREG_VOX_BATCH_FORM=1: a handful of clouds also take the kernels meant for hundreds (tests reach them through lisreg_voxel_grid)
   int vox_unfused = 0;    // LISREG_VOX_UNFUSED=1: frame-sized clouds take the multi-kernel voxel path too (parity check of k_vox_block)
   int knn_noskip = 0;   // LISREG_KNN_NOSKIP=1: search every query from scratch at every iteration (parity check of the CHECK path)
   // profiling
@@ -428,6 +429,7 @@ int32_t lisreg_create(const lisreg_config* cfg, lisreg_ctx** out) {
   if (const char* e2 = getenv("LISREG_KNN_NOSKIP")) ctx->knn_noskip = atoi(e2) ? 1 : 0;
   if (const char* e3 = getenv("LISREG_FEAT_FUSED")) ctx->feat_fused = atoi(e3) ? 1 : 0;
   if (const char* e5 = getenv("LISREG_VOX_UNFUSED")) ctx->vox_unfused = atoi(e5) ? 1 : 0;
+  if (const char* e6 = getenv("LISREG_VOX_BATCH_FORM")) ctx->vox_batch_form = atoi(e6) ? 1 : 0;
   if (const char* e4 = getenv("LISREG_KNN_COOP_MAX")) ctx->knn_coop_max = std::max(0, atoi(e4));
   if (const char* e3 = getenv("LISREG_E2E_CHUNK")) ctx->e2e_chunk = std::max(0, atoi(e3));
   if (const char* e4 = getenv("LISREG_DEV_SPLIT")) ctx->dev_split = std::min(4, std::max(0, atoi(e4)));
@@ -1039,14 +1041,21 @@ static int run_voxel(lisreg_ctx* ctx, VoxSeg* d_segs, int nseg, int max_n, doubl
   ProfScope ps(ctx, PROF_VOXEL, alg_bytes, 16);
   // single-block scans are the cheaper choice when there are many clouds to keep the GPU busy; with a handful of clouds
   // (streaming odometry: one frame's two clouds, the 2 M-point window map) they serialise, so those take the parallel forms
-  const bool big = nseg < 64;
+  const bool big = nseg < 64 && !ctx->vox_batch_form;
   if (max_n <= VOX_BLOCK_MAX_N && !ctx->vox_unfused) {
     // clouds of frame size: bounding box -> keys -> runs -> sort -> voxel heads by ONE block per cloud, the sort in shared memory
     static bool attr_set = false;
-    if (!attr_set) { CK(cudaFuncSetAttribute(k_vox_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VB_SMEM)); attr_set = true; }
-    k_vox_block<<<nseg, VB_THREADS, VB_SMEM, st>>>(d_segs); LAUNCH_CK();
-    if (big) { k_vox_centroid_warp<<<dim3(std::max(1, std::min(2 * ctx->n_sm, (max_n + 255) / 256)), nseg), 256, 0, st>>>(d_segs); LAUNCH_CK(); }
-    else { k_vox_centroid<<<dim3(std::max(1, (max_n + VC_CHUNK - 1) / VC_CHUNK), nseg), 256, 0, st>>>(d_segs); LAUNCH_CK(); }
+    if (!attr_set) {
+      CK(cudaFuncSetAttribute(k_vox_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VB_SMEM));
+      CK(cudaFuncSetAttribute(k_vox_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VB_SMEM));
+      attr_set = true;
+    }
+    if (big) {
+      k_vox_block<false><<<nseg, VB_THREADS, VB_SMEM, st>>>(d_segs); LAUNCH_CK();
+      k_vox_centroid_warp<<<dim3(std::max(1, std::min(2 * ctx->n_sm, (max_n + 255) / 256)), nseg), 256, 0, st>>>(d_segs); LAUNCH_CK();
+    } else {
+      k_vox_block<true><<<nseg, VB_THREADS, VB_SMEM, st>>>(d_segs); LAUNCH_CK();
+    }
     return LISREG_OK;
   }
   k_vox_bbox_init<<<(nseg * 6 + 255) / 256, 256, 0, st>>>(d_segs, nseg); LAUNCH_CK();

@@ -450,6 +450,7 @@ __device__ __forceinline__ VoxPlan vox_make_plan(const float* mn, const float* m
 }
 
 constexpr int VB_THREADS = 1024;
+constexpr int VB_LEN_SAT = 32767;           // run lengths are packed in 15 bits next to the 17-bit first index (clouds of <= 131072 points)
 constexpr int VB_PER = 4;                 // points per thread and round of the two passes over the cloud (loads in flight)
 constexpr int VB_CAP = 22528;              // runs sorted in shared memory: 8 B each + 32 KB of digit counters
 constexpr size_t VB_SMEM = (size_t)VB_CAP * 8 + 32 * 256 * 4;
@@ -540,6 +541,10 @@ __device__ __forceinline__ int vb_rank(int count, int* s_w, int* s_tot, int& tot
   return r;
 }
 
+// CENTROID: the block also computes the centroids (batched frames: hundreds of clouds keep every SM busy); without it the
+// voxel starts / sorted run ids go to global memory for k_vox_centroid_warp (a single frame: two clouds, the centroids
+// are better spread over the whole GPU).
+template <bool CENTROID>
 __global__ void __launch_bounds__(VB_THREADS, 1)
 k_vox_block(VoxSeg* segs) {
   extern __shared__ __align__(16) unsigned char vb_smem[];
@@ -659,6 +664,8 @@ k_vox_block(VoxSeg* segs) {
     vb_sort<uint32_t>(s.key_a, s.val_b, s.val_a, n_runs, p.npass, s_cnt, s_dtot);   // pass 0 writes val_b: an odd pass count ends there
   }
   const uint16_t* fin16 = (p.npass & 1) ? s_va : s_vb;
+  uint16_t* s_seg = (p.npass & 1) ? s_vb : s_va;                // CENTROID: voxel starts stay in shared memory (the idle id array)
+  const bool meta_smem = CENTROID && in_smem;
   int n_vox = 0;
   for (int base = 0; base < n_runs; base += VB_THREADS) {
     const int i = base + threadIdx.x;
@@ -669,14 +676,73 @@ k_vox_block(VoxSeg* segs) {
       if (in_smem) { v = fin16[i]; k = s_key[v]; if (i) kp = s_key[fin16[i - 1]]; }
       else { v = sval_out[i]; k = s.key_a[v]; if (i) kp = s.key_a[sval_out[i - 1]]; }
       head = (i == 0 || k != kp) ? 1 : 0;
-      if (in_smem) sval_out[i] = v;
+      if (in_smem && !meta_smem) sval_out[i] = v;
     }
     int total;
     const int r = n_vox + vb_rank(head, s_w, &s_tot, total);
-    if (head) s.seg_start[r] = i;
+    if (head) { if (meta_smem) s_seg[r] = (uint16_t)i; else s.seg_start[r] = i; }
     n_vox += total;
   }
-  if (threadIdx.x == 0) { s.seg_start[n_vox] = n_runs; *s.out_n = n_vox; }
+  if (threadIdx.x == 0) { if (!meta_smem) s.seg_start[n_vox] = n_runs; *s.out_n = n_vox; }
+  if (!CENTROID) return;
+  __syncthreads();
+  // ---- (5) centroids by this block: one thread per voxel, points added in ascending input index (see k_vox_centroid) ----
+  // Shared-memory case: the keys are dead now, their array takes (first point, length) of every run in SORTED order, so a
+  // voxel's thread reads its runs from shared memory and only the index list and the points themselves from L2 / HBM.
+  uint32_t* s_run = s_key;                                     // first input index (17 bits) | min(length, VB_LEN_SAT) << 17
+  if (meta_smem) {
+    for (int i = threadIdx.x; i < n_runs; i += VB_THREADS) {
+      const int v = fin16[i];
+      const int a = s.run_start[v], len = s.run_start[v + 1] - a;
+      s_run[i] = (uint32_t)a | ((uint32_t)min(len, VB_LEN_SAT) << 17);
+    }
+    __syncthreads();
+  }
+  const float4* __restrict__ src = s.src;
+  const int* __restrict__ gat = s.gather;
+  for (int v = threadIdx.x; v < n_vox; v += VB_THREADS) {
+    const int rb = meta_smem ? (int)s_seg[v] : s.seg_start[v];
+    const int re = meta_smem ? (v + 1 < n_vox ? (int)s_seg[v + 1] : n_runs) : s.seg_start[v + 1];
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    int cnt = 0;
+    for (int r = rb; r < re; r++) {
+      int a, len;
+      if (meta_smem) {
+        const uint32_t pk = s_run[r];
+        a = (int)(pk & 0x1ffffu); len = (int)(pk >> 17);
+        if (len == VB_LEN_SAT) len = s.run_start[fin16[r] + 1] - a;      // a run longer than the packed field
+      } else {
+        const int run = (int)sval_out[r];
+        a = s.run_start[run]; len = s.run_start[run + 1] - a;
+      }
+      const int e = a + len;
+      int j = a;
+      for (; j + 4 <= e; j += 4) {
+        int i0 = j, i1 = j + 1, i2 = j + 2, i3 = j + 3;
+        if (gat) { i0 = __ldg(&gat[j]); i1 = __ldg(&gat[j + 1]); i2 = __ldg(&gat[j + 2]); i3 = __ldg(&gat[j + 3]); }
+        const float4 p0 = __ldg(&src[i0]), p1 = __ldg(&src[i1]), p2 = __ldg(&src[i2]), p3 = __ldg(&src[i3]);
+        sx += p0.x; sy += p0.y; sz += p0.z; si += p0.w;
+        sx += p1.x; sy += p1.y; sz += p1.z; si += p1.w;
+        sx += p2.x; sy += p2.y; sz += p2.z; si += p2.w;
+        sx += p3.x; sy += p3.y; sz += p3.z; si += p3.w;
+      }
+      if (j < e) {                                             // 1..3 points left: their loads go out together as well
+        const int m = e - j;
+        int i0 = j, i1 = j + 1, i2 = j + 2;
+        if (gat) { i0 = __ldg(&gat[j]); if (m > 1) i1 = __ldg(&gat[j + 1]); if (m > 2) i2 = __ldg(&gat[j + 2]); }
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 p0 = __ldg(&src[i0]);
+        const float4 p1 = m > 1 ? __ldg(&src[i1]) : z4;
+        const float4 p2 = m > 2 ? __ldg(&src[i2]) : z4;
+        sx += p0.x; sy += p0.y; sz += p0.z; si += p0.w;
+        if (m > 1) { sx += p1.x; sy += p1.y; sz += p1.z; si += p1.w; }
+        if (m > 2) { sx += p2.x; sy += p2.y; sz += p2.z; si += p2.w; }
+      }
+      cnt += len;
+    }
+    const float c = (float)cnt;
+    s.out[v] = make_float4(sx / c, sy / c, sz / c, si / c);
+  }
 }
 
 // (5) centroids, fp32 accumulation in ascending input index: the runs of a voxel are adjacent in the sorted arrays and -

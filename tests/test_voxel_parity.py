@@ -86,11 +86,13 @@ def test_block_kernel_equals_multi_kernel_path(monkeypatch):
     clouds = [(surf, 0.4), (surf[rng.permutation(len(surf))], 0.4), (_cloud(22528, 1), 0.2), (_cloud(22529, 2), 0.2), (_cloud(131072, 3), 0.4),
               (surf[:1], 0.4)]
     outs = {}
-    for mode in ("0", "1"):
+    for mode, batch in (("0", "0"), ("1", "0"), ("0", "1"), ("1", "1")):     # batch form: centroids inside the block kernel / thread per voxel
         monkeypatch.setenv("LISREG_VOX_UNFUSED", mode)
+        monkeypatch.setenv("LISREG_VOX_BATCH_FORM", batch)
         eng = E.Engine(device=0)
-        outs[mode] = [eng.voxel_grid(c, leaf) for c, leaf in clouds]
+        outs[(mode, batch)] = [eng.voxel_grid(c, leaf) for c, leaf in clouds]
         eng.close()
-    for a, b, (c, leaf) in zip(outs["0"], outs["1"], clouds):
-        assert np.array_equal(a, b)
-    assert np.array_equal(outs["0"][0], orc.voxel_grid(surf, 0.4))
+    ref = [orc.voxel_grid(c, leaf) for c, leaf in clouds]
+    for k, v in outs.items():
+        for a, b in zip(ref, v):
+            assert np.array_equal(a, b), k
