@@ -38,6 +38,7 @@ struct VoxSeg {
   float4* out;             // cap
   int* out_n;              // number of voxels
   int cap;
+  int gather_increasing;   // the index list is strictly increasing (a surface list; NOT a corner list, which is in pick order): lets k_vox_block detect runs that are contiguous in src
   float bound;             // > 0: every coordinate is known to lie in [-bound, bound] (range-gated sweep points): lets k_vox_block skip its bounding-box pass
 };
 
@@ -450,10 +451,11 @@ __device__ __forceinline__ VoxPlan vox_make_plan(const float* mn, const float* m
 }
 
 constexpr int VB_THREADS = 1024;
-constexpr int VB_LEN_SAT = 32767;           // run lengths are packed in 15 bits next to the 17-bit first index (clouds of <= 131072 points)
+constexpr int VB_LEN_SAT = 16383;           // run lengths are packed in 14 bits next to the 17-bit first index (clouds of <= 131072 points) and a flag
 constexpr int VB_PER = 4;                 // points per thread and round of the two passes over the cloud (loads in flight)
 constexpr int VB_CAP = 22528;              // runs sorted in shared memory: 8 B each + 32 KB of digit counters
 constexpr size_t VB_SMEM = (size_t)VB_CAP * 8 + 32 * 256 * 4;
+constexpr int VOX_BLOCK_MAX_N_FEW = 49152;  // ... and so do clouds above this size when there are only a few of them (no other block to fill the SMs)
 constexpr int VOX_BLOCK_MAX_N = 131072;    // larger clouds (the 2 M-point window map) take the multi-block kernels
 
 template <typename V>
@@ -689,17 +691,28 @@ k_vox_block(VoxSeg* segs) {
   // ---- (5) centroids by this block: one thread per voxel, points added in ascending input index (see k_vox_centroid) ----
   // Shared-memory case: the keys are dead now, their array takes (first point, length) of every run in SORTED order, so a
   // voxel's thread reads its runs from shared memory and only the index list and the points themselves from L2 / HBM.
-  uint32_t* s_run = s_key;                                     // first input index (17 bits) | min(length, VB_LEN_SAT) << 17
+  // s_run[i] = first index (17 bits) | min(length, VB_LEN_SAT) << 17 | direct << 31.  direct: the run's points are CONSECUTIVE
+  // in the source cloud (always without an index list; with one, whenever the list does not skip inside the run - a feature
+  // list only skips the few corner picks), so the first index is stored as a SOURCE index and the points are read without
+  // going through the list: one dependent load per batch instead of two.
+  uint32_t* s_run = s_key;
+  const float4* __restrict__ src = s.src;
+  const int* __restrict__ gat = s.gather;
   if (meta_smem) {
     for (int i = threadIdx.x; i < n_runs; i += VB_THREADS) {
       const int v = fin16[i];
       const int a = s.run_start[v], len = s.run_start[v + 1] - a;
-      s_run[i] = (uint32_t)a | ((uint32_t)min(len, VB_LEN_SAT) << 17);
+      uint32_t first = (uint32_t)a, direct = 1u;
+      if (gat && !s.gather_increasing) direct = 0u;
+      else if (gat) {
+        const int g0 = __ldg(&gat[a]), g1 = __ldg(&gat[a + len - 1]);
+        direct = (g1 - g0 == len - 1 && (unsigned)g0 < 0x20000u) ? 1u : 0u;   // the list is strictly increasing: equal span <=> no skip
+        if (direct) first = (uint32_t)g0;
+      }
+      s_run[i] = first | ((uint32_t)min(len, VB_LEN_SAT) << 17) | (direct << 31);
     }
     __syncthreads();
   }
-  const float4* __restrict__ src = s.src;
-  const int* __restrict__ gat = s.gather;
   for (int v = threadIdx.x; v < n_vox; v += VB_THREADS) {
     const int rb = meta_smem ? (int)s_seg[v] : s.seg_start[v];
     const int re = meta_smem ? (v + 1 < n_vox ? (int)s_seg[v + 1] : n_runs) : s.seg_start[v + 1];
@@ -707,19 +720,24 @@ k_vox_block(VoxSeg* segs) {
     int cnt = 0;
     for (int r = rb; r < re; r++) {
       int a, len;
+      bool direct = false;
       if (meta_smem) {
         const uint32_t pk = s_run[r];
-        a = (int)(pk & 0x1ffffu); len = (int)(pk >> 17);
-        if (len == VB_LEN_SAT) len = s.run_start[fin16[r] + 1] - a;      // a run longer than the packed field
+        a = (int)(pk & 0x1ffffu); len = (int)((pk >> 17) & (uint32_t)VB_LEN_SAT); direct = (pk >> 31) != 0u;
+        if (len == VB_LEN_SAT) {                                 // a run longer than the packed field: the exact length from the table
+          const int run = fin16[r];
+          len = s.run_start[run + 1] - s.run_start[run];
+        }
       } else {
         const int run = (int)sval_out[r];
         a = s.run_start[run]; len = s.run_start[run + 1] - a;
       }
+      const bool use_list = gat != nullptr && !direct;
       const int e = a + len;
       int j = a;
       for (; j + 4 <= e; j += 4) {
         int i0 = j, i1 = j + 1, i2 = j + 2, i3 = j + 3;
-        if (gat) { i0 = __ldg(&gat[j]); i1 = __ldg(&gat[j + 1]); i2 = __ldg(&gat[j + 2]); i3 = __ldg(&gat[j + 3]); }
+        if (use_list) { i0 = __ldg(&gat[j]); i1 = __ldg(&gat[j + 1]); i2 = __ldg(&gat[j + 2]); i3 = __ldg(&gat[j + 3]); }
         const float4 p0 = __ldg(&src[i0]), p1 = __ldg(&src[i1]), p2 = __ldg(&src[i2]), p3 = __ldg(&src[i3]);
         sx += p0.x; sy += p0.y; sz += p0.z; si += p0.w;
         sx += p1.x; sy += p1.y; sz += p1.z; si += p1.w;
@@ -729,7 +747,7 @@ k_vox_block(VoxSeg* segs) {
       if (j < e) {                                             // 1..3 points left: their loads go out together as well
         const int m = e - j;
         int i0 = j, i1 = j + 1, i2 = j + 2;
-        if (gat) { i0 = __ldg(&gat[j]); if (m > 1) i1 = __ldg(&gat[j + 1]); if (m > 2) i2 = __ldg(&gat[j + 2]); }
+        if (use_list) { i0 = __ldg(&gat[j]); if (m > 1) i1 = __ldg(&gat[j + 1]); if (m > 2) i2 = __ldg(&gat[j + 2]); }
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 p0 = __ldg(&src[i0]);
         const float4 p1 = m > 1 ? __ldg(&src[i1]) : z4;
