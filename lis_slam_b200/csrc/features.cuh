@@ -24,6 +24,7 @@ struct FeatParamsDev {
   int n_scan, horizon, downsample;
   float min_range, max_range, edge_thr, surf_thr;
   lisreg_cloud_layout lay;     // point_step == 0: packed float4 records + ring array
+  int lean;                    // the per-point curvature / occlusion arrays are not used (k_feat_segments<true> computes both itself): do not initialise them
 };
 
 // Per-frame views into the batch work buffers (all device pointers).
@@ -259,7 +260,8 @@ __global__ void k_feat_compact(FeatFrame* frames, FeatParamsDev prm) {
       f.ext_src[pos] = own;
       f.col[pos] = (unsigned short)j;
       f.range[pos] = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
-      f.picked[pos] = 0; f.label[pos] = 0; f.curv[pos] = 0.f;     // resetParameters (:61-75): cleared per extracted slot
+      f.label[pos] = 0;                                           // resetParameters (:61-75): cleared per extracted slot
+      if (!prm.lean) { f.picked[pos] = 0; f.curv[pos] = 0.f; }
     }
   }
 }
@@ -399,7 +401,8 @@ k_feat_front(FeatFrame* frames, FeatParamsDev prm, int R, int G, int F, int* ctl
       f.ext_src[pos] = own;
       f.col[pos] = (unsigned short)j;
       f.range[pos] = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
-      f.picked[pos] = 0; f.label[pos] = 0; f.curv[pos] = 0.f;       // resetParameters (:61-75): cleared per extracted slot
+      f.label[pos] = 0;                                             // resetParameters (:61-75): cleared per extracted slot
+      if (!prm.lean) { f.picked[pos] = 0; f.curv[pos] = 0.f; }
     }
   }
   // ---- replay safety: the last block to finish clears the control words ----
@@ -455,6 +458,18 @@ constexpr int FEAT_CH = 12;              // segment elements per lane: a segment
 // reductions (redux.sync) for the winning (curvature, index) key, the pre-computed suppression reach of the winner,
 // and an O(1) alive-mask update per lane.  ~40 steps per
 // segment instead of a 512-key bitonic sort plus a 300-element sequential walk by one lane.
+// FUSED: smoothness (F3) and the occlusion / isolated-point marks (F4) are computed here from the extracted ranges and
+// columns instead of being read back from k_feat_curv_occl's arrays (the batched pipelines, where neither is an output).
+// The marks are "pulled": condition bits of every point i (A: marks i-5..i, B: marks i+1..i+6, :575-593) go into two
+// bit masks per ring window by ballot; a point is marked when any A bit of [k, k+5] or B bit of [k-6, k-1] is set, or
+// when it is isolated itself (:597-603).
+__device__ __forceinline__ float feat_curv_at(const float* __restrict__ r, int i, int M) {
+  if (i < 5 || i >= M - 5) return 0.f;                          // never computed upstream: the cleared value
+  const float d = r[i - 5] + r[i - 4] + r[i - 3] + r[i - 2] + r[i - 1] - r[i] * 10 +
+                  r[i + 1] + r[i + 2] + r[i + 3] + r[i + 4] + r[i + 5];   // exact op order (:549-553)
+  return d * d;
+}
+template <bool FUSED>
 __global__ void __launch_bounds__(32 * FEAT_WARPS, 7)
 k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
   const FeatFrame f = frames[blockIdx.y];
@@ -463,6 +478,7 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
   __shared__ unsigned char s_pick[FEAT_WARPS][FEAT_RING_MAX];
   __shared__ unsigned char s_reach[FEAT_WARPS][FEAT_RING_MAX];   // suppression reach of every point: right | left << 4
   __shared__ float s_cv[FEAT_WARPS][32 * FEAT_CH];
+  __shared__ unsigned s_mask[FUSED ? FEAT_WARPS : 1][2][FUSED ? (FEAT_RING_MAX + 12) / 32 + 3 : 1];   // FUSED: occlusion condition bits A / B of the ring window
   __shared__ unsigned s_gap[FEAT_WARPS][FEAT_RING_MAX / 32 + 3];  // column-gap bits of the ring window               // curvature of the current segment, slot-major
   if (ring >= prm.n_scan) return;
   const unsigned FULL = 0xffffffffu;
@@ -474,12 +490,47 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
   const int hi = min(end + 5 + 6, M - 1);
   const int wlen = max(hi - lo + 1, 0);
   unsigned char* sreach = s_reach[wid];
-  for (int t = lane; t < wlen; t += 32) spick[t] = f.picked[lo + t];
+  unsigned* sgap = s_gap[wid];
+  if (!FUSED) {
+    for (int t = lane; t < wlen; t += 32) spick[t] = f.picked[lo + t];
+  } else {
+    const float* __restrict__ rr = f.range;
+    const unsigned short* __restrict__ cc = f.col;
+    unsigned* sA = s_mask[wid][0]; unsigned* sB = s_mask[wid][1];
+    const int mlo = lo - 6;                                     // bit u of the masks <-> extracted index mlo + u
+    const int nbits = wlen + 12;
+    for (int u0 = 0; u0 < nbits + 32; u0 += 32) {               // one spare word: the funnel shifts read word w + 1
+      const int i = mlo + u0 + lane;
+      bool a = false, b = false;
+      if (u0 + lane < nbits && i >= 5 && i < M - 6) {
+        const float depth1 = rr[i], depth2 = rr[i + 1];
+        if (abs((int)cc[i + 1] - (int)cc[i]) < 10) {
+          if ((double)(depth1 - depth2) > 0.3) a = true;
+          else if ((double)(depth2 - depth1) > 0.3) b = true;
+        }
+      }
+      const unsigned ma = __ballot_sync(FULL, a), mb = __ballot_sync(FULL, b);
+      if (lane == 0) { sA[u0 >> 5] = ma; sB[u0 >> 5] = mb; }
+    }
+    __syncwarp();
+    for (int t = lane; t < wlen; t += 32) {
+      const int k = lo + t;
+      const int ua = t + 6, ub = t;                             // A bits of [k, k+5] start at u = k - mlo; B bits of [k-6, k-1] at u - 6
+      const unsigned abits = __funnelshift_r(sA[ua >> 5], sA[(ua >> 5) + 1], ua & 31) & 0x3fu;
+      const unsigned bbits = __funnelshift_r(sB[ub >> 5], sB[(ub >> 5) + 1], ub & 31) & 0x3fu;
+      bool pk = (abits | bbits) != 0u;
+      if (!pk && k >= 5 && k < M - 6) {
+        const float r0 = rr[k];
+        const float diff1 = fabsf(rr[k - 1] - r0), diff2 = fabsf(rr[k + 1] - r0);
+        pk = (double)diff1 > 0.02 * (double)r0 && (double)diff2 > 0.02 * (double)r0;
+      }
+      spick[t] = pk ? 1 : 0;
+    }
+  }
   __syncwarp();
   // How far a pick of each point suppresses to the right / left (:648-661) depends on the column indices only:
   // gap bit t = "the walk cannot step from t to t+1" (column jump > 10, or t+1 outside the window / the cloud); the
   // reach of a point is the run of clear gap bits next to it, capped at 5 - one ffs / clz per point.
-  unsigned* sgap = s_gap[wid];
   for (int base = 0; base < wlen + 32; base += 32) {
     const int t = base + lane;
     const bool gap = (t + 1 >= wlen) || abs((int)f.col[lo + t + 1] - (int)f.col[lo + t]) > 10;   // column indices straight from global memory
@@ -513,7 +564,7 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
 #pragma unroll
     for (int t = 0; t < FEAT_CH; t++) {
       const int idx = sp + 32 * t + lane;
-      cv[t] = idx < ep ? f.curv[idx] : KNN_SEG_INF;
+      cv[t] = idx < ep ? (FUSED ? feat_curv_at(f.range, idx, M) : f.curv[idx]) : KNN_SEG_INF;
       scv[32 * t + lane] = cv[t];
     }
     unsigned long long slot_of_rank = 0ull, rank_of_slot = 0ull;
@@ -525,7 +576,7 @@ k_feat_segments(FeatFrame* frames, FeatParamsDev prm) {
       slot_of_rank |= (unsigned long long)t << (4 * rk);
       rank_of_slot |= (unsigned long long)rk << (4 * t);
     }
-    const float cv_ep = f.curv[ep];
+    const float cv_ep = FUSED ? feat_curv_at(f.range, ep, M) : f.curv[ep];
     auto mark = [&](int ind, unsigned& alive_r) {
       const int rch = sreach[ind - lo];
       const int a0 = ind - (rch >> 4), b0 = ind + (rch & 15);

@@ -156,6 +156,7 @@ struct lisreg_ctx {
   int knn_coop_max = 16384;   // scan lists shorter than this are searched warp-per-query (LISREG_KNN_COOP_MAX; 0 = never)
   int feat_fused = 0;     // LISREG_FEAT_FUSED=1: projection + compaction in one kernel with the range-image slice in shared memory (k_feat_front);
                           // measured slower than the global range image on firing-order sweeps (8x redundant ring-id scans), so off by default
+  int feat_seg_unfused = 0; // LISREG_FEAT_SEG_UNFUSED=1: the batched pipelines run k_feat_curv_occl + the plain selection kernel too (parity check)
   int vox_batch_form = 0; // LISREG_VOX_BATCH_FORM=1: a handful of clouds also take the kernels meant for hundreds (tests reach them through lisreg_voxel_grid)
   int vox_unfused = 0;    // LISREG_VOX_UNFUSED=1: frame-sized clouds take the multi-kernel voxel path too (parity check of k_vox_block)
   int knn_noskip = 0;   // LISREG_KNN_NOSKIP=1: search every query from scratch at every iteration (parity check of the CHECK path)
@@ -430,6 +431,7 @@ int32_t lisreg_create(const lisreg_config* cfg, lisreg_ctx** out) {
   if (const char* e3 = getenv("LISREG_FEAT_FUSED")) ctx->feat_fused = atoi(e3) ? 1 : 0;
   if (const char* e5 = getenv("LISREG_VOX_UNFUSED")) ctx->vox_unfused = atoi(e5) ? 1 : 0;
   if (const char* e6 = getenv("LISREG_VOX_BATCH_FORM")) ctx->vox_batch_form = atoi(e6) ? 1 : 0;
+  if (const char* e7 = getenv("LISREG_FEAT_SEG_UNFUSED")) ctx->feat_seg_unfused = atoi(e7) ? 1 : 0;
   if (const char* e4 = getenv("LISREG_KNN_COOP_MAX")) ctx->knn_coop_max = std::max(0, atoi(e4));
   if (const char* e3 = getenv("LISREG_E2E_CHUNK")) ctx->e2e_chunk = std::max(0, atoi(e3));
   if (const char* e4 = getenv("LISREG_DEV_SPLIT")) ctx->dev_split = std::min(4, std::max(0, atoi(e4)));
@@ -896,10 +898,12 @@ static int feat_reserve(lisreg_ctx* ctx, int F, int cells, int nscan) {
 }
 
 // runs F1-F5 for F frames whose FeatFrame descriptors (device) are ready
+// lean: the caller consumes the feature lists only (not the per-point curvature / label arrays of lisreg_extract_features)
 static int run_features(lisreg_ctx* ctx, FeatFrame* d_frames, int F, const lisreg_feat_params* prm, int max_n, double alg_bytes,
-                        bool with_deskew = false) {
+                        bool with_deskew = false, bool lean = false) {
   cudaStream_t st = ctx->cur->stream;
-  FeatParamsDev dp{prm->n_scan, prm->horizon, prm->downsample_rate, prm->min_range, prm->max_range, prm->edge_thr, prm->surf_thr, prm->layout};
+  const bool seg_fused = lean && !ctx->feat_seg_unfused;
+  FeatParamsDev dp{prm->n_scan, prm->horizon, prm->downsample_rate, prm->min_range, prm->max_range, prm->edge_thr, prm->surf_thr, prm->layout, seg_fused ? 1 : 0};
   const int cells = prm->n_scan * prm->horizon;
   ProfScope ps(ctx, PROF_FEAT, alg_bytes, 7);
   // F1 + F2 on chip (k_feat_front, opt-in) when the ring ids come as their own array and no de-skew reference has to be found
@@ -924,8 +928,13 @@ static int run_features(lisreg_ctx* ctx, FeatFrame* d_frames, int F, const lisre
     if (with_deskew) { k_feat_compact<true><<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK(); }
     else { k_feat_compact<false><<<dim3(prm->n_scan, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK(); }
   }
-  k_feat_curv_occl<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames); LAUNCH_CK();
-  k_feat_segments<<<dim3((prm->n_scan + FEAT_WARPS - 1) / FEAT_WARPS, F), 32 * FEAT_WARPS, 0, st>>>(d_frames, dp); LAUNCH_CK();
+  if (seg_fused) {
+    // pipelines that only consume the feature lists: smoothness and occlusion marks are computed inside the selection kernel
+    k_feat_segments<true><<<dim3((prm->n_scan + FEAT_WARPS - 1) / FEAT_WARPS, F), 32 * FEAT_WARPS, 0, st>>>(d_frames, dp); LAUNCH_CK();
+  } else {
+    k_feat_curv_occl<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames); LAUNCH_CK();
+    k_feat_segments<false><<<dim3((prm->n_scan + FEAT_WARPS - 1) / FEAT_WARPS, F), 32 * FEAT_WARPS, 0, st>>>(d_frames, dp); LAUNCH_CK();
+  }
   k_feat_gather<<<dim3(FEAT_GATHER_SPLIT, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
   return LISREG_OK;
 }
@@ -1223,7 +1232,7 @@ static int run_frames(lisreg_ctx* ctx, int F, const lisreg_frame_item* items, co
   CK(cudaMemcpyAsync(ctx->cur->d_vox_segs.p, hv, sizeof(VoxSeg) * 2 * (size_t)F, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->cur->d_descs.p, hd, sizeof(RegDesc) * (size_t)F, cudaMemcpyHostToDevice, st));
   if (imu_doubles) CK(cudaMemcpyAsync(ctx->cur->d_imu.p, h_imu.data(), sizeof(double) * imu_doubles, cudaMemcpyHostToDevice, st));   // pageable: consumed on return
-  rc = run_features(ctx, (FeatFrame*)ctx->cur->d_feat_frames.p, F, fp, max_n, feat_bytes, dsk != nullptr);
+  rc = run_features(ctx, (FeatFrame*)ctx->cur->d_feat_frames.p, F, fp, max_n, feat_bytes, dsk != nullptr, true);
   if (rc) return rc;
   rc = run_voxel(ctx, (VoxSeg*)ctx->cur->d_vox_segs.p, 2 * F, std::min(max_n, cells), 2.0 * feat_bytes);
   if (rc) return rc;
@@ -2265,7 +2274,7 @@ static int odom_push_impl(lisreg_ctx* ctx, int32_t odom_id, const float* pts, co
     // FirstFlag (:175-183): features and the first key frame only, no registration
     f.pts = d_pts; f.ring = d_ring; f.n = n;
     CK(cudaMemcpyAsync(ctx->cur->d_feat_frames.p, &f, sizeof(f), cudaMemcpyHostToDevice, st));   // pageable: consumed on return
-    rc = run_features(ctx, (FeatFrame*)ctx->cur->d_feat_frames.p, 1, &fp, n, 17.0 * n);
+    rc = run_features(ctx, (FeatFrame*)ctx->cur->d_feat_frames.p, 1, &fp, n, 17.0 * n, false, true);
     if (rc) return rc;
     CK(cudaMemcpyAsync(hio + o_cnt, f.counts, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

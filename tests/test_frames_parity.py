@@ -149,9 +149,12 @@ def test_device_resident_sub_batches_are_bit_identical(monkeypatch):
     dev = torch.device("cuda", 0)
     d_sw = {id(s): (torch.from_numpy(np.ascontiguousarray(s["pts"], np.float32)).to(dev), torch.from_numpy(s["ring"].astype(np.int16)).to(dev)) for s in base}
     out = {}
-    for split, fused in (("0", "0"), ("4", "0"), ("0", "1"), ("4", "1")):      # fused: k_feat_front with 8-ring groups (opt-in)
+    # fused: k_feat_front with 8-ring groups (opt-in); plain: curvature / occlusion marks by k_feat_curv_occl instead of inside
+    # the selection kernel
+    for split, fused, plain in (("0", "0", "0"), ("4", "0", "0"), ("0", "1", "0"), ("4", "1", "0"), ("4", "0", "1")):
         monkeypatch.setenv("LISREG_DEV_SPLIT", split)
         monkeypatch.setenv("LISREG_FEAT_FUSED", fused)
+        monkeypatch.setenv("LISREG_FEAT_SEG_UNFUSED", plain)
         eng = E.Engine(device=0)
         mid = eng.map_create(m["corner"], m["surf"], gate_hint=1.0)
         items = (E.FrameItem * F)()
@@ -170,8 +173,8 @@ def test_device_resident_sub_batches_are_bit_identical(monkeypatch):
             runs.append((pose[k].cpu().numpy().copy(), [(r.status, r.iters, r.n_corner, r.n_surf, r.n_sel_last) for r in rr]))
         eng.close()
         assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1] == runs[1][1]
-        out[(split, fused)] = runs[0]
-    ref = out[("0", "0")]
+        out[(split, fused, plain)] = runs[0]
+    ref = out[("0", "0", "0")]
     for k, v in out.items():
         assert np.array_equal(ref[0], v[0]), k
         assert ref[1] == v[1], k
