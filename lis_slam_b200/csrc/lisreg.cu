@@ -902,7 +902,9 @@ static int feat_reserve(lisreg_ctx* ctx, int F, int cells, int nscan) {
 static int run_features(lisreg_ctx* ctx, FeatFrame* d_frames, int F, const lisreg_feat_params* prm, int max_n, double alg_bytes,
                         bool with_deskew = false, bool lean = false) {
   cudaStream_t st = ctx->cur->stream;
-  const bool seg_fused = lean && !ctx->feat_seg_unfused;
+  // (a single frame keeps the separate 4-us k_feat_curv_occl launch: inside the selection kernel the same work sits on the
+  // critical path of 64 lone warps)
+  const bool seg_fused = lean && !ctx->feat_seg_unfused && F >= 16;
   FeatParamsDev dp{prm->n_scan, prm->horizon, prm->downsample_rate, prm->min_range, prm->max_range, prm->edge_thr, prm->surf_thr, prm->layout, seg_fused ? 1 : 0};
   const int cells = prm->n_scan * prm->horizon;
   ProfScope ps(ctx, PROF_FEAT, alg_bytes, 7);

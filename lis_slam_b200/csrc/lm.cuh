@@ -174,9 +174,16 @@ LISREG_HD inline void lm_solve_tail(RegState& st, const LmParamsDev& prm, const 
     int q = 0;
     for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) { sc.AtA[r * 6 + c] = sc.AtA[c * 6 + r] = (float)sums[q]; q++; }
     for (int r = 0; r < 6; r++) sc.AtB[r] = (float)sums[21 + r];
-    for (int i = 0; i < 36; i++) sc.a[i] = sc.AtA[i];
-    for (int i = 0; i < 6; i++) sc.X[i] = sc.AtB[i];
-    if (!qr_solve<6>(sc.a, sc.X)) for (int i = 0; i < 6; i++) sc.X[i] = 0.f;
+    {   // the factorisation runs on register copies (shared-memory operands made it a chain of dependent LDS / STS)
+      float qa[36], qx[6];
+#pragma unroll
+      for (int i = 0; i < 36; i++) qa[i] = sc.AtA[i];
+#pragma unroll
+      for (int i = 0; i < 6; i++) qx[i] = sc.AtB[i];
+      const int ok = qr_solve<6>(qa, qx);
+#pragma unroll
+      for (int i = 0; i < 6; i++) sc.X[i] = ok ? qx[i] : 0.f;
+    }
     for (int i = 0; i < 36; i++) sc.matP[i] = 0.f;   // Q1: local all-zero matP on iterations >= 1
     if (iter == 0) {
       for (int i = 0; i < 36; i++) sc.a[i] = sc.AtA[i];

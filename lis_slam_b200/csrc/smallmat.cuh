@@ -174,36 +174,51 @@ LISREG_HD __forceinline__ void jacobi_eigen3(float a00, float a01, float a02, fl
   }
 }
 
-// Householder QR solve, square N x N (A destroyed, b -> x). Returns 0 if singular.
+// Householder QR solve, square N x N (A destroyed, b -> x). Returns 0 if singular.  Every loop has a compile-time trip
+// count and is unrolled: called on local arrays the whole factorisation stays in registers (lm_solve_tail).
 template <int N>
-LISREG_HD int qr_solve(float* A, float* b) {
+LISREG_HD __forceinline__ int qr_solve(float* A, float* b) {
   const float eps = FLT_EPSILON * 10;
   float vl[N], hF[N];
+  #pragma unroll
   for (int l = 0; l < N; l++) {
     int vlSize = N - l;
     float vlNorm = 0.f;
+    #pragma unroll
     for (int i = 0; i < vlSize; i++) { vl[i] = A[(l + i) * N + l]; vlNorm += vl[i] * vl[i]; }
     float tmpV = vl[0];
     vl[0] = vl[0] + (vl[0] >= 0.f ? 1.f : -1.f) * sqrtf(vlNorm);
     vlNorm = sqrtf(vlNorm + vl[0] * vl[0] - tmpV * tmpV);
+    #pragma unroll
     for (int i = 0; i < vlSize; i++) vl[i] /= vlNorm;
+    #pragma unroll
     for (int j = l; j < N; j++) {
       float v_lA = 0.f;
+      #pragma unroll
       for (int i = l; i < N; i++) v_lA += vl[i - l] * A[i * N + j];
+      #pragma unroll
       for (int i = l; i < N; i++) A[i * N + j] -= 2 * vl[i - l] * v_lA;
     }
     hF[l] = vl[0] * vl[0];
+    #pragma unroll
     for (int i = 1; i < vlSize; i++) A[(l + i) * N + l] = vl[i] / vl[0];
   }
+  #pragma unroll
   for (int l = 0; l < N; l++) {
+    #pragma unroll
     for (int j = 0; j < l; j++) vl[j] = 0.f;
     vl[l] = 1.f;
+    #pragma unroll
     for (int j = l + 1; j < N; j++) vl[j] = A[j * N + l];
     float v_lB = 0.f;
+    #pragma unroll
     for (int i = l; i < N; i++) v_lB += vl[i] * b[i];
+    #pragma unroll
     for (int i = l; i < N; i++) b[i] -= 2 * vl[i] * v_lB * hF[l];
   }
+  #pragma unroll
   for (int i = N - 1; i >= 0; i--) {
+    #pragma unroll
     for (int j = N - 1; j > i; j--) b[i] -= b[j] * A[i * N + j];
     if (fabsf(A[i * N + i]) < eps) return 0;
     b[i] /= A[i * N + i];
