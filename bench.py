@@ -234,12 +234,15 @@ def run_ours(args, rank, world, local_rank):
     eng = E.Engine(device=local_rank, stream=stream.cuda_stream)
     F = args.batch
     frame_stage = args.stage == "frame"
-    if frame_stage:
-        wl = workload.frame_batch(F=F, n_maps=args.maps, n_sweeps=args.sweeps, seed=rank)
-        arena_np, offs = workload.pack_frame_arena(wl)
-    else:
-        wl = workload.throughput_batch(B=F, n_maps=args.maps, n_scans=args.scans, seed=rank)
-        arena_np, offs = workload.pack_arena(wl)
+    wl = (workload.frame_batch(F=F, n_maps=args.maps, n_sweeps=args.sweeps, seed=args.seed) if frame_stage else
+          workload.throughput_batch(B=F, n_maps=args.maps, n_scans=args.scans, seed=args.seed))
+    # Weak scaling = the same work on every GPU: all ranks draw the SAME pool of F frames (synthetic batches of different seeds
+    # differ in cost by up to 7 %, which a max-over-ranks timing would book as a scaling loss) and rank r starts r * F / N
+    # frames into it, so the ranks hold different frames at every position of their batch.
+    if world > 1:
+        sh = (rank * F // world) % F
+        wl["regs"] = wl["regs"][sh:] + wl["regs"][:sh]
+    arena_np, offs = workload.pack_frame_arena(wl) if frame_stage else workload.pack_arena(wl)
     if args.distinct_maps:
         # one private 200k-point map PER FRAME (F x 3.2 MB + index: the HBM-streaming regime of SURVEY.md 8d): jittered copies
         # of the base maps - distinct buffers, same geometry - so the maps cannot stay L2-resident
@@ -299,7 +302,7 @@ def run_ours(args, rank, world, local_rank):
     def step_dev(p=None):
         k = step_no[0]; step_no[0] += 1
         pb = pose_bufs[k & 1] if world > 1 else pose_dev
-        if world > 1 and k >= 2:
+        if world > 1 and k >= 2 and not args.no_gather:
             eng.allgather_wait(1)                       # the gather of step k-2 has landed: buffers k & 1 are free; step k-1 stays in flight
         flush.zero_()                                   # L2 flush between timed iterations
         pb.copy_(guess_dev)
@@ -307,7 +310,7 @@ def run_ours(args, rank, world, local_rank):
             eng.frames_batch_dev(items_dev, F, pb.data_ptr(), p or prm, res_dev.data_ptr())
         else:
             eng.scan2map_batch_dev(items_dev, F, pb.data_ptr(), p or prm, res_dev.data_ptr())
-        if world > 1:
+        if world > 1 and not args.no_gather:
             eng.allgather_results(pb.data_ptr(), gathered[k & 1].data_ptr(), F * 24)
 
     pose_host = guess_np.copy()
@@ -946,6 +949,8 @@ def main():
     ap.add_argument("--cpu-check", type=int, default=-1, help="frames of the batch checked against the CPU path (-1 = all)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-early", action="store_true", help="skip the early-exit throughput probe")
+    ap.add_argument("--seed", type=int, default=0, help="seed of the synthetic frame pool (every rank uses the same pool, rotated by rank)")
+    ap.add_argument("--no-gather", action="store_true", help="diagnostic (N > 1): skip the per-step all-gather of the poses")
     ap.add_argument("--no-compact", action="store_true", help="skip the e2e run with the 14 B / point input layout")
     ap.add_argument("--distinct-maps", action="store_true", help="one private 200k map per frame (HBM-streaming regime)")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-frame latency probe")

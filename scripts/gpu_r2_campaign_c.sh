@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 N=${1:-2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531"
-timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 --no-latency > gpurun_out/r2_n${N}_frames.json 2> gpurun_out/r2_n${N}_frames.err; echo "frames rc=$?"; tail -c 400 gpurun_out/r2_n${N}_frames.err
+timeout 900 $TR bench.py --gpus $N --steps 30 --warmup 5 --no-latency > gpurun_out/r2_n${N}_frames.json 2> gpurun_out/r2_n${N}_frames.err; echo "frames rc=$?"; tail -c 400 gpurun_out/r2_n${N}_frames.err
 timeout 900 $TR bench.py --gpus $N --workload loop --steps 3 --warmup 1 > gpurun_out/r2_n${N}_loop.json 2> gpurun_out/r2_n${N}_loop.err; echo "loop rc=$?"; tail -c 400 gpurun_out/r2_n${N}_loop.err
 python - <<PY
 import json

@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""profiles/r02_summary.md from the committed round-2 artefacts (bench JSON lines, ncu launch list / tables, traffic JSON).
+usage: make_r02_summary.py > profiles/r02_summary.md"""
+import json, os
+P = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles")
+def L(name):
+    fn = os.path.join(P, name)
+    if not os.path.exists(fn): return None
+    t = [l for l in open(fn) if l.startswith("{")]
+    return json.loads(t[-1]) if t else None
+def f1(x, n=1): return ("%." + str(n) + "f") % x
+fr, b5, dm, ref = L("r02_bench_frames.json"), L("r02_bench_frames_b512_64sweeps.json"), L("r02_bench_frames_distinct_maps.json"), L("r02_bench_reference_arm.json")
+sh, sv, lp = L("r02_stream_hdl64.json"), L("r02_stream_vlp16.json"), L("r02_bench_loop.json")
+n2, n8, l2, l8 = L("r02_bench_frames_n2.json"), L("r02_bench_frames_n8.json"), L("r02_bench_loop_n2.json"), L("r02_bench_loop_n8.json")
+tr, trd = json.load(open(os.path.join(P, "lm_iter_traffic.json"))), json.load(open(os.path.join(P, "lm_iter_traffic_distinct_maps.json")))
+print("# r02 - measured numbers and ncu evidence (one B200 per rank, SM clock 1965 MHz, no throttle reasons in any run)\n")
+print("Every line below is a committed artefact: `profiles/r02_*.json` are the unedited bench lines, `r02_launches_*` / `r02_ncu_*` the ncu")
+print("exports.  Commands: `scripts/gpu_r2_campaign_a.sh` (bench lines), `_b.sh` (ncu, `LISREG_DEV_SPLIT=0`: whole-batch launches),")
+print("`_c.sh N` (torchrun, N GPUs).  Regenerate this file with `python scripts/make_r02_summary.py`.\n")
+print("## Bench lines\n")
+print("| line | value | e2e (host buffers) | ms / step | notes |\n|---|---|---|---|---|")
+def row(name, d, notes=""):
+    if not d: return
+    e = d.get("e2e") or {}
+    print("| %s | %s %s | %s | %s | %s |" % (name, f1(d["value"]), d["unit"], f1(e.get("value", 0)), f1(d.get("ms_per_step", 0), 3), notes))
+st = fr["roofline"]["stage_ms_per_step"]
+row("frames (default, 256 frames/step, 8 shared maps)", fr, "stages (whole batch, serial): features %s + voxel %s + 10 GN iterations %s ms; e2e 14 B/pt input %s; early exit %s frames/s (%.1f iterations); CPU 1 thread %s frames/s; all 256 frames within %.1e rad / %.1e m of the CPU path" % (
+    f1(st["features"], 2), f1(st["voxel_grid"], 2), f1(st["lm_iterations"], 2), f1(fr["e2e_compact_input"]["value"]), f1(fr["value_early_exit"]["value_per_gpu"]), fr["value_early_exit"]["mean_iters"], f1(fr["cpu_baseline"]["value"]),
+    fr["pose_err_vs_cpu"]["max_rot_rad"], fr["pose_err_vs_cpu"]["max_trans_m"]))
+if ref: row("`--impl reference` (CPU arm, %d threads)" % ref["cpu_baseline"]["cores"], ref, "per frame: features+voxel %s ms, kd-tree build %s ms, iterations %s ms" % tuple(f1(ref["cpu_baseline"]["ms_per_frame"][k]) for k in ("feat_voxel_ms", "tree_build_ms", "iters_ms")))
+row("frames `--batch 512 --sweeps 64` (config-exact)", b5, "roofline.frac %s" % f1(b5["roofline"]["frac"], 3))
+row("frames `--distinct-maps` (256 maps: HBM regime)", dm, "GN iterations %s ms; roofline.frac %s; ncu DRAM %s MB / iteration (shared maps: %s MB)" % (f1(dm["roofline"]["stage_ms_per_step"]["lm_iterations"], 2), f1(dm["roofline"]["frac"], 3), f1(trd["dram_bytes_per_iteration"] / 1e6), f1(tr["dram_bytes_per_iteration"] / 1e6)))
+for nm, d in (("stream_hdl64 (configs[1], 600 frames)", sh), ("stream_vlp16 (configs[4], 1000 frames)", sv)):
+    if d:
+        lat = d["latency_ms"]["e2e_host_call"]; pe = d["pose_err_vs_cpu"]
+        row(nm, d, "per-frame latency p50 %s / p90 %s / p99 %s ms; CPU flow %s frames/s; %d of %d frames checked vs the CPU flow: max %.1e rad / %.1e m, same iteration counts: %s" % (
+            f1(lat["p50"], 3), f1(lat["p90"], 3), f1(lat["p99"], 3), f1(d["cpu_baseline"]["value"]), pe["frames_checked"], pe["of"], pe["max_rot_rad"], pe["max_trans_m"], pe.get("same_iteration_counts")))
+if lp:
+    s = lp["stage_ms"]
+    row("loop (configs[3], 5000 descriptors)", lp, "score + top-k %s ms, ICP verify of %d candidates %s ms; k_epsc_score at %s of the measured integer-ALU peak; CPU 16 threads %s pairs/s" % (
+        f1(s["score_topk_incl_h2d"], 2), lp["icp"]["of"], f1(s["icp_verify_incl_h2d"]), f1(lp["roofline"]["frac"], 3), f1(lp["cpu_baseline"]["value"])))
+print("\n## Multi-GPU (torchrun, one rank per GPU; device-timed max over ranks)\n")
+print("| N | frames value | per-GPU vs N=1 | frames e2e | e2e 14 B/pt | loop pairs/s | all-gather |\n|---|---|---|---|---|---|---|")
+for n, a, b in ((1, fr, lp), (2, n2, l2), (8, n8, l8)):
+    if not a: continue
+    print("| %d | %s | %s | %s | %s | %s | %s |" % (n, f1(a["value"]), f1(a["value"] / n / fr["value"], 3), f1(a["e2e"]["value"]), f1((a.get("e2e_compact_input") or {}).get("value", 0)),
+          f1(b["value"]) if b else "-", "own block matches: %s" % (a.get("allgather") or {}).get("own_block_matches") if a.get("allgather") else "-"))
+print("\n(N = 2 / 8 rows are from the commit named in the file's `config`; the e2e columns are bound by the host's PCIe / memory fabric, not by the GPUs.)\n")
+for title, fn in (("Launch list of one whole-batch step (`ncu --metrics gpu__time_duration.sum`, cold-cache and serialised: compare SHARES)", "r02_launches_frame_batch256.md"),
+                  ("`ncu --set full` of the top kernels (first launches of a step)", "r02_ncu_full_table.md")):
+    fnp = os.path.join(P, fn)
+    if os.path.exists(fnp):
+        print("## %s\n" % title); print(open(fnp).read())
+print("## Gauss-Newton iteration group: DRAM traffic per iteration (ncu), shared maps\n")
+print("| kernel | DRAM MB / iteration | us / iteration |\n|---|---|---|")
+for k, v in tr["per_kernel_per_iteration"].items():
+    print("| %s | %s | %s |" % (k, f1(v["dram_bytes"] / 1e6), f1(v["us"])))
+print("| total | %s | %s |" % (f1(tr["dram_bytes_per_iteration"] / 1e6), f1(sum(v["us"] for v in tr["per_kernel_per_iteration"].values()))))
