@@ -45,7 +45,7 @@ for n, a, b in ((1, fr, lp), (2, n2, l2), (8, n8, l8)):
     if not a: continue
     print("| %d | %s | %s | %s | %s | %s | %s |" % (n, f1(a["value"]), f1(a["value"] / n / fr["value"], 3), f1(a["e2e"]["value"]), f1((a.get("e2e_compact_input") or {}).get("value", 0)),
           f1(b["value"]) if b else "-", "own block matches: %s" % (a.get("allgather") or {}).get("own_block_matches") if a.get("allgather") else "-"))
-print("\n(N = 2 / 8 rows are from the commit named in the file's `config`; the e2e columns are bound by the host's PCIe / memory fabric, not by the GPUs.)\n")
+print("\nEvery rank runs the same pool of 256 frames, rotated by rank (synthetic batches of different seeds differ in cost by up to 7 %: seed 0 4.95 ms, seed 1 5.28 ms on one GPU - a max-over-ranks timing would book that as a scaling loss).  The e2e columns are bound by the host's PCIe / memory fabric (one NUMA node feeding N x 52 GB/s), not by the GPUs; the loop line loses to the uneven number of ICP candidates per rank (each rank verifies the candidates of its own query rows).\n")
 for title, fn in (("Launch list of one whole-batch step (`ncu --metrics gpu__time_duration.sum`, cold-cache and serialised: compare SHARES)", "r02_launches_frame_batch256.md"),
                   ("`ncu --set full` of the top kernels (first launches of a step)", "r02_ncu_full_table.md")):
     fnp = os.path.join(P, fn)
@@ -56,3 +56,33 @@ print("| kernel | DRAM MB / iteration | us / iteration |\n|---|---|---|")
 for k, v in tr["per_kernel_per_iteration"].items():
     print("| %s | %s | %s |" % (k, f1(v["dram_bytes"] / 1e6), f1(v["us"])))
 print("| total | %s | %s |" % (f1(tr["dram_bytes_per_iteration"] / 1e6), f1(sum(v["us"] for v in tr["per_kernel_per_iteration"].values()))))
+
+print("""
+## What moved the headline in round 2 (frames `value`, 256 frames per step, one GPU)
+
+| change | ms / step | frames/s |
+|---|---|---|
+| round 1 | 6.83 | 37.8 k |
+| voxel grid: runs of equal consecutive keys collapsed before the sort | 6.54 | 39.1 k |
+| `lisreg_frames_batch_dev` as four concurrent sub-batches on private streams (serial step 6.0 ms) | 5.74 | 44.6 k |
+| voxel grid: `k_vox_block` (box, keys, runs, shared-memory radix sort, heads in one block per cloud; no box pass for range-gated points) | 5.38 | 47.6 k |
+| ... centroids inside the block kernel, run table in shared memory, contiguous runs read without the index list | 5.08 | 50.4 k |
+| smoothness + occlusion marks inside `k_feat_segments`, no initialisation of their arrays | 5.01 | 51.1 k |
+| 6x6 QR on register copies, block-cooperative staging of the tile partials | 4.95 | 51.7 k |
+
+Streaming (HDL-64, one sweep per call): p50 1.0 ms (round 1, host-resident window) -> 0.56 ms (window + map in HBM, per-frame CUDA
+graph, pre-sized buffers, warp-per-voxel centroid for the window map); VLP-16: 0.85 -> 0.40 ms.
+
+## Measured and dropped (kept out of the default path, reasons in DESIGN.md 4 / 8)
+
+* `k_feat_front` - projection + compaction with the range-image slice in shared memory (`LISREG_FEAT_FUSED=1`, bit-identical):
+  1063 us vs 877 us for the four kernels it replaces, 541 M vs ~300 M warp-instructions (every 8-ring group scans the ring
+  ids of the whole sweep), DRAM 2.05 vs 2.39 GB; slower in the streaming mode too (p50 0.61 vs 0.56 ms).
+* the 6x6 solve in the last block of `k_lm_resid`: +0.3 ms per step (its stack frame lands in the hot kernel).
+* shared-memory staging of the centroid kernel at block level (two variants: 2.8 / 2.5 ms voxel stage vs 1.7).
+* padding the last batch of a run to four loads in the in-block centroid: 1.54 vs 1.17 ms (duplicate loads are not free).
+* 8 instead of 4 concurrent sub-batches: 5.42 vs 5.28 ms; 4-CTA instead of 2-CTA clusters in `k_epsc_score`: 0.886 vs 0.929
+  of the ALU peak (132 vs 148 usable SMs).
+* `k_vox_block` for a single full-size frame (2 clouds on 2 SMs): HDL-64 p50 0.63 vs 0.57 ms - a few large clouds keep the
+  multi-block kernels (`VOX_BLOCK_MAX_N_FEW`).
+""")
