@@ -812,7 +812,8 @@ def run_loop(args, rank, world, local_rank):
     targets = [sc.sample_map(n_edge=0, n_surf=200000, seed=3001 + 17 * k)["surf"] for k in range(n_tgt)]
     tids = [eng.target_create(t) for t in targets]
     rng = np.random.default_rng(77 + rank)
-    base_src = [t[rng.choice(len(t), 50000, replace=False)].copy() for t in targets]
+    # a key-frame cloud is stored in acquisition order (ring by ring), never shuffled: the subset keeps the order of the cloud it is drawn from
+    base_src = [t[np.sort(rng.choice(len(t), 50000, replace=False))].copy() for t in targets]
 
     def make_src(k, r):
         s = base_src[k].copy()
@@ -844,7 +845,8 @@ def run_loop(args, rank, world, local_rank):
         cand = np.argwhere(idx >= 0)[: args.loop_max_pairs]                       # (local row, slot)
         if "pairs" not in cache:      # the key-frame clouds of the candidates are inputs: generated once, outside the timed steps
             r2 = np.random.default_rng(1234 + rank)
-            cache["pairs"] = [(make_src(int(idx[r, k]) % n_tgt, r2), tids[int(idx[r, k]) % n_tgt]) for r, k in cand]
+            # (page-locked, like the sweep arena of the frames workload: the engine copies them to the device without a staging pass)
+            cache["pairs"] = [(torch.from_numpy(make_src(int(idx[r, k]) % n_tgt, r2)).pin_memory().numpy(), tids[int(idx[r, k]) % n_tgt]) for r, k in cand]
             cache["cand"] = cand.copy()
         assert np.array_equal(cand, cache["cand"])
         pairs = cache["pairs"]

@@ -21,6 +21,7 @@ namespace lisreg {
 struct IcpPair {
   const float4* src; int ns;        // source (already pre-transformed by the initial guess)
   float4* cur;                      // work copy (ns)
+  int* nn;                          // nearest target point of every source point at the previous iteration (-1: none yet)
   int tgt_slot;                     // map slot whose SURF cloud is the target
   int pad;
 };
@@ -57,7 +58,7 @@ __global__ void k_icp_init(const IcpPair* __restrict__ pairs, IcpState* __restri
 // copies the source into the work buffer.  grid = (blocks, P)
 __global__ void k_icp_copy(const IcpPair* __restrict__ pairs) {
   const IcpPair pr = pairs[blockIdx.y];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pr.ns; i += gridDim.x * blockDim.x) pr.cur[i] = __ldg(&pr.src[i]);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pr.ns; i += gridDim.x * blockDim.x) { pr.cur[i] = __ldg(&pr.src[i]); pr.nn[i] = -1; }
 }
 
 template <bool FITNESS>
@@ -83,9 +84,22 @@ k_icp_corr(const IcpPair* __restrict__ pairs, const IcpState* __restrict__ st, c
     float x = c.x, y = c.y, z = c.z;
     if (apply) { icp_xform(sT, c, x, y, z); if (!FITNESS) pr.cur[i] = make_float4(x, y, z, c.w); }
     knn_key best[1];
-    knn_grid<1>(g, x, y, z, FITNESS ? 3.0e38f : prm.max_d2 * 1.0000002f, best);   // (gate is exclusive; PCL keeps d2 <= max2)
+    float gate = FITNESS ? 3.0e38f : prm.max_d2 * 1.0000002f;                    // (gate is exclusive; PCL keeps d2 <= max2)
+    // The neighbour of the previous iteration bounds the search: the nearest point is at most as far as that one is NOW, so
+    // the exact search only has to look inside that radius (a point that moved a few centimetres no longer walks the
+    // shells out to the 10 m correspondence distance in sparse regions).  Same result, by construction.
+    const int prev = pr.nn[i];
+    if (prev >= 0) {
+      const float4 m = __ldg(&g.pts[prev]);
+      const float ddx = x - m.x, ddy = y - m.y, ddz = z - m.z;
+      float dp = ddx * ddx; dp = dp + ddy * ddy; dp = dp + ddz * ddz;        // the search's own expression (knn_scan_range)
+      const float gp = dp * 1.0000002f + 1e-30f;
+      if (gp < gate) gate = gp;
+    }
+    knn_grid<1>(g, x, y, z, gate, best);
     const int pos = knn_key_pos(best[0]);
     const float d2 = knn_key_d(best[0]);
+    if (!FITNESS) pr.nn[i] = pos;
     if (pos < 0 || (!FITNESS && d2 > prm.max_d2)) continue;
     if (FITNESS) { acc[15] += (double)d2; acc[16] += 1.0; continue; }
     const float4 q = __ldg(&g.pts[pos]);

@@ -1729,11 +1729,12 @@ static int icp_run_dev(lisreg_ctx* ctx, int P, const std::vector<size_t>& off, c
   for (int i = 0; i < P; i++) max_ns = std::max(max_ns, ns[i]);
   const int nblk = std::max(1, std::min(64, (max_ns + ICP_THREADS - 1) / ICP_THREADS));
   const size_t o_pairs = 0, o_states = al(sizeof(IcpPair) * (size_t)P), o_part = o_states + al(sizeof(IcpState) * (size_t)P),
-               o_res = o_part + al(sizeof(double) * ICP_NSUM * (size_t)P * nblk), o_cur = o_res + al(sizeof(lisreg_icp_result) * (size_t)P);
-  CK(ctx->d_icp.reserve(o_cur + src_bytes));
+               o_res = o_part + al(sizeof(double) * ICP_NSUM * (size_t)P * nblk), o_cur = o_res + al(sizeof(lisreg_icp_result) * (size_t)P),
+               o_nn = o_cur + al(src_bytes);
+  CK(ctx->d_icp.reserve(o_nn + src_bytes / 4 + 256));
   char* dsrc = (char*)ctx->d_stage.p; char* d = (char*)ctx->d_icp.p;
   std::vector<IcpPair> hp((size_t)P);
-  for (int i = 0; i < P; i++) { hp[i].src = (const float4*)(dsrc + off[i]); hp[i].ns = ns[i]; hp[i].cur = (float4*)(d + o_cur + off[i]); hp[i].tgt_slot = tgt[i]; hp[i].pad = 0; }
+  for (int i = 0; i < P; i++) { hp[i].src = (const float4*)(dsrc + off[i]); hp[i].ns = ns[i]; hp[i].cur = (float4*)(d + o_cur + off[i]); hp[i].nn = (int*)(d + o_nn + off[i] / 4); hp[i].tgt_slot = tgt[i]; hp[i].pad = 0; }
   CK(cudaMemcpyAsync(d + o_pairs, hp.data(), sizeof(IcpPair) * (size_t)P, cudaMemcpyHostToDevice, st));   // pageable: consumed on return
   IcpPair* dp = (IcpPair*)(d + o_pairs); IcpState* ds = (IcpState*)(d + o_states); double* part = (double*)(d + o_part);
   lisreg_icp_result* dres = (lisreg_icp_result*)(d + o_res);
@@ -1767,11 +1768,25 @@ int32_t lisreg_icp_verify_batch(lisreg_ctx* ctx, int32_t P, const lisreg_icp_pai
     off[i] = src_bytes; ns[i] = pr.ns; tgt[i] = pr.target_id;
     src_bytes += al(16 * (size_t)pr.ns);
   }
-  CK(ctx->h_stage.reserve(src_bytes + 256));
   CK(ctx->d_stage.reserve(src_bytes + 256));
+  // sources in page-locked memory go to the device straight from the caller's buffer; pageable ones through the pinned
+  // staging block (one host copy more)
+  std::vector<char> pinned((size_t)P, 0);
+  size_t staged = 0;
+  for (int i = 0; i < P; i++) {
+    if (!pairs[i].ns) continue;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, pairs[i].src) == cudaSuccess && at.type == cudaMemoryTypeHost) pinned[i] = 1;
+    else { cudaGetLastError(); staged += 16 * (size_t)pairs[i].ns; }
+  }
+  if (staged) CK(ctx->h_stage.reserve(src_bytes + 256));
   char* h = (char*)ctx->h_stage.p;
-  for (int i = 0; i < P; i++) if (pairs[i].ns) memcpy(h + off[i], pairs[i].src, 16 * (size_t)pairs[i].ns);
-  if (src_bytes) CK(cudaMemcpyAsync(ctx->d_stage.p, h, src_bytes, cudaMemcpyHostToDevice, st));
+  for (int i = 0; i < P; i++) {
+    if (!pairs[i].ns) continue;
+    const void* from = pairs[i].src;
+    if (!pinned[i]) { memcpy(h + off[i], pairs[i].src, 16 * (size_t)pairs[i].ns); from = h + off[i]; }
+    CK(cudaMemcpyAsync((char*)ctx->d_stage.p + off[i], from, 16 * (size_t)pairs[i].ns, cudaMemcpyHostToDevice, st));
+  }
   return icp_run_dev(ctx, P, off, ns, tgt, src_bytes, prm, out);
 }
 
