@@ -47,7 +47,9 @@ for n, a, b in ((1, fr, lp), (2, n2, l2), (8, n8, l8)):
           f1(b["value"]) if b else "-", "own block matches: %s" % (a.get("allgather") or {}).get("own_block_matches") if a.get("allgather") else "-"))
 print("\nEvery rank runs the same pool of 256 frames, rotated by rank (synthetic batches of different seeds differ in cost by up to 7 %: seed 0 4.95 ms, seed 1 5.28 ms on one GPU - a max-over-ranks timing would book that as a scaling loss).  The e2e columns are bound by the host's PCIe / memory fabric (one NUMA node feeding N x 52 GB/s), not by the GPUs; the loop line loses to the uneven number of ICP candidates per rank (each rank verifies the candidates of its own query rows).\n")
 for title, fn in (("Launch list of one whole-batch step (`ncu --metrics gpu__time_duration.sum`, cold-cache and serialised: compare SHARES)", "r02_launches_frame_batch256.md"),
-                  ("`ncu --set full` of the top kernels (first launches of a step)", "r02_ncu_full_table.md")):
+                  ("`ncu --set full` of the top kernels (first launches of a step)", "r02_ncu_full_table.md"),
+                  ("Streaming HDL-64: launch list of a typical frame of the first 24 (eager launches under ncu; most of these frames add a key frame, so the map rebuild is included)", "r02_launches_stream_hdl64_median.md"),
+                  ("Streaming VLP-16: launch list of a typical frame", "r02_launches_stream_vlp16_median.md")):
     fnp = os.path.join(P, fn)
     if os.path.exists(fnp):
         print("## %s\n" % title); print(open(fnp).read())
@@ -69,6 +71,10 @@ print("""
 | ... centroids inside the block kernel, run table in shared memory, contiguous runs read without the index list | 5.08 | 50.4 k |
 | smoothness + occlusion marks inside `k_feat_segments`, no initialisation of their arrays | 5.01 | 51.1 k |
 | 6x6 QR on register copies, block-cooperative staging of the tile partials | 4.95 | 51.7 k |
+
+Loop closure (configs[3]): 58.3 M -> 127 M pairs/s: ICP search radius bounded by the previous neighbour, page-locked sources uploaded
+without a staging pass, and the synthetic key-frame clouds kept in acquisition order (a shuffled source cloud makes every
+warp's queries spatially unrelated: 203 ms of ICP instead of 127 ms with the same kernels).
 
 Streaming (HDL-64, one sweep per call): p50 1.0 ms (round 1, host-resident window) -> 0.56 ms (window + map in HBM, per-frame CUDA
 graph, pre-sized buffers, warp-per-voxel centroid for the window map); VLP-16: 0.85 -> 0.40 ms.
