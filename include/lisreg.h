@@ -275,7 +275,10 @@ typedef struct lisreg_frame_item {
 } lisreg_frame_item;
 
 void lisreg_frame_params_default(lisreg_frame_params* p);
-/* everything resident in HBM; asynchronous on the context stream */
+/* everything resident in HBM; asynchronous with respect to the host and ordered on the context stream (work queued on
+ * that stream before the call is complete before the batch starts, work queued after it starts after the batch).  A batch of
+ * >= 64 frames runs internally as up to four sub-batches on private streams (LISREG_DEV_SPLIT, 0 = off) so that kernels of
+ * different pipeline stages overlap; the results do not depend on the split. */
 int32_t lisreg_frames_batch_dev(lisreg_ctx* ctx, int32_t F, const lisreg_frame_item* items,
                                 float* d_pose6xF, const lisreg_frame_params* prm, lisreg_lm_result* d_resxF);
 /* raw sweeps packed in one (pinned) host arena; items hold byte offsets (pts 16-byte aligned, ring 2-byte).  Blocking.

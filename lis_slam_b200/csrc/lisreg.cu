@@ -154,6 +154,7 @@ struct lisreg_ctx {
   cudaStream_t comm_stream = nullptr; cudaEvent_t comm_fence = nullptr, comm_done[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t comm_seq = 0;                    // gathers issued so far; gather k signals comm_done[k % 4]
   int knn_coop_max = 16384;   // scan lists shorter than this are searched warp-per-query (LISREG_KNN_COOP_MAX; 0 = never)
+  bool attr_front_set = false, attr_vox_set = false;   // opt-in to > 48 KB of dynamic shared memory done on this context's device
   int feat_fused = 0;     // LISREG_FEAT_FUSED=1: projection + compaction in one kernel with the range-image slice in shared memory (k_feat_front);
                           // measured slower than the global range image on firing-order sweeps (8x redundant ring-id scans), so off by default
   int feat_seg_unfused = 0; // LISREG_FEAT_SEG_UNFUSED=1: the batched pipelines run k_feat_curv_occl + the plain selection kernel too (parity check)
@@ -919,8 +920,7 @@ static int run_features(lisreg_ctx* ctx, FeatFrame* d_frames, int F, const lisre
     while (R > 1 && (long long)F * ((prm->n_scan + R - 1) / R) < 2 * 148) R--;
     const int G = (prm->n_scan + R - 1) / R;
     const size_t smem = sizeof(int) * ((size_t)R * (size_t)(prm->horizon + nchunk) + 1);
-    static bool attr_set = false;
-    if (!attr_set) { CK(cudaFuncSetAttribute(k_feat_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * (FEAT_FRONT_SMEM_INTS + 1)))); attr_set = true; }
+    if (!ctx->attr_front_set) { CK(cudaFuncSetAttribute(k_feat_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * (FEAT_FRONT_SMEM_INTS + 1)))); ctx->attr_front_set = true; }
     k_feat_front<<<F * G, FEAT_FRONT_THREADS, smem, st>>>(d_frames, dp, R, G, F, (int*)ctx->cur->d_feat_ctl.p); LAUNCH_CK();
   } else {
     k_feat_clear<<<dim3((cells + 255) / 256, F), 256, 0, st>>>(d_frames, dp); LAUNCH_CK();
@@ -1057,11 +1057,10 @@ static int run_voxel(lisreg_ctx* ctx, VoxSeg* d_segs, int nseg, int max_n, doubl
   // than on two SMs (measured: 0.57 vs 0.63 ms per frame), smaller ones (VLP-16) the other way round
   if (max_n <= (big ? VOX_BLOCK_MAX_N_FEW : VOX_BLOCK_MAX_N) && !ctx->vox_unfused) {
     // clouds of frame size: bounding box -> keys -> runs -> sort -> voxel heads by ONE block per cloud, the sort in shared memory
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->attr_vox_set) {                       // per context: the attribute belongs to the (function, device) pair
       CK(cudaFuncSetAttribute(k_vox_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VB_SMEM));
       CK(cudaFuncSetAttribute(k_vox_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VB_SMEM));
-      attr_set = true;
+      ctx->attr_vox_set = true;
     }
     if (big) {
       k_vox_block<false><<<nseg, VB_THREADS, VB_SMEM, st>>>(d_segs); LAUNCH_CK();
