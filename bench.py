@@ -838,17 +838,35 @@ def run_loop(args, rank, world, local_rank):
 
     cache = {}
 
+    send_c = torch.zeros(cap_rows * topk, 4, dtype=torch.float32, device=dev)
+    recv_c = torch.zeros(world * cap_rows * topk, 4, dtype=torch.float32, device=dev)
+
     def step(timing=None):
         t0 = time.perf_counter()
         idx, score, shift = eng.epsc_score_rows(desc, rank, world, topk)          # this rank's cyclic rows (H2D of the 8 MB inside)
         t1 = time.perf_counter()
-        cand = np.argwhere(idx >= 0)[: args.loop_max_pairs]                       # (local row, slot)
+        # candidate table of this rank in (row, slot) order: [q, j, score, shift], j = -1 for an empty slot
+        tab = np.full((cap_rows * topk, 4), -1.0, np.float32)
+        tab[: n_rows * topk, 0] = np.repeat(rows, topk); tab[: n_rows * topk, 1] = idx.reshape(-1)
+        tab[: n_rows * topk, 2] = score.reshape(-1); tab[: n_rows * topk, 3] = shift.reshape(-1)
+        if world > 1:
+            # exchange 1 (64 KB per rank): every rank learns ALL candidates and verifies every world-th one of the canonical list -
+            # the candidates of a rank's own rows are uneven (216 vs 263 at N = 2), the ICP stage is 85 % of the step
+            send_c.copy_(torch.from_numpy(tab))
+            eng.allgather_results(send_c.data_ptr(), recv_c.data_ptr(), send_c.numel() * 4)
+            eng.allgather_wait()
+            glob = shard.canonical_candidates(recv_c.cpu().numpy())
+            mine = glob[shard.deal_round_robin(len(glob), rank, world)]
+        else:
+            mine = shard.canonical_candidates(tab)
+        mine = mine[: args.loop_max_pairs]
+        t1b = time.perf_counter()
         if "pairs" not in cache:      # the key-frame clouds of the candidates are inputs: generated once, outside the timed steps
             r2 = np.random.default_rng(1234 + rank)
             # (page-locked, like the sweep arena of the frames workload: the engine copies them to the device without a staging pass)
-            cache["pairs"] = [(torch.from_numpy(make_src(int(idx[r, k]) % n_tgt, r2)).pin_memory().numpy(), tids[int(idx[r, k]) % n_tgt]) for r, k in cand]
-            cache["cand"] = cand.copy()
-        assert np.array_equal(cand, cache["cand"])
+            cache["pairs"] = [(torch.from_numpy(make_src(int(c[1]) % n_tgt, r2)).pin_memory().numpy(), tids[int(c[1]) % n_tgt]) for c in mine]
+            cache["cand"] = mine[:, :2].copy()
+        assert np.array_equal(mine[:, :2], cache["cand"])
         pairs = cache["pairs"]
         t2 = time.perf_counter()
         out = []
@@ -856,18 +874,18 @@ def run_loop(args, rank, world, local_rank):
             out += eng.icp_verify_batch(pairs[c0:c0 + 128])
         t3 = time.perf_counter()
         rec = np.zeros((cap_rows * topk, rec_w), np.float32)
-        if len(cand):
-            rr = cand[:, 0] * topk + cand[:, 1]
-            rec[rr, 0] = rows[cand[:, 0]]; rec[rr, 1] = idx[cand[:, 0], cand[:, 1]]; rec[rr, 2] = score[cand[:, 0], cand[:, 1]]; rec[rr, 3] = shift[cand[:, 0], cand[:, 1]]
-            rec[rr, 4:16] = np.array([np.frombuffer(bytes(o.T), np.float32)[:12] for o in out], np.float32)
-            rec[rr, 16] = [o.fitness for o in out]; rec[rr, 17] = [o.converged for o in out]; rec[rr, 18] = [o.iters for o in out]
+        rec[:, 1] = -1.0
+        if len(mine):
+            rec[: len(mine), 0:4] = mine
+            rec[: len(mine), 4:16] = np.array([np.frombuffer(bytes(o.T), np.float32)[:12] for o in out], np.float32)
+            rec[: len(mine), 16] = [o.fitness for o in out]; rec[: len(mine), 17] = [o.converged for o in out]; rec[: len(mine), 18] = [o.iters for o in out]
         send.copy_(torch.from_numpy(rec))
-        eng.allgather_results(send.data_ptr(), recv.data_ptr(), send.numel() * 4)  # the single exchange step
+        eng.allgather_results(send.data_ptr(), recv.data_ptr(), send.numel() * 4)  # exchange 2: the verified candidate records
         eng.allgather_wait()
         torch.cuda.synchronize(dev)
         t4 = time.perf_counter()
         if timing is not None:
-            timing.append((t1 - t0, t3 - t2, t4 - t3, t4 - t0 - (t2 - t1), len(pairs), int((idx >= 0).sum()), out))
+            timing.append((t1 - t0, t3 - t2, (t4 - t3) + (t1b - t1), t4 - t0 - (t2 - t1b), len(pairs), int((idx >= 0).sum()), out))
         return idx, score, shift
 
     for _ in range(max(1, min(args.warmup, 2))):
@@ -913,12 +931,13 @@ def run_loop(args, rank, world, local_rank):
         "unit": "descriptor pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1e3 * t_tot,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "loop (BASELINE configs[3]): %d FEPSC descriptors, all %d pairs x 20 shifts scored, top-%d per query with score > 0.75, every "
-                               "candidate ICP-verified (50k-point key frame vs 200k-point submap, reference ICP parameters), query rows dealt "
-                               "cyclically over the ranks, ONE NCCL all-gather of the candidate records" % (N, pairs_total, topk),
+                               "candidate ICP-verified (50k-point key frame vs 200k-point submap, reference ICP parameters; sources page-locked, in acquisition "
+                               "order), query rows dealt cyclically over the ranks, N > 1: all-gather of the candidate table, every rank verifies every "
+                               "N-th candidate, all-gather of the verified records" % (N, pairs_total, topk),
                    "candidates": n_cand, "icp_pairs": n_pairs_icp, "target_pool": n_tgt,
                    "l2": "descriptors (%.1f MB) are uploaded every step; ICP sources are uploaded every step (%.0f MB)" % (N * 1600 / 1e6, n_pairs_icp / world * 0.8)},
         "clocks": sampler.summary(),
-        "stage_ms": {"score_topk_incl_h2d": 1e3 * t_score, "icp_verify_incl_h2d": 1e3 * t_icp, "record_pack_and_allgather": 1e3 * float(np.mean([t[2] for t in timing])),
+        "stage_ms": {"score_topk_incl_h2d": 1e3 * t_score, "icp_verify_incl_h2d": 1e3 * t_icp, "candidate_exchange_record_pack_and_allgather": 1e3 * float(np.mean([t[2] for t in timing])),
                      "total": 1e3 * t_tot},
         "icp": {"pairs_per_s": n_pairs_icp / t_icp if t_icp > 0 else None, "mean_iters": float(np.mean([o.iters for o in icp_out])) if icp_out else None,
                 "converged": int(sum(o.converged for o in icp_out)), "of": len(icp_out)},

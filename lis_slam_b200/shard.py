@@ -17,6 +17,22 @@ def cyclic_rows(n_rows, rank, world):
     return np.arange(rank, n_rows, world, dtype=np.int64)
 
 
+def deal_round_robin(n_items, rank, world):
+    """Items (loop-closure candidates in canonical order, known to every rank after the candidate exchange) verified by
+    `rank`: every world-th one, so that the ICP work differs by at most one pair between ranks whatever rows produced them."""
+    return np.arange(rank, n_items, world, dtype=np.int64)
+
+
+def canonical_candidates(table):
+    """table: (n, 4) float32 rows [query q, history j, score, shift] gathered from all ranks, j < 0 = empty slot, each rank's
+    block in (row, slot) order.  Returns the valid rows ordered by (q, slot) - the same list on every rank."""
+    t = np.asarray(table)
+    pos = np.arange(len(t))
+    keep = t[:, 1] >= 0
+    t, pos = t[keep], pos[keep]
+    return t[np.lexsort((pos, t[:, 0]))]
+
+
 def gather_results(local, n_units, world, dist=None, device=None):
     """All-gathers per-rank result blocks (equal record width; ragged shard sizes are padded to the largest shard)
     into the global array ordered by unit id.  `local`: (n_local, width) float32 torch tensor."""

@@ -45,7 +45,7 @@ for n, a, b in ((1, fr, lp), (2, n2, l2), (8, n8, l8)):
     if not a: continue
     print("| %d | %s | %s | %s | %s | %s | %s |" % (n, f1(a["value"]), f1(a["value"] / n / fr["value"], 3), f1(a["e2e"]["value"]), f1((a.get("e2e_compact_input") or {}).get("value", 0)),
           f1(b["value"]) if b else "-", "own block matches: %s" % (a.get("allgather") or {}).get("own_block_matches") if a.get("allgather") else "-"))
-print("\nEvery rank runs the same pool of 256 frames, rotated by rank (synthetic batches of different seeds differ in cost by up to 7 %: seed 0 4.95 ms, seed 1 5.28 ms on one GPU - a max-over-ranks timing would book that as a scaling loss).  The e2e columns are bound by the host's PCIe / memory fabric (one NUMA node feeding N x 52 GB/s), not by the GPUs; the loop line loses to the uneven number of ICP candidates per rank (each rank verifies the candidates of its own query rows).\n")
+print("\nEvery rank runs the same pool of 256 frames, rotated by rank (synthetic batches of different seeds differ in cost by up to 7 %: seed 0 4.95 ms, seed 1 5.28 ms on one GPU - a max-over-ranks timing would book that as a scaling loss).  The e2e columns are bound by the host's PCIe / memory fabric (one NUMA node feeding N x 52 GB/s), not by the GPUs; the loop line at N = 2 deals the gathered candidates round-robin (0.99 of linear); the N = 8 loop number predates that change (each rank verified the candidates of its own rows: 0.74).\n")
 for title, fn in (("Launch list of one whole-batch step (`ncu --metrics gpu__time_duration.sum`, cold-cache and serialised: compare SHARES)", "r02_launches_frame_batch256.md"),
                   ("`ncu --set full` of the top kernels (first launches of a step)", "r02_ncu_full_table.md"),
                   ("Streaming HDL-64: launch list of a typical frame of the first 24 (eager launches under ncu; most of these frames add a key frame, so the map rebuild is included)", "r02_launches_stream_hdl64_median.md"),

@@ -58,3 +58,29 @@ def test_shard_covers_all_units():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             rows = np.concatenate([shard.cyclic_rows(n, r, w) for r in range(w)])
             assert sorted(rows.tolist()) == list(range(n))
+
+
+def test_candidate_deal_is_balanced_and_identical_on_every_rank():
+    """Loop closure at N > 1: every rank turns the gathered candidate table into the same canonical list (by query row, then
+    slot) and verifies every world-th entry: the shares cover the list exactly once and differ by at most one pair, however
+    unevenly the candidates fell on the ranks' own rows."""
+    from lis_slam_b200 import shard
+    rng = np.random.default_rng(4)
+    world, N, topk = 3, 64, 5
+    blocks = []
+    for r in range(world):
+        rows = shard.cyclic_rows(N, r, world)
+        cap = (N + world - 1) // world
+        t = np.full((cap * topk, 4), -1.0, np.float32)
+        idx = rng.integers(-1, 12, (len(rows), topk)) * (rng.random((len(rows), topk)) < (0.2 + 0.3 * r))   # rank 2 has many more
+        idx[idx == 0] = -1
+        t[: len(rows) * topk, 0] = np.repeat(rows, topk); t[: len(rows) * topk, 1] = idx.reshape(-1)
+        t[: len(rows) * topk, 2] = rng.random(len(rows) * topk)
+        blocks.append(t)
+    table = np.concatenate(blocks)
+    g = shard.canonical_candidates(table)
+    assert len(g) == int((table[:, 1] >= 0).sum()) and np.all(np.diff(g[:, 0]) >= 0)
+    shares = [g[shard.deal_round_robin(len(g), r, world)] for r in range(world)]
+    assert sum(len(s) for s in shares) == len(g) and max(map(len, shares)) - min(map(len, shares)) <= 1
+    merged = np.concatenate(shares)
+    assert np.array_equal(merged[np.lexsort((merged[:, 2], merged[:, 0]))], g[np.lexsort((g[:, 2], g[:, 0]))])
