@@ -130,3 +130,33 @@ def test_descriptor_distance_cpp_equals_python():
         sc, sh, sad = orc.epsc_distance(d1, d2)
         sp, shp = pyref.calculate_distance(d1, d2)
         assert sc == sp and (shp is None or shp == sh)
+
+
+def test_voxel_order_does_not_depend_on_the_enclosing_box():
+    """The claim behind `VoxSeg.bound` (k_vox_block skips its bounding-box pass for range-gated sweep points): PCL's voxel index
+    idx = (i - min_i) + (j - min_j) * dx + (k - min_k) * dx * dy is lexicographic in (k, j, i) for ANY box that contains the
+    cloud, so which points share a voxel and the order of the voxels - all that reaches the output - are the same for the
+    tight box and for a loose one.  Checked with numpy on clouds with many occupied voxels and with the oracle's own output."""
+    rng = np.random.default_rng(12)
+    for leaf, bound in ((0.4, 81.0), (0.2, 81.0), (0.4, 200.0)):      # (a bound whose index would overflow int32 makes the kernel fall back to the real box)
+        p = np.zeros((20000, 4), np.float32)
+        p[:, :3] = rng.uniform(-60, 60, (20000, 3)) * np.array([1, 1, 0.1])
+        inv = np.float32(1.0) / np.float32(leaf)
+        ijk = np.floor(p[:, :3] * inv).astype(np.int64)
+
+        def keys(lo, hi):
+            mn = np.floor(np.asarray(lo, np.float32) * inv).astype(np.int64); mx = np.floor(np.asarray(hi, np.float32) * inv).astype(np.int64)
+            div = mx - mn + 1
+            assert div[0] * div[1] * div[2] <= 2**31 - 1
+            return (ijk[:, 0] - mn[0]) + (ijk[:, 1] - mn[1]) * div[0] + (ijk[:, 2] - mn[2]) * div[0] * div[1]
+        tight = keys(p[:, :3].min(0), p[:, :3].max(0))
+        loose = keys([-bound] * 3, [bound] * 3)
+        o_t, o_l = np.argsort(tight, kind="stable"), np.argsort(loose, kind="stable")
+        assert np.array_equal(o_t, o_l)                                           # same voxel order, same order inside a voxel
+        assert np.array_equal(np.diff(tight[o_t]) != 0, np.diff(loose[o_l]) != 0)  # same voxel boundaries
+        # and the oracle (tight box, as PCL) produces one centroid per group of that order
+        out = orc.voxel_grid(p, leaf)
+        starts = np.concatenate([[0], np.nonzero(np.diff(loose[o_l]) != 0)[0] + 1])
+        assert len(out) == len(starts)
+        first = p[o_l[starts]]
+        assert np.all(np.floor(out[:, :3] * inv) == np.floor(first[:, :3] * inv))  # centroid lies in the voxel of its first point
