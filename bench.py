@@ -558,7 +558,8 @@ def run_ours(args, rank, world, local_rank):
                    "mean_raw_points": n_raw / F if frame_stage else None, "mean_query_points": n_query / F,
                    "map_points": 200000, "lm_iters": LM_ITERS,
                    "l2": "256 MB flush write between timed steps; per-step inputs %.0f MB" % (arena_np.nbytes / 1e6),
-                   "engine_sub_batches": int(os.environ.get("LISREG_DEV_SPLIT", "4"))},
+                   "engine_sub_batches": int(os.environ.get("LISREG_DEV_SPLIT", "4")),
+                   "per_rank_frames": "every rank holds the same pool of frames, rotated by rank * F / N (identical work per GPU)" if world > 1 else "one rank"},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(arena_np.nbytes + F * 24),
                 "d2h_bytes_per_step": int(F * C.sizeof(E.LmResult)), "ms_per_step": ms_e2e / args.steps,
