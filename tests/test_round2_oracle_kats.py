@@ -83,3 +83,34 @@ def test_local_map_insert_moves_clouds_and_extract_crops_to_the_box():
     assert len(corner) == cnt[1] and len(surf) == cnt[0] + cnt[2] + cnt[3]                # pole -> corner map; ground + building + dynamic -> surface map
     assert sum(cnt) < 15000                                                                # the crop and the voxel filter removed points
     sm.close()
+
+
+def test_loop_verify_recovers_a_known_key_frame_pose():
+    """detectLoopClosureForSubMap (subMapOptmizationNode.cpp:2739-2916): the key-frame cloud is the submap's own geometry seen
+    from a KNOWN pose T_true; the verifier starts from a pose that is 25 cm / 0.6 deg off (pose-based initial alignment
+    submap^-1 * key, :2807-2809), ICP pulls it back, and with an identity relative pose the returned tCorrect - hence the
+    loop constraint (:2876-2896) - is T_true: x, y, z and roll, pitch, yaw come back within a millimetre / 1e-4 rad."""
+    from lis_slam_b200 import synth
+    sc = synth.Scene(seed=1001)
+    m = sc.sample_map(n_edge=0, n_surf=60000, seed=3001)["surf"]
+    classes = [m[0::4], m[1::4], m[2::4], m[3::4], np.zeros((0, 4), np.float32)]
+    sm = orc.Submap()
+    sm.insert(classes, np.zeros(6, np.float32))                                       # submap frame = map frame
+    true6 = np.array([0.01, -0.02, 0.3, 4.0, -1.5, 0.2], np.float32)                  # roll pitch yaw x y z
+    R = Rotation.from_euler("ZYX", [true6[2], true6[1], true6[0]])
+    sub = m[::5]
+    key = sub.copy()
+    key[:, :3] = R.inv().apply(sub[:, :3].astype(np.float64) - true6[3:6].astype(np.float64)).astype(np.float32)   # T_true * key = sub
+    wrong6 = true6 + np.array([0.0, 0.0, 0.01, 0.2, -0.15, 0.0], np.float32)
+    cand = dict(submap=sm, use_epsc=False, prekey_pose6=np.zeros(6, np.float32), epsc_T=np.eye(4, dtype=np.float32), submap_pose6=np.zeros(6, np.float32))
+    r = orc.loop_verify(key, wrong6, np.zeros(6, np.float32), [cand])
+    assert r["found"] == 1 and r["best"] == 0 and r["converged"][0] == 1 and r["fitness"][0] < 1e-3
+    c = r["constraint6"]                                                              # x y z roll pitch yaw of tCorrect
+    assert np.abs(c[:3] - true6[3:6]).max() < 2e-3
+    assert np.abs(c[3:] - true6[:3]).max() < 2e-4
+    # the correction is what separates the wrong start from the truth: correction * key2pre == tCorrect
+    assert np.abs(r["correction"] @ r["key2pre"] - r["t_correct"]).max() < 1e-5
+    # a fitness threshold below the achieved score rejects the loop but still reports the best candidate
+    r2 = orc.loop_verify(key, wrong6, np.zeros(6, np.float32), [cand], fitness_threshold=0.0)
+    assert r2["found"] == 0 and r2["best"] == 0
+    sm.close()
