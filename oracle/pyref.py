@@ -402,3 +402,122 @@ def calculate_distance(d1, d2):
         if diff_temp < difference:
             difference, best = diff_temp, i
     return 1 - difference, best
+
+
+# ------------------------------------------------------------------------------------------------
+# LOAM feature extraction (round 2): projectPointCloud .. extractFeatures written again from
+# src/core/laserProcessing.cpp:467-713, as literally as Python allows (member arrays become numpy arrays, the loops stay
+# loops).  Used by tests/test_pyref_oracle.py to pin oracle/orc_features.cpp.  The same resolutions of reference UB as
+# listed at the top of orc_features.cpp apply (they are properties of the reference, not of either restatement): entries
+# of cloudSmoothness outside the stencil range are {0, i}; std::sort ties are ordered by index; a neighbour walk that would
+# read pointColInd outside [0, M) stops.
+# ------------------------------------------------------------------------------------------------
+def extract_features(pts4, ring, n_scan=64, horizon=1800, downsample_rate=1, min_range=0.0, max_range=70.0, edge_thr=1.0, surf_thr=0.1):
+    f32 = np.float32
+    p = np.asarray(pts4, f32)
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    rng = np.sqrt(x * x + y * y + z * z, dtype=f32)                                   # pointDistance (fp32, left to right)
+    row = np.asarray(ring, np.int64)
+    ok = ~((rng < f32(min_range)) | (rng > f32(max_range))) & (row >= 0) & (row < n_scan) & (row % downsample_rate == 0)
+    # atan2(float, float) is atan2f; taken as the correctly rounded float (see DESIGN.md numerics)
+    ang = (np.arctan2(x.astype(np.float64), y.astype(np.float64)).astype(f32) * f32(180)).astype(np.float64) / np.pi
+    ang = ang.astype(f32)                                                             # float horizonAngle
+    ang_res_x = np.float64(f32(360.0 / float(f32(horizon))))                          # static float ang_res_x = 360.0 / float(Horizon_SCAN)
+    t = (ang.astype(np.float64) - 90.0) / ang_res_x
+    rnd = np.where(t >= 0, np.floor(t + 0.5), -np.floor(-t + 0.5))                    # round(): halves away from zero
+    col = (-rnd + (horizon // 2)).astype(np.int64)                                    # double -> int truncation of an integral value
+    col = np.where(col >= horizon, col - horizon, col)
+    ok &= (col >= 0) & (col < horizon)
+    idx = np.nonzero(ok)[0]
+    cell = row[idx] * horizon + col[idx]
+    # "if (rangeMat(row, col) != FLT_MAX) continue": the first point to hit a cell keeps it
+    ucell, first = np.unique(cell, return_index=True)
+    owner = idx[first]                                                                 # ascending cell = row-major = extraction order
+    M = len(owner)
+    pointColInd = (ucell % horizon).astype(np.int64)
+    pointRange = rng[owner]
+    rows = ucell // horizon
+    start = np.zeros(n_scan, np.int64); end = np.zeros(n_scan, np.int64)
+    count = 0
+    for i in range(n_scan):
+        start[i] = count - 1 + 5
+        count += int(np.count_nonzero(rows == i))
+        end[i] = count - 1 - 5
+    # calculateSmoothness
+    curv = np.zeros(M, f32)
+    r = pointRange
+    for i in range(5, M - 5):
+        d = f32(r[i - 5] + r[i - 4]); d = f32(d + r[i - 3]); d = f32(d + r[i - 2]); d = f32(d + r[i - 1]); d = f32(d - f32(r[i] * f32(10)))
+        d = f32(d + r[i + 1]); d = f32(d + r[i + 2]); d = f32(d + r[i + 3]); d = f32(d + r[i + 4]); d = f32(d + r[i + 5])
+        curv[i] = f32(d * d)
+    picked = np.zeros(M, np.int32); label = np.zeros(M, np.int32)
+    # markOccludedPoints
+    for i in range(5, M - 6):
+        depth1, depth2 = r[i], r[i + 1]
+        if abs(int(pointColInd[i + 1] - pointColInd[i])) < 10:
+            if np.float64(f32(depth1 - depth2)) > 0.3:
+                picked[i - 5:i + 1] = 1
+            elif np.float64(f32(depth2 - depth1)) > 0.3:
+                picked[i + 1:i + 7] = 1
+        diff1 = abs(f32(r[i - 1] - r[i])); diff2 = abs(f32(r[i + 1] - r[i]))
+        if np.float64(diff1) > 0.02 * np.float64(r[i]) and np.float64(diff2) > 0.02 * np.float64(r[i]):
+            picked[i] = 1
+    # extractFeatures
+    smooth_val = curv.copy(); smooth_ind = np.arange(M)
+    corner, sharp, flat, surf = [], [], [], []
+
+    def mark(ind):
+        picked[ind] = 1
+        for l in range(1, 6):
+            if ind + l >= M or ind + l - 1 < 0:
+                break
+            if abs(int(pointColInd[ind + l] - pointColInd[ind + l - 1])) > 10:
+                break
+            picked[ind + l] = 1
+        for l in range(-1, -6, -1):
+            if ind + l < 0 or ind + l + 1 >= M:
+                break
+            if abs(int(pointColInd[ind + l] - pointColInd[ind + l + 1])) > 10:
+                break
+            picked[ind + l] = 1
+
+    for i in range(n_scan):
+        for j in range(6):
+            sp = int((start[i] * (6 - j) + end[i] * j) // 6) if (start[i] * (6 - j) + end[i] * j) >= 0 else -int((-(start[i] * (6 - j) + end[i] * j)) // 6)
+            e0 = start[i] * (5 - j) + end[i] * (j + 1)
+            ep = (int(e0 // 6) if e0 >= 0 else -int((-e0) // 6)) - 1                 # C integer division truncates toward zero
+            if sp >= ep:
+                continue
+            order = sorted(range(sp, ep), key=lambda k: (smooth_val[k], smooth_ind[k]))   # std::sort over [sp, ep), by_value + index
+            vals = [(smooth_val[k], smooth_ind[k]) for k in order]
+            for o, k in enumerate(range(sp, ep)):
+                smooth_val[k], smooth_ind[k] = vals[o]
+            n_pick = 0
+            for k in range(ep, sp - 1, -1):
+                ind = int(smooth_ind[k])
+                if picked[ind] == 0 and curv[ind] > f32(edge_thr):
+                    n_pick += 1
+                    if n_pick <= 20:
+                        label[ind] = 1
+                        corner.append(ind)
+                        if n_pick <= 4:
+                            sharp.append(ind)
+                    else:
+                        break
+                    mark(ind)
+            n_pick = 0
+            for k in range(sp, ep + 1):
+                ind = int(smooth_ind[k])
+                if picked[ind] == 0 and curv[ind] < f32(surf_thr):
+                    n_pick += 1
+                    label[ind] = -1
+                    if n_pick <= 10:
+                        flat.append(ind)
+                    mark(ind)
+            for k in range(sp, ep + 1):
+                if label[k] <= 0:
+                    surf.append(k)
+    return {"M": M, "src_index": owner.astype(np.int32), "col_ind": pointColInd.astype(np.int32), "range": pointRange, "curvature": curv,
+            "label": label, "start_ring": start.astype(np.int32), "end_ring": end.astype(np.int32),
+            "corner_idx": np.array(corner, np.int32), "sharp_idx": np.array(sharp, np.int32), "flat_idx": np.array(flat, np.int32),
+            "surf_idx": np.array(surf, np.int32)}

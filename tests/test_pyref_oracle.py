@@ -8,7 +8,7 @@ import pytest
 
 from oracle import orc, pyref
 
-from common import lattice_map, local_map, reg_case
+from common import lattice_map, local_map, reg_case, scene
 
 
 def _compare(f, m, guess, variant, labels=False, **kw):
@@ -160,3 +160,18 @@ def test_voxel_order_does_not_depend_on_the_enclosing_box():
         assert len(out) == len(starts)
         first = p[o_l[starts]]
         assert np.all(np.floor(out[:, :3] * inv) == np.floor(first[:, :3] * inv))  # centroid lies in the voxel of its first point
+
+
+@pytest.mark.parametrize("sensor,n_scan,kw", [("vlp16", 16, {}), ("hdl64", 64, {}), ("hdl64", 64, {"downsample_rate": 2, "min_range": 3.0, "max_range": 45.0})])
+def test_feature_extraction_cpp_oracle_matches_independent_python_restatement(sensor, n_scan, kw):
+    """F1-F5 (projectPointCloud .. extractFeatures, laserProcessing.cpp:467-713) written twice from the reference source -
+    oracle/orc_features.cpp and oracle/pyref.py extract_features (numpy + plain loops) - agree bit for bit on every output:
+    extracted order, column indices, ranges, curvatures, labels, ring windows and the four feature lists."""
+    sw = scene().scan(np.array([0.01, -0.02, 0.3, 2.0, 1.0, 0.0], np.float32), sensor=sensor, seed=2777, fast=True)
+    a = pyref.extract_features(sw["pts"], sw["ring"], n_scan=n_scan, **kw)
+    prm = orc.feat_params(n_scan=n_scan, **kw)
+    b = orc.extract_features(sw["pts"], sw["ring"], prm)
+    assert a["M"] == b["M"] > 1000 * n_scan // max(kw.get("downsample_rate", 1), 1) // 2
+    for k in ("src_index", "col_ind", "range", "curvature", "label", "start_ring", "end_ring", "corner_idx", "sharp_idx", "flat_idx", "surf_idx"):
+        assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+    assert len(a["corner_idx"]) > 100 and len(a["flat_idx"]) > 100
