@@ -521,3 +521,60 @@ def extract_features(pts4, ring, n_scan=64, horizon=1800, downsample_rate=1, min
             "label": label, "start_ring": start.astype(np.int32), "end_ring": end.astype(np.int32),
             "corner_idx": np.array(corner, np.int32), "sharp_idx": np.array(sharp, np.int32), "flat_idx": np.array(flat, np.int32),
             "surf_idx": np.array(surf, np.int32)}
+
+
+# ------------------------------------------------------------------------------------------------
+# EPSC / SEPSC / FEPSC descriptors (epscGeneration.cpp:478-607), numpy restatement pinning oracle/orc_epsc.cpp
+# ------------------------------------------------------------------------------------------------
+def _epsc_bins(xy):
+    f32 = np.float32
+    x, y = np.asarray(xy[:, 0], f32), np.asarray(xy[:, 1], f32)
+    dist = np.sqrt(x * x + y * y, dtype=f32).astype(np.float64)          # std::sqrt(float) -> float -> double distance
+    keep = ~((dist >= 60.0) | (dist < 3.0))
+    ring_step = (60.0 - 3.0) / 20
+    sector_step = 2 * np.pi / 80
+    ring_id = np.floor((dist - 3.0) / ring_step).astype(np.int64)
+    angle = np.pi + np.arctan2(y.astype(np.float64), x.astype(np.float64)).astype(f32).astype(np.float64)   # atan2f, correctly rounded
+    sector_id = np.floor(angle / sector_step).astype(np.int64)
+    keep &= (ring_id < 20) & (ring_id >= 0) & (sector_id < 80) & (sector_id >= 0)
+    return ring_id, sector_id, keep
+
+
+def _u8_counts(ring_id, sector_id, sel):
+    c = np.zeros((20, 80), np.int64)
+    np.add.at(c, (ring_id[sel], sector_id[sel]), 1)
+    return c % 256                                                          # unsigned char ++ wraps (Q4)
+
+
+def epsc_describe(corner4, surf4, sem4, sem_label, lut):
+    r, s, k = _epsc_bins(np.asarray(corner4, np.float32)); esc = _u8_counts(r, s, k)
+    r, s, k = _epsc_bins(np.asarray(surf4, np.float32)); psc = _u8_counts(r, s, k)
+    epsc = ((100 * psc) // (1 + esc)) % 256                                  # int division, narrowed to unsigned char
+    r, s, k = _epsc_bins(np.asarray(sem4, np.float32))
+    u = np.asarray(lut)[np.asarray(sem_label, np.int64)]
+    spsc = _u8_counts(r, s, k & ((u == 40) | (u == 50))); sesc = _u8_counts(r, s, k & (u == 81))
+    sepsc = ((100 * spsc) // (1 + sesc)) % 256
+    fepsc = np.trunc(sepsc.astype(np.float64) * 0.4 + epsc.astype(np.float64) * 0.6).astype(np.int64) % 256
+    return {"epsc": epsc.astype(np.uint8), "sepsc": sepsc.astype(np.uint8), "fepsc": fepsc.astype(np.uint8)}
+
+
+def loop_project(sem4, sem_label):
+    """EPSCGeneration::project (epscGeneration.cpp:84-120): 360 sectors, per sector {count (float ++), x, y, label of the LAST
+    point of the sector}; only labels 13, 14, 16, 18, 19; float distance / angle / step as declared upstream."""
+    f32 = np.float32
+    p = np.asarray(sem4, f32); lab = np.asarray(sem_label, np.int64)
+    out = np.zeros((360, 4), f32)
+    step = f32(2.0 * np.pi / np.float64(f32(360.0)))                          # float step = 2. * M_PI / sectors_range
+    for i in range(len(p)):
+        if lab[i] not in (13, 14, 16, 18, 19):
+            continue
+        x, y = p[i, 0], p[i, 1]
+        dist = np.sqrt(f32(x * x + y * y), dtype=f32)
+        if np.float64(dist) < 1e-2:
+            continue
+        angle = f32(np.pi + np.float64(f32(np.arctan2(np.float64(y), np.float64(x)))))   # float angle = M_PI + atan2f(y, x)
+        sector = int(np.floor(f32(angle / step)))                              # float / float
+        if sector >= 360 or sector < 0:
+            continue
+        out[sector, 0] = f32(out[sector, 0] + f32(1)); out[sector, 1] = x; out[sector, 2] = y; out[sector, 3] = f32(lab[i])
+    return out

@@ -175,3 +175,48 @@ def test_feature_extraction_cpp_oracle_matches_independent_python_restatement(se
     for k in ("src_index", "col_ind", "range", "curvature", "label", "start_ring", "end_ring", "corner_idx", "sharp_idx", "flat_idx", "surf_idx"):
         assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
     assert len(a["corner_idx"]) > 100 and len(a["flat_idx"]) > 100
+
+
+@pytest.mark.parametrize("sensor,n_scan", [("vlp16", 16), ("hdl64", 64)])
+def test_epsc_descriptors_cpp_oracle_matches_numpy_restatement(sensor, n_scan):
+    """calculateEPSC / calculateSEPSC / calculateFEPSC (epscGeneration.cpp:478-607) written twice from the reference source:
+    the 20x80 descriptors are equal byte for byte (float sqrt then double binning, u8 counter wrap, integer division narrowed
+    to u8, double blend truncated)."""
+    sw = scene().scan(np.array([0.01, -0.02, 0.3, 2.0, 1.0, 0.0], np.float32), sensor=sensor, seed=2777, fast=True)
+    fe = orc.extract_features(sw["pts"], sw["ring"], orc.feat_params(n_scan=n_scan))
+    ext = sw["pts"][fe["src_index"]]; lab = sw["label"][fe["src_index"]]
+    a = orc.epsc_describe(ext[fe["corner_idx"]], ext[fe["surf_idx"]], ext, lab)
+    b = pyref.epsc_describe(ext[fe["corner_idx"]], ext[fe["surf_idx"]], ext, lab, orc.using_map_lut())
+    for k in ("epsc", "sepsc", "fepsc"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["fepsc"].any()
+
+
+def test_map_distance_filter_matches_scipy_nearest_neighbour():
+    """map_scan_feature_pts_distance_removal (subMap.h:1063-1098): outside the centre disc everything stays; inside, a point
+    stays when its squared distance to the nearest map point is in (near^2, dyn_min^2) or above dyn_max^2 - recomputed with
+    scipy's cKDTree (the 1-NN distance is evaluated in fp32 in the reference's order, like the oracle does)."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(23)
+    m = local_map()["surf"][::4]
+    f = m[rng.choice(len(m), 6000, replace=False)].copy()
+    f[:2000, :3] += rng.normal(0, 0.01, (2000, 3)).astype(np.float32)        # on the map: mostly inside `near` -> dropped
+    f[2000:4000, :3] += rng.normal(0, 0.12, (2000, 3)).astype(np.float32)    # a little off: the (near, dyn_min) band -> kept
+    f[4000:, :3] += rng.normal(0, 1.5, (2000, 3)).astype(np.float32)         # far: beyond dyn_max or in the dropped middle band
+    keep = orc.map_distance_filter(f, m, center_radius=30.0, dyn_min=0.3, dyn_max=3.0, near=0.03)
+    _, j = cKDTree(m[:, :3].astype(np.float64)).query(f[:, :3].astype(np.float64), k=1)
+    d = f[:, :3] - m[j, :3]                                                  # fp32, FLANN's L2 order
+    d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    inside = ~(f[:, 0] * f[:, 0] + f[:, 1] * f[:, 1] > np.float32(30.0) * np.float32(30.0))
+    exp = ~inside | ((d2 > np.float32(0.03) ** 2) & (d2 < np.float32(0.3) ** 2)) | (d2 > np.float32(3.0) ** 2)
+    # a scipy / oracle disagreement can only come from two map points at (almost) the same distance: none expected here
+    assert np.array_equal(keep, exp)
+    assert 0.2 < keep.mean() < 0.9 and keep[:2000].mean() < keep[2000:4000].mean()
+
+
+def test_sector_projection_cpp_oracle_matches_python_restatement():
+    """EPSCGeneration::project (epscGeneration.cpp:84-120) written twice: the 360 x {count, x, y, label} sector table of a
+    labelled HDL-64 sweep is equal float for float (float step and angle as declared upstream, last point of a sector wins)."""
+    sw = scene().scan(np.array([0.01, -0.02, 0.3, 2.0, 1.0, 0.0], np.float32), sensor="hdl64", seed=2777, fast=True)
+    a = orc.loop_project(sw["pts"], sw["label"]); b = pyref.loop_project(sw["pts"], sw["label"])
+    assert np.array_equal(a, b) and (a[:, 0] > 0).sum() > 300
